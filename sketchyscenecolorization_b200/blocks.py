@@ -1,0 +1,258 @@
+"""MRU cells with hand-written backward passes (no autograd anywhere in this package).
+
+Reference: obj_lib/mru.py -- `mru_conv_block_v3` (:353-461, encoder + discriminator cell) and
+`mru_deconv_block_v2` (:527-591, decoder cell); normalisers/activations from
+models_collection.py:22-34 (conditional BN), :56-65 (prelu, miu_relu).
+
+Two exact algebraic rewrites are used:
+  * the decoder's hidden state is never materialised at full resolution: convs read it through the
+    `ups` flag, and the 1x1 skip conv + cBN + miu_relu run at LOW resolution (all three commute with the
+    nearest-neighbour x2 upsample, batch statistics included);
+  * `mean_pool(sk + h2)` is one fused pass.
+"""
+from __future__ import annotations
+
+from .ops_base import ACT_LRELU, ACT_MIU, ACT_NONE
+
+
+class WeightView:
+    """How a network hands (possibly spectrally-normalised) weights to the cells.
+
+    get(scope) -> (w_hwio, bias_1d); after the backward pass `gw(scope)` is the tensor wgrad accumulates into
+    (the raw grad view for plain weights, a temporary dL/dW_bar for SN weights)."""
+
+    def __init__(self, store, ops, sn=False, need_wgrad=True):
+        self.store, self.ops, self.sn, self.need_wgrad = store, ops, sn, need_wgrad
+        self.cache = {}
+        self.sn_ctx = {}
+        self.gwbar = {}
+
+    def get(self, scope):
+        if scope in self.cache:
+            return self.cache[scope]
+        w = self.store.p[scope + "/weights"]
+        b = self.store.p[scope + "/biases"].reshape(-1)
+        if self.sn:
+            u = self.store.state[scope + "/" + scope + "/u"]
+            wbar2d, ctx = self.ops.sn_fwd(w.reshape(-1, w.shape[-1]), u)
+            self.sn_ctx[scope] = ctx
+            w = wbar2d.view(w.shape)
+        self.cache[scope] = (w, b)
+        return w, b
+
+    def grads(self, scope):
+        """(dw, db) accumulation targets for `scope`."""
+        db = self.store.g[scope + "/biases"].reshape(-1)
+        if not self.sn:
+            return self.store.g[scope + "/weights"], db
+        if scope not in self.gwbar:
+            w = self.store.p[scope + "/weights"]
+            self.gwbar[scope] = self.ops.zeros_f32(w.shape)
+        return self.gwbar[scope], db
+
+    def finish_backward(self):
+        """Push dL/dW_bar through the spectral normalisation (sn.py) into the raw weight gradients."""
+        for scope, gwb in self.gwbar.items():
+            w = self.store.p[scope + "/weights"]
+            dw = self.store.g[scope + "/weights"]
+            self.ops.sn_bwd(gwb.reshape(-1, w.shape[-1]), w.reshape(-1, w.shape[-1]), self.sn_ctx[scope],
+                            dw.reshape(-1, w.shape[-1]))
+        self.gwbar = {}
+
+    def commit_u(self):
+        """u <- u' (the SPECTRAL_NORM_UPDATE_OPS run as a control dependency of the G step,
+        graph_single.py:178-180,208-210)."""
+        for scope, ctx in self.sn_ctx.items():
+            self.store.state[scope + "/" + scope + "/u"].copy_(ctx["u_new"])
+
+
+# ------------------------------------------------------------------------------------------------
+# norm + activation  (mru.py:367-376 `norm_activ`)
+# ------------------------------------------------------------------------------------------------
+def norm_act_fwd(ops, store, scope, x, labels, kind):
+    if kind == "cbn":
+        mean, rstd = ops.chan_stats(x)
+        y = ops.cbn_act_fwd(x, mean, rstd, store.p[scope + "/scale"], store.p[scope + "/offset"], labels, ACT_MIU)
+        return y, (x, mean, rstd)
+    a = store.p[scope + "/prelu/param"]
+    return ops.prelu_fwd(x, a), (x,)
+
+
+def norm_act_bwd(ops, store, scope, gy, ctx, labels, kind, need_wgrad=True):
+    if kind == "cbn":
+        x, mean, rstd = ctx
+        return ops.cbn_act_bwd(gy, x, mean, rstd, store.p[scope + "/scale"], store.p[scope + "/offset"], labels,
+                               store.g[scope + "/scale"], store.g[scope + "/offset"], ACT_MIU)
+    (x,) = ctx
+    return ops.prelu_bwd(gy, x, store.p[scope + "/prelu/param"],
+                         store.g[scope + "/prelu/param"] if need_wgrad else None)
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder / discriminator cell: mru_conv_block_v3 (mru.py:353-461), stride 2, norm_input=True
+# ------------------------------------------------------------------------------------------------
+def enc_block_fwd(ops, wv, scope, x, ht, labels, kind, save=True):
+    st = wv.store
+    a, c_a = norm_act_fwd(ops, st, scope + "/norm_activation_in", ht, labels, kind)
+    w, b = wv.get(scope + "/update_gate")
+    rg_raw = ops.conv_fwd([(a, False), (x, False)], w, b, act=ACT_LRELU)          # mru.py:408-414
+    rg, mn, mx = ops.minmax_fwd(rg_raw)                                          # mru.py:415-416
+    w, b = wv.get(scope + "/Conv")
+    im = ops.conv_fwd([(x, False)], w, b)                                        # mru.py:419-424
+    hp = ops.gate_fma_fwd(ht, rg, im)                                            # mru.py:426
+    p, c_p = norm_act_fwd(ops, st, scope + "/norm_activation_merge_1", hp, labels, kind)
+    w, b = wv.get(scope + "/Conv_1")
+    h1_raw = ops.conv_fwd([(p, False)], w, b)                                    # mru.py:431-436
+    h1, c_h1 = norm_act_fwd(ops, st, scope + "/Conv_1", h1_raw, labels, kind)
+    w, b = wv.get(scope + "/Conv_2")
+    h2 = ops.conv_fwd([(h1, False)], w, b)                                       # mru.py:437-442
+    w, b = wv.get(scope + "/Conv_3")
+    sk = ops.conv_fwd([(ht, False)], w, b)                                       # mru.py:446-452 (1x1)
+    out = ops.addpool_fwd(sk, h2)                                                # mru.py:453,457
+    ctx = None
+    if save:
+        ctx = dict(x=x, ht=ht, a=a, c_a=c_a, rg_raw=rg_raw, rg=rg, mn=mn, mx=mx, im=im, c_p=c_p, p=p, c_h1=c_h1, h1=h1)
+    return out, ctx
+
+
+def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False, need_ht_grad=True):
+    """Returns (g_ht, g_x or None).  Weight gradients accumulate through `wv.grads` when wv.need_wgrad."""
+    st, nw = wv.store, wv.need_wgrad
+    x, ht = ctx["x"], ctx["ht"]
+    cin = ht.shape[-1]
+    g_full = ops.unpool_bwd(g_out)                    # d/d(sk) = d/d(h2)
+    # Conv_3 (1x1 skip on the raw hidden state)
+    w3, _ = wv.get(scope + "/Conv_3")
+    if nw:
+        ops.conv_wgrad([(ht, False)], g_full, *wv.grads(scope + "/Conv_3"))
+    g_ht = ops.conv_dgrad(g_full, w3, 0, cin) if need_ht_grad else None
+    # Conv_2
+    w2, _ = wv.get(scope + "/Conv_2")
+    if nw:
+        ops.conv_wgrad([(ctx["h1"], False)], g_full, *wv.grads(scope + "/Conv_2"))
+    g_h1 = ops.conv_dgrad(g_full, w2, 0, w2.shape[2])
+    del g_full
+    g_h1raw = norm_act_bwd(ops, st, scope + "/Conv_1", g_h1, ctx["c_h1"], labels, kind, nw)
+    del g_h1
+    # Conv_1
+    w1, _ = wv.get(scope + "/Conv_1")
+    if nw:
+        ops.conv_wgrad([(ctx["p"], False)], g_h1raw, *wv.grads(scope + "/Conv_1"))
+    g_p = ops.conv_dgrad(g_h1raw, w1, 0, cin)
+    del g_h1raw
+    g_hp = norm_act_bwd(ops, st, scope + "/norm_activation_merge_1", g_p, ctx["c_p"], labels, kind, nw)
+    del g_p
+    if need_ht_grad:
+        ops.add_(g_ht, g_hp)
+    g_rg, g_im = ops.gate_fma_bwd(g_hp, ctx["rg"], ctx["im"])
+    del g_hp
+    # Conv (image branch)
+    wc, _ = wv.get(scope + "/Conv")
+    if nw:
+        ops.conv_wgrad([(x, False)], g_im, *wv.grads(scope + "/Conv"))
+    g_x = ops.conv_dgrad(g_im, wc, 0, x.shape[-1]) if need_x_grad else None
+    del g_im
+    # update gate
+    g_rgraw = ops.minmax_bwd(g_rg, ctx["rg_raw"], ctx["mn"], ctx["mx"])
+    del g_rg
+    wu, _ = wv.get(scope + "/update_gate")
+    if nw:
+        ops.conv_wgrad([(ctx["a"], False), (x, False)], g_rgraw, *wv.grads(scope + "/update_gate"))
+    if need_x_grad:
+        ops.conv_dgrad(g_rgraw, wu, cin, x.shape[-1], out=g_x, acc=True)
+    if need_ht_grad:
+        g_a = ops.conv_dgrad(g_rgraw, wu, 0, cin)
+        del g_rgraw
+        g_ht_in = norm_act_bwd(ops, st, scope + "/norm_activation_in", g_a, ctx["c_a"], labels, kind, nw)
+        ops.add_(g_ht, g_ht_in)
+    return g_ht, g_x
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder cell: mru_deconv_block_v2 (mru.py:527-591), stride 2
+# ------------------------------------------------------------------------------------------------
+def dec_block_fwd(ops, wv, scope, xs, ht_low, cout, labels, save=True):
+    """xs: list of full-resolution extra sources (sketch level first); ht_low: hidden state at half resolution."""
+    st = wv.store
+    chid = ht_low.shape[-1]
+    f = [(ht_low, True)] + [(x, False) for x in xs]
+    w, b = wv.get(scope + "/Conv")
+    rg_raw = ops.conv_fwd(f, w, b, act=ACT_LRELU)                                # mru.py:555-559
+    rg, mn0, mx0 = ops.minmax_fwd(rg_raw)
+    w, b = wv.get(scope + "/Conv_1")
+    zg_raw = ops.conv_fwd(f, w, b, act=ACT_LRELU)                                # mru.py:563-567
+    zg, mn1, mx1 = ops.minmax_fwd(zg_raw)
+    gh = ops.mul_up_fwd(rg, ht_low)                                              # rg * ht   (mru.py:572)
+    w, b = wv.get(scope + "/Conv_2")
+    h1_raw = ops.conv_fwd([(gh, False)] + [(x, False) for x in xs], w, b)
+    h1, c_h1 = norm_act_fwd(ops, st, scope + "/Conv_2", h1_raw, labels, "cbn")
+    w, b = wv.get(scope + "/Conv_3")
+    h2_raw = ops.conv_fwd([(h1, False)], w, b)                                   # mru.py:577-581
+    h2, c_h2 = norm_act_fwd(ops, st, scope + "/Conv_3", h2_raw, labels, "cbn")
+    c_sk = None
+    if chid != cout:
+        w, b = wv.get(scope + "/Conv_4")
+        sk_raw = ops.conv_fwd([(ht_low, False)], w, b)                           # mru.py:585-588 at low resolution
+        sk, c_sk = norm_act_fwd(ops, st, scope + "/Conv_4", sk_raw, labels, "cbn")
+    else:
+        sk = ht_low
+    out = ops.blend_fwd(sk, h2, zg)                                              # mru.py:589
+    ctx = None
+    if save:
+        ctx = dict(xs=xs, ht_low=ht_low, rg_raw=rg_raw, rg=rg, mn0=mn0, mx0=mx0, zg_raw=zg_raw, zg=zg, mn1=mn1,
+                   mx1=mx1, gh=gh, c_h1=c_h1, h1=h1, c_h2=c_h2, h2=h2, c_sk=c_sk, sk=sk, cout=cout)
+    return out, ctx
+
+
+def dec_block_bwd(ops, wv, scope, g_out, ctx, labels, xs_need_grad):
+    """Returns (g_ht_low, [g_x or None for x in xs])."""
+    st = wv.store
+    xs, ht_low, cout = ctx["xs"], ctx["ht_low"], ctx["cout"]
+    chid = ht_low.shape[-1]
+    f = [(ht_low, True)] + [(x, False) for x in xs]
+    offs, o = [], chid
+    for x in xs:
+        offs.append(o)
+        o += x.shape[-1]
+    g_sk, g_h2, g_zg = ops.blend_bwd(g_out, ctx["sk"], ctx["h2"], ctx["zg"])
+    # skip path
+    if chid != cout:
+        g_skraw = norm_act_bwd(ops, st, scope + "/Conv_4", g_sk, ctx["c_sk"], labels, "cbn")
+        w4, _ = wv.get(scope + "/Conv_4")
+        ops.conv_wgrad([(ht_low, False)], g_skraw, *wv.grads(scope + "/Conv_4"))
+        g_ht = ops.conv_dgrad(g_skraw, w4, 0, chid)
+        del g_skraw
+    else:
+        g_ht = g_sk
+    # Conv_3
+    g_h2raw = norm_act_bwd(ops, st, scope + "/Conv_3", g_h2, ctx["c_h2"], labels, "cbn")
+    del g_h2
+    w3, _ = wv.get(scope + "/Conv_3")
+    ops.conv_wgrad([(ctx["h1"], False)], g_h2raw, *wv.grads(scope + "/Conv_3"))
+    g_h1 = ops.conv_dgrad(g_h2raw, w3, 0, cout)
+    del g_h2raw
+    # Conv_2
+    g_h1raw = norm_act_bwd(ops, st, scope + "/Conv_2", g_h1, ctx["c_h1"], labels, "cbn")
+    del g_h1
+    w2, _ = wv.get(scope + "/Conv_2")
+    ops.conv_wgrad([(ctx["gh"], False)] + [(x, False) for x in xs], g_h1raw, *wv.grads(scope + "/Conv_2"))
+    g_gh = ops.conv_dgrad(g_h1raw, w2, 0, chid)
+    g_xs = [ops.conv_dgrad(g_h1raw, w2, offs[i], xs[i].shape[-1]) if xs_need_grad[i] else None
+            for i in range(len(xs))]
+    del g_h1raw
+    g_rg, g_ht_mul = ops.mul_up_bwd(g_gh, ctx["rg"], ht_low)
+    del g_gh
+    ops.add_(g_ht, g_ht_mul)
+    del g_ht_mul
+    # gates
+    for (gg, raw, mn, mx, sc) in ((g_rg, ctx["rg_raw"], ctx["mn0"], ctx["mx0"], scope + "/Conv"),
+                                  (g_zg, ctx["zg_raw"], ctx["mn1"], ctx["mx1"], scope + "/Conv_1")):
+        g_raw = ops.minmax_bwd(gg, raw, mn, mx)
+        w, _ = wv.get(sc)
+        ops.conv_wgrad(f, g_raw, *wv.grads(sc))
+        ops.conv_dgrad(g_raw, w, 0, chid, ups=True, out=g_ht, acc=True)
+        for i in range(len(xs)):
+            if xs_need_grad[i]:
+                ops.conv_dgrad(g_raw, w, offs[i], xs[i].shape[-1], out=g_xs[i], acc=True)
+        del g_raw
+    return g_ht, g_xs

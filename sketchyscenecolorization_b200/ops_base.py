@@ -1,0 +1,202 @@
+"""Operator contract of the fg-colorization hot path.
+
+The host-side network code (generator.py / discriminator.py / text_fusion.py / losses.py) is written
+against this interface only.  The product implementation is `cuda_ops.CudaOps` (hand-written sm_100a
+kernels behind the C-ABI of include/fgcolor.h); it raises at construction when the shared library or
+a CUDA device is missing -- there is NO CPU implementation in this package.
+
+Conventions
+  * activations are NHWC, contiguous, dtype `self.act_dtype` (fp32, or bf16 in the training mode);
+    2-D row tensors [R, C] are the NHWC special case H=W=1.
+  * weights / biases / tables / statistics / gradients of weights are always fp32; conv weights keep the
+    reference HWIO layout [k,k,Cin,Cout] (mru.py:118), a 2-D matrix [K,N] is HWIO with k=1.
+  * `srcs` of a conv is a list of (tensor, ups) pairs concatenated along channels in list order
+    (tf.concat, mru.py:403,552,572); ups=True reads the source through a nearest-neighbour x2 upsample
+    (mru.upsample, mru.py:22-28) without materialising it.
+  * ops that take `acc=True` add into the given output instead of overwriting it.
+"""
+from __future__ import annotations
+
+ACT_NONE, ACT_LRELU, ACT_TANH, ACT_MIU = 0, 1, 2, 3
+
+
+class OpsBase:
+    act_dtype = None
+
+    # ---------------- convolution family (mru.conv2d, mru.py:95-140) ----------------
+    def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None):
+        """y = act(conv2d_SAME(concat(srcs), w) + b);  w HWIO fp32, b fp32 [Cout] or None."""
+        raise NotImplementedError
+
+    def conv_dgrad(self, gy, w, c_off, c_len, *, ups=False, out=None, acc=False, out_dtype=None):
+        """Gradient of a stride-1 conv w.r.t. input channels [c_off, c_off+c_len) of the concatenated input.
+        ups=True: the source was read through the x2 upsample, the result is the 2x2-summed low-res gradient."""
+        raise NotImplementedError
+
+    def conv_wgrad(self, srcs, gy, dw, db, *, stride=1):
+        """dw += d/dw, db += sum_{n,h,w} gy  (always accumulating; dw HWIO fp32 view, db fp32 [Cout] or None)."""
+        raise NotImplementedError
+
+    # ---------------- normalisation / activations ----------------
+    def chan_stats(self, x):
+        """(mean[C], rstd[C]) over N,H,W; biased variance, eps 1e-5 (models_collection.batchnorm, :26,34)."""
+        raise NotImplementedError
+
+    def cbn_act_fwd(self, x, mean, rstd, scale, offset, labels, act=ACT_MIU):
+        """act(scale[l_n,c] * (x-mean)*rstd + offset[l_n,c]); act in {ACT_NONE, ACT_MIU}."""
+        raise NotImplementedError
+
+    def cbn_act_bwd(self, gy, x, mean, rstd, scale, offset, labels, dscale, doffset, act=ACT_MIU):
+        """returns gx; accumulates into dscale/doffset [25,C]."""
+        raise NotImplementedError
+
+    def prelu_fwd(self, x, a):
+        """max(a*x, x), a = fp32 scalar tensor (models_collection.prelu, :56-60)."""
+        raise NotImplementedError
+
+    def prelu_bwd(self, gy, x, a, da):
+        """returns gx; accumulates da (None => skip)."""
+        raise NotImplementedError
+
+    def minmax_fwd(self, x):
+        """(gate, mn[N,C], mx[N,C]) with gate = (x-mn)/(mx-mn) per (n,c) over H,W, no epsilon (mru.py:415-416)."""
+        raise NotImplementedError
+
+    def minmax_bwd(self, ggate, x, mn, mx):
+        """gradient w.r.t. the PRE-lrelu conv output: min-max backward (arg-min/arg-max routing, ties split
+        evenly) times lrelu'(x) with leak 0.2; x is the post-lrelu tensor given to minmax_fwd."""
+        raise NotImplementedError
+
+    def act_bwd(self, gy, y, act):
+        """gradient through an activation fused into a conv epilogue, from the OUTPUT y:
+        ACT_TANH: gy*(1-y^2);  ACT_MIU: gy*0.5*(1 + x/sqrt(0.09+x^2)) with x = y - 0.0225/y."""
+        raise NotImplementedError
+
+    # ---------------- gating (mru.py:426,453,572,589) ----------------
+    def gate_fma_fwd(self, ht, rg, im):
+        """ht + rg*im"""
+        raise NotImplementedError
+
+    def gate_fma_bwd(self, g, rg, im):
+        """(g*im, g*rg)"""
+        raise NotImplementedError
+
+    def mul_up_fwd(self, rg, ht_low):
+        """rg * up2(ht_low)"""
+        raise NotImplementedError
+
+    def mul_up_bwd(self, g, rg, ht_low):
+        """(g * up2(ht_low), sum2x2(g * rg))"""
+        raise NotImplementedError
+
+    def blend_fwd(self, sk_low, h2, zg):
+        """up2(sk_low)*(1-zg) + h2*zg"""
+        raise NotImplementedError
+
+    def blend_bwd(self, g, sk_low, h2, zg):
+        """(sum2x2(g*(1-zg)), g*zg, g*(h2-up2(sk_low)))"""
+        raise NotImplementedError
+
+    def addpool_fwd(self, a, b):
+        """mean_pool2x2(a + b)  (mru.py:453,457)"""
+        raise NotImplementedError
+
+    def unpool_bwd(self, g):
+        """up2(g)/4"""
+        raise NotImplementedError
+
+    def meanpool_fwd(self, x):
+        raise NotImplementedError
+
+    def zeros_f32(self, shape):
+        raise NotImplementedError
+
+    def add_(self, dst, src):
+        """dst += src (same shape); returns dst"""
+        raise NotImplementedError
+
+    def spatial_mean_fwd(self, x):
+        """[N,H,W,C] -> fp32-or-act [N,1,1,C] mean over H,W (models_collection.py:783)"""
+        raise NotImplementedError
+
+    def spatial_mean_bwd(self, g, H, W):
+        """[N,1,1,C] -> [N,H,W,C] broadcast g/(H*W)"""
+        raise NotImplementedError
+
+    # ---------------- layout ----------------
+    def nchw_to_nhwc(self, x, out_dtype=None):
+        raise NotImplementedError
+
+    def nhwc_to_nchw(self, x, out_dtype=None):
+        raise NotImplementedError
+
+    def cast(self, x, dtype):
+        raise NotImplementedError
+
+    # ---------------- text fusion (models_collection.encode_feat_with_text, :150-248) ----------------
+    def l2norm_rows_fwd(self, x):
+        """rows [R,D] fp32: (x * rsqrt(max(sum x^2,1e-12)), inv[R])"""
+        raise NotImplementedError
+
+    def l2norm_rows_bwd(self, gy, y, inv):
+        raise NotImplementedError
+
+    def embedding_fwd(self, table, ids, t):
+        """table[ids[:, t]] -> [N,D];  ids int32 [N,T] on the device"""
+        raise NotImplementedError
+
+    def embedding_bwd(self, g, ids, t, dtable):
+        """dtable[ids[n,t]] += g[n]"""
+        raise NotImplementedError
+
+    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P):
+        """BasicLSTMCell pointwise part.  pre = gates [+ gates2] [+ grow[r // P]]  ([R,4D], order i,j,f,o);
+        c = c_prev*sig(f+1) + sig(i)*tanh(j); h = tanh(c)*sig(o); rows whose sample token ids[r//P, t] == 0 (<pad>) keep
+        (c_prev, h_prev).  Returns (c, h, pre)."""
+        raise NotImplementedError
+
+    def lstm_cell_bwd(self, gc, gh, pre, c_prev, c, ids, t, P):
+        """returns (g_pre [R,4D], g_c_prev [R,D], g_h_pass [R,D]) where g_h_pass = gh on masked rows else 0."""
+        raise NotImplementedError
+
+    def rows_group_sum(self, x, P):
+        """[N*P, C] -> [N, C] sum over each group of P consecutive rows"""
+        raise NotImplementedError
+
+    def atanh_relu_fwd(self, h):
+        """relu(0.5*(log(1.001+h) - log(1.001-h)))  (models_collection.py:239-241)"""
+        raise NotImplementedError
+
+    def atanh_relu_bwd(self, gy, h):
+        raise NotImplementedError
+
+    # ---------------- spectral norm (sn.py:12-52) ----------------
+    def sn_fwd(self, w2d, u):
+        """w2d [K,C] fp32, u [1,C] -> (w_bar [K,C], ctx) with ctx holding v, u_new, sigma and norms."""
+        raise NotImplementedError
+
+    def sn_bwd(self, gwbar, w2d, ctx, dw):
+        """dw += dL/dW given gwbar = dL/dW_bar (differentiates through sigma and the power iteration)."""
+        raise NotImplementedError
+
+    # ---------------- losses (graph_single.py:340-353,388-402,552-555) ----------------
+    def softplus_mean(self, d, sign):
+        """(mean(softplus(sign*d)) as fp32 0-d tensor, gradient w.r.t. d in d's dtype)"""
+        raise NotImplementedError
+
+    def ce_loss(self, logits, labels, focal, weight):
+        """weight * mean_n( (1-p_t)^2 if focal else 1) * CE_n ) and its gradient w.r.t. logits [N,1,1,C]."""
+        raise NotImplementedError
+
+    def smooth_l1(self, target, gen, weight):
+        """weight*mean(smooth_l1(target-gen)) and gradient w.r.t. gen."""
+        raise NotImplementedError
+
+    def reg_loss(self, store):
+        """sum_i reg_i * sum(w_i^2)/2 over a ParamStore (fp32 0-d tensor)."""
+        raise NotImplementedError
+
+    # ---------------- optimiser (graph_single.py:584-593, tf.train.AdamOptimizer(beta1=0, beta2=0.9)) ----
+    def adam_step(self, store, lr, add_reg_grad=True):
+        """g += reg*w; v = .9v+.1g^2; w -= lr*sqrt(1-.9^t)*g/(sqrt(v)+1e-8); increments store.adam_t first."""
+        raise NotImplementedError

@@ -1,0 +1,228 @@
+"""Variable registry of the fg-colorization networks, with the reference's TF variable names.
+
+Every trainable tensor lives in ONE flat fp32 buffer per network (`flat`), with a matching flat
+gradient buffer and Adam second-moment buffer, so that the NCCL all-reduce and the fused Adam
+kernel touch a single contiguous range (reference: graph_single.py:33-68 `average_gradients`,
+:584-593 `get_optimizer`).  Per-tensor views keep the reference layout (conv `weights` HWIO
+[k,k,Cin,Cout], `biases` [1,C,1,1], cBN tables [25,C]) so a state dict keyed by the reference
+names round-trips without transposition.
+
+Naming follows tf.variable_scope uniquification in the reference:
+  generator: models_collection.py:68-147 (encoder), :150-248 (TextLSTM), :310-377 (decoder)
+  discriminator: models_collection.py:676-786; SN `u` vectors: sn.py:17-18
+  blocks: mru.py:353-461 (v3, scopes update_gate/Conv/Conv_1..3), mru.py:527-591 (v2, Conv..Conv_4)
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from dataclasses import dataclass
+
+import torch
+
+NUM_CLASSES = 25      # input_pipeline.py:11
+NOISE_DIM = 256       # models_collection.py:310
+ALIGN = 4             # every tensor starts on a 16-byte boundary inside the flat buffer
+
+
+@dataclass
+class VarSpec:
+    name: str
+    shape: tuple
+    init: tuple            # (kind, arg)
+    reg: float = 0.0       # l2_regularizer scale (loss = reg * sum(w^2)/2)
+    sn: bool = False       # spectrally normalised (discriminator weights)
+    trainable: bool = True
+
+    @property
+    def numel(self):
+        return int(math.prod(self.shape)) if self.shape else 1
+
+
+def _conv(scope, k, cin, cout, reg, sn, bias=0.0):
+    v = [VarSpec(scope + "/weights", (k, k, cin, cout), ("normal", 0.02), reg, sn)]
+    if sn:
+        v.append(VarSpec(scope + "/" + scope + "/u", (1, cout), ("trunc_normal", 1.0), trainable=False))
+    v.append(VarSpec(scope + "/biases", (1, cout, 1, 1), ("const", bias)))
+    return v
+
+
+def _cbn(scope, c):
+    return [VarSpec(scope + "/offset", (NUM_CLASSES, c), ("const", 0.0)),
+            VarSpec(scope + "/scale", (NUM_CLASSES, c), ("const", 1.0))]
+
+
+def _prelu(scope):
+    return [VarSpec(scope + "/prelu/param", (), ("const", 0.2))]
+
+
+def _norm(scope, c, kind):
+    return _cbn(scope, c) if kind == "cbn" else _prelu(scope)
+
+
+def _enc_unit(prefix, unit, cin, cout, kind, sn):
+    s = "%s/mru_conv_unit_t_%d_layer_0" % (prefix, unit)
+    v = _norm(s + "/norm_activation_in", cin, kind)
+    v += _conv(s + "/update_gate", 3, cin + 3, cin, 1e-5, sn, bias=0.5)
+    v += _conv(s + "/Conv", 3, 3, cin, 1e-5, sn)
+    v += _norm(s + "/norm_activation_merge_1", cin, kind)
+    v += _conv(s + "/Conv_1", 3, cin, cout, 1e-5, sn)
+    v += _norm(s + "/Conv_1", cout, kind)
+    v += _conv(s + "/Conv_2", 3, cout, cout, 1e-5, sn)
+    if cin != cout:
+        v += _conv(s + "/Conv_3", 1, cin, cout, 1e-5, sn)
+    return v
+
+
+def encoder_channels(size):
+    return [8, size, size * 2, size * 4, size * 8]
+
+
+def disc_channels(size):
+    return [8, size * 2, size * 4, size * 8, size * 12]
+
+
+def decoder_plan(size):
+    """(unit, [extra source channel counts after the 3-ch sketch], hidden C, out C)."""
+    return [(0, size, size * 8, size * 6), (2, size * 2, size * 6, size * 4), (4, size, size * 4, size * 2),
+            (6, 8, size * 2, size * 2), (8, 0, size * 2, size)]
+
+
+def generator_vars(size=64, vocab_size=58, H=192, W=192):
+    assert H % 32 == 0 and W % 32 == 0, "image size must be a multiple of 32"
+    p = "generator"
+    ch = encoder_channels(size)
+    v = _conv(p + "/Conv", 7, 3, 8, 0.0, False)
+    for u in range(1, 5):
+        v += _enc_unit(p, u, ch[u - 1], ch[u], "cbn", False)
+    v += _cbn(p + "/mru_conv_unit_last_norm", ch[4])
+    d = ch[4]
+    v.append(VarSpec(p + "/TextLSTM/embedding", (vocab_size, d), ("uniform", 0.08)))
+    for cell, kin in (("WLSTM", 2 * d), ("ALSTM", 4 * d)):
+        b = p + "/TextLSTM/RNN/%s/multi_rnn_cell/cell_0/basic_lstm_cell" % cell
+        v.append(VarSpec(b + "/kernel", (kin, 4 * d), ("glorot_uniform", None)))
+        v.append(VarSpec(b + "/bias", (4 * d,), ("const", 0.0)))
+    nfc = (d // 8) * (H // 16) * (W // 16)
+    v.append(VarSpec(p + "/fully_connected/weights", (NOISE_DIM, nfc), ("xavier", None), reg=1e-6))
+    v.append(VarSpec(p + "/fully_connected/biases", (nfc,), ("const", 0.0)))
+    for (u, cx, chid, cout) in decoder_plan(size):
+        s = "%s/mru_deconv_unit_t_%d_layer_0" % (p, u)
+        cin = chid + 3 + cx
+        v += _conv(s + "/Conv", 3, cin, chid, 1e-5, False)
+        v += _conv(s + "/Conv_1", 3, cin, cout, 1e-5, False)
+        v += _conv(s + "/Conv_2", 3, cin, cout, 1e-5, False) + _cbn(s + "/Conv_2", cout)
+        v += _conv(s + "/Conv_3", 3, cout, cout, 1e-5, False) + _cbn(s + "/Conv_3", cout)
+        if chid != cout:
+            v += _conv(s + "/Conv_4", 1, chid, cout, 0.0, False) + _cbn(s + "/Conv_4", cout)
+    v += _conv(p + "/Conv_1", 7, size, 3, 0.0, False)
+    return v
+
+
+def discriminator_vars(size=64):
+    p = "discriminator"
+    ch = disc_channels(size)
+    v = _conv(p + "/Conv", 7, 3, 8, 0.0, True) + _prelu(p + "/Conv")
+    for u in range(1, 5):
+        v += _enc_unit(p, u, ch[u - 1], ch[u], "prelu", True)
+    v += _prelu(p + "/mru_conv_unit_last_norm")
+    v += _conv(p + "/Conv_1", 1, ch[4], 1, 0.0, True)
+    fc = p + "/fully_connected"
+    v.append(VarSpec(fc + "/weights", (ch[4], NUM_CLASSES), ("xavier", None), reg=1e-6, sn=True))
+    v.append(VarSpec(fc + "/" + fc + "/u", (1, NUM_CLASSES), ("trunc_normal", 1.0), trainable=False))
+    v.append(VarSpec(fc + "/biases", (NUM_CLASSES,), ("const", 0.0)))
+    return v
+
+
+class ParamStore:
+    """Flat fp32 parameter / gradient / Adam-v buffers of one network plus named views."""
+
+    def __init__(self, specs, device, dtype=torch.float32):
+        self.specs = list(specs)
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.offsets = OrderedDict()
+        off = 0
+        for s in self.specs:
+            if s.trainable:
+                self.offsets[s.name] = off
+                off += (s.numel + ALIGN - 1) // ALIGN * ALIGN
+        self.n_flat = off
+        self.flat = torch.zeros(off, dtype=dtype, device=self.device)
+        self.grad = torch.zeros(off, dtype=dtype, device=self.device)
+        self.adam_v = torch.zeros(off, dtype=dtype, device=self.device)
+        self.adam_t = 0
+        self.p, self.g = OrderedDict(), OrderedDict()
+        self.state = OrderedDict()      # non-trainable (SN `u`)
+        for s in self.specs:
+            if s.trainable:
+                o = self.offsets[s.name]
+                self.p[s.name] = self.flat[o:o + s.numel].view(s.shape)
+                self.g[s.name] = self.grad[o:o + s.numel].view(s.shape)
+            else:
+                self.state[s.name] = torch.zeros(s.shape, dtype=dtype, device=self.device)
+        # chunk table for the fused Adam / weight-decay kernels: (start, length, reg) rows
+        rows = []
+        CH = 1 << 15
+        for s in self.specs:
+            if not s.trainable:
+                continue
+            o = self.offsets[s.name]
+            for c0 in range(0, s.numel, CH):
+                rows.append((o + c0, min(CH, s.numel - c0), s.reg))
+        self.chunk_start = torch.tensor([r[0] for r in rows], dtype=torch.int64, device=self.device)
+        self.chunk_len = torch.tensor([r[1] for r in rows], dtype=torch.int32, device=self.device)
+        self.chunk_reg = torch.tensor([r[2] for r in rows], dtype=torch.float32, device=self.device)
+
+    # --- counts (reference: main_procedure.print_parameter_count, :28-59) ---
+    def num_trainable_tensors(self):
+        return len(self.p)
+
+    def num_params(self):
+        return sum(s.numel for s in self.specs if s.trainable)
+
+    # --- state dict keyed by the reference variable names -------------------
+    def state_dict(self):
+        d = OrderedDict((k, v.detach().clone()) for k, v in self.p.items())
+        d.update((k, v.detach().clone()) for k, v in self.state.items())
+        return d
+
+    def load_state_dict(self, d, strict=True):
+        for k, v in list(self.p.items()) + list(self.state.items()):
+            if k in d:
+                v.copy_(torch.as_tensor(d[k]).reshape(v.shape).to(v.dtype))
+            elif strict:
+                raise KeyError("missing variable %s" % k)
+
+    def initialize(self, seed, perturb_tables=0.0):
+        """Reference initialisers: N(0,0.02) convs (models_collection.py:896), xavier FCs (mru.py:54),
+        U(+-0.08) embedding (:181), glorot-uniform LSTM kernels (TF default), zeros/ones cBN tables (:30-31),
+        0.5 update-gate biases (mru.py:359), 0.2 PReLU (:58), truncated-normal `u` (sn.py:18)."""
+        g = torch.Generator().manual_seed(seed)
+        f64 = torch.float64
+        for s in self.specs:
+            kind, arg = s.init
+            shape = s.shape
+            if kind == "normal":
+                t = torch.randn(shape, generator=g, dtype=f64) * arg
+            elif kind == "trunc_normal":
+                t = torch.randn(shape, generator=g, dtype=f64)
+                for _ in range(8):
+                    bad = t.abs() > 2
+                    if not bad.any():
+                        break
+                    t = torch.where(bad, torch.randn(shape, generator=g, dtype=f64), t)
+                t = t.clamp(-2, 2) * arg
+            elif kind == "const":
+                t = torch.full(shape, float(arg), dtype=f64)
+                if perturb_tables and (s.name.endswith("/offset") or s.name.endswith("/scale")
+                                       or s.name.endswith("prelu/param")):
+                    t = t + torch.randn(shape, generator=g, dtype=f64) * perturb_tables
+            elif kind == "uniform":
+                t = (torch.rand(shape, generator=g, dtype=f64) * 2 - 1) * arg
+            else:  # glorot_uniform / xavier
+                lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+                t = (torch.rand(shape, generator=g, dtype=f64) * 2 - 1) * lim
+            dst = self.p[s.name] if s.trainable else self.state[s.name]
+            dst.copy_(t.to(self.dtype))
+        self.adam_v.zero_()
+        self.adam_t = 0

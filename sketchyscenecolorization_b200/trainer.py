@@ -1,0 +1,121 @@
+"""The two graphs the reference's session loop evaluates every iteration, as explicit step functions.
+
+Reference: graph_single.build_single_graph (:221-314) wires G, D(real), D(fake) and get_losses (:317-581);
+main_procedure.train (:202-227) alternates `sess.run([opt_d, loss_d])` and `sess.run([opt_g, loss_g, ...])`,
+each on a freshly dequeued batch.  Here:
+
+  d_step = G forward (no tape) + D(real) + D(fake) + loss_d + D backward            (Gf + 6 Df conv FLOPs)
+  g_step = G forward + D(fake) + loss_g + D input-gradient + G backward + SN u<-u'  (3 Gf + 2 Df)
+
+followed by `average_gradients` (NCCL all-reduce when world_size > 1, graph_single.py:33-68) and Adam
+(beta1=0, beta2=0.9, lr*decay; graph_single.py:139-142,588).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .discriminator import Discriminator
+from .generator import Generator
+from .params import ParamStore, discriminator_vars, generator_vars
+
+
+def lr_decay(counter, max_iter):
+    """graph_single.py:139 -- max(0.2, 1 - 0.9*counter/max_iter)."""
+    return max(0.2, 1.0 - (float(counter) / max_iter * 0.9))
+
+
+class FgColorModel:
+    """Generator + discriminator + parameter stores on one device."""
+
+    def __init__(self, ops, device, *, size=64, H=192, W=192, vocab_size=58, lstm_hybrid=True,
+                 param_dtype=torch.float32, with_discriminator=True):
+        self.ops, self.device, self.size, self.H, self.W = ops, device, size, H, W
+        self.gstore = ParamStore(generator_vars(size, vocab_size, H, W), device, param_dtype)
+        self.G = Generator(ops, self.gstore, size, lstm_hybrid)
+        self.dstore = None
+        self.D = None
+        if with_discriminator:
+            self.dstore = ParamStore(discriminator_vars(size), device, param_dtype)
+            self.D = Discriminator(ops, self.dstore, size)
+
+    def initialize(self, seed=0, perturb_tables=0.0):
+        self.gstore.initialize(seed, perturb_tables)
+        if self.dstore is not None:
+            self.dstore.initialize(seed + 1, perturb_tables)
+
+    # ---- inference graph: build_single_graph(training=False) -> image_gens (graph_single.py:257-266)
+    def generate(self, sketch_nchw, text_ids_host, labels, noise):
+        out, _ = self.G.forward(sketch_nchw, text_ids_host, labels, noise, save=False)
+        return self.ops.nhwc_to_nchw(out, out_dtype=torch.float32)
+
+    # ---- loss_d and dL/dtheta_D
+    def d_step_grads(self, batch):
+        """batch: dict(sketch, images, images_d [N,3,H,W] fp32; cls, cls_d int32 [N]; text host [N,15]; noise [N,256]).
+        Leaves dL_d/dtheta_D in dstore.grad; returns dict of fp32 0-d loss tensors (total under 'loss')."""
+        ops = self.ops
+        self.dstore.grad.zero_()
+        fake, _ = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=False)
+        wv = self.D.new_weight_view(need_wgrad=True)
+        real = ops.nchw_to_nhwc(batch["images_d"])
+        rd, rl, rctx = self.D.forward(real, wv)
+        l_real, g_rd = ops.softplus_mean(rd, -1.0)                       # graph_single.py:402
+        l_ac, g_rl = ops.ce_loss(rl, batch["cls_d"], True, 1.0)         # :343-348 (focal, ld1 = 1)
+        self.D.backward(g_rd, g_rl, rctx, need_x_grad=False)
+        del rctx, rd, rl
+        fd, fl, fctx = self.D.forward(fake, wv)
+        l_fake, g_fd = ops.softplus_mean(fd, 1.0)                        # :402
+        self.D.backward(g_fd, None, fctx, need_x_grad=False)
+        del fctx
+        wv.finish_backward()
+        reg = ops.reg_loss(self.dstore)                                  # :571
+        return dict(loss=l_real + l_fake + l_ac + reg, gan=l_real + l_fake, ac=l_ac, reg=reg)
+
+    # ---- loss_g and dL/dtheta_G (+ SN u update)
+    def g_step_grads(self, batch):
+        ops = self.ops
+        self.gstore.grad.zero_()
+        fake, gctx = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=True)
+        wv = self.D.new_weight_view(need_wgrad=False)
+        fd, fl, fctx = self.D.forward(fake, wv)
+        l_gan, g_fd = ops.softplus_mean(fd, -1.0)                        # graph_single.py:401
+        l_ac, g_fl = ops.ce_loss(fl, batch["cls"], False, 0.5)          # :350-352 (ld2 = 0.5)
+        g_fake = self.D.backward(g_fd, g_fl, fctx, need_x_grad=True)
+        del fctx
+        target = ops.nchw_to_nhwc(batch["images"])
+        l_l1, g_l1 = ops.smooth_l1(target, fake, 100.0)                  # :552-555,575
+        ops.add_(g_fake, g_l1)
+        self.G.backward(g_fake, gctx)
+        wv.commit_u()                                                    # :178-180,208-210
+        reg = ops.reg_loss(self.gstore)
+        return dict(loss=l_gan + l_ac + l_l1 + reg, gan=l_gan, ac=l_ac, l1=l_l1, reg=reg)
+
+
+class FgColorTrainer:
+    """Alternating D / G optimisation with optional data-parallel gradient averaging."""
+
+    def __init__(self, model, *, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=None, world_size=1):
+        self.m, self.lr_g, self.lr_d, self.max_iter = model, lr_g, lr_d, max_iter
+        self.pg, self.world = process_group, world_size
+        self.counter = 0
+
+    def _allreduce(self, store):
+        """average_gradients (graph_single.py:33-68): one all-reduce of the flat fp32 gradient bucket."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(store.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            store.grad.mul_(1.0 / self.world)
+
+    def d_step(self, batch):
+        out = self.m.d_step_grads(batch)
+        self._allreduce(self.m.dstore)
+        self.m.ops.adam_step(self.m.dstore, self.lr_d * lr_decay(self.counter, self.max_iter))
+        return out
+
+    def g_step(self, batch):
+        out = self.m.g_step_grads(batch)
+        self._allreduce(self.m.gstore)
+        self.m.ops.adam_step(self.m.gstore, self.lr_g * lr_decay(self.counter, self.max_iter))
+        self.counter += 1                                                # counter_addition_op, main_procedure.py:106,221
+        return out
