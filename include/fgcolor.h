@@ -1,0 +1,174 @@
+/* fgcolor.h -- C-ABI of libfgcolor.so: hand-written sm_100a kernels for the
+ * SketchySceneColorization foreground-instance-colorization hot path.
+ *
+ * The reference (TensorFlow-1, pure Python) has no FFI of its own; the seam is the set of TF ops its layer
+ * library calls.  Each entry point below replaces one such call site (cited as file:line, paths relative to
+ * Foreground_Instance_Colorization/obj_lib/).  The Python host code binds these with ctypes
+ * (sketchyscenecolorization_b200/_lib.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers owned by the caller and must stay valid
+ *     until `stream` reaches the end of the call; nothing is allocated, nothing synchronises.
+ *   - every call returns 0 on success or a negative FGC_E* code; fgc_last_error() gives the message
+ *     (thread-local).
+ *   - activations are NHWC; `dtype` 0 = fp32, 1 = bf16 (the storage type of the tensor behind a void*).
+ *     Weights, biases, tables, statistics and weight gradients are always fp32; conv weights are HWIO.
+ */
+#ifndef FGCOLOR_H_
+#define FGCOLOR_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fgc_stream;     /* cudaStream_t */
+
+enum { FGC_OK = 0, FGC_EINVAL = -1, FGC_ECUDA = -2, FGC_EUNSUPPORTED = -3 };
+enum { FGC_F32 = 0, FGC_BF16 = 1 };
+enum { FGC_ACT_NONE = 0, FGC_ACT_LRELU = 1, FGC_ACT_TANH = 2, FGC_ACT_MIU = 3 };
+
+const char* fgc_last_error(void);
+int fgc_version(void);
+/* number of kernel launches issued through this library by the calling process (bench.py `gpu_launches`) */
+long long fgc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Convolution family.  Replaces tf.nn.conv2d(NCHW, SAME)+bias(+activation) in mru.conv2d (mru.py:95-140),
+ * tf.matmul in mru.fully_connected (mru.py:75) and BasicLSTMCell (models_collection.py:184-187), the
+ * tf.concat of conv inputs (mru.py:403,552,572; models_collection.py:323-353) and mru.upsample
+ * (mru.py:22-28) in front of a conv, plus the gradients TF autodiff derives for them.
+ * -------------------------------------------------------------------------------------------------------*/
+typedef struct {
+  const void* ptr;   /* NHWC [N, H/(ups?2:1), W/(ups?2:1), C] */
+  int C;
+  int ups;           /* 1: read through nearest-neighbour x2 upsample */
+} fgc_src;
+
+/* Bytes of device workspace `ws` a forward (n_out = Cout, sources = the conv inputs) or input-gradient
+ * (n_out = c_len, one source of Cout channels) call needs for its packed bf16 weight tiles. */
+size_t fgc_conv2d_ws_bytes(const int* src_C, int nsrc, int k, int n_out, int src_dtype);
+/* 0 = tcgen05 tensor-core path (default), 1 = CUDA-core checker (also: env FGC_CONV_IMPL=simple) */
+int fgc_set_conv_impl(int impl);
+
+/* y[N,OH,OW,Cout] = act(conv(concat_c(srcs), w) + bias); SAME padding (pad_t/pad_l = TF's top/left pad).
+ * w: fp32 HWIO [k,k,Cin_total,Cout]; bias fp32 [Cout] or NULL.  fp32 sources run the bf16x3 split-accumulate
+ * tensor-core mode, bf16 sources single-pass bf16; accumulation is fp32 in TMEM either way. */
+int fgc_conv2d_fwd(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W,
+                   const float* w, int k, int Cin_total, int Cout, const float* bias,
+                   int stride, int pad_t, int pad_l, int OH, int OW, int act,
+                   void* y, int y_dtype, void* ws, fgc_stream stream);
+
+/* gx[N,H,W,c_len] (=|+=) d/d(input channels [c_off,c_off+c_len)) of a stride-1 SAME conv given gy[N,H,W,Cout].
+ * ups=1: gx is the 2x2-summed low-res gradient [N,H/2,W/2,c_len]; `scratch` must then hold N*H*W*c_len floats. */
+int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const float* w, int k, int Cin_total,
+                     int Cout, int c_off, int c_len, int ups, int accumulate, void* gx, int gx_dtype,
+                     void* scratch, void* ws, fgc_stream stream);
+
+/* dw[k,k,Cin_total,Cout] += sum_m x[m+tap,ci]*gy[m,co];  db[Cout] += sum_m gy (db may be NULL). */
+int fgc_conv2d_wgrad(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W,
+                     const void* gy, int gy_dtype, int k, int Cin_total, int Cout,
+                     int stride, int pad_t, int pad_l, int OH, int OW,
+                     float* dw, float* db, fgc_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Conditional batch-norm with batch statistics (models_collection.batchnorm, :22-34) fused with miu_relu
+ * (:63-65); PReLU (:56-60); spatial min-max gate normalisation (mru.py:415-416,560-561,568-569).
+ * -------------------------------------------------------------------------------------------------------*/
+/* stats[0:C]=mean, stats[C:2C]=rstd over M=N*H*W rows; acc: 2*C doubles of scratch (zeroed by the call). */
+int fgc_chan_stats(const void* x, int dtype, long long M, int C, double* acc, float* stats, fgc_stream stream);
+int fgc_cbn_act_fwd(const void* x, int dtype, int N, int HW, int C, const float* stats, const float* scale,
+                    const float* offset, const int32_t* labels, int act, void* y, fgc_stream stream);
+/* scratch: 2*N*C + 2*C floats.  dscale/doffset [n_labels,C] accumulate. */
+int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int C, const float* stats,
+                    const float* scale, const float* offset, const int32_t* labels, int act,
+                    float* dscale, float* doffset, void* gx, float* scratch, fgc_stream stream);
+int fgc_prelu_fwd(const void* x, int dtype, long long n, const float* a, void* y, fgc_stream stream);
+int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, const float* a, float* da /*NULL ok*/,
+                  void* gx, fgc_stream stream);
+/* gate=(x-mn)/(mx-mn) per (n,c); mn,mx fp32 [N,C]; scratch: 2*N*C uint32. */
+int fgc_minmax_fwd(const void* x, int dtype, int N, int HW, int C, void* gate, float* mn, float* mx,
+                   uint32_t* scratch, fgc_stream stream);
+/* gradient w.r.t. the pre-lrelu conv output (leak 0.2); scratch: 4*N*C floats. */
+int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, int C, const float* mn,
+                   const float* mx, void* gpre, float* scratch, fgc_stream stream);
+/* gradient through an activation fused in a conv epilogue, from its output y (tanh / miu_relu). */
+int fgc_act_bwd(const void* gy, const void* y, int dtype, long long n, int act, void* gx, fgc_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Gating / resampling: ht + rg*img (mru.py:426), rg*up(ht) (:572), ht*(1-zg)+h*zg (:589),
+ * mean_pool(ht_orig+h_new) (:453,457 + :15-19), mean_pool pyramids (models_collection.py:84-86,268-272,697-699),
+ * reduce_mean over H,W (:783).
+ * -------------------------------------------------------------------------------------------------------*/
+int fgc_gate_fma_fwd(const void* ht, const void* rg, const void* im, int dtype, long long n, void* out, fgc_stream s);
+int fgc_gate_fma_bwd(const void* g, const void* rg, const void* im, int dtype, long long n, void* g_rg, void* g_im, fgc_stream s);
+/* full-res tensors are [N,2h,2w,C], low-res [N,h,w,C] */
+int fgc_mul_up_fwd(const void* rg, const void* ht_low, int dtype, int N, int h, int w, int C, void* out, fgc_stream s);
+int fgc_mul_up_bwd(const void* g, const void* rg, const void* ht_low, int dtype, int N, int h, int w, int C,
+                   void* g_rg, void* g_ht_low, fgc_stream s);
+int fgc_blend_fwd(const void* sk_low, const void* h2, const void* zg, int dtype, int N, int h, int w, int C, void* out, fgc_stream s);
+int fgc_blend_bwd(const void* g, const void* sk_low, const void* h2, const void* zg, int dtype, int N, int h, int w, int C,
+                  void* g_sk_low, void* g_h2, void* g_zg, fgc_stream s);
+/* out[N,h,w,C] = mean2x2(a + b); b may be NULL (plain mean_pool) */
+int fgc_addpool_fwd(const void* a, const void* b, int dtype, int N, int h, int w, int C, void* out, fgc_stream s);
+/* out[N,2h,2w,C] = up2(g)/4 */
+int fgc_unpool_bwd(const void* g, int dtype, int N, int h, int w, int C, void* out, fgc_stream s);
+/* out[N,h,w,C] (=|+=) sum over each 2x2 block of g[N,2h,2w,C]  (gradient of mru.upsample, mru.py:22-28) */
+int fgc_sum2x2(const void* g, int g_dtype, int N, int h, int w, int C, void* out, int out_dtype, int accumulate, fgc_stream s);
+int fgc_axpy(void* dst, const void* src, int dst_dtype, int src_dtype, long long n, float alpha, fgc_stream s); /* dst += alpha*src */
+int fgc_spatial_mean_fwd(const void* x, int dtype, int N, int HW, int C, void* out, fgc_stream s);
+int fgc_spatial_mean_bwd(const void* g, int dtype, int N, int HW, int C, void* out, fgc_stream s);
+int fgc_nchw_to_nhwc(const void* x, int x_dtype, int N, int C, int HW, void* y, int y_dtype, fgc_stream s);
+int fgc_nhwc_to_nchw(const void* x, int x_dtype, int N, int C, int HW, void* y, int y_dtype, fgc_stream s);
+int fgc_cast(const void* x, int x_dtype, void* y, int y_dtype, long long n, fgc_stream s);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Caption encoder pieces (models_collection.encode_feat_with_text, :150-248): tf.nn.l2_normalize (:202,216),
+ * embedding_lookup (:182), BasicLSTMCell gates (:213,226) with the tf.cond pad skip (:235), the
+ * 0.5*(log(1.001+h)-log(1.001-h)) -> relu output transform (:239-241).  All fp32.
+ * -------------------------------------------------------------------------------------------------------*/
+int fgc_l2norm_rows_fwd(const float* x, int R, int D, float* y, float* inv, fgc_stream s);
+int fgc_l2norm_rows_bwd(const float* gy, const float* y, const float* inv, int R, int D, float* gx, fgc_stream s);
+int fgc_embedding_fwd(const float* table, const int32_t* ids, int N, int T, int t, int D, float* out, fgc_stream s);
+int fgc_embedding_bwd(const float* g, const int32_t* ids, int N, int T, int t, int D, float* dtable, fgc_stream s);
+/* pre = gates (+gates2) (+grow[r/P]); R = N*P rows of 4*D; gates2/grow may be NULL */
+int fgc_lstm_cell_fwd(const float* gates, const float* gates2, const float* grow, const float* c_prev,
+                      const float* h_prev, const int32_t* ids, int T, int t, int N, int P, int D,
+                      float* c, float* h, float* pre, fgc_stream s);
+int fgc_lstm_cell_bwd(const float* gc, const float* gh, const float* pre, const float* c_prev,
+                      const int32_t* ids, int T, int t, int N, int P, int D,
+                      float* g_pre, float* g_c_prev, float* g_h_pass, fgc_stream s);
+int fgc_rows_group_sum(const float* x, int N, int P, int C, float* out, fgc_stream s);
+int fgc_atanh_relu_fwd(const float* h, long long n, float* y, fgc_stream s);
+int fgc_atanh_relu_bwd(const float* gy, const float* h, long long n, float* gx, fgc_stream s);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Spectral normalisation (sn.spectral_normed_weight, sn.py:12-52; one power iteration, gradient through
+ * sigma and through the iteration).  w [K,C]; u [C]; work: K + 2*C + 8 floats laid out as
+ * a[K] | b[C] | u_new[C] | scal[8] = {na^2 acc, na, nb, sigma, dot acc, cb, s acc, -}.
+ * -------------------------------------------------------------------------------------------------------*/
+int fgc_sn_fwd(const float* w, const float* u, int K, int C, float* wbar, float* work, fgc_stream s);
+int fgc_sn_bwd(const float* gwbar, const float* w, const float* u, int K, int C, float* work /*from fwd*/,
+               float* gv /*K floats scratch*/, float* dw, fgc_stream s);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Losses (graph_single.get_losses, :317-581) and optimiser (graph_single.py:139-142,588).
+ * Every loss call adds weight*loss to lossbuf[slot] and to lossbuf[0]; gradients are w.r.t. the logits/images.
+ * -------------------------------------------------------------------------------------------------------*/
+int fgc_softplus_mean(const void* d, int dtype, long long n, float sign, float* lossbuf, int slot, void* gd, fgc_stream s); /* :401-402 */
+int fgc_ce_loss(const void* logits, int dtype, const int32_t* labels, int N, int C, int focal, float weight,
+                float* lossbuf, int slot, void* glogits, fgc_stream s);                                                     /* :343-352 */
+int fgc_smooth_l1(const void* target, const void* gen, int dtype, long long n, float weight, float* lossbuf, int slot,
+                  void* ggen, fgc_stream s);                                                                                /* :552-555 */
+/* chunk table over a flat parameter buffer: chunk i covers [start[i], start[i]+len[i]) with l2 scale reg[i] */
+int fgc_reg_loss(const float* flat, const long long* start, const int32_t* len, const float* reg, int nchunks,
+                 float* lossbuf, int slot, fgc_stream s);                                                                   /* :570-576 */
+/* g += reg*w (if add_reg); v = b2 v + (1-b2) g^2; w -= lr_t * g / (sqrt(v)+eps), lr_t = lr*sqrt(1-b2^t) (beta1 = 0) */
+int fgc_adam_step(float* flat, float* grad, float* v, const long long* start, const int32_t* len, const float* reg,
+                  int nchunks, float lr_t, float beta2, float eps, int add_reg, fgc_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* FGCOLOR_H_ */

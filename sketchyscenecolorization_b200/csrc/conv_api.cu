@@ -1,0 +1,140 @@
+// C-ABI entry points of the convolution family (see include/fgcolor.h).
+// FGC_CONV_IMPL=simple selects the CUDA-core checker in conv_simple.cu; the default is the tcgen05 path.
+#include <cstdlib>
+#include <cstring>
+
+#include "conv_geom.cuh"
+
+namespace fgc {
+int conv_fwd_simple(const ConvGeom& g, int src_dtype, const float* w, int Cin_total, int Cout, const float* bias, int act,
+                    void* y, int y_dtype, cudaStream_t s);
+int conv_dgrad_simple(const void* gy, int gy_dtype, int N, int H, int W, const float* w, int k, int Cin_total, int Cout,
+                      int c_off, int c_len, int ups, int accumulate, void* gx, int gx_dtype, cudaStream_t s);
+int conv_wgrad_simple(const ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s);
+int colsum_launch(const void* x, int dtype, long long M, int C, float* out, cudaStream_t s);
+int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride, long long n_stride,
+                   long long base, int nout, const float* bias, int act, int accumulate, void* y, int y_dtype, void* ws,
+                   cudaStream_t s);
+int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s);
+size_t conv_ws_bytes(const ConvGeom& g, int nout, int x3);
+
+static int g_impl = -1;   // 0 = tcgen05, 1 = simple
+static int conv_impl() {
+  if (g_impl < 0) {
+    const char* e = getenv("FGC_CONV_IMPL");
+    g_impl = (e && !strcmp(e, "simple")) ? 1 : 0;
+  }
+  return g_impl;
+}
+
+static int build_geom(ConvGeom& g, const fgc_src* srcs, int nsrc, int N, int H, int W, int k, int stride, int pad_t, int pad_l,
+                      int OH, int OW, int sign) {
+  memset(&g, 0, sizeof(g));
+  FGC_REQUIRE(nsrc >= 1 && nsrc <= kMaxSrc, "conv: %d sources (max %d)", nsrc, kMaxSrc);
+  g.nsrc = nsrc;
+  for (int i = 0; i < nsrc; i++) {
+    g.src[i] = srcs[i].ptr;
+    g.C[i] = srcs[i].C;
+    g.ups[i] = srcs[i].ups;
+    FGC_REQUIRE(srcs[i].C > 0 && srcs[i].ptr, "conv: bad source %d", i);
+    if (srcs[i].ups) FGC_REQUIRE(H % 2 == 0 && W % 2 == 0, "conv: upsampled source needs even H, W");
+  }
+  g.N = N; g.H = H; g.W = W; g.OH = OH; g.OW = OW;
+  g.k = k; g.stride = stride; g.pad_t = pad_t; g.pad_l = pad_l; g.sign = sign;
+  return FGC_OK;
+}
+}  // namespace fgc
+
+using namespace fgc;
+
+extern "C" {
+
+int fgc_set_conv_impl(int impl) {
+  g_impl = impl ? 1 : 0;
+  return FGC_OK;
+}
+
+size_t fgc_conv2d_ws_bytes(const int* src_C, int nsrc, int k, int n_out, int src_dtype) {
+  ConvGeom g;
+  memset(&g, 0, sizeof(g));
+  g.nsrc = nsrc;
+  for (int i = 0; i < nsrc && i < kMaxSrc; i++) g.C[i] = src_C[i];
+  g.k = k;
+  g.N = g.OH = g.OW = g.H = g.W = 1;
+  finish_geom(g);
+  return conv_ws_bytes(g, n_out, src_dtype == FGC_F32) + 256;
+}
+
+int fgc_conv2d_fwd(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W,
+                   const float* w, int k, int Cin_total, int Cout, const float* bias,
+                   int stride, int pad_t, int pad_l, int OH, int OW, int act,
+                   void* y, int y_dtype, void* ws, fgc_stream stream) {
+  ConvGeom g;
+  int e = build_geom(g, srcs, nsrc, N, H, W, k, stride, pad_t, pad_l, OH, OW, 1);
+  if (e) return e;
+  int cin = finish_geom(g);
+  FGC_REQUIRE(cin == Cin_total, "conv_fwd: sources have %d channels, weights expect %d", cin, Cin_total);
+  cudaStream_t s = as_stream(stream);
+  if (conv_impl() == 1) {
+    e = conv_fwd_simple(g, src_dtype, w, Cin_total, Cout, bias, act, y, y_dtype, s);
+    if (e) return e;
+    FGC_LAUNCH_CHECK("conv_fwd_simple");
+    return FGC_OK;
+  }
+  return conv_igemm_run(g, src_dtype, w, (long long)Cin_total * Cout, Cout, 1, 0, Cout, bias, act, 0, y, y_dtype, ws, s);
+}
+
+int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const float* w, int k, int Cin_total,
+                     int Cout, int c_off, int c_len, int ups, int accumulate, void* gx, int gx_dtype,
+                     void* scratch, void* ws, fgc_stream stream) {
+  FGC_REQUIRE(k % 2 == 1, "conv_dgrad: odd kernel sizes only (got %d)", k);
+  FGC_REQUIRE(c_off >= 0 && c_len > 0 && c_off + c_len <= Cin_total, "conv_dgrad: bad channel slice");
+  cudaStream_t s = as_stream(stream);
+  if (conv_impl() == 1) {
+    int e = conv_dgrad_simple(gy, gy_dtype, N, H, W, w, k, Cin_total, Cout, c_off, c_len, ups, accumulate, gx, gx_dtype, s);
+    if (e) return e;
+    FGC_LAUNCH_CHECK("conv_dgrad_simple");
+    return FGC_OK;
+  }
+  // a stride-1 SAME conv over gy with the taps mirrored and the weight matrix transposed
+  fgc_src src{gy, Cout, 0};
+  ConvGeom g;
+  int pad = (k - 1) / 2;
+  int e = build_geom(g, &src, 1, N, H, W, k, 1, pad, pad, H, W, -1);
+  if (e) return e;
+  finish_geom(g);
+  if (!ups)
+    return conv_igemm_run(g, gy_dtype, w, (long long)Cin_total * Cout, 1, Cout, (long long)c_off * Cout, c_len, nullptr,
+                          FGC_ACT_NONE, accumulate, gx, gx_dtype, ws, s);
+  FGC_REQUIRE(scratch != nullptr, "conv_dgrad: ups needs a full-resolution fp32 scratch");
+  e = conv_igemm_run(g, gy_dtype, w, (long long)Cin_total * Cout, 1, Cout, (long long)c_off * Cout, c_len, nullptr, FGC_ACT_NONE, 0,
+                     scratch, FGC_F32, ws, s);
+  if (e) return e;
+  return fgc_sum2x2(scratch, FGC_F32, N, H / 2, W / 2, c_len, gx, gx_dtype, accumulate, stream);
+}
+
+int fgc_conv2d_wgrad(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W,
+                     const void* gy, int gy_dtype, int k, int Cin_total, int Cout,
+                     int stride, int pad_t, int pad_l, int OH, int OW,
+                     float* dw, float* db, fgc_stream stream) {
+  FGC_REQUIRE(src_dtype == gy_dtype, "conv_wgrad: sources and gy must share a dtype");
+  ConvGeom g;
+  int e = build_geom(g, srcs, nsrc, N, H, W, k, stride, pad_t, pad_l, OH, OW, 1);
+  if (e) return e;
+  int cin = finish_geom(g);
+  FGC_REQUIRE(cin == Cin_total, "conv_wgrad: sources have %d channels, weights expect %d", cin, Cin_total);
+  cudaStream_t s = as_stream(stream);
+  if (db) {
+    e = colsum_launch(gy, gy_dtype, g.M, Cout, db, s);
+    if (e) return e;
+  }
+  if (conv_impl() == 1) {
+    e = conv_wgrad_simple(g, src_dtype, gy, Cin_total, Cout, dw, s);
+    if (e) return e;
+    FGC_LAUNCH_CHECK("conv_wgrad_simple");
+    return FGC_OK;
+  }
+  return conv_wgrad_run(g, src_dtype, gy, Cin_total, Cout, dw, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// Plain CUDA-core (fp32 FMA) direct convolution: forward, input gradient, weight gradient.
+//
+// This is the library's own checker for the tcgen05 kernels in conv_tc.cu (selected with
+// FGC_CONV_IMPL=simple): same C-ABI, same geometry decode, no tensor cores, no staging -- one thread per
+// output element.  It is only meant for small shapes; the tcgen05 path is the product path.
+#include "conv_geom.cuh"
+
+namespace fgc {
+int ew_grid(long long work, int threads);
+int num_sms();
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case FGC_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
+    case FGC_ACT_TANH: return tanhf(v);
+    case FGC_ACT_MIU: return miu_relu(v);
+    default: return v;
+  }
+}
+
+template <typename TS, typename TO>
+__global__ void conv_fwd_simple_kernel(ConvGeom g, const float* __restrict__ w, int Cin_total, int Cout,
+                                       const float* __restrict__ bias, int act, TO* __restrict__ y) {
+  long long total = g.M * Cout;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int co = (int)(idx % Cout);
+    long long m = idx / Cout;
+    int ow = (int)(m % g.OW);
+    int oh = (int)((m / g.OW) % g.OH);
+    int n = (int)(m / ((long long)g.OW * g.OH));
+    float acc = bias ? bias[co] : 0.f;
+    for (int kh = 0; kh < g.k; kh++) {
+      int ih = oh * g.stride + g.sign * (kh - g.pad_t);
+      if (ih < 0 || ih >= g.H) continue;
+      for (int kw = 0; kw < g.k; kw++) {
+        int iw = ow * g.stride + g.sign * (kw - g.pad_l);
+        if (iw < 0 || iw >= g.W) continue;
+        const float* wt = w + (long long)(kh * g.k + kw) * Cin_total * Cout;
+        for (int s = 0; s < g.nsrc; s++) {
+          int Hs = g.ups[s] ? g.H / 2 : g.H, Ws = g.ups[s] ? g.W / 2 : g.W;
+          int hh = g.ups[s] ? ih >> 1 : ih, ww = g.ups[s] ? iw >> 1 : iw;
+          const TS* p = (const TS*)g.src[s] + (((long long)n * Hs + hh) * Ws + ww) * g.C[s];
+          const float* wc = wt + (long long)g.cbase[s] * Cout + co;
+          for (int c = 0; c < g.C[s]; c++) acc += ld1<TS>(p + c) * wc[(long long)c * Cout];
+        }
+      }
+    }
+    st1<TO>(y + idx, apply_act(acc, act));
+  }
+}
+
+// gx[n,h,w,ci] (=|+=) sum_{kh,kw,co} gy[n, h+pad_t-kh, w+pad_l-kw, co] * w[kh,kw,c_off+ci,co]; ups: 2x2-summed
+template <typename TG, typename TO>
+__global__ void conv_dgrad_simple_kernel(const TG* __restrict__ gy, int N, int H, int W, const float* __restrict__ w, int k,
+                                         int Cin_total, int Cout, int c_off, int c_len, int ups, int accumulate,
+                                         TO* __restrict__ gx) {
+  int oh_ = ups ? H / 2 : H, ow_ = ups ? W / 2 : W;
+  long long total = (long long)N * oh_ * ow_ * c_len;
+  int pad = (k - 1) / 2;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int ci = (int)(idx % c_len);
+    long long p = idx / c_len;
+    int x = (int)(p % ow_);
+    int y = (int)((p / ow_) % oh_);
+    int n = (int)(p / ((long long)ow_ * oh_));
+    float acc = 0.f;
+    int reps = ups ? 2 : 1;
+    for (int dy = 0; dy < reps; dy++)
+      for (int dx = 0; dx < reps; dx++) {
+        int h = ups ? 2 * y + dy : y, ww = ups ? 2 * x + dx : x;
+        for (int kh = 0; kh < k; kh++) {
+          int gh = h + pad - kh;
+          if (gh < 0 || gh >= H) continue;
+          for (int kw = 0; kw < k; kw++) {
+            int gw = ww + pad - kw;
+            if (gw < 0 || gw >= W) continue;
+            const TG* gp = gy + (((long long)n * H + gh) * W + gw) * Cout;
+            const float* wp = w + ((long long)(kh * k + kw) * Cin_total + c_off + ci) * Cout;
+            for (int co = 0; co < Cout; co++) acc += ld1<TG>(gp + co) * wp[co];
+          }
+        }
+      }
+    if (accumulate) acc += ld1<TO>(gx + idx);
+    st1<TO>(gx + idx, acc);
+  }
+}
+
+// one block per (tap, concat channel); threads over co; serial over all output pixels
+template <typename TS>
+__global__ void conv_wgrad_simple_kernel(ConvGeom g, const TS* __restrict__ gy, int Cin_total, int Cout, float* dw) {
+  int tap = blockIdx.x / Cin_total, cg = blockIdx.x % Cin_total;
+  int kh = tap / g.k, kw = tap % g.k;
+  int s = 0;
+  while (s + 1 < g.nsrc && cg >= g.cbase[s + 1]) s++;
+  int c = cg - g.cbase[s];
+  int Hs = g.ups[s] ? g.H / 2 : g.H, Ws = g.ups[s] ? g.W / 2 : g.W;
+  const TS* src = (const TS*)g.src[s];
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float acc = 0.f;
+    for (long long m = 0; m < g.M; m++) {
+      int ow = (int)(m % g.OW);
+      int oh = (int)((m / g.OW) % g.OH);
+      int n = (int)(m / ((long long)g.OW * g.OH));
+      int ih = oh * g.stride + kh - g.pad_t, iw = ow * g.stride + kw - g.pad_l;
+      if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) continue;
+      int hh = g.ups[s] ? ih >> 1 : ih, ww = g.ups[s] ? iw >> 1 : iw;
+      acc += ld1<TS>(src + (((long long)n * Hs + hh) * Ws + ww) * g.C[s] + c) * ld1<TS>(gy + m * Cout + co);
+    }
+    dw[((long long)tap * Cin_total + cg) * Cout + co] += acc;
+  }
+}
+
+// db[c] += sum_m gy[m,c]
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long M, int C, int rows_per_block, float* out) {
+  long long r0 = (long long)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  if (C <= (int)blockDim.x) {
+    int lanes = blockDim.x / C, c = threadIdx.x % C, rl = threadIdx.x / C;
+    if (rl >= lanes) return;
+    float s = 0.f;
+    for (long long r = r0 + rl; r < r1; r += lanes) s += ld1<T>(x + r * C + c);
+    atomicAdd(&out[c], s);
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (long long r = r0; r < r1; r++) s += ld1<T>(x + r * C + c);
+      atomicAdd(&out[c], s);
+    }
+  }
+}
+
+int colsum_launch(const void* x, int dtype, long long M, int C, float* out, cudaStream_t s) {
+  long long want = (long long)num_sms() * 4;
+  long long rpb = (M + want - 1) / want;
+  if (rpb < 32) rpb = 32;
+  int nblk = (int)((M + rpb - 1) / rpb);
+  FGC_DISPATCH_DTYPE(dtype, T, (colsum_kernel<T><<<nblk, 256, 0, s>>>((const T*)x, M, C, (int)rpb, out)));
+  count_launch();
+  return FGC_OK;
+}
+
+int conv_fwd_simple(const ConvGeom& g, int src_dtype, const float* w, int Cin_total, int Cout, const float* bias, int act,
+                    void* y, int y_dtype, cudaStream_t s) {
+  long long total = g.M * Cout;
+  int grid = ew_grid(total, 128);
+#define FGC_L(TS, TO) conv_fwd_simple_kernel<TS, TO><<<grid, 128, 0, s>>>(g, w, Cin_total, Cout, bias, act, (TO*)y)
+  if (src_dtype == FGC_F32 && y_dtype == FGC_F32) FGC_L(float, float);
+  else if (src_dtype == FGC_F32 && y_dtype == FGC_BF16) FGC_L(float, __nv_bfloat16);
+  else if (src_dtype == FGC_BF16 && y_dtype == FGC_F32) FGC_L(__nv_bfloat16, float);
+  else if (src_dtype == FGC_BF16 && y_dtype == FGC_BF16) FGC_L(__nv_bfloat16, __nv_bfloat16);
+  else { set_error("conv_fwd: bad dtypes"); return FGC_EINVAL; }
+#undef FGC_L
+  count_launch();
+  return FGC_OK;
+}
+
+int conv_dgrad_simple(const void* gy, int gy_dtype, int N, int H, int W, const float* w, int k, int Cin_total, int Cout,
+                      int c_off, int c_len, int ups, int accumulate, void* gx, int gx_dtype, cudaStream_t s) {
+  long long total = (long long)N * (ups ? H / 2 : H) * (ups ? W / 2 : W) * c_len;
+  int grid = ew_grid(total, 128);
+#define FGC_L(TG, TO) \
+  conv_dgrad_simple_kernel<TG, TO><<<grid, 128, 0, s>>>((const TG*)gy, N, H, W, w, k, Cin_total, Cout, c_off, c_len, ups, accumulate, (TO*)gx)
+  if (gy_dtype == FGC_F32 && gx_dtype == FGC_F32) FGC_L(float, float);
+  else if (gy_dtype == FGC_F32 && gx_dtype == FGC_BF16) FGC_L(float, __nv_bfloat16);
+  else if (gy_dtype == FGC_BF16 && gx_dtype == FGC_F32) FGC_L(__nv_bfloat16, float);
+  else if (gy_dtype == FGC_BF16 && gx_dtype == FGC_BF16) FGC_L(__nv_bfloat16, __nv_bfloat16);
+  else { set_error("conv_dgrad: bad dtypes"); return FGC_EINVAL; }
+#undef FGC_L
+  count_launch();
+  return FGC_OK;
+}
+
+int conv_wgrad_simple(const ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s) {
+  int blocks = g.k * g.k * Cin_total;
+  int threads = Cout < 32 ? 32 : (Cout > 256 ? 256 : ((Cout + 31) / 32) * 32);
+  if (src_dtype == FGC_F32) conv_wgrad_simple_kernel<float><<<blocks, threads, 0, s>>>(g, (const float*)gy, Cin_total, Cout, dw);
+  else conv_wgrad_simple_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>(g, (const __nv_bfloat16*)gy, Cin_total, Cout, dw);
+  count_launch();
+  return FGC_OK;
+}
+
+}  // namespace fgc

@@ -1,0 +1,804 @@
+// tcgen05 implicit-GEMM convolution for sm_100a: forward / input-gradient (one kernel) and weight-gradient.
+//
+// Replaces tf.nn.conv2d(SAME)+bias(+act) of mru.conv2d (mru.py:95-140), the tf.concat in front of it
+// (mru.py:403,552,572), mru.upsample in front of it (mru.py:22-28), tf.matmul of mru.fully_connected
+// (mru.py:75) / BasicLSTMCell (models_collection.py:184-187), and the conv gradients TF autodiff derives.
+//
+// Forward / dgrad  (conv_igemm_kernel):  D[128 pixels, BN channels] += A[128, 64] * B[BN, 64]^T per K-slab
+//   * im2col-free: the A tile of a slab is gathered straight from the NHWC sources -- tap shift, SAME zero
+//     padding, channel concat of up to 4 sources and the nearest-neighbour x2 upsample are address
+//     arithmetic in the producer warps, nothing is materialised in HBM.
+//   * A lands in shared memory in the canonical K-major SWIZZLE_128B layout (8-row x 128-byte atoms) that
+//     tcgen05.mma reads through a shared-memory descriptor; 16-byte chunk j of row r sits at j ^ (r & 7).
+//   * B (weights) is pre-packed once per call into bf16 [slab][Cout_pad][64], already swizzled, so a whole
+//     BN x 64 tile is ONE cp.async.bulk (TMA bulk copy, mbarrier complete_tx) per slab.
+//   * accumulators live in TMEM (BN fp32 columns x 128 lanes); one elected thread issues tcgen05.mma
+//     (kind::f16, M=128, N=BN, K=16) and releases smem stages with tcgen05.commit -> mbarrier.
+//   * precision: bf16 sources -> single-pass bf16 x bf16 -> fp32.  fp32 sources -> "bf16x3": x = xh + xl,
+//     w = wh + wl, three MMAs per K step (xh*wh + xh*wl + xl*wh) into the same TMEM accumulator, which
+//     keeps ~16 mantissa bits (needed for the 1e-3 inference parity bar).
+//   * epilogue: tcgen05.ld 32 lanes x 32 columns per warp, + bias, activation, dtype convert, NHWC store.
+//
+// Weight gradient (conv_wgrad_kernel):  dW[128 (tap,ci), BN co] += X^T[128, 64 pixels] * GY[64 pixels, BN]
+//   * both operands are MN-major here (the pixel axis is the reduction), same gathered smem image.
+//   * split over the pixel axis across CTAs, fp32 red.add into dW.
+#include <cuda.h>
+
+#include <type_traits>
+
+#include "conv_geom.cuh"
+
+namespace fgc {
+int num_sms();
+
+// ------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor bit layout, version 1, SWIZZLE_128B = 2)
+// K-major: 8-row x 128-byte atoms, atoms along M/N every `sbo` bytes.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// MN-major: 64-element (128-byte) runs along M/N, 8 K-rows per atom (1024 B); 64-wide M/N blocks every `lbo`
+// bytes, K atoms every `sbo` bytes.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor, kind::f16: D fp32, A/B bf16
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// operand staging: gather `ROWS` pixel rows x 64 channels into a swizzled [ROWS][128 B] bf16 block
+// ------------------------------------------------------------------------------------------------------
+constexpr int kProducers = 128;
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  float ar = a - __bfloat162float(ah), br = b - __bfloat162float(bh);
+  __nv_bfloat162 h;
+  h.x = ah; h.y = bh;
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = pack_bf16x2(ar, br);
+}
+
+#define PIX_INVALID 0xFFFFFFFFu
+__device__ __forceinline__ uint32_t pix_pack(long long m, const ConvGeom& g) {
+  if (m >= g.M) return PIX_INVALID;
+  int ow = (int)(m % g.OW);
+  long long t = m / g.OW;
+  int oh = (int)(t % g.OH);
+  uint32_t n = (uint32_t)(t / g.OH);
+  return (n << (g.ow_bits + g.oh_bits)) | ((uint32_t)oh << g.ow_bits) | (uint32_t)ow;
+}
+struct PixDec { int owb, ohb; uint32_t owm, ohm; };
+__device__ __forceinline__ PixDec pix_dec(const ConvGeom& g) {
+  PixDec d;
+  d.owb = g.ow_bits; d.ohb = g.oh_bits;
+  d.owm = (1u << g.ow_bits) - 1u; d.ohm = (1u << g.oh_bits) - 1u;
+  return d;
+}
+
+template <typename SrcT> struct Stage;
+template <> struct Stage<__nv_bfloat16> {
+  static constexpr int CPR = 8;      // 16-byte chunks per 64-channel row
+  static constexpr int EPC = 8;      // elements per chunk
+  static constexpr bool X3 = false;
+};
+template <> struct Stage<float> {
+  static constexpr int CPR = 16;
+  static constexpr int EPC = 4;
+  static constexpr bool X3 = true;
+};
+
+// "big" slab: channels [c0, c0+64) of one source at tap offset (dh, dw).  tid in [0,128).
+template <typename SrcT, int ROWS>
+__device__ __forceinline__ void gather_big(uint8_t* s_hi, uint8_t* s_lo, const SrcT* __restrict__ src, int C, int c0, int ups,
+                                           int H, int W, int stride, int dh, int dw, const uint32_t* pix, const PixDec pd, int tid) {
+  using S = Stage<SrcT>;
+  constexpr int RPP = kProducers / S::CPR;   // rows per pass
+  constexpr int NPASS = ROWS / RPP;
+  const int j = tid % S::CPR, g = tid / S::CPR;
+  const int cj = c0 + j * S::EPC;
+  const bool cvalid = cj < C;
+  const int Hs = ups ? (H >> 1) : H, Ws = ups ? (W >> 1) : W;
+  uint4 v[NPASS];
+#pragma unroll
+  for (int i = 0; i < NPASS; i++) {
+    uint32_t p = pix[i];
+    int n = (int)((p >> pd.owb) >> pd.ohb), oh = (int)((p >> pd.owb) & pd.ohm), ow = (int)(p & pd.owm);
+    int ih = oh * stride + dh, iw = ow * stride + dw;
+    bool ok = cvalid && p != PIX_INVALID && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
+    if (ups) { ih >>= 1; iw >>= 1; }
+    v[i] = make_uint4(0, 0, 0, 0);
+    if (ok) v[i] = __ldg(reinterpret_cast<const uint4*>(src + (((long long)n * Hs + ih) * Ws + iw) * C + cj));
+  }
+#pragma unroll
+  for (int i = 0; i < NPASS; i++) {
+    int r = g + RPP * i;
+    if constexpr (!S::X3) {
+      *reinterpret_cast<uint4*>(s_hi + r * 128 + ((j ^ (r & 7)) << 4)) = v[i];
+    } else {
+      uint2 hi, lo;
+      split2(__uint_as_float(v[i].x), __uint_as_float(v[i].y), hi.x, lo.x);
+      split2(__uint_as_float(v[i].z), __uint_as_float(v[i].w), hi.y, lo.y);
+      int off = r * 128 + (((j >> 1) ^ (r & 7)) << 4) + ((j & 1) << 3);
+      *reinterpret_cast<uint2*>(s_hi + off) = hi;
+      *reinterpret_cast<uint2*>(s_lo + off) = lo;
+    }
+  }
+}
+
+// "small" slab: flattened q = tap*C + c for q in [q0, q0+64) (zero beyond k*k*C).  128/ROWS threads per row.
+template <typename SrcT, int ROWS>
+__device__ __forceinline__ void gather_small(uint8_t* s_hi, uint8_t* s_lo, const SrcT* __restrict__ src, int C, int q0, int ups,
+                                             int H, int W, int stride, int k, int pad_t, int pad_l, int sign,
+                                             const uint32_t* pixrow, const PixDec pd, int tid) {
+  using S = Stage<SrcT>;
+  constexpr int TPR = kProducers / ROWS;     // threads per row (1 or 2)
+  constexpr int KPT = 64 / TPR;              // k elements per thread
+  const int r = tid % ROWS, part = tid / ROWS;
+  const uint32_t p = pixrow[0];
+  const int n = (int)((p >> pd.owb) >> pd.ohb), oh = (int)((p >> pd.owb) & pd.ohm), ow = (int)(p & pd.owm);
+  const int Hs = ups ? (H >> 1) : H, Ws = ups ? (W >> 1) : W;
+  const int qmax = k * k * C;
+  int q = q0 + part * KPT;
+  int tap = q / C, c = q % C;
+  int kh = tap / k, kw = tap % k;
+#pragma unroll 1
+  for (int ch = 0; ch < KPT / 8; ch++) {
+    float e[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      float val = 0.f;
+      if (q < qmax && p != PIX_INVALID) {
+        int ih = oh * stride + sign * (kh - pad_t), iw = ow * stride + sign * (kw - pad_l);
+        if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
+          if (ups) { ih >>= 1; iw >>= 1; }
+          val = ld1<SrcT>(src + (((long long)n * Hs + ih) * Ws + iw) * C + c);
+        }
+      }
+      e[t] = val;
+      q++; c++;
+      if (c == C) { c = 0; kw++; if (kw == k) { kw = 0; kh++; } }
+    }
+    int chunk = part * (KPT / 8) + ch;
+    int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+    uint4 hi, lo;
+    if constexpr (!S::X3) {
+      hi = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+      *reinterpret_cast<uint4*>(s_hi + off) = hi;
+    } else {
+      split2(e[0], e[1], hi.x, lo.x); split2(e[2], e[3], hi.y, lo.y);
+      split2(e[4], e[5], hi.z, lo.z); split2(e[6], e[7], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(s_hi + off) = hi;
+      *reinterpret_cast<uint4*>(s_lo + off) = lo;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// weight packing: fp32 HWIO -> bf16 (hi [, lo]) [slab][Npad][64], 16-byte chunks pre-swizzled by (row & 7)
+//   value(slab, n, kk) = w[tap*tap_stride + cglob*k_stride + n*n_stride + base]   (0 outside)
+// ------------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(ConvGeom g, const float* __restrict__ w, long long tap_stride, long long k_stride,
+                                    long long n_stride, long long base, int Nvalid, int Npad, int x3,
+                                    __nv_bfloat16* __restrict__ out) {
+  long long total = (long long)g.nslabs * Npad * 8;
+  long long plane = (long long)g.nslabs * Npad * 64;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int chunk = (int)(i & 7);
+    long long t = i >> 3;
+    int n = (int)(t % Npad);
+    int slab = (int)(t / Npad);
+    SlabInfo si = decode_slab(g, slab);
+    float e[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      int tap, cg;
+      e[q] = 0.f;
+      if (n < Nvalid && slab_elem(g, si, chunk * 8 + q, &tap, &cg)) e[q] = w[tap * tap_stride + cg * k_stride + n * n_stride + base];
+    }
+    long long off = ((long long)slab * Npad + n) * 64 + ((chunk ^ (n & 7)) << 3);
+    uint4 hi, lo;
+    if (x3) {
+      split2(e[0], e[1], hi.x, lo.x); split2(e[2], e[3], hi.y, lo.y);
+      split2(e[4], e[5], hi.z, lo.z); split2(e[6], e[7], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(out + off) = hi;
+      *reinterpret_cast<uint4*>(out + plane + off) = lo;
+    } else {
+      hi = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+      *reinterpret_cast<uint4*>(out + off) = hi;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// forward / dgrad implicit GEMM
+// ------------------------------------------------------------------------------------------------------
+struct IgemmArgs {
+  ConvGeom g;
+  const __nv_bfloat16* wp;   // packed weights, hi plane then lo plane
+  long long wp_plane;        // elements per plane
+  int Npad;                  // packed rows per slab
+  int Nout;                  // valid output channels
+  const float* bias;         // [Nout] or null
+  int act;
+  int accumulate;
+  void* y;                   // [M, Nout]
+  int y_dtype;
+  int vec_ok;                // y is 16-byte aligned
+  int stages;
+};
+
+__device__ __forceinline__ float epi_act(float v, int act) {
+  switch (act) {
+    case FGC_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
+    case FGC_ACT_TANH: return tanhf(v);
+    case FGC_ACT_MIU: return miu_relu(v);
+    default: return v;
+  }
+}
+
+template <typename SrcT, int BN>
+__global__ void __launch_bounds__(192) conv_igemm_kernel(const __grid_constant__ IgemmArgs a) {
+  using S = Stage<SrcT>;
+  constexpr int A_BYTES = 128 * 128;                 // one plane of the A tile
+  constexpr int B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = (S::X3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stages = a.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);   // full[stages], empty[stages], accum
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const ConvGeom& g = a.g;
+  const long long m0 = (long long)blockIdx.x * 128;
+  const int n0 = blockIdx.y * BN;
+  const int nslabs = g.nslabs;
+  const PixDec pd = pix_dec(g);
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; s++) {
+      mbar_init(smem_u32(&bars[s]), kProducers + 1);   // 128 producer arrivals + the bulk-copy issuer (with tx bytes)
+      mbar_init(smem_u32(&bars[stages + s]), 1);       // released by tcgen05.commit
+    }
+    mbar_init(smem_u32(&bars[2 * stages]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== A producers (then epilogue) =====================
+    constexpr int RPP = kProducers / S::CPR, NPASS = 128 / RPP;
+    uint32_t pix[NPASS];
+    {
+      const int gq = tid / S::CPR;
+#pragma unroll
+      for (int i = 0; i < NPASS; i++) pix[i] = pix_pack(m0 + gq + RPP * i, g);
+    }
+    const uint32_t pixrow = pix_pack(m0 + tid, g);
+    for (int slab = 0; slab < nslabs; slab++) {
+      const int st = slab % stages;
+      const uint32_t ph = (slab / stages) & 1;
+      mbar_wait(smem_u32(&bars[stages + st]), ph ^ 1);
+      uint8_t* sa_hi = smem + (size_t)st * STAGE_BYTES;
+      uint8_t* sa_lo = sa_hi + A_BYTES;
+      SlabInfo si = decode_slab(g, slab);
+      const SrcT* src = reinterpret_cast<const SrcT*>(g.src[si.s]);
+      if (si.big) {
+        int kh = si.tap / g.k, kw = si.tap % g.k;
+        gather_big<SrcT, 128>(sa_hi, sa_lo, src, g.C[si.s], si.c0, g.ups[si.s], g.H, g.W, g.stride, g.sign * (kh - g.pad_t),
+                              g.sign * (kw - g.pad_l), pix, pd, tid);
+      } else {
+        gather_small<SrcT, 128>(sa_hi, sa_lo, src, g.C[si.s], si.q0, g.ups[si.s], g.H, g.W, g.stride, g.k, g.pad_t, g.pad_l,
+                                g.sign, &pixrow, pd, tid);
+      }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&bars[st]));
+    }
+    // ===================== epilogue =====================
+    mbar_wait(smem_u32(&bars[2 * stages]), 0);
+    tc_fence_after();
+    const long long m = m0 + warp * 32 + lane;
+    const bool mvalid = m < g.M;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      if (!mvalid) continue;
+      const int nb = n0 + c0;
+      if (nb >= a.Nout) continue;
+      float v[32];
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        float t = __uint_as_float(r[q]);
+        int n = nb + q;
+        if (a.bias && n < a.Nout) t += __ldg(a.bias + n);
+        v[q] = epi_act(t, a.act);
+      }
+      const int nrem = a.Nout - nb;      // > 0
+      if (a.y_dtype == FGC_F32) {
+        float* yp = reinterpret_cast<float*>(a.y) + m * a.Nout + nb;
+        if (a.vec_ok && nrem >= 32 && (a.Nout & 3) == 0) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+            if (a.accumulate) {
+              float4 p = *reinterpret_cast<float4*>(yp + q);
+              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+            }
+            *reinterpret_cast<float4*>(yp + q) = o;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; q++)
+            if (q < nrem) yp[q] = a.accumulate ? yp[q] + v[q] : v[q];
+        }
+      } else {
+        __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.Nout + nb;
+        if (a.vec_ok && nrem >= 32 && (a.Nout & 7) == 0) {
+#pragma unroll
+          for (int q = 0; q < 32; q += 8) {
+            if (a.accumulate) {
+              uint4 p = *reinterpret_cast<uint4*>(yp + q);
+              const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&p);
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                float2 f = __bfloat1622float2(pp[e]);
+                v[q + 2 * e] += f.x; v[q + 2 * e + 1] += f.y;
+              }
+            }
+            uint4 o = make_uint4(pack_bf16x2(v[q], v[q + 1]), pack_bf16x2(v[q + 2], v[q + 3]), pack_bf16x2(v[q + 4], v[q + 5]),
+                                 pack_bf16x2(v[q + 6], v[q + 7]));
+            *reinterpret_cast<uint4*>(yp + q) = o;
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; q++)
+            if (q < nrem) yp[q] = __float2bfloat16_rn(a.accumulate ? __bfloat162float(yp[q]) + v[q] : v[q]);
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    for (int slab = 0; slab < nslabs; slab++) {
+      const int st = slab % stages;
+      const uint32_t ph = (slab / stages) & 1;
+      mbar_wait(smem_u32(&bars[st]), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa_hi = smem_u32(smem + (size_t)st * STAGE_BYTES);
+        const uint32_t sa_lo = sa_hi + A_BYTES;
+        const uint32_t sb_hi = sa_hi + (S::X3 ? 2 : 1) * A_BYTES;
+        const uint32_t sb_lo = sb_hi + B_BYTES;
+        const uint64_t da_hi = desc_kmajor(sa_hi, 1024), db_hi = desc_kmajor(sb_hi, 1024);
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          const uint32_t acc = (slab > 0 || kk > 0) ? 1u : 0u;
+          umma_bf16(tmem_base, da_hi + 2 * kk, db_hi + 2 * kk, IDESC, acc);
+          if constexpr (S::X3) {
+            const uint64_t da_lo = desc_kmajor(sa_lo, 1024), db_lo = desc_kmajor(sb_lo, 1024);
+            umma_bf16(tmem_base, da_hi + 2 * kk, db_lo + 2 * kk, IDESC, 1u);
+            umma_bf16(tmem_base, da_lo + 2 * kk, db_hi + 2 * kk, IDESC, 1u);
+          }
+        }
+        umma_commit(smem_u32(&bars[stages + st]));
+        if (slab == nslabs - 1) umma_commit(smem_u32(&bars[2 * stages]));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== B loader: one bulk copy per slab (and plane) =====================
+    if (lane == 0) {
+      for (int slab = 0; slab < nslabs; slab++) {
+        const int st = slab % stages;
+        const uint32_t ph = (slab / stages) & 1;
+        mbar_wait(smem_u32(&bars[stages + st]), ph ^ 1);
+        const uint32_t sb_hi = smem_u32(smem + (size_t)st * STAGE_BYTES) + (S::X3 ? 2 : 1) * A_BYTES;
+        const uint32_t bar = smem_u32(&bars[st]);
+        const __nv_bfloat16* wsrc = a.wp + ((long long)slab * a.Npad + n0) * 64;
+        mbar_arrive_expect_tx(bar, (S::X3 ? 2 : 1) * B_BYTES);
+        bulk_g2s(sb_hi, wsrc, B_BYTES, bar);
+        if constexpr (S::X3) bulk_g2s(sb_hi + B_BYTES, wsrc + a.wp_plane, B_BYTES, bar);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  ConvGeom g;
+  const void* gy;     // [M, Cout]
+  int Cout;
+  int Cin_total;
+  float* dw;          // HWIO fp32, accumulated with red.add
+  int kslabs;         // ceil(M/64)
+  int kslabs_per_cta;
+  int stages;
+};
+
+template <typename SrcT, int BN>
+__global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+  using S = Stage<SrcT>;
+  constexpr int NBB = (BN + 63) / 64;                // 64-wide gy blocks
+  constexpr int BLK = 64 * 128;                      // bytes of one [64 rows][128 B] block
+  constexpr int A_BYTES = 2 * BLK, B_BYTES = NBB * BLK;
+  constexpr int STAGE_BYTES = (S::X3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t IDESC = make_idesc(128, BN, 1, 1);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stages = a.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const ConvGeom& g = a.g;
+  const int mt = blockIdx.x;                         // pair of slabs (2*mt, 2*mt+1) = 128 rows of dW
+  const int n0 = blockIdx.y * BN;
+  const int ks0 = blockIdx.z * a.kslabs_per_cta;
+  const int ks1 = min(ks0 + a.kslabs_per_cta, a.kslabs);
+  const int niter = ks1 - ks0;
+  const PixDec pd = pix_dec(g);
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; s++) {
+      mbar_init(smem_u32(&bars[s]), kProducers);
+      mbar_init(smem_u32(&bars[stages + s]), 1);
+    }
+    mbar_init(smem_u32(&bars[2 * stages]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    constexpr int RPP = kProducers / S::CPR, NPASS = 64 / RPP;
+    SlabInfo si[2];
+    bool have[2];
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      have[b] = 2 * mt + b < g.nslabs;
+      si[b] = decode_slab(g, have[b] ? 2 * mt + b : 0);
+    }
+    for (int it = 0; it < niter; it++) {
+      const int st = it % stages;
+      const uint32_t ph = (it / stages) & 1;
+      mbar_wait(smem_u32(&bars[stages + st]), ph ^ 1);
+      uint8_t* sa_hi = smem + (size_t)st * STAGE_BYTES;
+      uint8_t* sa_lo = sa_hi + A_BYTES;
+      uint8_t* sb_hi = sa_hi + (S::X3 ? 2 : 1) * A_BYTES;
+      uint8_t* sb_lo = sb_hi + B_BYTES;
+      const long long mbase = (long long)(ks0 + it) * 64;
+      uint32_t pix[NPASS];
+      {
+        const int gq = tid / S::CPR;
+#pragma unroll
+        for (int i = 0; i < NPASS; i++) pix[i] = pix_pack(mbase + gq + RPP * i, g);
+      }
+      const uint32_t pixrow = pix_pack(mbase + (tid & 63), g);
+      // A': x rows (tap-shifted), two 64-wide blocks of the flattened (tap, ci) axis
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        uint8_t* dh_ = sa_hi + b * BLK;
+        uint8_t* dl_ = sa_lo + b * BLK;
+        if (!have[b]) {
+          // zero block
+          for (int i = tid; i < BLK / 16; i += kProducers) {
+            reinterpret_cast<uint4*>(dh_)[i] = make_uint4(0, 0, 0, 0);
+            if constexpr (S::X3) reinterpret_cast<uint4*>(dl_)[i] = make_uint4(0, 0, 0, 0);
+          }
+          continue;
+        }
+        const SrcT* src = reinterpret_cast<const SrcT*>(g.src[si[b].s]);
+        if (si[b].big) {
+          int kh = si[b].tap / g.k, kw = si[b].tap % g.k;
+          gather_big<SrcT, 64>(dh_, dl_, src, g.C[si[b].s], si[b].c0, g.ups[si[b].s], g.H, g.W, g.stride, kh - g.pad_t,
+                               kw - g.pad_l, pix, pd, tid);
+        } else {
+          gather_small<SrcT, 64>(dh_, dl_, src, g.C[si[b].s], si[b].q0, g.ups[si[b].s], g.H, g.W, g.stride, g.k, g.pad_t,
+                                 g.pad_l, 1, &pixrow, pd, tid);
+        }
+      }
+      // B': gy rows, NBB blocks of 64 output channels
+#pragma unroll
+      for (int b = 0; b < NBB; b++) {
+        int c0 = n0 + b * 64;
+        if ((a.Cout & 7) == 0 && a.Cout >= 8)
+          gather_big<SrcT, 64>(sb_hi + b * BLK, sb_lo + b * BLK, reinterpret_cast<const SrcT*>(a.gy), a.Cout, c0, 0, g.OH, g.OW, 1,
+                               0, 0, pix, pd, tid);
+        else  // odd channel counts (1, 3, 25): flattened path with k=1 semantics
+          gather_small<SrcT, 64>(sb_hi + b * BLK, sb_lo + b * BLK, reinterpret_cast<const SrcT*>(a.gy), a.Cout, c0, 0, g.OH, g.OW,
+                                 1, 1, 0, 0, 1, &pixrow, pd, tid);
+      }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&bars[st]));
+    }
+    // epilogue: lane = row of dW (flattened (tap, ci)), columns = co
+    if (niter > 0) {
+      mbar_wait(smem_u32(&bars[2 * stages]), 0);
+      tc_fence_after();
+      const int row = warp * 32 + lane;
+      const int b = row >> 6, kk = row & 63;
+      int tap = 0, cg = 0;
+      bool rvalid = have[b] && slab_elem(g, si[b], kk, &tap, &cg);
+      float* dwrow = a.dw + ((long long)tap * a.Cin_total + cg) * a.Cout;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+        if (!rvalid) continue;
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+          int n = n0 + c0 + q;
+          if (n < a.Cout) atomicAdd(dwrow + n, __uint_as_float(r[q]));
+        }
+      }
+      tc_fence_before();
+    }
+  } else if (warp == 4) {
+    for (int it = 0; it < niter; it++) {
+      const int st = it % stages;
+      const uint32_t ph = (it / stages) & 1;
+      mbar_wait(smem_u32(&bars[st]), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa_hi = smem_u32(smem + (size_t)st * STAGE_BYTES);
+        const uint32_t sa_lo = sa_hi + A_BYTES;
+        const uint32_t sb_hi = sa_hi + (S::X3 ? 2 : 1) * A_BYTES;
+        const uint32_t sb_lo = sb_hi + B_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {      // 16 pixel rows per MMA = 2 atoms of 1024 B
+          const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+          const uint64_t da_hi = desc_mnmajor(sa_hi + kk * 2048, BLK, 1024), db_hi = desc_mnmajor(sb_hi + kk * 2048, BLK, 1024);
+          umma_bf16(tmem_base, da_hi, db_hi, IDESC, acc);
+          if constexpr (S::X3) {
+            const uint64_t da_lo = desc_mnmajor(sa_lo + kk * 2048, BLK, 1024), db_lo = desc_mnmajor(sb_lo + kk * 2048, BLK, 1024);
+            umma_bf16(tmem_base, da_hi, db_lo, IDESC, 1u);
+            umma_bf16(tmem_base, da_lo, db_hi, IDESC, 1u);
+          }
+        }
+        umma_commit(smem_u32(&bars[stages + st]));
+        if (it == niter - 1) umma_commit(smem_u32(&bars[2 * stages]));
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------------
+static int pick_bn(int nout) {
+  if (nout <= 16) return 16;
+  if (nout <= 32) return 32;
+  if (nout <= 64) return 64;
+  return 128;
+}
+
+size_t conv_ws_bytes(const ConvGeom& g, int nout, int x3) {
+  int bn = pick_bn(nout);
+  int npad = ((nout + bn - 1) / bn) * bn;
+  return (size_t)g.nslabs * npad * 64 * 2 * (x3 ? 2 : 1);
+}
+
+template <typename SrcT, int BN>
+static int launch_igemm(IgemmArgs& a, cudaStream_t s) {
+  using S = Stage<SrcT>;
+  constexpr int STAGE_BYTES = (S::X3 ? 2 : 1) * (128 * 128 + BN * 128);
+  int budget = S::X3 ? 200 * 1024 : 100 * 1024;
+  int stages = budget / STAGE_BYTES;
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  if (stages > a.g.nslabs) stages = a.g.nslabs < 1 ? 1 : a.g.nslabs;
+  a.stages = stages;
+  size_t smem = (size_t)stages * STAGE_BYTES + (2 * stages + 1) * 8 + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_igemm_kernel<SrcT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((a.g.M + 127) / 128), (unsigned)(a.Npad / BN));
+  conv_igemm_kernel<SrcT, BN><<<grid, 192, smem, s>>>(a);
+  count_launch();
+  return check_launch("conv_igemm");
+}
+
+template <typename SrcT>
+static int launch_igemm_bn(IgemmArgs& a, int bn, cudaStream_t s) {
+  switch (bn) {
+    case 16: return launch_igemm<SrcT, 16>(a, s);
+    case 32: return launch_igemm<SrcT, 32>(a, s);
+    case 64: return launch_igemm<SrcT, 64>(a, s);
+    default: return launch_igemm<SrcT, 128>(a, s);
+  }
+}
+
+// run y[M, nout] (=|+=) act(implicit_gemm(g) + bias) with weights w addressed as described in pack_weights_kernel
+int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride, long long n_stride,
+                   long long base, int nout, const float* bias, int act, int accumulate, void* y, int y_dtype, void* ws,
+                   cudaStream_t s) {
+  FGC_REQUIRE(geom_fits(g), "conv: tensor too large for pixel packing");
+  FGC_REQUIRE(ws != nullptr, "conv: workspace required");
+  FGC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "conv: workspace must be 16-byte aligned");
+  for (int i = 0; i < g.nsrc; i++)
+    if (g.big[i]) FGC_REQUIRE((reinterpret_cast<uintptr_t>(g.src[i]) & 15) == 0, "conv: source %d not 16-byte aligned", i);
+  const int x3 = src_dtype == FGC_F32;
+  const int bn = pick_bn(nout);
+  const int npad = ((nout + bn - 1) / bn) * bn;
+  {
+    long long total = (long long)g.nslabs * npad * 8;
+    int grid = (int)((total + 255) / 256);
+    if (grid > num_sms() * 8) grid = num_sms() * 8;
+    pack_weights_kernel<<<grid, 256, 0, s>>>(g, w, tap_stride, k_stride, n_stride, base, nout, npad, x3, (__nv_bfloat16*)ws);
+    count_launch();
+  }
+  IgemmArgs a;
+  a.g = g;
+  a.wp = (const __nv_bfloat16*)ws;
+  a.wp_plane = (long long)g.nslabs * npad * 64;
+  a.Npad = npad;
+  a.Nout = nout;
+  a.bias = bias;
+  a.act = act;
+  a.accumulate = accumulate;
+  a.y = y;
+  a.y_dtype = y_dtype;
+  a.vec_ok = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+  a.stages = 0;
+  if (x3) return launch_igemm_bn<float>(a, bn, s);
+  return launch_igemm_bn<__nv_bfloat16>(a, bn, s);
+}
+
+template <typename SrcT, int BN>
+static int launch_wgrad(WgradArgs& a, cudaStream_t s) {
+  using S = Stage<SrcT>;
+  constexpr int NBB = (BN + 63) / 64;
+  constexpr int STAGE_BYTES = (S::X3 ? 2 : 1) * (2 + NBB) * 64 * 128;
+  int budget = S::X3 ? 200 * 1024 : 100 * 1024;
+  int stages = budget / STAGE_BYTES;
+  if (stages > 6) stages = 6;
+  if (stages < 2) stages = 2;
+  a.stages = stages;
+  size_t smem = (size_t)stages * STAGE_BYTES + (2 * stages + 1) * 8 + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_wgrad_kernel<SrcT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  int mtiles = (a.g.nslabs + 1) / 2;
+  int ntiles = (a.Cout + BN - 1) / BN;
+  a.kslabs = (int)((a.g.M + 63) / 64);
+  long long want = (long long)num_sms() * 4;
+  int splits = (int)((want + (long long)mtiles * ntiles - 1) / ((long long)mtiles * ntiles));
+  if (splits < 1) splits = 1;
+  if (splits > a.kslabs) splits = a.kslabs;
+  a.kslabs_per_cta = (a.kslabs + splits - 1) / splits;
+  splits = (a.kslabs + a.kslabs_per_cta - 1) / a.kslabs_per_cta;
+  dim3 grid(mtiles, ntiles, splits);
+  conv_wgrad_kernel<SrcT, BN><<<grid, 160, smem, s>>>(a);
+  count_launch();
+  return check_launch("conv_wgrad");
+}
+
+int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s) {
+  FGC_REQUIRE(geom_fits(g), "wgrad: tensor too large for pixel packing");
+  WgradArgs a;
+  a.g = g;
+  a.gy = gy;
+  a.Cout = Cout;
+  a.Cin_total = Cin_total;
+  a.dw = dw;
+  int bn = pick_bn(Cout);
+#define FGC_W(T)                                          \
+  switch (bn) {                                           \
+    case 16: return launch_wgrad<T, 16>(a, s);            \
+    case 32: return launch_wgrad<T, 32>(a, s);            \
+    case 64: return launch_wgrad<T, 64>(a, s);            \
+    default: return launch_wgrad<T, 128>(a, s);           \
+  }
+  if (src_dtype == FGC_F32) { FGC_W(float) } else { FGC_W(__nv_bfloat16) }
+#undef FGC_W
+}
+
+}  // namespace fgc

@@ -1,0 +1,935 @@
+// Normalisation, activation, gating and resampling kernels of libfgcolor (sm_100a).
+//
+// All of these are HBM-bound streaming passes over NHWC activations: one thread owns V=4 consecutive
+// channels (128-bit fp32 / 64-bit bf16 accesses, coalesced along C), grids are sized to a multiple of the
+// SM count and grid-stride over the tensor.  Reductions over H*W or N*H*W are two-stage: per-thread fp32
+// partials over a short run of rows, then one atomic per (thread, channel) into a small global table.
+//
+// Reference call sites (Foreground_Instance_Colorization/obj_lib/):
+//   models_collection.batchnorm :22-34, prelu :56-60, miu_relu :63-65; mru.lrelu :10-12,
+//   min-max gates mru.py:415-416,560-561,568-569; gating mru.py:426,453,572,589; mean_pool mru.py:15-19;
+//   upsample mru.py:22-28.
+#include "common.cuh"
+
+namespace fgc {
+
+static int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+// grid for a grid-stride loop over `work` thread-items with `threads` per block
+int ew_grid(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// order-preserving float <-> uint32 map for atomicMin/atomicMax on floats
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+#define FGC_DISPATCH_TV(dtype, vec_ok, T, V, ...)                                     \
+  do {                                                                                \
+    if ((dtype) == FGC_F32) {                                                         \
+      using T = float;                                                                \
+      if (vec_ok) { constexpr int V = 4; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; } \
+    } else if ((dtype) == FGC_BF16) {                                                 \
+      using T = __nv_bfloat16;                                                        \
+      if (vec_ok) { constexpr int V = 4; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; } \
+    } else {                                                                          \
+      fgc::set_error("bad dtype %d", (int)(dtype));                                   \
+      return FGC_EINVAL;                                                              \
+    }                                                                                 \
+  } while (0)
+
+// ======================================================================================================
+// channel statistics (tf.nn.moments over N,H,W; biased variance)
+// ======================================================================================================
+template <typename T, int V>
+__global__ void chan_stats_kernel(const T* __restrict__ x, long long M, int C, int rows_per_block, double* acc) {
+  const int CV = C / V;
+  const int lanes = blockDim.x / CV;          // row lanes per block
+  const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
+  if (rl >= lanes) return;
+  long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  double s[V], ss[V];
+#pragma unroll
+  for (int i = 0; i < V; i++) s[i] = ss[i] = 0.0;
+  for (long long rb = r0 + rl; rb < r1; rb += (long long)lanes * 16) {
+    float ps[V], pss[V];
+#pragma unroll
+    for (int i = 0; i < V; i++) ps[i] = pss[i] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < 16; j++) {
+      long long r = rb + (long long)j * lanes;
+      if (r < r1) {
+        float a[4];
+        ldv<T, V>(x + r * C + v * V, a);
+#pragma unroll
+        for (int i = 0; i < V; i++) { ps[i] += a[i]; pss[i] += a[i] * a[i]; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; i++) { s[i] += ps[i]; ss[i] += pss[i]; }
+  }
+#pragma unroll
+  for (int i = 0; i < V; i++) {
+    atomicAdd(&acc[v * V + i], s[i]);
+    atomicAdd(&acc[C + v * V + i], ss[i]);
+  }
+}
+__global__ void chan_stats_finalize(const double* acc, long long M, int C, float* stats) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean = acc[c] / (double)M;
+  double var = acc[C + c] / (double)M - mean * mean;
+  if (var < 0) var = 0;
+  stats[c] = (float)mean;
+  stats[C + c] = (float)(1.0 / sqrt(var + 1e-5));
+}
+
+// ======================================================================================================
+// conditional BN apply (+ miu_relu)
+// ======================================================================================================
+template <typename T, int V>
+__global__ void cbn_act_fwd_kernel(const T* __restrict__ x, long long nvec, int HW, int C, const float* __restrict__ stats,
+                                   const float* __restrict__ scale, const float* __restrict__ offset,
+                                   const int32_t* __restrict__ labels, int act, T* __restrict__ y) {
+  const int CV = C / V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long row = i / CV;
+    int n = (int)(row / HW);
+    int l = labels[n];
+    float a[4], o[4];
+    ldv<T, V>(x + i * V, a);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      int c = cv * V + k;
+      float xh = (a[k] - stats[c]) * stats[C + c];
+      float t = xh * scale[l * C + c] + offset[l * C + c];
+      o[k] = act == FGC_ACT_MIU ? miu_relu(t) : t;
+    }
+    stv<T, V>(y + i * V, o);
+  }
+}
+
+// per-(n,c) sums of g and g*xhat where g = gy*act'(y)    -> sums[0][n][c], sums[1][n][c]
+template <typename T, int V>
+__global__ void cbn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restrict__ x, int HW, int C, int rows_per_block,
+                                      const float* __restrict__ stats, const float* __restrict__ scale,
+                                      const float* __restrict__ offset, const int32_t* __restrict__ labels, int act,
+                                      int N, float* sums) {
+  const int CV = C / V;
+  const int lanes = blockDim.x / CV;
+  const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
+  if (rl >= lanes) return;
+  const int n = blockIdx.y;
+  const int l = labels[n];
+  int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  float mean[V], rstd[V], ga[V], be[V], s1[V], s2[V];
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    int c = v * V + k;
+    mean[k] = stats[c]; rstd[k] = stats[C + c];
+    ga[k] = scale[l * C + c]; be[k] = offset[l * C + c];
+    s1[k] = s2[k] = 0.f;
+  }
+  for (int r = r0 + rl; r < r1; r += lanes) {
+    long long off = ((long long)n * HW + r) * C + v * V;
+    float a[4], g[4];
+    ldv<T, V>(x + off, a);
+    ldv<T, V>(gy + off, g);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      float xh = (a[k] - mean[k]) * rstd[k];
+      float gg = g[k];
+      if (act == FGC_ACT_MIU) gg *= miu_relu_grad(xh * ga[k] + be[k]);
+      s1[k] += gg; s2[k] += gg * xh;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    atomicAdd(&sums[(long long)n * C + v * V + k], s1[k]);
+    atomicAdd(&sums[((long long)N + n) * C + v * V + k], s2[k]);
+  }
+}
+// one thread per channel: table gradients (no atomics: a channel is owned by one thread) and batch means
+__global__ void cbn_bwd_finalize_kernel(const float* sums, int N, int C, long long M, const float* __restrict__ scale,
+                                        const int32_t* __restrict__ labels, float* dscale, float* doffset, float* m12) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m1 = 0, m2 = 0;
+  for (int n = 0; n < N; n++) {
+    int l = labels[n];
+    float s1 = sums[(long long)n * C + c], s2 = sums[((long long)N + n) * C + c];
+    doffset[l * C + c] += s1;
+    dscale[l * C + c] += s2;
+    float g = scale[l * C + c];
+    m1 += (double)g * s1; m2 += (double)g * s2;
+  }
+  m12[c] = (float)(m1 / (double)M);
+  m12[C + c] = (float)(m2 / (double)M);
+}
+template <typename T, int V>
+__global__ void cbn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, long long nvec, int HW, int C,
+                                     const float* __restrict__ stats, const float* __restrict__ scale,
+                                     const float* __restrict__ offset, const int32_t* __restrict__ labels, int act,
+                                     const float* __restrict__ m12, T* __restrict__ gx) {
+  const int CV = C / V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long row = i / CV;
+    int n = (int)(row / HW);
+    int l = labels[n];
+    float a[4], g[4], o[4];
+    ldv<T, V>(x + i * V, a);
+    ldv<T, V>(gy + i * V, g);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      int c = cv * V + k;
+      float rstd = stats[C + c];
+      float xh = (a[k] - stats[c]) * rstd;
+      float ga = scale[l * C + c];
+      float gg = g[k];
+      if (act == FGC_ACT_MIU) gg *= miu_relu_grad(xh * ga + offset[l * C + c]);
+      o[k] = rstd * (gg * ga - m12[c] - xh * m12[C + c]);
+    }
+    stv<T, V>(gx + i * V, o);
+  }
+}
+
+// ======================================================================================================
+// PReLU
+// ======================================================================================================
+template <typename T, int V>
+__global__ void prelu_fwd_kernel(const T* __restrict__ x, long long nvec, const float* __restrict__ ap, T* __restrict__ y) {
+  const float a = *ap;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float v[4], o[4];
+    ldv<T, V>(x + i * V, v);
+#pragma unroll
+    for (int k = 0; k < V; k++) o[k] = (a * v[k] >= v[k]) ? a * v[k] : v[k];
+    stv<T, V>(y + i * V, o);
+  }
+}
+template <typename T, int V>
+__global__ void prelu_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, long long nvec,
+                                 const float* __restrict__ ap, float* da, T* __restrict__ gx) {
+  __shared__ float red[32];
+  const float a = *ap;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float v[4], g[4], o[4];
+    ldv<T, V>(x + i * V, v);
+    ldv<T, V>(gy + i * V, g);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      bool m = a * v[k] >= v[k];
+      o[k] = m ? a * g[k] : g[k];
+      if (m) acc += g[k] * v[k];
+    }
+    stv<T, V>(gx + i * V, o);
+  }
+  if (da) {
+    float t = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(da, t);
+  }
+}
+
+// ======================================================================================================
+// min-max gate normalisation
+// ======================================================================================================
+template <typename T, int V>
+__global__ void minmax_reduce_kernel(const T* __restrict__ x, int HW, int C, int rows_per_block, uint32_t* mn_ord,
+                                     uint32_t* mx_ord) {
+  const int CV = C / V;
+  const int lanes = blockDim.x / CV;
+  const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
+  if (rl >= lanes) return;
+  const int n = blockIdx.y;
+  int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  float lo[V], hi[V];
+#pragma unroll
+  for (int k = 0; k < V; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
+  for (int r = r0 + rl; r < r1; r += lanes) {
+    float a[4];
+    ldv<T, V>(x + ((long long)n * HW + r) * C + v * V, a);
+#pragma unroll
+    for (int k = 0; k < V; k++) { lo[k] = fminf(lo[k], a[k]); hi[k] = fmaxf(hi[k], a[k]); }
+  }
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    atomicMin(&mn_ord[(long long)n * C + v * V + k], f2ord(lo[k]));
+    atomicMax(&mx_ord[(long long)n * C + v * V + k], f2ord(hi[k]));
+  }
+}
+template <typename T, int V>
+__global__ void minmax_apply_kernel(const T* __restrict__ x, long long nvec, int HW, int C, const uint32_t* __restrict__ mn_ord,
+                                    const uint32_t* __restrict__ mx_ord, T* __restrict__ gate, float* mn, float* mx) {
+  const int CV = C / V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long row = i / CV;
+    int n = (int)(row / HW);
+    bool first = (row % HW) == 0;
+    float a[4], o[4];
+    ldv<T, V>(x + i * V, a);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      int c = cv * V + k;
+      float lo = ord2f(mn_ord[(long long)n * C + c]), hi = ord2f(mx_ord[(long long)n * C + c]);
+      o[k] = (a[k] - lo) / (hi - lo);
+      if (first) { mn[(long long)n * C + c] = lo; mx[(long long)n * C + c] = hi; }
+    }
+    stv<T, V>(gate + i * V, o);
+  }
+}
+// sums[0] = sum g*(x-mn), sums[1] = sum g, sums[2] = #(x==mx), sums[3] = #(x==mn)   each [N,C]
+template <typename T, int V>
+__global__ void minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
+                                         const float* __restrict__ mn, const float* __restrict__ mx, int N, float* sums) {
+  const int CV = C / V;
+  const int lanes = blockDim.x / CV;
+  const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
+  if (rl >= lanes) return;
+  const int n = blockIdx.y;
+  int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  float lo[V], hi[V], s0[V], s1[V], c0[V], c1[V];
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    lo[k] = mn[(long long)n * C + v * V + k]; hi[k] = mx[(long long)n * C + v * V + k];
+    s0[k] = s1[k] = c0[k] = c1[k] = 0.f;
+  }
+  for (int r = r0 + rl; r < r1; r += lanes) {
+    long long off = ((long long)n * HW + r) * C + v * V;
+    float a[4], g[4];
+    ldv<T, V>(x + off, a);
+    ldv<T, V>(gg + off, g);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      s0[k] += g[k] * (a[k] - lo[k]); s1[k] += g[k];
+      c0[k] += (a[k] == hi[k]) ? 1.f : 0.f;
+      c1[k] += (a[k] == lo[k]) ? 1.f : 0.f;
+    }
+  }
+  long long NC = (long long)N * C;
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    long long o = (long long)n * C + v * V + k;
+    atomicAdd(&sums[o], s0[k]); atomicAdd(&sums[NC + o], s1[k]);
+    if (c0[k] != 0.f) atomicAdd(&sums[2 * NC + o], c0[k]);
+    if (c1[k] != 0.f) atomicAdd(&sums[3 * NC + o], c1[k]);
+  }
+}
+template <typename T, int V>
+__global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __restrict__ x, long long nvec, int HW, int C,
+                                        const float* __restrict__ mn, const float* __restrict__ mx, int N,
+                                        const float* __restrict__ sums, T* __restrict__ gpre) {
+  const int CV = C / V;
+  const long long NC = (long long)N * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long row = i / CV;
+    int n = (int)(row / HW);
+    float a[4], g[4], o[4];
+    ldv<T, V>(x + i * V, a);
+    ldv<T, V>(gg + i * V, g);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      long long q = (long long)n * C + cv * V + k;
+      float lo = mn[q], hi = mx[q], d = hi - lo;
+      float A = sums[q], S = sums[NC + q];
+      float g_mx = -A / (d * d);
+      float g_mn = (A - d * S) / (d * d);
+      float r = g[k] / d;
+      if (a[k] == hi) r += g_mx / sums[2 * NC + q];
+      if (a[k] == lo) r += g_mn / sums[3 * NC + q];
+      o[k] = r * (a[k] > 0.f ? 1.f : 0.2f);
+    }
+    stv<T, V>(gpre + i * V, o);
+  }
+}
+
+// ======================================================================================================
+// activation backward from the output
+// ======================================================================================================
+template <typename T, int V>
+__global__ void act_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, long long nvec, int act, T* __restrict__ gx) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float g[4], v[4], o[4];
+    ldv<T, V>(gy + i * V, g);
+    ldv<T, V>(y + i * V, v);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      if (act == FGC_ACT_TANH) o[k] = g[k] * (1.f - v[k] * v[k]);
+      else {  // miu_relu: x = y - 0.0225/y
+        float xx = v[k] - 0.0225f / v[k];
+        o[k] = g[k] * miu_relu_grad(xx);
+      }
+    }
+    stv<T, V>(gx + i * V, o);
+  }
+}
+
+// ======================================================================================================
+// gating
+// ======================================================================================================
+template <typename T, int V>
+__global__ void gate_fma_fwd_kernel(const T* __restrict__ ht, const T* __restrict__ rg, const T* __restrict__ im, long long nvec,
+                                    T* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float a[4], b[4], c[4], o[4];
+    ldv<T, V>(ht + i * V, a); ldv<T, V>(rg + i * V, b); ldv<T, V>(im + i * V, c);
+#pragma unroll
+    for (int k = 0; k < V; k++) o[k] = a[k] + b[k] * c[k];
+    stv<T, V>(out + i * V, o);
+  }
+}
+template <typename T, int V>
+__global__ void gate_fma_bwd_kernel(const T* __restrict__ g, const T* __restrict__ rg, const T* __restrict__ im, long long nvec,
+                                    T* __restrict__ g_rg, T* __restrict__ g_im) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float a[4], b[4], c[4], o1[4], o2[4];
+    ldv<T, V>(g + i * V, a); ldv<T, V>(rg + i * V, b); ldv<T, V>(im + i * V, c);
+#pragma unroll
+    for (int k = 0; k < V; k++) { o1[k] = a[k] * c[k]; o2[k] = a[k] * b[k]; }
+    stv<T, V>(g_rg + i * V, o1); stv<T, V>(g_im + i * V, o2);
+  }
+}
+
+// index helpers for low-res thread -> 4 full-res positions.  low-res tensor [N,h,w,C], full [N,2h,2w,C]
+struct UpIdx {
+  long long lo;      // element offset in the low-res tensor
+  long long hi[4];   // element offsets in the full-res tensor
+};
+template <int V>
+__device__ __forceinline__ UpIdx up_index(long long i, int h, int w, int C) {
+  const int CV = C / V;
+  int cv = (int)(i % CV);
+  long long p = i / CV;
+  int x = (int)(p % w);
+  long long q = p / w;
+  int y = (int)(q % h);
+  long long n = q / h;
+  UpIdx r;
+  r.lo = i * V;
+  long long base = ((n * (2 * h) + 2 * y) * (2LL * w) + 2 * x) * C + cv * V;
+  r.hi[0] = base; r.hi[1] = base + C; r.hi[2] = base + 2LL * w * C; r.hi[3] = base + 2LL * w * C + C;
+  return r;
+}
+
+template <typename T, int V>
+__global__ void mul_up_fwd_kernel(const T* __restrict__ rg, const T* __restrict__ ht, long long nlow, int h, int w, int C,
+                                  T* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
+    UpIdx u = up_index<V>(i, h, w, C);
+    float a[4];
+    ldv<T, V>(ht + u.lo, a);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float b[4], o[4];
+      ldv<T, V>(rg + u.hi[j], b);
+#pragma unroll
+      for (int k = 0; k < V; k++) o[k] = a[k] * b[k];
+      stv<T, V>(out + u.hi[j], o);
+    }
+  }
+}
+template <typename T, int V>
+__global__ void mul_up_bwd_kernel(const T* __restrict__ g, const T* __restrict__ rg, const T* __restrict__ ht, long long nlow,
+                                  int h, int w, int C, T* __restrict__ g_rg, T* __restrict__ g_ht) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
+    UpIdx u = up_index<V>(i, h, w, C);
+    float a[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+    ldv<T, V>(ht + u.lo, a);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float gg[4], b[4], o[4];
+      ldv<T, V>(g + u.hi[j], gg);
+      ldv<T, V>(rg + u.hi[j], b);
+#pragma unroll
+      for (int k = 0; k < V; k++) { o[k] = gg[k] * a[k]; acc[k] += gg[k] * b[k]; }
+      stv<T, V>(g_rg + u.hi[j], o);
+    }
+    stv<T, V>(g_ht + u.lo, acc);
+  }
+}
+template <typename T, int V>
+__global__ void blend_fwd_kernel(const T* __restrict__ sk, const T* __restrict__ h2, const T* __restrict__ zg, long long nlow,
+                                 int h, int w, int C, T* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
+    UpIdx u = up_index<V>(i, h, w, C);
+    float s[4];
+    ldv<T, V>(sk + u.lo, s);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float a[4], z[4], o[4];
+      ldv<T, V>(h2 + u.hi[j], a);
+      ldv<T, V>(zg + u.hi[j], z);
+#pragma unroll
+      for (int k = 0; k < V; k++) o[k] = s[k] * (1.f - z[k]) + a[k] * z[k];
+      stv<T, V>(out + u.hi[j], o);
+    }
+  }
+}
+template <typename T, int V>
+__global__ void blend_bwd_kernel(const T* __restrict__ g, const T* __restrict__ sk, const T* __restrict__ h2,
+                                 const T* __restrict__ zg, long long nlow, int h, int w, int C, T* __restrict__ g_sk,
+                                 T* __restrict__ g_h2, T* __restrict__ g_zg) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
+    UpIdx u = up_index<V>(i, h, w, C);
+    float s[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+    ldv<T, V>(sk + u.lo, s);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float gg[4], a[4], z[4], o1[4], o2[4];
+      ldv<T, V>(g + u.hi[j], gg);
+      ldv<T, V>(h2 + u.hi[j], a);
+      ldv<T, V>(zg + u.hi[j], z);
+#pragma unroll
+      for (int k = 0; k < V; k++) {
+        acc[k] += gg[k] * (1.f - z[k]);
+        o1[k] = gg[k] * z[k];
+        o2[k] = gg[k] * (a[k] - s[k]);
+      }
+      stv<T, V>(g_h2 + u.hi[j], o1);
+      stv<T, V>(g_zg + u.hi[j], o2);
+    }
+    stv<T, V>(g_sk + u.lo, acc);
+  }
+}
+template <typename T, int V>
+__global__ void addpool_fwd_kernel(const T* __restrict__ a, const T* __restrict__ b, long long nlow, int h, int w, int C,
+                                   T* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
+    UpIdx u = up_index<V>(i, h, w, C);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float p[4];
+      ldv<T, V>(a + u.hi[j], p);
+#pragma unroll
+      for (int k = 0; k < V; k++) acc[k] += p[k];
+      if (b) {
+        ldv<T, V>(b + u.hi[j], p);
+#pragma unroll
+        for (int k = 0; k < V; k++) acc[k] += p[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; k++) acc[k] *= 0.25f;
+    stv<T, V>(out + u.lo, acc);
+  }
+}
+template <typename T, int V>
+__global__ void unpool_bwd_kernel(const T* __restrict__ g, long long nlow, int h, int w, int C, T* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
+    UpIdx u = up_index<V>(i, h, w, C);
+    float a[4];
+    ldv<T, V>(g + u.lo, a);
+#pragma unroll
+    for (int k = 0; k < V; k++) a[k] *= 0.25f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) stv<T, V>(out + u.hi[j], a);
+  }
+}
+// out[N,h,w,C] (+)= sum2x2(g[N,2h,2w,C])   (used by the upsampled-source dgrad)
+template <typename TI, typename TO>
+__global__ void sum2x2_kernel(const TI* __restrict__ g, long long nlow, int h, int w, int C, TO* __restrict__ out, int acc) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
+    UpIdx u = up_index<1>(i, h, w, C);
+    float s = ld1<TI>(g + u.hi[0]) + ld1<TI>(g + u.hi[1]) + ld1<TI>(g + u.hi[2]) + ld1<TI>(g + u.hi[3]);
+    if (acc) s += ld1<TO>(out + u.lo);
+    st1<TO>(out + u.lo, s);
+  }
+}
+
+template <typename TD, typename TS>
+__global__ void axpy_kernel(TD* __restrict__ dst, const TS* __restrict__ src, long long n, float alpha) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    st1<TD>(dst + i, ld1<TD>(dst + i) + alpha * ld1<TS>(src + i));
+}
+template <typename T, int V>
+__global__ void axpy_vec_kernel(T* __restrict__ dst, const T* __restrict__ src, long long nvec, float alpha) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float a[4], b[4];
+    ldv<T, V>(dst + i * V, a);
+    ldv<T, V>(src + i * V, b);
+#pragma unroll
+    for (int k = 0; k < V; k++) a[k] += alpha * b[k];
+    stv<T, V>(dst + i * V, a);
+  }
+}
+
+template <typename T>
+__global__ void spatial_mean_fwd_kernel(const T* __restrict__ x, int HW, int C, T* __restrict__ out) {
+  int n = blockIdx.y;
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int r = 0; r < HW; r++) s += ld1<T>(x + ((long long)n * HW + r) * C + c);
+  st1<T>(out + (long long)n * C + c, s / (float)HW);
+}
+template <typename T>
+__global__ void spatial_mean_bwd_kernel(const T* __restrict__ g, long long total, int HW, int C, T* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long n = i / ((long long)HW * C);
+    st1<T>(out + i, ld1<T>(g + n * C + c) / (float)HW);
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void nchw_to_nhwc_kernel(const TI* __restrict__ x, long long total, int C, int HW, TO* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long p = i / C;
+    int s = (int)(p % HW);
+    long long n = p / HW;
+    st1<TO>(y + i, ld1<TI>(x + (n * C + c) * HW + s));
+  }
+}
+template <typename TI, typename TO>
+__global__ void nhwc_to_nchw_kernel(const TI* __restrict__ x, long long total, int C, int HW, TO* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int s = (int)(i % HW);
+    long long p = i / HW;
+    int c = (int)(p % C);
+    long long n = p / C;
+    st1<TO>(y + i, ld1<TI>(x + (n * HW + s) * C + c));
+  }
+}
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    st1<TO>(y + i, ld1<TI>(x + i));
+}
+
+// choose block / rows-per-block for the per-(n,c) row reductions
+struct RowRed { int threads, V, lanes, rows_per_block, nblk; };
+static RowRed rowred_plan(int C, bool vec, long long rows, long long other_blocks) {
+  RowRed p;
+  p.V = vec ? 4 : 1;
+  int CV = C / p.V;
+  p.threads = 256;
+  if (CV > 256) p.threads = ((CV + 31) / 32) * 32;
+  p.lanes = p.threads / CV;
+  long long target = (long long)num_sms() * 8;                      // blocks wanted overall
+  long long want = target / (other_blocks > 0 ? other_blocks : 1);
+  if (want < 1) want = 1;
+  long long rpb = (rows + want - 1) / want;
+  long long min_rpb = (long long)p.lanes * 8;
+  if (rpb < min_rpb) rpb = min_rpb;
+  if (rpb > rows) rpb = rows;
+  p.rows_per_block = (int)rpb;
+  p.nblk = (int)((rows + rpb - 1) / rpb);
+  return p;
+}
+
+}  // namespace fgc
+
+using namespace fgc;
+
+extern "C" {
+
+int fgc_chan_stats(const void* x, int dtype, long long M, int C, double* acc, float* stats, fgc_stream stream) {
+  FGC_REQUIRE(M > 0 && C > 0 && C <= 1024, "chan_stats: bad shape M=%lld C=%d", M, C);
+  cudaStream_t s = as_stream(stream);
+  cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, s);
+  bool vec = vec4_ok(x, C, dtype);
+  RowRed p = rowred_plan(C, vec, M, 1);
+  FGC_DISPATCH_TV(dtype, vec, T, V,
+                  (chan_stats_kernel<T, V><<<p.nblk, p.threads, 0, s>>>((const T*)x, M, C, p.rows_per_block, acc)));
+  chan_stats_finalize<<<cdiv(C, 128), 128, 0, s>>>(acc, M, C, stats);
+  count_launch(2);
+  FGC_LAUNCH_CHECK("chan_stats");
+  return FGC_OK;
+}
+
+int fgc_cbn_act_fwd(const void* x, int dtype, int N, int HW, int C, const float* stats, const float* scale,
+                    const float* offset, const int32_t* labels, int act, void* y, fgc_stream stream) {
+  FGC_REQUIRE(act == FGC_ACT_NONE || act == FGC_ACT_MIU, "cbn_act_fwd: act %d", act);
+  cudaStream_t s = as_stream(stream);
+  bool vec = vec4_ok(x, C, dtype) && vec4_ok(y, C, dtype);
+  long long n = (long long)N * HW * C;
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    long long nvec = n / V;
+    cbn_act_fwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)x, nvec, HW, C, stats, scale, offset, labels, act, (T*)y);
+  });
+  count_launch();
+  FGC_LAUNCH_CHECK("cbn_act_fwd");
+  return FGC_OK;
+}
+
+int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int C, const float* stats,
+                    const float* scale, const float* offset, const int32_t* labels, int act,
+                    float* dscale, float* doffset, void* gx, float* scratch, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  bool vec = vec4_ok(x, C, dtype) && vec4_ok(gy, C, dtype) && vec4_ok(gx, C, dtype);
+  float* sums = scratch;                       // [2,N,C]
+  float* m12 = scratch + 2LL * N * C;          // [2,C]
+  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, s);
+  RowRed p = rowred_plan(C, vec, HW, N);
+  long long n = (long long)N * HW * C;
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    cbn_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 0, s>>>((const T*)gy, (const T*)x, HW, C, p.rows_per_block, stats,
+                                                                      scale, offset, labels, act, N, sums);
+    cbn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, N, C, (long long)N * HW, scale, labels, dscale, doffset, m12);
+    long long nvec = n / V;
+    cbn_bwd_apply_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)gy, (const T*)x, nvec, HW, C, stats, scale, offset,
+                                                                  labels, act, m12, (T*)gx);
+  });
+  count_launch(3);
+  FGC_LAUNCH_CHECK("cbn_act_bwd");
+  return FGC_OK;
+}
+
+int fgc_prelu_fwd(const void* x, int dtype, long long n, const float* a, void* y, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  bool vec = vec4_ok(x, n, dtype) && vec4_ok(y, n, dtype);
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    long long nvec = n / V;
+    prelu_fwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)x, nvec, a, (T*)y);
+  });
+  count_launch();
+  FGC_LAUNCH_CHECK("prelu_fwd");
+  return FGC_OK;
+}
+int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, const float* a, float* da, void* gx,
+                  fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  bool vec = vec4_ok(x, n, dtype) && vec4_ok(gy, n, dtype) && vec4_ok(gx, n, dtype);
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    long long nvec = n / V;
+    prelu_bwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)gy, (const T*)x, nvec, a, da, (T*)gx);
+  });
+  count_launch();
+  FGC_LAUNCH_CHECK("prelu_bwd");
+  return FGC_OK;
+}
+
+int fgc_minmax_fwd(const void* x, int dtype, int N, int HW, int C, void* gate, float* mn, float* mx,
+                   uint32_t* scratch, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  bool vec = vec4_ok(x, C, dtype) && vec4_ok(gate, C, dtype);
+  uint32_t* mn_ord = scratch;
+  uint32_t* mx_ord = scratch + (long long)N * C;
+  cudaMemsetAsync(mn_ord, 0xFF, sizeof(uint32_t) * N * C, s);
+  cudaMemsetAsync(mx_ord, 0x00, sizeof(uint32_t) * N * C, s);
+  RowRed p = rowred_plan(C, vec, HW, N);
+  long long n = (long long)N * HW * C;
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    minmax_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 0, s>>>((const T*)x, HW, C, p.rows_per_block, mn_ord, mx_ord);
+    long long nvec = n / V;
+    minmax_apply_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)x, nvec, HW, C, mn_ord, mx_ord, (T*)gate, mn, mx);
+  });
+  count_launch(2);
+  FGC_LAUNCH_CHECK("minmax_fwd");
+  return FGC_OK;
+}
+int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, int C, const float* mn,
+                   const float* mx, void* gpre, float* scratch, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  bool vec = vec4_ok(x, C, dtype) && vec4_ok(ggate, C, dtype) && vec4_ok(gpre, C, dtype);
+  cudaMemsetAsync(scratch, 0, sizeof(float) * 4 * N * C, s);
+  RowRed p = rowred_plan(C, vec, HW, N);
+  long long n = (long long)N * HW * C;
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    minmax_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 0, s>>>((const T*)ggate, (const T*)x, HW, C, p.rows_per_block,
+                                                                         mn, mx, N, scratch);
+    long long nvec = n / V;
+    minmax_bwd_apply_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)ggate, (const T*)x, nvec, HW, C, mn, mx, N,
+                                                                     scratch, (T*)gpre);
+  });
+  count_launch(2);
+  FGC_LAUNCH_CHECK("minmax_bwd");
+  return FGC_OK;
+}
+
+int fgc_act_bwd(const void* gy, const void* y, int dtype, long long n, int act, void* gx, fgc_stream stream) {
+  FGC_REQUIRE(act == FGC_ACT_TANH || act == FGC_ACT_MIU, "act_bwd: act %d", act);
+  cudaStream_t s = as_stream(stream);
+  bool vec = vec4_ok(gy, n, dtype) && vec4_ok(y, n, dtype) && vec4_ok(gx, n, dtype);
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    long long nvec = n / V;
+    act_bwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)gy, (const T*)y, nvec, act, (T*)gx);
+  });
+  count_launch();
+  FGC_LAUNCH_CHECK("act_bwd");
+  return FGC_OK;
+}
+
+int fgc_gate_fma_fwd(const void* ht, const void* rg, const void* im, int dtype, long long n, void* out, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  bool vec = vec4_ok(ht, n, dtype) && vec4_ok(rg, n, dtype) && vec4_ok(im, n, dtype) && vec4_ok(out, n, dtype);
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    long long nvec = n / V;
+    gate_fma_fwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)ht, (const T*)rg, (const T*)im, nvec, (T*)out);
+  });
+  count_launch();
+  FGC_LAUNCH_CHECK("gate_fma_fwd");
+  return FGC_OK;
+}
+int fgc_gate_fma_bwd(const void* g, const void* rg, const void* im, int dtype, long long n, void* g_rg, void* g_im,
+                     fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  bool vec = vec4_ok(g, n, dtype) && vec4_ok(rg, n, dtype) && vec4_ok(im, n, dtype) && vec4_ok(g_rg, n, dtype) &&
+             vec4_ok(g_im, n, dtype);
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    long long nvec = n / V;
+    gate_fma_bwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)g, (const T*)rg, (const T*)im, nvec, (T*)g_rg, (T*)g_im);
+  });
+  count_launch();
+  FGC_LAUNCH_CHECK("gate_fma_bwd");
+  return FGC_OK;
+}
+
+#define FGC_UP_LAUNCH(name, kern, ...)                                                          \
+  do {                                                                                          \
+    cudaStream_t s = as_stream(stream);                                                         \
+    long long nlow = (long long)N * h * w * C;                                                  \
+    FGC_DISPATCH_TV(dtype, vec, T, V, {                                                         \
+      long long nv = nlow / V;                                                                  \
+      kern<T, V><<<ew_grid(nv, 256), 256, 0, s>>>(__VA_ARGS__);                                 \
+    });                                                                                         \
+    count_launch();                                                                             \
+    FGC_LAUNCH_CHECK(name);                                                                     \
+    return FGC_OK;                                                                              \
+  } while (0)
+
+int fgc_mul_up_fwd(const void* rg, const void* ht_low, int dtype, int N, int h, int w, int C, void* out, fgc_stream stream) {
+  bool vec = vec4_ok(rg, C, dtype) && vec4_ok(ht_low, C, dtype) && vec4_ok(out, C, dtype);
+  FGC_UP_LAUNCH("mul_up_fwd", mul_up_fwd_kernel, (const T*)rg, (const T*)ht_low, nv, h, w, C, (T*)out);
+}
+int fgc_mul_up_bwd(const void* g, const void* rg, const void* ht_low, int dtype, int N, int h, int w, int C,
+                   void* g_rg, void* g_ht_low, fgc_stream stream) {
+  bool vec = vec4_ok(g, C, dtype) && vec4_ok(rg, C, dtype) && vec4_ok(ht_low, C, dtype) && vec4_ok(g_rg, C, dtype) &&
+             vec4_ok(g_ht_low, C, dtype);
+  FGC_UP_LAUNCH("mul_up_bwd", mul_up_bwd_kernel, (const T*)g, (const T*)rg, (const T*)ht_low, nv, h, w, C, (T*)g_rg, (T*)g_ht_low);
+}
+int fgc_blend_fwd(const void* sk_low, const void* h2, const void* zg, int dtype, int N, int h, int w, int C, void* out,
+                  fgc_stream stream) {
+  bool vec = vec4_ok(sk_low, C, dtype) && vec4_ok(h2, C, dtype) && vec4_ok(zg, C, dtype) && vec4_ok(out, C, dtype);
+  FGC_UP_LAUNCH("blend_fwd", blend_fwd_kernel, (const T*)sk_low, (const T*)h2, (const T*)zg, nv, h, w, C, (T*)out);
+}
+int fgc_blend_bwd(const void* g, const void* sk_low, const void* h2, const void* zg, int dtype, int N, int h, int w, int C,
+                  void* g_sk_low, void* g_h2, void* g_zg, fgc_stream stream) {
+  bool vec = vec4_ok(g, C, dtype) && vec4_ok(sk_low, C, dtype) && vec4_ok(h2, C, dtype) && vec4_ok(zg, C, dtype) &&
+             vec4_ok(g_sk_low, C, dtype) && vec4_ok(g_h2, C, dtype) && vec4_ok(g_zg, C, dtype);
+  FGC_UP_LAUNCH("blend_bwd", blend_bwd_kernel, (const T*)g, (const T*)sk_low, (const T*)h2, (const T*)zg, nv, h, w, C,
+                (T*)g_sk_low, (T*)g_h2, (T*)g_zg);
+}
+int fgc_addpool_fwd(const void* a, const void* b, int dtype, int N, int h, int w, int C, void* out, fgc_stream stream) {
+  bool vec = vec4_ok(a, C, dtype) && (!b || vec4_ok(b, C, dtype)) && vec4_ok(out, C, dtype);
+  FGC_UP_LAUNCH("addpool_fwd", addpool_fwd_kernel, (const T*)a, (const T*)b, nv, h, w, C, (T*)out);
+}
+int fgc_unpool_bwd(const void* g, int dtype, int N, int h, int w, int C, void* out, fgc_stream stream) {
+  bool vec = vec4_ok(g, C, dtype) && vec4_ok(out, C, dtype);
+  FGC_UP_LAUNCH("unpool_bwd", unpool_bwd_kernel, (const T*)g, nv, h, w, C, (T*)out);
+}
+
+int fgc_sum2x2(const void* g, int g_dtype, int N, int h, int w, int C, void* out, int out_dtype, int accumulate,
+               fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  long long nlow = (long long)N * h * w * C;
+  int grid = ew_grid(nlow, 256);
+  if (g_dtype == FGC_F32 && out_dtype == FGC_F32)
+    sum2x2_kernel<float, float><<<grid, 256, 0, s>>>((const float*)g, nlow, h, w, C, (float*)out, accumulate);
+  else if (g_dtype == FGC_F32 && out_dtype == FGC_BF16)
+    sum2x2_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((const float*)g, nlow, h, w, C, (__nv_bfloat16*)out, accumulate);
+  else if (g_dtype == FGC_BF16 && out_dtype == FGC_BF16)
+    sum2x2_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)g, nlow, h, w, C, (__nv_bfloat16*)out, accumulate);
+  else if (g_dtype == FGC_BF16 && out_dtype == FGC_F32)
+    sum2x2_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)g, nlow, h, w, C, (float*)out, accumulate);
+  else { set_error("sum2x2: bad dtypes"); return FGC_EINVAL; }
+  count_launch();
+  FGC_LAUNCH_CHECK("sum2x2");
+  return FGC_OK;
+}
+
+int fgc_axpy(void* dst, const void* src, int dst_dtype, int src_dtype, long long n, float alpha, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  if (dst_dtype == src_dtype && vec4_ok(dst, n, dst_dtype) && vec4_ok(src, n, src_dtype)) {
+    if (dst_dtype == FGC_F32) axpy_vec_kernel<float, 4><<<ew_grid(n / 4, 256), 256, 0, s>>>((float*)dst, (const float*)src, n / 4, alpha);
+    else axpy_vec_kernel<__nv_bfloat16, 4><<<ew_grid(n / 4, 256), 256, 0, s>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, n / 4, alpha);
+  } else {
+    int grid = ew_grid(n, 256);
+    if (dst_dtype == FGC_F32 && src_dtype == FGC_F32) axpy_kernel<float, float><<<grid, 256, 0, s>>>((float*)dst, (const float*)src, n, alpha);
+    else if (dst_dtype == FGC_F32 && src_dtype == FGC_BF16) axpy_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((float*)dst, (const __nv_bfloat16*)src, n, alpha);
+    else if (dst_dtype == FGC_BF16 && src_dtype == FGC_F32) axpy_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((__nv_bfloat16*)dst, (const float*)src, n, alpha);
+    else if (dst_dtype == FGC_BF16 && src_dtype == FGC_BF16) axpy_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, n, alpha);
+    else { set_error("axpy: bad dtypes"); return FGC_EINVAL; }
+  }
+  count_launch();
+  FGC_LAUNCH_CHECK("axpy");
+  return FGC_OK;
+}
+
+int fgc_spatial_mean_fwd(const void* x, int dtype, int N, int HW, int C, void* out, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  FGC_DISPATCH_DTYPE(dtype, T, (spatial_mean_fwd_kernel<T><<<dim3(cdiv(C, 128), N), 128, 0, s>>>((const T*)x, HW, C, (T*)out)));
+  count_launch();
+  FGC_LAUNCH_CHECK("spatial_mean_fwd");
+  return FGC_OK;
+}
+int fgc_spatial_mean_bwd(const void* g, int dtype, int N, int HW, int C, void* out, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  long long total = (long long)N * HW * C;
+  FGC_DISPATCH_DTYPE(dtype, T, (spatial_mean_bwd_kernel<T><<<ew_grid(total, 256), 256, 0, s>>>((const T*)g, total, HW, C, (T*)out)));
+  count_launch();
+  FGC_LAUNCH_CHECK("spatial_mean_bwd");
+  return FGC_OK;
+}
+
+#define FGC_DISPATCH_2(dt_in, dt_out, TI, TO, ...)                                                   \
+  do {                                                                                               \
+    if ((dt_in) == FGC_F32 && (dt_out) == FGC_F32) { using TI = float; using TO = float; __VA_ARGS__; }                 \
+    else if ((dt_in) == FGC_F32 && (dt_out) == FGC_BF16) { using TI = float; using TO = __nv_bfloat16; __VA_ARGS__; }   \
+    else if ((dt_in) == FGC_BF16 && (dt_out) == FGC_F32) { using TI = __nv_bfloat16; using TO = float; __VA_ARGS__; }   \
+    else if ((dt_in) == FGC_BF16 && (dt_out) == FGC_BF16) { using TI = __nv_bfloat16; using TO = __nv_bfloat16; __VA_ARGS__; } \
+    else { fgc::set_error("bad dtypes %d %d", (int)(dt_in), (int)(dt_out)); return FGC_EINVAL; }    \
+  } while (0)
+
+int fgc_nchw_to_nhwc(const void* x, int x_dtype, int N, int C, int HW, void* y, int y_dtype, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  long long total = (long long)N * C * HW;
+  FGC_DISPATCH_2(x_dtype, y_dtype, TI, TO,
+                 (nchw_to_nhwc_kernel<TI, TO><<<ew_grid(total, 256), 256, 0, s>>>((const TI*)x, total, C, HW, (TO*)y)));
+  count_launch();
+  FGC_LAUNCH_CHECK("nchw_to_nhwc");
+  return FGC_OK;
+}
+int fgc_nhwc_to_nchw(const void* x, int x_dtype, int N, int C, int HW, void* y, int y_dtype, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  long long total = (long long)N * C * HW;
+  FGC_DISPATCH_2(x_dtype, y_dtype, TI, TO,
+                 (nhwc_to_nchw_kernel<TI, TO><<<ew_grid(total, 256), 256, 0, s>>>((const TI*)x, total, C, HW, (TO*)y)));
+  count_launch();
+  FGC_LAUNCH_CHECK("nhwc_to_nchw");
+  return FGC_OK;
+}
+int fgc_cast(const void* x, int x_dtype, void* y, int y_dtype, long long n, fgc_stream stream) {
+  cudaStream_t s = as_stream(stream);
+  FGC_DISPATCH_2(x_dtype, y_dtype, TI, TO, (cast_kernel<TI, TO><<<ew_grid(n, 256), 256, 0, s>>>((const TI*)x, (TO*)y, n)));
+  count_launch();
+  FGC_LAUNCH_CHECK("cast");
+  return FGC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,423 @@
+"""CudaOps: the operator contract (ops_base.OpsBase) on hand-written sm_100a kernels behind the C-ABI of
+include/fgcolor.h.  PyTorch tensors are used only as device-buffer containers (allocation + data_ptr);
+every arithmetic op is a call into libfgcolor.so on torch's current CUDA stream.
+
+There is no CPU implementation: constructing CudaOps without a CUDA device or without the built library
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import FgcSrc, check
+from .ops_base import ACT_LRELU, ACT_MIU, ACT_NONE, ACT_TANH, OpsBase
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _same_pad(size, k, stride):
+    out = -(-size // stride)
+    total = max((out - 1) * stride + k - size, 0)
+    return out, total // 2
+
+
+class CudaOps(OpsBase):
+    def __init__(self, device="cuda:0", act_dtype=torch.float32):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CudaOps needs a CUDA device (sm_100a); there is no CPU path in this package")
+        if act_dtype not in _DT:
+            raise ValueError("act_dtype must be float32 (bf16x3 tensor-core mode) or bfloat16 (single-pass bf16)")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.act_dtype = act_dtype
+        torch.cuda.set_device(self.device)
+
+    # ---------------- helpers ----------------
+    @staticmethod
+    def _s():
+        return torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _p(t):
+        if t is None:
+            return None
+        assert t.is_contiguous(), "libfgcolor needs contiguous buffers"
+        return t.data_ptr()
+
+    @staticmethod
+    def _dt(t):
+        return _DT[t.dtype]
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def _f32(self, t):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        return t.data_ptr()
+
+    def launch_count(self):
+        return int(self.lib.fgc_launch_count())
+
+    # ---------------- convolution family ----------------
+    def _srcs(self, srcs):
+        dt = srcs[0][0].dtype
+        arr = (FgcSrc * len(srcs))()
+        H = W = None
+        for i, (t, ups) in enumerate(srcs):
+            assert t.dtype == dt, "all conv sources must share a dtype"
+            assert t.dim() == 4
+            arr[i].ptr = self._p(t)
+            arr[i].C = t.shape[3]
+            arr[i].ups = 1 if ups else 0
+            h, w = (t.shape[1] * 2, t.shape[2] * 2) if ups else (t.shape[1], t.shape[2])
+            assert H is None or (H, W) == (h, w), "conv sources disagree on the spatial size"
+            H, W = h, w
+        return arr, srcs[0][0].shape[0], H, W, _DT[dt]
+
+    def _ws(self, cs, k, nout, dt):
+        arr = (C.c_int * len(cs))(*cs)
+        n = self.lib.fgc_conv2d_ws_bytes(arr, len(cs), k, nout, dt)
+        return self._empty((n,), torch.uint8)
+
+    def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None):
+        arr, N, H, W, dt = self._srcs(srcs)
+        k, cin, cout = w.shape[0], w.shape[2], w.shape[3]
+        OH, pt = _same_pad(H, k, stride)
+        OW, pl = _same_pad(W, k, stride)
+        y = self._empty((N, OH, OW, cout), out_dtype or self.act_dtype)
+        ws = self._ws([t.shape[3] for t, _ in srcs], k, cout, dt)
+        check(self.lib.fgc_conv2d_fwd(arr, len(srcs), dt, N, H, W, self._f32(w), k, cin, cout,
+                                      None if b is None else self._f32(b.reshape(-1)), stride, pt, pl, OH, OW, act,
+                                      self._p(y), self._dt(y), self._p(ws), self._s()), "conv2d_fwd")
+        return y
+
+    def conv_dgrad(self, gy, w, c_off, c_len, *, ups=False, out=None, acc=False, out_dtype=None):
+        N, H, W, cout = gy.shape
+        k, cin = w.shape[0], w.shape[2]
+        assert w.shape[3] == cout
+        oshape = (N, H // 2, W // 2, c_len) if ups else (N, H, W, c_len)
+        if out is None:
+            out = self._empty(oshape, out_dtype or self.act_dtype)
+            acc = False
+        assert tuple(out.shape) == oshape
+        scratch = self._empty((N, H, W, c_len), torch.float32) if ups else None
+        ws = self._ws([cout], k, c_len, self._dt(gy))
+        check(self.lib.fgc_conv2d_dgrad(self._p(gy), self._dt(gy), N, H, W, self._f32(w), k, cin, cout, c_off, c_len,
+                                        1 if ups else 0, 1 if acc else 0, self._p(out), self._dt(out),
+                                        self._p(scratch), self._p(ws), self._s()), "conv2d_dgrad")
+        return out
+
+    def conv_wgrad(self, srcs, gy, dw, db, *, stride=1):
+        arr, N, H, W, dt = self._srcs(srcs)
+        k, cin, cout = dw.shape[0], dw.shape[2], dw.shape[3]
+        OH, pt = _same_pad(H, k, stride)
+        OW, pl = _same_pad(W, k, stride)
+        assert tuple(gy.shape) == (N, OH, OW, cout)
+        check(self.lib.fgc_conv2d_wgrad(arr, len(srcs), dt, N, H, W, self._p(gy), self._dt(gy), k, cin, cout, stride, pt, pl,
+                                        OH, OW, self._f32(dw), None if db is None else self._f32(db.reshape(-1)), self._s()),
+              "conv2d_wgrad")
+
+    # ---------------- normalisation / activations ----------------
+    def chan_stats(self, x):
+        Cc = x.shape[-1]
+        M = x.numel() // Cc
+        acc = self._empty((2 * Cc,), torch.float64)
+        stats = self._empty((2 * Cc,), torch.float32)
+        check(self.lib.fgc_chan_stats(self._p(x), self._dt(x), M, Cc, self._p(acc), self._p(stats), self._s()), "chan_stats")
+        return stats[:Cc], stats[Cc:]
+
+    @staticmethod
+    def _stats(mean, rstd):
+        Cc = mean.numel()
+        if mean.data_ptr() + 4 * Cc == rstd.data_ptr():
+            return mean.data_ptr()
+        return None
+
+    def _stats_ptr(self, mean, rstd, keep):
+        p = self._stats(mean, rstd)
+        if p is None:
+            t = torch.cat([mean.reshape(-1), rstd.reshape(-1)]).contiguous()
+            keep.append(t)
+            p = t.data_ptr()
+        return p
+
+    def cbn_act_fwd(self, x, mean, rstd, scale, offset, labels, act=ACT_MIU):
+        N, H, W, Cc = x.shape
+        y = self._empty(x.shape, x.dtype)
+        keep = []
+        check(self.lib.fgc_cbn_act_fwd(self._p(x), self._dt(x), N, H * W, Cc, self._stats_ptr(mean, rstd, keep), self._f32(scale),
+                                       self._f32(offset), self._p(labels), act, self._p(y), self._s()), "cbn_act_fwd")
+        return y
+
+    def cbn_act_bwd(self, gy, x, mean, rstd, scale, offset, labels, dscale, doffset, act=ACT_MIU):
+        N, H, W, Cc = x.shape
+        assert gy.dtype == x.dtype
+        gx = self._empty(x.shape, x.dtype)
+        scratch = self._empty((2 * N * Cc + 2 * Cc,), torch.float32)
+        keep = []
+        check(self.lib.fgc_cbn_act_bwd(self._p(gy), self._p(x), self._dt(x), N, H * W, Cc, self._stats_ptr(mean, rstd, keep),
+                                       self._f32(scale), self._f32(offset), self._p(labels), act, self._f32(dscale),
+                                       self._f32(doffset), self._p(gx), self._p(scratch), self._s()), "cbn_act_bwd")
+        return gx
+
+    def prelu_fwd(self, x, a):
+        y = self._empty(x.shape, x.dtype)
+        check(self.lib.fgc_prelu_fwd(self._p(x), self._dt(x), x.numel(), self._f32(a), self._p(y), self._s()), "prelu_fwd")
+        return y
+
+    def prelu_bwd(self, gy, x, a, da):
+        assert gy.dtype == x.dtype
+        gx = self._empty(x.shape, x.dtype)
+        check(self.lib.fgc_prelu_bwd(self._p(gy), self._p(x), self._dt(x), x.numel(), self._f32(a),
+                                     None if da is None else self._f32(da), self._p(gx), self._s()), "prelu_bwd")
+        return gx
+
+    def minmax_fwd(self, x):
+        N, H, W, Cc = x.shape
+        gate = self._empty(x.shape, x.dtype)
+        mn = self._empty((N, Cc), torch.float32)
+        mx = self._empty((N, Cc), torch.float32)
+        scratch = self._empty((2 * N * Cc,), torch.int32)
+        check(self.lib.fgc_minmax_fwd(self._p(x), self._dt(x), N, H * W, Cc, self._p(gate), self._p(mn), self._p(mx),
+                                      self._p(scratch), self._s()), "minmax_fwd")
+        return gate, mn, mx
+
+    def minmax_bwd(self, ggate, x, mn, mx):
+        N, H, W, Cc = x.shape
+        assert ggate.dtype == x.dtype
+        gpre = self._empty(x.shape, x.dtype)
+        scratch = self._empty((4 * N * Cc,), torch.float32)
+        check(self.lib.fgc_minmax_bwd(self._p(ggate), self._p(x), self._dt(x), N, H * W, Cc, self._f32(mn), self._f32(mx),
+                                      self._p(gpre), self._p(scratch), self._s()), "minmax_bwd")
+        return gpre
+
+    def act_bwd(self, gy, y, act):
+        assert gy.dtype == y.dtype
+        gx = self._empty(y.shape, y.dtype)
+        check(self.lib.fgc_act_bwd(self._p(gy), self._p(y), self._dt(y), y.numel(), act, self._p(gx), self._s()), "act_bwd")
+        return gx
+
+    # ---------------- gating ----------------
+    def gate_fma_fwd(self, ht, rg, im):
+        out = self._empty(ht.shape, ht.dtype)
+        check(self.lib.fgc_gate_fma_fwd(self._p(ht), self._p(rg), self._p(im), self._dt(ht), ht.numel(), self._p(out), self._s()),
+              "gate_fma_fwd")
+        return out
+
+    def gate_fma_bwd(self, g, rg, im):
+        g_rg = self._empty(g.shape, g.dtype)
+        g_im = self._empty(g.shape, g.dtype)
+        check(self.lib.fgc_gate_fma_bwd(self._p(g), self._p(rg), self._p(im), self._dt(g), g.numel(), self._p(g_rg), self._p(g_im),
+                                        self._s()), "gate_fma_bwd")
+        return g_rg, g_im
+
+    def mul_up_fwd(self, rg, ht_low):
+        N, h, w, Cc = ht_low.shape
+        out = self._empty(rg.shape, rg.dtype)
+        check(self.lib.fgc_mul_up_fwd(self._p(rg), self._p(ht_low), self._dt(rg), N, h, w, Cc, self._p(out), self._s()), "mul_up_fwd")
+        return out
+
+    def mul_up_bwd(self, g, rg, ht_low):
+        N, h, w, Cc = ht_low.shape
+        g_rg = self._empty(g.shape, g.dtype)
+        g_ht = self._empty(ht_low.shape, g.dtype)
+        check(self.lib.fgc_mul_up_bwd(self._p(g), self._p(rg), self._p(ht_low), self._dt(g), N, h, w, Cc, self._p(g_rg),
+                                      self._p(g_ht), self._s()), "mul_up_bwd")
+        return g_rg, g_ht
+
+    def blend_fwd(self, sk_low, h2, zg):
+        N, h, w, Cc = sk_low.shape
+        out = self._empty(h2.shape, h2.dtype)
+        check(self.lib.fgc_blend_fwd(self._p(sk_low), self._p(h2), self._p(zg), self._dt(h2), N, h, w, Cc, self._p(out), self._s()),
+              "blend_fwd")
+        return out
+
+    def blend_bwd(self, g, sk_low, h2, zg):
+        N, h, w, Cc = sk_low.shape
+        g_sk = self._empty(sk_low.shape, g.dtype)
+        g_h2 = self._empty(g.shape, g.dtype)
+        g_zg = self._empty(g.shape, g.dtype)
+        check(self.lib.fgc_blend_bwd(self._p(g), self._p(sk_low), self._p(h2), self._p(zg), self._dt(g), N, h, w, Cc,
+                                     self._p(g_sk), self._p(g_h2), self._p(g_zg), self._s()), "blend_bwd")
+        return g_sk, g_h2, g_zg
+
+    def addpool_fwd(self, a, b):
+        N, H, W, Cc = a.shape
+        out = self._empty((N, H // 2, W // 2, Cc), a.dtype)
+        check(self.lib.fgc_addpool_fwd(self._p(a), self._p(b), self._dt(a), N, H // 2, W // 2, Cc, self._p(out), self._s()),
+              "addpool_fwd")
+        return out
+
+    def meanpool_fwd(self, x):
+        return self.addpool_fwd(x, None)
+
+    def unpool_bwd(self, g):
+        N, h, w, Cc = g.shape
+        out = self._empty((N, 2 * h, 2 * w, Cc), g.dtype)
+        check(self.lib.fgc_unpool_bwd(self._p(g), self._dt(g), N, h, w, Cc, self._p(out), self._s()), "unpool_bwd")
+        return out
+
+    def zeros_f32(self, shape):
+        return torch.zeros(shape, dtype=torch.float32, device=self.device)
+
+    def add_(self, dst, src):
+        assert dst.numel() == src.numel()
+        check(self.lib.fgc_axpy(self._p(dst), self._p(src), self._dt(dst), self._dt(src), dst.numel(), 1.0, self._s()), "axpy")
+        return dst
+
+    def spatial_mean_fwd(self, x):
+        N, H, W, Cc = x.shape
+        out = self._empty((N, 1, 1, Cc), x.dtype)
+        check(self.lib.fgc_spatial_mean_fwd(self._p(x), self._dt(x), N, H * W, Cc, self._p(out), self._s()), "spatial_mean_fwd")
+        return out
+
+    def spatial_mean_bwd(self, g, H, W):
+        N, Cc = g.shape[0], g.shape[3]
+        out = self._empty((N, H, W, Cc), g.dtype)
+        check(self.lib.fgc_spatial_mean_bwd(self._p(g), self._dt(g), N, H * W, Cc, self._p(out), self._s()), "spatial_mean_bwd")
+        return out
+
+    # ---------------- layout ----------------
+    def nchw_to_nhwc(self, x, out_dtype=None):
+        N, Cc, H, W = x.shape
+        y = self._empty((N, H, W, Cc), out_dtype or self.act_dtype)
+        check(self.lib.fgc_nchw_to_nhwc(self._p(x), self._dt(x), N, Cc, H * W, self._p(y), self._dt(y), self._s()), "nchw_to_nhwc")
+        return y
+
+    def nhwc_to_nchw(self, x, out_dtype=None):
+        N, H, W, Cc = x.shape
+        y = self._empty((N, Cc, H, W), out_dtype or self.act_dtype)
+        check(self.lib.fgc_nhwc_to_nchw(self._p(x), self._dt(x), N, Cc, H * W, self._p(y), self._dt(y), self._s()), "nhwc_to_nchw")
+        return y
+
+    def cast(self, x, dtype):
+        if x.dtype == dtype:
+            return x
+        y = self._empty(x.shape, dtype)
+        check(self.lib.fgc_cast(self._p(x), self._dt(x), self._p(y), self._dt(y), x.numel(), self._s()), "cast")
+        return y
+
+    # ---------------- text fusion ----------------
+    def l2norm_rows_fwd(self, x):
+        R, D = x.shape
+        y = self._empty((R, D), torch.float32)
+        inv = self._empty((R,), torch.float32)
+        check(self.lib.fgc_l2norm_rows_fwd(self._f32(x), R, D, self._p(y), self._p(inv), self._s()), "l2norm_rows_fwd")
+        return y, inv
+
+    def l2norm_rows_bwd(self, gy, y, inv):
+        R, D = y.shape
+        gx = self._empty((R, D), torch.float32)
+        check(self.lib.fgc_l2norm_rows_bwd(self._f32(gy), self._f32(y), self._f32(inv), R, D, self._p(gx), self._s()),
+              "l2norm_rows_bwd")
+        return gx
+
+    def embedding_fwd(self, table, ids, t):
+        N, T = ids.shape
+        D = table.shape[1]
+        out = self._empty((N, D), torch.float32)
+        check(self.lib.fgc_embedding_fwd(self._f32(table), self._p(ids), N, T, t, D, self._p(out), self._s()), "embedding_fwd")
+        return out
+
+    def embedding_bwd(self, g, ids, t, dtable):
+        N, T = ids.shape
+        D = dtable.shape[1]
+        check(self.lib.fgc_embedding_bwd(self._f32(g), self._p(ids), N, T, t, D, self._f32(dtable), self._s()), "embedding_bwd")
+
+    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P):
+        R, D = c_prev.shape
+        N, T = ids.shape
+        assert R == N * P
+        c = self._empty((R, D), torch.float32)
+        h = self._empty((R, D), torch.float32)
+        pre = self._empty((R, 4 * D), torch.float32)
+        check(self.lib.fgc_lstm_cell_fwd(self._f32(gates), None if gates2 is None else self._f32(gates2),
+                                         None if grow is None else self._f32(grow), self._f32(c_prev), self._f32(h_prev),
+                                         self._p(ids), T, t, N, P, D, self._p(c), self._p(h), self._p(pre), self._s()),
+              "lstm_cell_fwd")
+        return c, h, pre
+
+    def lstm_cell_bwd(self, gc, gh, pre, c_prev, c, ids, t, P):
+        R, D = c_prev.shape
+        N, T = ids.shape
+        g_pre = self._empty((R, 4 * D), torch.float32)
+        g_c_prev = self._empty((R, D), torch.float32)
+        g_h_pass = self._empty((R, D), torch.float32)
+        check(self.lib.fgc_lstm_cell_bwd(self._f32(gc), self._f32(gh), self._f32(pre), self._f32(c_prev), self._p(ids), T, t, N, P,
+                                         D, self._p(g_pre), self._p(g_c_prev), self._p(g_h_pass), self._s()), "lstm_cell_bwd")
+        return g_pre, g_c_prev, g_h_pass
+
+    def rows_group_sum(self, x, P):
+        R, Cc = x.shape
+        out = self._empty((R // P, Cc), torch.float32)
+        check(self.lib.fgc_rows_group_sum(self._f32(x), R // P, P, Cc, self._p(out), self._s()), "rows_group_sum")
+        return out
+
+    def atanh_relu_fwd(self, h):
+        y = self._empty(h.shape, torch.float32)
+        check(self.lib.fgc_atanh_relu_fwd(self._f32(h), h.numel(), self._p(y), self._s()), "atanh_relu_fwd")
+        return y
+
+    def atanh_relu_bwd(self, gy, h):
+        gx = self._empty(h.shape, torch.float32)
+        check(self.lib.fgc_atanh_relu_bwd(self._f32(gy), self._f32(h), h.numel(), self._p(gx), self._s()), "atanh_relu_bwd")
+        return gx
+
+    # ---------------- spectral norm ----------------
+    def sn_fwd(self, w2d, u):
+        K, Cc = w2d.shape
+        wbar = self._empty((K, Cc), torch.float32)
+        work = self._empty((K + 2 * Cc + 8,), torch.float32)
+        uc = u.reshape(-1).clone()
+        check(self.lib.fgc_sn_fwd(self._f32(w2d), self._f32(uc), K, Cc, self._p(wbar), self._p(work), self._s()), "sn_fwd")
+        return wbar, dict(work=work, u=uc, u_new=work[K + Cc:K + 2 * Cc].view(1, Cc), sigma=work[K + 2 * Cc + 3])
+
+    def sn_bwd(self, gwbar, w2d, ctx, dw):
+        K, Cc = w2d.shape
+        gv = self._empty((K,), torch.float32)
+        check(self.lib.fgc_sn_bwd(self._f32(gwbar), self._f32(w2d), self._f32(ctx["u"]), K, Cc, self._p(ctx["work"]), self._p(gv),
+                                  self._f32(dw), self._s()), "sn_bwd")
+
+    # ---------------- losses ----------------
+    def softplus_mean(self, d, sign):
+        buf = self.zeros_f32((2,))
+        gd = self._empty(d.shape, d.dtype)
+        check(self.lib.fgc_softplus_mean(self._p(d), self._dt(d), d.numel(), float(sign), self._p(buf), 1, self._p(gd), self._s()),
+              "softplus_mean")
+        return buf[1], gd
+
+    def ce_loss(self, logits, labels, focal, weight):
+        N = logits.shape[0]
+        Cc = logits.numel() // N
+        buf = self.zeros_f32((2,))
+        g = self._empty(logits.shape, logits.dtype)
+        check(self.lib.fgc_ce_loss(self._p(logits), self._dt(logits), self._p(labels), N, Cc, 1 if focal else 0, float(weight),
+                                   self._p(buf), 1, self._p(g), self._s()), "ce_loss")
+        return buf[1], g
+
+    def smooth_l1(self, target, gen, weight):
+        assert target.dtype == gen.dtype
+        buf = self.zeros_f32((2,))
+        g = self._empty(gen.shape, gen.dtype)
+        check(self.lib.fgc_smooth_l1(self._p(target), self._p(gen), self._dt(gen), gen.numel(), float(weight), self._p(buf), 1,
+                                     self._p(g), self._s()), "smooth_l1")
+        return buf[1], g
+
+    def reg_loss(self, store):
+        buf = self.zeros_f32((2,))
+        check(self.lib.fgc_reg_loss(self._f32(store.flat), self._p(store.chunk_start), self._p(store.chunk_len),
+                                    self._p(store.chunk_reg), store.chunk_start.numel(), self._p(buf), 1, self._s()), "reg_loss")
+        return buf[1]
+
+    # ---------------- optimiser ----------------
+    def adam_step(self, store, lr, add_reg_grad=True):
+        store.adam_t += 1
+        lr_t = lr * math.sqrt(1.0 - 0.9 ** store.adam_t)
+        check(self.lib.fgc_adam_step(self._f32(store.flat), self._f32(store.grad), self._f32(store.adam_v),
+                                     self._p(store.chunk_start), self._p(store.chunk_len), self._p(store.chunk_reg),
+                                     store.chunk_start.numel(), float(lr_t), 0.9, 1e-8, 1 if add_reg_grad else 0, self._s()),
+              "adam_step")

@@ -1,0 +1,341 @@
+"""GPU parity of every libfgcolor op against the plain-torch op of the same name (tests/torch_ops.py, fp64).
+
+All calls go through the C-ABI (ctypes) via CudaOps.  Convolutions are checked on both implementations: the
+tcgen05 tensor-core path (the product) and the CUDA-core checker, on shapes that exercise every producer
+path (big / small sources, concat, upsampled source, stride 2, 7x7, 1x1, FC rows, ragged M and N tiles).
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from sketchyscenecolorization_b200.ops_base import ACT_LRELU, ACT_MIU, ACT_NONE, ACT_TANH  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def env():
+    from sketchyscenecolorization_b200.cuda_ops import CudaOps
+    from torch_ops import TorchOps
+    dev = torch.device("cuda:0")
+    return dict(cu=CudaOps(dev, torch.float32), cub=CudaOps(dev, torch.bfloat16), ref=TorchOps(torch.float64, dev), dev=dev)
+
+
+def rnd(shape, seed, dev, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g, dtype=torch.float64) * scale).to(dev)
+
+
+def close(a, b, tol, what=""):
+    a = a.double()
+    b = b.double()
+    scale = max(b.abs().max().item(), 1e-30)
+    err = (a - b).abs().max().item() / scale
+    assert err <= tol, "%s: rel-to-max err %.3e > %.1e" % (what, err, tol)
+
+
+CONV_CASES = [
+    # (N, H, W, [(C, ups), ...], k, stride, Cout, act)
+    (2, 16, 16, [(64, False)], 3, 1, 64, ACT_NONE),
+    (3, 12, 12, [(128, False)], 3, 1, 96, ACT_LRELU),           # ragged M (432) and N (96 -> 128 tile)
+    (2, 16, 16, [(64, True), (3, False), (8, False)], 3, 1, 128, ACT_LRELU),   # decoder-style concat + upsample
+    (2, 24, 24, [(8, False), (3, False)], 3, 1, 8, ACT_LRELU),  # stem-level update gate 11 -> 8
+    (2, 32, 32, [(3, False)], 7, 2, 8, ACT_NONE),               # generator stem 7x7 s2, asymmetric SAME pad
+    (2, 16, 16, [(64, False)], 7, 1, 3, ACT_TANH),              # head 7x7 -> 3 + tanh
+    (2, 12, 12, [(192, False)], 1, 1, 64, ACT_NONE),            # 1x1 projection
+    (70, 1, 1, [(256, False)], 1, 1, 200, ACT_MIU),             # fully connected rows
+    (5, 1, 1, [(512, False), (512, False)], 1, 1, 2048, ACT_NONE),   # LSTM gates
+    (2, 6, 6, [(96, False)], 3, 1, 1, ACT_NONE),                # patch logits (Cout 1), partial K slab
+]
+
+
+def _conv_inputs(case, dev, seed=0):
+    N, H, W, srcs, k, stride, cout, act = case
+    xs = []
+    for i, (c, ups) in enumerate(srcs):
+        h, w = (H // 2, W // 2) if ups else (H, W)
+        xs.append((rnd((N, h, w, c), seed + i, dev), ups))
+    cin = sum(c for c, _ in srcs)
+    w_ = rnd((k, k, cin, cout), seed + 10, dev, 1.0 / math.sqrt(k * k * cin))
+    b = rnd((cout,), seed + 11, dev, 0.3)
+    return xs, w_, b
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simple", "tcgen05"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(i) for i in range(len(CONV_CASES))])
+def test_conv_fwd(env, case, impl):
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    cu.lib.fgc_set_conv_impl(impl)
+    try:
+        N, H, W, srcs, k, stride, cout, act = case
+        xs, w, b = _conv_inputs(case, dev)
+        want = ref.conv_fwd(xs, w, b, stride=stride, act=act)
+        got = cu.conv_fwd([(x.float().contiguous(), u) for x, u in xs], w.float().contiguous(), b.float().contiguous(),
+                          stride=stride, act=act)
+        torch.cuda.synchronize()
+        close(got, want, 2e-5 if impl == 1 else 1e-4, "conv_fwd fp32")
+        gotb = env["cub"].conv_fwd([(x.bfloat16().contiguous(), u) for x, u in xs], w.float().contiguous(),
+                                   b.float().contiguous(), stride=stride, act=act)
+        torch.cuda.synchronize()
+        assert gotb.dtype == torch.bfloat16
+        close(gotb, want, 3e-2, "conv_fwd bf16")
+    finally:
+        cu.lib.fgc_set_conv_impl(0)
+
+
+DGRAD_CASES = [
+    # (N, H, W, Cin_total, c_off, c_len, k, Cout, ups, acc)
+    (2, 16, 16, 64, 0, 64, 3, 64, False, False),
+    (2, 12, 12, 131, 128, 3, 3, 128, False, True),      # gradient to the 3-channel image slice, accumulating
+    (2, 16, 16, 75, 0, 64, 3, 96, True, False),         # upsampled hidden state: 2x2-summed low-res gradient
+    (2, 16, 16, 75, 67, 8, 3, 96, False, False),
+    (3, 8, 8, 64, 0, 64, 7, 3, False, False),           # head 7x7 (Cout 3)
+    (2, 12, 12, 192, 0, 192, 1, 64, False, False),
+    (70, 1, 1, 1024, 512, 512, 1, 2048, False, False),  # LSTM kernel slice
+    (2, 6, 6, 96, 0, 96, 1, 1, False, True),            # from the 1-channel patch logits
+]
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simple", "tcgen05"])
+@pytest.mark.parametrize("case", DGRAD_CASES, ids=[str(i) for i in range(len(DGRAD_CASES))])
+def test_conv_dgrad(env, case, impl):
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    cu.lib.fgc_set_conv_impl(impl)
+    try:
+        N, H, W, cin, c_off, c_len, k, cout, ups, acc = case
+        gy = rnd((N, H, W, cout), 1, dev)
+        w = rnd((k, k, cin, cout), 2, dev, 1.0 / math.sqrt(k * k * cout))
+        oshape = (N, H // 2, W // 2, c_len) if ups else (N, H, W, c_len)
+        init = rnd(oshape, 3, dev)
+        want = ref.conv_dgrad(gy, w, c_off, c_len, ups=ups, out=init.clone() if acc else None, acc=acc)
+        out = init.float().contiguous() if acc else None
+        got = cu.conv_dgrad(gy.float().contiguous(), w.float().contiguous(), c_off, c_len, ups=ups, out=out, acc=acc)
+        torch.cuda.synchronize()
+        close(got, want, 2e-5 if impl == 1 else 1e-4, "conv_dgrad fp32")
+        outb = init.bfloat16().contiguous() if acc else None
+        gotb = env["cub"].conv_dgrad(gy.bfloat16().contiguous(), w.float().contiguous(), c_off, c_len, ups=ups, out=outb, acc=acc)
+        torch.cuda.synchronize()
+        close(gotb, want, 3e-2, "conv_dgrad bf16")
+    finally:
+        cu.lib.fgc_set_conv_impl(0)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simple", "tcgen05"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[str(i) for i in range(len(CONV_CASES))])
+def test_conv_wgrad(env, case, impl):
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    cu.lib.fgc_set_conv_impl(impl)
+    try:
+        N, H, W, srcs, k, stride, cout, act = case
+        xs, w, b = _conv_inputs(case, dev, seed=20)
+        OH, OW = -(-H // stride), -(-W // stride)
+        gy = rnd((N, OH, OW, cout), 31, dev)
+        dw0, db0 = rnd(w.shape, 32, dev), rnd(b.shape, 33, dev)
+        dw_ref, db_ref = dw0.clone(), db0.clone()
+        ref.conv_wgrad(xs, gy, dw_ref, db_ref, stride=stride)
+        dw, db = dw0.float().contiguous(), db0.float().contiguous()
+        cu.conv_wgrad([(x.float().contiguous(), u) for x, u in xs], gy.float().contiguous(), dw, db, stride=stride)
+        torch.cuda.synchronize()
+        close(dw, dw_ref, 2e-5 if impl == 1 else 1e-4, "conv_wgrad dw fp32")
+        close(db, db_ref, 2e-5, "conv_wgrad db fp32")
+        dwb, dbb = dw0.float().contiguous(), db0.float().contiguous()
+        env["cub"].conv_wgrad([(x.bfloat16().contiguous(), u) for x, u in xs], gy.bfloat16().contiguous(), dwb, dbb, stride=stride)
+        torch.cuda.synchronize()
+        close(dwb, dw_ref, 3e-2, "conv_wgrad dw bf16")
+    finally:
+        cu.lib.fgc_set_conv_impl(0)
+
+
+# ------------------------------------------------------------------------------------------------
+# normalisation / activations / gating
+# ------------------------------------------------------------------------------------------------
+SHAPES = [(3, 10, 10, 64), (2, 6, 6, 8), (4, 5, 7, 3), (2, 4, 4, 768)]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_cbn(env, shape):
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    N, H, W, Cc = shape
+    x = rnd(shape, 1, dev) * 2 + 0.5
+    gy = rnd(shape, 2, dev)
+    scale, offset = rnd((25, Cc), 3, dev) * 0.2 + 1, rnd((25, Cc), 4, dev) * 0.2
+    labels = torch.randint(0, 25, (N,), generator=torch.Generator().manual_seed(5)).to(dev).int()
+    mean_r, rstd_r = ref.chan_stats(x)
+    xf = x.float().contiguous()
+    mean, rstd = cu.chan_stats(xf)
+    close(mean, mean_r, 1e-5, "mean")
+    close(rstd, rstd_r, 1e-5, "rstd")
+    for act in (ACT_MIU, ACT_NONE):
+        want = ref.cbn_act_fwd(x, mean_r, rstd_r, scale, offset, labels, act)
+        got = cu.cbn_act_fwd(xf, mean, rstd, scale.float(), offset.float(), labels, act)
+        close(got, want, 1e-5, "cbn fwd")
+        ds_r, do_r = torch.zeros_like(scale), torch.zeros_like(offset)
+        gx_r = ref.cbn_act_bwd(gy, x, mean_r, rstd_r, scale, offset, labels, ds_r, do_r, act)
+        ds, do = torch.zeros_like(scale).float(), torch.zeros_like(offset).float()
+        gx = cu.cbn_act_bwd(gy.float().contiguous(), xf, mean, rstd, scale.float(), offset.float(), labels, ds, do, act)
+        close(gx, gx_r, 2e-4, "cbn bwd gx")
+        close(ds, ds_r, 1e-4, "cbn dscale")
+        close(do, do_r, 1e-4, "cbn doffset")
+    # bf16 storage
+    xb = x.bfloat16().contiguous()
+    mb, rb = env["cub"].chan_stats(xb)
+    got = env["cub"].cbn_act_fwd(xb, mb, rb, scale.float(), offset.float(), labels, ACT_MIU)
+    m2, r2 = ref.chan_stats(xb.double())
+    close(got, ref.cbn_act_fwd(xb.double(), m2, r2, scale, offset, labels, ACT_MIU), 1e-2, "cbn fwd bf16")
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_prelu_minmax_actbwd(env, shape):
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    x, gy = rnd(shape, 1, dev), rnd(shape, 2, dev)
+    a = torch.tensor(0.23, device=dev, dtype=torch.float64)
+    xf, gf, af = x.float().contiguous(), gy.float().contiguous(), a.float()
+    close(cu.prelu_fwd(xf, af), ref.prelu_fwd(x, a), 1e-6, "prelu fwd")
+    da_r, da = torch.zeros((), device=dev, dtype=torch.float64), torch.zeros((), device=dev)
+    close(cu.prelu_bwd(gf, xf, af, da), ref.prelu_bwd(gy, x, a, da_r), 1e-6, "prelu bwd")
+    close(da, da_r, 1e-4, "prelu da")
+    # min-max (with an exact tie for the maximum in one map)
+    xl = torch.where(x > 0, x, 0.2 * x)
+    xl[0, 0, 0, 0] = xl[0, 1, 1, 0] = xl[0, :, :, 0].max() + 0.5
+    xlf = xl.float().contiguous()
+    g_r, mn_r, mx_r = ref.minmax_fwd(xlf.double())
+    g, mn, mx = cu.minmax_fwd(xlf)
+    close(g, g_r, 1e-5, "minmax fwd")
+    close(mn, mn_r, 1e-7, "mn")
+    close(mx, mx_r, 1e-7, "mx")
+    close(cu.minmax_bwd(gf, xlf, mn, mx), ref.minmax_bwd(gy, xlf.double(), mn_r, mx_r), 2e-4, "minmax bwd")
+    # activation backward from the output
+    y_t, y_m = torch.tanh(x), (x + torch.sqrt(0.09 + x * x)) / 2
+    close(cu.act_bwd(gf, y_t.float().contiguous(), ACT_TANH), ref.act_bwd(gy, y_t, ACT_TANH), 1e-5, "tanh bwd")
+    close(cu.act_bwd(gf, y_m.float().contiguous(), ACT_MIU), ref.act_bwd(gy, y_m, ACT_MIU), 1e-4, "miu bwd")
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_gating(env, shape, dt):
+    cu, ref, dev = (env["cu"] if dt == torch.float32 else env["cub"]), env["ref"], env["dev"]
+    tol = 1e-5 if dt == torch.float32 else 2e-2
+    N, h, w, Cc = shape
+    full = (N, 2 * h, 2 * w, Cc)
+    lo, a, b, c, g = (rnd(shape, 1, dev).to(dt), rnd(full, 2, dev).to(dt), rnd(full, 3, dev).to(dt), rnd(full, 4, dev).to(dt),
+                      rnd(full, 5, dev).to(dt))
+    D = lambda t: t.double()  # noqa: E731
+    close(cu.gate_fma_fwd(a, b, c), ref.gate_fma_fwd(D(a), D(b), D(c)), tol, "gate_fma")
+    for got, want in zip(cu.gate_fma_bwd(g, b, c), ref.gate_fma_bwd(D(g), D(b), D(c))):
+        close(got, want, tol, "gate_fma_bwd")
+    close(cu.mul_up_fwd(a, lo), ref.mul_up_fwd(D(a), D(lo)), tol, "mul_up")
+    for got, want in zip(cu.mul_up_bwd(g, a, lo), ref.mul_up_bwd(D(g), D(a), D(lo))):
+        close(got, want, tol, "mul_up_bwd")
+    close(cu.blend_fwd(lo, a, b), ref.blend_fwd(D(lo), D(a), D(b)), tol, "blend")
+    for got, want in zip(cu.blend_bwd(g, lo, a, b), ref.blend_bwd(D(g), D(lo), D(a), D(b))):
+        close(got, want, tol, "blend_bwd")
+    close(cu.addpool_fwd(a, b), ref.addpool_fwd(D(a), D(b)), tol, "addpool")
+    close(cu.meanpool_fwd(a), ref.meanpool_fwd(D(a)), tol, "meanpool")
+    close(cu.unpool_bwd(lo), ref.unpool_bwd(D(lo)), tol, "unpool")
+    close(cu.spatial_mean_fwd(a), ref.spatial_mean_fwd(D(a)), tol, "spatial_mean")
+    sm = cu.spatial_mean_fwd(a)
+    close(cu.spatial_mean_bwd(sm, 2 * h, 2 * w), ref.spatial_mean_bwd(D(sm), 2 * h, 2 * w), tol, "spatial_mean_bwd")
+    d = a.clone()
+    close(cu.add_(d, b), D(a) + D(b), tol, "add_")
+    nchw = rnd((N, Cc, 2 * h, 2 * w), 7, dev).float()
+    assert torch.equal(cu.nchw_to_nhwc(nchw, out_dtype=torch.float32), nchw.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(cu.nhwc_to_nchw(a, out_dtype=dt), a.permute(0, 3, 1, 2).contiguous())
+    assert torch.equal(cu.cast(a, torch.bfloat16), a.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------------
+# caption encoder pieces, spectral norm, losses, Adam
+# ------------------------------------------------------------------------------------------------
+def test_text_ops(env):
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    N, P, D, T = 3, 4, 64, 5
+    R = N * P
+    x, gy = rnd((R, D), 1, dev), rnd((R, D), 2, dev)
+    y_r, inv_r = ref.l2norm_rows_fwd(x)
+    y, inv = cu.l2norm_rows_fwd(x.float())
+    close(y, y_r, 1e-6, "l2norm")
+    close(inv, inv_r, 1e-6, "l2norm inv")
+    close(cu.l2norm_rows_bwd(gy.float(), y, inv), ref.l2norm_rows_bwd(gy, y_r, inv_r), 1e-5, "l2norm bwd")
+    table = rnd((58, D), 3, dev)
+    ids = torch.tensor([[0, 0, 5, 7, 9], [0, 3, 3, 3, 3], [2, 4, 6, 8, 10]], device=dev, dtype=torch.int32)
+    for t in (0, 1, 4):
+        close(cu.embedding_fwd(table.float(), ids, t), ref.embedding_fwd(table, ids, t), 1e-7, "embedding")
+        dt_r, dt_ = torch.zeros_like(table), torch.zeros_like(table).float()
+        g = rnd((N, D), 4, dev)
+        ref.embedding_bwd(g, ids, t, dt_r)
+        cu.embedding_bwd(g.float(), ids, t, dt_)
+        close(dt_, dt_r, 1e-6, "embedding bwd")
+        gates, gates2, grow = rnd((R, 4 * D), 5, dev), rnd((R, 4 * D), 6, dev), rnd((N, 4 * D), 7, dev)
+        c0, h0 = rnd((R, D), 8, dev), rnd((R, D), 9, dev)
+        want = ref.lstm_cell_fwd(gates, gates2, grow, c0, h0, ids, t, P)
+        got = cu.lstm_cell_fwd(gates.float(), gates2.float(), grow.float(), c0.float(), h0.float(), ids, t, P)
+        for a, b in zip(got, want):
+            close(a, b, 1e-5, "lstm fwd")
+        gc, gh = rnd((R, D), 10, dev), rnd((R, D), 11, dev)
+        wantb = ref.lstm_cell_bwd(gc, gh, want[2], c0, want[0], ids, t, P)
+        gotb = cu.lstm_cell_bwd(gc.float(), gh.float(), got[2], c0.float(), got[0], ids, t, P)
+        for a, b in zip(gotb, wantb):
+            close(a, b, 1e-5, "lstm bwd")
+        # word-LSTM form: no gates2 / grow, P = 1
+        want1 = ref.lstm_cell_fwd(grow, None, None, c0[:N], h0[:N], ids, t, 1)
+        got1 = cu.lstm_cell_fwd(grow.float(), None, None, c0[:N].float().contiguous(), h0[:N].float().contiguous(), ids, t, 1)
+        for a, b in zip(got1, want1):
+            close(a, b, 1e-5, "lstm fwd P=1")
+    close(cu.rows_group_sum(x.float(), P), ref.rows_group_sum(x, P), 1e-6, "rows_group_sum")
+    h = torch.tanh(rnd((R, D), 12, dev))
+    close(cu.atanh_relu_fwd(h.float()), ref.atanh_relu_fwd(h), 1e-5, "atanh_relu")
+    close(cu.atanh_relu_bwd(gy.float(), h.float()), ref.atanh_relu_bwd(gy, h), 1e-5, "atanh_relu bwd")
+
+
+@pytest.mark.parametrize("kc", [(27 * 8, 8), (1152, 128), (768, 1), (768, 25), (6912, 768)], ids=str)
+def test_spectral_norm(env, kc):
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    K, Cc = kc
+    w, u, gw = rnd((K, Cc), 1, dev, 0.02), rnd((1, Cc), 2, dev), rnd((K, Cc), 3, dev)
+    wbar_r, ctx_r = ref.sn_fwd(w, u)
+    wbar, ctx = cu.sn_fwd(w.float().contiguous(), u.float().contiguous())
+    close(wbar, wbar_r, 2e-5, "wbar")
+    close(ctx["u_new"], ctx_r["u_new"], 2e-5, "u_new")
+    dw_r, dw = rnd((K, Cc), 4, dev), None
+    dw = dw_r.float().contiguous()
+    ref.sn_bwd(gw, w, ctx_r, dw_r)
+    cu.sn_bwd(gw.float().contiguous(), w.float().contiguous(), ctx, dw)
+    close(dw, dw_r, 1e-4, "sn dw")
+
+
+def test_losses_and_adam(env):
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    d = rnd((4, 12, 12, 1), 1, dev) * 3
+    for sign in (1.0, -1.0):
+        l_r, g_r = ref.softplus_mean(d, sign)
+        l, g = cu.softplus_mean(d.float(), sign)
+        close(l, l_r, 1e-5, "softplus")
+        close(g, g_r, 1e-5, "softplus grad")
+    logits = rnd((6, 1, 1, 25), 2, dev) * 2
+    labels = torch.tensor([0, 24, 3, 3, 7, 11], device=dev, dtype=torch.int32)
+    for focal, wgt in ((True, 1.0), (False, 0.5)):
+        l_r, g_r = ref.ce_loss(logits, labels, focal, wgt)
+        l, g = cu.ce_loss(logits.float(), labels, focal, wgt)
+        close(l, l_r, 1e-5, "ce")
+        close(g, g_r, 1e-5, "ce grad")
+    t, gen = rnd((2, 16, 16, 3), 3, dev) * 1.5, rnd((2, 16, 16, 3), 4, dev)
+    l_r, g_r = ref.smooth_l1(t, gen, 100.0)
+    l, g = cu.smooth_l1(t.float(), gen.float(), 100.0)
+    close(l, l_r, 1e-5, "smooth_l1")
+    close(g, g_r, 1e-6, "smooth_l1 grad")
+    # reg loss + Adam on a real parameter store
+    from sketchyscenecolorization_b200.params import ParamStore, discriminator_vars
+    st = ParamStore(discriminator_vars(8), dev)
+    st.initialize(3)
+    st_r = ParamStore(discriminator_vars(8), dev, torch.float64)
+    st_r.load_state_dict(st.state_dict())
+    close(cu.reg_loss(st), ref.reg_loss(st_r), 1e-5, "reg")
+    gr = rnd((st.n_flat,), 5, dev, 0.01)
+    for it in range(3):
+        st.grad.copy_(gr.float())
+        st_r.grad.copy_(gr)
+        cu.adam_step(st, 1e-3)
+        ref.adam_step(st_r, 1e-3)
+    close(st.flat, st_r.flat, 1e-5, "adam params")
+    close(st.adam_v, st_r.adam_v, 1e-5, "adam v")
