@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""Headline benchmark: fg-colorization training images/sec @192x192, bs 64 per GPU (BASELINE.json configs[1]).
+
+One step = one training iteration of the reference's session loop (main_procedure.py:202-227): a D step
+(G forward, D(real), D(fake), D backward, Adam) and a G step (G forward, D(fake), D input-gradient, G backward,
+Adam, SN u update) on two different synthetic batches, through hand-written sm_100a kernels (libfgcolor.so).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]             # product arm (one process per GPU under torchrun)
+  python bench.py --impl reference ...                            # CPU restatement of the reference graph (oracle)
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 192
+BS = 64
+SIZE = 64
+GF_GFLOP = 57.989          # generator conv forward, GFLOP / image   
+DF_GFLOP = 64.633          # discriminator conv forward
+STEP_GFLOP = 4 * GF_GFLOP + 8 * DF_GFLOP      # 749.02 GFLOP / image / iteration
+METRIC = "fg-colorization train images/sec @192x192 bs64 per GPU"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], burst=d["bf16_tflops"], sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_batch(n, seed):
+    """+-1 stroke sketches (~5% black), U(-1,1) images, labels U{0..24}, 15 non-pad ids, N(0,1) noise."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    sk = torch.ones(n, 1, H, W)
+    for i in range(n):
+        for _ in range(6):
+            p = torch.rand(5, 2, generator=g) * torch.tensor([H - 1.0, W - 1.0])
+            for a, b in zip(p[:-1], p[1:]):
+                L = int(max(abs(b[0] - a[0]), abs(b[1] - a[1]))) + 1
+                ys = torch.linspace(a[0].item(), b[0].item(), L).round().long()
+                xs = torch.linspace(a[1].item(), b[1].item(), L).round().long()
+                sk[i, 0, ys, xs] = -1.0
+    return dict(sketch=sk.expand(n, 3, H, W).contiguous(),
+                images=torch.rand(n, 3, H, W, generator=g) * 2 - 1,
+                images_d=torch.rand(n, 3, H, W, generator=g) * 2 - 1,
+                cls=torch.randint(0, 25, (n,), generator=g).int(), cls_d=torch.randint(0, 25, (n,), generator=g).int(),
+                text=torch.randint(2, 58, (n, 15), generator=g).int(), noise=torch.randn(n, 256, generator=g))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference graph (TensorFlow 1.x cannot be installed here)
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_images_per_sec(steps, warmup, bs=2, seed=0):
+    import torch
+    from oracle import fgcolor_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gspecs, dspecs = O.generator_specs(SIZE, 58, H, W), O.discriminator_specs(SIZE)
+    gp = {k: v.requires_grad_(v.is_floating_point()) for k, v in O.init_params(gspecs, seed).items()}
+    dp = {k: v.requires_grad_(v.is_floating_point()) for k, v in O.init_params(dspecs, seed + 1).items()}
+    vg = {k: torch.zeros_like(v) for k, v in gp.items()}
+    vd = {k: torch.zeros_like(v) for k, v in dp.items()}
+    bA, bB = O.make_batch(bs, H, W, 1), O.make_batch(bs, H, W, 2)
+
+    def one_iter(t):
+        ld, _, _ = O.d_step_loss(gp, dp, gspecs, dspecs, bA, SIZE)
+        gd = O.grads_of(ld, dp, dspecs)
+        with torch.no_grad():
+            for k, g in gd.items():
+                new, vd[k] = O.adam_update(dp[k], g, vd[k], 1e-4, t)
+                dp[k].copy_(new)
+        lg, _, u_new, _ = O.g_step_loss(gp, dp, gspecs, dspecs, bB, SIZE)
+        gg = O.grads_of(lg, gp, gspecs)
+        with torch.no_grad():
+            for k, g in gg.items():
+                new, vg[k] = O.adam_update(gp[k], g, vg[k], 2e-4, t)
+                gp[k].copy_(new)
+            for k, u in u_new.items():
+                dp[k].copy_(u)
+        return float(ld.detach()), float(lg.detach())
+
+    for i in range(warmup):
+        one_iter(i + 1)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one_iter(warmup + i + 1)
+    dt = time.perf_counter() - t0
+    return bs * steps / dt, dt / steps, cores, bs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    ips, spi, cores, bs = cpu_reference_images_per_sec(steps, warmup)
+    sample = "bs %d (the reference default batch), %d timed iteration(s) after %d warm-up, same 192x192 graph" % (bs, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": spi * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "fg-colorization MRU G+D training iteration (D step + G step), 192x192, 15-token captions",
+                       "note": "CPU restatement of the reference TF1 graph (oracle/fgcolor_oracle.py, torch-CPU autograd); "
+                               "TensorFlow 1.x is not installable in this image"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# product arm
+# ----------------------------------------------------------------------------------------------------------
+def dominant_kernel_roofline(ops, torch, pk, reps=5):
+    """The dominant kernel of the step: the 128->128 3x3 conv at 192x192 (D unit-1 Conv_2 / G decoder unit 8), bs 64,
+    single-pass bf16.  Algorithmic FLOPs per launch = 2 * 64 * 192^2 * 9 * 128 * 128."""
+    dev = ops.device
+    x = torch.randn(BS, H, W, 128, device=dev).to(torch.bfloat16)
+    wgt = (torch.randn(3, 3, 128, 128, device=dev) * 0.02).contiguous()
+    b = torch.zeros(128, device=dev)
+    flop = 2.0 * BS * H * W * 9 * 128 * 128
+    for _ in range(2):
+        ops.conv_fwd([(x, False)], wgt, b)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for e0, e1 in evs:            # input (604 MB) + output (604 MB) per launch exceed the 126 MB L2
+        e0.record()
+        ops.conv_fwd([(x, False)], wgt, b)
+        e1.record()
+    torch.cuda.synchronize()
+    ms = sorted(e0.elapsed_time(e1) for e0, e1 in evs)[len(evs) // 2]
+    ach = flop / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "conv_igemm_kernel<bf16,128> 3x3 128->128 @192x192 bs64 (incl. weight pack)",
+            "achieved": round(ach, 2), "peak": pk["burst"], "unit": "TFLOP/s", "frac": round(ach / pk["burst"], 4),
+            "peak_source": pk["src"] + " bf16 burst", "ms_per_launch": round(ms, 4), "flop_per_launch": flop, "traffic": None}
+
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    from sketchyscenecolorization_b200.cuda_ops import CudaOps
+    from sketchyscenecolorization_b200.trainer import FgColorModel, FgColorTrainer
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = "cuda:%d" % local
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+        pg = dist.group.WORLD
+    ops = CudaOps(dev, torch.bfloat16)          # training mode: bf16 NHWC activations, fp32 master weights / stats / Adam
+    model = FgColorModel(ops, dev, size=SIZE, H=H, W=W)
+    model.initialize(seed=0)                    # identical on every rank (reference initialisers)
+    tr = FgColorTrainer(model, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=pg, world_size=world)
+
+    hostA, hostB = synth_batch(BS, 1234 + rank), synth_batch(BS, 4321 + rank)
+    pin = lambda b: {k: v.pin_memory() for k, v in b.items()}  # noqa: E731
+    hostA, hostB = pin(hostA), pin(hostB)
+
+    def to_dev(hb):
+        d = {k: v.to(dev, non_blocking=True) for k, v in hb.items() if k != "text"}
+        d["text"] = hb["text"].numpy()          # caption ids: the host copy drives the pad-skip control flow
+        return d
+
+    def h2d_bytes(hb, keys):
+        return sum(hb[k].numel() * hb[k].element_size() for k in keys)
+
+    devA, devB = to_dev(hostA), to_dev(hostB)
+    torch.cuda.synchronize()
+
+    def iteration(bA, bB):
+        od = tr.d_step(bA)
+        og = tr.g_step(bB)
+        return od["loss"], og["loss"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        iteration(devA, devB)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ld, lg = iteration(devA, devB)
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    ld_v, lg_v = float(ld), float(lg)
+
+    # ---- end to end: pinned host buffers -> device every step, losses read back every step
+    d_keys = ("sketch", "images_d", "cls", "cls_d", "noise", "text")
+    g_keys = ("sketch", "images", "cls", "noise", "text")
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        bA = {k: (hostA[k].to(dev, non_blocking=True) if k != "text" else hostA[k].numpy()) for k in d_keys}
+        bA["images"] = None
+        od = tr.d_step(bA)
+        bB = {k: (hostB[k].to(dev, non_blocking=True) if k != "text" else hostB[k].numpy()) for k in g_keys}
+        og = tr.g_step(bB)
+        _ = (float(od["loss"]), float(og["loss"]))        # D2H read of both loss scalars
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        pk = peaks()
+        ips = BS * world * args.steps / (ms * 1e-3)
+        ips_e2e = BS * world * args.steps / (ms_e2e * 1e-3)
+        roof = dominant_kernel_roofline(ops, torch, pk)
+        step_tflops = STEP_GFLOP * 1e9 * ips / world / 1e12
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            c_ips, c_spi, cores, c_bs = cpu_reference_images_per_sec(1, 1)
+            cpu = {"value": c_ips, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": "oracle (torch-CPU restatement of the TF1 graph), bs %d, 1 timed training iteration after 1 warm-up" % c_bs}
+        line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "fg-colorization MRU G+D training iteration (D step + G step), 192x192, bs 64/GPU, "
+                                       "15-token captions (BASELINE.json configs[1])",
+                           "global_batch": BS * world, "parallelism": "dp%d" % world,
+                           "precision": "bf16 activations + single-pass bf16 tcgen05 convs, fp32 accumulate/master/BN/LSTM/Adam",
+                           "l2_policy": "per-step working set (tens of GB of activations) far exceeds the 126 MB L2",
+                           "conv_flop_per_image": STEP_GFLOP * 1e9,
+                           "step_conv_tflops_per_gpu": round(step_tflops, 2),
+                           "step_conv_frac_of_sustained_peak": round(step_tflops / pk["sustained"], 4),
+                           "loss_d": ld_v, "loss_g": lg_v},
+                "clocks": clocks,
+                "e2e": {"value": ips_e2e, "unit": "images/s",
+                        "h2d_bytes_per_step": h2d_bytes(hostA, d_keys) + h2d_bytes(hostB, g_keys), "d2h_bytes_per_step": 8},
+                "gpu_launches": launches,
+                "roofline": roof}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

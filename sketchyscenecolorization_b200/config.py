@@ -1,0 +1,19 @@
+"""Global flags of the fg-colorization path -- same singleton contract as the reference's obj_lib/config.py:4-17
+(class attributes set from the CLI dict with `Config.set_from_dict`, read everywhere)."""
+
+
+class Config(object):
+    data_format = 'NCHW'     # layout at the boundary (feeds / outputs); kernels run NHWC internally
+    sn = True                # spectral normalisation on every discriminator weight (config.py:8)
+    proj_d = False
+    wgan = False
+    pre_calculated_dist_map = False
+    # B200 additions (not in the reference): numeric mode of the tensor-core convolutions
+    train_precision = 'bf16'     # 'bf16' (single pass) | 'fp32' (bf16x3 split accumulate)
+    infer_precision = 'fp32'     # inference / val / test always meet the 1e-3 parity bar
+
+    @staticmethod
+    def set_from_dict(d):
+        assert type(d) is dict
+        for k, v in d.items():
+            setattr(Config, k, v)

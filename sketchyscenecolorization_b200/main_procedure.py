@@ -1,0 +1,198 @@
+"""Session loops of the fg-colorization path on the B200 kernels: train / validation / test / inference.
+
+Same entry points, `Config` keys, status codes and on-disk layout as the reference's obj_lib/main_procedure.py
+(`train` :62-242 -> 0 ok / -1 NaN, `inference` :495-621 writes <stem>_output.png and <stem>_input.png);
+the TF1 session, queue runners and Saver are replaced by FgColorTrainer, an input iterator and checkpoint.py."""
+from __future__ import annotations
+
+import json
+import math
+import os
+from time import time
+
+import numpy as np
+import torch
+
+from . import checkpoint, graph_single
+from .config import Config
+from .input_pipeline import CATEGORIES, SyntheticInput, resize_and_padding_mask_image
+from .text_processing import default_vocab_dict, load_vocab_dict_from_file, preprocess_sentence
+
+SIZE = {True: (64, 64), False: (192, 192)}
+T = 15      # main_procedure.py:503
+
+
+def _dtype(name):
+    return torch.bfloat16 if name == 'bf16' else torch.float32
+
+
+def _build_model(precision, img_dim, vocab_size, lstm_hybrid, device=None, with_discriminator=True):
+    from .cuda_ops import CudaOps
+    from .trainer import FgColorModel
+    dev = device or "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
+    ops = CudaOps(dev, _dtype(precision))
+    return FgColorModel(ops, dev, H=img_dim[0], W=img_dim[1], vocab_size=vocab_size, lstm_hybrid=lstm_hybrid,
+                        with_discriminator=with_discriminator)
+
+
+def _categories():
+    base = os.path.join('data', 'captions')
+    if os.path.isdir(base):
+        return sorted(os.listdir(base))            # main_procedure.py:506-508
+    return list(CATEGORIES)
+
+
+def _vocab():
+    f = os.path.join('data', 'vocab.txt')
+    return load_vocab_dict_from_file(f) if os.path.exists(f) else default_vocab_dict()
+
+
+def print_parameter_count(model, verbose=False):
+    """main_procedure.print_parameter_count (:28-59)."""
+    g, d = model.gstore.num_params(), model.dstore.num_params() if model.dstore is not None else 0
+    print('generator: %d trainable parameters in %d tensors' % (g, model.gstore.num_trainable_tensors()))
+    if model.dstore is not None:
+        print('discriminator: %d trainable parameters in %d tensors' % (d, model.dstore.num_trainable_tensors()))
+    return g, d
+
+
+def train(**kwargs):
+    """Alternating D / G optimisation (main_procedure.py:62-242).  kwargs: iter_from, and optionally `input_iter`
+    (two-queue stand-in yielding batch dicts) and `process_group`/`world_size` for data parallelism."""
+    from .trainer import FgColorTrainer
+    status = 0
+    batch_size, max_iter_step, diters = Config.batch_size, Config.max_iter_step, Config.disc_iterations
+    log_dir, ckpt_dir = Config.log_dir, Config.ckpt_dir
+    small, lstm_hybrid = Config.small_img != 0, Config.LSTM_hybrid != 0
+    if Config.block_type != 'MRU':
+        raise NotImplementedError("block_type %r is not built (MRU only)" % Config.block_type)
+    if Config.optimizer != 'Adam':
+        raise NotImplementedError("optimizer %r: the path is built for the default Adam(beta1=0, beta2=0.9)" % Config.optimizer)
+    iter_from = kwargs['iter_from']
+    world = int(kwargs.get('world_size', 1))
+    print('Iteration starts from: %d' % iter_from)
+
+    model = _build_model(Config.train_precision, SIZE[small], Config.vocab_size, lstm_hybrid)
+    model.initialize(seed=int(kwargs.get('seed', 0)))
+    tr = FgColorTrainer(model, lr_g=Config.lr_G, lr_d=Config.lr_D, max_iter=max_iter_step,
+                        process_group=kwargs.get('process_group'), world_size=world)
+    if iter_from > 0:
+        prefix = checkpoint.latest_checkpoint(ckpt_dir)
+        print('Restore:', prefix)
+        checkpoint.restore(model, prefix)
+    tr.counter = iter_from                                          # sess.run(counter.assign(iter_from)), :176
+    print_parameter_count(model)
+    rank = int(os.environ.get("RANK", "0"))
+    q1 = kwargs.get('input_iter') or SyntheticInput(batch_size, *SIZE[small], vocab_size=Config.vocab_size, seed=1234 + rank)
+    q2 = kwargs.get('input_iter_d') or SyntheticInput(batch_size, *SIZE[small], vocab_size=Config.vocab_size, seed=4321 + rank)
+    dev = model.device
+    summ = open(os.path.join(log_dir, 'summaries.jsonl'), 'a') if rank == 0 else None
+
+    def fetch():
+        a, b = next(q1), next(q2)      # (images, sketches, ids, text) and an independent images_d queue, :109-122
+        out = {k: a[k].to(dev, non_blocking=True) for k in ('sketch', 'images', 'cls')}
+        out['images_d'], out['cls_d'] = b['images_d'].to(dev, non_blocking=True), b['cls_d'].to(dev, non_blocking=True)
+        out['text'] = a['text'].numpy()
+        out['noise'] = torch.randn(batch_size, 256, device=dev)
+        return out
+
+    prev_time = float("-inf")
+    for i in range(iter_from, max_iter_step):
+        if i % Config.count_left_time_freq == 0:
+            curr_time = time()
+            elapsed = curr_time - prev_time
+            print("Now at iteration %d. Elapsed time: %.5fs. Average time: %.5fs/iter"
+                  % (i, elapsed, elapsed / float(Config.count_left_time_freq)))
+            prev_time = curr_time
+        want_summary = i % Config.summary_write_freq == 0
+        for j in range(diters):                                       # each sess.run dequeues a fresh batch
+            od = tr.d_step(fetch())
+            loss_d_out = float(od['loss'])
+            if math.isnan(loss_d_out):
+                print("NaN occurred during training D")
+                return -1
+        og = tr.g_step(fetch())
+        loss_g_out = float(og['loss'])
+        if math.isnan(loss_g_out):
+            print("NaN occurred during training G")
+            return -1
+        if want_summary and summ is not None:                         # scalar names of graph_single.py:71-98
+            rec = {"step": i, "GAN_loss/G": float(og['gan']), "GAN_loss/D": float(od['gan']), "ACGAN_loss/G": float(og['ac']),
+                   "ACGAN_loss/D": float(od['ac']), "l1_perceptual_loss": float(og['l1']), "total_loss/g": loss_g_out,
+                   "total_loss/d": loss_d_out, "learning_rate_g": Config.lr_G * max(0.2, 1 - 0.9 * i / max_iter_step)}
+            summ.write(json.dumps(rec) + "\n")
+            summ.flush()
+        if i % Config.save_model_freq == Config.save_model_freq - 1 and rank == 0:
+            checkpoint.save(model, ckpt_dir, i, tr.counter)
+            print('Save model_{}.ckpt'.format(i))
+    return status
+
+
+def _load_sketch(path, img_dim, category):
+    from PIL import Image
+    im = Image.open(path).convert("RGB")
+    if im.width != img_dim[0] or im.height != img_dim[1]:
+        arr = resize_and_padding_mask_image(im, img_dim[0], margin_size=0 if category in ['road'] else 10).astype(np.float32)
+    else:
+        arr = np.array(im, dtype=np.float32)
+    arr = arr / 255. * 2. - 1
+    return np.transpose(arr[None], [0, 3, 1, 2])                    # [1, 3, H, W]
+
+
+def _write_pair(folder, stem, generated, sketch):
+    """NCHW -> NHWC, (x+1)/2*255 truncated to uint8, generated image RGB->BGR for cv2 (main_procedure.py:601-619)."""
+    import cv2
+    gen = np.transpose(generated, (0, 2, 3, 1))
+    sk = np.transpose(sketch, (0, 2, 3, 1))
+    gen = (((gen + 1) / 2.) * 255)[:, :, :, ::-1].astype(np.uint8)
+    sk = (((sk + 1) / 2.) * 255).astype(np.uint8)
+    cv2.imwrite(os.path.join(folder, stem + '_output.png'), gen[0])
+    cv2.imwrite(os.path.join(folder, stem + '_input.png'), sk[0])
+
+
+def inference(img_name, instruction, model=None, noise=None):
+    """One sketch + caption -> colourised PNG (main_procedure.py:495-621)."""
+    wild_cate = img_name[:img_name.find('.png')]
+    categories = _categories()
+    if wild_cate not in categories:
+        wild_cate = categories[2]                                   # 'bus', :510-511
+    small, lstm_hybrid = Config.small_img != 0, Config.LSTM_hybrid != 0
+    img_dim = SIZE[small]
+    os.makedirs(Config.results_dir, exist_ok=True)
+    print('output_folder:', Config.results_dir)
+    if model is None:
+        model = _build_model(Config.infer_precision, img_dim, Config.vocab_size, lstm_hybrid, with_discriminator=False)
+        prefix = checkpoint.latest_checkpoint(Config.ckpt_dir)
+        print('Restore trained model:', prefix)
+        if prefix is None:
+            raise RuntimeError("no snapshot in %s" % Config.ckpt_dir)
+        checkpoint.restore(model, prefix, strict=True)
+    sketch = _load_sketch(os.path.join('examples', img_name), img_dim, wild_cate)
+    class_id = np.array([categories.index(wild_cate)])
+    ids = np.array(preprocess_sentence(instruction, _vocab(), T), dtype=np.int32)[None]
+    ret = graph_single.build_single_graph(sketch, sketch, None, class_id, None, ids, batch_size=1, training=False,
+                                          LSTM_hybrid=lstm_hybrid, vocab_size=Config.vocab_size, data_format=Config.data_format,
+                                          distance_map=Config.distance_map != 0, block_type=Config.block_type, model=model,
+                                          noise=noise)
+    generated, input_sketch = ret[0].cpu().numpy(), ret[2].cpu().numpy()
+    _write_pair(Config.results_dir, img_name[:-4], generated, input_sketch)
+    print('Saved file %s' % (img_name[:-4] + '_output.png'))
+    return generated
+
+
+def test(model=None):
+    """Loops `inference` over data/captions/<category>/test.json (main_procedure.py:361-492).  The dataset is not
+    shipped with the reference; without it this raises."""
+    base = os.path.join('data', 'captions')
+    if not os.path.isdir(base):
+        raise FileNotFoundError("data/captions is missing: the FOREGROUND dataset is not part of the repository")
+    for cate in sorted(os.listdir(base)):
+        with open(os.path.join(base, cate, 'test.json')) as f:
+            for entry in json.load(f):
+                inference(entry['key'] if 'key' in entry else entry['image'], entry['caption'] if 'caption' in entry else entry['text'],
+                          model=model)
+
+
+def validation(**kwargs):
+    raise NotImplementedError("validation reads the TFRecord validation queue (main_procedure.py:245-358); the TFRecord reader "
+                              "is listed under 'next' in DESIGN.md")

@@ -1,0 +1,100 @@
+"""CPU tests of the host-side network code (hand-derived backward passes, no autograd) against torch autograd on
+the oracle, using the plain-torch operator set in tests/torch_ops.py (fp64).  This validates
+blocks.py / generator.py / discriminator.py / text_fusion.py / trainer.py before any GPU time is spent;
+the GPU tests then swap in the CUDA operator set under the same host code."""
+import pytest
+import torch
+
+from oracle import fgcolor_oracle as O
+from sketchyscenecolorization_b200.params import ParamStore, discriminator_vars, generator_vars
+from sketchyscenecolorization_b200.trainer import FgColorModel, FgColorTrainer, lr_decay
+from torch_ops import TorchOps
+
+SIZE, H, W, N = 16, 64, 64, 3
+
+
+@pytest.fixture(scope="module")
+def setup():
+    ops = TorchOps(torch.float64)
+    m = FgColorModel(ops, "cpu", size=SIZE, H=H, W=W, param_dtype=torch.float64)
+    m.initialize(seed=3, perturb_tables=0.1)
+    gp = {k: v.clone().requires_grad_(True) for k, v in m.gstore.state_dict().items()}
+    dp = {k: v.clone().requires_grad_(True) for k, v in m.dstore.state_dict().items()}
+    b = O.make_batch(N, H, W, 5, torch.float64, n_pad=3)
+    b["text"][0, :7] = 0
+    bb = dict(b)
+    bb["cls"], bb["cls_d"], bb["text"] = b["cls"].int(), b["cls_d"].int(), b["text"].numpy()
+    return dict(ops=ops, m=m, gp=gp, dp=dp, b=b, bb=bb, gspecs=O.generator_specs(SIZE, 58, H, W), dspecs=O.discriminator_specs(SIZE))
+
+
+def _worst(store, ref, ops):
+    ops.add_reg_grad(store)      # the oracle differentiates the l2 decay; the product adds it inside the Adam kernel
+    gs = max(g.abs().max().item() for g in ref.values())
+    return max((store.g[k] - g).abs().max().item() / max(g.abs().max().item(), 1e-6 * gs) for k, g in ref.items())
+
+
+def test_parameter_inventory_matches_survey():
+    """G = 153 trainable tensors / 30 306 499 params, D = 60 / 17 159 752 (+23 SN u vectors)."""
+    g = ParamStore(generator_vars(64, 58, 192, 192), "cpu")
+    d = ParamStore(discriminator_vars(64), "cpu")
+    assert (g.num_trainable_tensors(), g.num_params()) == (153, 30306499)
+    assert (d.num_trainable_tensors(), d.num_params()) == (60, 17159752)
+    assert len(d.state) == 23
+    ospec = {s.name: s.shape for s in O.generator_specs(64, 58, 192, 192) + O.discriminator_specs(64)}
+    mine = {s.name: tuple(s.shape) for s in generator_vars(64, 58, 192, 192) + discriminator_vars(64)}
+    assert ospec == mine
+
+
+def test_generator_forward_matches_oracle(setup):
+    s = setup
+    out = s["m"].generate(s["b"]["sketch"], s["bb"]["text"], s["bb"]["cls"], s["b"]["noise"])
+    ref = O.generator_forward(s["gp"], s["b"]["sketch"], s["b"]["text"], s["b"]["cls"], s["b"]["noise"], SIZE)
+    assert (out - ref).abs().max().item() < 1e-10
+
+
+def test_d_step_gradients_match_autograd(setup):
+    s = setup
+    r = s["m"].d_step_grads(s["bb"])
+    ld, _, _ = O.d_step_loss(s["gp"], s["dp"], s["gspecs"], s["dspecs"], s["b"], SIZE)
+    assert abs(r["loss"].item() - ld.item()) < 1e-10
+    assert _worst(s["m"].dstore, O.grads_of(ld, s["dp"], s["dspecs"]), s["ops"]) < 1e-7
+
+
+def test_g_step_gradients_and_u_update(setup):
+    s = setup
+    m = s["m"]
+    saved = {k: v.clone() for k, v in m.dstore.state.items()}
+    r = m.g_step_grads(s["bb"])
+    lg, _, u_new, _ = O.g_step_loss(s["gp"], s["dp"], s["gspecs"], s["dspecs"], s["b"], SIZE)
+    assert abs(r["loss"].item() - lg.item()) < 1e-10
+    assert _worst(m.gstore, O.grads_of(lg, s["gp"], s["gspecs"]), s["ops"]) < 1e-7
+    for k, v in m.dstore.state.items():
+        assert (v - u_new[k]).abs().max().item() < 1e-12
+        v.copy_(saved[k])            # leave the fixture as it was
+
+
+def test_all_pad_caption_and_lr_decay(setup):
+    s = setup
+    bb = dict(s["bb"])
+    bb["text"] = bb["text"].copy()
+    bb["text"][:] = 0
+    b = dict(s["b"])
+    b["text"] = torch.zeros_like(b["text"])
+    out = s["m"].generate(b["sketch"], bb["text"], bb["cls"], b["noise"])
+    ref = O.generator_forward(s["gp"], b["sketch"], b["text"], b["cls"], b["noise"], SIZE)
+    assert (out - ref).abs().max().item() < 1e-10
+    assert lr_decay(0, 100) == 1.0 and abs(lr_decay(50, 100) - 0.55) < 1e-12 and lr_decay(100, 100) == 0.2
+
+
+def test_adam_matches_oracle_update(setup):
+    s = setup
+    m, ops = s["m"], s["ops"]
+    tr = FgColorTrainer(m, lr_g=2e-4, lr_d=1e-4, max_iter=1000)
+    before = m.dstore.flat.clone()
+    tr.d_step(s["bb"])
+    g = m.dstore.grad.clone()       # includes the decay term after the step
+    want, _ = O.adam_update(before, g, torch.zeros_like(g), 1e-4 * lr_decay(0, 1000), 1)
+    assert (m.dstore.flat - want).abs().max().item() < 1e-12
+    m.dstore.flat.copy_(before)
+    m.dstore.adam_v.zero_()
+    m.dstore.adam_t = 0
