@@ -51,6 +51,9 @@ typedef struct {
 size_t fgc_conv2d_ws_bytes(const int* src_C, int nsrc, int k, int n_out, int src_dtype);
 /* 0 = tcgen05 tensor-core path (default), 1 = CUDA-core checker (also: env FGC_CONV_IMPL=simple) */
 int fgc_set_conv_impl(int impl);
+/* debug aid: per-role event trace (role, event, tile, clock64) of CTA 0 of the implicit-GEMM kernel; buf holds
+ * 4 + 4*capacity int64 on the device, buf[0] is the event count.  NULL disables. */
+int fgc_debug_set_trace(long long* buf, int capacity);
 
 /* y[N,OH,OW,Cout] = act(conv(concat_c(srcs), w) + bias); SAME padding (pad_t/pad_l = TF's top/left pad).
  * w: fp32 HWIO [k,k,Cin_total,Cout]; bias fp32 [Cout] or NULL.  fp32 sources run the bf16x3 split-accumulate

@@ -25,7 +25,7 @@ for impl in (1, 0):
     rows = []
     for k, g in gg.items():
         a = (m.gstore.g[k].detach().cpu().double() - g).abs().max().item()
-        rows.append((a / max(g.abs().max().item(), 1e-30), a, g.abs().max().item(), k))
+        rows.append((a / max(g.abs().max().item(), 1e-4 * gs), a, g.abs().max().item(), k))
     rows.sort(reverse=True)
     print("impl", impl, "loss", r["loss"].item(), lg.item(), "global max grad", gs)
     for rel, a, mx, k in rows[:12]:

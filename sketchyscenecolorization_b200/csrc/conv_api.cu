@@ -17,6 +17,8 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
                    cudaStream_t s);
 int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s);
 size_t conv_ws_bytes(const ConvGeom& g, int nout, int x3);
+extern long long* g_trace;
+extern int g_trace_cap;
 
 static int g_impl = -1;   // 0 = tcgen05, 1 = simple
 static int conv_impl() {
@@ -48,6 +50,13 @@ static int build_geom(ConvGeom& g, const fgc_src* srcs, int nsrc, int N, int H, 
 using namespace fgc;
 
 extern "C" {
+
+// debug: event trace of CTA 0 of the implicit-GEMM kernel; buf = [4 + 4*capacity] int64 on the device (buf[0] = count)
+int fgc_debug_set_trace(long long* buf, int capacity) {
+  g_trace = buf;
+  g_trace_cap = capacity;
+  return FGC_OK;
+}
 
 int fgc_set_conv_impl(int impl) {
   g_impl = impl ? 1 : 0;

@@ -24,6 +24,7 @@
 //   * split over the pixel axis across CTAs, fp32 red.add into dW.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "conv_geom.cuh"
@@ -165,7 +166,29 @@ template <> struct Stage<float> {
   static constexpr bool X3 = true;
 };
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives this thread's arrival once all of its prior cp.async copies have landed (no count increment:
+// the barrier's expected count already includes the thread) -- the producer never waits for its own loads
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most n of this thread's cp.async groups are still in flight (n <= 3)
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
+
 // "big" slab: channels [c0, c0+64) of one source at tap offset (dh, dw).  tid in [0,128).
+// bf16 sources are copied with cp.async (LDGSTS, zero-fill for padding): no register staging, the caller keeps
+// several slabs in flight and fences/arrives when a group has landed.  fp32 sources go through registers for the
+// hi/lo split.
 template <typename SrcT, int ROWS>
 __device__ __forceinline__ void gather_big(uint8_t* s_hi, uint8_t* s_lo, const SrcT* __restrict__ src, int C, int c0, int ups,
                                            int H, int W, int stride, int dh, int dw, const uint32_t* pix, const PixDec pd, int tid) {
@@ -176,6 +199,21 @@ __device__ __forceinline__ void gather_big(uint8_t* s_hi, uint8_t* s_lo, const S
   const int cj = c0 + j * S::EPC;
   const bool cvalid = cj < C;
   const int Hs = ups ? (H >> 1) : H, Ws = ups ? (W >> 1) : W;
+  if constexpr (!S::X3) {
+    const uint32_t sbase = smem_u32(s_hi);
+#pragma unroll
+    for (int i = 0; i < NPASS; i++) {
+      uint32_t p = pix[i];
+      int n = (int)((p >> pd.owb) >> pd.ohb), oh = (int)((p >> pd.owb) & pd.ohm), ow = (int)(p & pd.owm);
+      int ih = oh * stride + dh, iw = ow * stride + dw;
+      bool ok = cvalid && p != PIX_INVALID && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
+      if (ups) { ih >>= 1; iw >>= 1; }
+      const SrcT* ptr = ok ? src + (((long long)n * Hs + ih) * Ws + iw) * C + cj : src;
+      int r = g + RPP * i;
+      cp_async16(sbase + r * 128 + ((j ^ (r & 7)) << 4), ptr, ok ? 16u : 0u);
+    }
+    return;
+  }
   uint4 v[NPASS];
 #pragma unroll
   for (int i = 0; i < NPASS; i++) {
@@ -199,6 +237,41 @@ __device__ __forceinline__ void gather_big(uint8_t* s_hi, uint8_t* s_lo, const S
       int off = r * 128 + (((j >> 1) ^ (r & 7)) << 4) + ((j & 1) << 3);
       *reinterpret_cast<uint2*>(s_hi + off) = hi;
       *reinterpret_cast<uint2*>(s_lo + off) = lo;
+    }
+  }
+}
+
+// Fast path of the above for bf16 sources of stride-1 SAME convolutions (output pixel index == input pixel index):
+// per row only a bounds test and one address add remain in the slab loop.
+//   pk[i]    = oh | ow << 16 of the thread's i-th row (0xFFFFFFFF for rows past M: fails every bounds test)
+//   base4[i] = (n*H*W) / 4 of that row (pixel index of its image in a half-resolution source)
+//   m_g      = flattened pixel index of the thread's first row; rows are RPP apart
+template <int ROWS>
+__device__ __forceinline__ void gather_big_fast(uint32_t sbase, const __nv_bfloat16* __restrict__ src, int C, int c0, int ups,
+                                                int H, int W, int dh, int dw, long long m_g, const uint32_t* pk,
+                                                const int* base4, int tid) {
+  constexpr int RPP = kProducers / 8, NPASS = ROWS / RPP;
+  const int j = tid & 7, g = tid >> 3;
+  const int cj = c0 + j * 8;
+  const bool cvalid = cj < C;
+  const uint32_t dst0 = sbase + g * 128 + ((j ^ (g & 7)) << 4);      // (g + RPP*i) & 7 == g & 7 because RPP % 8 == 0
+  if (!ups) {
+    const __nv_bfloat16* p0 = src + (m_g + (long long)dh * W + dw) * C + cj;
+    const long long rstride = (long long)RPP * C;
+#pragma unroll
+    for (int i = 0; i < NPASS; i++) {
+      int ih = (int)(pk[i] & 0xFFFFu) + dh, iw = (int)(pk[i] >> 16) + dw;
+      bool ok = cvalid && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
+      cp_async16(dst0 + i * (RPP * 128), ok ? p0 + i * rstride : src, ok ? 16u : 0u);
+    }
+  } else {
+    const int Ws = W >> 1;
+#pragma unroll
+    for (int i = 0; i < NPASS; i++) {
+      int ih = (int)(pk[i] & 0xFFFFu) + dh, iw = (int)(pk[i] >> 16) + dw;
+      bool ok = cvalid && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
+      long long idx = (long long)base4[i] + (ih >> 1) * Ws + (iw >> 1);
+      cp_async16(dst0 + i * (RPP * 128), ok ? src + idx * C + cj : src, ok ? 16u : 0u);
     }
   }
 }
@@ -257,7 +330,13 @@ __device__ __forceinline__ void gather_small(uint8_t* s_hi, uint8_t* s_lo, const
 // ------------------------------------------------------------------------------------------------------
 __global__ void pack_weights_kernel(ConvGeom g, const float* __restrict__ w, long long tap_stride, long long k_stride,
                                     long long n_stride, long long base, int Nvalid, int Npad, int x3,
-                                    __nv_bfloat16* __restrict__ out) {
+                                    __nv_bfloat16* __restrict__ out, int4* __restrict__ tbl) {
+  // slab table for the producers: {source | big << 8, dh, dw, first channel (big) or first flattened index (small)}
+  for (int sl = blockIdx.x * blockDim.x + threadIdx.x; sl < g.nslabs; sl += gridDim.x * blockDim.x) {
+    SlabInfo si = decode_slab(g, sl);
+    int kh = si.tap / g.k, kw = si.tap % g.k;
+    tbl[sl] = make_int4(si.s | (si.big << 8), g.sign * (kh - g.pad_t), g.sign * (kw - g.pad_l), si.big ? si.c0 : si.q0);
+  }
   long long total = (long long)g.nslabs * Npad * 8;
   long long plane = (long long)g.nslabs * Npad * 64;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -292,6 +371,9 @@ __global__ void pack_weights_kernel(ConvGeom g, const float* __restrict__ w, lon
 // ------------------------------------------------------------------------------------------------------
 struct IgemmArgs {
   ConvGeom g;
+  long long* trace;          // optional event trace of CTA 0 (debug builds of the benchmark scripts): [n][4]
+  int trace_cap;
+  int dbg;                   // debug switches (env FGC_DBG): 1 = skip epilogue stores, 2 = skip bias/act
   const __nv_bfloat16* wp;   // packed weights, hi plane then lo plane
   long long wp_plane;        // elements per plane
   int Npad;                  // packed rows per slab
@@ -303,7 +385,23 @@ struct IgemmArgs {
   int y_dtype;
   int vec_ok;                // y is 16-byte aligned
   int stages;
+  int depth;                 // unused
+  const int4* tbl;           // slab table written by pack_weights_kernel
+  int fast;                  // stride-1 SAME geometry: output pixel index == input pixel index
+  int tiles_m;               // ceil(M / (128*MT))
+  int any_small;             // some source goes through the flattened (small) path
 };
+
+// event trace: (role, event, tile, clock64) rows appended by one lane of CTA 0
+__device__ __forceinline__ void trace_ev(const IgemmArgs& a, int role, int ev, int tile) {
+  if (a.trace && blockIdx.x == 0) {
+    unsigned long long n = atomicAdd(reinterpret_cast<unsigned long long*>(a.trace), 1ULL);
+    if ((int)n < a.trace_cap) {
+      long long* p = a.trace + 4 + 4 * n;
+      p[0] = role; p[1] = ev; p[2] = tile; p[3] = clock64();
+    }
+  }
+}
 
 __device__ __forceinline__ float epi_act(float v, int act) {
   switch (act) {
@@ -314,181 +412,282 @@ __device__ __forceinline__ float epi_act(float v, int act) {
   }
 }
 
-template <typename SrcT, int BN>
-__global__ void __launch_bounds__(192) conv_igemm_kernel(const __grid_constant__ IgemmArgs a) {
+// Persistent, warp-specialised kernel.  One CTA per SM loops over output tiles (tile = 128*MT pixels x BN channels):
+//   warps [0, 4*MT)        A producers (cp.async / register-staged gather into the smem ring)
+//   warp  4*MT             MMA issuer (one elected lane) + TMEM allocation
+//   warp  4*MT+1           B loader (one bulk-TMA copy per slab)
+//   warps [4*MT+2, 8*MT+2) epilogue (TMEM -> registers -> bias/act -> NHWC global)
+// The smem ring runs across tile boundaries and the accumulator is double buffered in TMEM (NACC = 2), so the
+// epilogue of tile i overlaps the main loop of tile i+1 and the per-tile fixed costs are paid once per CTA.
+template <typename SrcT, int BN, int MT, int NACC>
+__global__ void __launch_bounds__(32 * (8 * MT + 2), 1) conv_igemm_kernel(const __grid_constant__ IgemmArgs a) {
   using S = Stage<SrcT>;
-  constexpr int A_BYTES = 128 * 128;                 // one plane of the A tile
+  static_assert(!(S::X3 && MT != 1), "bf16x3 mode uses one A tile per CTA");
+  static_assert(NACC * MT * BN <= 512, "accumulators exceed TMEM");
+  constexpr int A_BYTES = 128 * 128;                 // one plane of one A tile
   constexpr int B_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = (S::X3 ? 2 : 1) * (A_BYTES + B_BYTES);
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int PLANES = S::X3 ? 2 : 1;
+  constexpr int STAGE_BYTES = PLANES * (MT * A_BYTES + B_BYTES);
+  constexpr int ACC_COLS = MT * BN;
+  constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : (NACC * ACC_COLS <= 64 ? 64 : (NACC * ACC_COLS <= 128 ? 128 : (NACC * ACC_COLS <= 256 ? 256 : 512)));
   constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
+  constexpr int NPROD = 128 * MT;
+  constexpr int MMA_WARP = 4 * MT, LOAD_WARP = 4 * MT + 1, EPI_WARP0 = 4 * MT + 2;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int stages = a.stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);   // full[stages], empty[stages], accum
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+  // barriers: full[stages], empty[stages], acc_full[NACC], acc_empty[NACC]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * STAGE_BYTES);
+  uint64_t* acc_full = bars + 2 * stages;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const ConvGeom& g = a.g;
-  const long long m0 = (long long)blockIdx.x * 128;
-  const int n0 = blockIdx.y * BN;
   const int nslabs = g.nslabs;
-  const PixDec pd = pix_dec(g);
+  const int tiles_n = a.Npad / BN;
+  const int ntiles = a.tiles_m * tiles_n;
 
   if (tid == 0) {
     for (int s = 0; s < stages; s++) {
-      mbar_init(smem_u32(&bars[s]), kProducers + 1);   // 128 producer arrivals + the bulk-copy issuer (with tx bytes)
+      mbar_init(smem_u32(&bars[s]), NPROD + 1);        // producer arrivals + the bulk-copy issuer (with tx bytes)
       mbar_init(smem_u32(&bars[stages + s]), 1);       // released by tcgen05.commit
     }
-    mbar_init(smem_u32(&bars[2 * stages]), 1);
+    for (int i = 0; i < NACC; i++) {
+      mbar_init(smem_u32(&acc_full[i]), 1);            // tcgen05.commit after the last slab of a tile
+      mbar_init(smem_u32(&acc_empty[i]), NPROD);       // every epilogue thread, once its TMEM reads are done
+    }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ===================== A producers (then epilogue) =====================
+  if (warp < 4 * MT) {
+    // ===================== A producers =====================
+    const int tile = tid >> 7, ltid = tid & 127;
     constexpr int RPP = kProducers / S::CPR, NPASS = 128 / RPP;
-    uint32_t pix[NPASS];
-    {
-      const int gq = tid / S::CPR;
+    const PixDec pd = pix_dec(g);
+    const bool fast = !S::X3 && a.fast;
+    const int hw4 = (g.OH * g.OW) >> 2;
+    int gs = 0;                                        // slabs produced so far (ring position)
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const long long mt0 = (long long)(t / tiles_n) * (128 * MT) + tile * 128;
+      // row state: rows ltid/CPR + RPP*i of the tile; decode the first by division, step the others
+      uint32_t pix[NPASS];          // generic path: packed (n, oh, ow)
+      uint32_t pk[NPASS];           // fast path: oh | ow << 16
+      int base4[NPASS];             // fast path: n * (OH*OW/4)
+      const long long m_g = mt0 + ltid / S::CPR;
+      {
+        uint32_t n, oh, ow;
+        if (m_g < g.M) {
+          uint32_t m32 = (uint32_t)m_g;                // M < 2^31 is checked on the host
+          ow = m32 % (uint32_t)g.OW;
+          uint32_t q = m32 / (uint32_t)g.OW;
+          oh = q % (uint32_t)g.OH;
+          n = q / (uint32_t)g.OH;
+        } else { n = oh = ow = 0; }
 #pragma unroll
-      for (int i = 0; i < NPASS; i++) pix[i] = pix_pack(m0 + gq + RPP * i, g);
-    }
-    const uint32_t pixrow = pix_pack(m0 + tid, g);
-    for (int slab = 0; slab < nslabs; slab++) {
-      const int st = slab % stages;
-      const uint32_t ph = (slab / stages) & 1;
-      mbar_wait(smem_u32(&bars[stages + st]), ph ^ 1);
-      uint8_t* sa_hi = smem + (size_t)st * STAGE_BYTES;
-      uint8_t* sa_lo = sa_hi + A_BYTES;
-      SlabInfo si = decode_slab(g, slab);
-      const SrcT* src = reinterpret_cast<const SrcT*>(g.src[si.s]);
-      if (si.big) {
-        int kh = si.tap / g.k, kw = si.tap % g.k;
-        gather_big<SrcT, 128>(sa_hi, sa_lo, src, g.C[si.s], si.c0, g.ups[si.s], g.H, g.W, g.stride, g.sign * (kh - g.pad_t),
-                              g.sign * (kw - g.pad_l), pix, pd, tid);
-      } else {
-        gather_small<SrcT, 128>(sa_hi, sa_lo, src, g.C[si.s], si.q0, g.ups[si.s], g.H, g.W, g.stride, g.k, g.pad_t, g.pad_l,
-                                g.sign, &pixrow, pd, tid);
+        for (int i = 0; i < NPASS; i++) {
+          const bool valid = m_g + RPP * i < g.M;
+          pix[i] = valid ? ((n << (g.ow_bits + g.oh_bits)) | (oh << g.ow_bits) | ow) : PIX_INVALID;
+          pk[i] = valid ? (oh | (ow << 16)) : 0xFFFFFFFFu;
+          base4[i] = (int)n * hw4;
+          ow += RPP;
+          while (ow >= (uint32_t)g.OW) { ow -= g.OW; oh++; }
+          while (oh >= (uint32_t)g.OH) { oh -= g.OH; n++; }
+        }
       }
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&bars[st]));
-    }
-    // ===================== epilogue =====================
-    mbar_wait(smem_u32(&bars[2 * stages]), 0);
-    tc_fence_after();
-    const long long m = m0 + warp * 32 + lane;
-    const bool mvalid = m < g.M;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-      if (!mvalid) continue;
-      const int nb = n0 + c0;
-      if (nb >= a.Nout) continue;
-      float v[32];
-#pragma unroll
-      for (int q = 0; q < 32; q++) {
-        float t = __uint_as_float(r[q]);
-        int n = nb + q;
-        if (a.bias && n < a.Nout) t += __ldg(a.bias + n);
-        v[q] = epi_act(t, a.act);
-      }
-      const int nrem = a.Nout - nb;      // > 0
-      if (a.y_dtype == FGC_F32) {
-        float* yp = reinterpret_cast<float*>(a.y) + m * a.Nout + nb;
-        if (a.vec_ok && nrem >= 32 && (a.Nout & 3) == 0) {
-#pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-            if (a.accumulate) {
-              float4 p = *reinterpret_cast<float4*>(yp + q);
-              o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-            }
-            *reinterpret_cast<float4*>(yp + q) = o;
+      uint32_t pixrow = PIX_INVALID;
+      if (a.any_small) pixrow = pix_pack(mt0 + ltid, g);
+      if (tid == 0) trace_ev(a, 0, 0, t);
+      for (int slab = 0; slab < nslabs; slab++, gs++) {
+        const int st = gs % stages;
+        const uint32_t ph = (gs / stages) & 1;
+        const int4 e = __ldg(a.tbl + slab);
+        const int si_s = e.x & 0xFF, si_big = e.x >> 8;
+        mbar_wait(smem_u32(&bars[stages + st]), ph ^ 1);
+        if (tid == 0) trace_ev(a, 0, 1, t);
+        uint8_t* sa_hi = smem + (size_t)st * STAGE_BYTES + tile * A_BYTES;
+        uint8_t* sa_lo = sa_hi + MT * A_BYTES;
+        const SrcT* src = reinterpret_cast<const SrcT*>(g.src[si_s]);
+        if (si_big) {
+          if constexpr (!S::X3) {
+            if (fast)
+              gather_big_fast<128>(smem_u32(sa_hi), src, g.C[si_s], e.w, g.ups[si_s], g.H, g.W, e.y, e.z, m_g, pk, base4, ltid);
+            else
+              gather_big<SrcT, 128>(sa_hi, sa_lo, src, g.C[si_s], e.w, g.ups[si_s], g.H, g.W, g.stride, e.y, e.z, pix, pd, ltid);
+          } else {
+            gather_big<SrcT, 128>(sa_hi, sa_lo, src, g.C[si_s], e.w, g.ups[si_s], g.H, g.W, g.stride, e.y, e.z, pix, pd, ltid);
           }
         } else {
-#pragma unroll
-          for (int q = 0; q < 32; q++)
-            if (q < nrem) yp[q] = a.accumulate ? yp[q] + v[q] : v[q];
+          gather_small<SrcT, 128>(sa_hi, sa_lo, src, g.C[si_s], e.w, g.ups[si_s], g.H, g.W, g.stride, g.k, g.pad_t, g.pad_l,
+                                  g.sign, &pixrow, pd, ltid);
         }
-      } else {
-        __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.Nout + nb;
-        if (a.vec_ok && nrem >= 32 && (a.Nout & 7) == 0) {
+        if (!S::X3 && si_big) {
+          cp_async_mbar_arrive_noinc(smem_u32(&bars[st]));     // arrives when the copies have landed
+        } else {
+          fence_proxy_async();                                 // st.shared (generic proxy) -> visible to the MMA (async proxy)
+          mbar_arrive(smem_u32(&bars[st]));
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    int gs = 0, ti = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ti++) {
+      const int buf = ti % NACC;
+      mbar_wait(smem_u32(&acc_empty[buf]), ((ti / NACC) & 1) ^ 1);     // epilogue has drained this accumulator
+      tc_fence_after();
+      if (lane == 0) trace_ev(a, 1, 0, t);
+      for (int slab = 0; slab < nslabs; slab++, gs++) {
+        const int st = gs % stages;
+        const uint32_t ph = (gs / stages) & 1;
+        mbar_wait(smem_u32(&bars[st]), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          trace_ev(a, 1, 1, t);
+          const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+          const uint32_t sb_hi = sa + PLANES * MT * A_BYTES;
+          const uint32_t sb_lo = sb_hi + B_BYTES;
+          const uint64_t db_hi = desc_kmajor(sb_hi, 1024);
 #pragma unroll
-          for (int q = 0; q < 32; q += 8) {
-            if (a.accumulate) {
-              uint4 p = *reinterpret_cast<uint4*>(yp + q);
-              const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&p);
+          for (int tt = 0; tt < MT; tt++) {
+            const uint64_t da_hi = desc_kmajor(sa + tt * A_BYTES, 1024);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS + tt * BN);
 #pragma unroll
-              for (int e = 0; e < 4; e++) {
-                float2 f = __bfloat1622float2(pp[e]);
-                v[q + 2 * e] += f.x; v[q + 2 * e + 1] += f.y;
+            for (int kk = 0; kk < 4; kk++) {
+              const uint32_t acc = (slab > 0 || kk > 0) ? 1u : 0u;
+              umma_bf16(d_tmem, da_hi + 2 * kk, db_hi + 2 * kk, IDESC, acc);
+              if constexpr (S::X3) {
+                const uint64_t da_lo = desc_kmajor(sa + MT * A_BYTES, 1024), db_lo = desc_kmajor(sb_lo, 1024);
+                umma_bf16(d_tmem, da_hi + 2 * kk, db_lo + 2 * kk, IDESC, 1u);
+                umma_bf16(d_tmem, da_lo + 2 * kk, db_hi + 2 * kk, IDESC, 1u);
               }
             }
-            uint4 o = make_uint4(pack_bf16x2(v[q], v[q + 1]), pack_bf16x2(v[q + 2], v[q + 3]), pack_bf16x2(v[q + 4], v[q + 5]),
-                                 pack_bf16x2(v[q + 6], v[q + 7]));
-            *reinterpret_cast<uint4*>(yp + q) = o;
           }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 32; q++)
-            if (q < nrem) yp[q] = __float2bfloat16_rn(a.accumulate ? __bfloat162float(yp[q]) + v[q] : v[q]);
+          umma_commit(smem_u32(&bars[stages + st]));
+          if (slab == nslabs - 1) umma_commit(smem_u32(&acc_full[buf]));
         }
+        __syncwarp();
       }
     }
-    tc_fence_before();
-  } else if (warp == 4) {
-    // ===================== MMA issuer =====================
-    for (int slab = 0; slab < nslabs; slab++) {
-      const int st = slab % stages;
-      const uint32_t ph = (slab / stages) & 1;
-      mbar_wait(smem_u32(&bars[st]), ph);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa_hi = smem_u32(smem + (size_t)st * STAGE_BYTES);
-        const uint32_t sa_lo = sa_hi + A_BYTES;
-        const uint32_t sb_hi = sa_hi + (S::X3 ? 2 : 1) * A_BYTES;
-        const uint32_t sb_lo = sb_hi + B_BYTES;
-        const uint64_t da_hi = desc_kmajor(sa_hi, 1024), db_hi = desc_kmajor(sb_hi, 1024);
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-          const uint32_t acc = (slab > 0 || kk > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, da_hi + 2 * kk, db_hi + 2 * kk, IDESC, acc);
-          if constexpr (S::X3) {
-            const uint64_t da_lo = desc_kmajor(sa_lo, 1024), db_lo = desc_kmajor(sb_lo, 1024);
-            umma_bf16(tmem_base, da_hi + 2 * kk, db_lo + 2 * kk, IDESC, 1u);
-            umma_bf16(tmem_base, da_lo + 2 * kk, db_hi + 2 * kk, IDESC, 1u);
-          }
-        }
-        umma_commit(smem_u32(&bars[stages + st]));
-        if (slab == nslabs - 1) umma_commit(smem_u32(&bars[2 * stages]));
-      }
-      __syncwarp();
-    }
-  } else {
+  } else if (warp == LOAD_WARP) {
     // ===================== B loader: one bulk copy per slab (and plane) =====================
     if (lane == 0) {
-      for (int slab = 0; slab < nslabs; slab++) {
-        const int st = slab % stages;
-        const uint32_t ph = (slab / stages) & 1;
-        mbar_wait(smem_u32(&bars[stages + st]), ph ^ 1);
-        const uint32_t sb_hi = smem_u32(smem + (size_t)st * STAGE_BYTES) + (S::X3 ? 2 : 1) * A_BYTES;
-        const uint32_t bar = smem_u32(&bars[st]);
-        const __nv_bfloat16* wsrc = a.wp + ((long long)slab * a.Npad + n0) * 64;
-        mbar_arrive_expect_tx(bar, (S::X3 ? 2 : 1) * B_BYTES);
-        bulk_g2s(sb_hi, wsrc, B_BYTES, bar);
-        if constexpr (S::X3) bulk_g2s(sb_hi + B_BYTES, wsrc + a.wp_plane, B_BYTES, bar);
+      int gs = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int n0 = (t % tiles_n) * BN;
+        for (int slab = 0; slab < nslabs; slab++, gs++) {
+          const int st = gs % stages;
+          const uint32_t ph = (gs / stages) & 1;
+          mbar_wait(smem_u32(&bars[stages + st]), ph ^ 1);
+          const uint32_t sb_hi = smem_u32(smem + (size_t)st * STAGE_BYTES) + PLANES * MT * A_BYTES;
+          const uint32_t bar = smem_u32(&bars[st]);
+          const __nv_bfloat16* wsrc = a.wp + ((long long)slab * a.Npad + n0) * 64;
+          mbar_arrive_expect_tx(bar, PLANES * B_BYTES);
+          bulk_g2s(sb_hi, wsrc, B_BYTES, bar);
+          if constexpr (S::X3) bulk_g2s(sb_hi + B_BYTES, wsrc + a.wp_plane, B_BYTES, bar);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ei = warp - EPI_WARP0;
+    const int tile = ei >> 2, quarter = warp & 3;      // a warp may only read TMEM lanes [32*(warp%4), +32)
+    int ti = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ti++) {
+      const int buf = ti % NACC;
+      const int n0 = (t % tiles_n) * BN;
+      const long long m = (long long)(t / tiles_n) * (128 * MT) + tile * 128 + quarter * 32 + lane;
+      const bool mvalid = m < g.M;
+      mbar_wait(smem_u32(&acc_full[buf]), (ti / NACC) & 1);
+      tc_fence_after();
+      if (ei == 0 && lane == 0) trace_ev(a, 2, 0, t);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int nb = n0 + c0;
+        // this lane's bias value of the chunk, fetched before the accumulator is read (broadcast by shuffle below)
+        float bias_l = 0.f;
+        if (a.bias && nb + lane < a.Nout) bias_l = __ldg(a.bias + nb + lane);
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + tile * BN + c0), r);
+        if (ei == 0 && lane == 0) trace_ev(a, 2, 1, t);
+        if (c0 + 32 >= BN) {                           // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(smem_u32(&acc_empty[buf]));
+        }
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 32; q++) v[q] = __uint_as_float(r[q]) + __shfl_sync(0xffffffffu, bias_l, q);
+        switch (a.act) {                               // one branch per chunk, branch-free inner loops
+          case FGC_ACT_LRELU:
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = v[q] > 0.f ? v[q] : 0.2f * v[q];
+            break;
+          case FGC_ACT_TANH:
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = tanhf(v[q]);
+            break;
+          case FGC_ACT_MIU:
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
+            break;
+          default: break;
+        }
+        if (!mvalid) continue;
+        if (nb >= a.Nout) continue;
+        const int nrem = a.Nout - nb;      // > 0
+        if (a.y_dtype == FGC_F32) {
+          float* yp = reinterpret_cast<float*>(a.y) + m * a.Nout + nb;
+          if (a.vec_ok && nrem >= 32 && (a.Nout & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+              if (a.accumulate) {
+                float4 p = *reinterpret_cast<float4*>(yp + q);
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+              }
+              *reinterpret_cast<float4*>(yp + q) = o;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; q++)
+              if (q < nrem) yp[q] = a.accumulate ? yp[q] + v[q] : v[q];
+          }
+        } else {
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.Nout + nb;
+          if (a.vec_ok && nrem >= 32 && (a.Nout & 7) == 0) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 8) {
+              if (a.accumulate) {
+                uint4 p = *reinterpret_cast<uint4*>(yp + q);
+                const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&p);
+#pragma unroll
+                for (int e2 = 0; e2 < 4; e2++) {
+                  float2 f = __bfloat1622float2(pp[e2]);
+                  v[q + 2 * e2] += f.x; v[q + 2 * e2 + 1] += f.y;
+                }
+              }
+              uint4 o = make_uint4(pack_bf16x2(v[q], v[q + 1]), pack_bf16x2(v[q + 2], v[q + 3]), pack_bf16x2(v[q + 4], v[q + 5]),
+                                   pack_bf16x2(v[q + 6], v[q + 7]));
+              *reinterpret_cast<uint4*>(yp + q) = o;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; q++)
+              if (q < nrem) yp[q] = __float2bfloat16_rn(a.accumulate ? __bfloat162float(yp[q]) + v[q] : v[q]);
+          }
+        }
       }
     }
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -506,6 +705,8 @@ struct WgradArgs {
   int kslabs;         // ceil(M/64)
   int kslabs_per_cta;
   int stages;
+  int depth;
+  int fast;           // stride-1 SAME geometry
 };
 
 template <typename SrcT, int BN>
@@ -556,6 +757,19 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
       have[b] = 2 * mt + b < g.nslabs;
       si[b] = decode_slab(g, have[b] ? 2 * mt + b : 0);
     }
+    const bool gy_vec = (a.Cout & 7) == 0 && a.Cout >= 8;
+    // fast path (bf16, stride-1 SAME): per-row (oh, ow) advanced incrementally by 64 pixels per iteration
+    const bool fast = !S::X3 && a.fast;
+    int roh[NPASS], row_[NPASS];
+    const int d64 = 64 / g.OW, r64 = 64 % g.OW;
+    if (fast) {
+#pragma unroll
+      for (int i = 0; i < NPASS; i++) {
+        long long m = (long long)ks0 * 64 + (tid >> 3) + RPP * i;
+        row_[i] = (int)(m % g.OW);
+        roh[i] = (int)((m / g.OW) % g.OH);
+      }
+    }
     for (int it = 0; it < niter; it++) {
       const int st = it % stages;
       const uint32_t ph = (it / stages) & 1;
@@ -566,19 +780,37 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
       uint8_t* sb_lo = sb_hi + B_BYTES;
       const long long mbase = (long long)(ks0 + it) * 64;
       uint32_t pix[NPASS];
-      {
+      uint32_t pixrow = 0;
+      if (!fast) {
         const int gq = tid / S::CPR;
 #pragma unroll
         for (int i = 0; i < NPASS; i++) pix[i] = pix_pack(mbase + gq + RPP * i, g);
       }
-      const uint32_t pixrow = pix_pack(mbase + (tid & 63), g);
+      if (!fast || !gy_vec || !(have[0] && si[0].big) || !(!have[1] || si[1].big)) pixrow = pix_pack(mbase + (tid & 63), g);
+      uint32_t pk[NPASS];
+      int base4[NPASS];
+      const long long m_g = mbase + (tid >> 3);
+      if constexpr (!S::X3) {
+        if (fast) {
+#pragma unroll
+          for (int i = 0; i < NPASS; i++) {
+            long long m = m_g + RPP * i;
+            pk[i] = m < g.M ? ((uint32_t)roh[i] | ((uint32_t)row_[i] << 16)) : 0xFFFFFFFFu;
+            base4[i] = (int)((m - (long long)roh[i] * g.OW - row_[i]) >> 2);
+            // advance to the next 64-pixel slab
+            row_[i] += r64;
+            roh[i] += d64;
+            if (row_[i] >= g.OW) { row_[i] -= g.OW; roh[i]++; }
+            while (roh[i] >= g.OH) roh[i] -= g.OH;
+          }
+        }
+      }
       // A': x rows (tap-shifted), two 64-wide blocks of the flattened (tap, ci) axis
 #pragma unroll
       for (int b = 0; b < 2; b++) {
         uint8_t* dh_ = sa_hi + b * BLK;
         uint8_t* dl_ = sa_lo + b * BLK;
         if (!have[b]) {
-          // zero block
           for (int i = tid; i < BLK / 16; i += kProducers) {
             reinterpret_cast<uint4*>(dh_)[i] = make_uint4(0, 0, 0, 0);
             if constexpr (S::X3) reinterpret_cast<uint4*>(dl_)[i] = make_uint4(0, 0, 0, 0);
@@ -588,8 +820,17 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
         const SrcT* src = reinterpret_cast<const SrcT*>(g.src[si[b].s]);
         if (si[b].big) {
           int kh = si[b].tap / g.k, kw = si[b].tap % g.k;
-          gather_big<SrcT, 64>(dh_, dl_, src, g.C[si[b].s], si[b].c0, g.ups[si[b].s], g.H, g.W, g.stride, kh - g.pad_t,
-                               kw - g.pad_l, pix, pd, tid);
+          bool done = false;
+          if constexpr (!S::X3) {
+            if (fast) {
+              gather_big_fast<64>(smem_u32(dh_), src, g.C[si[b].s], si[b].c0, g.ups[si[b].s], g.H, g.W, kh - g.pad_t, kw - g.pad_l,
+                                  m_g, pk, base4, tid);
+              done = true;
+            }
+          }
+          if (!done)
+            gather_big<SrcT, 64>(dh_, dl_, src, g.C[si[b].s], si[b].c0, g.ups[si[b].s], g.H, g.W, g.stride, kh - g.pad_t,
+                                 kw - g.pad_l, pix, pd, tid);
         } else {
           gather_small<SrcT, 64>(dh_, dl_, src, g.C[si[b].s], si[b].q0, g.ups[si[b].s], g.H, g.W, g.stride, g.k, g.pad_t,
                                  g.pad_l, 1, &pixrow, pd, tid);
@@ -599,15 +840,31 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
 #pragma unroll
       for (int b = 0; b < NBB; b++) {
         int c0 = n0 + b * 64;
-        if ((a.Cout & 7) == 0 && a.Cout >= 8)
-          gather_big<SrcT, 64>(sb_hi + b * BLK, sb_lo + b * BLK, reinterpret_cast<const SrcT*>(a.gy), a.Cout, c0, 0, g.OH, g.OW, 1,
-                               0, 0, pix, pd, tid);
-        else  // odd channel counts (1, 3, 25): flattened path with k=1 semantics
+        if (gy_vec) {
+          bool done = false;
+          if constexpr (!S::X3) {
+            if (fast) {
+              gather_big_fast<64>(smem_u32(sb_hi + b * BLK), reinterpret_cast<const __nv_bfloat16*>(a.gy), a.Cout, c0, 0, g.OH, g.OW,
+                                  0, 0, m_g, pk, base4, tid);
+              done = true;
+            }
+          }
+          if (!done)
+            gather_big<SrcT, 64>(sb_hi + b * BLK, sb_lo + b * BLK, reinterpret_cast<const SrcT*>(a.gy), a.Cout, c0, 0, g.OH, g.OW, 1,
+                                 0, 0, pix, pd, tid);
+        } else {  // odd channel counts (1, 3, 25): flattened path with k=1 semantics
           gather_small<SrcT, 64>(sb_hi + b * BLK, sb_lo + b * BLK, reinterpret_cast<const SrcT*>(a.gy), a.Cout, c0, 0, g.OH, g.OW,
                                  1, 1, 0, 0, 1, &pixrow, pd, tid);
+        }
       }
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&bars[st]));
+      // st.shared parts (small / fp32 / zero blocks) need the cross-proxy fence; cp.async parts are tracked by the
+      // barrier itself.  One arrival per thread either way.
+      bool any_sync = S::X3 || !gy_vec;
+#pragma unroll
+      for (int b = 0; b < 2; b++) any_sync = any_sync || !have[b] || !si[b].big;
+      if (any_sync) fence_proxy_async();
+      if (!S::X3) cp_async_mbar_arrive_noinc(smem_u32(&bars[st]));
+      else mbar_arrive(smem_u32(&bars[st]));
     }
     // epilogue: lane = row of dW (flattened (tap, ci)), columns = co
     if (niter > 0) {
@@ -669,72 +926,91 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
 // ------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------
-static int pick_bn(int nout) {
+static int pick_bn(int nout, int x3) {
   if (nout <= 16) return 16;
   if (nout <= 32) return 32;
   if (nout <= 64) return 64;
+  if (!x3 && nout % 256 == 0) return 256;
   return 128;
 }
 
 size_t conv_ws_bytes(const ConvGeom& g, int nout, int x3) {
-  int bn = pick_bn(nout);
+  int bn = pick_bn(nout, x3);
   int npad = ((nout + bn - 1) / bn) * bn;
-  return (size_t)g.nslabs * npad * 64 * 2 * (x3 ? 2 : 1);
+  return (size_t)g.nslabs * npad * 64 * 2 * (x3 ? 2 : 1) + (size_t)g.nslabs * 16;
 }
 
-template <typename SrcT, int BN>
+template <typename SrcT, int BN, int MT, int NACC>
 static int launch_igemm(IgemmArgs& a, cudaStream_t s) {
   using S = Stage<SrcT>;
-  constexpr int STAGE_BYTES = (S::X3 ? 2 : 1) * (128 * 128 + BN * 128);
-  int budget = S::X3 ? 200 * 1024 : 100 * 1024;
-  int stages = budget / STAGE_BYTES;
-  if (stages > 6) stages = 6;
+  constexpr int STAGE_BYTES = (S::X3 ? 2 : 1) * (MT * 128 * 128 + BN * 128);
+  int stages = (200 * 1024) / STAGE_BYTES;
+  if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
-  if (stages > a.g.nslabs) stages = a.g.nslabs < 1 ? 1 : a.g.nslabs;
   a.stages = stages;
-  size_t smem = (size_t)stages * STAGE_BYTES + (2 * stages + 1) * 8 + 16 + 1024;
+  a.tiles_m = (int)((a.g.M + 128 * MT - 1) / (128 * MT));
+  size_t smem = (size_t)stages * STAGE_BYTES + (2 * stages + 2 * NACC) * 8 + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_igemm_kernel<SrcT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_igemm_kernel<SrcT, BN, MT, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  dim3 grid((unsigned)((a.g.M + 127) / 128), (unsigned)(a.Npad / BN));
-  conv_igemm_kernel<SrcT, BN><<<grid, 192, smem, s>>>(a);
+  long long ntiles = (long long)a.tiles_m * (a.Npad / BN);
+  int grid = ntiles < num_sms() ? (int)ntiles : num_sms();
+  conv_igemm_kernel<SrcT, BN, MT, NACC><<<grid, 32 * (8 * MT + 2), smem, s>>>(a);
   count_launch();
   return check_launch("conv_igemm");
 }
 
-template <typename SrcT>
-static int launch_igemm_bn(IgemmArgs& a, int bn, cudaStream_t s) {
+static int launch_igemm_f32(IgemmArgs& a, int bn, cudaStream_t s) {
   switch (bn) {
-    case 16: return launch_igemm<SrcT, 16>(a, s);
-    case 32: return launch_igemm<SrcT, 32>(a, s);
-    case 64: return launch_igemm<SrcT, 64>(a, s);
-    default: return launch_igemm<SrcT, 128>(a, s);
+    case 16: return launch_igemm<float, 16, 1, 2>(a, s);
+    case 32: return launch_igemm<float, 32, 1, 2>(a, s);
+    case 64: return launch_igemm<float, 64, 1, 2>(a, s);
+    default: return launch_igemm<float, 128, 1, 2>(a, s);
   }
 }
+static int launch_igemm_bf16(IgemmArgs& a, int bn, int mt, cudaStream_t s) {
+#define FGC_I(BN_) return mt == 2 ? launch_igemm<__nv_bfloat16, BN_, 2, 2>(a, s) : launch_igemm<__nv_bfloat16, BN_, 1, 2>(a, s)
+  switch (bn) {
+    case 16: FGC_I(16);
+    case 32: FGC_I(32);
+    case 64: FGC_I(64);
+    case 256: return mt == 2 ? launch_igemm<__nv_bfloat16, 256, 2, 1>(a, s) : launch_igemm<__nv_bfloat16, 256, 1, 2>(a, s);
+    default: FGC_I(128);
+  }
+#undef FGC_I
+}
+
+long long* g_trace = nullptr;
+int g_trace_cap = 0;
 
 // run y[M, nout] (=|+=) act(implicit_gemm(g) + bias) with weights w addressed as described in pack_weights_kernel
 int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride, long long n_stride,
                    long long base, int nout, const float* bias, int act, int accumulate, void* y, int y_dtype, void* ws,
                    cudaStream_t s) {
   FGC_REQUIRE(geom_fits(g), "conv: tensor too large for pixel packing");
+  FGC_REQUIRE(g.M < (1LL << 31), "conv: more than 2^31 output pixels");
   FGC_REQUIRE(ws != nullptr, "conv: workspace required");
   FGC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "conv: workspace must be 16-byte aligned");
   for (int i = 0; i < g.nsrc; i++)
     if (g.big[i]) FGC_REQUIRE((reinterpret_cast<uintptr_t>(g.src[i]) & 15) == 0, "conv: source %d not 16-byte aligned", i);
   const int x3 = src_dtype == FGC_F32;
-  const int bn = pick_bn(nout);
+  const int bn = pick_bn(nout, x3);
   const int npad = ((nout + bn - 1) / bn) * bn;
+  int4* tbl = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(ws) + (size_t)g.nslabs * npad * 64 * 2 * (x3 ? 2 : 1));
   {
     long long total = (long long)g.nslabs * npad * 8;
     int grid = (int)((total + 255) / 256);
     if (grid > num_sms() * 8) grid = num_sms() * 8;
-    pack_weights_kernel<<<grid, 256, 0, s>>>(g, w, tap_stride, k_stride, n_stride, base, nout, npad, x3, (__nv_bfloat16*)ws);
+    pack_weights_kernel<<<grid, 256, 0, s>>>(g, w, tap_stride, k_stride, n_stride, base, nout, npad, x3, (__nv_bfloat16*)ws, tbl);
     count_launch();
   }
   IgemmArgs a;
   a.g = g;
+  a.trace = g_trace;
+  a.trace_cap = g_trace_cap;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FGC_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   a.wp = (const __nv_bfloat16*)ws;
   a.wp_plane = (long long)g.nslabs * npad * 64;
   a.Npad = npad;
@@ -746,8 +1022,17 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
   a.y_dtype = y_dtype;
   a.vec_ok = (reinterpret_cast<uintptr_t>(y) & 15) == 0;
   a.stages = 0;
-  if (x3) return launch_igemm_bn<float>(a, bn, s);
-  return launch_igemm_bn<__nv_bfloat16>(a, bn, s);
+  a.depth = 1;
+  a.tbl = tbl;
+  a.tiles_m = 0;
+  a.any_small = 0;
+  for (int i = 0; i < g.nsrc; i++) a.any_small |= !g.big[i];
+  a.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
+  if (x3) return launch_igemm_f32(a, bn, s);
+  // two A tiles per CTA (each weight tile feeds 256 pixels) once there is enough work to fill the machine twice over
+  long long ctas2 = ((g.M + 255) / 256) * (npad / bn);
+  int mt = ctas2 >= (long long)num_sms() ? 2 : 1;
+  return launch_igemm_bf16(a, bn, mt, s);
 }
 
 template <typename SrcT, int BN>
@@ -760,6 +1045,10 @@ static int launch_wgrad(WgradArgs& a, cudaStream_t s) {
   if (stages > 6) stages = 6;
   if (stages < 2) stages = 2;
   a.stages = stages;
+  int depth = S::X3 ? 1 : stages - 1;
+  if (depth > 3) depth = 3;
+  if (depth < 1) depth = 1;
+  a.depth = depth;
   size_t smem = (size_t)stages * STAGE_BYTES + (2 * stages + 1) * 8 + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -781,6 +1070,13 @@ static int launch_wgrad(WgradArgs& a, cudaStream_t s) {
   return check_launch("conv_wgrad");
 }
 
+static int pick_bn_wgrad(int nout) {
+  if (nout <= 16) return 16;
+  if (nout <= 32) return 32;
+  if (nout <= 64) return 64;
+  return 128;
+}
+
 int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s) {
   FGC_REQUIRE(geom_fits(g), "wgrad: tensor too large for pixel packing");
   WgradArgs a;
@@ -789,7 +1085,8 @@ int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, in
   a.Cout = Cout;
   a.Cin_total = Cin_total;
   a.dw = dw;
-  int bn = pick_bn(Cout);
+  a.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
+  int bn = pick_bn_wgrad(Cout);
 #define FGC_W(T)                                          \
   switch (bn) {                                           \
     case 16: return launch_wgrad<T, 16>(a, s);            \

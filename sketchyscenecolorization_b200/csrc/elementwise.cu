@@ -60,38 +60,44 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
 // ======================================================================================================
 template <typename T, int V>
 __global__ void chan_stats_kernel(const T* __restrict__ x, long long M, int C, int rows_per_block, double* acc) {
+  extern __shared__ double sh_stats[];          // [2*C] block-level partial sums
   const int CV = C / V;
   const int lanes = blockDim.x / CV;          // row lanes per block
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
-  if (rl >= lanes) return;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh_stats[i] = 0.0;
+  __syncthreads();
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > M) r1 = M;
-  double s[V], ss[V];
+  if (rl < lanes) {
+    double s[V], ss[V];
 #pragma unroll
-  for (int i = 0; i < V; i++) s[i] = ss[i] = 0.0;
-  for (long long rb = r0 + rl; rb < r1; rb += (long long)lanes * 16) {
-    float ps[V], pss[V];
+    for (int i = 0; i < V; i++) s[i] = ss[i] = 0.0;
+    for (long long rb = r0 + rl; rb < r1; rb += (long long)lanes * 16) {
+      float ps[V], pss[V];
 #pragma unroll
-    for (int i = 0; i < V; i++) ps[i] = pss[i] = 0.f;
+      for (int i = 0; i < V; i++) ps[i] = pss[i] = 0.f;
 #pragma unroll 4
-    for (int j = 0; j < 16; j++) {
-      long long r = rb + (long long)j * lanes;
-      if (r < r1) {
-        float a[4];
-        ldv<T, V>(x + r * C + v * V, a);
+      for (int j = 0; j < 16; j++) {
+        long long r = rb + (long long)j * lanes;
+        if (r < r1) {
+          float a[4];
+          ldv<T, V>(x + r * C + v * V, a);
 #pragma unroll
-        for (int i = 0; i < V; i++) { ps[i] += a[i]; pss[i] += a[i] * a[i]; }
+          for (int i = 0; i < V; i++) { ps[i] += a[i]; pss[i] += a[i] * a[i]; }
+        }
       }
+#pragma unroll
+      for (int i = 0; i < V; i++) { s[i] += ps[i]; ss[i] += pss[i]; }
     }
 #pragma unroll
-    for (int i = 0; i < V; i++) { s[i] += ps[i]; ss[i] += pss[i]; }
+    for (int i = 0; i < V; i++) {
+      atomicAdd(&sh_stats[v * V + i], s[i]);
+      atomicAdd(&sh_stats[C + v * V + i], ss[i]);
+    }
   }
-#pragma unroll
-  for (int i = 0; i < V; i++) {
-    atomicAdd(&acc[v * V + i], s[i]);
-    atomicAdd(&acc[C + v * V + i], ss[i]);
-  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&acc[i], sh_stats[i]);
 }
 __global__ void chan_stats_finalize(const double* acc, long long M, int C, float* stats) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -655,7 +661,7 @@ int fgc_chan_stats(const void* x, int dtype, long long M, int C, double* acc, fl
   bool vec = vec4_ok(x, C, dtype);
   RowRed p = rowred_plan(C, vec, M, 1);
   FGC_DISPATCH_TV(dtype, vec, T, V,
-                  (chan_stats_kernel<T, V><<<p.nblk, p.threads, 0, s>>>((const T*)x, M, C, p.rows_per_block, acc)));
+                  (chan_stats_kernel<T, V><<<p.nblk, p.threads, 2 * C * sizeof(double), s>>>((const T*)x, M, C, p.rows_per_block, acc)));
   chan_stats_finalize<<<cdiv(C, 128), 128, 0, s>>>(acc, M, C, stats);
   count_launch(2);
   FGC_LAUNCH_CHECK("chan_stats");

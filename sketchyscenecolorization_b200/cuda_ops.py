@@ -421,3 +421,35 @@ class CudaOps(OpsBase):
                                      self._p(store.chunk_start), self._p(store.chunk_len), self._p(store.chunk_reg),
                                      store.chunk_start.numel(), float(lr_t), 0.9, 1e-8, 1 if add_reg_grad else 0, self._s()),
               "adam_step")
+
+
+def enable_op_timing(ops):
+    """Debug aid: wrap every operator of a CudaOps instance with CUDA events (synchronising after each call) and
+    collect per-operator totals in ops.op_times = {name: [calls, ms]}.  Used by scripts/op_breakdown.py only."""
+    import functools
+    ops.op_times = {}
+
+    def wrap(name, fn):
+        @functools.wraps(fn)
+        def inner(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            e1.synchronize()
+            key = name
+            if name in ("conv_fwd", "conv_dgrad", "conv_wgrad"):
+                key = name + ("/f32" if (a[0][0][0] if name != "conv_dgrad" else a[0]).dtype == torch.float32 else "")
+            t = ops.op_times.setdefault(key, [0, 0.0])
+            t[0] += 1
+            t[1] += e0.elapsed_time(e1)
+            return r
+        return inner
+
+    for name in dir(OpsBase):
+        if name.startswith("_"):
+            continue
+        fn = getattr(ops, name, None)
+        if callable(fn) and name in CudaOps.__dict__:
+            setattr(ops, name, wrap(name, fn))
+    return ops

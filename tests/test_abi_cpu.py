@@ -38,8 +38,8 @@ def test_workspace_query_is_host_only():
     arr = (ctypes.c_int * 3)(128, 3, 8)
     n_f32 = lib.fgc_conv2d_ws_bytes(arr, 3, 3, 128, 0)
     n_bf16 = lib.fgc_conv2d_ws_bytes(arr, 3, 3, 128, 1)
-    # slabs: 9*2 (128 ch) + 1 (27 -> 64) + 2 (72 -> 128) = 21; 128 rows x 64 x 2 B per slab and plane
-    assert n_bf16 == 21 * 128 * 64 * 2 + 256 and n_f32 == 2 * 21 * 128 * 64 * 2 + 256
+    # slabs: 9*2 (128 ch) + 1 (27 -> 64) + 2 (72 -> 128) = 21; 128 rows x 64 x 2 B per slab and plane, + 16 B/slab table
+    assert n_bf16 == 21 * 128 * 64 * 2 + 21 * 16 + 256 and n_f32 == 2 * 21 * 128 * 64 * 2 + 21 * 16 + 256
 
 
 def test_no_cpu_fallback_in_product():
