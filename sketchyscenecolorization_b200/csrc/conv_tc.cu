@@ -189,11 +189,11 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {
 // bf16 sources are copied with cp.async (LDGSTS, zero-fill for padding): no register staging, the caller keeps
 // several slabs in flight and fences/arrives when a group has landed.  fp32 sources go through registers for the
 // hi/lo split.
-template <typename SrcT, int ROWS>
+template <typename SrcT, int ROWS, int NP = kProducers>
 __device__ __forceinline__ void gather_big(uint8_t* s_hi, uint8_t* s_lo, const SrcT* __restrict__ src, int C, int c0, int ups,
                                            int H, int W, int stride, int dh, int dw, const uint32_t* pix, const PixDec pd, int tid) {
   using S = Stage<SrcT>;
-  constexpr int RPP = kProducers / S::CPR;   // rows per pass
+  constexpr int RPP = NP / S::CPR;   // rows per pass
   constexpr int NPASS = ROWS / RPP;
   const int j = tid % S::CPR, g = tid / S::CPR;
   const int cj = c0 + j * S::EPC;
@@ -246,11 +246,11 @@ __device__ __forceinline__ void gather_big(uint8_t* s_hi, uint8_t* s_lo, const S
 //   pk[i]    = oh | ow << 16 of the thread's i-th row (0xFFFFFFFF for rows past M: fails every bounds test)
 //   base4[i] = (n*H*W) / 4 of that row (pixel index of its image in a half-resolution source)
 //   m_g      = flattened pixel index of the thread's first row; rows are RPP apart
-template <int ROWS>
+template <int ROWS, int NP = kProducers>
 __device__ __forceinline__ void gather_big_fast(uint32_t sbase, const __nv_bfloat16* __restrict__ src, int C, int c0, int ups,
                                                 int H, int W, int dh, int dw, long long m_g, const uint32_t* pk,
                                                 const int* base4, int tid) {
-  constexpr int RPP = kProducers / 8, NPASS = ROWS / RPP;
+  constexpr int RPP = NP / 8, NPASS = ROWS / RPP;
   const int j = tid & 7, g = tid >> 3;
   const int cj = c0 + j * 8;
   const bool cvalid = cj < C;
@@ -277,12 +277,12 @@ __device__ __forceinline__ void gather_big_fast(uint32_t sbase, const __nv_bfloa
 }
 
 // "small" slab: flattened q = tap*C + c for q in [q0, q0+64) (zero beyond k*k*C).  128/ROWS threads per row.
-template <typename SrcT, int ROWS>
+template <typename SrcT, int ROWS, int NP = kProducers>
 __device__ __forceinline__ void gather_small(uint8_t* s_hi, uint8_t* s_lo, const SrcT* __restrict__ src, int C, int q0, int ups,
                                              int H, int W, int stride, int k, int pad_t, int pad_l, int sign,
                                              const uint32_t* pixrow, const PixDec pd, int tid) {
   using S = Stage<SrcT>;
-  constexpr int TPR = kProducers / ROWS;     // threads per row (1 or 2)
+  constexpr int TPR = NP / ROWS;     // threads per row (1, 2 or 4)
   constexpr int KPT = 64 / TPR;              // k elements per thread
   const int r = tid % ROWS, part = tid / ROWS;
   const uint32_t p = pixrow[0];
@@ -705,19 +705,27 @@ struct WgradArgs {
   int kslabs;         // ceil(M/64)
   int kslabs_per_cta;
   int stages;
-  int depth;
   int fast;           // stride-1 SAME geometry
+  int dbg;            // debug switches (env FGC_DBG): 4 = skip the MMAs, 8 = skip the loads
 };
 
-template <typename SrcT, int BN>
-__global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+// dW tile of one CTA: G blocks of 128 rows of the flattened (tap, ci) axis (= 2 K-slabs of the forward geometry each)
+// x BN output channels, reduced over a range of 64-pixel slabs.  All G blocks share the gy tile of a stage, so the
+// L2 -> smem traffic per MMA is (G*16 + BN/8) KB per G*4 instructions.  8 producer warps + 1 MMA warp; the
+// producers run the red.add epilogue when the reduction is done.
+template <typename SrcT, int BN, int G>
+__global__ void __launch_bounds__(288, 1) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
   using S = Stage<SrcT>;
+  constexpr int NP = 256;                            // producer threads
   constexpr int NBB = (BN + 63) / 64;                // 64-wide gy blocks
   constexpr int BLK = 64 * 128;                      // bytes of one [64 rows][128 B] block
-  constexpr int A_BYTES = 2 * BLK, B_BYTES = NBB * BLK;
-  constexpr int STAGE_BYTES = (S::X3 ? 2 : 1) * (A_BYTES + B_BYTES);
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int A_BYTES = G * 2 * BLK, B_BYTES = NBB * BLK;
+  constexpr int PLANES = S::X3 ? 2 : 1;
+  constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  constexpr int TMEM_COLS = G * BN <= 32 ? 32 : (G * BN <= 64 ? 64 : (G * BN <= 128 ? 128 : (G * BN <= 256 ? 256 : 512)));
+  static_assert(G * BN <= 512, "accumulators exceed TMEM");
   constexpr uint32_t IDESC = make_idesc(128, BN, 1, 1);
+  constexpr int MMA_WARP = NP / 32;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -727,7 +735,6 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const ConvGeom& g = a.g;
-  const int mt = blockIdx.x;                         // pair of slabs (2*mt, 2*mt+1) = 128 rows of dW
   const int n0 = blockIdx.y * BN;
   const int ks0 = blockIdx.z * a.kslabs_per_cta;
   const int ks1 = min(ks0 + a.kslabs_per_cta, a.kslabs);
@@ -736,30 +743,65 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
 
   if (tid == 0) {
     for (int s = 0; s < stages; s++) {
-      mbar_init(smem_u32(&bars[s]), kProducers);
+      mbar_init(smem_u32(&bars[s]), NP);
       mbar_init(smem_u32(&bars[stages + s]), 1);
     }
     mbar_init(smem_u32(&bars[2 * stages]), 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    constexpr int RPP = kProducers / S::CPR, NPASS = 64 / RPP;
-    SlabInfo si[2];
-    bool have[2];
+  // slab (= 64 rows of dW) descriptors of this CTA: block b holds slabs 2*(G*blockIdx.x + b) and +1
+  SlabInfo si[2 * G];
+  bool have[2 * G];
 #pragma unroll
-    for (int b = 0; b < 2; b++) {
-      have[b] = 2 * mt + b < g.nslabs;
-      si[b] = decode_slab(g, have[b] ? 2 * mt + b : 0);
-    }
+  for (int q = 0; q < 2 * G; q++) {
+    int sl = 2 * G * blockIdx.x + q;
+    have[q] = sl < g.nslabs;
+    si[q] = decode_slab(g, have[q] ? sl : 0);
+  }
+
+  if (warp < MMA_WARP) {
+    constexpr int RPP = NP / S::CPR, NPASS = 64 / RPP;
     const bool gy_vec = (a.Cout & 7) == 0 && a.Cout >= 8;
-    // fast path (bf16, stride-1 SAME): per-row (oh, ow) advanced incrementally by 64 pixels per iteration
     const bool fast = !S::X3 && a.fast;
+    bool all_async = fast && gy_vec;
+#pragma unroll
+    for (int q = 0; q < 2 * G; q++) all_async = all_async && (!have[q] || si[q].big);
+    // blocks that never receive data stay zero for the whole kernel
+    for (int st = 0; st < stages; st++) {
+#pragma unroll
+      for (int q = 0; q < 2 * G; q++) {
+        if (have[q]) continue;
+        uint8_t* d = smem + (size_t)st * STAGE_BYTES + q * BLK;
+        for (int i = tid; i < BLK / 16; i += NP) {
+          reinterpret_cast<uint4*>(d)[i] = make_uint4(0, 0, 0, 0);
+          if constexpr (S::X3) reinterpret_cast<uint4*>(d + A_BYTES)[i] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+    fence_proxy_async();
+    // loop-invariant per-block gather parameters, kept in registers (static indexing only)
+    const SrcT* bsrc[2 * G];
+    int bC[2 * G], bc0[2 * G], bups[2 * G], bdh[2 * G], bdw[2 * G];
+    bool bbig[2 * G], bhave[2 * G];
+#pragma unroll
+    for (int q = 0; q < 2 * G; q++) {
+      const SlabInfo sq = si[q];
+      bhave[q] = have[q];
+      bbig[q] = sq.big != 0;
+      bsrc[q] = reinterpret_cast<const SrcT*>(g.src[sq.s]);
+      bC[q] = g.C[sq.s];
+      bups[q] = g.ups[sq.s];
+      bc0[q] = sq.big ? sq.c0 : sq.q0;
+      bdh[q] = sq.tap / g.k - g.pad_t;
+      bdw[q] = sq.tap % g.k - g.pad_l;
+    }
+    // fast path row state: (oh, ow) of rows tid/8 + RPP*i, advanced by 64 pixels per iteration
     int roh[NPASS], row_[NPASS];
     const int d64 = 64 / g.OW, r64 = 64 % g.OW;
     if (fast) {
@@ -776,7 +818,7 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
       mbar_wait(smem_u32(&bars[stages + st]), ph ^ 1);
       uint8_t* sa_hi = smem + (size_t)st * STAGE_BYTES;
       uint8_t* sa_lo = sa_hi + A_BYTES;
-      uint8_t* sb_hi = sa_hi + (S::X3 ? 2 : 1) * A_BYTES;
+      uint8_t* sb_hi = sa_hi + PLANES * A_BYTES;
       uint8_t* sb_lo = sb_hi + B_BYTES;
       const long long mbase = (long long)(ks0 + it) * 64;
       uint32_t pix[NPASS];
@@ -786,7 +828,7 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < NPASS; i++) pix[i] = pix_pack(mbase + gq + RPP * i, g);
       }
-      if (!fast || !gy_vec || !(have[0] && si[0].big) || !(!have[1] || si[1].big)) pixrow = pix_pack(mbase + (tid & 63), g);
+      if (!all_async) pixrow = pix_pack(mbase + (tid & 63), g);
       uint32_t pk[NPASS];
       int base4[NPASS];
       const long long m_g = mbase + (tid >> 3);
@@ -797,7 +839,6 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
             long long m = m_g + RPP * i;
             pk[i] = m < g.M ? ((uint32_t)roh[i] | ((uint32_t)row_[i] << 16)) : 0xFFFFFFFFu;
             base4[i] = (int)((m - (long long)roh[i] * g.OW - row_[i]) >> 2);
-            // advance to the next 64-pixel slab
             row_[i] += r64;
             roh[i] += d64;
             if (row_[i] >= g.OW) { row_[i] -= g.OW; roh[i]++; }
@@ -805,90 +846,81 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
           }
         }
       }
-      // A': x rows (tap-shifted), two 64-wide blocks of the flattened (tap, ci) axis
+      // A': x rows (tap-shifted), 2*G blocks of 64 rows of the flattened (tap, ci) axis
 #pragma unroll
-      for (int b = 0; b < 2; b++) {
-        uint8_t* dh_ = sa_hi + b * BLK;
-        uint8_t* dl_ = sa_lo + b * BLK;
-        if (!have[b]) {
-          for (int i = tid; i < BLK / 16; i += kProducers) {
-            reinterpret_cast<uint4*>(dh_)[i] = make_uint4(0, 0, 0, 0);
-            if constexpr (S::X3) reinterpret_cast<uint4*>(dl_)[i] = make_uint4(0, 0, 0, 0);
-          }
-          continue;
-        }
-        const SrcT* src = reinterpret_cast<const SrcT*>(g.src[si[b].s]);
-        if (si[b].big) {
-          int kh = si[b].tap / g.k, kw = si[b].tap % g.k;
+      for (int q = 0; q < 2 * G; q++) {
+        if (!bhave[q] || (a.dbg & 8)) continue;
+        uint8_t* dh_ = sa_hi + q * BLK;
+        uint8_t* dl_ = sa_lo + q * BLK;
+        if (bbig[q]) {
           bool done = false;
           if constexpr (!S::X3) {
             if (fast) {
-              gather_big_fast<64>(smem_u32(dh_), src, g.C[si[b].s], si[b].c0, g.ups[si[b].s], g.H, g.W, kh - g.pad_t, kw - g.pad_l,
-                                  m_g, pk, base4, tid);
+              gather_big_fast<64, NP>(smem_u32(dh_), bsrc[q], bC[q], bc0[q], bups[q], g.H, g.W, bdh[q], bdw[q], m_g, pk, base4, tid);
               done = true;
             }
           }
           if (!done)
-            gather_big<SrcT, 64>(dh_, dl_, src, g.C[si[b].s], si[b].c0, g.ups[si[b].s], g.H, g.W, g.stride, kh - g.pad_t,
-                                 kw - g.pad_l, pix, pd, tid);
+            gather_big<SrcT, 64, NP>(dh_, dl_, bsrc[q], bC[q], bc0[q], bups[q], g.H, g.W, g.stride, bdh[q], bdw[q], pix, pd, tid);
         } else {
-          gather_small<SrcT, 64>(dh_, dl_, src, g.C[si[b].s], si[b].q0, g.ups[si[b].s], g.H, g.W, g.stride, g.k, g.pad_t,
-                                 g.pad_l, 1, &pixrow, pd, tid);
+          gather_small<SrcT, 64, NP>(dh_, dl_, bsrc[q], bC[q], bc0[q], bups[q], g.H, g.W, g.stride, g.k, g.pad_t, g.pad_l, 1,
+                                     &pixrow, pd, tid);
         }
       }
       // B': gy rows, NBB blocks of 64 output channels
 #pragma unroll
       for (int b = 0; b < NBB; b++) {
         int c0 = n0 + b * 64;
+        if (a.dbg & 8) continue;
         if (gy_vec) {
           bool done = false;
           if constexpr (!S::X3) {
             if (fast) {
-              gather_big_fast<64>(smem_u32(sb_hi + b * BLK), reinterpret_cast<const __nv_bfloat16*>(a.gy), a.Cout, c0, 0, g.OH, g.OW,
-                                  0, 0, m_g, pk, base4, tid);
+              gather_big_fast<64, NP>(smem_u32(sb_hi + b * BLK), reinterpret_cast<const __nv_bfloat16*>(a.gy), a.Cout, c0, 0, g.OH,
+                                      g.OW, 0, 0, m_g, pk, base4, tid);
               done = true;
             }
           }
           if (!done)
-            gather_big<SrcT, 64>(sb_hi + b * BLK, sb_lo + b * BLK, reinterpret_cast<const SrcT*>(a.gy), a.Cout, c0, 0, g.OH, g.OW, 1,
-                                 0, 0, pix, pd, tid);
+            gather_big<SrcT, 64, NP>(sb_hi + b * BLK, sb_lo + b * BLK, reinterpret_cast<const SrcT*>(a.gy), a.Cout, c0, 0, g.OH,
+                                     g.OW, 1, 0, 0, pix, pd, tid);
         } else {  // odd channel counts (1, 3, 25): flattened path with k=1 semantics
-          gather_small<SrcT, 64>(sb_hi + b * BLK, sb_lo + b * BLK, reinterpret_cast<const SrcT*>(a.gy), a.Cout, c0, 0, g.OH, g.OW,
-                                 1, 1, 0, 0, 1, &pixrow, pd, tid);
+          gather_small<SrcT, 64, NP>(sb_hi + b * BLK, sb_lo + b * BLK, reinterpret_cast<const SrcT*>(a.gy), a.Cout, c0, 0, g.OH,
+                                     g.OW, 1, 1, 0, 0, 1, &pixrow, pd, tid);
         }
       }
-      // st.shared parts (small / fp32 / zero blocks) need the cross-proxy fence; cp.async parts are tracked by the
-      // barrier itself.  One arrival per thread either way.
-      bool any_sync = S::X3 || !gy_vec;
-#pragma unroll
-      for (int b = 0; b < 2; b++) any_sync = any_sync || !have[b] || !si[b].big;
-      if (any_sync) fence_proxy_async();
+      // st.shared parts (small / fp32 blocks) need the cross-proxy fence; cp.async parts are tracked by the barrier.
+      if (!all_async) fence_proxy_async();
       if (!S::X3) cp_async_mbar_arrive_noinc(smem_u32(&bars[st]));
       else mbar_arrive(smem_u32(&bars[st]));
     }
-    // epilogue: lane = row of dW (flattened (tap, ci)), columns = co
+    // epilogue: TMEM lane = row of a dW block, columns = co.  Warp w reads lane quarter w&3 of blocks w>>2, +2, ...
     if (niter > 0) {
       mbar_wait(smem_u32(&bars[2 * stages]), 0);
       tc_fence_after();
-      const int row = warp * 32 + lane;
-      const int b = row >> 6, kk = row & 63;
-      int tap = 0, cg = 0;
-      bool rvalid = have[b] && slab_elem(g, si[b], kk, &tap, &cg);
-      float* dwrow = a.dw + ((long long)tap * a.Cin_total + cg) * a.Cout;
+      const int quarter = warp & 3;
+      for (int b = warp >> 2; b < G; b += 2) {
+        const int row = quarter * 32 + lane;
+        const int q = 2 * b + (row >> 6), kk = row & 63;
+        int tap = 0, cg = 0;
+        bool rvalid = have[q] && slab_elem(g, si[q], kk, &tap, &cg);
+        float* dwrow = a.dw + ((long long)tap * a.Cin_total + cg) * a.Cout;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-        if (!rvalid) continue;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * BN + c0), r);
+          if (!rvalid) continue;
 #pragma unroll
-        for (int q = 0; q < 32; q++) {
-          int n = n0 + c0 + q;
-          if (n < a.Cout) atomicAdd(dwrow + n, __uint_as_float(r[q]));
+          for (int e = 0; e < 32; e++) {
+            int n = n0 + c0 + e;
+            if (n < a.Cout) atomicAdd(dwrow + n, __uint_as_float(r[e]));
+          }
         }
       }
       tc_fence_before();
     }
-  } else if (warp == 4) {
+  } else {
+    // ===================== MMA issuer =====================
     for (int it = 0; it < niter; it++) {
       const int st = it % stages;
       const uint32_t ph = (it / stages) & 1;
@@ -897,17 +929,24 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
       if (lane == 0) {
         const uint32_t sa_hi = smem_u32(smem + (size_t)st * STAGE_BYTES);
         const uint32_t sa_lo = sa_hi + A_BYTES;
-        const uint32_t sb_hi = sa_hi + (S::X3 ? 2 : 1) * A_BYTES;
+        const uint32_t sb_hi = sa_hi + PLANES * A_BYTES;
         const uint32_t sb_lo = sb_hi + B_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) {      // 16 pixel rows per MMA = 2 atoms of 1024 B
-          const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
-          const uint64_t da_hi = desc_mnmajor(sa_hi + kk * 2048, BLK, 1024), db_hi = desc_mnmajor(sb_hi + kk * 2048, BLK, 1024);
-          umma_bf16(tmem_base, da_hi, db_hi, IDESC, acc);
-          if constexpr (S::X3) {
-            const uint64_t da_lo = desc_mnmajor(sa_lo + kk * 2048, BLK, 1024), db_lo = desc_mnmajor(sb_lo + kk * 2048, BLK, 1024);
-            umma_bf16(tmem_base, da_hi, db_lo, IDESC, 1u);
-            umma_bf16(tmem_base, da_lo, db_hi, IDESC, 1u);
+        for (int b = 0; b < G; b++) {
+          if (!have[2 * b] || (a.dbg & 4)) continue;
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {      // 16 pixel rows per MMA = 2 atoms of 1024 B
+            const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(b * BN);
+            const uint64_t da_hi = desc_mnmajor(sa_hi + b * 2 * BLK + kk * 2048, BLK, 1024);
+            const uint64_t db_hi = desc_mnmajor(sb_hi + kk * 2048, BLK, 1024);
+            umma_bf16(d_tmem, da_hi, db_hi, IDESC, acc);
+            if constexpr (S::X3) {
+              const uint64_t da_lo = desc_mnmajor(sa_lo + b * 2 * BLK + kk * 2048, BLK, 1024);
+              const uint64_t db_lo = desc_mnmajor(sb_lo + kk * 2048, BLK, 1024);
+              umma_bf16(d_tmem, da_hi, db_lo, IDESC, 1u);
+              umma_bf16(d_tmem, da_lo, db_hi, IDESC, 1u);
+            }
           }
         }
         umma_commit(smem_u32(&bars[stages + st]));
@@ -916,8 +955,9 @@ __global__ void __launch_bounds__(160) conv_wgrad_kernel(const __grid_constant__
       __syncwarp();
     }
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -1035,45 +1075,42 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
   return launch_igemm_bf16(a, bn, mt, s);
 }
 
-template <typename SrcT, int BN>
+template <typename SrcT, int BN, int G>
 static int launch_wgrad(WgradArgs& a, cudaStream_t s) {
   using S = Stage<SrcT>;
   constexpr int NBB = (BN + 63) / 64;
-  constexpr int STAGE_BYTES = (S::X3 ? 2 : 1) * (2 + NBB) * 64 * 128;
-  int budget = S::X3 ? 200 * 1024 : 100 * 1024;
-  int stages = budget / STAGE_BYTES;
+  constexpr int STAGE_BYTES = (S::X3 ? 2 : 1) * (2 * G + NBB) * 64 * 128;
+  int stages = (200 * 1024) / STAGE_BYTES;
   if (stages > 6) stages = 6;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  int depth = S::X3 ? 1 : stages - 1;
-  if (depth > 3) depth = 3;
-  if (depth < 1) depth = 1;
-  a.depth = depth;
   size_t smem = (size_t)stages * STAGE_BYTES + (2 * stages + 1) * 8 + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_wgrad_kernel<SrcT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_wgrad_kernel<SrcT, BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  int mtiles = (a.g.nslabs + 1) / 2;
+  int groups = (a.g.nslabs + 2 * G - 1) / (2 * G);
   int ntiles = (a.Cout + BN - 1) / BN;
   a.kslabs = (int)((a.g.M + 63) / 64);
-  long long want = (long long)num_sms() * 4;
-  int splits = (int)((want + (long long)mtiles * ntiles - 1) / ((long long)mtiles * ntiles));
+  // one CTA per SM: split the pixel reduction so that the grid fills the machine once (or twice for short reductions)
+  long long want = num_sms();
+  int splits = (int)(want / ((long long)groups * ntiles));       // floor: never spill a few CTAs into a second wave
   if (splits < 1) splits = 1;
   if (splits > a.kslabs) splits = a.kslabs;
   a.kslabs_per_cta = (a.kslabs + splits - 1) / splits;
   splits = (a.kslabs + a.kslabs_per_cta - 1) / a.kslabs_per_cta;
-  dim3 grid(mtiles, ntiles, splits);
-  conv_wgrad_kernel<SrcT, BN><<<grid, 160, smem, s>>>(a);
+  dim3 grid(groups, ntiles, splits);
+  conv_wgrad_kernel<SrcT, BN, G><<<grid, 288, smem, s>>>(a);
   count_launch();
   return check_launch("conv_wgrad");
 }
 
-static int pick_bn_wgrad(int nout) {
+static int pick_bn_wgrad(int nout, int x3) {
   if (nout <= 16) return 16;
   if (nout <= 32) return 32;
   if (nout <= 64) return 64;
+  if (!x3 && nout % 256 == 0) return 256;
   return 128;
 }
 
@@ -1086,16 +1123,24 @@ int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, in
   a.Cin_total = Cin_total;
   a.dw = dw;
   a.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
-  int bn = pick_bn_wgrad(Cout);
-#define FGC_W(T)                                          \
-  switch (bn) {                                           \
-    case 16: return launch_wgrad<T, 16>(a, s);            \
-    case 32: return launch_wgrad<T, 32>(a, s);            \
-    case 64: return launch_wgrad<T, 64>(a, s);            \
-    default: return launch_wgrad<T, 128>(a, s);           \
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FGC_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
+  const int x3 = src_dtype == FGC_F32;
+  int bn = pick_bn_wgrad(Cout, x3);
+  if (x3) {
+    switch (bn) {
+      case 16: return launch_wgrad<float, 16, 1>(a, s);
+      case 32: return launch_wgrad<float, 32, 1>(a, s);
+      case 64: return launch_wgrad<float, 64, 1>(a, s);
+      default: return launch_wgrad<float, 128, 1>(a, s);
+    }
   }
-  if (src_dtype == FGC_F32) { FGC_W(float) } else { FGC_W(__nv_bfloat16) }
-#undef FGC_W
+  switch (bn) {
+    case 16: return launch_wgrad<__nv_bfloat16, 16, 3>(a, s);
+    case 32: return launch_wgrad<__nv_bfloat16, 32, 3>(a, s);
+    case 64: return launch_wgrad<__nv_bfloat16, 64, 3>(a, s);
+    case 256: return launch_wgrad<__nv_bfloat16, 256, 2>(a, s);
+    default: return launch_wgrad<__nv_bfloat16, 128, 3>(a, s);
+  }
 }
 
 }  // namespace fgc
