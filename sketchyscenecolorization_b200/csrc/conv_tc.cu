@@ -68,6 +68,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// 4-D tiled TMA load (tensor map in kernel-parameter space): box lands in smem with the map's 128-byte swizzle,
+// out-of-bounds elements (negative / past-the-end coordinates: the SAME padding of the convolution) are zero filled
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -707,6 +718,12 @@ struct WgradArgs {
   int stages;
   int fast;           // stride-1 SAME geometry
   int dbg;            // debug switches (env FGC_DBG): 4 = skip the MMAs, 8 = skip the loads
+  // tiled mode (bf16): a K-slab is a tw x th pixel rectangle of one image and TMA-able blocks are fetched by tensor TMA
+  int tiled, tw_log2, th, tiles_w, tiles_per_img;
+  int tma_mask;       // bit s: source s is loaded by TMA
+  int tma_gy;         // gy blocks are loaded by TMA
+  CUtensorMap tm_src[kMaxSrc];
+  CUtensorMap tm_gy;
 };
 
 // dW tile of one CTA: G blocks of 128 rows of the flattened (tap, ci) axis (= 2 K-slabs of the forward geometry each)
@@ -714,7 +731,7 @@ struct WgradArgs {
 // L2 -> smem traffic per MMA is (G*16 + BN/8) KB per G*4 instructions.  8 producer warps + 1 MMA warp; the
 // producers run the red.add epilogue when the reduction is done.
 template <typename SrcT, int BN, int G>
-__global__ void __launch_bounds__(288, 1) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+__global__ void __launch_bounds__(320, 1) conv_wgrad_kernel(const __grid_constant__ WgradArgs a) {
   using S = Stage<SrcT>;
   constexpr int NP = 256;                            // producer threads
   constexpr int NBB = (BN + 63) / 64;                // 64-wide gy blocks
@@ -725,7 +742,7 @@ __global__ void __launch_bounds__(288, 1) conv_wgrad_kernel(const __grid_constan
   constexpr int TMEM_COLS = G * BN <= 32 ? 32 : (G * BN <= 64 ? 64 : (G * BN <= 128 ? 128 : (G * BN <= 256 ? 256 : 512)));
   static_assert(G * BN <= 512, "accumulators exceed TMEM");
   constexpr uint32_t IDESC = make_idesc(128, BN, 1, 1);
-  constexpr int MMA_WARP = NP / 32;
+  constexpr int MMA_WARP = NP / 32, TMA_WARP = NP / 32 + 1;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -736,6 +753,7 @@ __global__ void __launch_bounds__(288, 1) conv_wgrad_kernel(const __grid_constan
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const ConvGeom& g = a.g;
   const int n0 = blockIdx.y * BN;
+  const bool tiled = !S::X3 && a.tiled;
   const int ks0 = blockIdx.z * a.kslabs_per_cta;
   const int ks1 = min(ks0 + a.kslabs_per_cta, a.kslabs);
   const int niter = ks1 - ks0;
@@ -743,7 +761,7 @@ __global__ void __launch_bounds__(288, 1) conv_wgrad_kernel(const __grid_constan
 
   if (tid == 0) {
     for (int s = 0; s < stages; s++) {
-      mbar_init(smem_u32(&bars[s]), NP);
+      mbar_init(smem_u32(&bars[s]), NP + (tiled ? 1 : 0));   // producers (+ the TMA issuer with its tx bytes)
       mbar_init(smem_u32(&bars[stages + s]), 1);
     }
     mbar_init(smem_u32(&bars[2 * stages]), 1);
@@ -764,6 +782,10 @@ __global__ void __launch_bounds__(288, 1) conv_wgrad_kernel(const __grid_constan
     have[q] = sl < g.nslabs;
     si[q] = decode_slab(g, have[q] ? sl : 0);
   }
+  bool btma[2 * G];        // block is fetched by the TMA warp
+#pragma unroll
+  for (int q = 0; q < 2 * G; q++) btma[q] = tiled && have[q] && si[q].big && ((a.tma_mask >> si[q].s) & 1);
+  const bool gy_tma = tiled && a.tma_gy;
 
   if (warp < MMA_WARP) {
     constexpr int RPP = NP / S::CPR, NPASS = 64 / RPP;
@@ -772,6 +794,8 @@ __global__ void __launch_bounds__(288, 1) conv_wgrad_kernel(const __grid_constan
     bool all_async = fast && gy_vec;
 #pragma unroll
     for (int q = 0; q < 2 * G; q++) all_async = all_async && (!have[q] || si[q].big);
+    const int hw4 = (g.OH * g.OW) >> 2;
+    const int twm = (1 << a.tw_log2) - 1;
     // blocks that never receive data stay zero for the whole kernel
     for (int st = 0; st < stages; st++) {
 #pragma unroll
@@ -823,33 +847,53 @@ __global__ void __launch_bounds__(288, 1) conv_wgrad_kernel(const __grid_constan
       const long long mbase = (long long)(ks0 + it) * 64;
       uint32_t pix[NPASS];
       uint32_t pixrow = 0;
-      if (!fast) {
-        const int gq = tid / S::CPR;
-#pragma unroll
-        for (int i = 0; i < NPASS; i++) pix[i] = pix_pack(mbase + gq + RPP * i, g);
-      }
-      if (!all_async) pixrow = pix_pack(mbase + (tid & 63), g);
       uint32_t pk[NPASS];
       int base4[NPASS];
       const long long m_g = mbase + (tid >> 3);
-      if constexpr (!S::X3) {
-        if (fast) {
+      if (tiled) {
+        // slab = tile (n, h0.., w0..) of tw x th pixels; row r of the slab is pixel (h0 + r / tw, w0 + r % tw)
+        const int ks = ks0 + it;
+        const int n = ks / a.tiles_per_img, rr = ks - n * a.tiles_per_img;
+        const int ty = rr / a.tiles_w, tx = rr - ty * a.tiles_w;
+        const int h0 = ty * a.th, w0 = tx << a.tw_log2;
 #pragma unroll
-          for (int i = 0; i < NPASS; i++) {
-            long long m = m_g + RPP * i;
-            pk[i] = m < g.M ? ((uint32_t)roh[i] | ((uint32_t)row_[i] << 16)) : 0xFFFFFFFFu;
-            base4[i] = (int)((m - (long long)roh[i] * g.OW - row_[i]) >> 2);
-            row_[i] += r64;
-            roh[i] += d64;
-            if (row_[i] >= g.OW) { row_[i] -= g.OW; roh[i]++; }
-            while (roh[i] >= g.OH) roh[i] -= g.OH;
+        for (int i = 0; i < NPASS; i++) {
+          const int r = (tid >> 3) + RPP * i;
+          const uint32_t oh = h0 + (r >> a.tw_log2), ow = w0 + (r & twm);
+          pk[i] = oh | (ow << 16);
+          base4[i] = n * hw4;
+          pix[i] = ((uint32_t)n << (g.ow_bits + g.oh_bits)) | (oh << g.ow_bits) | ow;
+        }
+        if (!all_async) {
+          const int r = tid & 63;
+          pixrow = ((uint32_t)n << (g.ow_bits + g.oh_bits)) | ((uint32_t)(h0 + (r >> a.tw_log2)) << g.ow_bits) | (uint32_t)(w0 + (r & twm));
+        }
+      } else {
+        if (!fast) {
+          const int gq = tid / S::CPR;
+#pragma unroll
+          for (int i = 0; i < NPASS; i++) pix[i] = pix_pack(mbase + gq + RPP * i, g);
+        }
+        if (!all_async) pixrow = pix_pack(mbase + (tid & 63), g);
+        if constexpr (!S::X3) {
+          if (fast) {
+#pragma unroll
+            for (int i = 0; i < NPASS; i++) {
+              long long m = m_g + RPP * i;
+              pk[i] = m < g.M ? ((uint32_t)roh[i] | ((uint32_t)row_[i] << 16)) : 0xFFFFFFFFu;
+              base4[i] = (int)((m - (long long)roh[i] * g.OW - row_[i]) >> 2);
+              row_[i] += r64;
+              roh[i] += d64;
+              if (row_[i] >= g.OW) { row_[i] -= g.OW; roh[i]++; }
+              while (roh[i] >= g.OH) roh[i] -= g.OH;
+            }
           }
         }
       }
       // A': x rows (tap-shifted), 2*G blocks of 64 rows of the flattened (tap, ci) axis
 #pragma unroll
       for (int q = 0; q < 2 * G; q++) {
-        if (!bhave[q] || (a.dbg & 8)) continue;
+        if (!bhave[q] || btma[q] || (a.dbg & 8)) continue;
         uint8_t* dh_ = sa_hi + q * BLK;
         uint8_t* dl_ = sa_lo + q * BLK;
         if (bbig[q]) {
@@ -871,7 +915,7 @@ __global__ void __launch_bounds__(288, 1) conv_wgrad_kernel(const __grid_constan
 #pragma unroll
       for (int b = 0; b < NBB; b++) {
         int c0 = n0 + b * 64;
-        if (a.dbg & 8) continue;
+        if (gy_tma || (a.dbg & 8)) continue;
         if (gy_vec) {
           bool done = false;
           if constexpr (!S::X3) {
@@ -918,6 +962,41 @@ __global__ void __launch_bounds__(288, 1) conv_wgrad_kernel(const __grid_constan
         }
       }
       tc_fence_before();
+    }
+  } else if (warp == TMA_WARP) {
+    // ===================== TMA issuer (tiled mode): one tensor-map box per block and stage =====================
+    if (tiled && lane == 0) {
+      int ntma = gy_tma ? NBB : 0;
+#pragma unroll
+      for (int q = 0; q < 2 * G; q++) ntma += btma[q] ? 1 : 0;
+      for (int s2 = 0; s2 < g.nsrc; s2++)
+        if ((a.tma_mask >> s2) & 1) tma_prefetch_desc(&a.tm_src[s2]);
+      if (gy_tma) tma_prefetch_desc(&a.tm_gy);
+      for (int it = 0; it < niter; it++) {
+        const int st = it % stages;
+        const uint32_t ph = (it / stages) & 1;
+        mbar_wait(smem_u32(&bars[stages + st]), ph ^ 1);
+        const int ks = ks0 + it;
+        const int n = ks / a.tiles_per_img, rr = ks - n * a.tiles_per_img;
+        const int ty = rr / a.tiles_w, tx = rr - ty * a.tiles_w;
+        const int h0 = ty * a.th, w0 = tx << a.tw_log2;
+        const uint32_t sa = smem_u32(smem + (size_t)st * STAGE_BYTES);
+        const uint32_t sb = sa + PLANES * A_BYTES;
+        const uint32_t bar = smem_u32(&bars[st]);
+        mbar_arrive_expect_tx(bar, (uint32_t)ntma * BLK);
+        {
+#pragma unroll
+          for (int q = 0; q < 2 * G; q++) {
+            if (!btma[q]) continue;
+            const int kh = si[q].tap / g.k, kw = si[q].tap % g.k;
+            tma_load_4d(sa + q * BLK, &a.tm_src[si[q].s], si[q].c0, w0 + kw - g.pad_l, h0 + kh - g.pad_t, n, bar);
+          }
+          if (gy_tma) {
+#pragma unroll
+            for (int b = 0; b < NBB; b++) tma_load_4d(sb + b * BLK, &a.tm_gy, n0 + b * 64, w0, h0, n, bar);
+          }
+        }
+      }
     }
   } else {
     // ===================== MMA issuer =====================
@@ -1075,6 +1154,73 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
   return launch_igemm_bf16(a, bn, mt, s);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+// NHWC bf16 tensor [N,H,W,C] as a 4-D map (C, W, H, N) with a {64, tw, th, 1} box and 128-byte swizzle
+static bool make_tmap_nhwc(CUtensorMap* out, const void* ptr, int C, int W, int H, int N, int tw, int th) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// tiled mode for the weight gradient: pick the 64-pixel rectangle and build the tensor maps
+static void wgrad_setup_tiled(WgradArgs& a, int x3) {
+  a.tiled = 0;
+  a.tma_mask = 0;
+  a.tma_gy = 0;
+  a.tw_log2 = a.th = a.tiles_w = a.tiles_per_img = 0;
+  const ConvGeom& g = a.g;
+  if (x3 || !a.fast) return;
+  const char* e = getenv("FGC_NO_TMA");
+  if (e && atoi(e)) return;
+  int tw = 64;
+  while (tw > 1 && g.W % tw) tw >>= 1;
+  int th = 64 / tw;
+  if (tw < 8 || g.H % th) return;
+  bool any = false;
+  for (int s = 0; s < g.nsrc; s++) {
+    if (!g.big[s]) continue;
+    if (g.ups[s]) continue;                    // read through the x2 upsample: gathered by the producer warps
+    if (!make_tmap_nhwc(&a.tm_src[s], g.src[s], g.C[s], g.W, g.H, g.N, tw, th)) return;
+    a.tma_mask |= 1 << s;
+    any = true;
+  }
+  if ((a.Cout & 7) == 0 && a.Cout >= 8 && (reinterpret_cast<uintptr_t>(a.gy) & 15) == 0) {
+    if (!make_tmap_nhwc(&a.tm_gy, a.gy, a.Cout, g.OW, g.OH, g.N, tw, th)) return;
+    a.tma_gy = 1;
+    any = true;
+  }
+  if (!any) { a.tma_mask = 0; a.tma_gy = 0; return; }
+  a.tiled = 1;
+  a.tw_log2 = 0;
+  while ((1 << a.tw_log2) < tw) a.tw_log2++;
+  a.th = th;
+  a.tiles_w = g.W / tw;
+  a.tiles_per_img = a.tiles_w * (g.H / th);
+}
+
 template <typename SrcT, int BN, int G>
 static int launch_wgrad(WgradArgs& a, cudaStream_t s) {
   using S = Stage<SrcT>;
@@ -1092,7 +1238,7 @@ static int launch_wgrad(WgradArgs& a, cudaStream_t s) {
   }
   int groups = (a.g.nslabs + 2 * G - 1) / (2 * G);
   int ntiles = (a.Cout + BN - 1) / BN;
-  a.kslabs = (int)((a.g.M + 63) / 64);
+  a.kslabs = a.tiled ? a.g.N * a.tiles_per_img : (int)((a.g.M + 63) / 64);
   // one CTA per SM: split the pixel reduction so that the grid fills the machine once (or twice for short reductions)
   long long want = num_sms();
   int splits = (int)(want / ((long long)groups * ntiles));       // floor: never spill a few CTAs into a second wave
@@ -1101,7 +1247,7 @@ static int launch_wgrad(WgradArgs& a, cudaStream_t s) {
   a.kslabs_per_cta = (a.kslabs + splits - 1) / splits;
   splits = (a.kslabs + a.kslabs_per_cta - 1) / a.kslabs_per_cta;
   dim3 grid(groups, ntiles, splits);
-  conv_wgrad_kernel<SrcT, BN, G><<<grid, 288, smem, s>>>(a);
+  conv_wgrad_kernel<SrcT, BN, G><<<grid, 320, smem, s>>>(a);
   count_launch();
   return check_launch("conv_wgrad");
 }
@@ -1125,6 +1271,7 @@ int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, in
   a.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FGC_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   const int x3 = src_dtype == FGC_F32;
+  wgrad_setup_tiled(a, x3);
   int bn = pick_bn_wgrad(Cout, x3);
   if (x3) {
     switch (bn) {
