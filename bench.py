@@ -204,7 +204,9 @@ def run_product(args):
     ops = CudaOps(dev, torch.bfloat16)          # training mode: bf16 NHWC activations, fp32 master weights / stats / Adam
     model = FgColorModel(ops, dev, size=SIZE, H=H, W=W)
     model.initialize(seed=0)                    # identical on every rank (reference initialisers)
-    tr = FgColorTrainer(model, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=pg, world_size=world)
+    graphs = not args.no_graphs
+    tr = FgColorTrainer(model, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=pg, world_size=world,
+                        use_cuda_graphs=graphs)
 
     hostA, hostB = synth_batch(BS, 1234 + rank), synth_batch(BS, 4321 + rank)
     pin = lambda b: {k: v.pin_memory() for k, v in b.items()}  # noqa: E731
@@ -212,7 +214,8 @@ def run_product(args):
 
     def to_dev(hb):
         d = {k: v.to(dev, non_blocking=True) for k, v in hb.items() if k != "text"}
-        d["text"] = hb["text"].numpy()          # caption ids: the host copy drives the pad-skip control flow
+        # caption ids: eager mode keeps a host copy (it drives the pad-skip control flow); graph mode keeps them on the device
+        d["text"] = hb["text"].to(dev, non_blocking=True) if graphs else hb["text"].numpy()
         return d
 
     def h2d_bytes(hb, keys):
@@ -232,7 +235,7 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(args.warmup + (2 if graphs else 0)):      # +2 untimed set-up steps: eager run, then graph capture
         iteration(devA, devB)
     barrier()
     sampler = ClockSampler(local)
@@ -241,11 +244,15 @@ def run_product(args):
     n0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         ld, lg = iteration(devA, devB)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps      # time to ENQUEUE one step (no sync inside)
     e1.record()
     barrier()
     launches = ops.launch_count() - n0
+    if graphs:          # launches are recorded once at capture; every replay re-issues all of them
+        launches = args.steps * sum(tr.launches_per_step.values())
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     ld_v, lg_v = float(ld), float(lg)
@@ -257,10 +264,12 @@ def run_product(args):
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        bA = {k: (hostA[k].to(dev, non_blocking=True) if k != "text" else hostA[k].numpy()) for k in d_keys}
-        bA["images"] = None
+        if graphs:      # pinned host tensors are copied straight into the graphs' static input buffers
+            bA, bB = {k: hostA[k] for k in d_keys}, {k: hostB[k] for k in g_keys}
+        else:
+            bA = {k: (hostA[k].to(dev, non_blocking=True) if k != "text" else hostA[k].numpy()) for k in d_keys}
+            bB = {k: (hostB[k].to(dev, non_blocking=True) if k != "text" else hostB[k].numpy()) for k in g_keys}
         od = tr.d_step(bA)
-        bB = {k: (hostB[k].to(dev, non_blocking=True) if k != "text" else hostB[k].numpy()) for k in g_keys}
         og = tr.g_step(bB)
         _ = (float(od["loss"]), float(og["loss"]))        # D2H read of both loss scalars
     f1.record()
@@ -294,6 +303,8 @@ def run_product(args):
                            "conv_flop_per_image": STEP_GFLOP * 1e9,
                            "step_conv_tflops_per_gpu": round(step_tflops, 2),
                            "step_conv_frac_of_sustained_peak": round(step_tflops / pk["sustained"], 4),
+                           "host_enqueue_ms_per_step": round(host_ms, 2),
+                           "cuda_graphs": graphs,
                            "loss_d": ld_v, "loss_g": lg_v},
                 "clocks": clocks,
                 "e2e": {"value": ips_e2e, "unit": "images/s",
@@ -314,6 +325,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

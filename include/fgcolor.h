@@ -167,9 +167,10 @@ int fgc_smooth_l1(const void* target, const void* gen, int dtype, long long n, f
 /* chunk table over a flat parameter buffer: chunk i covers [start[i], start[i]+len[i]) with l2 scale reg[i] */
 int fgc_reg_loss(const float* flat, const long long* start, const int32_t* len, const float* reg, int nchunks,
                  float* lossbuf, int slot, fgc_stream s);                                                                   /* :570-576 */
-/* g += reg*w (if add_reg); v = b2 v + (1-b2) g^2; w -= lr_t * g / (sqrt(v)+eps), lr_t = lr*sqrt(1-b2^t) (beta1 = 0) */
+/* g += reg*w (if add_reg); v = b2 v + (1-b2) g^2; w -= lr_t * g / (sqrt(v)+eps), lr_t = lr*sqrt(1-b2^t) (beta1 = 0).
+ * lr_t_dev (device pointer, may be NULL) overrides lr_t: lets a captured CUDA graph be replayed with a new step size. */
 int fgc_adam_step(float* flat, float* grad, float* v, const long long* start, const int32_t* len, const float* reg,
-                  int nchunks, float lr_t, float beta2, float eps, int add_reg, fgc_stream s);
+                  int nchunks, float lr_t, const float* lr_t_dev, float beta2, float eps, int add_reg, fgc_stream s);
 
 #ifdef __cplusplus
 }

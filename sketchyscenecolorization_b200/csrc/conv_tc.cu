@@ -287,29 +287,69 @@ __device__ __forceinline__ void gather_big_fast(uint32_t sbase, const __nv_bfloa
   }
 }
 
-// "small" slab: flattened q = tap*C + c for q in [q0, q0+64) (zero beyond k*k*C).  128/ROWS threads per row.
+// "small" slab: flattened q = tap*C + c for q in [q0, q0+64) (zero beyond k*k*C).  NP/ROWS threads per row.
+//   C == 8: one 16-byte chunk of the slab is exactly one filter tap -> one vector load per chunk;
+//   otherwise: scalar gather, 16 independent loads in flight per batch.
 template <typename SrcT, int ROWS, int NP = kProducers>
 __device__ __forceinline__ void gather_small(uint8_t* s_hi, uint8_t* s_lo, const SrcT* __restrict__ src, int C, int q0, int ups,
                                              int H, int W, int stride, int k, int pad_t, int pad_l, int sign,
                                              const uint32_t* pixrow, const PixDec pd, int tid) {
   using S = Stage<SrcT>;
   constexpr int TPR = NP / ROWS;     // threads per row (1, 2 or 4)
-  constexpr int KPT = 64 / TPR;              // k elements per thread
+  constexpr int KPT = 64 / TPR;      // k elements per thread
   const int r = tid % ROWS, part = tid / ROWS;
   const uint32_t p = pixrow[0];
   const int n = (int)((p >> pd.owb) >> pd.ohb), oh = (int)((p >> pd.owb) & pd.ohm), ow = (int)(p & pd.owm);
   const int Hs = ups ? (H >> 1) : H, Ws = ups ? (W >> 1) : W;
   const int qmax = k * k * C;
+  const bool rvalid = p != PIX_INVALID;
+  if (C == 8 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    constexpr int CPT = KPT / 8;     // chunks (= taps) per thread
+    uint4 v[CPT], v2[CPT];
+#pragma unroll
+    for (int ch = 0; ch < CPT; ch++) {
+      const int tap = (q0 >> 3) + part * CPT + ch;
+      const int kh = tap / k, kw = tap - kh * k;
+      int ih = oh * stride + sign * (kh - pad_t), iw = ow * stride + sign * (kw - pad_l);
+      const bool ok = rvalid && tap < k * k && (unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W;
+      if (ups) { ih >>= 1; iw >>= 1; }
+      v[ch] = make_uint4(0, 0, 0, 0);
+      v2[ch] = make_uint4(0, 0, 0, 0);
+      if (ok) {
+        const uint4* ptr = reinterpret_cast<const uint4*>(src + (((long long)n * Hs + ih) * Ws + iw) * 8);
+        v[ch] = __ldg(ptr);
+        if constexpr (S::X3) v2[ch] = __ldg(ptr + 1);
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < CPT; ch++) {
+      const int chunk = part * CPT + ch;
+      const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+      if constexpr (!S::X3) {
+        *reinterpret_cast<uint4*>(s_hi + off) = v[ch];
+      } else {
+        uint4 hi, lo;
+        split2(__uint_as_float(v[ch].x), __uint_as_float(v[ch].y), hi.x, lo.x);
+        split2(__uint_as_float(v[ch].z), __uint_as_float(v[ch].w), hi.y, lo.y);
+        split2(__uint_as_float(v2[ch].x), __uint_as_float(v2[ch].y), hi.z, lo.z);
+        split2(__uint_as_float(v2[ch].z), __uint_as_float(v2[ch].w), hi.w, lo.w);
+        *reinterpret_cast<uint4*>(s_hi + off) = hi;
+        *reinterpret_cast<uint4*>(s_lo + off) = lo;
+      }
+    }
+    return;
+  }
   int q = q0 + part * KPT;
   int tap = q / C, c = q % C;
   int kh = tap / k, kw = tap % k;
+  constexpr int BATCH = KPT < 16 ? KPT : 16;
 #pragma unroll 1
-  for (int ch = 0; ch < KPT / 8; ch++) {
-    float e[8];
+  for (int bt = 0; bt < KPT / BATCH; bt++) {
+    float e[BATCH];
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
+    for (int t = 0; t < BATCH; t++) {
       float val = 0.f;
-      if (q < qmax && p != PIX_INVALID) {
+      if (q < qmax && rvalid) {
         int ih = oh * stride + sign * (kh - pad_t), iw = ow * stride + sign * (kw - pad_l);
         if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
           if (ups) { ih >>= 1; iw >>= 1; }
@@ -320,17 +360,21 @@ __device__ __forceinline__ void gather_small(uint8_t* s_hi, uint8_t* s_lo, const
       q++; c++;
       if (c == C) { c = 0; kw++; if (kw == k) { kw = 0; kh++; } }
     }
-    int chunk = part * (KPT / 8) + ch;
-    int off = r * 128 + ((chunk ^ (r & 7)) << 4);
-    uint4 hi, lo;
-    if constexpr (!S::X3) {
-      hi = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-      *reinterpret_cast<uint4*>(s_hi + off) = hi;
-    } else {
-      split2(e[0], e[1], hi.x, lo.x); split2(e[2], e[3], hi.y, lo.y);
-      split2(e[4], e[5], hi.z, lo.z); split2(e[6], e[7], hi.w, lo.w);
-      *reinterpret_cast<uint4*>(s_hi + off) = hi;
-      *reinterpret_cast<uint4*>(s_lo + off) = lo;
+#pragma unroll
+    for (int ch = 0; ch < BATCH / 8; ch++) {
+      const int chunk = part * (KPT / 8) + bt * (BATCH / 8) + ch;
+      const int off = r * 128 + ((chunk ^ (r & 7)) << 4);
+      const float* f = e + ch * 8;
+      uint4 hi, lo;
+      if constexpr (!S::X3) {
+        hi = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(s_hi + off) = hi;
+      } else {
+        split2(f[0], f[1], hi.x, lo.x); split2(f[2], f[3], hi.y, lo.y);
+        split2(f[4], f[5], hi.z, lo.z); split2(f[6], f[7], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(s_hi + off) = hi;
+        *reinterpret_cast<uint4*>(s_lo + off) = lo;
+      }
     }
   }
 }

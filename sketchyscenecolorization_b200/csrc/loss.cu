@@ -86,7 +86,9 @@ __global__ void reg_loss_kernel(const float* __restrict__ flat, const long long*
 
 __global__ void adam_step_kernel(float* __restrict__ flat, float* __restrict__ grad, float* __restrict__ v,
                                  const long long* __restrict__ start, const int32_t* __restrict__ len,
-                                 const float* __restrict__ reg, float lr_t, float beta2, float eps, int add_reg) {
+                                 const float* __restrict__ reg, float lr_t, const float* __restrict__ lr_t_dev, float beta2,
+                                 float eps, int add_reg) {
+  if (lr_t_dev) lr_t = *lr_t_dev;       // step size kept in device memory (CUDA-graph replay: no baked-in scalars)
   int ch = blockIdx.x;
   long long s0 = start[ch];
   int L = len[ch];
@@ -143,8 +145,8 @@ int fgc_reg_loss(const float* flat, const long long* start, const int32_t* len, 
   return FGC_OK;
 }
 int fgc_adam_step(float* flat, float* grad, float* v, const long long* start, const int32_t* len, const float* reg,
-                  int nchunks, float lr_t, float beta2, float eps, int add_reg, fgc_stream stream) {
-  adam_step_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(flat, grad, v, start, len, reg, lr_t, beta2, eps, add_reg);
+                  int nchunks, float lr_t, const float* lr_t_dev, float beta2, float eps, int add_reg, fgc_stream stream) {
+  adam_step_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(flat, grad, v, start, len, reg, lr_t, lr_t_dev, beta2, eps, add_reg);
   count_launch();
   FGC_LAUNCH_CHECK("adam_step");
   return FGC_OK;

@@ -414,13 +414,17 @@ class CudaOps(OpsBase):
         return buf[1]
 
     # ---------------- optimiser ----------------
-    def adam_step(self, store, lr, add_reg_grad=True):
-        store.adam_t += 1
-        lr_t = lr * math.sqrt(1.0 - 0.9 ** store.adam_t)
+    def adam_step(self, store, lr, add_reg_grad=True, lr_dev=None):
+        """lr_dev: optional fp32 device scalar holding lr*sqrt(1-0.9^t); then `lr` and store.adam_t are left to the caller
+        (CUDA-graph replay must not bake the step size into the kernel arguments)."""
+        lr_t = 0.0
+        if lr_dev is None:
+            store.adam_t += 1
+            lr_t = lr * math.sqrt(1.0 - 0.9 ** store.adam_t)
         check(self.lib.fgc_adam_step(self._f32(store.flat), self._f32(store.grad), self._f32(store.adam_v),
                                      self._p(store.chunk_start), self._p(store.chunk_len), self._p(store.chunk_reg),
-                                     store.chunk_start.numel(), float(lr_t), 0.9, 1e-8, 1 if add_reg_grad else 0, self._s()),
-              "adam_step")
+                                     store.chunk_start.numel(), float(lr_t), None if lr_dev is None else self._f32(lr_dev),
+                                     0.9, 1e-8, 1 if add_reg_grad else 0, self._s()), "adam_step")
 
 
 def enable_op_timing(ops):

@@ -197,6 +197,6 @@ class OpsBase:
         raise NotImplementedError
 
     # ---------------- optimiser (graph_single.py:584-593, tf.train.AdamOptimizer(beta1=0, beta2=0.9)) ----
-    def adam_step(self, store, lr, add_reg_grad=True):
+    def adam_step(self, store, lr, add_reg_grad=True, lr_dev=None):
         """g += reg*w; v = .9v+.1g^2; w -= lr*sqrt(1-.9^t)*g/(sqrt(v)+1e-8); increments store.adam_t first."""
         raise NotImplementedError

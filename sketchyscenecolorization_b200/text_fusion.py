@@ -37,15 +37,20 @@ def _rows(t):
 
 
 def text_fusion_fwd(ops, store, e4, ids_host, save=True):
-    """e4: [N,h,w,D] activation; ids_host: numpy/torch int array [N,T] on the HOST.  Returns ([N,h,w,D], ctx)."""
-    ids_np = np.asarray(ids_host, dtype=np.int32)
+    """e4: [N,h,w,D] activation; ids_host: int array [N,T] on the HOST (numpy / CPU tensor), or an int32 DEVICE tensor.
+    With host ids, time steps at which every caption is <pad> are skipped outright (the reference's tf.cond, :235);
+    with device ids nothing on the host depends on the data (CUDA-graph capture): every step runs and <pad> samples
+    are masked inside the cell kernel -- same result.  Returns ([N,h,w,D], ctx)."""
+    on_device = torch.is_tensor(ids_host) and ids_host.is_cuda
+    ids_np = None if on_device else np.asarray(ids_host, dtype=np.int32)
     N, hh, ww, D = e4.shape
     P = hh * ww
     R = N * P
-    T = ids_np.shape[1]
+    T = ids_host.shape[1]
     dev = e4.device
     emb, kw, bw, ka, ba = store.p[_EMB], store.p[_KW], store.p[_BW], store.p[_KA], store.p[_BA]
-    ids_dev = torch.as_tensor(ids_np, device=dev).contiguous()   # [N,T] int32; pad mask = (id == 0)
+    # [N,T] int32 on the device; pad mask = (id == 0)
+    ids_dev = ids_host.to(torch.int32).contiguous() if on_device else torch.as_tensor(ids_np, device=dev).contiguous()
     f32 = torch.float32
 
     e4r = ops.cast(e4, f32).view(R, D)
@@ -55,7 +60,7 @@ def text_fusion_fwd(ops, store, e4, ids_host, save=True):
     ca = ops.zeros_f32((R, D)); ha = ops.zeros_f32((R, D))                          # :196,204
     steps = []
     for t in range(T):
-        if not (ids_np[:, t] != 0).any():      # every sample is <pad> here: state passes through (tf.cond f1)
+        if ids_np is not None and not (ids_np[:, t] != 0).any():      # every sample is <pad> here: state passes through
             continue
         e_t = ops.embedding_fwd(emb, ids_dev, t)                                         # :182,211
         gw = ops.conv_fwd([(_rows(e_t), False), (_rows(hw), False)], _mat(kw), bw, out_dtype=f32).view(N, 4 * D)

@@ -93,12 +93,25 @@ class FgColorModel:
 
 
 class FgColorTrainer:
-    """Alternating D / G optimisation with optional data-parallel gradient averaging."""
+    """Alternating D / G optimisation with optional data-parallel gradient averaging.
 
-    def __init__(self, model, *, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=None, world_size=1):
+    use_cuda_graphs=True (CUDA operator set only): the first call of each step runs eagerly, the second one is captured
+    into a CUDA graph (kernels, memsets, the NCCL all-reduce and the fused Adam), and every later call copies the batch
+    into the graph's static input buffers and replays it -- the ~3500 per-step kernel launches cost one graph launch
+    on the host.  Nothing inside a captured step depends on host data: caption ids stay on the device (pad steps are
+    masked in the LSTM kernel instead of skipped) and the Adam step size is read from a device scalar."""
+
+    D_KEYS = ("sketch", "images_d", "cls", "cls_d", "text", "noise")
+    G_KEYS = ("sketch", "images", "cls", "text", "noise")
+
+    def __init__(self, model, *, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=None, world_size=1,
+                 use_cuda_graphs=False):
         self.m, self.lr_g, self.lr_d, self.max_iter = model, lr_g, lr_d, max_iter
         self.pg, self.world = process_group, world_size
         self.counter = 0
+        self.use_graphs = use_cuda_graphs
+        self._g = {}          # kind -> dict(graph, inputs, outputs, lr, calls)
+        self.launches_per_step = {}
 
     def _allreduce(self, store):
         """average_gradients (graph_single.py:33-68): one all-reduce of the flat fp32 gradient bucket."""
@@ -107,15 +120,61 @@ class FgColorTrainer:
             dist.all_reduce(store.grad, op=dist.ReduceOp.SUM, group=self.pg)
             store.grad.mul_(1.0 / self.world)
 
-    def d_step(self, batch):
+    # ---- eager steps
+    def _d_eager(self, batch, lr_dev=None):
         out = self.m.d_step_grads(batch)
         self._allreduce(self.m.dstore)
-        self.m.ops.adam_step(self.m.dstore, self.lr_d * lr_decay(self.counter, self.max_iter))
+        self.m.ops.adam_step(self.m.dstore, self.lr_d * lr_decay(self.counter, self.max_iter), lr_dev=lr_dev)
         return out
 
-    def g_step(self, batch):
+    def _g_eager(self, batch, lr_dev=None):
         out = self.m.g_step_grads(batch)
         self._allreduce(self.m.gstore)
-        self.m.ops.adam_step(self.m.gstore, self.lr_g * lr_decay(self.counter, self.max_iter))
+        self.m.ops.adam_step(self.m.gstore, self.lr_g * lr_decay(self.counter, self.max_iter), lr_dev=lr_dev)
+        return out
+
+    # ---- CUDA-graph steps
+    def _graph_step(self, kind, batch):
+        store = self.m.dstore if kind == "d" else self.m.gstore
+        keys = self.D_KEYS if kind == "d" else self.G_KEYS
+        eager = self._d_eager if kind == "d" else self._g_eager
+        base_lr = self.lr_d if kind == "d" else self.lr_g
+        st = self._g.setdefault(kind, dict(calls=0))
+        st["calls"] += 1
+        if st["calls"] == 1:                    # lazy one-time initialisation inside the library happens here
+            return eager(batch)
+        dev = self.m.device
+        if "graph" not in st:
+            st["inputs"] = {}
+            for k in keys:
+                v = batch[k]
+                v = torch.as_tensor(v) if not torch.is_tensor(v) else v
+                st["inputs"][k] = torch.empty(v.shape, dtype=torch.int32 if not v.is_floating_point() else torch.float32,
+                                              device=dev)
+            st["lr"] = torch.zeros((), dtype=torch.float32, device=dev)
+            n0 = self.m.ops.launch_count() if hasattr(self.m.ops, "launch_count") else 0
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st["outputs"] = eager(dict(st["inputs"]), lr_dev=st["lr"])
+            st["graph"] = graph
+            if hasattr(self.m.ops, "launch_count"):
+                self.launches_per_step[kind] = self.m.ops.launch_count() - n0
+        for k in keys:
+            v = batch[k]
+            v = torch.as_tensor(v) if not torch.is_tensor(v) else v
+            st["inputs"][k].copy_(v, non_blocking=True)
+        store.adam_t += 1
+        st["lr"].fill_(base_lr * lr_decay(self.counter, self.max_iter) * math.sqrt(1.0 - 0.9 ** store.adam_t))
+        st["graph"].replay()
+        return st["outputs"]
+
+    def d_step(self, batch):
+        if self.use_graphs:
+            return self._graph_step("d", batch)
+        return self._d_eager(batch)
+
+    def g_step(self, batch):
+        out = self._graph_step("g", batch) if self.use_graphs else self._g_eager(batch)
         self.counter += 1                                                # counter_addition_op, main_procedure.py:106,221
         return out

@@ -345,7 +345,7 @@ class TorchOps(OpsBase):
             if s.trainable and s.reg > 0:
                 store.g[s.name] += s.reg * store.p[s.name]
 
-    def adam_step(self, store, lr, add_reg_grad=True):
+    def adam_step(self, store, lr, add_reg_grad=True, lr_dev=None):
         if add_reg_grad:
             self.add_reg_grad(store)
         store.adam_t += 1
