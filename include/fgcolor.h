@@ -117,6 +117,9 @@ int fgc_blend_bwd(const void* g, const void* sk_low, const void* h2, const void*
 int fgc_addpool_fwd(const void* a, const void* b, int dtype, int N, int h, int w, int C, void* out, fgc_stream s);
 /* out[N,2h,2w,C] = up2(g)/4 */
 int fgc_unpool_bwd(const void* g, int dtype, int N, int h, int w, int C, void* out, fgc_stream s);
+/* out[N,2h,2w,C] = nearest-neighbour x2 upsample of x (mru.upsample, mru.py:22-28), materialised: only the weight-gradient
+ * kernel wants it in memory (its TMA tiles cannot replicate pixels); forward convs read the low-res tensor directly */
+int fgc_upsample2x(const void* x, int dtype, int N, int h, int w, int C, void* out, fgc_stream s);
 /* out[N,h,w,C] (=|+=) sum over each 2x2 block of g[N,2h,2w,C]  (gradient of mru.upsample, mru.py:22-28) */
 int fgc_sum2x2(const void* g, int g_dtype, int N, int h, int w, int C, void* out, int out_dtype, int accumulate, fgc_stream s);
 int fgc_axpy(void* dst, const void* src, int dst_dtype, int src_dtype, long long n, float alpha, fgc_stream s); /* dst += alpha*src */

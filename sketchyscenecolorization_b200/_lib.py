@@ -93,6 +93,7 @@ SIGNATURES = {
     "fgc_blend_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "fgc_addpool_fwd": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "fgc_unpool_bwd": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "fgc_upsample2x": [_P, _I, _I, _I, _I, _I, _P, _P],
     "fgc_sum2x2": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P],
     "fgc_axpy": [_P, _P, _I, _I, _LL, _F, _P],
     "fgc_spatial_mean_fwd": [_P, _I, _I, _I, _I, _P, _P],

@@ -244,15 +244,18 @@ def dec_block_bwd(ops, wv, scope, g_out, ctx, labels, xs_need_grad):
     del g_gh
     ops.add_(g_ht, g_ht_mul)
     del g_ht_mul
-    # gates
+    # gates.  The weight-gradient kernel fetches its tiles with tensor TMA, which cannot replicate pixels: give it the
+    # upsampled hidden state in memory (one write of H, read by both gate wgrads) instead of the (ht_low, ups) view.
+    f_w = [(ops.upsample_fwd(ht_low), False)] + [(x, False) for x in xs]
     for (gg, raw, mn, mx, sc) in ((g_rg, ctx["rg_raw"], ctx["mn0"], ctx["mx0"], scope + "/Conv"),
                                   (g_zg, ctx["zg_raw"], ctx["mn1"], ctx["mx1"], scope + "/Conv_1")):
         g_raw = ops.minmax_bwd(gg, raw, mn, mx)
         w, _ = wv.get(sc)
-        ops.conv_wgrad(f, g_raw, *wv.grads(sc))
+        ops.conv_wgrad(f_w, g_raw, *wv.grads(sc))
         ops.conv_dgrad(g_raw, w, 0, chid, ups=True, out=g_ht, acc=True)
         for i in range(len(xs)):
             if xs_need_grad[i]:
                 ops.conv_dgrad(g_raw, w, offs[i], xs[i].shape[-1], out=g_xs[i], acc=True)
         del g_raw
+    del f_w
     return g_ht, g_xs

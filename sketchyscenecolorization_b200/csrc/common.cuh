@@ -43,40 +43,53 @@ template <> __device__ __forceinline__ void st1<__nv_bfloat16>(__nv_bfloat16* p,
   *p = __float2bfloat16_rn(v);
 }
 
-// 4 consecutive elements (pointer must be aligned to 4 elements)
-template <typename T> __device__ __forceinline__ void ld4(const T* p, float (&v)[4]);
-template <> __device__ __forceinline__ void ld4<float>(const float* p, float (&v)[4]) {
+// V consecutive elements (V = 8, 4 or 1; pointer aligned to V elements), widened to fp32 in v[0..V)
+constexpr int kMaxV = 8;
+template <typename T, int V> __device__ __forceinline__ void ldv(const T* p, float (&v)[kMaxV]);
+template <> __device__ __forceinline__ void ldv<float, 1>(const float* p, float (&v)[kMaxV]) { v[0] = __ldg(p); }
+template <> __device__ __forceinline__ void ldv<float, 4>(const float* p, float (&v)[kMaxV]) {
   float4 t = __ldg(reinterpret_cast<const float4*>(p));
   v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
-template <> __device__ __forceinline__ void ld4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+template <> __device__ __forceinline__ void ldv<float, 8>(const float* p, float (&v)[kMaxV]) {
+  float4 t = __ldg(reinterpret_cast<const float4*>(p)), u = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; v[4] = u.x; v[5] = u.y; v[6] = u.z; v[7] = u.w;
+}
+template <> __device__ __forceinline__ void ldv<__nv_bfloat16, 1>(const __nv_bfloat16* p, float (&v)[kMaxV]) {
+  v[0] = __bfloat162float(*p);
+}
+template <> __device__ __forceinline__ void ldv<__nv_bfloat16, 4>(const __nv_bfloat16* p, float (&v)[kMaxV]) {
   uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
-  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
-  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
-  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  float2 fa = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.x)), fb = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.y));
   v[0] = fa.x; v[1] = fa.y; v[2] = fb.x; v[3] = fb.y;
 }
-template <typename T> __device__ __forceinline__ void st4(T* p, const float (&v)[4]);
-template <> __device__ __forceinline__ void st4<float>(float* p, const float (&v)[4]) {
+template <> __device__ __forceinline__ void ldv<__nv_bfloat16, 8>(const __nv_bfloat16* p, float (&v)[kMaxV]) {
+  uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+  float2 f0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.x)), f1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.y));
+  float2 f2 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.z)), f3 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.w));
+  v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+}
+__device__ __forceinline__ uint32_t bf16x2_bits(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+template <typename T, int V> __device__ __forceinline__ void stv(T* p, const float (&v)[kMaxV]);
+template <> __device__ __forceinline__ void stv<float, 1>(float* p, const float (&v)[kMaxV]) { *p = v[0]; }
+template <> __device__ __forceinline__ void stv<float, 4>(float* p, const float (&v)[kMaxV]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
-template <> __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-  uint2 t;
-  t.x = *reinterpret_cast<uint32_t*>(&a);
-  t.y = *reinterpret_cast<uint32_t*>(&b);
-  *reinterpret_cast<uint2*>(p) = t;
+template <> __device__ __forceinline__ void stv<float, 8>(float* p, const float (&v)[kMaxV]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
-
-// V-wide access (V = 4 or 1)
-template <typename T, int V> __device__ __forceinline__ void ldv(const T* p, float (&v)[4]) {
-  if constexpr (V == 4) ld4<T>(p, v);
-  else { v[0] = ld1<T>(p); v[1] = v[2] = v[3] = 0.f; }
+template <> __device__ __forceinline__ void stv<__nv_bfloat16, 1>(__nv_bfloat16* p, const float (&v)[kMaxV]) {
+  *p = __float2bfloat16_rn(v[0]);
 }
-template <typename T, int V> __device__ __forceinline__ void stv(T* p, const float (&v)[4]) {
-  if constexpr (V == 4) st4<T>(p, v);
-  else st1<T>(p, v[0]);
+template <> __device__ __forceinline__ void stv<__nv_bfloat16, 4>(__nv_bfloat16* p, const float (&v)[kMaxV]) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(bf16x2_bits(v[0], v[1]), bf16x2_bits(v[2], v[3]));
+}
+template <> __device__ __forceinline__ void stv<__nv_bfloat16, 8>(__nv_bfloat16* p, const float (&v)[kMaxV]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(bf16x2_bits(v[0], v[1]), bf16x2_bits(v[2], v[3]), bf16x2_bits(v[4], v[5]), bf16x2_bits(v[6], v[7]));
 }
 
 __device__ __forceinline__ float miu_relu(float x) { return 0.5f * (x + sqrtf(0.09f + x * x)); }
@@ -114,10 +127,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
-// can we use 4-wide vector access on a tensor whose channel count is C?
-static inline bool vec4_ok(const void* p, long long C, int dtype) {
-  if (C % 4) return false;
-  return dtype == FGC_BF16 ? aligned8(p) : aligned16(p);
+// widest vector access (8, 4 or 1 elements) usable on a tensor whose channel count is C
+static inline int vec_width(const void* p, long long C, int dtype) {
+  if (C % 8 == 0 && aligned16(p) && (dtype == FGC_BF16 || (reinterpret_cast<uintptr_t>(p) & 31) == 0)) return 8;
+  if (C % 4 == 0 && (dtype == FGC_BF16 ? aligned8(p) : aligned16(p))) return 4;
+  return 1;
 }
+static inline int vmin(int a, int b) { return a < b ? a : b; }
 
 }  // namespace fgc

@@ -757,6 +757,10 @@ struct WgradArgs {
   int Cout;
   int Cin_total;
   float* dw;          // HWIO fp32, accumulated with red.add
+  // dW(tap, c, n) lives at dw + tap_eff*dw_tap + c*dw_c + n*dw_n, tap_eff = tap or k*k-1-tap (mirrored) -- the mirrored,
+  // transposed form serves the operand-swapped evaluation of small-Cout convolutions (see conv_wgrad_run)
+  long long dw_tap, dw_c, dw_n;
+  int tap_flip;
   int kslabs;         // ceil(M/64)
   int kslabs_per_cta;
   int stages;
@@ -992,7 +996,8 @@ __global__ void __launch_bounds__(320, 1) conv_wgrad_kernel(const __grid_constan
         const int q = 2 * b + (row >> 6), kk = row & 63;
         int tap = 0, cg = 0;
         bool rvalid = have[q] && slab_elem(g, si[q], kk, &tap, &cg);
-        float* dwrow = a.dw + ((long long)tap * a.Cin_total + cg) * a.Cout;
+        if (a.tap_flip) tap = g.k * g.k - 1 - tap;
+        float* dwrow = a.dw + tap * a.dw_tap + cg * a.dw_c;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t r[32];
@@ -1001,7 +1006,7 @@ __global__ void __launch_bounds__(320, 1) conv_wgrad_kernel(const __grid_constan
 #pragma unroll
           for (int e = 0; e < 32; e++) {
             int n = n0 + c0 + e;
-            if (n < a.Cout) atomicAdd(dwrow + n, __uint_as_float(r[e]));
+            if (n < a.Cout) atomicAdd(dwrow + n * a.dw_n, __uint_as_float(r[e]));
           }
         }
       }
@@ -1296,6 +1301,9 @@ static int launch_wgrad(WgradArgs& a, cudaStream_t s) {
   return check_launch("conv_wgrad");
 }
 
+struct WgradArgs;
+static int conv_wgrad_run_args(WgradArgs& a, int src_dtype, cudaStream_t s);
+
 static int pick_bn_wgrad(int nout, int x3) {
   if (nout <= 16) return 16;
   if (nout <= 32) return 32;
@@ -1312,6 +1320,35 @@ int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, in
   a.Cout = Cout;
   a.Cin_total = Cin_total;
   a.dw = dw;
+  a.dw_tap = (long long)Cin_total * Cout;
+  a.dw_c = Cout;
+  a.dw_n = 1;
+  a.tap_flip = 0;
+  // Few output channels under a large filter (the 7x7, 64 -> 3 generator head): as written the reduction would gather
+  // k*k shifted copies of the wide input.  Swap the operands instead -- dW[tap][ci][co] = sum_q x[q][ci] * gy[q - tap][co]
+  // -- i.e. the same kernel with the narrow gy as the (mirrored-tap) gathered source and x as the plain operand, and the
+  // result scattered back transposed.
+  if (g.nsrc == 1 && g.stride == 1 && g.OH == g.H && g.OW == g.W && !g.ups[0] && g.k >= 5 && Cout <= 8 && g.C[0] >= 32 &&
+      g.C[0] % 8 == 0 && g.pad_t == (g.k - 1) / 2 && g.pad_l == (g.k - 1) / 2) {
+    ConvGeom gs = g;
+    gs.src[0] = gy;
+    gs.C[0] = Cout;
+    finish_geom(gs);
+    a.g = gs;
+    a.gy = g.src[0];
+    a.Cout = g.C[0];
+    a.Cin_total = Cout;
+    a.dw_c = 1;
+    a.dw_n = Cout;
+    a.tap_flip = 1;
+    return conv_wgrad_run_args(a, src_dtype, s);
+  }
+  return conv_wgrad_run_args(a, src_dtype, s);
+}
+
+static int conv_wgrad_run_args(WgradArgs& a, int src_dtype, cudaStream_t s) {
+  const ConvGeom& g = a.g;
+  const int Cout = a.Cout;
   a.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FGC_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   const int x3 = src_dtype == FGC_F32;

@@ -41,15 +41,18 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-#define FGC_DISPATCH_TV(dtype, vec_ok, T, V, ...)                                     \
+// `vw` = vector width chosen with vec_width(): 8, 4 or 1 elements per thread and access
+#define FGC_DISPATCH_V(vw, V, ...)                                                    \
   do {                                                                                \
-    if ((dtype) == FGC_F32) {                                                         \
-      using T = float;                                                                \
-      if (vec_ok) { constexpr int V = 4; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; } \
-    } else if ((dtype) == FGC_BF16) {                                                 \
-      using T = __nv_bfloat16;                                                        \
-      if (vec_ok) { constexpr int V = 4; __VA_ARGS__; } else { constexpr int V = 1; __VA_ARGS__; } \
-    } else {                                                                          \
+    if ((vw) >= 8) { constexpr int V = 8; __VA_ARGS__; }                              \
+    else if ((vw) >= 4) { constexpr int V = 4; __VA_ARGS__; }                         \
+    else { constexpr int V = 1; __VA_ARGS__; }                                        \
+  } while (0)
+#define FGC_DISPATCH_TV(dtype, vw, T, V, ...)                                         \
+  do {                                                                                \
+    if ((dtype) == FGC_F32) { using T = float; FGC_DISPATCH_V(vw, V, __VA_ARGS__); }  \
+    else if ((dtype) == FGC_BF16) { using T = __nv_bfloat16; FGC_DISPATCH_V(vw, V, __VA_ARGS__); } \
+    else {                                                                            \
       fgc::set_error("bad dtype %d", (int)(dtype));                                   \
       return FGC_EINVAL;                                                              \
     }                                                                                 \
@@ -81,7 +84,7 @@ __global__ void chan_stats_kernel(const T* __restrict__ x, long long M, int C, i
       for (int j = 0; j < 16; j++) {
         long long r = rb + (long long)j * lanes;
         if (r < r1) {
-          float a[4];
+          float a[kMaxV];
           ldv<T, V>(x + r * C + v * V, a);
 #pragma unroll
           for (int i = 0; i < V; i++) { ps[i] += a[i]; pss[i] += a[i] * a[i]; }
@@ -122,7 +125,7 @@ __global__ void cbn_act_fwd_kernel(const T* __restrict__ x, long long nvec, int 
     long long row = i / CV;
     int n = (int)(row / HW);
     int l = labels[n];
-    float a[4], o[4];
+    float a[kMaxV], o[kMaxV];
     ldv<T, V>(x + i * V, a);
 #pragma unroll
     for (int k = 0; k < V; k++) {
@@ -141,13 +144,15 @@ __global__ void cbn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restr
                                       const float* __restrict__ stats, const float* __restrict__ scale,
                                       const float* __restrict__ offset, const int32_t* __restrict__ labels, int act,
                                       int N, float* sums) {
+  extern __shared__ float sh_red[];              // [2][C] block-level partial sums
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
-  if (rl >= lanes) return;
   const int n = blockIdx.y;
   const int l = labels[n];
-  int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh_red[i] = 0.f;
+  __syncthreads();
+  int r0 = blockIdx.x * rows_per_block, r1 = rl < lanes ? min(r0 + rows_per_block, HW) : 0;
   float mean[V], rstd[V], ga[V], be[V], s1[V], s2[V];
 #pragma unroll
   for (int k = 0; k < V; k++) {
@@ -156,23 +161,40 @@ __global__ void cbn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restr
     ga[k] = scale[l * C + c]; be[k] = offset[l * C + c];
     s1[k] = s2[k] = 0.f;
   }
-  for (int r = r0 + rl; r < r1; r += lanes) {
-    long long off = ((long long)n * HW + r) * C + v * V;
-    float a[4], g[4];
-    ldv<T, V>(x + off, a);
-    ldv<T, V>(gy + off, g);
+  for (int rb = r0 + rl; rb < r1; rb += 2 * lanes) {       // two independent row loads in flight per thread
+    float a[2][kMaxV], g[2][kMaxV];
 #pragma unroll
-    for (int k = 0; k < V; k++) {
-      float xh = (a[k] - mean[k]) * rstd[k];
-      float gg = g[k];
-      if (act == FGC_ACT_MIU) gg *= miu_relu_grad(xh * ga[k] + be[k]);
-      s1[k] += gg; s2[k] += gg * xh;
+    for (int u = 0; u < 2; u++) {
+      int r = rb + u * lanes;
+      if (r < r1) {
+        long long off = ((long long)n * HW + r) * C + v * V;
+        ldv<T, V>(x + off, a[u]);
+        ldv<T, V>(gy + off, g[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (rb + u * lanes >= r1) continue;
+#pragma unroll
+      for (int k = 0; k < V; k++) {
+        float xh = (a[u][k] - mean[k]) * rstd[k];
+        float gg = g[u][k];
+        if (act == FGC_ACT_MIU) gg *= miu_relu_grad(xh * ga[k] + be[k]);
+        s1[k] += gg; s2[k] += gg * xh;
+      }
     }
   }
+  if (rl < lanes) {
 #pragma unroll
-  for (int k = 0; k < V; k++) {
-    atomicAdd(&sums[(long long)n * C + v * V + k], s1[k]);
-    atomicAdd(&sums[((long long)N + n) * C + v * V + k], s2[k]);
+    for (int k = 0; k < V; k++) {
+      atomicAdd(&sh_red[v * V + k], s1[k]);
+      atomicAdd(&sh_red[C + v * V + k], s2[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {       // one global atomic per table entry and block
+    int q = i / C, c = i - q * C;
+    atomicAdd(&sums[((long long)q * N + n) * C + c], sh_red[i]);
   }
 }
 // one thread per channel: table gradients (no atomics: a channel is owned by one thread) and batch means
@@ -203,7 +225,7 @@ __global__ void cbn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restri
     long long row = i / CV;
     int n = (int)(row / HW);
     int l = labels[n];
-    float a[4], g[4], o[4];
+    float a[kMaxV], g[kMaxV], o[kMaxV];
     ldv<T, V>(x + i * V, a);
     ldv<T, V>(gy + i * V, g);
 #pragma unroll
@@ -227,7 +249,7 @@ template <typename T, int V>
 __global__ void prelu_fwd_kernel(const T* __restrict__ x, long long nvec, const float* __restrict__ ap, T* __restrict__ y) {
   const float a = *ap;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    float v[4], o[4];
+    float v[kMaxV], o[kMaxV];
     ldv<T, V>(x + i * V, v);
 #pragma unroll
     for (int k = 0; k < V; k++) o[k] = (a * v[k] >= v[k]) ? a * v[k] : v[k];
@@ -241,7 +263,7 @@ __global__ void prelu_bwd_kernel(const T* __restrict__ gy, const T* __restrict__
   const float a = *ap;
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    float v[4], g[4], o[4];
+    float v[kMaxV], g[kMaxV], o[kMaxV];
     ldv<T, V>(x + i * V, v);
     ldv<T, V>(gy + i * V, g);
 #pragma unroll
@@ -264,25 +286,42 @@ __global__ void prelu_bwd_kernel(const T* __restrict__ gy, const T* __restrict__
 template <typename T, int V>
 __global__ void minmax_reduce_kernel(const T* __restrict__ x, int HW, int C, int rows_per_block, uint32_t* mn_ord,
                                      uint32_t* mx_ord) {
+  extern __shared__ uint32_t sh_mm[];            // [2][C] block-level min / max (order-preserving encoding)
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
-  if (rl >= lanes) return;
   const int n = blockIdx.y;
-  int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh_mm[i] = i < C ? 0xFFFFFFFFu : 0u;
+  __syncthreads();
+  int r0 = blockIdx.x * rows_per_block, r1 = rl < lanes ? min(r0 + rows_per_block, HW) : 0;
   float lo[V], hi[V];
 #pragma unroll
   for (int k = 0; k < V; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
-  for (int r = r0 + rl; r < r1; r += lanes) {
-    float a[4];
-    ldv<T, V>(x + ((long long)n * HW + r) * C + v * V, a);
+  for (int rb = r0 + rl; rb < r1; rb += 4 * lanes) {       // four independent row loads in flight per thread
+    float a[4][kMaxV];
 #pragma unroll
-    for (int k = 0; k < V; k++) { lo[k] = fminf(lo[k], a[k]); hi[k] = fmaxf(hi[k], a[k]); }
+    for (int u = 0; u < 4; u++) {
+      int r = rb + u * lanes;
+      if (r < r1) ldv<T, V>(x + ((long long)n * HW + r) * C + v * V, a[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (rb + u * lanes >= r1) continue;
+#pragma unroll
+      for (int k = 0; k < V; k++) { lo[k] = fminf(lo[k], a[u][k]); hi[k] = fmaxf(hi[k], a[u][k]); }
+    }
   }
+  if (rl < lanes) {
 #pragma unroll
-  for (int k = 0; k < V; k++) {
-    atomicMin(&mn_ord[(long long)n * C + v * V + k], f2ord(lo[k]));
-    atomicMax(&mx_ord[(long long)n * C + v * V + k], f2ord(hi[k]));
+    for (int k = 0; k < V; k++) {
+      atomicMin(&sh_mm[v * V + k], f2ord(lo[k]));
+      atomicMax(&sh_mm[C + v * V + k], f2ord(hi[k]));
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicMin(&mn_ord[(long long)n * C + c], sh_mm[c]);
+    atomicMax(&mx_ord[(long long)n * C + c], sh_mm[C + c]);
   }
 }
 template <typename T, int V>
@@ -294,7 +333,7 @@ __global__ void minmax_apply_kernel(const T* __restrict__ x, long long nvec, int
     long long row = i / CV;
     int n = (int)(row / HW);
     bool first = (row % HW) == 0;
-    float a[4], o[4];
+    float a[kMaxV], o[kMaxV];
     ldv<T, V>(x + i * V, a);
 #pragma unroll
     for (int k = 0; k < V; k++) {
@@ -310,37 +349,57 @@ __global__ void minmax_apply_kernel(const T* __restrict__ x, long long nvec, int
 template <typename T, int V>
 __global__ void minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                          const float* __restrict__ mn, const float* __restrict__ mx, int N, float* sums) {
+  extern __shared__ float sh_red[];              // [4][C] block-level partial sums
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
-  if (rl >= lanes) return;
   const int n = blockIdx.y;
-  int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) sh_red[i] = 0.f;
+  __syncthreads();
+  int r0 = blockIdx.x * rows_per_block, r1 = rl < lanes ? min(r0 + rows_per_block, HW) : 0;
   float lo[V], hi[V], s0[V], s1[V], c0[V], c1[V];
 #pragma unroll
   for (int k = 0; k < V; k++) {
     lo[k] = mn[(long long)n * C + v * V + k]; hi[k] = mx[(long long)n * C + v * V + k];
     s0[k] = s1[k] = c0[k] = c1[k] = 0.f;
   }
-  for (int r = r0 + rl; r < r1; r += lanes) {
-    long long off = ((long long)n * HW + r) * C + v * V;
-    float a[4], g[4];
-    ldv<T, V>(x + off, a);
-    ldv<T, V>(gg + off, g);
+  for (int rb = r0 + rl; rb < r1; rb += 2 * lanes) {       // two independent row loads in flight per thread
+    float a[2][kMaxV], g[2][kMaxV];
 #pragma unroll
-    for (int k = 0; k < V; k++) {
-      s0[k] += g[k] * (a[k] - lo[k]); s1[k] += g[k];
-      c0[k] += (a[k] == hi[k]) ? 1.f : 0.f;
-      c1[k] += (a[k] == lo[k]) ? 1.f : 0.f;
+    for (int u = 0; u < 2; u++) {
+      int r = rb + u * lanes;
+      if (r < r1) {
+        long long off = ((long long)n * HW + r) * C + v * V;
+        ldv<T, V>(x + off, a[u]);
+        ldv<T, V>(gg + off, g[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      if (rb + u * lanes >= r1) continue;
+#pragma unroll
+      for (int k = 0; k < V; k++) {
+        s0[k] += g[u][k] * (a[u][k] - lo[k]); s1[k] += g[u][k];
+        c0[k] += (a[u][k] == hi[k]) ? 1.f : 0.f;
+        c1[k] += (a[u][k] == lo[k]) ? 1.f : 0.f;
+      }
     }
   }
-  long long NC = (long long)N * C;
+  if (rl < lanes) {
 #pragma unroll
-  for (int k = 0; k < V; k++) {
-    long long o = (long long)n * C + v * V + k;
-    atomicAdd(&sums[o], s0[k]); atomicAdd(&sums[NC + o], s1[k]);
-    if (c0[k] != 0.f) atomicAdd(&sums[2 * NC + o], c0[k]);
-    if (c1[k] != 0.f) atomicAdd(&sums[3 * NC + o], c1[k]);
+    for (int k = 0; k < V; k++) {
+      int c = v * V + k;
+      atomicAdd(&sh_red[c], s0[k]); atomicAdd(&sh_red[C + c], s1[k]);
+      if (c0[k] != 0.f) atomicAdd(&sh_red[2 * C + c], c0[k]);
+      if (c1[k] != 0.f) atomicAdd(&sh_red[3 * C + c], c1[k]);
+    }
+  }
+  __syncthreads();
+  long long NC = (long long)N * C;
+  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    int q = i / C, c = i - q * C;
+    float val = sh_red[i];
+    if (val != 0.f) atomicAdd(&sums[q * NC + (long long)n * C + c], val);
   }
 }
 template <typename T, int V>
@@ -353,7 +412,7 @@ __global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __res
     int cv = (int)(i % CV);
     long long row = i / CV;
     int n = (int)(row / HW);
-    float a[4], g[4], o[4];
+    float a[kMaxV], g[kMaxV], o[kMaxV];
     ldv<T, V>(x + i * V, a);
     ldv<T, V>(gg + i * V, g);
 #pragma unroll
@@ -378,7 +437,7 @@ __global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __res
 template <typename T, int V>
 __global__ void act_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, long long nvec, int act, T* __restrict__ gx) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    float g[4], v[4], o[4];
+    float g[kMaxV], v[kMaxV], o[kMaxV];
     ldv<T, V>(gy + i * V, g);
     ldv<T, V>(y + i * V, v);
 #pragma unroll
@@ -400,7 +459,7 @@ template <typename T, int V>
 __global__ void gate_fma_fwd_kernel(const T* __restrict__ ht, const T* __restrict__ rg, const T* __restrict__ im, long long nvec,
                                     T* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    float a[4], b[4], c[4], o[4];
+    float a[kMaxV], b[kMaxV], c[kMaxV], o[kMaxV];
     ldv<T, V>(ht + i * V, a); ldv<T, V>(rg + i * V, b); ldv<T, V>(im + i * V, c);
 #pragma unroll
     for (int k = 0; k < V; k++) o[k] = a[k] + b[k] * c[k];
@@ -411,7 +470,7 @@ template <typename T, int V>
 __global__ void gate_fma_bwd_kernel(const T* __restrict__ g, const T* __restrict__ rg, const T* __restrict__ im, long long nvec,
                                     T* __restrict__ g_rg, T* __restrict__ g_im) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    float a[4], b[4], c[4], o1[4], o2[4];
+    float a[kMaxV], b[kMaxV], c[kMaxV], o1[kMaxV], o2[kMaxV];
     ldv<T, V>(g + i * V, a); ldv<T, V>(rg + i * V, b); ldv<T, V>(im + i * V, c);
 #pragma unroll
     for (int k = 0; k < V; k++) { o1[k] = a[k] * c[k]; o2[k] = a[k] * b[k]; }
@@ -445,11 +504,11 @@ __global__ void mul_up_fwd_kernel(const T* __restrict__ rg, const T* __restrict_
                                   T* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
     UpIdx u = up_index<V>(i, h, w, C);
-    float a[4];
+    float a[kMaxV];
     ldv<T, V>(ht + u.lo, a);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      float b[4], o[4];
+      float b[kMaxV], o[kMaxV];
       ldv<T, V>(rg + u.hi[j], b);
 #pragma unroll
       for (int k = 0; k < V; k++) o[k] = a[k] * b[k];
@@ -462,11 +521,11 @@ __global__ void mul_up_bwd_kernel(const T* __restrict__ g, const T* __restrict__
                                   int h, int w, int C, T* __restrict__ g_rg, T* __restrict__ g_ht) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
     UpIdx u = up_index<V>(i, h, w, C);
-    float a[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float a[kMaxV], acc[kMaxV] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     ldv<T, V>(ht + u.lo, a);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      float gg[4], b[4], o[4];
+      float gg[kMaxV], b[kMaxV], o[kMaxV];
       ldv<T, V>(g + u.hi[j], gg);
       ldv<T, V>(rg + u.hi[j], b);
 #pragma unroll
@@ -481,11 +540,11 @@ __global__ void blend_fwd_kernel(const T* __restrict__ sk, const T* __restrict__
                                  int h, int w, int C, T* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
     UpIdx u = up_index<V>(i, h, w, C);
-    float s[4];
+    float s[kMaxV];
     ldv<T, V>(sk + u.lo, s);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      float a[4], z[4], o[4];
+      float a[kMaxV], z[kMaxV], o[kMaxV];
       ldv<T, V>(h2 + u.hi[j], a);
       ldv<T, V>(zg + u.hi[j], z);
 #pragma unroll
@@ -500,11 +559,11 @@ __global__ void blend_bwd_kernel(const T* __restrict__ g, const T* __restrict__ 
                                  T* __restrict__ g_h2, T* __restrict__ g_zg) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
     UpIdx u = up_index<V>(i, h, w, C);
-    float s[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float s[kMaxV], acc[kMaxV] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     ldv<T, V>(sk + u.lo, s);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      float gg[4], a[4], z[4], o1[4], o2[4];
+      float gg[kMaxV], a[kMaxV], z[kMaxV], o1[kMaxV], o2[kMaxV];
       ldv<T, V>(g + u.hi[j], gg);
       ldv<T, V>(h2 + u.hi[j], a);
       ldv<T, V>(zg + u.hi[j], z);
@@ -525,10 +584,10 @@ __global__ void addpool_fwd_kernel(const T* __restrict__ a, const T* __restrict_
                                    T* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
     UpIdx u = up_index<V>(i, h, w, C);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[kMaxV] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      float p[4];
+      float p[kMaxV];
       ldv<T, V>(a + u.hi[j], p);
 #pragma unroll
       for (int k = 0; k < V; k++) acc[k] += p[k];
@@ -544,13 +603,13 @@ __global__ void addpool_fwd_kernel(const T* __restrict__ a, const T* __restrict_
   }
 }
 template <typename T, int V>
-__global__ void unpool_bwd_kernel(const T* __restrict__ g, long long nlow, int h, int w, int C, T* __restrict__ out) {
+__global__ void unpool_bwd_kernel(const T* __restrict__ g, long long nlow, int h, int w, int C, float scale, T* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
     UpIdx u = up_index<V>(i, h, w, C);
-    float a[4];
+    float a[kMaxV];
     ldv<T, V>(g + u.lo, a);
 #pragma unroll
-    for (int k = 0; k < V; k++) a[k] *= 0.25f;
+    for (int k = 0; k < V; k++) a[k] *= scale;
 #pragma unroll
     for (int j = 0; j < 4; j++) stv<T, V>(out + u.hi[j], a);
   }
@@ -574,7 +633,7 @@ __global__ void axpy_kernel(TD* __restrict__ dst, const TS* __restrict__ src, lo
 template <typename T, int V>
 __global__ void axpy_vec_kernel(T* __restrict__ dst, const T* __restrict__ src, long long nvec, float alpha) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    float a[4], b[4];
+    float a[kMaxV], b[kMaxV];
     ldv<T, V>(dst + i * V, a);
     ldv<T, V>(src + i * V, b);
 #pragma unroll
@@ -629,9 +688,9 @@ __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long l
 
 // choose block / rows-per-block for the per-(n,c) row reductions
 struct RowRed { int threads, V, lanes, rows_per_block, nblk; };
-static RowRed rowred_plan(int C, bool vec, long long rows, long long other_blocks) {
+static RowRed rowred_plan(int C, int vec, long long rows, long long other_blocks) {
   RowRed p;
-  p.V = vec ? 4 : 1;
+  p.V = vec >= 8 ? 8 : (vec >= 4 ? 4 : 1);
   int CV = C / p.V;
   p.threads = 256;
   if (CV > 256) p.threads = ((CV + 31) / 32) * 32;
@@ -658,7 +717,7 @@ int fgc_chan_stats(const void* x, int dtype, long long M, int C, double* acc, fl
   FGC_REQUIRE(M > 0 && C > 0 && C <= 1024, "chan_stats: bad shape M=%lld C=%d", M, C);
   cudaStream_t s = as_stream(stream);
   cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, s);
-  bool vec = vec4_ok(x, C, dtype);
+  int vec = vmin(vec_width(x, C, dtype), 4);     // reductions: 4-wide keeps the register count (occupancy) in check
   RowRed p = rowred_plan(C, vec, M, 1);
   FGC_DISPATCH_TV(dtype, vec, T, V,
                   (chan_stats_kernel<T, V><<<p.nblk, p.threads, 2 * C * sizeof(double), s>>>((const T*)x, M, C, p.rows_per_block, acc)));
@@ -672,7 +731,7 @@ int fgc_cbn_act_fwd(const void* x, int dtype, int N, int HW, int C, const float*
                     const float* offset, const int32_t* labels, int act, void* y, fgc_stream stream) {
   FGC_REQUIRE(act == FGC_ACT_NONE || act == FGC_ACT_MIU, "cbn_act_fwd: act %d", act);
   cudaStream_t s = as_stream(stream);
-  bool vec = vec4_ok(x, C, dtype) && vec4_ok(y, C, dtype);
+  int vec = vmin(vec_width(x, C, dtype), vec_width(y, C, dtype));
   long long n = (long long)N * HW * C;
   FGC_DISPATCH_TV(dtype, vec, T, V, {
     long long nvec = n / V;
@@ -687,16 +746,20 @@ int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int
                     const float* scale, const float* offset, const int32_t* labels, int act,
                     float* dscale, float* doffset, void* gx, float* scratch, fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
-  bool vec = vec4_ok(x, C, dtype) && vec4_ok(gy, C, dtype) && vec4_ok(gx, C, dtype);
+  int vec = vmin(vmin(vec_width(x, C, dtype), vec_width(gy, C, dtype)), vec_width(gx, C, dtype));
   float* sums = scratch;                       // [2,N,C]
   float* m12 = scratch + 2LL * N * C;          // [2,C]
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, s);
-  RowRed p = rowred_plan(C, vec, HW, N);
+  const int rvec = vmin(vec, 4);
+  RowRed p = rowred_plan(C, rvec, HW, N);
   long long n = (long long)N * HW * C;
+  FGC_DISPATCH_TV(dtype, rvec, T, V, {
+    cbn_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 2 * C * sizeof(float), s>>>((const T*)gy, (const T*)x, HW, C,
+                                                                                          p.rows_per_block, stats, scale, offset,
+                                                                                          labels, act, N, sums);
+  });
+  cbn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, N, C, (long long)N * HW, scale, labels, dscale, doffset, m12);
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    cbn_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 0, s>>>((const T*)gy, (const T*)x, HW, C, p.rows_per_block, stats,
-                                                                      scale, offset, labels, act, N, sums);
-    cbn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, N, C, (long long)N * HW, scale, labels, dscale, doffset, m12);
     long long nvec = n / V;
     cbn_bwd_apply_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)gy, (const T*)x, nvec, HW, C, stats, scale, offset,
                                                                   labels, act, m12, (T*)gx);
@@ -708,7 +771,7 @@ int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int
 
 int fgc_prelu_fwd(const void* x, int dtype, long long n, const float* a, void* y, fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
-  bool vec = vec4_ok(x, n, dtype) && vec4_ok(y, n, dtype);
+  int vec = vmin(vec_width(x, n, dtype), vec_width(y, n, dtype));
   FGC_DISPATCH_TV(dtype, vec, T, V, {
     long long nvec = n / V;
     prelu_fwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)x, nvec, a, (T*)y);
@@ -720,7 +783,7 @@ int fgc_prelu_fwd(const void* x, int dtype, long long n, const float* a, void* y
 int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, const float* a, float* da, void* gx,
                   fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
-  bool vec = vec4_ok(x, n, dtype) && vec4_ok(gy, n, dtype) && vec4_ok(gx, n, dtype);
+  int vec = vmin(vmin(vec_width(x, n, dtype), vec_width(gy, n, dtype)), vec_width(gx, n, dtype));
   FGC_DISPATCH_TV(dtype, vec, T, V, {
     long long nvec = n / V;
     prelu_bwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)gy, (const T*)x, nvec, a, da, (T*)gx);
@@ -733,15 +796,19 @@ int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, const f
 int fgc_minmax_fwd(const void* x, int dtype, int N, int HW, int C, void* gate, float* mn, float* mx,
                    uint32_t* scratch, fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
-  bool vec = vec4_ok(x, C, dtype) && vec4_ok(gate, C, dtype);
+  int vec = vmin(vec_width(x, C, dtype), vec_width(gate, C, dtype));
   uint32_t* mn_ord = scratch;
   uint32_t* mx_ord = scratch + (long long)N * C;
   cudaMemsetAsync(mn_ord, 0xFF, sizeof(uint32_t) * N * C, s);
   cudaMemsetAsync(mx_ord, 0x00, sizeof(uint32_t) * N * C, s);
-  RowRed p = rowred_plan(C, vec, HW, N);
+  const int rvec = vmin(vec, 4);
+  RowRed p = rowred_plan(C, rvec, HW, N);
   long long n = (long long)N * HW * C;
+  FGC_DISPATCH_TV(dtype, rvec, T, V, {
+    minmax_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 2 * C * sizeof(uint32_t), s>>>((const T*)x, HW, C, p.rows_per_block,
+                                                                                            mn_ord, mx_ord);
+  });
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    minmax_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 0, s>>>((const T*)x, HW, C, p.rows_per_block, mn_ord, mx_ord);
     long long nvec = n / V;
     minmax_apply_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)x, nvec, HW, C, mn_ord, mx_ord, (T*)gate, mn, mx);
   });
@@ -752,13 +819,16 @@ int fgc_minmax_fwd(const void* x, int dtype, int N, int HW, int C, void* gate, f
 int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, int C, const float* mn,
                    const float* mx, void* gpre, float* scratch, fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
-  bool vec = vec4_ok(x, C, dtype) && vec4_ok(ggate, C, dtype) && vec4_ok(gpre, C, dtype);
+  int vec = vmin(vmin(vec_width(x, C, dtype), vec_width(ggate, C, dtype)), vec_width(gpre, C, dtype));
   cudaMemsetAsync(scratch, 0, sizeof(float) * 4 * N * C, s);
-  RowRed p = rowred_plan(C, vec, HW, N);
+  const int rvec = vmin(vec, 4);
+  RowRed p = rowred_plan(C, rvec, HW, N);
   long long n = (long long)N * HW * C;
+  FGC_DISPATCH_TV(dtype, rvec, T, V, {
+    minmax_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 4 * C * sizeof(float), s>>>((const T*)ggate, (const T*)x, HW, C,
+                                                                                             p.rows_per_block, mn, mx, N, scratch);
+  });
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    minmax_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 0, s>>>((const T*)ggate, (const T*)x, HW, C, p.rows_per_block,
-                                                                         mn, mx, N, scratch);
     long long nvec = n / V;
     minmax_bwd_apply_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)ggate, (const T*)x, nvec, HW, C, mn, mx, N,
                                                                      scratch, (T*)gpre);
@@ -771,7 +841,7 @@ int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, i
 int fgc_act_bwd(const void* gy, const void* y, int dtype, long long n, int act, void* gx, fgc_stream stream) {
   FGC_REQUIRE(act == FGC_ACT_TANH || act == FGC_ACT_MIU, "act_bwd: act %d", act);
   cudaStream_t s = as_stream(stream);
-  bool vec = vec4_ok(gy, n, dtype) && vec4_ok(y, n, dtype) && vec4_ok(gx, n, dtype);
+  int vec = vmin(vmin(vec_width(gy, n, dtype), vec_width(y, n, dtype)), vec_width(gx, n, dtype));
   FGC_DISPATCH_TV(dtype, vec, T, V, {
     long long nvec = n / V;
     act_bwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)gy, (const T*)y, nvec, act, (T*)gx);
@@ -783,7 +853,7 @@ int fgc_act_bwd(const void* gy, const void* y, int dtype, long long n, int act, 
 
 int fgc_gate_fma_fwd(const void* ht, const void* rg, const void* im, int dtype, long long n, void* out, fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
-  bool vec = vec4_ok(ht, n, dtype) && vec4_ok(rg, n, dtype) && vec4_ok(im, n, dtype) && vec4_ok(out, n, dtype);
+  int vec = vmin(vmin(vmin(vec_width(ht, n, dtype), vec_width(rg, n, dtype)), vec_width(im, n, dtype)), vec_width(out, n, dtype));
   FGC_DISPATCH_TV(dtype, vec, T, V, {
     long long nvec = n / V;
     gate_fma_fwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)ht, (const T*)rg, (const T*)im, nvec, (T*)out);
@@ -795,8 +865,7 @@ int fgc_gate_fma_fwd(const void* ht, const void* rg, const void* im, int dtype, 
 int fgc_gate_fma_bwd(const void* g, const void* rg, const void* im, int dtype, long long n, void* g_rg, void* g_im,
                      fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
-  bool vec = vec4_ok(g, n, dtype) && vec4_ok(rg, n, dtype) && vec4_ok(im, n, dtype) && vec4_ok(g_rg, n, dtype) &&
-             vec4_ok(g_im, n, dtype);
+  int vec = vmin(vmin(vmin(vmin(vec_width(g, n, dtype), vec_width(rg, n, dtype)), vec_width(im, n, dtype)), vec_width(g_rg, n, dtype)), vec_width(g_im, n, dtype));
   FGC_DISPATCH_TV(dtype, vec, T, V, {
     long long nvec = n / V;
     gate_fma_bwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)g, (const T*)rg, (const T*)im, nvec, (T*)g_rg, (T*)g_im);
@@ -820,34 +889,37 @@ int fgc_gate_fma_bwd(const void* g, const void* rg, const void* im, int dtype, l
   } while (0)
 
 int fgc_mul_up_fwd(const void* rg, const void* ht_low, int dtype, int N, int h, int w, int C, void* out, fgc_stream stream) {
-  bool vec = vec4_ok(rg, C, dtype) && vec4_ok(ht_low, C, dtype) && vec4_ok(out, C, dtype);
+  int vec = vmin(vmin(vec_width(rg, C, dtype), vec_width(ht_low, C, dtype)), vec_width(out, C, dtype));
   FGC_UP_LAUNCH("mul_up_fwd", mul_up_fwd_kernel, (const T*)rg, (const T*)ht_low, nv, h, w, C, (T*)out);
 }
 int fgc_mul_up_bwd(const void* g, const void* rg, const void* ht_low, int dtype, int N, int h, int w, int C,
                    void* g_rg, void* g_ht_low, fgc_stream stream) {
-  bool vec = vec4_ok(g, C, dtype) && vec4_ok(rg, C, dtype) && vec4_ok(ht_low, C, dtype) && vec4_ok(g_rg, C, dtype) &&
-             vec4_ok(g_ht_low, C, dtype);
+  int vec = vmin(vmin(vmin(vmin(vec_width(g, C, dtype), vec_width(rg, C, dtype)), vec_width(ht_low, C, dtype)), vec_width(g_rg, C, dtype)), vec_width(g_ht_low, C, dtype));
   FGC_UP_LAUNCH("mul_up_bwd", mul_up_bwd_kernel, (const T*)g, (const T*)rg, (const T*)ht_low, nv, h, w, C, (T*)g_rg, (T*)g_ht_low);
 }
 int fgc_blend_fwd(const void* sk_low, const void* h2, const void* zg, int dtype, int N, int h, int w, int C, void* out,
                   fgc_stream stream) {
-  bool vec = vec4_ok(sk_low, C, dtype) && vec4_ok(h2, C, dtype) && vec4_ok(zg, C, dtype) && vec4_ok(out, C, dtype);
+  int vec = vmin(vmin(vmin(vec_width(sk_low, C, dtype), vec_width(h2, C, dtype)), vec_width(zg, C, dtype)), vec_width(out, C, dtype));
   FGC_UP_LAUNCH("blend_fwd", blend_fwd_kernel, (const T*)sk_low, (const T*)h2, (const T*)zg, nv, h, w, C, (T*)out);
 }
 int fgc_blend_bwd(const void* g, const void* sk_low, const void* h2, const void* zg, int dtype, int N, int h, int w, int C,
                   void* g_sk_low, void* g_h2, void* g_zg, fgc_stream stream) {
-  bool vec = vec4_ok(g, C, dtype) && vec4_ok(sk_low, C, dtype) && vec4_ok(h2, C, dtype) && vec4_ok(zg, C, dtype) &&
-             vec4_ok(g_sk_low, C, dtype) && vec4_ok(g_h2, C, dtype) && vec4_ok(g_zg, C, dtype);
+  int vec = vmin(vmin(vmin(vmin(vmin(vmin(vec_width(g, C, dtype), vec_width(sk_low, C, dtype)), vec_width(h2, C, dtype)), vec_width(zg, C, dtype)), vec_width(g_sk_low, C, dtype)), vec_width(g_h2, C, dtype)), vec_width(g_zg, C, dtype));
   FGC_UP_LAUNCH("blend_bwd", blend_bwd_kernel, (const T*)g, (const T*)sk_low, (const T*)h2, (const T*)zg, nv, h, w, C,
                 (T*)g_sk_low, (T*)g_h2, (T*)g_zg);
 }
 int fgc_addpool_fwd(const void* a, const void* b, int dtype, int N, int h, int w, int C, void* out, fgc_stream stream) {
-  bool vec = vec4_ok(a, C, dtype) && (!b || vec4_ok(b, C, dtype)) && vec4_ok(out, C, dtype);
+  int vec = vmin(vmin(vec_width(a, C, dtype), b ? vec_width(b, C, dtype) : 8), vec_width(out, C, dtype));
   FGC_UP_LAUNCH("addpool_fwd", addpool_fwd_kernel, (const T*)a, (const T*)b, nv, h, w, C, (T*)out);
 }
 int fgc_unpool_bwd(const void* g, int dtype, int N, int h, int w, int C, void* out, fgc_stream stream) {
-  bool vec = vec4_ok(g, C, dtype) && vec4_ok(out, C, dtype);
-  FGC_UP_LAUNCH("unpool_bwd", unpool_bwd_kernel, (const T*)g, nv, h, w, C, (T*)out);
+  int vec = vmin(vec_width(g, C, dtype), vec_width(out, C, dtype));
+  FGC_UP_LAUNCH("unpool_bwd", unpool_bwd_kernel, (const T*)g, nv, h, w, C, 0.25f, (T*)out);
+}
+int fgc_upsample2x(const void* x, int dtype, int N, int h, int w, int C, void* out, fgc_stream stream) {
+  int vec = vmin(vec_width(x, C, dtype), vec_width(out, C, dtype));
+  const void* g = x;
+  FGC_UP_LAUNCH("upsample2x", unpool_bwd_kernel, (const T*)g, nv, h, w, C, 1.0f, (T*)out);
 }
 
 int fgc_sum2x2(const void* g, int g_dtype, int N, int h, int w, int C, void* out, int out_dtype, int accumulate,
@@ -871,7 +943,11 @@ int fgc_sum2x2(const void* g, int g_dtype, int N, int h, int w, int C, void* out
 
 int fgc_axpy(void* dst, const void* src, int dst_dtype, int src_dtype, long long n, float alpha, fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
-  if (dst_dtype == src_dtype && vec4_ok(dst, n, dst_dtype) && vec4_ok(src, n, src_dtype)) {
+  int vw = dst_dtype == src_dtype ? vmin(vec_width(dst, n, dst_dtype), vec_width(src, n, src_dtype)) : 1;
+  if (vw >= 8) {
+    if (dst_dtype == FGC_F32) axpy_vec_kernel<float, 8><<<ew_grid(n / 8, 256), 256, 0, s>>>((float*)dst, (const float*)src, n / 8, alpha);
+    else axpy_vec_kernel<__nv_bfloat16, 8><<<ew_grid(n / 8, 256), 256, 0, s>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, n / 8, alpha);
+  } else if (vw >= 4) {
     if (dst_dtype == FGC_F32) axpy_vec_kernel<float, 4><<<ew_grid(n / 4, 256), 256, 0, s>>>((float*)dst, (const float*)src, n / 4, alpha);
     else axpy_vec_kernel<__nv_bfloat16, 4><<<ew_grid(n / 4, 256), 256, 0, s>>>((__nv_bfloat16*)dst, (const __nv_bfloat16*)src, n / 4, alpha);
   } else {

@@ -261,6 +261,12 @@ class CudaOps(OpsBase):
         check(self.lib.fgc_unpool_bwd(self._p(g), self._dt(g), N, h, w, Cc, self._p(out), self._s()), "unpool_bwd")
         return out
 
+    def upsample_fwd(self, x):
+        N, h, w, Cc = x.shape
+        out = self._empty((N, 2 * h, 2 * w, Cc), x.dtype)
+        check(self.lib.fgc_upsample2x(self._p(x), self._dt(x), N, h, w, Cc, self._p(out), self._s()), "upsample2x")
+        return out
+
     def zeros_f32(self, shape):
         return torch.zeros(shape, dtype=torch.float32, device=self.device)
 
@@ -432,6 +438,7 @@ def enable_op_timing(ops):
     collect per-operator totals in ops.op_times = {name: [calls, ms]}.  Used by scripts/op_breakdown.py only."""
     import functools
     ops.op_times = {}
+    ops.op_detail = {}
 
     def wrap(name, fn):
         @functools.wraps(fn)
@@ -442,11 +449,25 @@ def enable_op_timing(ops):
             e1.record()
             e1.synchronize()
             key = name
+            ms = e0.elapsed_time(e1)
             if name in ("conv_fwd", "conv_dgrad", "conv_wgrad"):
-                key = name + ("/f32" if (a[0][0][0] if name != "conv_dgrad" else a[0]).dtype == torch.float32 else "")
+                t0 = a[0][0][0] if name != "conv_dgrad" else a[0]
+                key = name + ("/f32" if t0.dtype == torch.float32 else "")
+                if name == "conv_dgrad":
+                    sig = "%s gy%s k%d cin%d[%d:+%d]%s" % (key, tuple(a[0].shape), a[1].shape[0], a[1].shape[2], a[2], a[3],
+                                                          " ups" if k.get("ups") else "")
+                else:
+                    wshape = a[1].shape if name == "conv_fwd" else a[2].shape
+                    sig = "%s N%d %dx%d srcs[%s] k%d cout%d" % (key, t0.shape[0], t0.shape[1] * (2 if a[0][0][1] else 1),
+                                                               t0.shape[2] * (2 if a[0][0][1] else 1),
+                                                               ",".join("%d%s" % (t.shape[3], "u" if u else "") for t, u in a[0]),
+                                                               wshape[0], wshape[3])
+                d = ops.op_detail.setdefault(sig, [0, 0.0])
+                d[0] += 1
+                d[1] += ms
             t = ops.op_times.setdefault(key, [0, 0.0])
             t[0] += 1
-            t[1] += e0.elapsed_time(e1)
+            t[1] += ms
             return r
         return inner
 

@@ -108,6 +108,10 @@ class OpsBase:
     def meanpool_fwd(self, x):
         raise NotImplementedError
 
+    def upsample_fwd(self, x):
+        """up2(x), materialised (only the weight-gradient path wants it in memory)"""
+        raise NotImplementedError
+
     def zeros_f32(self, shape):
         raise NotImplementedError
 

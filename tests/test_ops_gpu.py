@@ -233,6 +233,7 @@ def test_gating(env, shape, dt):
     close(cu.addpool_fwd(a, b), ref.addpool_fwd(D(a), D(b)), tol, "addpool")
     close(cu.meanpool_fwd(a), ref.meanpool_fwd(D(a)), tol, "meanpool")
     close(cu.unpool_bwd(lo), ref.unpool_bwd(D(lo)), tol, "unpool")
+    assert torch.equal(cu.upsample_fwd(lo), ref.upsample_fwd(lo))
     close(cu.spatial_mean_fwd(a), ref.spatial_mean_fwd(D(a)), tol, "spatial_mean")
     sm = cu.spatial_mean_fwd(a)
     close(cu.spatial_mean_bwd(sm, 2 * h, 2 * w), ref.spatial_mean_bwd(D(sm), 2 * h, 2 * w), tol, "spatial_mean_bwd")

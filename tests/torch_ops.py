@@ -202,6 +202,9 @@ class TorchOps(OpsBase):
     def meanpool_fwd(self, x):
         return (_sum2(self._c(x)) / 4).to(x.dtype)
 
+    def upsample_fwd(self, x):
+        return _up(x).contiguous()
+
     def zeros_f32(self, shape):
         return torch.zeros(shape, dtype=self.cdt, device=self.device)
 
