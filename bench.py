@@ -242,6 +242,9 @@ def run_product(args):
     if rank == 0:
         sampler.start()
     n0 = ops.launch_count()
+    ncu_range = bool(os.environ.get("FGC_NCU_RANGE"))      # `ncu --profile-from-start off`: list only the timed region
+    if ncu_range:
+        torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_host0 = time.perf_counter()
@@ -250,6 +253,8 @@ def run_product(args):
     host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps      # time to ENQUEUE one step (no sync inside)
     e1.record()
     barrier()
+    if ncu_range:
+        torch.cuda.profiler.stop()
     launches = ops.launch_count() - n0
     if graphs:          # launches are recorded once at capture; every replay re-issues all of them
         launches = args.steps * sum(tr.launches_per_step.values())
