@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libfgcolor.so")
-SOURCES = ["api.cu", "elementwise.cu", "text.cu", "sn.cu", "loss.cu", "conv_simple.cu", "conv_tc.cu", "conv_api.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "text.cu", "sn.cu", "loss.cu", "conv_simple.cu", "conv_small.cu", "conv_tc.cu", "conv_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -175,7 +175,10 @@ def dec_block_fwd(ops, wv, scope, xs, ht_low, cout, labels, save=True):
     """xs: list of full-resolution extra sources (sketch level first); ht_low: hidden state at half resolution."""
     st = wv.store
     chid = ht_low.shape[-1]
-    f = [(ht_low, True)] + [(x, False) for x in xs]
+    # H = upsample(ht) is written once and read by both gate convolutions (and by their weight gradients): tensor-map
+    # TMA, which feeds the halo-reuse conv kernel, cannot replicate pixels.  The 1x1 skip below still runs at low resolution.
+    h_up = ops.upsample_fwd(ht_low)
+    f = [(h_up, False)] + [(x, False) for x in xs]
     w, b = wv.get(scope + "/Conv")
     rg_raw = ops.conv_fwd(f, w, b, act=ACT_LRELU)                                # mru.py:555-559
     rg, mn0, mx0 = ops.minmax_fwd(rg_raw)
@@ -200,7 +203,7 @@ def dec_block_fwd(ops, wv, scope, xs, ht_low, cout, labels, save=True):
     ctx = None
     if save:
         ctx = dict(xs=xs, ht_low=ht_low, rg_raw=rg_raw, rg=rg, mn0=mn0, mx0=mx0, zg_raw=zg_raw, zg=zg, mn1=mn1,
-                   mx1=mx1, gh=gh, c_h1=c_h1, h1=h1, c_h2=c_h2, h2=h2, c_sk=c_sk, sk=sk, cout=cout)
+                   mx1=mx1, gh=gh, c_h1=c_h1, h1=h1, c_h2=c_h2, h2=h2, c_sk=c_sk, sk=sk, cout=cout, h_up=h_up)
     return out, ctx
 
 
@@ -209,7 +212,6 @@ def dec_block_bwd(ops, wv, scope, g_out, ctx, labels, xs_need_grad):
     st = wv.store
     xs, ht_low, cout = ctx["xs"], ctx["ht_low"], ctx["cout"]
     chid = ht_low.shape[-1]
-    f = [(ht_low, True)] + [(x, False) for x in xs]
     offs, o = [], chid
     for x in xs:
         offs.append(o)
@@ -244,9 +246,8 @@ def dec_block_bwd(ops, wv, scope, g_out, ctx, labels, xs_need_grad):
     del g_gh
     ops.add_(g_ht, g_ht_mul)
     del g_ht_mul
-    # gates.  The weight-gradient kernel fetches its tiles with tensor TMA, which cannot replicate pixels: give it the
-    # upsampled hidden state in memory (one write of H, read by both gate wgrads) instead of the (ht_low, ups) view.
-    f_w = [(ops.upsample_fwd(ht_low), False)] + [(x, False) for x in xs]
+    # gates: the weight gradients read the upsampled hidden state kept by the forward pass
+    f_w = [(ctx["h_up"], False)] + [(x, False) for x in xs]
     for (gg, raw, mn, mx, sc) in ((g_rg, ctx["rg_raw"], ctx["mn0"], ctx["mx0"], scope + "/Conv"),
                                   (g_zg, ctx["zg_raw"], ctx["mn1"], ctx["mx1"], scope + "/Conv_1")):
         g_raw = ops.minmax_bwd(gg, raw, mn, mx)

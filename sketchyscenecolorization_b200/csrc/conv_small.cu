@@ -1,0 +1,285 @@
+// CUDA-core direct convolutions for the narrow layers of the MRU networks (sm_100a).
+//
+// The stem-level layers -- 7x7 3 -> 8 stems (models_collection.py:93,710), the unit-1 gates 11 -> 8 and image
+// branches 3 -> 8 (mru.py:408-424) and the input gradients that end in 8 or 3 channels -- carry < 0.5% of the FLOPs
+// but run at 192x192: on the tensor path they pay a 64-wide K slab and a 16-wide N tile for 3..11 real channels and
+// a scalar gather per element.  They are HBM-bound streaming layers, so they get direct kernels:
+//   conv_small_fwd_kernel   : one thread per output pixel, all (<= 8) output channels in registers; the input tile
+//                             (with halo) and the weights sit in shared memory as fp32.  Serves forward and (with
+//                             mirrored taps / transposed weight addressing) input-gradient calls.
+//   conv_small_wgrad_kernel : one thread per row of dW[k*k*Cin, Cout<=8], persistent CTAs walk 16x16 pixel tiles and
+//                             keep the partial dW in registers; one red.add per entry and CTA at the end.
+// Eligibility: every source "small" (C < 64 or C % 8 != 0, conv_geom.cuh), <= 8 output channels.
+#include "conv_geom.cuh"
+
+namespace fgc {
+int num_sms();
+
+constexpr int kTS = 16;        // output tile edge
+
+struct SmallArgs {
+  ConvGeom g;
+  const float* w;            // value(tap, c, n) = w[tap*tap_stride + c*k_stride + n*n_stride + base]
+  long long tap_stride, k_stride, n_stride, base;
+  int nout;
+  const float* bias;
+  int act, accumulate;
+  void* y;
+  int y_dtype;
+  int ctot;
+  int tile_h, tile_w;        // input tile extent: (kTS-1)*stride + k
+  int tiles_x, tiles_y;
+};
+
+__device__ __forceinline__ float small_act(float v, int act) {
+  switch (act) {
+    case FGC_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
+    case FGC_ACT_TANH: return tanhf(v);
+    case FGC_ACT_MIU: return miu_relu(v);
+    default: return v;
+  }
+}
+
+// input tile of every source -> shared memory, channel-planar fp32 [ctot][tile_h][tile_w], zero outside the image
+template <typename T>
+__device__ __forceinline__ void load_x_tile(const ConvGeom& g, int n, int ih0, int iw0, int tile_h, int tile_w, float* xt) {
+  const int plane = tile_h * tile_w;
+  for (int s = 0; s < g.nsrc; s++) {
+    const T* src = reinterpret_cast<const T*>(g.src[s]);
+    const int C = g.C[s], ups = g.ups[s];
+    const int Hs = ups ? (g.H >> 1) : g.H, Ws = ups ? (g.W >> 1) : g.W;
+    float* dst = xt + g.cbase[s] * plane;
+    for (int idx = threadIdx.x; idx < plane * C; idx += blockDim.x) {
+      const int c = idx % C, pos = idx / C;
+      const int r = pos / tile_w, col = pos - r * tile_w;
+      int ih = ih0 + r, iw = iw0 + col;
+      float v = 0.f;
+      if ((unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W) {
+        if (ups) { ih >>= 1; iw >>= 1; }
+        v = ld1<T>(src + (((long long)n * Hs + ih) * Ws + iw) * C + c);
+      }
+      dst[c * plane + pos] = v;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_small_fwd_kernel(const __grid_constant__ SmallArgs a) {
+  extern __shared__ __align__(16) float sm_small[];
+  const ConvGeom& g = a.g;
+  const int k = g.k, ctot = a.ctot, KK = k * k * ctot;
+  float* wsm = sm_small;                     // [KK][8]
+  float* xt = sm_small + KK * 8;             // [ctot][tile_h][tile_w]
+  const int tid = threadIdx.x;
+  int bt = blockIdx.x;
+  const int tx = bt % a.tiles_x; bt /= a.tiles_x;
+  const int ty = bt % a.tiles_y;
+  const int n = bt / a.tiles_y;
+  for (int i = tid; i < KK * 8; i += blockDim.x) {
+    const int q = i >> 3, co = i & 7;
+    const int tap = q / ctot, c = q - tap * ctot;
+    wsm[i] = co < a.nout ? __ldg(a.w + tap * a.tap_stride + c * a.k_stride + co * a.n_stride + a.base) : 0.f;
+  }
+  // input row of output row oh under filter row kh:  oh*stride + sign*(kh - pad_t)
+  const int org_h = g.sign > 0 ? -g.pad_t : g.pad_t - (k - 1);
+  const int org_w = g.sign > 0 ? -g.pad_l : g.pad_l - (k - 1);
+  load_x_tile<T>(g, n, ty * kTS * g.stride + org_h, tx * kTS * g.stride + org_w, a.tile_h, a.tile_w, xt);
+  __syncthreads();
+  const int ly = tid >> 4, lx = tid & 15;
+  const int plane = a.tile_h * a.tile_w;
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) acc[q] = 0.f;
+  for (int kh = 0; kh < k; kh++) {
+    const int khl = g.sign > 0 ? kh : k - 1 - kh;
+    for (int kw = 0; kw < k; kw++) {
+      const int kwl = g.sign > 0 ? kw : k - 1 - kw;
+      const float* xp = xt + (ly * g.stride + khl) * a.tile_w + lx * g.stride + kwl;
+      const float4* wp = reinterpret_cast<const float4*>(wsm + (size_t)(kh * k + kw) * ctot * 8);
+#pragma unroll 4
+      for (int c = 0; c < ctot; c++) {
+        const float x = xp[c * plane];
+        const float4 w0 = wp[2 * c], w1 = wp[2 * c + 1];
+        acc[0] += x * w0.x; acc[1] += x * w0.y; acc[2] += x * w0.z; acc[3] += x * w0.w;
+        acc[4] += x * w1.x; acc[5] += x * w1.y; acc[6] += x * w1.z; acc[7] += x * w1.w;
+      }
+    }
+  }
+  const int oh = ty * kTS + ly, ow = tx * kTS + lx;
+  if (oh >= g.OH || ow >= g.OW) return;
+  const long long m = ((long long)n * g.OH + oh) * g.OW + ow;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    float v = acc[q];
+    if (a.bias && q < a.nout) v += __ldg(a.bias + q);
+    acc[q] = small_act(v, a.act);
+  }
+  if (a.y_dtype == FGC_F32) {
+    float* yp = reinterpret_cast<float*>(a.y) + m * a.nout;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (q < a.nout) yp[q] = a.accumulate ? yp[q] + acc[q] : acc[q];
+  } else {
+    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.nout;
+    if (a.nout == 8 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
+      if (a.accumulate) {
+        uint4 p = *reinterpret_cast<const uint4*>(yp);
+        const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&p);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          float2 f = __bfloat1622float2(pp[e]);
+          acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+        }
+      }
+      *reinterpret_cast<uint4*>(yp) = make_uint4(bf16x2_bits(acc[0], acc[1]), bf16x2_bits(acc[2], acc[3]),
+                                                 bf16x2_bits(acc[4], acc[5]), bf16x2_bits(acc[6], acc[7]));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        if (q < a.nout) yp[q] = __float2bfloat16_rn(a.accumulate ? __bfloat162float(yp[q]) + acc[q] : acc[q]);
+    }
+  }
+}
+
+struct SmallWgradArgs {
+  ConvGeom g;
+  const void* gy;            // [N, OH, OW, Cout]
+  int Cout;
+  int ctot;
+  float* dw;                 // HWIO fp32 [k*k*ctot][Cout], accumulated
+  int tile_h, tile_w;
+  int tiles_x, tiles_y, ntiles;
+  int KKP, S;                // threads per pixel slice (multiple of 32), pixel slices per CTA
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const __grid_constant__ SmallWgradArgs a) {
+  extern __shared__ __align__(16) float sm_small[];
+  const ConvGeom& g = a.g;
+  const int k = g.k, ctot = a.ctot, KK = k * k * ctot;
+  const int plane = a.tile_h * a.tile_w;
+  float* xt = sm_small;                          // [ctot][tile_h][tile_w]
+  float* gyt = sm_small + ((ctot * plane + 3) & ~3);   // [256][8], 16-byte aligned rows
+  const int tid = threadIdx.x;
+  const int kk = tid % a.KKP, slice = tid / a.KKP;
+  const bool active = kk < KK;
+  int xoff = 0;
+  if (active) {
+    const int tap = kk / ctot, c = kk - tap * ctot;
+    const int kh = tap / k, kw = tap - kh * k;
+    xoff = c * plane + kh * a.tile_w + kw;
+  }
+  float acc[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) acc[q] = 0.f;
+  const T* gy = reinterpret_cast<const T*>(a.gy);
+  for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+    int bt = t;
+    const int tx = bt % a.tiles_x; bt /= a.tiles_x;
+    const int ty = bt % a.tiles_y;
+    const int n = bt / a.tiles_y;
+    __syncthreads();                             // previous tile fully consumed
+    load_x_tile<T>(g, n, ty * kTS * g.stride - g.pad_t, tx * kTS * g.stride - g.pad_l, a.tile_h, a.tile_w, xt);
+    for (int i = tid; i < 256 * 8; i += blockDim.x) {
+      const int p = i >> 3, co = i & 7;
+      const int oh = ty * kTS + (p >> 4), ow = tx * kTS + (p & 15);
+      float v = 0.f;
+      if (co < a.Cout && oh < g.OH && ow < g.OW) v = ld1<T>(gy + (((long long)n * g.OH + oh) * g.OW + ow) * a.Cout + co);
+      gyt[i] = v;
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int p = slice; p < 256; p += a.S) {
+        const float x = xt[xoff + ((p >> 4) * a.tile_w + (p & 15)) * g.stride];
+        const float4 g0 = *reinterpret_cast<const float4*>(gyt + p * 8), g1 = *reinterpret_cast<const float4*>(gyt + p * 8 + 4);
+        acc[0] += x * g0.x; acc[1] += x * g0.y; acc[2] += x * g0.z; acc[3] += x * g0.w;
+        acc[4] += x * g1.x; acc[5] += x * g1.y; acc[6] += x * g1.z; acc[7] += x * g1.w;
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (q < a.Cout) atomicAdd(a.dw + (long long)kk * a.Cout + q, acc[q]);
+  }
+}
+
+static bool all_small(const ConvGeom& g) {
+  for (int i = 0; i < g.nsrc; i++)
+    if (g.big[i]) return false;
+  return true;
+}
+static int small_mode() {
+  static int mode = -1;        // FGC_SMALL=0 sends the narrow layers through the tensor-core path as well
+  if (mode < 0) { const char* e = getenv("FGC_SMALL"); mode = e ? atoi(e) : 1; }
+  return mode;
+}
+
+// returns -1 when the layer is not eligible, else the launch status
+int conv_small_fwd_try(const ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride,
+                       long long n_stride, long long base, int nout, const float* bias, int act, int accumulate, void* y,
+                       int y_dtype, cudaStream_t s) {
+  if (!small_mode() || !all_small(g) || nout > 8) return -1;
+  if (g.sign < 0 && g.stride != 1) return -1;
+  SmallArgs a;
+  a.g = g;
+  a.w = w; a.tap_stride = tap_stride; a.k_stride = k_stride; a.n_stride = n_stride; a.base = base;
+  a.nout = nout; a.bias = bias; a.act = act; a.accumulate = accumulate; a.y = y; a.y_dtype = y_dtype;
+  a.ctot = g.cbase[g.nsrc - 1] + g.C[g.nsrc - 1];
+  a.tile_h = a.tile_w = (kTS - 1) * g.stride + g.k;
+  a.tiles_x = (g.OW + kTS - 1) / kTS;
+  a.tiles_y = (g.OH + kTS - 1) / kTS;
+  size_t smem = sizeof(float) * ((size_t)g.k * g.k * a.ctot * 8 + (size_t)a.ctot * a.tile_h * a.tile_w);
+  if (smem > 96 * 1024) return -1;
+  long long blocks = (long long)g.N * a.tiles_x * a.tiles_y;
+  if (blocks > 0x7FFFFFFFLL) return -1;
+  if (src_dtype == FGC_F32) {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(conv_small_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
+    conv_small_fwd_kernel<float><<<(int)blocks, 256, smem, s>>>(a);
+  } else {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(conv_small_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
+    conv_small_fwd_kernel<__nv_bfloat16><<<(int)blocks, 256, smem, s>>>(a);
+  }
+  count_launch();
+  return check_launch("conv_small_fwd");
+}
+
+int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s) {
+  if (!small_mode() || !all_small(g) || Cout > 8 || g.sign < 0) return -1;
+  const int KK = g.k * g.k * Cin_total;
+  if (KK > 512) return -1;
+  SmallWgradArgs a;
+  a.g = g;
+  a.gy = gy; a.Cout = Cout; a.ctot = Cin_total; a.dw = dw;
+  a.tile_h = a.tile_w = (kTS - 1) * g.stride + g.k;
+  a.tiles_x = (g.OW + kTS - 1) / kTS;
+  a.tiles_y = (g.OH + kTS - 1) / kTS;
+  long long ntiles = (long long)g.N * a.tiles_x * a.tiles_y;
+  if (ntiles > 0x7FFFFFFFLL) return -1;
+  a.ntiles = (int)ntiles;
+  a.KKP = ((KK + 31) / 32) * 32;
+  a.S = 512 / a.KKP;
+  if (a.S < 1) a.S = 1;
+  if (a.S > 16) a.S = 16;
+  const int threads = a.KKP * a.S;
+  size_t smem = sizeof(float) * ((((size_t)Cin_total * a.tile_h * a.tile_w + 3) & ~(size_t)3) + 256 * 8);
+  if (smem > 96 * 1024) return -1;
+  int grid = num_sms() * 2;
+  if (grid > a.ntiles) grid = a.ntiles;
+  if (src_dtype == FGC_F32) {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(conv_small_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
+    conv_small_wgrad_kernel<float><<<grid, threads, smem, s>>>(a);
+  } else {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(conv_small_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
+    conv_small_wgrad_kernel<__nv_bfloat16><<<grid, threads, smem, s>>>(a);
+  }
+  count_launch();
+  return check_launch("conv_small_wgrad");
+}
+
+}  // namespace fgc

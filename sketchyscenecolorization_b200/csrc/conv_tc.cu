@@ -749,6 +749,328 @@ __global__ void __launch_bounds__(32 * (8 * MT + 2), 1) conv_igemm_kernel(const 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// forward / dgrad with halo reuse: stride-1 SAME convolutions over bf16 sources  (conv_halo_kernel)
+//
+// conv_igemm_kernel re-fetches the activation tile once per filter tap, so a 3x3 layer pulls 9x its input through
+// L2 -> shared memory; at 128 -> 128 channels that traffic (8.1 GB per launch at 192x192x64), not the tensor pipe,
+// bounds the kernel (ncu: 7.2 TB/s of L2 -> SM reads, tensor pipe 29% active).  Here an M tile is a th x 8 pixel
+// rectangle of one image (th = 16*MT) and, per 64-channel group and filter COLUMN kw, ONE tensor-map TMA box of
+// (th + k - 1) rows x 8 pixels x 64 channels lands in shared memory (out-of-image rows / columns zero filled = SAME
+// padding).  A box row is 8 pixels x 128 B = one 1024-byte swizzle atom, so the A operand of filter row kh is the
+// same box read through a descriptor advanced by kh atoms: k taps per box, 3x fewer activation bytes for 3x3,
+// 7x fewer for 7x7, and no producer-warp address arithmetic at all.
+//   warps 0-3   : producers for "small" sources only (3-channel sketch pyramid, 8-channel stem features): flattened
+//                 (tap, channel) slabs gathered into a plain A tile, as in conv_igemm_kernel
+//   warp 4      : MMA issuer (+ TMEM allocation)        warp 5 : A loader (tensor TMA)
+//   warp 6      : B loader (bulk TMA of packed weights)  warps 8.. : epilogue (4 per 128-pixel sub-tile)
+// A boxes and B slabs run through separate mbarrier rings across tile boundaries; accumulators are double buffered
+// in TMEM when they fit.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kMaxItems = 160;
+struct HaloArgs {
+  ConvGeom g;
+  const __nv_bfloat16* wp;   // packed weights [slab][Npad][64], pre-swizzled
+  int Npad, Nout;
+  const float* bias;
+  int act, accumulate;
+  void* y;
+  int y_dtype, vec_ok;
+  const int4* tbl;           // slab table written by pack_weights_kernel (small slabs: source and first flattened index)
+  int any_small;
+  int box_rows;              // 16*MT + k - 1
+  int a_slot_bytes;          // box_rows * 1024  (>= MT * 16384)
+  int a_slots, b_slots;
+  int tiles_w, tiles_per_img, tiles_m;
+  int nitems;
+  // K-loop of one tile.  big item: bit 15 | source << 12 | kw << 8 | channel group  -> one box, k weight slabs (kh = 0..k-1);
+  // small item: global slab index -> one gathered A tile, one weight slab
+  uint16_t items[kMaxItems];
+  CUtensorMap tm[kMaxSrc];
+};
+
+template <int BN, int MT, int NACC>
+__global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
+  static_assert(NACC * MT * BN <= 512, "accumulators exceed TMEM");
+  constexpr int B_BYTES = BN * 128;
+  constexpr int ACC_COLS = MT * BN;
+  constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : (NACC * ACC_COLS <= 64 ? 64 : (NACC * ACC_COLS <= 128 ? 128 : (NACC * ACC_COLS <= 256 ? 256 : 512)));
+  constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
+  constexpr int MMA_WARP = 4, ALOAD_WARP = 5, BLOAD_WARP = 6, EPI_WARP0 = 8;
+  constexpr int TH = 16 * MT;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int a_slots = a.a_slots, b_slots = a.b_slots;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)a_slots * a.a_slot_bytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + (size_t)b_slots * B_BYTES);
+  uint64_t* a_empty = a_full + a_slots;
+  uint64_t* b_full = a_empty + a_slots;
+  uint64_t* b_empty = b_full + b_slots;
+  uint64_t* acc_full = b_empty + b_slots;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NACC);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const ConvGeom& g = a.g;
+  const int k = g.k, pad = g.pad_t, sign = g.sign;
+  const int tiles_n = a.Npad / BN;
+  const int ntiles = a.tiles_m * tiles_n;
+  const int nitems = a.nitems;
+
+  if (tid == 0) {
+    for (int s = 0; s < a_slots; s++) {
+      mbar_init(smem_u32(&a_full[s]), 1 + (a.any_small ? 128 : 0));   // A loader (+ the small-source producers)
+      mbar_init(smem_u32(&a_empty[s]), 1);                            // tcgen05.commit
+    }
+    for (int s = 0; s < b_slots; s++) {
+      mbar_init(smem_u32(&b_full[s]), 1);
+      mbar_init(smem_u32(&b_empty[s]), 1);
+    }
+    for (int i = 0; i < NACC; i++) {
+      mbar_init(smem_u32(&acc_full[i]), 1);
+      mbar_init(smem_u32(&acc_empty[i]), 128 * MT);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers of the small-source slabs =====================
+    if (a.any_small) {
+      const PixDec pd = pix_dec(g);
+      int ga = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tm = t / tiles_n;
+        const int n = tm / a.tiles_per_img, rr = tm - n * a.tiles_per_img;
+        const int ty = rr / a.tiles_w, tx = rr - ty * a.tiles_w;
+        uint32_t pixrow[MT];
+#pragma unroll
+        for (int tt = 0; tt < MT; tt++) {
+          const int oh = ty * TH + 16 * tt + (tid >> 3), ow = tx * 8 + (tid & 7);
+          pixrow[tt] = (oh < g.OH && ow < g.OW) ? (((uint32_t)n << (g.ow_bits + g.oh_bits)) | ((uint32_t)oh << g.ow_bits) | (uint32_t)ow)
+                                                : PIX_INVALID;
+        }
+        for (int it = 0; it < nitems; it++, ga++) {
+          const int slot = ga % a_slots;
+          const uint32_t ph = (ga / a_slots) & 1;
+          const uint32_t item = a.items[it];
+          mbar_wait(smem_u32(&a_empty[slot]), ph ^ 1);
+          if (!(item & 0x8000u)) {
+            const int4 e = __ldg(a.tbl + item);
+            const int si_s = e.x & 0xFF;
+            const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(g.src[si_s]);
+            uint8_t* dst = sA + (size_t)slot * a.a_slot_bytes;
+#pragma unroll
+            for (int tt = 0; tt < MT; tt++)
+              gather_small<__nv_bfloat16, 128>(dst + tt * 16384, dst + tt * 16384, src, g.C[si_s], e.w, g.ups[si_s], g.H, g.W, 1, k,
+                                               g.pad_t, g.pad_l, sign, &pixrow[tt], pd, tid);
+            fence_proxy_async();
+          }
+          mbar_arrive(smem_u32(&a_full[slot]));
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ===================== MMA issuer =====================
+    int ga = 0, gb = 0, ti = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ti++) {
+      const int buf = ti % NACC;
+      mbar_wait(smem_u32(&acc_empty[buf]), ((ti / NACC) & 1) ^ 1);
+      tc_fence_after();
+      for (int it = 0; it < nitems; it++, ga++) {
+        const int slot = ga % a_slots;
+        const uint32_t item = a.items[it];
+        const bool big = (item & 0x8000u) != 0;
+        const int nb = big ? k : 1;
+        mbar_wait(smem_u32(&a_full[slot]), (ga / a_slots) & 1);
+        const uint32_t sa = smem_u32(sA + (size_t)slot * a.a_slot_bytes);
+        for (int j = 0; j < nb; j++, gb++) {
+          const int bslot = gb % b_slots;
+          mbar_wait(smem_u32(&b_full[bslot]), (gb / b_slots) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t db = desc_kmajor(smem_u32(sB + (size_t)bslot * B_BYTES), 1024);
+            // box row of output row r under filter row kh = j:  r + j (forward) or r + k-1-j (mirrored taps of dgrad)
+            const int jrow = big ? (sign > 0 ? j : k - 1 - j) : 0;
+#pragma unroll
+            for (int tt = 0; tt < MT; tt++) {
+              const uint32_t aoff = big ? (uint32_t)(16 * tt + jrow) * 1024u : (uint32_t)tt * 16384u;
+              const uint64_t da = desc_kmajor(sa + aoff, 1024);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS + tt * BN);
+#pragma unroll
+              for (int kk = 0; kk < 4; kk++) {
+                const uint32_t acc = (it > 0 || j > 0 || kk > 0) ? 1u : 0u;
+                umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, acc);
+              }
+            }
+            umma_commit(smem_u32(&b_empty[bslot]));
+            if (j == nb - 1) {
+              umma_commit(smem_u32(&a_empty[slot]));
+              if (it == nitems - 1) umma_commit(smem_u32(&acc_full[buf]));
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == ALOAD_WARP) {
+    // ===================== A loader: one tensor-map box per big item =====================
+    if (lane == 0) {
+      for (int s2 = 0; s2 < g.nsrc; s2++)
+        if (g.big[s2]) tma_prefetch_desc(&a.tm[s2]);
+      const uint32_t box_bytes = (uint32_t)a.box_rows * 1024u;
+      int ga = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tm = t / tiles_n;
+        const int n = tm / a.tiles_per_img, rr = tm - n * a.tiles_per_img;
+        const int ty = rr / a.tiles_w, tx = rr - ty * a.tiles_w;
+        const int h0 = ty * TH - pad, w0 = tx * 8;
+        for (int it = 0; it < nitems; it++, ga++) {
+          const int slot = ga % a_slots;
+          const uint32_t ph = (ga / a_slots) & 1;
+          const uint32_t item = a.items[it];
+          mbar_wait(smem_u32(&a_empty[slot]), ph ^ 1);
+          const uint32_t bar = smem_u32(&a_full[slot]);
+          if (item & 0x8000u) {
+            const int s2 = (item >> 12) & 3, kw = (item >> 8) & 15, cg = item & 0xFF;
+            mbar_arrive_expect_tx(bar, box_bytes);
+            tma_load_4d(smem_u32(sA + (size_t)slot * a.a_slot_bytes), &a.tm[s2], cg * 64, w0 + sign * (kw - pad), h0, n, bar);
+          } else {
+            mbar_arrive(bar);
+          }
+        }
+      }
+    }
+  } else if (warp == BLOAD_WARP) {
+    // ===================== B loader: one bulk copy per weight slab =====================
+    if (lane == 0) {
+      int gb = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int n0 = (t % tiles_n) * BN;
+        for (int it = 0; it < nitems; it++) {
+          const uint32_t item = a.items[it];
+          const bool big = (item & 0x8000u) != 0;
+          const int s2 = (item >> 12) & 3, kw = (item >> 8) & 15, cg = item & 0xFF;
+          const int ncb = big ? (g.C[s2] + 63) >> 6 : 0;
+          const int nb = big ? k : 1;
+          for (int j = 0; j < nb; j++, gb++) {
+            const int slab = big ? g.slab_begin[s2] + (j * k + kw) * ncb + cg : (int)item;
+            const int bslot = gb % b_slots;
+            mbar_wait(smem_u32(&b_empty[bslot]), ((gb / b_slots) & 1) ^ 1);
+            const uint32_t bar = smem_u32(&b_full[bslot]);
+            mbar_arrive_expect_tx(bar, B_BYTES);
+            bulk_g2s(smem_u32(sB + (size_t)bslot * B_BYTES), a.wp + ((long long)slab * a.Npad + n0) * 64, B_BYTES, bar);
+          }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue =====================
+    const int ei = warp - EPI_WARP0;
+    const int tile = ei >> 2, quarter = warp & 3;      // a warp may only read TMEM lanes [32*(warp%4), +32)
+    const int l = quarter * 32 + lane;                 // row of the 128-pixel sub-tile = TMEM lane
+    int ti = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ti++) {
+      const int buf = ti % NACC;
+      const int n0 = (t % tiles_n) * BN;
+      const int tm = t / tiles_n;
+      const int n = tm / a.tiles_per_img, rr = tm - n * a.tiles_per_img;
+      const int ty = rr / a.tiles_w, tx = rr - ty * a.tiles_w;
+      const int oh = ty * TH + 16 * tile + (l >> 3), ow = tx * 8 + (l & 7);
+      const bool mvalid = oh < g.OH && ow < g.OW;
+      const long long m = ((long long)n * g.OH + oh) * g.OW + ow;
+      mbar_wait(smem_u32(&acc_full[buf]), (ti / NACC) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int nb = n0 + c0;
+        float bias_l = 0.f;
+        if (a.bias && nb + lane < a.Nout) bias_l = __ldg(a.bias + nb + lane);
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + tile * BN + c0), r);
+        if (c0 + 32 >= BN) {                           // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(smem_u32(&acc_empty[buf]));
+        }
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < 32; q++) v[q] = __uint_as_float(r[q]) + __shfl_sync(0xffffffffu, bias_l, q);
+        switch (a.act) {
+          case FGC_ACT_LRELU:
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = v[q] > 0.f ? v[q] : 0.2f * v[q];
+            break;
+          case FGC_ACT_TANH:
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = tanhf(v[q]);
+            break;
+          case FGC_ACT_MIU:
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
+            break;
+          default: break;
+        }
+        if (!mvalid) continue;
+        if (nb >= a.Nout) continue;
+        const int nrem = a.Nout - nb;
+        if (a.y_dtype == FGC_F32) {
+          float* yp = reinterpret_cast<float*>(a.y) + m * a.Nout + nb;
+          if (a.vec_ok && nrem >= 32 && (a.Nout & 3) == 0) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) {
+              float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+              if (a.accumulate) {
+                float4 p = *reinterpret_cast<float4*>(yp + q);
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+              }
+              *reinterpret_cast<float4*>(yp + q) = o;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; q++)
+              if (q < nrem) yp[q] = a.accumulate ? yp[q] + v[q] : v[q];
+          }
+        } else {
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.Nout + nb;
+          if (a.vec_ok && nrem >= 32 && (a.Nout & 7) == 0) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 8) {
+              if (a.accumulate) {
+                uint4 p = *reinterpret_cast<uint4*>(yp + q);
+                const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&p);
+#pragma unroll
+                for (int e2 = 0; e2 < 4; e2++) {
+                  float2 f = __bfloat1622float2(pp[e2]);
+                  v[q + 2 * e2] += f.x; v[q + 2 * e2 + 1] += f.y;
+                }
+              }
+              uint4 o = make_uint4(pack_bf16x2(v[q], v[q + 1]), pack_bf16x2(v[q + 2], v[q + 3]), pack_bf16x2(v[q + 4], v[q + 5]),
+                                   pack_bf16x2(v[q + 6], v[q + 7]));
+              *reinterpret_cast<uint4*>(yp + q) = o;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; q++)
+              if (q < nrem) yp[q] = __float2bfloat16_rn(a.accumulate ? __bfloat162float(yp[q]) + v[q] : v[q]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // weight gradient
 // ------------------------------------------------------------------------------------------------------
 struct WgradArgs {
@@ -1153,12 +1475,22 @@ static int launch_igemm_bf16(IgemmArgs& a, int bn, int mt, cudaStream_t s) {
 long long* g_trace = nullptr;
 int g_trace_cap = 0;
 
+static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s);
+int conv_small_fwd_try(const ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride,
+                       long long n_stride, long long base, int nout, const float* bias, int act, int accumulate, void* y,
+                       int y_dtype, cudaStream_t s);
+int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s);
+
 // run y[M, nout] (=|+=) act(implicit_gemm(g) + bias) with weights w addressed as described in pack_weights_kernel
 int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride, long long n_stride,
                    long long base, int nout, const float* bias, int act, int accumulate, void* y, int y_dtype, void* ws,
                    cudaStream_t s) {
   FGC_REQUIRE(geom_fits(g), "conv: tensor too large for pixel packing");
   FGC_REQUIRE(g.M < (1LL << 31), "conv: more than 2^31 output pixels");
+  {
+    int r = conv_small_fwd_try(g, src_dtype, w, tap_stride, k_stride, n_stride, base, nout, bias, act, accumulate, y, y_dtype, s);
+    if (r >= 0) return r;                 // narrow layer: CUDA-core direct kernel (conv_small.cu)
+  }
   FGC_REQUIRE(ws != nullptr, "conv: workspace required");
   FGC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "conv: workspace must be 16-byte aligned");
   for (int i = 0; i < g.nsrc; i++)
@@ -1197,6 +1529,10 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
   for (int i = 0; i < g.nsrc; i++) a.any_small |= !g.big[i];
   a.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
   if (x3) return launch_igemm_f32(a, bn, s);
+  {
+    int r = conv_halo_try(a, bn, s);      // stride-1 SAME layers with wide sources: halo-reuse kernel (tensor-map TMA)
+    if (r >= 0) return r;
+  }
   // two A tiles per CTA (each weight tile feeds 256 pixels) once there is enough work to fill the machine twice over
   long long ctas2 = ((g.M + 255) / 256) * (npad / bn);
   int mt = ctas2 >= (long long)num_sms() ? 2 : 1;
@@ -1232,6 +1568,111 @@ static bool make_tmap_nhwc(CUtensorMap* out, const void* ptr, int C, int W, int 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+// ---- halo-reuse forward / dgrad launcher ----
+template <int BN, int MT, int NACC>
+static int launch_halo(HaloArgs& h, cudaStream_t s) {
+  constexpr int B_BYTES = BN * 128;
+  const int budget = 216 * 1024;
+  h.box_rows = 16 * MT + h.g.k - 1;
+  h.a_slot_bytes = h.box_rows * 1024;
+  int a_slots = 3;
+  while (a_slots > 2 && a_slots * h.a_slot_bytes + 2 * B_BYTES > budget) a_slots--;
+  if (a_slots * h.a_slot_bytes + 2 * B_BYTES > budget) return -1;
+  int b_slots = (budget - a_slots * h.a_slot_bytes) / B_BYTES;
+  if (b_slots > 8) b_slots = 8;
+  // spend what is left on a fourth activation box
+  if (b_slots >= 4 && (a_slots + 1) * h.a_slot_bytes + b_slots * B_BYTES <= budget) a_slots++;
+  h.a_slots = a_slots;
+  h.b_slots = b_slots;
+  const int TH = 16 * MT;
+  const int tiles_h = (h.g.OH + TH - 1) / TH;
+  h.tiles_w = (h.g.OW + 7) / 8;
+  h.tiles_per_img = tiles_h * h.tiles_w;
+  h.tiles_m = h.g.N * h.tiles_per_img;
+  for (int i = 0; i < h.g.nsrc; i++) {
+    if (!h.g.big[i]) continue;
+    if (!make_tmap_nhwc(&h.tm[i], h.g.src[i], h.g.C[i], h.g.W, h.g.H, h.g.N, 8, h.box_rows)) return -1;
+  }
+  size_t smem = (size_t)a_slots * h.a_slot_bytes + (size_t)b_slots * B_BYTES + (2 * a_slots + 2 * b_slots + 2 * NACC) * 8 + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_halo_kernel<BN, MT, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  long long ntiles = (long long)h.tiles_m * (h.Npad / BN);
+  int grid = ntiles < num_sms() ? (int)ntiles : num_sms();
+  conv_halo_kernel<BN, MT, NACC><<<grid, 32 * (8 + 4 * MT), smem, s>>>(h);
+  count_launch();
+  return check_launch("conv_halo");
+}
+
+// returns -1 when the layer is not eligible (the caller falls back to conv_igemm_kernel), else the launch status
+static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
+  static int mode = -1;        // FGC_HALO: 0 = off, 1 = on (default), 2 = also 1x1 layers
+  if (mode < 0) { const char* e = getenv("FGC_HALO"); mode = e ? atoi(e) : 1; }
+  if (!mode) return -1;
+  const ConvGeom& g = ia.g;
+  if (!ia.fast || (g.k & 1) == 0 || g.k > 15 || g.pad_t != (g.k - 1) / 2 || g.pad_l != g.pad_t) return -1;
+  if (g.k == 1 && mode < 2) return -1;
+  bool any_big = false;
+  for (int i = 0; i < g.nsrc; i++) {
+    if (!g.big[i]) continue;
+    if (g.ups[i]) return -1;                       // tensor TMA cannot replicate pixels
+    any_big = true;
+  }
+  if (!any_big) return -1;
+  // tile efficiency: th x 8 rectangles against the image size
+  auto eff = [&](int mt) {
+    int th = 16 * mt;
+    double cover = (double)(((g.OH + th - 1) / th) * th) * (((g.OW + 7) / 8) * 8);
+    return (double)g.OH * g.OW / cover;
+  };
+  int mt = 2;
+  long long tiles2 = (long long)g.N * ((g.OH + 31) / 32) * ((g.OW + 7) / 8) * (ia.Npad / bn);
+  if (eff(1) > eff(2) + 1e-9 || tiles2 < (long long)num_sms()) mt = 1;
+  if (eff(mt) < 0.7) return -1;
+  HaloArgs h;
+  h.g = g;
+  h.wp = ia.wp;
+  h.Npad = ia.Npad;
+  h.Nout = ia.Nout;
+  h.bias = ia.bias;
+  h.act = ia.act;
+  h.accumulate = ia.accumulate;
+  h.y = ia.y;
+  h.y_dtype = ia.y_dtype;
+  h.vec_ok = ia.vec_ok;
+  h.tbl = ia.tbl;
+  h.any_small = ia.any_small;
+  int ni = 0;
+  for (int i = 0; i < g.nsrc; i++) {
+    if (g.big[i]) {
+      int ncb = (g.C[i] + 63) / 64;
+      if (ncb > 255) return -1;
+      for (int cg = 0; cg < ncb; cg++)
+        for (int kw = 0; kw < g.k; kw++) {
+          if (ni >= kMaxItems) return -1;
+          h.items[ni++] = (uint16_t)(0x8000u | (i << 12) | (kw << 8) | cg);
+        }
+    } else {
+      for (int sl = g.slab_begin[i]; sl < g.slab_begin[i + 1]; sl++) {
+        if (ni >= kMaxItems || sl >= 0x8000) return -1;
+        h.items[ni++] = (uint16_t)sl;
+      }
+    }
+  }
+  h.nitems = ni;
+#define FGC_H(BN_, NACC2_) return mt == 2 ? launch_halo<BN_, 2, NACC2_>(h, s) : launch_halo<BN_, 1, 2>(h, s)
+  switch (bn) {
+    case 16: FGC_H(16, 2);
+    case 32: FGC_H(32, 2);
+    case 64: FGC_H(64, 2);
+    case 256: FGC_H(256, 1);
+    default: FGC_H(128, 2);
+  }
+#undef FGC_H
 }
 
 // tiled mode for the weight gradient: pick the 64-pixel rectangle and build the tensor maps
@@ -1314,6 +1755,10 @@ static int pick_bn_wgrad(int nout, int x3) {
 
 int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s) {
   FGC_REQUIRE(geom_fits(g), "wgrad: tensor too large for pixel packing");
+  {
+    int r = conv_small_wgrad_try(g, src_dtype, gy, Cin_total, Cout, dw, s);
+    if (r >= 0) return r;                 // narrow layer: CUDA-core direct kernel (conv_small.cu)
+  }
   WgradArgs a;
   a.g = g;
   a.gy = gy;

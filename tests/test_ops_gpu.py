@@ -47,6 +47,12 @@ CONV_CASES = [
     (70, 1, 1, [(256, False)], 1, 1, 200, ACT_MIU),             # fully connected rows
     (5, 1, 1, [(512, False), (512, False)], 1, 1, 2048, ACT_NONE),   # LSTM gates
     (2, 6, 6, [(96, False)], 3, 1, 1, ACT_NONE),                # patch logits (Cout 1), partial K slab
+    # halo-reuse kernel (bf16, stride 1, wide sources through tensor-map TMA)
+    (8, 64, 80, [(64, False)], 3, 1, 128, ACT_LRELU),           # two sub-tiles per CTA (32 x 8 pixel tiles)
+    (2, 24, 24, [(128, False), (3, False)], 3, 1, 64, ACT_NONE),    # wide + sketch source, ragged tile rows (24 = 16 + 8)
+    (8, 64, 80, [(64, False), (8, False), (3, False)], 3, 1, 256, ACT_NONE),   # 256-wide N tile, two small sources
+    (2, 32, 40, [(192, False)], 7, 1, 3, ACT_TANH),             # 7x7 over three channel groups, Cout 3
+    (3, 30, 22, [(72, False)], 3, 1, 40, ACT_MIU),              # partial channel group (72 = 64 + 8), ragged rows and columns
 ]
 
 
@@ -94,6 +100,11 @@ DGRAD_CASES = [
     (2, 12, 12, 192, 0, 192, 1, 64, False, False),
     (70, 1, 1, 1024, 512, 512, 1, 2048, False, False),  # LSTM kernel slice
     (2, 6, 6, 96, 0, 96, 1, 1, False, True),            # from the 1-channel patch logits
+    (8, 64, 80, 72, 64, 8, 3, 128, False, False),       # halo kernel, mirrored taps, narrow output (N tile 16)
+    (2, 16, 24, 64, 0, 64, 7, 64, False, True),         # halo kernel, 7x7 mirrored taps, accumulating
+    (2, 20, 20, 11, 8, 3, 3, 8, False, True),           # direct narrow kernel: 8-channel gy -> image slice, accumulating
+    (2, 20, 20, 3, 0, 3, 7, 8, False, False),           # direct narrow kernel: stem 7x7, mirrored taps
+    (2, 20, 20, 11, 0, 8, 3, 8, False, False),          # direct narrow kernel: 8 -> 8
 ]
 
 
