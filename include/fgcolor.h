@@ -51,6 +51,14 @@ typedef struct {
 size_t fgc_conv2d_ws_bytes(const int* src_C, int nsrc, int k, int n_out, int src_dtype);
 /* 0 = tcgen05 tensor-core path (default), 1 = CUDA-core checker (also: env FGC_CONV_IMPL=simple) */
 int fgc_set_conv_impl(int impl);
+/* tuning / A-B switches of the tensor-core path (also: env FGC_HALO, FGC_SMALL): halo = 1 routes stride-1 SAME layers
+ * with wide bf16 sources through the halo-reuse kernel (tensor-map TMA), 0 through the per-tap gather kernel;
+ * small = 1 routes the narrow stem-level layers (all sources < 64 channels, <= 8 outputs) through the CUDA-core
+ * direct kernels.  A negative value leaves that switch unchanged. */
+int fgc_set_conv_flags(int halo, int small);
+/* launches so far per convolution kernel family: out[0] halo-reuse fwd/dgrad, out[1] per-tap gather fwd/dgrad,
+ * out[2] direct narrow fwd/dgrad, out[3] direct narrow wgrad, out[4] tensor-core wgrad (tests assert the routing) */
+int fgc_debug_conv_counts(long long out[5]);
 /* debug aid: per-role event trace (role, event, tile, clock64) of CTA 0 of the implicit-GEMM kernel; buf holds
  * 4 + 4*capacity int64 on the device, buf[0] is the event count.  NULL disables. */
 int fgc_debug_set_trace(long long* buf, int capacity);

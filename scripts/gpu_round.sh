@@ -5,7 +5,19 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T=${TAG:-cur}
 if [ -z "$NO_TESTS" ]; then
-bash scripts/gpu_tests.sh ${TIERS:-ops_base conv_fwd conv_dgrad conv_wgrad model}
+bash scripts/gpu_tests.sh conv_fwd conv_dgrad conv_wgrad
+# a failing / hanging new conv kernel must not take the rest of the session down: fall back to the older kernels
+if ! tail -n 1 gpurun_out/conv_fwd.log | grep -q passed || grep -q failed gpurun_out/conv_fwd.log || \
+   ! tail -n 1 gpurun_out/conv_dgrad.log | grep -q passed || grep -q failed gpurun_out/conv_dgrad.log || \
+   ! tail -n 1 gpurun_out/conv_wgrad.log | grep -q passed || grep -q failed gpurun_out/conv_wgrad.log; then
+  echo "!!! conv tiers not green: details"; grep -E "^(FAILED|ERROR)|Error|rel-to-max" gpurun_out/conv_fwd.log gpurun_out/conv_dgrad.log gpurun_out/conv_wgrad.log | head -40
+  for v in "FGC_HALO=0" "FGC_SMALL=0" "FGC_HALO=0 FGC_SMALL=0"; do
+    echo "--- retry with $v"; env $v timeout -k 10 200 python -m pytest -q -m gpu -p no:cacheprovider tests/test_ops_gpu.py -k "tcgen05 and not gather and conv" -x 2>&1 | tail -n 3
+  done
+  export FGC_HALO=${FALLBACK_HALO:-0} FGC_SMALL=${FALLBACK_SMALL:-0}
+  echo "continuing with FGC_HALO=$FGC_HALO FGC_SMALL=$FGC_SMALL"
+fi
+bash scripts/gpu_tests.sh ops_base model
 echo "=== smoke"; timeout -k 10 300 python __graft_entry__.py --smoke > gpurun_out/smoke_$T.log 2>&1; tail -n 3 gpurun_out/smoke_$T.log
 fi
 echo "=== prof_conv"; timeout -k 10 300 python scripts/prof_conv.py > gpurun_out/prof_conv_$T.log 2>&1; cat gpurun_out/prof_conv_$T.log
@@ -24,7 +36,7 @@ if [ "$(wc -l < gpurun_out/launches_$T.csv)" -lt 200 ]; then
   wc -l gpurun_out/launches_$T.csv
 fi
 echo "=== ncu full"
-ONLY_FIRST=1 REPS=1 timeout -k 10 600 ncu --set full --clock-control none --import-source on -k "regex:conv_igemm|conv_wgrad_kernel" -c 6 -f -o gpurun_out/prof_conv_$T \
+ONLY_FIRST=1 REPS=1 timeout -k 10 600 ncu --set full --clock-control none --import-source on -k "regex:conv_halo|conv_igemm|conv_wgrad_kernel" -c 6 -f -o gpurun_out/prof_conv_$T \
     python scripts/prof_conv.py > gpurun_out/ncu_full_$T.log 2>&1
 echo "=== ncu full (elementwise)"
 ONLY=cbn_act_fwd,cbn_act_bwd,minmax_fwd,gate_fma_fwd,blend_fwd REPS=1 timeout -k 10 600 ncu --set full --clock-control none --import-source on \

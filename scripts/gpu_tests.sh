@@ -14,9 +14,9 @@ tiers=${@:-"ops_base conv_fwd conv_dgrad conv_wgrad model"}
 for t in $tiers; do
   case $t in
     ops_base)   run ops_base 600 tests/test_ops_gpu.py -k "not tcgen05" ;;
-    conv_fwd)   run conv_fwd 300 tests/test_ops_gpu.py -k "tcgen05 and conv_fwd" ;;
-    conv_dgrad) run conv_dgrad 300 tests/test_ops_gpu.py -k "tcgen05 and conv_dgrad" ;;
-    conv_wgrad) run conv_wgrad 300 tests/test_ops_gpu.py -k "tcgen05 and conv_wgrad" ;;
+    conv_fwd)   run conv_fwd 150 tests/test_ops_gpu.py -k "tcgen05 and conv_fwd" ;;
+    conv_dgrad) run conv_dgrad 150 tests/test_ops_gpu.py -k "tcgen05 and conv_dgrad" ;;
+    conv_wgrad) run conv_wgrad 150 tests/test_ops_gpu.py -k "tcgen05 and conv_wgrad" ;;
     model)      run model 900 tests/test_model_gpu.py ;;
   esac
 done

@@ -1,5 +1,6 @@
-"""Runs the dominant convolution of the training step (3x3, 128->128, 192x192, bs 64, bf16) forward, dgrad and wgrad a few
-times -- the target of the `ncu --set full` capture; also prints CUDA-event timings when run without a profiler."""
+"""Times the convolution shapes that dominate the training step (bs 64, bf16) forward / dgrad / wgrad with CUDA events,
+A/B between the kernels (halo-reuse vs per-tap gather; direct narrow vs tensor path).  With ONLY_FIRST=1 it runs just the
+dominant 3x3 128->128 @192x192 layer: the target of the `ncu --set full` capture."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import torch
@@ -7,28 +8,48 @@ from sketchyscenecolorization_b200.cuda_ops import CudaOps
 
 bs = int(os.environ.get("BS", "64"))
 reps = int(os.environ.get("REPS", "3"))
-cases = [("128->128@192", 192, 128, 128), ("256->256@96", 96, 256, 256), ("512->512@48", 48, 512, 512), ("768->768@24", 24, 768, 768)]
+# name, H=W, source channels, Cout, k
+cases = [("128->128@192", 192, [128], 128, 3), ("128+3->64@192", 192, [128, 3], 64, 3), ("64->64@192", 192, [64], 64, 3),
+         ("64->3 k7@192", 192, [64], 3, 7), ("3->8 k7@192", 192, [3], 8, 7), ("8+3->8@192", 192, [8, 3], 8, 3),
+         ("128+3+8->128@96", 96, [128, 3, 8], 128, 3), ("256->256@96", 96, [256], 256, 3), ("512->512@48", 48, [512], 512, 3),
+         ("768->768@24", 24, [768], 768, 3)]
 if os.environ.get("ONLY_FIRST"):
     cases = cases[:1]
 ops = CudaOps("cuda:0", torch.bfloat16)
-for name, hw, cin, cout in cases:
-    x = torch.randn(bs, hw, hw, cin, device="cuda").to(torch.bfloat16)
+lib = ops.lib
+
+
+def timeit(fn):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+for name, hw, cins, cout, k in cases:
+    xs = [(torch.randn(bs, hw, hw, c, device="cuda").to(torch.bfloat16), False) for c in cins]
+    cin = sum(cins)
     gy = torch.randn(bs, hw, hw, cout, device="cuda").to(torch.bfloat16)
-    w = (torch.randn(3, 3, cin, cout, device="cuda") * 0.02).contiguous()
+    w = (torch.randn(k, k, cin, cout, device="cuda") * 0.02).contiguous()
     b = torch.zeros(cout, device="cuda")
     dw = torch.zeros_like(w)
     db = torch.zeros_like(b)
-    flop = 2.0 * bs * hw * hw * 9 * cin * cout
-    for what, fn in (("fwd", lambda: ops.conv_fwd([(x, False)], w, b)),
-                     ("dgrad", lambda: ops.conv_dgrad(gy, w, 0, cin)),
-                     ("wgrad", lambda: ops.conv_wgrad([(x, False)], gy, dw, db))):
-        fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        print("%-14s %-6s %8.3f ms  %7.1f TFLOP/s" % (name, what, ms, flop / ms / 1e9), flush=True)
+    flop = 2.0 * bs * hw * hw * k * k * cin * cout
+    fns = (("fwd", lambda: ops.conv_fwd(xs, w, b)),
+           ("dgrad", lambda: ops.conv_dgrad(gy, w, 0, cins[0])),
+           ("wgrad", lambda: ops.conv_wgrad(xs, gy, dw, db)))
+    for what, fn in fns:
+        lib.fgc_set_conv_flags(1, 1)
+        ms = timeit(fn)
+        line = "%-16s %-6s %8.3f ms  %7.1f TFLOP/s" % (name, what, ms, flop * (cins[0] / cin if what == "dgrad" else 1.0) / ms / 1e9)
+        if not os.environ.get("ONLY_FIRST"):
+            lib.fgc_set_conv_flags(0, 0)
+            ms0 = timeit(fn)
+            lib.fgc_set_conv_flags(1, 1)
+            line += "   | gather/tensor-only kernels: %8.3f ms" % ms0
+        print(line, flush=True)

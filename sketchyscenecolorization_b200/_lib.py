@@ -73,6 +73,8 @@ SIGNATURES = {
     "fgc_launch_count": [],
     "fgc_conv2d_ws_bytes": [C.POINTER(C.c_int), _I, _I, _I, _I],
     "fgc_set_conv_impl": [_I],
+    "fgc_set_conv_flags": [_I, _I],
+    "fgc_debug_conv_counts": [_P],
     "fgc_debug_set_trace": [_P, _I],
     "fgc_conv2d_fwd": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "fgc_conv2d_dgrad": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P],

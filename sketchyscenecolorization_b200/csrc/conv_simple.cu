@@ -130,7 +130,64 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long M, int C, int r
   }
 }
 
+// vectorised variant: a thread owns V consecutive channels and walks rows, four independent loads in flight; the block
+// combines its row lanes in shared memory and issues one atomic per channel
+template <typename T, int V>
+__global__ void colsum_vec_kernel(const T* __restrict__ x, long long M, int C, int rows_per_block, float* out) {
+  extern __shared__ float sh_col[];              // [C]
+  const int CV = C / V;
+  const int lanes = blockDim.x / CV;
+  const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sh_col[i] = 0.f;
+  __syncthreads();
+  long long r0 = (long long)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  if (rl < lanes) {
+    float s[V];
+#pragma unroll
+    for (int k = 0; k < V; k++) s[k] = 0.f;
+    for (long long rb = r0 + rl; rb < r1; rb += 4LL * lanes) {
+      float a[4][kMaxV];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        long long r = rb + (long long)u * lanes;
+        if (r < r1) ldv<T, V>(x + r * C + v * V, a[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (rb + (long long)u * lanes >= r1) continue;
+#pragma unroll
+        for (int k = 0; k < V; k++) s[k] += a[u][k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; k++) atomicAdd(&sh_col[v * V + k], s[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[i], sh_col[i]);
+}
+
 int colsum_launch(const void* x, int dtype, long long M, int C, float* out, cudaStream_t s) {
+  int vec = vec_width(x, C, dtype);
+  if (vec >= 4 && C / vec <= 256 && M >= 4096) {
+    const int V = vec >= 8 ? 8 : 4;
+    const int CV = C / V;
+    const int lanes = 256 / CV;
+    long long want = (long long)num_sms() * 16;
+    long long rpb = (M + want - 1) / want;
+    if (rpb < lanes * 8LL) rpb = lanes * 8LL;
+    int nblk = (int)((M + rpb - 1) / rpb);
+    size_t sm = sizeof(float) * C;
+    if (dtype == FGC_F32) {
+      if (V == 8) colsum_vec_kernel<float, 8><<<nblk, 256, sm, s>>>((const float*)x, M, C, (int)rpb, out);
+      else colsum_vec_kernel<float, 4><<<nblk, 256, sm, s>>>((const float*)x, M, C, (int)rpb, out);
+    } else {
+      if (V == 8) colsum_vec_kernel<__nv_bfloat16, 8><<<nblk, 256, sm, s>>>((const __nv_bfloat16*)x, M, C, (int)rpb, out);
+      else colsum_vec_kernel<__nv_bfloat16, 4><<<nblk, 256, sm, s>>>((const __nv_bfloat16*)x, M, C, (int)rpb, out);
+    }
+    count_launch();
+    return FGC_OK;
+  }
   long long want = (long long)num_sms() * 4;
   long long rpb = (M + want - 1) / want;
   if (rpb < 32) rpb = 32;

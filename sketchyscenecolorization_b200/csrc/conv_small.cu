@@ -210,10 +210,11 @@ static bool all_small(const ConvGeom& g) {
     if (g.big[i]) return false;
   return true;
 }
+extern long long g_conv_counts[5];
+int g_small_mode = -1;         // fgc_set_conv_flags / env FGC_SMALL; 0 sends the narrow layers through the tensor-core path
 static int small_mode() {
-  static int mode = -1;        // FGC_SMALL=0 sends the narrow layers through the tensor-core path as well
-  if (mode < 0) { const char* e = getenv("FGC_SMALL"); mode = e ? atoi(e) : 1; }
-  return mode;
+  if (g_small_mode < 0) { const char* e = getenv("FGC_SMALL"); g_small_mode = e ? atoi(e) : 1; }
+  return g_small_mode;
 }
 
 // returns -1 when the layer is not eligible, else the launch status
@@ -243,6 +244,7 @@ int conv_small_fwd_try(const ConvGeom& g, int src_dtype, const float* w, long lo
     if (!set) { cudaFuncSetAttribute(conv_small_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
     conv_small_fwd_kernel<__nv_bfloat16><<<(int)blocks, 256, smem, s>>>(a);
   }
+  g_conv_counts[2]++;
   count_launch();
   return check_launch("conv_small_fwd");
 }
@@ -278,6 +280,7 @@ int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int C
     if (!set) { cudaFuncSetAttribute(conv_small_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
     conv_small_wgrad_kernel<__nv_bfloat16><<<grid, threads, smem, s>>>(a);
   }
+  g_conv_counts[3]++;
   count_launch();
   return check_launch("conv_small_wgrad");
 }

@@ -31,6 +31,7 @@
 
 namespace fgc {
 int num_sms();
+long long g_conv_counts[5] = {0, 0, 0, 0, 0};   // launches per kernel family (fgc_debug_conv_counts)
 
 // ------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -1448,6 +1449,7 @@ static int launch_igemm(IgemmArgs& a, cudaStream_t s) {
   long long ntiles = (long long)a.tiles_m * (a.Npad / BN);
   int grid = ntiles < num_sms() ? (int)ntiles : num_sms();
   conv_igemm_kernel<SrcT, BN, MT, NACC><<<grid, 32 * (8 * MT + 2), smem, s>>>(a);
+  g_conv_counts[1]++;
   count_launch();
   return check_launch("conv_igemm");
 }
@@ -1474,6 +1476,7 @@ static int launch_igemm_bf16(IgemmArgs& a, int bn, int mt, cudaStream_t s) {
 
 long long* g_trace = nullptr;
 int g_trace_cap = 0;
+int g_halo_mode = -1;      // fgc_set_conv_flags / env FGC_HALO
 
 static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s);
 int conv_small_fwd_try(const ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride,
@@ -1604,14 +1607,15 @@ static int launch_halo(HaloArgs& h, cudaStream_t s) {
   long long ntiles = (long long)h.tiles_m * (h.Npad / BN);
   int grid = ntiles < num_sms() ? (int)ntiles : num_sms();
   conv_halo_kernel<BN, MT, NACC><<<grid, 32 * (8 + 4 * MT), smem, s>>>(h);
+  g_conv_counts[0]++;
   count_launch();
   return check_launch("conv_halo");
 }
 
 // returns -1 when the layer is not eligible (the caller falls back to conv_igemm_kernel), else the launch status
 static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
-  static int mode = -1;        // FGC_HALO: 0 = off, 1 = on (default), 2 = also 1x1 layers
-  if (mode < 0) { const char* e = getenv("FGC_HALO"); mode = e ? atoi(e) : 1; }
+  if (g_halo_mode < 0) { const char* e = getenv("FGC_HALO"); g_halo_mode = e ? atoi(e) : 1; }
+  const int mode = g_halo_mode;      // 0 = off, 1 = on (default), 2 = also 1x1 layers
   if (!mode) return -1;
   const ConvGeom& g = ia.g;
   if (!ia.fast || (g.k & 1) == 0 || g.k > 15 || g.pad_t != (g.k - 1) / 2 || g.pad_l != g.pad_t) return -1;
@@ -1738,6 +1742,7 @@ static int launch_wgrad(WgradArgs& a, cudaStream_t s) {
   splits = (a.kslabs + a.kslabs_per_cta - 1) / a.kslabs_per_cta;
   dim3 grid(groups, ntiles, splits);
   conv_wgrad_kernel<SrcT, BN, G><<<grid, 320, smem, s>>>(a);
+  g_conv_counts[4]++;
   count_launch();
   return check_launch("conv_wgrad");
 }

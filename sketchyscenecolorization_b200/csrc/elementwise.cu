@@ -115,26 +115,38 @@ __global__ void chan_stats_finalize(const double* acc, long long M, int C, float
 // ======================================================================================================
 // conditional BN apply (+ miu_relu)
 // ======================================================================================================
+// The "apply" passes below share one thread layout: grid (row blocks, N); a thread owns V fixed channels of image n and
+// walks rows (pixels), so the per-(n,c) parameters (statistics, class-table rows, min/max) are loaded ONCE per thread
+// instead of once per element -- the first versions were bound by L1/TEX parameter traffic (ncu: 87-96% L1, < 2 TB/s).
 template <typename T, int V>
-__global__ void cbn_act_fwd_kernel(const T* __restrict__ x, long long nvec, int HW, int C, const float* __restrict__ stats,
+__global__ void cbn_act_fwd_kernel(const T* __restrict__ x, int HW, int C, int rows_per_block, const float* __restrict__ stats,
                                    const float* __restrict__ scale, const float* __restrict__ offset,
                                    const int32_t* __restrict__ labels, int act, T* __restrict__ y) {
   const int CV = C / V;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
-    long long row = i / CV;
-    int n = (int)(row / HW);
-    int l = labels[n];
+  const int lanes = blockDim.x / CV;
+  const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
+  if (rl >= lanes) return;
+  const int n = blockIdx.y;
+  const int l = labels[n];
+  float mean[V], rstd[V], ga[V], be[V];
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    int c = v * V + k;
+    mean[k] = stats[c]; rstd[k] = stats[C + c];
+    ga[k] = scale[l * C + c]; be[k] = offset[l * C + c];
+  }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  const long long base = (long long)n * HW * C + v * V;
+#pragma unroll 4
+  for (int r = r0 + rl; r < r1; r += lanes) {
     float a[kMaxV], o[kMaxV];
-    ldv<T, V>(x + i * V, a);
+    ldv<T, V>(x + base + (long long)r * C, a);
 #pragma unroll
     for (int k = 0; k < V; k++) {
-      int c = cv * V + k;
-      float xh = (a[k] - stats[c]) * stats[C + c];
-      float t = xh * scale[l * C + c] + offset[l * C + c];
+      float t = (a[k] - mean[k]) * rstd[k] * ga[k] + be[k];
       o[k] = act == FGC_ACT_MIU ? miu_relu(t) : t;
     }
-    stv<T, V>(y + i * V, o);
+    stv<T, V>(y + base + (long long)r * C, o);
   }
 }
 
@@ -215,30 +227,39 @@ __global__ void cbn_bwd_finalize_kernel(const float* sums, int N, int C, long lo
   m12[C + c] = (float)(m2 / (double)M);
 }
 template <typename T, int V>
-__global__ void cbn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, long long nvec, int HW, int C,
+__global__ void cbn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                      const float* __restrict__ stats, const float* __restrict__ scale,
                                      const float* __restrict__ offset, const int32_t* __restrict__ labels, int act,
                                      const float* __restrict__ m12, T* __restrict__ gx) {
   const int CV = C / V;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
-    long long row = i / CV;
-    int n = (int)(row / HW);
-    int l = labels[n];
+  const int lanes = blockDim.x / CV;
+  const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
+  if (rl >= lanes) return;
+  const int n = blockIdx.y;
+  const int l = labels[n];
+  float mean[V], rstd[V], ga[V], be[V], m1[V], m2[V];
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    int c = v * V + k;
+    mean[k] = stats[c]; rstd[k] = stats[C + c];
+    ga[k] = scale[l * C + c]; be[k] = offset[l * C + c];
+    m1[k] = m12[c]; m2[k] = m12[C + c];
+  }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  const long long base = (long long)n * HW * C + v * V;
+#pragma unroll 2
+  for (int r = r0 + rl; r < r1; r += lanes) {
     float a[kMaxV], g[kMaxV], o[kMaxV];
-    ldv<T, V>(x + i * V, a);
-    ldv<T, V>(gy + i * V, g);
+    ldv<T, V>(x + base + (long long)r * C, a);
+    ldv<T, V>(gy + base + (long long)r * C, g);
 #pragma unroll
     for (int k = 0; k < V; k++) {
-      int c = cv * V + k;
-      float rstd = stats[C + c];
-      float xh = (a[k] - stats[c]) * rstd;
-      float ga = scale[l * C + c];
+      float xh = (a[k] - mean[k]) * rstd[k];
       float gg = g[k];
-      if (act == FGC_ACT_MIU) gg *= miu_relu_grad(xh * ga + offset[l * C + c]);
-      o[k] = rstd * (gg * ga - m12[c] - xh * m12[C + c]);
+      if (act == FGC_ACT_MIU) gg *= miu_relu_grad(xh * ga[k] + be[k]);
+      o[k] = rstd[k] * (gg * ga[k] - m1[k] - xh * m2[k]);
     }
-    stv<T, V>(gx + i * V, o);
+    stv<T, V>(gx + base + (long long)r * C, o);
   }
 }
 
@@ -325,24 +346,29 @@ __global__ void minmax_reduce_kernel(const T* __restrict__ x, int HW, int C, int
   }
 }
 template <typename T, int V>
-__global__ void minmax_apply_kernel(const T* __restrict__ x, long long nvec, int HW, int C, const uint32_t* __restrict__ mn_ord,
+__global__ void minmax_apply_kernel(const T* __restrict__ x, int HW, int C, int rows_per_block, const uint32_t* __restrict__ mn_ord,
                                     const uint32_t* __restrict__ mx_ord, T* __restrict__ gate, float* mn, float* mx) {
   const int CV = C / V;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
-    long long row = i / CV;
-    int n = (int)(row / HW);
-    bool first = (row % HW) == 0;
-    float a[kMaxV], o[kMaxV];
-    ldv<T, V>(x + i * V, a);
+  const int lanes = blockDim.x / CV;
+  const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
+  if (rl >= lanes) return;
+  const int n = blockIdx.y;
+  float lo[V], hi[V];
 #pragma unroll
-    for (int k = 0; k < V; k++) {
-      int c = cv * V + k;
-      float lo = ord2f(mn_ord[(long long)n * C + c]), hi = ord2f(mx_ord[(long long)n * C + c]);
-      o[k] = (a[k] - lo) / (hi - lo);
-      if (first) { mn[(long long)n * C + c] = lo; mx[(long long)n * C + c] = hi; }
-    }
-    stv<T, V>(gate + i * V, o);
+  for (int k = 0; k < V; k++) {
+    long long q = (long long)n * C + v * V + k;
+    lo[k] = ord2f(mn_ord[q]); hi[k] = ord2f(mx_ord[q]);
+    if (blockIdx.x == 0 && rl == 0) { mn[q] = lo[k]; mx[q] = hi[k]; }
+  }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  const long long base = (long long)n * HW * C + v * V;
+#pragma unroll 4
+  for (int r = r0 + rl; r < r1; r += lanes) {
+    float a[kMaxV], o[kMaxV];
+    ldv<T, V>(x + base + (long long)r * C, a);
+#pragma unroll
+    for (int k = 0; k < V; k++) o[k] = (a[k] - lo[k]) / (hi[k] - lo[k]);
+    stv<T, V>(gate + base + (long long)r * C, o);
   }
 }
 // sums[0] = sum g*(x-mn), sums[1] = sum g, sums[2] = #(x==mx), sums[3] = #(x==mn)   each [N,C]
@@ -403,31 +429,39 @@ __global__ void minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __re
   }
 }
 template <typename T, int V>
-__global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __restrict__ x, long long nvec, int HW, int C,
+__global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                         const float* __restrict__ mn, const float* __restrict__ mx, int N,
                                         const float* __restrict__ sums, T* __restrict__ gpre) {
   const int CV = C / V;
+  const int lanes = blockDim.x / CV;
+  const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
+  if (rl >= lanes) return;
+  const int n = blockIdx.y;
   const long long NC = (long long)N * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    int cv = (int)(i % CV);
-    long long row = i / CV;
-    int n = (int)(row / HW);
+  float lo[V], hi[V], d[V], a_mx[V], a_mn[V];   // per-(n,c): min, max, range, gradient shares of the arg-max / arg-min pixels
+#pragma unroll
+  for (int k = 0; k < V; k++) {
+    long long q = (long long)n * C + v * V + k;
+    lo[k] = mn[q]; hi[k] = mx[q]; d[k] = hi[k] - lo[k];
+    float A = sums[q], S = sums[NC + q];
+    a_mx[k] = (-A / (d[k] * d[k])) / sums[2 * NC + q];
+    a_mn[k] = ((A - d[k] * S) / (d[k] * d[k])) / sums[3 * NC + q];
+  }
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  const long long base = (long long)n * HW * C + v * V;
+#pragma unroll 2
+  for (int r = r0 + rl; r < r1; r += lanes) {
     float a[kMaxV], g[kMaxV], o[kMaxV];
-    ldv<T, V>(x + i * V, a);
-    ldv<T, V>(gg + i * V, g);
+    ldv<T, V>(x + base + (long long)r * C, a);
+    ldv<T, V>(gg + base + (long long)r * C, g);
 #pragma unroll
     for (int k = 0; k < V; k++) {
-      long long q = (long long)n * C + cv * V + k;
-      float lo = mn[q], hi = mx[q], d = hi - lo;
-      float A = sums[q], S = sums[NC + q];
-      float g_mx = -A / (d * d);
-      float g_mn = (A - d * S) / (d * d);
-      float r = g[k] / d;
-      if (a[k] == hi) r += g_mx / sums[2 * NC + q];
-      if (a[k] == lo) r += g_mn / sums[3 * NC + q];
-      o[k] = r * (a[k] > 0.f ? 1.f : 0.2f);
+      float rr = g[k] / d[k];
+      if (a[k] == hi[k]) rr += a_mx[k];
+      if (a[k] == lo[k]) rr += a_mn[k];
+      o[k] = rr * (a[k] > 0.f ? 1.f : 0.2f);
     }
-    stv<T, V>(gpre + i * V, o);
+    stv<T, V>(gpre + base + (long long)r * C, o);
   }
 }
 
@@ -695,7 +729,7 @@ static RowRed rowred_plan(int C, int vec, long long rows, long long other_blocks
   p.threads = 256;
   if (CV > 256) p.threads = ((CV + 31) / 32) * 32;
   p.lanes = p.threads / CV;
-  long long target = (long long)num_sms() * 8;                      // blocks wanted overall
+  long long target = (long long)num_sms() * 24;                     // blocks wanted overall (several waves: short tail)
   long long want = target / (other_blocks > 0 ? other_blocks : 1);
   if (want < 1) want = 1;
   long long rpb = (rows + want - 1) / want;
@@ -717,8 +751,8 @@ int fgc_chan_stats(const void* x, int dtype, long long M, int C, double* acc, fl
   FGC_REQUIRE(M > 0 && C > 0 && C <= 1024, "chan_stats: bad shape M=%lld C=%d", M, C);
   cudaStream_t s = as_stream(stream);
   cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, s);
-  int vec = vmin(vec_width(x, C, dtype), 4);     // reductions: 4-wide keeps the register count (occupancy) in check
-  RowRed p = rowred_plan(C, vec, M, 1);
+  int vec = vec_width(x, C, dtype);
+  RowRed p = rowred_plan(C, vec, M, 3);      // a third of the usual block count: every block ends in 2*C fp64 atomics
   FGC_DISPATCH_TV(dtype, vec, T, V,
                   (chan_stats_kernel<T, V><<<p.nblk, p.threads, 2 * C * sizeof(double), s>>>((const T*)x, M, C, p.rows_per_block, acc)));
   chan_stats_finalize<<<cdiv(C, 128), 128, 0, s>>>(acc, M, C, stats);
@@ -733,9 +767,11 @@ int fgc_cbn_act_fwd(const void* x, int dtype, int N, int HW, int C, const float*
   cudaStream_t s = as_stream(stream);
   int vec = vmin(vec_width(x, C, dtype), vec_width(y, C, dtype));
   long long n = (long long)N * HW * C;
+  (void)n;
+  RowRed p = rowred_plan(C, vec, HW, N);
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    long long nvec = n / V;
-    cbn_act_fwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)x, nvec, HW, C, stats, scale, offset, labels, act, (T*)y);
+    cbn_act_fwd_kernel<T, V><<<dim3(p.nblk, N), p.threads, 0, s>>>((const T*)x, HW, C, p.rows_per_block, stats, scale, offset, labels,
+                                                                  act, (T*)y);
   });
   count_launch();
   FGC_LAUNCH_CHECK("cbn_act_fwd");
@@ -750,7 +786,7 @@ int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int
   float* sums = scratch;                       // [2,N,C]
   float* m12 = scratch + 2LL * N * C;          // [2,C]
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, s);
-  const int rvec = vmin(vec, 4);
+  const int rvec = vec;
   RowRed p = rowred_plan(C, rvec, HW, N);
   long long n = (long long)N * HW * C;
   FGC_DISPATCH_TV(dtype, rvec, T, V, {
@@ -759,10 +795,11 @@ int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int
                                                                                           labels, act, N, sums);
   });
   cbn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, s>>>(sums, N, C, (long long)N * HW, scale, labels, dscale, doffset, m12);
+  (void)n;
+  RowRed pa = rowred_plan(C, vec, HW, N);
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    long long nvec = n / V;
-    cbn_bwd_apply_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)gy, (const T*)x, nvec, HW, C, stats, scale, offset,
-                                                                  labels, act, m12, (T*)gx);
+    cbn_bwd_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, 0, s>>>((const T*)gy, (const T*)x, HW, C, pa.rows_per_block, stats,
+                                                                      scale, offset, labels, act, m12, (T*)gx);
   });
   count_launch(3);
   FGC_LAUNCH_CHECK("cbn_act_bwd");
@@ -801,16 +838,18 @@ int fgc_minmax_fwd(const void* x, int dtype, int N, int HW, int C, void* gate, f
   uint32_t* mx_ord = scratch + (long long)N * C;
   cudaMemsetAsync(mn_ord, 0xFF, sizeof(uint32_t) * N * C, s);
   cudaMemsetAsync(mx_ord, 0x00, sizeof(uint32_t) * N * C, s);
-  const int rvec = vmin(vec, 4);
+  const int rvec = vec;
   RowRed p = rowred_plan(C, rvec, HW, N);
   long long n = (long long)N * HW * C;
   FGC_DISPATCH_TV(dtype, rvec, T, V, {
     minmax_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 2 * C * sizeof(uint32_t), s>>>((const T*)x, HW, C, p.rows_per_block,
                                                                                             mn_ord, mx_ord);
   });
+  (void)n;
+  RowRed pa = rowred_plan(C, vec, HW, N);
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    long long nvec = n / V;
-    minmax_apply_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)x, nvec, HW, C, mn_ord, mx_ord, (T*)gate, mn, mx);
+    minmax_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, 0, s>>>((const T*)x, HW, C, pa.rows_per_block, mn_ord, mx_ord, (T*)gate,
+                                                                     mn, mx);
   });
   count_launch(2);
   FGC_LAUNCH_CHECK("minmax_fwd");
@@ -821,17 +860,18 @@ int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, i
   cudaStream_t s = as_stream(stream);
   int vec = vmin(vmin(vec_width(x, C, dtype), vec_width(ggate, C, dtype)), vec_width(gpre, C, dtype));
   cudaMemsetAsync(scratch, 0, sizeof(float) * 4 * N * C, s);
-  const int rvec = vmin(vec, 4);
+  const int rvec = vec;
   RowRed p = rowred_plan(C, rvec, HW, N);
   long long n = (long long)N * HW * C;
   FGC_DISPATCH_TV(dtype, rvec, T, V, {
     minmax_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 4 * C * sizeof(float), s>>>((const T*)ggate, (const T*)x, HW, C,
                                                                                              p.rows_per_block, mn, mx, N, scratch);
   });
+  (void)n;
+  RowRed pa = rowred_plan(C, vec, HW, N);
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    long long nvec = n / V;
-    minmax_bwd_apply_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)ggate, (const T*)x, nvec, HW, C, mn, mx, N,
-                                                                     scratch, (T*)gpre);
+    minmax_bwd_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, 0, s>>>((const T*)ggate, (const T*)x, HW, C, pa.rows_per_block, mn,
+                                                                         mx, N, scratch, (T*)gpre);
   });
   count_launch(2);
   FGC_LAUNCH_CHECK("minmax_bwd");

@@ -35,6 +35,20 @@ def close(a, b, tol, what=""):
     assert err <= tol, "%s: rel-to-max err %.3e > %.1e" % (what, err, tol)
 
 
+def _set_impl(cu, impl):
+    """1: CUDA-core checker; 0: product routing (halo-reuse / direct narrow / gather kernels); 2: tensor-core gather
+    kernels only (halo-reuse and direct narrow kernels switched off)."""
+    cu.lib.fgc_set_conv_impl(1 if impl == 1 else 0)
+    cu.lib.fgc_set_conv_flags(0 if impl == 2 else 1, 0 if impl == 2 else 1)
+
+
+def conv_counts(cu):
+    import ctypes
+    arr = (ctypes.c_longlong * 5)()
+    cu.lib.fgc_debug_conv_counts(arr)
+    return list(arr)
+
+
 CONV_CASES = [
     # (N, H, W, [(C, ups), ...], k, stride, Cout, act)
     (2, 16, 16, [(64, False)], 3, 1, 64, ACT_NONE),
@@ -68,11 +82,11 @@ def _conv_inputs(case, dev, seed=0):
     return xs, w_, b
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["simple", "tcgen05"])
+@pytest.mark.parametrize("impl", [1, 0, 2], ids=["simple", "tcgen05", "tcgen05-gather"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[str(i) for i in range(len(CONV_CASES))])
 def test_conv_fwd(env, case, impl):
     cu, ref, dev = env["cu"], env["ref"], env["dev"]
-    cu.lib.fgc_set_conv_impl(impl)
+    _set_impl(cu, impl)
     try:
         N, H, W, srcs, k, stride, cout, act = case
         xs, w, b = _conv_inputs(case, dev)
@@ -80,14 +94,14 @@ def test_conv_fwd(env, case, impl):
         got = cu.conv_fwd([(x.float().contiguous(), u) for x, u in xs], w.float().contiguous(), b.float().contiguous(),
                           stride=stride, act=act)
         torch.cuda.synchronize()
-        close(got, want, 2e-5 if impl == 1 else 1e-4, "conv_fwd fp32")
+        close(got, want, 1e-4 if impl != 1 else 2e-5, "conv_fwd fp32")
         gotb = env["cub"].conv_fwd([(x.bfloat16().contiguous(), u) for x, u in xs], w.float().contiguous(),
                                    b.float().contiguous(), stride=stride, act=act)
         torch.cuda.synchronize()
         assert gotb.dtype == torch.bfloat16
         close(gotb, want, 3e-2, "conv_fwd bf16")
     finally:
-        cu.lib.fgc_set_conv_impl(0)
+        _set_impl(cu, 0)
 
 
 DGRAD_CASES = [
@@ -108,11 +122,11 @@ DGRAD_CASES = [
 ]
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["simple", "tcgen05"])
+@pytest.mark.parametrize("impl", [1, 0, 2], ids=["simple", "tcgen05", "tcgen05-gather"])
 @pytest.mark.parametrize("case", DGRAD_CASES, ids=[str(i) for i in range(len(DGRAD_CASES))])
 def test_conv_dgrad(env, case, impl):
     cu, ref, dev = env["cu"], env["ref"], env["dev"]
-    cu.lib.fgc_set_conv_impl(impl)
+    _set_impl(cu, impl)
     try:
         N, H, W, cin, c_off, c_len, k, cout, ups, acc = case
         gy = rnd((N, H, W, cout), 1, dev)
@@ -129,14 +143,14 @@ def test_conv_dgrad(env, case, impl):
         torch.cuda.synchronize()
         close(gotb, want, 3e-2, "conv_dgrad bf16")
     finally:
-        cu.lib.fgc_set_conv_impl(0)
+        _set_impl(cu, 0)
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["simple", "tcgen05"])
+@pytest.mark.parametrize("impl", [1, 0, 2], ids=["simple", "tcgen05", "tcgen05-gather"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[str(i) for i in range(len(CONV_CASES))])
 def test_conv_wgrad(env, case, impl):
     cu, ref, dev = env["cu"], env["ref"], env["dev"]
-    cu.lib.fgc_set_conv_impl(impl)
+    _set_impl(cu, impl)
     try:
         N, H, W, srcs, k, stride, cout, act = case
         xs, w, b = _conv_inputs(case, dev, seed=20)
@@ -155,7 +169,7 @@ def test_conv_wgrad(env, case, impl):
         torch.cuda.synchronize()
         close(dwb, dw_ref, 3e-2, "conv_wgrad dw bf16")
     finally:
-        cu.lib.fgc_set_conv_impl(0)
+        _set_impl(cu, 0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -353,3 +367,35 @@ def test_losses_and_adam(env):
         close(st.p[k], st_r.p[k], 1e-5, "adam params " + k)
     o = st.offsets["discriminator/Conv_1/weights"]
     close(st.adam_v[o:o + 64], st_r.adam_v[o:o + 64], 1e-5, "adam v")
+
+
+def test_conv_routing(env):
+    """The product routing really uses the kernels it claims: halo-reuse for wide stride-1 bf16 layers (also when the TMA box
+    is taller than the image), the direct kernels for the narrow stem layers, the gather kernel for fp32 / upsampled sources."""
+    cub, cu, dev = env["cub"], env["cu"], env["dev"]
+    _set_impl(cu, 0)
+
+    def delta(fn):
+        c0 = conv_counts(cu)
+        fn()
+        torch.cuda.synchronize()
+        return [b - a for a, b in zip(c0, conv_counts(cu))]
+
+    x128 = rnd((2, 24, 24, 128), 1, dev).bfloat16()
+    w = rnd((3, 3, 128, 64), 2, dev, 0.05).float()
+    b = torch.zeros(64, device=dev)
+    assert delta(lambda: cub.conv_fwd([(x128, False)], w, b))[:2] == [1, 0]               # 34-row box over a 24-row image
+    assert delta(lambda: cu.conv_fwd([(x128.float(), False)], w, b))[:2] == [0, 1]        # fp32 (bf16x3): gather kernel
+    xlow = rnd((2, 12, 12, 128), 3, dev).bfloat16()
+    assert delta(lambda: cub.conv_fwd([(xlow, True)], w, b))[:2] == [0, 1]                # upsampled source: gather kernel
+    gy = rnd((2, 24, 24, 64), 4, dev).bfloat16()
+    assert delta(lambda: cub.conv_dgrad(gy, w, 0, 128))[:2] == [1, 0]
+    x3 = rnd((2, 24, 24, 3), 5, dev).bfloat16()
+    w3 = rnd((7, 7, 3, 8), 6, dev, 0.05).float()
+    b8 = torch.zeros(8, device=dev)
+    assert delta(lambda: cub.conv_fwd([(x3, False)], w3, b8))[2] == 1
+    gy8 = rnd((2, 24, 24, 8), 7, dev).bfloat16()
+    dw, db = torch.zeros_like(w3), torch.zeros_like(b8)
+    assert delta(lambda: cub.conv_wgrad([(x3, False)], gy8, dw, db))[3] == 1
+    dw2, db2 = torch.zeros_like(w), torch.zeros_like(b)
+    assert delta(lambda: cub.conv_wgrad([(x128, False)], gy, dw2, db2))[4] == 1
