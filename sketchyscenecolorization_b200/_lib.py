@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
 
 
 class FgcSrc(C.Structure):
-    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int), ("ups", C.c_int)]
+    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int), ("ups", C.c_int), ("patch", C.c_void_p)]
 
 
 _P, _I, _LL, _F, _SZ = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
@@ -75,6 +75,7 @@ SIGNATURES = {
     "fgc_set_conv_impl": [_I],
     "fgc_set_conv_flags": [_I, _I],
     "fgc_debug_conv_counts": [_P],
+    "fgc_im2col_small": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "fgc_debug_set_trace": [_P, _I],
     "fgc_conv2d_fwd": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "fgc_conv2d_dgrad": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P],

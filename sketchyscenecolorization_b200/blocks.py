@@ -94,11 +94,12 @@ def norm_act_bwd(ops, store, scope, gy, ctx, labels, kind, need_wgrad=True):
 def enc_block_fwd(ops, wv, scope, x, ht, labels, kind, save=True):
     st = wv.store
     a, c_a = norm_act_fwd(ops, st, scope + "/norm_activation_in", ht, labels, kind)
+    xs_ = (x, False, ops.small_patch(x, 3))      # the 3-channel image level: flattened once, read by 2 convs + 2 wgrads
     w, b = wv.get(scope + "/update_gate")
-    rg_raw = ops.conv_fwd([(a, False), (x, False)], w, b, act=ACT_LRELU)          # mru.py:408-414
+    rg_raw = ops.conv_fwd([(a, False), xs_], w, b, act=ACT_LRELU)                 # mru.py:408-414
     rg, mn, mx = ops.minmax_fwd(rg_raw)                                          # mru.py:415-416
     w, b = wv.get(scope + "/Conv")
-    im = ops.conv_fwd([(x, False)], w, b)                                        # mru.py:419-424
+    im = ops.conv_fwd([xs_], w, b)                                               # mru.py:419-424
     hp = ops.gate_fma_fwd(ht, rg, im)                                            # mru.py:426
     p, c_p = norm_act_fwd(ops, st, scope + "/norm_activation_merge_1", hp, labels, kind)
     w, b = wv.get(scope + "/Conv_1")
@@ -111,7 +112,7 @@ def enc_block_fwd(ops, wv, scope, x, ht, labels, kind, save=True):
     out = ops.addpool_fwd(sk, h2)                                                # mru.py:453,457
     ctx = None
     if save:
-        ctx = dict(x=x, ht=ht, a=a, c_a=c_a, rg_raw=rg_raw, rg=rg, mn=mn, mx=mx, im=im, c_p=c_p, p=p, c_h1=c_h1, h1=h1)
+        ctx = dict(x=x, xs_=xs_, ht=ht, a=a, c_a=c_a, rg_raw=rg_raw, rg=rg, mn=mn, mx=mx, im=im, c_p=c_p, p=p, c_h1=c_h1, h1=h1)
     return out, ctx
 
 
@@ -149,7 +150,7 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
     # Conv (image branch)
     wc, _ = wv.get(scope + "/Conv")
     if nw:
-        ops.conv_wgrad([(x, False)], g_im, *wv.grads(scope + "/Conv"))
+        ops.conv_wgrad([ctx["xs_"]], g_im, *wv.grads(scope + "/Conv"))
     g_x = ops.conv_dgrad(g_im, wc, 0, x.shape[-1]) if need_x_grad else None
     del g_im
     # update gate
@@ -157,7 +158,7 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
     del g_rg
     wu, _ = wv.get(scope + "/update_gate")
     if nw:
-        ops.conv_wgrad([(ctx["a"], False), (x, False)], g_rgraw, *wv.grads(scope + "/update_gate"))
+        ops.conv_wgrad([(ctx["a"], False), ctx["xs_"]], g_rgraw, *wv.grads(scope + "/update_gate"))
     if need_x_grad:
         ops.conv_dgrad(g_rgraw, wu, cin, x.shape[-1], out=g_x, acc=True)
     if need_ht_grad:
@@ -178,7 +179,8 @@ def dec_block_fwd(ops, wv, scope, xs, ht_low, cout, labels, save=True):
     # H = upsample(ht) is written once and read by both gate convolutions (and by their weight gradients): tensor-map
     # TMA, which feeds the halo-reuse conv kernel, cannot replicate pixels.  The 1x1 skip below still runs at low resolution.
     h_up = ops.upsample_fwd(ht_low)
-    f = [(h_up, False)] + [(x, False) for x in xs]
+    xsrc = [(x, False, ops.small_patch(x, 3) if x.shape[-1] < 64 else None) for x in xs]
+    f = [(h_up, False)] + xsrc
     w, b = wv.get(scope + "/Conv")
     rg_raw = ops.conv_fwd(f, w, b, act=ACT_LRELU)                                # mru.py:555-559
     rg, mn0, mx0 = ops.minmax_fwd(rg_raw)
@@ -187,7 +189,7 @@ def dec_block_fwd(ops, wv, scope, xs, ht_low, cout, labels, save=True):
     zg, mn1, mx1 = ops.minmax_fwd(zg_raw)
     gh = ops.mul_up_fwd(rg, ht_low)                                              # rg * ht   (mru.py:572)
     w, b = wv.get(scope + "/Conv_2")
-    h1_raw = ops.conv_fwd([(gh, False)] + [(x, False) for x in xs], w, b)
+    h1_raw = ops.conv_fwd([(gh, False)] + xsrc, w, b)
     h1, c_h1 = norm_act_fwd(ops, st, scope + "/Conv_2", h1_raw, labels, "cbn")
     w, b = wv.get(scope + "/Conv_3")
     h2_raw = ops.conv_fwd([(h1, False)], w, b)                                   # mru.py:577-581
@@ -203,7 +205,7 @@ def dec_block_fwd(ops, wv, scope, xs, ht_low, cout, labels, save=True):
     ctx = None
     if save:
         ctx = dict(xs=xs, ht_low=ht_low, rg_raw=rg_raw, rg=rg, mn0=mn0, mx0=mx0, zg_raw=zg_raw, zg=zg, mn1=mn1,
-                   mx1=mx1, gh=gh, c_h1=c_h1, h1=h1, c_h2=c_h2, h2=h2, c_sk=c_sk, sk=sk, cout=cout, h_up=h_up)
+                   mx1=mx1, gh=gh, c_h1=c_h1, h1=h1, c_h2=c_h2, h2=h2, c_sk=c_sk, sk=sk, cout=cout, h_up=h_up, xsrc=xsrc)
     return out, ctx
 
 
@@ -237,7 +239,7 @@ def dec_block_bwd(ops, wv, scope, g_out, ctx, labels, xs_need_grad):
     g_h1raw = norm_act_bwd(ops, st, scope + "/Conv_2", g_h1, ctx["c_h1"], labels, "cbn")
     del g_h1
     w2, _ = wv.get(scope + "/Conv_2")
-    ops.conv_wgrad([(ctx["gh"], False)] + [(x, False) for x in xs], g_h1raw, *wv.grads(scope + "/Conv_2"))
+    ops.conv_wgrad([(ctx["gh"], False)] + ctx["xsrc"], g_h1raw, *wv.grads(scope + "/Conv_2"))
     g_gh = ops.conv_dgrad(g_h1raw, w2, 0, chid)
     g_xs = [ops.conv_dgrad(g_h1raw, w2, offs[i], xs[i].shape[-1]) if xs_need_grad[i] else None
             for i in range(len(xs))]
@@ -247,7 +249,7 @@ def dec_block_bwd(ops, wv, scope, g_out, ctx, labels, xs_need_grad):
     ops.add_(g_ht, g_ht_mul)
     del g_ht_mul
     # gates: the weight gradients read the upsampled hidden state kept by the forward pass
-    f_w = [(ctx["h_up"], False)] + [(x, False) for x in xs]
+    f_w = [(ctx["h_up"], False)] + ctx["xsrc"]
     for (gg, raw, mn, mx, sc) in ((g_rg, ctx["rg_raw"], ctx["mn0"], ctx["mx0"], scope + "/Conv"),
                                   (g_zg, ctx["zg_raw"], ctx["mn1"], ctx["mx1"], scope + "/Conv_1")):
         g_raw = ops.minmax_bwd(gg, raw, mn, mx)

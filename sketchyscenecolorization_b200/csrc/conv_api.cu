@@ -40,6 +40,7 @@ static int build_geom(ConvGeom& g, const fgc_src* srcs, int nsrc, int N, int H, 
     g.src[i] = srcs[i].ptr;
     g.C[i] = srcs[i].C;
     g.ups[i] = srcs[i].ups;
+    g.patch[i] = srcs[i].patch;
     FGC_REQUIRE(srcs[i].C > 0 && srcs[i].ptr, "conv: bad source %d", i);
     if (srcs[i].ups) FGC_REQUIRE(H % 2 == 0 && W % 2 == 0, "conv: upsampled source needs even H, W");
   }
@@ -119,7 +120,7 @@ int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const fl
     return FGC_OK;
   }
   // a stride-1 SAME conv over gy with the taps mirrored and the weight matrix transposed
-  fgc_src src{gy, Cout, 0};
+  fgc_src src{gy, Cout, 0, nullptr};
   ConvGeom g;
   int pad = (k - 1) / 2;
   int e = build_geom(g, &src, 1, N, H, W, k, 1, pad, pad, H, W, -1);

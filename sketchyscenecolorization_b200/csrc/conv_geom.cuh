@@ -17,6 +17,7 @@ constexpr int kMaxSrc = 4;
 
 struct ConvGeom {
   const void* src[kMaxSrc];
+  const void* patch[kMaxSrc];   // narrow sources: optional pre-flattened (tap, channel) bf16 tensor, 64 channels per slab
   int C[kMaxSrc];
   int ups[kMaxSrc];
   int cbase[kMaxSrc];        // first channel of the source inside the concatenated input

@@ -205,6 +205,45 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const __grid_cons
   }
 }
 
+// Patch tensor of a narrow source: out[n,h,w,q] = x[n, h+kh-pad, w+kw-pad, c], q = (kh*k+kw)*C + c, zero beyond k*k*C and
+// outside the image (stride 1, SAME).  One thread writes one 16-byte chunk (8 consecutive q).
+template <typename T>
+__global__ void im2col_small_kernel(const T* __restrict__ x, long long nchunks, int H, int W, int C, int ups, int k, int CP,
+                                    __nv_bfloat16* __restrict__ out) {
+  const int pad = (k - 1) / 2, KK = k * k * C, CPV = CP / 8;
+  const int Hs = ups ? (H >> 1) : H, Ws = ups ? (W >> 1) : W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nchunks; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % CPV);
+    long long p = i / CPV;
+    const int w = (int)(p % W);
+    p /= W;
+    const int h = (int)(p % H);
+    const long long n = p / H;
+    float v[8];
+    int q = ch * 8;
+    int tap = q / C, c = q - tap * C;
+    int kh = tap / k, kw = tap - kh * k;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      float val = 0.f;
+      if (q < KK) {
+        int ih = h + kh - pad, iw = w + kw - pad;
+        if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
+          if (ups) { ih >>= 1; iw >>= 1; }
+          val = ld1<T>(x + ((n * Hs + ih) * Ws + iw) * C + c);
+        }
+      }
+      v[e] = val;
+      q++; c++;
+      if (c == C) { c = 0; kw++; if (kw == k) { kw = 0; kh++; } }
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(bf16x2_bits(v[0], v[1]), bf16x2_bits(v[2], v[3]), bf16x2_bits(v[4], v[5]),
+                                                       bf16x2_bits(v[6], v[7]));
+  }
+}
+
+int ew_grid(long long work, int threads);
+
 static bool all_small(const ConvGeom& g) {
   for (int i = 0; i < g.nsrc; i++)
     if (g.big[i]) return false;
@@ -286,3 +325,21 @@ int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int C
 }
 
 }  // namespace fgc
+
+extern "C" int fgc_im2col_small(const void* x, int dtype, int N, int H, int W, int C, int ups, int k, void* out, fgc_stream stream) {
+  using namespace fgc;
+  FGC_REQUIRE(k % 2 == 1 && C > 0 && N > 0, "im2col_small: bad arguments");
+  FGC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "im2col_small: out must be 16-byte aligned");
+  if (ups) FGC_REQUIRE(H % 2 == 0 && W % 2 == 0, "im2col_small: upsampled source needs even H, W");
+  const int CP = 64 * ((k * k * C + 63) / 64);
+  const long long nchunks = (long long)N * H * W * (CP / 8);
+  cudaStream_t s = as_stream(stream);
+  if (dtype == FGC_F32)
+    im2col_small_kernel<float><<<ew_grid(nchunks, 256), 256, 0, s>>>((const float*)x, nchunks, H, W, C, ups, k, CP, (__nv_bfloat16*)out);
+  else if (dtype == FGC_BF16)
+    im2col_small_kernel<__nv_bfloat16><<<ew_grid(nchunks, 256), 256, 0, s>>>((const __nv_bfloat16*)x, nchunks, H, W, C, ups, k, CP,
+                                                                            (__nv_bfloat16*)out);
+  else { set_error("im2col_small: bad dtype %d", dtype); return FGC_EINVAL; }
+  count_launch();
+  return check_launch("im2col_small");
+}

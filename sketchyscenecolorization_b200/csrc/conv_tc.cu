@@ -784,9 +784,10 @@ struct HaloArgs {
   int tiles_w, tiles_per_img, tiles_m;
   int nitems;
   // K-loop of one tile.  big item: bit 15 | source << 12 | kw << 8 | channel group  -> one box, k weight slabs (kh = 0..k-1);
-  // small item: global slab index -> one gathered A tile, one weight slab
+  // patch item: bit 14 | source << 12 | slab within the source -> one box of the source's pre-flattened (tap, channel)
+  // tensor at the tile's own rows, one weight slab;  small item: global slab index -> one gathered A tile, one weight slab
   uint16_t items[kMaxItems];
-  CUtensorMap tm[kMaxSrc];
+  CUtensorMap tm[kMaxSrc];   // wide sources: the source itself; patched narrow sources: the patch tensor
 };
 
 template <int BN, int MT, int NACC>
@@ -861,7 +862,7 @@ __global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const _
           const uint32_t ph = (ga / a_slots) & 1;
           const uint32_t item = a.items[it];
           mbar_wait(smem_u32(&a_empty[slot]), ph ^ 1);
-          if (!(item & 0x8000u)) {
+          if (!(item & 0xC000u)) {
             const int4 e = __ldg(a.tbl + item);
             const int si_s = e.x & 0xFF;
             const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(g.src[si_s]);
@@ -887,6 +888,7 @@ __global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const _
         const int slot = ga % a_slots;
         const uint32_t item = a.items[it];
         const bool big = (item & 0x8000u) != 0;
+        const bool boxed = (item & 0xC000u) != 0;      // A operand is a TMA box (8-pixel rows), not a gathered tile
         const int nb = big ? k : 1;
         mbar_wait(smem_u32(&a_full[slot]), (ga / a_slots) & 1);
         const uint32_t sa = smem_u32(sA + (size_t)slot * a.a_slot_bytes);
@@ -900,7 +902,7 @@ __global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const _
             const int jrow = big ? (sign > 0 ? j : k - 1 - j) : 0;
 #pragma unroll
             for (int tt = 0; tt < MT; tt++) {
-              const uint32_t aoff = big ? (uint32_t)(16 * tt + jrow) * 1024u : (uint32_t)tt * 16384u;
+              const uint32_t aoff = boxed ? (uint32_t)(16 * tt + jrow) * 1024u : (uint32_t)tt * 16384u;
               const uint64_t da = desc_kmajor(sa + aoff, 1024);
               const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS + tt * BN);
 #pragma unroll
@@ -923,7 +925,7 @@ __global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const _
     // ===================== A loader: one tensor-map box per big item =====================
     if (lane == 0) {
       for (int s2 = 0; s2 < g.nsrc; s2++)
-        if (g.big[s2]) tma_prefetch_desc(&a.tm[s2]);
+        if (g.big[s2] || g.patch[s2]) tma_prefetch_desc(&a.tm[s2]);
       const uint32_t box_bytes = (uint32_t)a.box_rows * 1024u;
       int ga = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -941,6 +943,10 @@ __global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const _
             const int s2 = (item >> 12) & 3, kw = (item >> 8) & 15, cg = item & 0xFF;
             mbar_arrive_expect_tx(bar, box_bytes);
             tma_load_4d(smem_u32(sA + (size_t)slot * a.a_slot_bytes), &a.tm[s2], cg * 64, w0 + sign * (kw - pad), h0, n, bar);
+          } else if (item & 0x4000u) {
+            const int s2 = (item >> 12) & 3, j = item & 0xFF;
+            mbar_arrive_expect_tx(bar, box_bytes);     // the tile's own rows first; the k-1 extra rows of the box go unused
+            tma_load_4d(smem_u32(sA + (size_t)slot * a.a_slot_bytes), &a.tm[s2], j * 64, w0, h0 + pad, n, bar);
           } else {
             mbar_arrive(bar);
           }
@@ -960,7 +966,8 @@ __global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const _
           const int ncb = big ? (g.C[s2] + 63) >> 6 : 0;
           const int nb = big ? k : 1;
           for (int j = 0; j < nb; j++, gb++) {
-            const int slab = big ? g.slab_begin[s2] + (j * k + kw) * ncb + cg : (int)item;
+            const int slab = big ? g.slab_begin[s2] + (j * k + kw) * ncb + cg
+                                 : ((item & 0x4000u) ? g.slab_begin[s2] + cg : (int)item);
             const int bslot = gb % b_slots;
             mbar_wait(smem_u32(&b_empty[bslot]), ((gb / b_slots) & 1) ^ 1);
             const uint32_t bar = smem_u32(&b_full[bslot]);
@@ -1091,7 +1098,8 @@ struct WgradArgs {
   int dbg;            // debug switches (env FGC_DBG): 4 = skip the MMAs, 8 = skip the loads
   // tiled mode (bf16): a K-slab is a tw x th pixel rectangle of one image and TMA-able blocks are fetched by tensor TMA
   int tiled, tw_log2, th, tiles_w, tiles_per_img;
-  int tma_mask;       // bit s: source s is loaded by TMA
+  int tma_mask;       // bit s: source s is loaded by TMA (wide source: the source itself, shifted by the tap; narrow source
+                      // with a patch tensor: its pre-flattened (tap, channel) blocks at the slab's own pixels)
   int tma_gy;         // gy blocks are loaded by TMA
   CUtensorMap tm_src[kMaxSrc];
   CUtensorMap tm_gy;
@@ -1155,7 +1163,7 @@ __global__ void __launch_bounds__(320, 1) conv_wgrad_kernel(const __grid_constan
   }
   bool btma[2 * G];        // block is fetched by the TMA warp
 #pragma unroll
-  for (int q = 0; q < 2 * G; q++) btma[q] = tiled && have[q] && si[q].big && ((a.tma_mask >> si[q].s) & 1);
+  for (int q = 0; q < 2 * G; q++) btma[q] = tiled && have[q] && ((a.tma_mask >> si[q].s) & 1);
   const bool gy_tma = tiled && a.tma_gy;
 
   if (warp < MMA_WARP) {
@@ -1164,7 +1172,7 @@ __global__ void __launch_bounds__(320, 1) conv_wgrad_kernel(const __grid_constan
     const bool fast = !S::X3 && a.fast;
     bool all_async = fast && gy_vec;
 #pragma unroll
-    for (int q = 0; q < 2 * G; q++) all_async = all_async && (!have[q] || si[q].big);
+    for (int q = 0; q < 2 * G; q++) all_async = all_async && (!have[q] || si[q].big || btma[q]);
     const int hw4 = (g.OH * g.OW) >> 2;
     const int twm = (1 << a.tw_log2) - 1;
     // blocks that never receive data stay zero for the whole kernel
@@ -1360,8 +1368,12 @@ __global__ void __launch_bounds__(320, 1) conv_wgrad_kernel(const __grid_constan
 #pragma unroll
           for (int q = 0; q < 2 * G; q++) {
             if (!btma[q]) continue;
-            const int kh = si[q].tap / g.k, kw = si[q].tap % g.k;
-            tma_load_4d(sa + q * BLK, &a.tm_src[si[q].s], si[q].c0, w0 + kw - g.pad_l, h0 + kh - g.pad_t, n, bar);
+            if (si[q].big) {
+              const int kh = si[q].tap / g.k, kw = si[q].tap % g.k;
+              tma_load_4d(sa + q * BLK, &a.tm_src[si[q].s], si[q].c0, w0 + kw - g.pad_l, h0 + kh - g.pad_t, n, bar);
+            } else {            // patch tensor: channel block q0 holds the flattened (tap, channel) values of these pixels
+              tma_load_4d(sa + q * BLK, &a.tm_src[si[q].s], si[q].q0, w0, h0, n, bar);
+            }
           }
           if (gy_tma) {
 #pragma unroll
@@ -1595,8 +1607,12 @@ static int launch_halo(HaloArgs& h, cudaStream_t s) {
   h.tiles_per_img = tiles_h * h.tiles_w;
   h.tiles_m = h.g.N * h.tiles_per_img;
   for (int i = 0; i < h.g.nsrc; i++) {
-    if (!h.g.big[i]) continue;
-    if (!make_tmap_nhwc(&h.tm[i], h.g.src[i], h.g.C[i], h.g.W, h.g.H, h.g.N, 8, h.box_rows)) return -1;
+    if (h.g.big[i]) {
+      if (!make_tmap_nhwc(&h.tm[i], h.g.src[i], h.g.C[i], h.g.W, h.g.H, h.g.N, 8, h.box_rows)) return -1;
+    } else if (h.g.patch[i]) {
+      const int cp = 64 * (h.g.slab_begin[i + 1] - h.g.slab_begin[i]);
+      if (!make_tmap_nhwc(&h.tm[i], h.g.patch[i], cp, h.g.W, h.g.H, h.g.N, 8, h.box_rows)) return -1;
+    }
   }
   size_t smem = (size_t)a_slots * h.a_slot_bytes + (size_t)b_slots * B_BYTES + (2 * a_slots + 2 * b_slots + 2 * NACC) * 8 + 16 + 1024;
   static bool attr_set = false;
@@ -1620,9 +1636,13 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
   const ConvGeom& g = ia.g;
   if (!ia.fast || (g.k & 1) == 0 || g.k > 15 || g.pad_t != (g.k - 1) / 2 || g.pad_l != g.pad_t) return -1;
   if (g.k == 1 && mode < 2) return -1;
-  bool any_big = false;
+  bool any_big = false, any_gather = false;
   for (int i = 0; i < g.nsrc; i++) {
-    if (!g.big[i]) continue;
+    if (!g.big[i]) {
+      if (g.patch[i] && (reinterpret_cast<uintptr_t>(g.patch[i]) & 15) == 0) any_big = true;
+      else any_gather = true;
+      continue;
+    }
     if (g.ups[i]) return -1;                       // tensor TMA cannot replicate pixels
     any_big = true;
   }
@@ -1636,7 +1656,7 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
   int mt = 2;
   long long tiles2 = (long long)g.N * ((g.OH + 31) / 32) * ((g.OW + 7) / 8) * (ia.Npad / bn);
   if (eff(1) > eff(2) + 1e-9 || tiles2 < (long long)num_sms()) mt = 1;
-  if (eff(mt) < 0.7) return -1;
+  if (eff(mt) < 0.8) return -1;               // e.g. 24x24 images (75%): the per-tap gather kernel wastes nothing there
   HaloArgs h;
   h.g = g;
   h.wp = ia.wp;
@@ -1649,7 +1669,7 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
   h.y_dtype = ia.y_dtype;
   h.vec_ok = ia.vec_ok;
   h.tbl = ia.tbl;
-  h.any_small = ia.any_small;
+  h.any_small = any_gather ? 1 : 0;
   int ni = 0;
   for (int i = 0; i < g.nsrc; i++) {
     if (g.big[i]) {
@@ -1660,9 +1680,16 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
           if (ni >= kMaxItems) return -1;
           h.items[ni++] = (uint16_t)(0x8000u | (i << 12) | (kw << 8) | cg);
         }
+    } else if (g.patch[i] && (reinterpret_cast<uintptr_t>(g.patch[i]) & 15) == 0) {
+      const int ns = g.slab_begin[i + 1] - g.slab_begin[i];
+      if (ns > 255) return -1;
+      for (int j = 0; j < ns; j++) {
+        if (ni >= kMaxItems) return -1;
+        h.items[ni++] = (uint16_t)(0x4000u | (i << 12) | j);
+      }
     } else {
       for (int sl = g.slab_begin[i]; sl < g.slab_begin[i + 1]; sl++) {
-        if (ni >= kMaxItems || sl >= 0x8000) return -1;
+        if (ni >= kMaxItems || sl >= 0x4000) return -1;
         h.items[ni++] = (uint16_t)sl;
       }
     }
@@ -1695,7 +1722,14 @@ static void wgrad_setup_tiled(WgradArgs& a, int x3) {
   if (tw < 8 || g.H % th) return;
   bool any = false;
   for (int s = 0; s < g.nsrc; s++) {
-    if (!g.big[s]) continue;
+    if (!g.big[s]) {
+      if (!g.patch[s] || (reinterpret_cast<uintptr_t>(g.patch[s]) & 15)) continue;
+      const int cp = 64 * (g.slab_begin[s + 1] - g.slab_begin[s]);
+      if (!make_tmap_nhwc(&a.tm_src[s], g.patch[s], cp, g.W, g.H, g.N, tw, th)) return;
+      a.tma_mask |= 1 << s;
+      any = true;
+      continue;
+    }
     if (g.ups[s]) continue;                    // read through the x2 upsample: gathered by the producer warps
     if (!make_tmap_nhwc(&a.tm_src[s], g.src[s], g.C[s], g.W, g.H, g.N, tw, th)) return;
     a.tma_mask |= 1 << s;
@@ -1782,6 +1816,7 @@ int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, in
       g.C[0] % 8 == 0 && g.pad_t == (g.k - 1) / 2 && g.pad_l == (g.k - 1) / 2) {
     ConvGeom gs = g;
     gs.src[0] = gy;
+    gs.patch[0] = nullptr;
     gs.C[0] = Cout;
     finish_geom(gs);
     a.g = gs;

@@ -67,12 +67,15 @@ class CudaOps(OpsBase):
         dt = srcs[0][0].dtype
         arr = (FgcSrc * len(srcs))()
         H = W = None
-        for i, (t, ups) in enumerate(srcs):
+        for i, e in enumerate(srcs):
+            t, ups = e[0], e[1]
+            patch = e[2] if len(e) > 2 else None
             assert t.dtype == dt, "all conv sources must share a dtype"
             assert t.dim() == 4
             arr[i].ptr = self._p(t)
             arr[i].C = t.shape[3]
             arr[i].ups = 1 if ups else 0
+            arr[i].patch = None if patch is None else self._p(patch)
             h, w = (t.shape[1] * 2, t.shape[2] * 2) if ups else (t.shape[1], t.shape[2])
             assert H is None or (H, W) == (h, w), "conv sources disagree on the spatial size"
             H, W = h, w
@@ -89,11 +92,23 @@ class CudaOps(OpsBase):
         OH, pt = _same_pad(H, k, stride)
         OW, pl = _same_pad(W, k, stride)
         y = self._empty((N, OH, OW, cout), out_dtype or self.act_dtype)
-        ws = self._ws([t.shape[3] for t, _ in srcs], k, cout, dt)
+        ws = self._ws([e[0].shape[3] for e in srcs], k, cout, dt)
         check(self.lib.fgc_conv2d_fwd(arr, len(srcs), dt, N, H, W, self._f32(w), k, cin, cout,
                                       None if b is None else self._f32(b.reshape(-1)), stride, pt, pl, OH, OW, act,
                                       self._p(y), self._dt(y), self._p(ws), self._s()), "conv2d_fwd")
         return y
+
+    def small_patch(self, x, k, ups=False):
+        """bf16 training mode only: flattened (tap, channel) copy of a narrow source for the TMA-fed conv kernels."""
+        N, h, w, Cc = x.shape
+        H, W = (2 * h, 2 * w) if ups else (h, w)
+        if x.dtype != torch.bfloat16 or Cc >= 64 or k < 3 or W % 8 != 0:
+            return None
+        cp = 64 * ((k * k * Cc + 63) // 64)
+        out = self._empty((N, H, W, cp), torch.bfloat16)
+        check(self.lib.fgc_im2col_small(self._p(x), self._dt(x), N, H, W, Cc, 1 if ups else 0, k, self._p(out), self._s()),
+              "im2col_small")
+        return out
 
     def conv_dgrad(self, gy, w, c_off, c_len, *, ups=False, out=None, acc=False, out_dtype=None):
         N, H, W, cout = gy.shape
@@ -460,7 +475,8 @@ def enable_op_timing(ops):
                     wshape = a[1].shape if name == "conv_fwd" else a[2].shape
                     sig = "%s N%d %dx%d srcs[%s] k%d cout%d" % (key, t0.shape[0], t0.shape[1] * (2 if a[0][0][1] else 1),
                                                                t0.shape[2] * (2 if a[0][0][1] else 1),
-                                                               ",".join("%d%s" % (t.shape[3], "u" if u else "") for t, u in a[0]),
+                                                               ",".join("%d%s%s" % (e[0].shape[3], "u" if e[1] else "", "p" if len(e) > 2 and e[2] is not None else "")
+                                                                        for e in a[0]),
                                                                wshape[0], wshape[3])
                 d = ops.op_detail.setdefault(sig, [0, 0.0])
                 d[0] += 1

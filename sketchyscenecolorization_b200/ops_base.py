@@ -10,7 +10,8 @@ Conventions
     2-D row tensors [R, C] are the NHWC special case H=W=1.
   * weights / biases / tables / statistics / gradients of weights are always fp32; conv weights keep the
     reference HWIO layout [k,k,Cin,Cout] (mru.py:118), a 2-D matrix [K,N] is HWIO with k=1.
-  * `srcs` of a conv is a list of (tensor, ups) pairs concatenated along channels in list order
+  * `srcs` of a conv is a list of (tensor, ups) pairs -- or (tensor, ups, patch) triples, see `small_patch` --
+    concatenated along channels in list order
     (tf.concat, mru.py:403,552,572); ups=True reads the source through a nearest-neighbour x2 upsample
     (mru.upsample, mru.py:22-28) without materialising it.
   * ops that take `acc=True` add into the given output instead of overwriting it.
@@ -107,6 +108,12 @@ class OpsBase:
 
     def meanpool_fwd(self, x):
         raise NotImplementedError
+
+    def small_patch(self, x, k, ups=False):
+        """Optional accelerator for a NARROW conv source (C < 64): a pre-flattened (tap, channel) copy of x for kernel size k
+        that TMA-fed kernels fetch instead of gathering element-wise; pass it as the third element of the source tuple.
+        Returns None where it would not help (implementations are free to ignore it: the value of the conv is unchanged)."""
+        return None
 
     def upsample_fwd(self, x):
         """up2(x), materialised (only the weight-gradient path wants it in memory)"""

@@ -63,7 +63,7 @@ CONV_CASES = [
     (2, 6, 6, [(96, False)], 3, 1, 1, ACT_NONE),                # patch logits (Cout 1), partial K slab
     # halo-reuse kernel (bf16, stride 1, wide sources through tensor-map TMA)
     (8, 64, 80, [(64, False)], 3, 1, 128, ACT_LRELU),           # two sub-tiles per CTA (32 x 8 pixel tiles)
-    (2, 24, 24, [(128, False), (3, False)], 3, 1, 64, ACT_NONE),    # wide + sketch source, ragged tile rows (24 = 16 + 8)
+    (2, 28, 24, [(128, False), (3, False)], 3, 1, 64, ACT_NONE),    # wide + sketch source, ragged tile rows (28 = 16 + 12)
     (8, 64, 80, [(64, False), (8, False), (3, False)], 3, 1, 256, ACT_NONE),   # 256-wide N tile, two small sources
     (2, 32, 40, [(192, False)], 7, 1, 3, ACT_TANH),             # 7x7 over three channel groups, Cout 3
     (3, 30, 22, [(72, False)], 3, 1, 40, ACT_MIU),              # partial channel group (72 = 64 + 8), ragged rows and columns
@@ -381,14 +381,14 @@ def test_conv_routing(env):
         torch.cuda.synchronize()
         return [b - a for a, b in zip(c0, conv_counts(cu))]
 
-    x128 = rnd((2, 24, 24, 128), 1, dev).bfloat16()
+    x128 = rnd((2, 16, 24, 128), 1, dev).bfloat16()
     w = rnd((3, 3, 128, 64), 2, dev, 0.05).float()
     b = torch.zeros(64, device=dev)
-    assert delta(lambda: cub.conv_fwd([(x128, False)], w, b))[:2] == [1, 0]               # 34-row box over a 24-row image
+    assert delta(lambda: cub.conv_fwd([(x128, False)], w, b))[:2] == [1, 0]               # 18-row box over a 16-row image
     assert delta(lambda: cu.conv_fwd([(x128.float(), False)], w, b))[:2] == [0, 1]        # fp32 (bf16x3): gather kernel
-    xlow = rnd((2, 12, 12, 128), 3, dev).bfloat16()
+    xlow = rnd((2, 8, 12, 128), 3, dev).bfloat16()
     assert delta(lambda: cub.conv_fwd([(xlow, True)], w, b))[:2] == [0, 1]                # upsampled source: gather kernel
-    gy = rnd((2, 24, 24, 64), 4, dev).bfloat16()
+    gy = rnd((2, 16, 24, 64), 4, dev).bfloat16()
     assert delta(lambda: cub.conv_dgrad(gy, w, 0, 128))[:2] == [1, 0]
     x3 = rnd((2, 24, 24, 3), 5, dev).bfloat16()
     w3 = rnd((7, 7, 3, 8), 6, dev, 0.05).float()
@@ -399,3 +399,35 @@ def test_conv_routing(env):
     assert delta(lambda: cub.conv_wgrad([(x3, False)], gy8, dw, db))[3] == 1
     dw2, db2 = torch.zeros_like(w), torch.zeros_like(b)
     assert delta(lambda: cub.conv_wgrad([(x128, False)], gy, dw2, db2))[4] == 1
+
+
+@pytest.mark.parametrize("case", [(8, 64, 80, [(64, False), (8, False), (3, False)], 3, 64),
+                                  (2, 28, 24, [(3, False)], 3, 128),
+                                  (3, 32, 64, [(128, False), (3, True)], 3, 32)], ids=str)
+def test_conv_with_patch_sources(env, case):
+    """Narrow sources handed over as pre-flattened patch tensors (fgc_im2col_small): forward and weight gradient fetch them by
+    TMA (halo-reuse kernel / tiled wgrad); values equal the plain-source result."""
+    cub, ref, dev = env["cub"], env["ref"], env["dev"]
+    N, H, W, srcs, k, cout = case
+    xs, w, b = _conv_inputs((N, H, W, srcs, k, 1, cout, ACT_NONE), dev, seed=40)
+    want = ref.conv_fwd(xs, w, b)
+    xb = []
+    for x, u in xs:
+        t = x.bfloat16().contiguous()
+        p = cub.small_patch(t, k, ups=u) if t.shape[-1] < 64 else None
+        if t.shape[-1] < 64:
+            assert p is not None and p.shape[-1] % 64 == 0
+        xb.append((t, u, p))
+    c0 = conv_counts(cub)
+    got = cub.conv_fwd(xb, w.float().contiguous(), b.float().contiguous())
+    torch.cuda.synchronize()
+    assert conv_counts(cub)[0] == c0[0] + 1          # halo-reuse kernel, no gathered slabs needed
+    close(got, want, 3e-2, "conv_fwd with patch sources")
+    gy = rnd((N, H, W, cout), 51, dev)
+    dw0, db0 = rnd(w.shape, 52, dev), rnd(b.shape, 53, dev)
+    dw_ref, db_ref = dw0.clone(), db0.clone()
+    ref.conv_wgrad(xs, gy, dw_ref, db_ref)
+    dw, db = dw0.float().contiguous(), db0.float().contiguous()
+    cub.conv_wgrad(xb, gy.bfloat16().contiguous(), dw, db)
+    torch.cuda.synchronize()
+    close(dw, dw_ref, 3e-2, "conv_wgrad with patch sources")

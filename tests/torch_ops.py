@@ -58,7 +58,7 @@ class TorchOps(OpsBase):
 
     # ---- conv family
     def _cat(self, srcs):
-        return torch.cat([_up(self._c(t)) if ups else self._c(t) for t, ups in srcs], dim=-1)
+        return torch.cat([_up(self._c(e[0])) if e[1] else self._c(e[0]) for e in srcs], dim=-1)
 
     def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None):
         x = self._cat(srcs).permute(0, 3, 1, 2)
