@@ -14,6 +14,7 @@
 
 namespace fgc {
 int num_sms();
+extern long long g_conv_counts[5];
 
 constexpr int kTS = 16;        // output tile edge
 
@@ -244,12 +245,143 @@ __global__ void im2col_small_kernel(const T* __restrict__ x, long long nchunks, 
 
 int ew_grid(long long work, int threads);
 
+// ------------------------------------------------------------------------------------------------------
+// Skinny products: y[M <= 64 rows, Nout] = x[M, K] * W (+ bias, act) with fp32 accumulation on the CUDA cores.
+// These are the per-time-step products of the caption encoder (word LSTM gates [N,2D]x[2D,4D], the row term of the
+// multimodal LSTM, and their input gradients; models_collection.py:184-187,212-226): one 128-row tensor-core tile
+// would be half empty and the 16 CTAs it yields spend their time on pipeline latency (75 us per call, 60+60 calls
+// per iteration).  Here a CTA owns 32 output columns; its 8 warps split every 128-wide K chunk 8 ways, each thread
+// keeps all 64 rows of one column in registers, x is staged in shared memory and read as warp-wide broadcasts.
+// Weight addressing is the packer's: value(k, n) = w[k*k_stride + n*n_stride + base], so the forward product
+// (n contiguous) and the input-gradient product (k contiguous, float4 loads) share the kernel.
+// ------------------------------------------------------------------------------------------------------
+struct RowsArgs {
+  const void* src[kMaxSrc];
+  int C[kMaxSrc], cbase[kMaxSrc];
+  int nsrc;
+  int M, K;
+  const float* w;
+  long long k_stride, n_stride, base;
+  int nout;
+  const float* bias;
+  int act, accumulate;
+  void* y;
+  int y_dtype;
+  int wvec;                  // k_stride == 1 and 16-byte aligned rows: float4 weight loads
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_rows_kernel(const __grid_constant__ RowsArgs a) {
+  constexpr int KC = 128, NB = 32, NS = 8, MR = 64;
+  __shared__ __align__(16) float xs[MR * KC];        // 32 KB: x chunk [64][128]; reused as the slice-reduction buffer
+  const int tid = threadIdx.x, lane = tid & 31, slice = tid >> 5;
+  const int n = blockIdx.x * NB + lane;
+  const bool nvalid = n < a.nout;
+  float acc[MR];
+#pragma unroll
+  for (int m = 0; m < MR; m++) acc[m] = 0.f;
+  const float* wn = a.w + (long long)(nvalid ? n : 0) * a.n_stride + a.base;
+  for (int k0 = 0; k0 < a.K; k0 += KC) {
+    __syncthreads();
+    for (int i = tid; i < MR * KC; i += 256) {
+      const int m = i / KC, kk = i - m * KC;
+      const int kg = k0 + kk;
+      float v = 0.f;
+      if (m < a.M && kg < a.K) {
+        int s = 0;
+        while (s + 1 < a.nsrc && kg >= a.cbase[s + 1]) s++;
+        v = ld1<T>(reinterpret_cast<const T*>(a.src[s]) + (long long)m * a.C[s] + (kg - a.cbase[s]));
+      }
+      xs[i] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int kk = slice * (KC / NS); kk < (slice + 1) * (KC / NS); kk += 4) {
+      const int kg = k0 + kk;
+      float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+      if (nvalid) {
+        if (a.wvec && kg + 3 < a.K) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(wn + kg));
+          w0 = t.x; w1 = t.y; w2 = t.z; w3 = t.w;
+        } else {
+          if (kg < a.K) w0 = __ldg(wn + (long long)kg * a.k_stride);
+          if (kg + 1 < a.K) w1 = __ldg(wn + (long long)(kg + 1) * a.k_stride);
+          if (kg + 2 < a.K) w2 = __ldg(wn + (long long)(kg + 2) * a.k_stride);
+          if (kg + 3 < a.K) w3 = __ldg(wn + (long long)(kg + 3) * a.k_stride);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < MR; m++) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xs + m * KC + kk);
+        acc[m] += x4.x * w0 + x4.y * w1 + x4.z * w2 + x4.w * w3;
+      }
+    }
+  }
+  // combine the 8 K slices: two halves of 32 rows through shared memory [slice][row][column]
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < 32; mm++) xs[(slice * 32 + mm) * NB + lane] = acc[half * 32 + mm];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int mm = slice * 4 + r, m = half * 32 + mm;
+      float v = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < NS; sl++) v += xs[(sl * 32 + mm) * NB + lane];
+      if (m < a.M && nvalid) {
+        if (a.bias) v += __ldg(a.bias + n);
+        v = small_act(v, a.act);
+        const long long o = (long long)m * a.nout + n;
+        if (a.y_dtype == FGC_F32) {
+          float* yp = reinterpret_cast<float*>(a.y);
+          yp[o] = a.accumulate ? yp[o] + v : v;
+        } else {
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y);
+          yp[o] = __float2bfloat16_rn(a.accumulate ? __bfloat162float(yp[o]) + v : v);
+        }
+      }
+    }
+  }
+}
+
+static int rows_mode() {
+  static int mode = -1;        // FGC_ROWS=0 sends the skinny products through the tensor-core path as well
+  if (mode < 0) { const char* e = getenv("FGC_ROWS"); mode = e ? atoi(e) : 1; }
+  return mode;
+}
+
+// returns -1 when the product is not eligible, else the launch status
+int conv_rows_try(const ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride, long long n_stride,
+                  long long base, int nout, const float* bias, int act, int accumulate, void* y, int y_dtype, cudaStream_t s) {
+  (void)tap_stride;
+  if (!rows_mode() || g.k != 1 || g.stride != 1 || g.M > 64 || g.M < 1) return -1;
+  RowsArgs a;
+  a.nsrc = g.nsrc;
+  for (int i = 0; i < g.nsrc; i++) {
+    if (g.ups[i]) return -1;
+    a.src[i] = g.src[i]; a.C[i] = g.C[i]; a.cbase[i] = g.cbase[i];
+  }
+  a.M = (int)g.M;
+  a.K = g.cbase[g.nsrc - 1] + g.C[g.nsrc - 1];
+  if (a.K < 64) return -1;
+  a.w = w; a.k_stride = k_stride; a.n_stride = n_stride; a.base = base;
+  a.nout = nout; a.bias = bias; a.act = act; a.accumulate = accumulate; a.y = y; a.y_dtype = y_dtype;
+  a.wvec = (k_stride == 1 && (n_stride & 3) == 0 && (base & 3) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0) ? 1 : 0;
+  const int grid = (nout + 31) / 32;
+  if (src_dtype == FGC_F32) conv_rows_kernel<float><<<grid, 256, 0, s>>>(a);
+  else conv_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(a);
+  g_conv_counts[2]++;
+  count_launch();
+  return check_launch("conv_rows");
+}
+
 static bool all_small(const ConvGeom& g) {
   for (int i = 0; i < g.nsrc; i++)
     if (g.big[i]) return false;
   return true;
 }
-extern long long g_conv_counts[5];
 int g_small_mode = -1;         // fgc_set_conv_flags / env FGC_SMALL; 0 sends the narrow layers through the tensor-core path
 static int small_mode() {
   if (g_small_mode < 0) { const char* e = getenv("FGC_SMALL"); g_small_mode = e ? atoi(e) : 1; }

@@ -1494,6 +1494,8 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s);
 int conv_small_fwd_try(const ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride,
                        long long n_stride, long long base, int nout, const float* bias, int act, int accumulate, void* y,
                        int y_dtype, cudaStream_t s);
+int conv_rows_try(const ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride, long long n_stride,
+                  long long base, int nout, const float* bias, int act, int accumulate, void* y, int y_dtype, cudaStream_t s);
 int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s);
 
 // run y[M, nout] (=|+=) act(implicit_gemm(g) + bias) with weights w addressed as described in pack_weights_kernel
@@ -1503,7 +1505,9 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
   FGC_REQUIRE(geom_fits(g), "conv: tensor too large for pixel packing");
   FGC_REQUIRE(g.M < (1LL << 31), "conv: more than 2^31 output pixels");
   {
-    int r = conv_small_fwd_try(g, src_dtype, w, tap_stride, k_stride, n_stride, base, nout, bias, act, accumulate, y, y_dtype, s);
+    int r = conv_rows_try(g, src_dtype, w, tap_stride, k_stride, n_stride, base, nout, bias, act, accumulate, y, y_dtype, s);
+    if (r >= 0) return r;                 // skinny product (<= 64 rows): CUDA-core kernel (conv_small.cu)
+    r = conv_small_fwd_try(g, src_dtype, w, tap_stride, k_stride, n_stride, base, nout, bias, act, accumulate, y, y_dtype, s);
     if (r >= 0) return r;                 // narrow layer: CUDA-core direct kernel (conv_small.cu)
   }
   FGC_REQUIRE(ws != nullptr, "conv: workspace required");

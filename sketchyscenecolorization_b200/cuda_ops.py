@@ -323,9 +323,15 @@ class CudaOps(OpsBase):
         return y
 
     # ---------------- text fusion ----------------
-    def l2norm_rows_fwd(self, x):
+    def _dst(self, out, shape, dtype=torch.float32):
+        if out is None:
+            return self._empty(shape, dtype)
+        assert tuple(out.shape) == tuple(shape) and out.dtype == dtype and out.is_contiguous()
+        return out
+
+    def l2norm_rows_fwd(self, x, out=None):
         R, D = x.shape
-        y = self._empty((R, D), torch.float32)
+        y = self._dst(out, (R, D))
         inv = self._empty((R,), torch.float32)
         check(self.lib.fgc_l2norm_rows_fwd(self._f32(x), R, D, self._p(y), self._p(inv), self._s()), "l2norm_rows_fwd")
         return y, inv
@@ -337,10 +343,10 @@ class CudaOps(OpsBase):
               "l2norm_rows_bwd")
         return gx
 
-    def embedding_fwd(self, table, ids, t):
+    def embedding_fwd(self, table, ids, t, out=None):
         N, T = ids.shape
         D = table.shape[1]
-        out = self._empty((N, D), torch.float32)
+        out = self._dst(out, (N, D))
         check(self.lib.fgc_embedding_fwd(self._f32(table), self._p(ids), N, T, t, D, self._p(out), self._s()), "embedding_fwd")
         return out
 
@@ -349,12 +355,12 @@ class CudaOps(OpsBase):
         D = dtable.shape[1]
         check(self.lib.fgc_embedding_bwd(self._f32(g), self._p(ids), N, T, t, D, self._f32(dtable), self._s()), "embedding_bwd")
 
-    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P):
+    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None):
         R, D = c_prev.shape
         N, T = ids.shape
         assert R == N * P
         c = self._empty((R, D), torch.float32)
-        h = self._empty((R, D), torch.float32)
+        h = self._dst(out_h, (R, D))
         pre = self._empty((R, 4 * D), torch.float32)
         check(self.lib.fgc_lstm_cell_fwd(self._f32(gates), None if gates2 is None else self._f32(gates2),
                                          None if grow is None else self._f32(grow), self._f32(c_prev), self._f32(h_prev),
@@ -362,19 +368,19 @@ class CudaOps(OpsBase):
               "lstm_cell_fwd")
         return c, h, pre
 
-    def lstm_cell_bwd(self, gc, gh, pre, c_prev, c, ids, t, P):
+    def lstm_cell_bwd(self, gc, gh, pre, c_prev, c, ids, t, P, out_gpre=None):
         R, D = c_prev.shape
         N, T = ids.shape
-        g_pre = self._empty((R, 4 * D), torch.float32)
+        g_pre = self._dst(out_gpre, (R, 4 * D))
         g_c_prev = self._empty((R, D), torch.float32)
         g_h_pass = self._empty((R, D), torch.float32)
         check(self.lib.fgc_lstm_cell_bwd(self._f32(gc), self._f32(gh), self._f32(pre), self._f32(c_prev), self._p(ids), T, t, N, P,
                                          D, self._p(g_pre), self._p(g_c_prev), self._p(g_h_pass), self._s()), "lstm_cell_bwd")
         return g_pre, g_c_prev, g_h_pass
 
-    def rows_group_sum(self, x, P):
+    def rows_group_sum(self, x, P, out=None):
         R, Cc = x.shape
-        out = self._empty((R // P, Cc), torch.float32)
+        out = self._dst(out, (R // P, Cc))
         check(self.lib.fgc_rows_group_sum(self._f32(x), R // P, P, Cc, self._p(out), self._s()), "rows_group_sum")
         return out
 

@@ -145,33 +145,35 @@ class OpsBase:
         raise NotImplementedError
 
     # ---------------- text fusion (models_collection.encode_feat_with_text, :150-248) ----------------
-    def l2norm_rows_fwd(self, x):
-        """rows [R,D] fp32: (x * rsqrt(max(sum x^2,1e-12)), inv[R])"""
+    def l2norm_rows_fwd(self, x, out=None):
+        """rows [R,D] fp32: (x * rsqrt(max(sum x^2,1e-12)), inv[R]).  `out`: optional destination of the normalised rows
+        (a slot of a per-time-step stack, so that the weight gradients can run once over all steps)."""
         raise NotImplementedError
 
     def l2norm_rows_bwd(self, gy, y, inv):
         raise NotImplementedError
 
-    def embedding_fwd(self, table, ids, t):
-        """table[ids[:, t]] -> [N,D];  ids int32 [N,T] on the device"""
+    def embedding_fwd(self, table, ids, t, out=None):
+        """table[ids[:, t]] -> [N,D];  ids int32 [N,T] on the device; `out`: optional destination"""
         raise NotImplementedError
 
     def embedding_bwd(self, g, ids, t, dtable):
         """dtable[ids[n,t]] += g[n]"""
         raise NotImplementedError
 
-    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P):
+    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None):
         """BasicLSTMCell pointwise part.  pre = gates [+ gates2] [+ grow[r // P]]  ([R,4D], order i,j,f,o);
         c = c_prev*sig(f+1) + sig(i)*tanh(j); h = tanh(c)*sig(o); rows whose sample token ids[r//P, t] == 0 (<pad>) keep
-        (c_prev, h_prev).  Returns (c, h, pre)."""
+        (c_prev, h_prev).  Returns (c, h, pre); `out_h`: optional destination of h."""
         raise NotImplementedError
 
-    def lstm_cell_bwd(self, gc, gh, pre, c_prev, c, ids, t, P):
-        """returns (g_pre [R,4D], g_c_prev [R,D], g_h_pass [R,D]) where g_h_pass = gh on masked rows else 0."""
+    def lstm_cell_bwd(self, gc, gh, pre, c_prev, c, ids, t, P, out_gpre=None):
+        """returns (g_pre [R,4D], g_c_prev [R,D], g_h_pass [R,D]) where g_h_pass = gh on masked rows else 0;
+        `out_gpre`: optional destination of g_pre."""
         raise NotImplementedError
 
-    def rows_group_sum(self, x, P):
-        """[N*P, C] -> [N, C] sum over each group of P consecutive rows"""
+    def rows_group_sum(self, x, P, out=None):
+        """[N*P, C] -> [N, C] sum over each group of P consecutive rows; `out`: optional destination"""
         raise NotImplementedError
 
     def atanh_relu_fwd(self, h):

@@ -10,8 +10,11 @@ mLSTM input product is hoisted (SURVEY 7.2 "mLSTM algebra"):
         + tile([e, l2n(h_w)] @ K_a[D:3D])     (one [N,2D]x[2D,4D] product per step, broadcast over positions)
         + h_a @ K_a[3D:4D]                    (the only per-step [N*P, D] x [D, 4D] product)
 
-All state is fp32 (LSTM state, gates, l2-norms); matrices are multiplied by the conv kernels with k=1.
-BPTT is written out by hand.
+All state is fp32 (LSTM state, gates, l2-norms); matrices are multiplied by the conv kernels with k=1 (per-sample
+[N, .] products run on the skinny-product kernel of conv_small.cu).  BPTT is written out by hand.  The per-step operands
+of the weight gradients (embeddings, l2n(h_w), h_w, h_a and the gate gradients) are written into per-time-step stacks, so
+each LSTM kernel gets ONE weight-gradient product over all steps instead of one per step, and the gradient to the
+embedding rows -- which is not part of the recurrence -- is computed once at the end.
 """
 from __future__ import annotations
 
@@ -52,31 +55,42 @@ def text_fusion_fwd(ops, store, e4, ids_host, save=True):
     # [N,T] int32 on the device; pad mask = (id == 0)
     ids_dev = ids_host.to(torch.int32).contiguous() if on_device else torch.as_tensor(ids_np, device=dev).contiguous()
     f32 = torch.float32
+    # steps at which at least one caption has a real token (all of them when the ids live on the device)
+    ts = [t for t in range(T) if ids_np is None or (ids_np[:, t] != 0).any()]
+    S = len(ts)
 
     e4r = ops.cast(e4, f32).view(R, D)
     vis, inv_v = ops.l2norm_rows_fwd(e4r)                                           # :201-202
     gv = ops.conv_fwd([(_rows(vis), False)], _mat(ka[0:D]), None, out_dtype=f32).view(R, 4 * D)
-    cw = ops.zeros_f32((N, D)); hw = ops.zeros_f32((N, D))                          # :190
-    ca = ops.zeros_f32((R, D)); ha = ops.zeros_f32((R, D))                          # :196,204
+    # stacks over the executed steps: slot j holds the operand of step ts[j]; the h stacks hold the INPUT state of step j
+    # in slot j (slot 0 = the zero initial state, :190,:196,:204) and receive the output state in slot j+1
+    e_all = ops.zeros_f32((max(S, 1), N, D))
+    lang_all = ops.zeros_f32((max(S, 1), N, D))
+    hw_all = ops.zeros_f32((S + 1, N, D))
+    ha_all = ops.zeros_f32((S + 1, R, D))
+    cw = ops.zeros_f32((N, D))
+    ca = ops.zeros_f32((R, D))
     steps = []
-    for t in range(T):
-        if ids_np is not None and not (ids_np[:, t] != 0).any():      # every sample is <pad> here: state passes through
-            continue
-        e_t = ops.embedding_fwd(emb, ids_dev, t)                                         # :182,211
+    for j, t in enumerate(ts):
+        hw, ha = hw_all[j], ha_all[j]
+        e_t = ops.embedding_fwd(emb, ids_dev, t, out=e_all[j])                           # :182,211
         gw = ops.conv_fwd([(_rows(e_t), False), (_rows(hw), False)], _mat(kw), bw, out_dtype=f32).view(N, 4 * D)
-        cw2, hw2, pre_w = ops.lstm_cell_fwd(gw, None, None, cw, hw, ids_dev, t, 1)        # :212-213
-        lang, inv_l = ops.l2norm_rows_fwd(hw2)                                      # :215-216
+        cw2, hw2, pre_w = ops.lstm_cell_fwd(gw, None, None, cw, hw, ids_dev, t, 1, out_h=hw_all[j + 1])    # :212-213
+        lang, inv_l = ops.l2norm_rows_fwd(hw2, out=lang_all[j])                     # :215-216
         r_t = ops.conv_fwd([(_rows(e_t), False), (_rows(lang), False)], _mat(ka[D:3 * D]), None,
                            out_dtype=f32).view(N, 4 * D)
         ga = ops.conv_fwd([(_rows(ha), False)], _mat(ka[3 * D:4 * D]), ba, out_dtype=f32).view(R, 4 * D)
-        ca2, ha2, pre_a = ops.lstm_cell_fwd(ga, gv, r_t, ca, ha, ids_dev, t, P)           # :225-226
+        ca2, ha2, pre_a = ops.lstm_cell_fwd(ga, gv, r_t, ca, ha, ids_dev, t, P, out_h=ha_all[j + 1])       # :225-226
         if save:
-            steps.append(dict(t=t, e=e_t, cw_prev=cw, hw_prev=hw, cw=cw2, hw=hw2, pre_w=pre_w,
-                              lang=lang, inv_l=inv_l, ca_prev=ca, ha_prev=ha, ca=ca2, pre_a=pre_a))
-        cw, hw, ca, ha = cw2, hw2, ca2, ha2
+            steps.append(dict(t=t, cw_prev=cw, cw=cw2, pre_w=pre_w, inv_l=inv_l, ca_prev=ca, ca=ca2, pre_a=pre_a))
+        cw, ca = cw2, ca2
+    ha = ha_all[S]
     out = ops.atanh_relu_fwd(ha)                                                    # :239-241
     out = ops.cast(out.view(N, hh, ww, D), e4.dtype)
-    ctx = dict(steps=steps, ids=ids_dev, vis=vis, inv_v=inv_v, ha=ha, shape=(N, hh, ww, D), in_dtype=e4.dtype) if save else None
+    ctx = None
+    if save:
+        ctx = dict(steps=steps, ids=ids_dev, vis=vis, inv_v=inv_v, ha=ha, shape=(N, hh, ww, D), in_dtype=e4.dtype,
+                   e_all=e_all, lang_all=lang_all, hw_all=hw_all, ha_all=ha_all)
     return out, ctx
 
 
@@ -88,41 +102,48 @@ def text_fusion_bwd(ops, store, g_out, ctx):
     f32 = torch.float32
     kw, ka = store.p[_KW], store.p[_KA]
     dkw, dbw, dka, dba, demb = store.g[_KW], store.g[_BW], store.g[_KA], store.g[_BA], store.g[_EMB]
+    steps = ctx["steps"]
+    S = len(steps)
+    if S == 0:                # all-pad batch: output is relu(0) = 0, no gradient reaches e4
+        return ops.cast(ops.zeros_f32((N, hh, ww, D)), ctx["in_dtype"])
+    e_all, lang_all, hw_all, ha_all = ctx["e_all"], ctx["lang_all"], ctx["hw_all"], ctx["ha_all"]
+    ids = ctx["ids"]
 
     g_ha = ops.atanh_relu_bwd(ops.cast(g_out, f32).view(R, D), ctx["ha"])
     g_ca = ops.zeros_f32((R, D))
     g_hw = ops.zeros_f32((N, D))
     g_cw = ops.zeros_f32((N, D))
-    g_gv = None
-    ids = ctx["ids"]
-    for s in reversed(ctx["steps"]):
+    g_gv = ops.zeros_f32((R, 4 * D))
+    gpa_all = ops.zeros_f32((S, R, 4 * D))       # gate gradients of every step, operands of the batched weight gradients
+    gr_all = ops.zeros_f32((S, N, 4 * D))
+    gpw_all = ops.zeros_f32((S, N, 4 * D))
+    for j in range(S - 1, -1, -1):
+        s = steps[j]
         t = s["t"]
         # ---- mLSTM cell
-        g_pre_a, g_ca, g_ha_pass = ops.lstm_cell_bwd(g_ca, g_ha, s["pre_a"], s["ca_prev"], s["ca"], ids, t, P)
-        gpa4 = _rows(g_pre_a)
-        ops.conv_wgrad([(_rows(s["ha_prev"]), False)], gpa4, _mat(dka[3 * D:4 * D]), dba)
-        g_ha = ops.conv_dgrad(gpa4, _mat(ka[3 * D:4 * D]), 0, D, out_dtype=f32).view(R, D)
+        g_pre_a, g_ca, g_ha_pass = ops.lstm_cell_bwd(g_ca, g_ha, s["pre_a"], s["ca_prev"], s["ca"], ids, t, P, out_gpre=gpa_all[j])
+        g_ha = ops.conv_dgrad(_rows(g_pre_a), _mat(ka[3 * D:4 * D]), 0, D, out_dtype=f32).view(R, D)
         ops.add_(g_ha, g_ha_pass)
-        if g_gv is None:
-            g_gv = g_pre_a
-        else:
-            ops.add_(g_gv, g_pre_a)
-        g_r = ops.rows_group_sum(g_pre_a, P)                                         # [N,4D]
-        gr4 = _rows(g_r)
-        ops.conv_wgrad([(_rows(s["e"]), False), (_rows(s["lang"]), False)], gr4, _mat(dka[D:3 * D]), None)
-        g_e = ops.conv_dgrad(gr4, _mat(ka[D:3 * D]), 0, D, out_dtype=f32).view(N, D)
-        g_lang = ops.conv_dgrad(gr4, _mat(ka[D:3 * D]), D, D, out_dtype=f32).view(N, D)
-        ops.add_(g_hw, ops.l2norm_rows_bwd(g_lang, s["lang"], s["inv_l"]))
+        ops.add_(g_gv, g_pre_a)
+        g_r = ops.rows_group_sum(g_pre_a, P, out=gr_all[j])                          # [N,4D]
+        g_lang = ops.conv_dgrad(_rows(g_r), _mat(ka[D:3 * D]), D, D, out_dtype=f32).view(N, D)
+        ops.add_(g_hw, ops.l2norm_rows_bwd(g_lang, lang_all[j], s["inv_l"]))
         # ---- word LSTM cell
-        g_pre_w, g_cw, g_hw_pass = ops.lstm_cell_bwd(g_cw, g_hw, s["pre_w"], s["cw_prev"], s["cw"], ids, t, 1)
-        gpw4 = _rows(g_pre_w)
-        ops.conv_wgrad([(_rows(s["e"]), False), (_rows(s["hw_prev"]), False)], gpw4, _mat(dkw), dbw)
-        ops.add_(g_e, ops.conv_dgrad(gpw4, _mat(kw), 0, D, out_dtype=f32).view(N, D))
-        g_hw = ops.conv_dgrad(gpw4, _mat(kw), D, D, out_dtype=f32).view(N, D)
+        g_pre_w, g_cw, g_hw_pass = ops.lstm_cell_bwd(g_cw, g_hw, s["pre_w"], s["cw_prev"], s["cw"], ids, t, 1, out_gpre=gpw_all[j])
+        g_hw = ops.conv_dgrad(_rows(g_pre_w), _mat(kw), D, D, out_dtype=f32).view(N, D)
         ops.add_(g_hw, g_hw_pass)
-        ops.embedding_bwd(g_e, ids, t, demb)
-    if g_gv is None:          # all-pad batch: output is relu(0) = 0, no gradient reaches e4
-        return ops.cast(ops.zeros_f32((N, hh, ww, D)), ctx["in_dtype"])
+    # ---- weight gradients: one product per kernel block over all steps (rows = step x sample [x position])
+    gpa, gr, gpw = gpa_all.view(S * R, 4 * D), gr_all.view(S * N, 4 * D), gpw_all.view(S * N, 4 * D)
+    e_rows, lang_rows = e_all[:S].view(S * N, D), lang_all[:S].view(S * N, D)
+    ops.conv_wgrad([(_rows(ha_all[:S].view(S * R, D)), False)], _rows(gpa), _mat(dka[3 * D:4 * D]), dba)
+    ops.conv_wgrad([(_rows(e_rows), False), (_rows(lang_rows), False)], _rows(gr), _mat(dka[D:3 * D]), None)
+    ops.conv_wgrad([(_rows(e_rows), False), (_rows(hw_all[:S].view(S * N, D)), False)], _rows(gpw), _mat(dkw), dbw)
+    # ---- embedding rows: d/d(e_t) through both LSTMs, all steps at once, then one scatter-add per step
+    g_e = ops.conv_dgrad(_rows(gr), _mat(ka[D:3 * D]), 0, D, out_dtype=f32)
+    ops.conv_dgrad(_rows(gpw), _mat(kw), 0, D, out=g_e, acc=True)
+    g_e = g_e.view(S, N, D)
+    for j in range(S):
+        ops.embedding_bwd(g_e[j], ids, steps[j]["t"], demb)
     ops.conv_wgrad([(_rows(ctx["vis"]), False)], _rows(g_gv), _mat(dka[0:D]), None)
     g_vis = ops.conv_dgrad(_rows(g_gv), _mat(ka[0:D]), 0, D, out_dtype=f32).view(R, D)
     g_e4 = ops.l2norm_rows_bwd(g_vis, ctx["vis"], ctx["inv_v"])

@@ -61,6 +61,7 @@ CONV_CASES = [
     (70, 1, 1, [(256, False)], 1, 1, 200, ACT_MIU),             # fully connected rows
     (5, 1, 1, [(512, False), (512, False)], 1, 1, 2048, ACT_NONE),   # LSTM gates
     (2, 6, 6, [(96, False)], 3, 1, 1, ACT_NONE),                # patch logits (Cout 1), partial K slab
+    (64, 1, 1, [(100, False), (37, False)], 1, 1, 77, ACT_LRELU),   # skinny-product kernel: two sources, ragged K and N
     # halo-reuse kernel (bf16, stride 1, wide sources through tensor-map TMA)
     (8, 64, 80, [(64, False)], 3, 1, 128, ACT_LRELU),           # two sub-tiles per CTA (32 x 8 pixel tiles)
     (2, 28, 24, [(128, False), (3, False)], 3, 1, 64, ACT_NONE),    # wide + sketch source, ragged tile rows (28 = 16 + 12)
@@ -119,6 +120,8 @@ DGRAD_CASES = [
     (2, 20, 20, 11, 8, 3, 3, 8, False, True),           # direct narrow kernel: 8-channel gy -> image slice, accumulating
     (2, 20, 20, 3, 0, 3, 7, 8, False, False),           # direct narrow kernel: stem 7x7, mirrored taps
     (2, 20, 20, 11, 0, 8, 3, 8, False, False),          # direct narrow kernel: 8 -> 8
+    (48, 1, 1, 1024, 512, 512, 1, 2048, False, False),  # skinny-product kernel (<= 64 rows): LSTM kernel slice, float4 weights
+    (33, 1, 1, 200, 7, 90, 1, 130, False, True),        # skinny-product kernel: ragged K / N, unaligned slice, accumulating
 ]
 
 

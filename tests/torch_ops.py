@@ -231,21 +231,28 @@ class TorchOps(OpsBase):
         return x.to(dtype)
 
     # ---- text fusion
-    def l2norm_rows_fwd(self, x):
+    @staticmethod
+    def _into(out, val):
+        if out is None:
+            return val
+        out.copy_(val)
+        return out
+
+    def l2norm_rows_fwd(self, x, out=None):
         inv = torch.rsqrt(torch.clamp((x * x).sum(1), min=1e-12))
-        return x * inv[:, None], inv
+        return self._into(out, x * inv[:, None]), inv
 
     def l2norm_rows_bwd(self, gy, y, inv):
         # y = x*inv (inv treated as a function of x unless clamped; clamp never active on real data)
         return (gy - y * (gy * y).sum(1, keepdim=True)) * inv[:, None]
 
-    def embedding_fwd(self, table, ids, t):
-        return table[ids[:, t].long()].to(self.cdt)
+    def embedding_fwd(self, table, ids, t, out=None):
+        return self._into(out, table[ids[:, t].long()].to(self.cdt))
 
     def embedding_bwd(self, g, ids, t, dtable):
         dtable.index_add_(0, ids[:, t].long(), g.to(dtable.dtype))
 
-    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P):
+    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None):
         pre = gates.clone()
         if gates2 is not None:
             pre = pre + gates2
@@ -255,9 +262,9 @@ class TorchOps(OpsBase):
         c = c_prev * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j)
         h = torch.tanh(c) * torch.sigmoid(o)
         m = (ids[:, t] != 0).repeat_interleave(P)[:, None]
-        return torch.where(m, c, c_prev), torch.where(m, h, h_prev), pre
+        return torch.where(m, c, c_prev), self._into(out_h, torch.where(m, h, h_prev)), pre
 
-    def lstm_cell_bwd(self, gc, gh, pre, c_prev, c, ids, t, P):
+    def lstm_cell_bwd(self, gc, gh, pre, c_prev, c, ids, t, P, out_gpre=None):
         m = (ids[:, t] != 0).repeat_interleave(P)[:, None]
         i, j, f, o = pre.chunk(4, dim=1)
         si, sf, so, tj = torch.sigmoid(i), torch.sigmoid(f + 1.0), torch.sigmoid(o), torch.tanh(j)
@@ -270,10 +277,11 @@ class TorchOps(OpsBase):
         g_j = g_cn * si * (1 - tj * tj)
         g_pre = torch.cat([g_i, g_j, g_f, g_o], 1)
         z = torch.zeros_like(gc)
-        return torch.where(m, g_pre, torch.zeros_like(g_pre)), torch.where(m, g_cn * sf, gc), torch.where(m, z, gh)
+        return (self._into(out_gpre, torch.where(m, g_pre, torch.zeros_like(g_pre))), torch.where(m, g_cn * sf, gc),
+                torch.where(m, z, gh))
 
-    def rows_group_sum(self, x, P):
-        return x.view(-1, P, x.shape[1]).sum(1)
+    def rows_group_sum(self, x, P, out=None):
+        return self._into(out, x.view(-1, P, x.shape[1]).sum(1))
 
     def atanh_relu_fwd(self, h):
         return torch.relu(0.5 * (torch.log(1.001 + h) - torch.log(1.001 - h)))
