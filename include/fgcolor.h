@@ -44,12 +44,12 @@ typedef struct {
   const void* ptr;   /* NHWC [N, H/(ups?2:1), W/(ups?2:1), C] */
   int C;
   int ups;           /* 1: read through nearest-neighbour x2 upsample */
-  const void* patch; /* optional (NULL = none), narrow sources only: bf16 [N,H,W,64*ceil(k*k*C/64)] written by
+  const void* patch; /* optional (NULL = none), narrow sources only: bf16 [N,H,W,8*ceil(k*k*C/8)] written by
                       * fgc_im2col_small for this conv's k -- lets the TMA-fed kernels fetch the source's flattened
                       * (tap, channel) slabs as ordinary 64-channel blocks instead of gathering them element-wise */
 } fgc_src;
 /* out[n,h,w,q] = x[n, h+kh-pad, w+kw-pad, c] for q = (kh*k+kw)*C + c < k*k*C, else 0 (stride 1, SAME); out is bf16 with
- * 64*ceil(k*k*C/64) channels.  ups = 1 reads x through the x2 nearest-neighbour upsample. */
+ * 8*ceil(k*k*C/8) channels (the TMA boxes of the consumers are 64 channels wide; the rest is out-of-bounds zero fill).  ups = 1 reads x through the x2 nearest-neighbour upsample. */
 int fgc_im2col_small(const void* x, int dtype, int N, int H, int W, int C, int ups, int k, void* out, fgc_stream stream);
 
 /* Bytes of device workspace `ws` a forward (n_out = Cout, sources = the conv inputs) or input-gradient

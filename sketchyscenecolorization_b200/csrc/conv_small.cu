@@ -463,7 +463,7 @@ extern "C" int fgc_im2col_small(const void* x, int dtype, int N, int H, int W, i
   FGC_REQUIRE(k % 2 == 1 && C > 0 && N > 0, "im2col_small: bad arguments");
   FGC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "im2col_small: out must be 16-byte aligned");
   if (ups) FGC_REQUIRE(H % 2 == 0 && W % 2 == 0, "im2col_small: upsampled source needs even H, W");
-  const int CP = 64 * ((k * k * C + 63) / 64);
+  const int CP = 8 * ((k * k * C + 7) / 8);
   const long long nchunks = (long long)N * H * W * (CP / 8);
   cudaStream_t s = as_stream(stream);
   if (dtype == FGC_F32)

@@ -1614,7 +1614,7 @@ static int launch_halo(HaloArgs& h, cudaStream_t s) {
     if (h.g.big[i]) {
       if (!make_tmap_nhwc(&h.tm[i], h.g.src[i], h.g.C[i], h.g.W, h.g.H, h.g.N, 8, h.box_rows)) return -1;
     } else if (h.g.patch[i]) {
-      const int cp = 64 * (h.g.slab_begin[i + 1] - h.g.slab_begin[i]);
+      const int cp = ((h.g.k * h.g.k * h.g.C[i] + 7) / 8) * 8;     // channels past cp: out-of-bounds zero fill
       if (!make_tmap_nhwc(&h.tm[i], h.g.patch[i], cp, h.g.W, h.g.H, h.g.N, 8, h.box_rows)) return -1;
     }
   }
@@ -1728,7 +1728,7 @@ static void wgrad_setup_tiled(WgradArgs& a, int x3) {
   for (int s = 0; s < g.nsrc; s++) {
     if (!g.big[s]) {
       if (!g.patch[s] || (reinterpret_cast<uintptr_t>(g.patch[s]) & 15)) continue;
-      const int cp = 64 * (g.slab_begin[s + 1] - g.slab_begin[s]);
+      const int cp = ((g.k * g.k * g.C[s] + 7) / 8) * 8;           // channels past cp: out-of-bounds zero fill
       if (!make_tmap_nhwc(&a.tm_src[s], g.patch[s], cp, g.W, g.H, g.N, tw, th)) return;
       a.tma_mask |= 1 << s;
       any = true;

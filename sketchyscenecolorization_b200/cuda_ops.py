@@ -104,7 +104,7 @@ class CudaOps(OpsBase):
         H, W = (2 * h, 2 * w) if ups else (h, w)
         if x.dtype != torch.bfloat16 or Cc >= 64 or k < 3 or W % 8 != 0:
             return None
-        cp = 64 * ((k * k * Cc + 63) // 64)
+        cp = 8 * ((k * k * Cc + 7) // 8)
         out = self._empty((N, H, W, cp), torch.bfloat16)
         check(self.lib.fgc_im2col_small(self._p(x), self._dt(x), N, H, W, Cc, 1 if ups else 0, k, self._p(out), self._s()),
               "im2col_small")
