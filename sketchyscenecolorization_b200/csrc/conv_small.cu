@@ -347,8 +347,11 @@ __global__ void __launch_bounds__(256) conv_rows_kernel(const __grid_constant__ 
 }
 
 static int rows_mode() {
-  static int mode = -1;        // FGC_ROWS=0 sends the skinny products through the tensor-core path as well
-  if (mode < 0) { const char* e = getenv("FGC_ROWS"); mode = e ? atoi(e) : 1; }
+  // Measured on B200 (profiles/r1d): 166 us per [64,1024]x[1024,2048] call against 60 us on the tensor-core path -- one
+  // column per thread leaves the kernel bound by shared-memory return bandwidth (one LDS.128 per 4 FMAs).  Kept behind
+  // FGC_ROWS=1 as the starting point for a register-tiled version; the default routing does not use it.
+  static int mode = -1;
+  if (mode < 0) { const char* e = getenv("FGC_ROWS"); mode = e ? atoi(e) : 0; }
   return mode;
 }
 
