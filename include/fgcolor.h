@@ -63,8 +63,9 @@ int fgc_set_conv_impl(int impl);
  * direct kernels.  A negative value leaves that switch unchanged. */
 int fgc_set_conv_flags(int halo, int small);
 /* launches so far per convolution kernel family: out[0] halo-reuse fwd/dgrad, out[1] per-tap gather fwd/dgrad,
- * out[2] direct narrow fwd/dgrad, out[3] direct narrow wgrad, out[4] tensor-core wgrad (tests assert the routing) */
-int fgc_debug_conv_counts(long long out[5]);
+ * out[2] direct narrow fwd/dgrad, out[3] direct narrow wgrad, out[4] per-tap tensor-core wgrad, out[5] halo-reuse wgrad
+ * (tests assert the routing) */
+int fgc_debug_conv_counts(long long out[6]);
 /* debug aid: per-role event trace (role, event, tile, clock64) of CTA 0 of the implicit-GEMM kernel; buf holds
  * 4 + 4*capacity int64 on the device, buf[0] is the event count.  NULL disables. */
 int fgc_debug_set_trace(long long* buf, int capacity);

@@ -18,7 +18,7 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
 int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s);
 size_t conv_ws_bytes(const ConvGeom& g, int nout, int x3);
 extern int g_halo_mode, g_small_mode;
-extern long long g_conv_counts[5];
+extern long long g_conv_counts[6];
 extern long long* g_trace;
 extern int g_trace_cap;
 
@@ -67,8 +67,8 @@ int fgc_set_conv_flags(int halo, int small) {
   return FGC_OK;
 }
 
-int fgc_debug_conv_counts(long long out[5]) {
-  for (int i = 0; i < 5; i++) out[i] = g_conv_counts[i];
+int fgc_debug_conv_counts(long long out[6]) {
+  for (int i = 0; i < 6; i++) out[i] = g_conv_counts[i];
   return FGC_OK;
 }
 

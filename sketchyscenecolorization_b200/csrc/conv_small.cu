@@ -14,7 +14,7 @@
 
 namespace fgc {
 int num_sms();
-extern long long g_conv_counts[5];
+extern long long g_conv_counts[6];
 
 constexpr int kTS = 16;        // output tile edge
 

@@ -31,7 +31,7 @@
 
 namespace fgc {
 int num_sms();
-long long g_conv_counts[5] = {0, 0, 0, 0, 0};   // launches per kernel family (fgc_debug_conv_counts)
+long long g_conv_counts[6] = {0, 0, 0, 0, 0, 0};   // launches per kernel family (fgc_debug_conv_counts)
 
 // ------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -1427,6 +1427,191 @@ __global__ void __launch_bounds__(320, 1) conv_wgrad_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------------
+// weight gradient with halo reuse (conv_wgrad_halo_kernel): stride-1 SAME layers, bf16, every operand block by tensor TMA
+//
+// conv_wgrad_kernel fetches one 64-pixel x 64-channel block of x per (tap, channel group): 9 shifted copies of x for a
+// 3x3 layer, and at Cout = 64..128 the L2 -> shared-memory traffic (83-146 B per tensor-pipe cycle and SM) bounds it
+// (measured 225-640 TFLOP/s).  Here a K slab is an 8 x 8 pixel tile of one image and the rows of dW are visited in the
+// order (source, channel group, kw, kh): ONE box of (8 + k - 1) rows x 8 pixels x 64 channels serves the k filter rows
+// of a column -- a box row is one 1024-byte swizzle atom, so the operand of filter row kh starts kh atoms into the box.
+// The two 64-row halves of a 128-row MMA operand may sit in different boxes: the descriptor's leading-dimension offset
+// is simply the distance between them.  Narrow sources come as patch tensors (one 8-row box per slab).
+//   warp 0: TMA issuer   warp 1: MMA issuer (+ TMEM)   all 4 warps: red.add epilogue after the reduction
+// ------------------------------------------------------------------------------------------------------
+constexpr int kMaxVS = 192;          // slabs (64 rows of dW) per layer the kernel accepts
+struct WgradHaloArgs {
+  ConvGeom g;
+  int Cout;
+  float* dw;                 // HWIO fp32, accumulated with red.add
+  long long dw_tap, dw_c;    // dW(tap, c, n) at dw + tap*dw_tap + c*dw_c + n
+  int nvs;                   // slabs of the layer
+  int kslabs, kslabs_per_cta;
+  int tiles_w, tiles_per_img;
+  int stages, a_stage_bytes;
+  uint16_t vslab[kMaxVS];    // visiting order -> slab index (conv_geom.cuh numbering)
+  CUtensorMap tm_src[kMaxSrc];
+  CUtensorMap tm_gy;
+};
+
+template <int BN, int G>
+__global__ void __launch_bounds__(128, 1) conv_wgrad_halo_kernel(const __grid_constant__ WgradHaloArgs a) {
+  constexpr int NBB = (BN + 63) / 64;
+  constexpr int BLK = 64 * 128;
+  constexpr int B_BYTES = NBB * BLK;
+  constexpr int TMEM_COLS = G * BN <= 32 ? 32 : (G * BN <= 64 ? 64 : (G * BN <= 128 ? 128 : (G * BN <= 256 ? 256 : 512)));
+  static_assert(G * BN <= 512, "accumulators exceed TMEM");
+  constexpr uint32_t IDESC = make_idesc(128, BN, 1, 1);
+  constexpr int NQ = 2 * G;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stages = a.stages;
+  const int stage_bytes = a.a_stage_bytes + B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);     // full[stages], empty[stages], done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 1);
+  __shared__ int s_off[NQ];          // byte offset of slab q's operand inside the A region of a stage
+  __shared__ int s_box[NQ][6];       // per box: source, first channel, w shift, h shift, rows, byte offset
+  __shared__ int s_nbox;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const ConvGeom& g = a.g;
+  const int k = g.k;
+  const int n0 = blockIdx.y * BN;
+  const int ks0 = blockIdx.z * a.kslabs_per_cta;
+  const int ks1 = min(ks0 + a.kslabs_per_cta, a.kslabs);
+  const int niter = ks1 - ks0;
+
+  // this CTA's slabs and the boxes that hold them
+  SlabInfo si[NQ];
+  bool have[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int v = NQ * blockIdx.x + q;
+    have[q] = v < a.nvs;
+    si[q] = decode_slab(g, have[q] ? (int)a.vslab[v] : 0);
+  }
+  if (tid == 0) {
+    int nbox = 0, off = 0, prev_key = -1;
+    for (int q = 0; q < NQ; q++) {
+      if (!have[q]) { s_off[q] = q > 0 ? s_off[q - 1] + 1024 : 0; continue; }
+      const SlabInfo& sq = si[q];
+      const int kh = sq.big ? sq.tap / k : 0, kw = sq.big ? sq.tap % k : 0;
+      const int key = sq.big ? ((sq.s << 20) | ((sq.c0 >> 6) << 8) | kw) : ((1 << 24) | (sq.s << 20) | (sq.q0 >> 6));
+      if (key != prev_key) {
+        const int rows = sq.big ? 8 + k - 1 : 8;
+        s_box[nbox][0] = sq.s;
+        s_box[nbox][1] = sq.big ? sq.c0 : sq.q0;
+        s_box[nbox][2] = sq.big ? kw - g.pad_l : 0;
+        s_box[nbox][3] = sq.big ? -g.pad_t : 0;
+        s_box[nbox][4] = rows;
+        s_box[nbox][5] = off;
+        off += rows * 1024;
+        nbox++;
+        prev_key = key;
+      }
+      s_off[q] = s_box[nbox - 1][5] + kh * 1024;
+    }
+    s_nbox = nbox;
+    for (int s2 = 0; s2 < stages; s2++) {
+      mbar_init(smem_u32(&bars[s2]), 1);
+      mbar_init(smem_u32(&bars[stages + s2]), 1);
+    }
+    mbar_init(smem_u32(&bars[2 * stages]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA issuer =====================
+    if (lane == 0 && niter > 0) {
+      const int nbox = s_nbox;
+      uint32_t tx = (uint32_t)B_BYTES;
+      for (int b = 0; b < nbox; b++) tx += (uint32_t)s_box[b][4] * 1024u;
+      for (int s2 = 0; s2 < g.nsrc; s2++) tma_prefetch_desc(&a.tm_src[s2]);
+      tma_prefetch_desc(&a.tm_gy);
+      for (int it = 0; it < niter; it++) {
+        const int st = it % stages;
+        mbar_wait(smem_u32(&bars[stages + st]), ((it / stages) & 1) ^ 1);
+        const int ks = ks0 + it;
+        const int n = ks / a.tiles_per_img, rr = ks - n * a.tiles_per_img;
+        const int ty = rr / a.tiles_w, tx_ = rr - ty * a.tiles_w;
+        const int h0 = ty * 8, w0 = tx_ * 8;
+        const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t sb = sa + a.a_stage_bytes;
+        const uint32_t bar = smem_u32(&bars[st]);
+        mbar_arrive_expect_tx(bar, tx);
+        for (int b = 0; b < nbox; b++)
+          tma_load_4d(sa + s_box[b][5], &a.tm_src[s_box[b][0]], s_box[b][1], w0 + s_box[b][2], h0 + s_box[b][3], n, bar);
+#pragma unroll
+        for (int b = 0; b < NBB; b++) tma_load_4d(sb + b * BLK, &a.tm_gy, n0 + b * 64, w0, h0, n, bar);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    for (int it = 0; it < niter; it++) {
+      const int st = it % stages;
+      mbar_wait(smem_u32(&bars[st]), (it / stages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t sb = sa + a.a_stage_bytes;
+#pragma unroll
+        for (int b = 0; b < G; b++) {
+          if (!have[2 * b]) continue;
+          const uint32_t lo = (uint32_t)s_off[2 * b];
+          const uint32_t lbo = (uint32_t)(s_off[2 * b + 1] - s_off[2 * b]);     // second 64-row half: possibly in another box
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) {      // 16 pixels per MMA = 2 atoms of 1024 B
+            const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+            const uint64_t da = desc_mnmajor(sa + lo + kk * 2048, lbo, 1024);
+            const uint64_t db = desc_mnmajor(sb + kk * 2048, BLK, 1024);
+            umma_bf16(tmem_base + (uint32_t)(b * BN), da, db, IDESC, acc);
+          }
+        }
+        umma_commit(smem_u32(&bars[stages + st]));
+        if (it == niter - 1) umma_commit(smem_u32(&bars[2 * stages]));
+      }
+      __syncwarp();
+    }
+  }
+  // ===================== epilogue: TMEM lane = row of a 128-row dW block, columns = co =====================
+  if (niter > 0) {
+    mbar_wait(smem_u32(&bars[2 * stages]), 0);
+    tc_fence_after();
+    const int quarter = warp & 3;
+    for (int b = 0; b < G; b++) {
+      const int row = quarter * 32 + lane;
+      const int q = 2 * b + (row >> 6), kk = row & 63;
+      int tap = 0, cg = 0;
+      const bool rvalid = have[q] && slab_elem(g, si[q], kk, &tap, &cg);
+      float* dwrow = a.dw + tap * a.dw_tap + cg * a.dw_c;
+      if (!have[2 * b]) continue;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * BN + c0), r);
+        if (!rvalid) continue;
+#pragma unroll
+        for (int e = 0; e < 32; e++) {
+          const int n = n0 + c0 + e;
+          if (n < a.Cout) atomicAdd(dwrow + n, __uint_as_float(r[e]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------
 static int pick_bn(int nout, int x3) {
@@ -1788,6 +1973,99 @@ static int launch_wgrad(WgradArgs& a, cudaStream_t s) {
 struct WgradArgs;
 static int conv_wgrad_run_args(WgradArgs& a, int src_dtype, cudaStream_t s);
 
+// ---- halo-reuse weight gradient launcher; returns -1 when the layer is not eligible ----
+template <int BN, int G>
+static int launch_wgrad_halo(WgradHaloArgs& h, cudaStream_t s) {
+  constexpr int NBB = (BN + 63) / 64;
+  constexpr int B_BYTES = NBB * 64 * 128;
+  constexpr int NQ = 2 * G;
+  const ConvGeom& g = h.g;
+  // shared memory of the busiest CTA: one box per run of slabs that share (source, channel group, kw)
+  int a_bytes = 0;
+  const int groups = (h.nvs + NQ - 1) / NQ;
+  for (int c = 0; c < groups; c++) {
+    int bytes = 0, prev_key = -1;
+    for (int q = 0; q < NQ && c * NQ + q < h.nvs; q++) {
+      SlabInfo sq = decode_slab(g, h.vslab[c * NQ + q]);
+      const int kw = sq.big ? sq.tap % g.k : 0;
+      const int key = sq.big ? ((sq.s << 20) | ((sq.c0 >> 6) << 8) | kw) : ((1 << 24) | (sq.s << 20) | (sq.q0 >> 6));
+      if (key != prev_key) { bytes += (sq.big ? 8 + g.k - 1 : 8) * 1024; prev_key = key; }
+    }
+    if (bytes > a_bytes) a_bytes = bytes;
+  }
+  a_bytes += 2048;                               // slack: absent second halves are addressed one atom further
+  h.a_stage_bytes = a_bytes;
+  const int stage_bytes = a_bytes + B_BYTES;
+  int stages = (208 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return -1;
+  h.stages = stages;
+  size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_wgrad_halo_kernel<BN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_set = true;
+  }
+  const int ntiles = (h.Cout + BN - 1) / BN;
+  h.tiles_w = g.W / 8;
+  h.tiles_per_img = h.tiles_w * (g.H / 8);
+  h.kslabs = g.N * h.tiles_per_img;
+  int splits = (int)((long long)num_sms() / ((long long)groups * ntiles));
+  if (splits < 1) splits = 1;
+  if (splits > h.kslabs) splits = h.kslabs;
+  h.kslabs_per_cta = (h.kslabs + splits - 1) / splits;
+  splits = (h.kslabs + h.kslabs_per_cta - 1) / h.kslabs_per_cta;
+  dim3 grid(groups, ntiles, splits);
+  conv_wgrad_halo_kernel<BN, G><<<grid, 128, smem, s>>>(h);
+  g_conv_counts[5]++;
+  count_launch();
+  return check_launch("conv_wgrad_halo");
+}
+
+int g_wgrad_halo_mode = -1;    // env FGC_WGRAD_HALO (default 1); fgc_set_conv_flags' halo switch covers it too
+
+static int conv_wgrad_halo_try(const WgradArgs& a, int bn, cudaStream_t s) {
+  if (g_wgrad_halo_mode < 0) { const char* e = getenv("FGC_WGRAD_HALO"); g_wgrad_halo_mode = e ? atoi(e) : 1; }
+  if (g_halo_mode < 0) { const char* e = getenv("FGC_HALO"); g_halo_mode = e ? atoi(e) : 1; }
+  if (!g_wgrad_halo_mode || !g_halo_mode) return -1;
+  const ConvGeom& g = a.g;
+  if (!a.fast || a.tap_flip || (g.k & 1) == 0 || g.k < 3 || g.k > 9 || g.pad_t != (g.k - 1) / 2 || g.pad_l != g.pad_t) return -1;
+  if ((g.H & 7) || (g.W & 7)) return -1;
+  if ((a.Cout & 7) || a.Cout < 8 || (reinterpret_cast<uintptr_t>(a.gy) & 15)) return -1;
+  if (a.dw_n != 1 || g.nslabs > kMaxVS) return -1;
+  WgradHaloArgs h;
+  h.g = g;
+  h.Cout = a.Cout;
+  h.dw = a.dw;
+  h.dw_tap = a.dw_tap;
+  h.dw_c = a.dw_c;
+  int nv = 0;
+  for (int i = 0; i < g.nsrc; i++) {
+    if (g.big[i]) {
+      if (g.ups[i] || (reinterpret_cast<uintptr_t>(g.src[i]) & 15)) return -1;
+      const int ncb = (g.C[i] + 63) / 64;
+      for (int cb = 0; cb < ncb; cb++)
+        for (int kw = 0; kw < g.k; kw++)
+          for (int kh = 0; kh < g.k; kh++) h.vslab[nv++] = (uint16_t)(g.slab_begin[i] + (kh * g.k + kw) * ncb + cb);
+      if (!make_tmap_nhwc(&h.tm_src[i], g.src[i], g.C[i], g.W, g.H, g.N, 8, 8 + g.k - 1)) return -1;
+    } else {
+      if (!g.patch[i] || (reinterpret_cast<uintptr_t>(g.patch[i]) & 15)) return -1;
+      for (int sl = g.slab_begin[i]; sl < g.slab_begin[i + 1]; sl++) h.vslab[nv++] = (uint16_t)sl;
+      const int cp = ((g.k * g.k * g.C[i] + 7) / 8) * 8;
+      if (!make_tmap_nhwc(&h.tm_src[i], g.patch[i], cp, g.W, g.H, g.N, 8, 8)) return -1;
+    }
+  }
+  h.nvs = nv;
+  if (!make_tmap_nhwc(&h.tm_gy, a.gy, a.Cout, g.OW, g.OH, g.N, 8, 8)) return -1;
+  switch (bn) {
+    case 16: return launch_wgrad_halo<16, 6>(h, s);
+    case 32: return launch_wgrad_halo<32, 6>(h, s);
+    case 64: return launch_wgrad_halo<64, 6>(h, s);
+    case 256: return launch_wgrad_halo<256, 2>(h, s);
+    default: return launch_wgrad_halo<128, 3>(h, s);
+  }
+}
+
 static int pick_bn_wgrad(int nout, int x3) {
   if (nout <= 16) return 16;
   if (nout <= 32) return 32;
@@ -1841,8 +2119,12 @@ static int conv_wgrad_run_args(WgradArgs& a, int src_dtype, cudaStream_t s) {
   a.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FGC_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   const int x3 = src_dtype == FGC_F32;
-  wgrad_setup_tiled(a, x3);
   int bn = pick_bn_wgrad(Cout, x3);
+  if (!x3) {
+    int r = conv_wgrad_halo_try(a, bn, s);      // stride-1 SAME bf16 layers whose operands are all TMA-able
+    if (r >= 0) return r;
+  }
+  wgrad_setup_tiled(a, x3);
   if (x3) {
     switch (bn) {
       case 16: return launch_wgrad<float, 16, 1>(a, s);

@@ -44,7 +44,7 @@ def _set_impl(cu, impl):
 
 def conv_counts(cu):
     import ctypes
-    arr = (ctypes.c_longlong * 5)()
+    arr = (ctypes.c_longlong * 6)()
     cu.lib.fgc_debug_conv_counts(arr)
     return list(arr)
 
@@ -67,6 +67,9 @@ CONV_CASES = [
     (2, 28, 24, [(128, False), (3, False)], 3, 1, 64, ACT_NONE),    # wide + sketch source, ragged tile rows (28 = 16 + 12)
     (8, 64, 80, [(64, False), (8, False), (3, False)], 3, 1, 256, ACT_NONE),   # 256-wide N tile, two small sources
     (2, 32, 40, [(192, False)], 7, 1, 3, ACT_TANH),             # 7x7 over three channel groups, Cout 3
+    (4, 24, 24, [(256, False)], 3, 1, 256, ACT_NONE),           # halo-reuse wgrad: 256-wide N tile, boxes shared across CTAs
+    (2, 16, 24, [(128, False)], 3, 1, 96, ACT_NONE),            # halo-reuse wgrad: ragged N tile
+    (2, 16, 16, [(64, False)], 5, 1, 64, ACT_NONE),             # 5x5: 12-row boxes
     (3, 30, 22, [(72, False)], 3, 1, 40, ACT_MIU),              # partial channel group (72 = 64 + 8), ragged rows and columns
 ]
 
@@ -401,7 +404,8 @@ def test_conv_routing(env):
     dw, db = torch.zeros_like(w3), torch.zeros_like(b8)
     assert delta(lambda: cub.conv_wgrad([(x3, False)], gy8, dw, db))[3] == 1
     dw2, db2 = torch.zeros_like(w), torch.zeros_like(b)
-    assert delta(lambda: cub.conv_wgrad([(x128, False)], gy, dw2, db2))[4] == 1
+    assert delta(lambda: cub.conv_wgrad([(x128, False)], gy, dw2, db2))[4:6] == [0, 1]    # halo-reuse wgrad
+    assert delta(lambda: cub.conv_wgrad([(xlow, True)], gy, dw2, db2))[4:6] == [1, 0]     # upsampled source: per-tap wgrad
 
 
 @pytest.mark.parametrize("case", [(8, 64, 80, [(64, False), (8, False), (3, False)], 3, 64),
