@@ -22,7 +22,7 @@ echo "=== smoke"; timeout -k 10 300 python __graft_entry__.py --smoke > gpurun_o
 fi
 echo "=== prof_conv"; timeout -k 10 300 python scripts/prof_conv.py > gpurun_out/prof_conv_$T.log 2>&1; cat gpurun_out/prof_conv_$T.log
 echo "=== prof_elem"; timeout -k 10 300 python scripts/prof_elem.py > gpurun_out/prof_elem_$T.log 2>&1; cat gpurun_out/prof_elem_$T.log
-echo "=== op_breakdown"; timeout -k 10 300 python scripts/op_breakdown.py > gpurun_out/op_breakdown_$T.log 2>&1; head -n 70 gpurun_out/op_breakdown_$T.log
+echo "=== op_breakdown"; timeout -k 10 300 python scripts/op_breakdown.py > gpurun_out/op_breakdown_$T.log 2>&1; head -n 60 gpurun_out/op_breakdown_$T.log
 echo "=== bench"; timeout -k 10 900 python bench.py --steps ${STEPS:-5} --warmup 3 > gpurun_out/bench_$T.json 2> gpurun_out/bench_$T.err; tail -c 3000 gpurun_out/bench_$T.json; tail -n 5 gpurun_out/bench_$T.err
 if [ -z "$NO_NCU" ]; then
 echo "=== ncu launches (timed region only: cudaProfilerStart/Stop around it)"

@@ -24,5 +24,5 @@ print("total op time %.1f ms" % tot)
 for k, (n, ms) in sorted(ops.op_times.items(), key=lambda kv: -kv[1][1]):
     print("%-22s %5d calls %9.2f ms %5.1f%%" % (k, n, ms, 100 * ms / tot))
 print("---- convolutions by shape")
-for k, (n, ms) in sorted(ops.op_detail.items(), key=lambda kv: -kv[1][1])[:45]:
+for k, (n, ms) in sorted(ops.op_detail.items(), key=lambda kv: -kv[1][1]):
     print("%7.2f ms %3d x  %s" % (ms, n, k))

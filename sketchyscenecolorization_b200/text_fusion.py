@@ -39,6 +39,13 @@ def _rows(t):
     return t.view(t.shape[0], 1, 1, t.shape[1])
 
 
+def _op(ops, t):
+    """Matrix-product operand in the operator set's activation dtype: in bf16 training mode the LSTM products run as
+    single-pass bf16 tensor-core GEMMs like every convolution (state, gates and accumulation stay fp32); in fp32 mode
+    (inference, parity tests) this is the identity and the products run in the bf16x3 split mode."""
+    return _rows(t if ops.act_dtype != torch.bfloat16 else ops.cast(t, torch.bfloat16))
+
+
 def text_fusion_fwd(ops, store, e4, ids_host, save=True):
     """e4: [N,h,w,D] activation; ids_host: int array [N,T] on the HOST (numpy / CPU tensor), or an int32 DEVICE tensor.
     With host ids, time steps at which every caption is <pad> are skipped outright (the reference's tf.cond, :235);
@@ -61,7 +68,7 @@ def text_fusion_fwd(ops, store, e4, ids_host, save=True):
 
     e4r = ops.cast(e4, f32).view(R, D)
     vis, inv_v = ops.l2norm_rows_fwd(e4r)                                           # :201-202
-    gv = ops.conv_fwd([(_rows(vis), False)], _mat(ka[0:D]), None, out_dtype=f32).view(R, 4 * D)
+    gv = ops.conv_fwd([(_op(ops, vis), False)], _mat(ka[0:D]), None, out_dtype=f32).view(R, 4 * D)
     # stacks over the executed steps: slot j holds the operand of step ts[j]; the h stacks hold the INPUT state of step j
     # in slot j (slot 0 = the zero initial state, :190,:196,:204) and receive the output state in slot j+1
     e_all = ops.zeros_f32((max(S, 1), N, D))
@@ -74,12 +81,13 @@ def text_fusion_fwd(ops, store, e4, ids_host, save=True):
     for j, t in enumerate(ts):
         hw, ha = hw_all[j], ha_all[j]
         e_t = ops.embedding_fwd(emb, ids_dev, t, out=e_all[j])                           # :182,211
-        gw = ops.conv_fwd([(_rows(e_t), False), (_rows(hw), False)], _mat(kw), bw, out_dtype=f32).view(N, 4 * D)
+        e_op = _op(ops, e_t)
+        gw = ops.conv_fwd([(e_op, False), (_op(ops, hw), False)], _mat(kw), bw, out_dtype=f32).view(N, 4 * D)
         cw2, hw2, pre_w = ops.lstm_cell_fwd(gw, None, None, cw, hw, ids_dev, t, 1, out_h=hw_all[j + 1])    # :212-213
         lang, inv_l = ops.l2norm_rows_fwd(hw2, out=lang_all[j])                     # :215-216
-        r_t = ops.conv_fwd([(_rows(e_t), False), (_rows(lang), False)], _mat(ka[D:3 * D]), None,
+        r_t = ops.conv_fwd([(e_op, False), (_op(ops, lang), False)], _mat(ka[D:3 * D]), None,
                            out_dtype=f32).view(N, 4 * D)
-        ga = ops.conv_fwd([(_rows(ha), False)], _mat(ka[3 * D:4 * D]), ba, out_dtype=f32).view(R, 4 * D)
+        ga = ops.conv_fwd([(_op(ops, ha), False)], _mat(ka[3 * D:4 * D]), ba, out_dtype=f32).view(R, 4 * D)
         ca2, ha2, pre_a = ops.lstm_cell_fwd(ga, gv, r_t, ca, ha, ids_dev, t, P, out_h=ha_all[j + 1])       # :225-226
         if save:
             steps.append(dict(t=t, cw_prev=cw, cw=cw2, pre_w=pre_w, inv_l=inv_l, ca_prev=ca, ca=ca2, pre_a=pre_a))
@@ -122,29 +130,30 @@ def text_fusion_bwd(ops, store, g_out, ctx):
         t = s["t"]
         # ---- mLSTM cell
         g_pre_a, g_ca, g_ha_pass = ops.lstm_cell_bwd(g_ca, g_ha, s["pre_a"], s["ca_prev"], s["ca"], ids, t, P, out_gpre=gpa_all[j])
-        g_ha = ops.conv_dgrad(_rows(g_pre_a), _mat(ka[3 * D:4 * D]), 0, D, out_dtype=f32).view(R, D)
+        g_ha = ops.conv_dgrad(_op(ops, g_pre_a), _mat(ka[3 * D:4 * D]), 0, D, out_dtype=f32).view(R, D)
         ops.add_(g_ha, g_ha_pass)
         ops.add_(g_gv, g_pre_a)
         g_r = ops.rows_group_sum(g_pre_a, P, out=gr_all[j])                          # [N,4D]
-        g_lang = ops.conv_dgrad(_rows(g_r), _mat(ka[D:3 * D]), D, D, out_dtype=f32).view(N, D)
+        g_lang = ops.conv_dgrad(_op(ops, g_r), _mat(ka[D:3 * D]), D, D, out_dtype=f32).view(N, D)
         ops.add_(g_hw, ops.l2norm_rows_bwd(g_lang, lang_all[j], s["inv_l"]))
         # ---- word LSTM cell
         g_pre_w, g_cw, g_hw_pass = ops.lstm_cell_bwd(g_cw, g_hw, s["pre_w"], s["cw_prev"], s["cw"], ids, t, 1, out_gpre=gpw_all[j])
-        g_hw = ops.conv_dgrad(_rows(g_pre_w), _mat(kw), D, D, out_dtype=f32).view(N, D)
+        g_hw = ops.conv_dgrad(_op(ops, g_pre_w), _mat(kw), D, D, out_dtype=f32).view(N, D)
         ops.add_(g_hw, g_hw_pass)
     # ---- weight gradients: one product per kernel block over all steps (rows = step x sample [x position])
-    gpa, gr, gpw = gpa_all.view(S * R, 4 * D), gr_all.view(S * N, 4 * D), gpw_all.view(S * N, 4 * D)
-    e_rows, lang_rows = e_all[:S].view(S * N, D), lang_all[:S].view(S * N, D)
-    ops.conv_wgrad([(_rows(ha_all[:S].view(S * R, D)), False)], _rows(gpa), _mat(dka[3 * D:4 * D]), dba)
-    ops.conv_wgrad([(_rows(e_rows), False), (_rows(lang_rows), False)], _rows(gr), _mat(dka[D:3 * D]), None)
-    ops.conv_wgrad([(_rows(e_rows), False), (_rows(hw_all[:S].view(S * N, D)), False)], _rows(gpw), _mat(dkw), dbw)
+    gpa, gr, gpw = _op(ops, gpa_all.view(S * R, 4 * D)), _op(ops, gr_all.view(S * N, 4 * D)), _op(ops, gpw_all.view(S * N, 4 * D))
+    e_rows, lang_rows = _op(ops, e_all[:S].view(S * N, D)), _op(ops, lang_all[:S].view(S * N, D))
+    ops.conv_wgrad([(_op(ops, ha_all[:S].view(S * R, D)), False)], gpa, _mat(dka[3 * D:4 * D]), dba)
+    ops.conv_wgrad([(e_rows, False), (lang_rows, False)], gr, _mat(dka[D:3 * D]), None)
+    ops.conv_wgrad([(e_rows, False), (_op(ops, hw_all[:S].view(S * N, D)), False)], gpw, _mat(dkw), dbw)
     # ---- embedding rows: d/d(e_t) through both LSTMs, all steps at once, then one scatter-add per step
-    g_e = ops.conv_dgrad(_rows(gr), _mat(ka[D:3 * D]), 0, D, out_dtype=f32)
-    ops.conv_dgrad(_rows(gpw), _mat(kw), 0, D, out=g_e, acc=True)
+    g_e = ops.conv_dgrad(gr, _mat(ka[D:3 * D]), 0, D, out_dtype=f32)
+    ops.conv_dgrad(gpw, _mat(kw), 0, D, out=g_e, acc=True)
     g_e = g_e.view(S, N, D)
     for j in range(S):
         ops.embedding_bwd(g_e[j], ids, steps[j]["t"], demb)
-    ops.conv_wgrad([(_rows(ctx["vis"]), False)], _rows(g_gv), _mat(dka[0:D]), None)
-    g_vis = ops.conv_dgrad(_rows(g_gv), _mat(ka[0:D]), 0, D, out_dtype=f32).view(R, D)
+    g_gv_op = _op(ops, g_gv)
+    ops.conv_wgrad([(_op(ops, ctx["vis"]), False)], g_gv_op, _mat(dka[0:D]), None)
+    g_vis = ops.conv_dgrad(g_gv_op, _mat(ka[0:D]), 0, D, out_dtype=f32).view(R, D)
     g_e4 = ops.l2norm_rows_bwd(g_vis, ctx["vis"], ctx["inv_v"])
     return ops.cast(g_e4.view(N, hh, ww, D), ctx["in_dtype"])

@@ -59,15 +59,25 @@ class FgColorModel:
         fake, _ = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=False)
         wv = self.D.new_weight_view(need_wgrad=True)
         real = ops.nchw_to_nhwc(batch["images_d"])
-        rd, rl, rctx = self.D.forward(real, wv)
-        l_real, g_rd = ops.softplus_mean(rd, -1.0)                       # graph_single.py:402
-        l_ac, g_rl = ops.ce_loss(rl, batch["cls_d"], True, 1.0)         # :343-348 (focal, ld1 = 1)
-        self.D.backward(g_rd, g_rl, rctx, need_x_grad=False)
-        del rctx, rd, rl
-        fd, fl, fctx = self.D.forward(fake, wv)
-        l_fake, g_fd = ops.softplus_mean(fd, 1.0)                        # :402
-        self.D.backward(g_fd, None, fctx, need_x_grad=False)
-        del fctx
+        # D(real) and D(fake) as ONE pass over the 2N images: the discriminator has no batch statistics (PReLU, per-sample
+        # min-max gates, spectral norm), so this equals the reference's two instantiations (graph_single.py:269,271) while
+        # every kernel sees twice the work per launch.  The loss means stay per half (:401-402).
+        N = real.shape[0]
+        both = torch.empty((2 * N,) + tuple(real.shape[1:]), dtype=real.dtype, device=real.device)
+        both[:N].copy_(real)
+        both[N:].copy_(fake)
+        del real, fake
+        d, lg, dctx = self.D.forward(both, wv)
+        l_real, g_rd = ops.softplus_mean(d[:N], -1.0)                    # graph_single.py:402
+        l_fake, g_fd = ops.softplus_mean(d[N:], 1.0)                     # :402
+        l_ac, g_rl = ops.ce_loss(lg[:N], batch["cls_d"], True, 1.0)     # :343-348 (focal, ld1 = 1), real images only
+        g_d = torch.empty_like(d)
+        g_d[:N].copy_(g_rd)
+        g_d[N:].copy_(g_fd)
+        g_l = torch.zeros_like(lg)
+        g_l[:N].copy_(g_rl)
+        self.D.backward(g_d, g_l, dctx, need_x_grad=False)
+        del dctx
         wv.finish_backward()
         reg = ops.reg_loss(self.dstore)                                  # :571
         return dict(loss=l_real + l_fake + l_ac + reg, gan=l_real + l_fake, ac=l_ac, reg=reg)
