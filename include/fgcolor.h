@@ -58,7 +58,8 @@ size_t fgc_conv2d_ws_bytes(const int* src_C, int nsrc, int k, int n_out, int src
 /* 0 = tcgen05 tensor-core path (default), 1 = CUDA-core checker (also: env FGC_CONV_IMPL=simple) */
 int fgc_set_conv_impl(int impl);
 /* tuning / A-B switches of the tensor-core path (also: env FGC_HALO, FGC_SMALL): halo = 1 routes stride-1 SAME layers
- * with wide bf16 sources through the halo-reuse kernel (tensor-map TMA), 0 through the per-tap gather kernel;
+ * with wide bf16 sources through the halo-reuse kernels (tensor-map TMA), 0 through the per-tap gather kernels
+ * (2: also 1x1 layers; 3: force the 64 x 8 pixel tile variant wherever it fits -- test coverage on small problems);
  * small = 1 routes the narrow stem-level layers (all sources < 64 channels, <= 8 outputs) through the CUDA-core
  * direct kernels.  A negative value leaves that switch unchanged. */
 int fgc_set_conv_flags(int halo, int small);

@@ -790,9 +790,13 @@ struct HaloArgs {
   CUtensorMap tm[kMaxSrc];   // wide sources: the source itself; patched narrow sources: the patch tensor
 };
 
+// epilogue warps: one group of 4 per sub-tile, at most 2 groups (MT = 4: each group drains two sub-tiles in turn)
+__host__ __device__ constexpr int halo_epi_warps(int mt) { return mt > 2 ? 8 : 4 * mt; }
+
 template <int BN, int MT, int NACC>
-__global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
+__global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
   static_assert(NACC * MT * BN <= 512, "accumulators exceed TMEM");
+  constexpr int EW = halo_epi_warps(MT);
   constexpr int B_BYTES = BN * 128;
   constexpr int ACC_COLS = MT * BN;
   constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : (NACC * ACC_COLS <= 64 ? 64 : (NACC * ACC_COLS <= 128 ? 128 : (NACC * ACC_COLS <= 256 ? 256 : 512)));
@@ -831,7 +835,7 @@ __global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const _
     }
     for (int i = 0; i < NACC; i++) {
       mbar_init(smem_u32(&acc_full[i]), 1);
-      mbar_init(smem_u32(&acc_empty[i]), 128 * MT);
+      mbar_init(smem_u32(&acc_empty[i]), 32 * EW);
     }
     fence_barrier_init();
   }
@@ -980,7 +984,7 @@ __global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const _
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================
     const int ei = warp - EPI_WARP0;
-    const int tile = ei >> 2, quarter = warp & 3;      // a warp may only read TMEM lanes [32*(warp%4), +32)
+    const int grp = ei >> 2, quarter = warp & 3;       // a warp may only read TMEM lanes [32*(warp%4), +32)
     const int l = quarter * 32 + lane;                 // row of the 128-pixel sub-tile = TMEM lane
     int ti = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ti++) {
@@ -989,82 +993,86 @@ __global__ void __launch_bounds__(32 * (8 + 4 * MT), 1) conv_halo_kernel(const _
       const int tm = t / tiles_n;
       const int n = tm / a.tiles_per_img, rr = tm - n * a.tiles_per_img;
       const int ty = rr / a.tiles_w, tx = rr - ty * a.tiles_w;
-      const int oh = ty * TH + 16 * tile + (l >> 3), ow = tx * 8 + (l & 7);
-      const bool mvalid = oh < g.OH && ow < g.OW;
-      const long long m = ((long long)n * g.OH + oh) * g.OW + ow;
       mbar_wait(smem_u32(&acc_full[buf]), (ti / NACC) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int nb = n0 + c0;
-        float bias_l = 0.f;
-        if (a.bias && nb + lane < a.Nout) bias_l = __ldg(a.bias + nb + lane);
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + tile * BN + c0), r);
-        if (c0 + 32 >= BN) {                           // last read of this accumulator: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(smem_u32(&acc_empty[buf]));
-        }
-        float v[32];
-#pragma unroll
-        for (int q = 0; q < 32; q++) v[q] = __uint_as_float(r[q]) + __shfl_sync(0xffffffffu, bias_l, q);
-        switch (a.act) {
-          case FGC_ACT_LRELU:
-#pragma unroll
-            for (int q = 0; q < 32; q++) v[q] = v[q] > 0.f ? v[q] : 0.2f * v[q];
-            break;
-          case FGC_ACT_TANH:
-#pragma unroll
-            for (int q = 0; q < 32; q++) v[q] = tanhf(v[q]);
-            break;
-          case FGC_ACT_MIU:
-#pragma unroll
-            for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
-            break;
-          default: break;
-        }
-        if (!mvalid) continue;
-        if (nb >= a.Nout) continue;
-        const int nrem = a.Nout - nb;
-        if (a.y_dtype == FGC_F32) {
-          float* yp = reinterpret_cast<float*>(a.y) + m * a.Nout + nb;
-          if (a.vec_ok && nrem >= 32 && (a.Nout & 3) == 0) {
-#pragma unroll
-            for (int q = 0; q < 32; q += 4) {
-              float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-              if (a.accumulate) {
-                float4 p = *reinterpret_cast<float4*>(yp + q);
-                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-              }
-              *reinterpret_cast<float4*>(yp + q) = o;
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; q++)
-              if (q < nrem) yp[q] = a.accumulate ? yp[q] + v[q] : v[q];
+      for (int tile = grp; tile < MT; tile += EW / 4) {
+        const int oh = ty * TH + 16 * tile + (l >> 3), ow = tx * 8 + (l & 7);
+        const bool mvalid = oh < g.OH && ow < g.OW;
+        const long long m = ((long long)n * g.OH + oh) * g.OW + ow;
+        const bool last_tile = tile + EW / 4 >= MT;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int nb = n0 + c0;
+          float bias_l = 0.f;
+          if (a.bias && nb + lane < a.Nout) bias_l = __ldg(a.bias + nb + lane);
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + tile * BN + c0), r);
+          if (last_tile && c0 + 32 >= BN) {            // last read of this accumulator set: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(smem_u32(&acc_empty[buf]));
           }
-        } else {
-          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.Nout + nb;
-          if (a.vec_ok && nrem >= 32 && (a.Nout & 7) == 0) {
+          float v[32];
 #pragma unroll
-            for (int q = 0; q < 32; q += 8) {
-              if (a.accumulate) {
-                uint4 p = *reinterpret_cast<uint4*>(yp + q);
-                const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&p);
+          for (int q = 0; q < 32; q++) v[q] = __uint_as_float(r[q]) + __shfl_sync(0xffffffffu, bias_l, q);
+          switch (a.act) {
+            case FGC_ACT_LRELU:
 #pragma unroll
-                for (int e2 = 0; e2 < 4; e2++) {
-                  float2 f = __bfloat1622float2(pp[e2]);
-                  v[q + 2 * e2] += f.x; v[q + 2 * e2 + 1] += f.y;
+              for (int q = 0; q < 32; q++) v[q] = v[q] > 0.f ? v[q] : 0.2f * v[q];
+              break;
+            case FGC_ACT_TANH:
+#pragma unroll
+              for (int q = 0; q < 32; q++) v[q] = tanhf(v[q]);
+              break;
+            case FGC_ACT_MIU:
+#pragma unroll
+              for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
+              break;
+            default: break;
+          }
+          if (!mvalid) continue;
+          if (nb >= a.Nout) continue;
+          const int nrem = a.Nout - nb;
+          if (a.y_dtype == FGC_F32) {
+            float* yp = reinterpret_cast<float*>(a.y) + m * a.Nout + nb;
+            if (a.vec_ok && nrem >= 32 && (a.Nout & 3) == 0) {
+#pragma unroll
+              for (int q = 0; q < 32; q += 4) {
+                float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+                if (a.accumulate) {
+                  float4 p = *reinterpret_cast<float4*>(yp + q);
+                  o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
                 }
+                *reinterpret_cast<float4*>(yp + q) = o;
               }
-              uint4 o = make_uint4(pack_bf16x2(v[q], v[q + 1]), pack_bf16x2(v[q + 2], v[q + 3]), pack_bf16x2(v[q + 4], v[q + 5]),
-                                   pack_bf16x2(v[q + 6], v[q + 7]));
-              *reinterpret_cast<uint4*>(yp + q) = o;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; q++)
+                if (q < nrem) yp[q] = a.accumulate ? yp[q] + v[q] : v[q];
             }
           } else {
+            __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.Nout + nb;
+            if (a.vec_ok && nrem >= 32 && (a.Nout & 7) == 0) {
 #pragma unroll
-            for (int q = 0; q < 32; q++)
-              if (q < nrem) yp[q] = __float2bfloat16_rn(a.accumulate ? __bfloat162float(yp[q]) + v[q] : v[q]);
+              for (int q = 0; q < 32; q += 8) {
+                if (a.accumulate) {
+                  uint4 p = *reinterpret_cast<uint4*>(yp + q);
+                  const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&p);
+#pragma unroll
+                  for (int e2 = 0; e2 < 4; e2++) {
+                    float2 f = __bfloat1622float2(pp[e2]);
+                    v[q + 2 * e2] += f.x; v[q + 2 * e2 + 1] += f.y;
+                  }
+                }
+                uint4 o = make_uint4(pack_bf16x2(v[q], v[q + 1]), pack_bf16x2(v[q + 2], v[q + 3]), pack_bf16x2(v[q + 4], v[q + 5]),
+                                     pack_bf16x2(v[q + 6], v[q + 7]));
+                *reinterpret_cast<uint4*>(yp + q) = o;
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; q++)
+                if (q < nrem) yp[q] = __float2bfloat16_rn(a.accumulate ? __bfloat162float(yp[q]) + v[q] : v[q]);
+            }
           }
         }
       }
@@ -1782,7 +1790,7 @@ static int launch_halo(HaloArgs& h, cudaStream_t s) {
   h.box_rows = 16 * MT + h.g.k - 1;
   h.a_slot_bytes = h.box_rows * 1024;
   int a_slots = 3;
-  while (a_slots > 2 && a_slots * h.a_slot_bytes + 2 * B_BYTES > budget) a_slots--;
+  while (a_slots > 2 && a_slots * h.a_slot_bytes + 4 * B_BYTES > budget) a_slots--;      // keep >= 4 weight slabs in flight
   if (a_slots * h.a_slot_bytes + 2 * B_BYTES > budget) return -1;
   int b_slots = (budget - a_slots * h.a_slot_bytes) / B_BYTES;
   if (b_slots > 8) b_slots = 8;
@@ -1811,7 +1819,7 @@ static int launch_halo(HaloArgs& h, cudaStream_t s) {
   }
   long long ntiles = (long long)h.tiles_m * (h.Npad / BN);
   int grid = ntiles < num_sms() ? (int)ntiles : num_sms();
-  conv_halo_kernel<BN, MT, NACC><<<grid, 32 * (8 + 4 * MT), smem, s>>>(h);
+  conv_halo_kernel<BN, MT, NACC><<<grid, 32 * (8 + halo_epi_warps(MT)), smem, s>>>(h);
   g_conv_counts[0]++;
   count_launch();
   return check_launch("conv_halo");
@@ -1820,7 +1828,7 @@ static int launch_halo(HaloArgs& h, cudaStream_t s) {
 // returns -1 when the layer is not eligible (the caller falls back to conv_igemm_kernel), else the launch status
 static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
   if (g_halo_mode < 0) { const char* e = getenv("FGC_HALO"); g_halo_mode = e ? atoi(e) : 1; }
-  const int mode = g_halo_mode;      // 0 = off, 1 = on (default), 2 = also 1x1 layers
+  const int mode = g_halo_mode;      // 0 = off, 1 = on (default), 2 = also 1x1 layers, 3 = on + 64 x 8 tiles wherever they fit
   if (!mode) return -1;
   const ConvGeom& g = ia.g;
   if (!ia.fast || (g.k & 1) == 0 || g.k > 15 || g.pad_t != (g.k - 1) / 2 || g.pad_l != g.pad_t) return -1;
@@ -1845,6 +1853,12 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
   int mt = 2;
   long long tiles2 = (long long)g.N * ((g.OH + 31) / 32) * ((g.OW + 7) / 8) * (ia.Npad / bn);
   if (eff(1) > eff(2) + 1e-9 || tiles2 < (long long)num_sms()) mt = 1;
+  // 64 x 8 pixel tiles halve the weight bytes per pixel again (the weights are re-read per tile and are 59% of the
+  // L2 -> SM traffic of a 128 -> 128 layer); worth it where there are many tiles and the accumulators still fit
+  static int mt4 = -1;
+  if (mt4 < 0) { const char* e = getenv("FGC_HALO_MT4"); mt4 = e ? atoi(e) : 1; }
+  if (mt4 && mt == 2 && bn <= 128 && eff(4) >= eff(2) - 1e-9 && tiles2 >= 8LL * num_sms()) mt = 4;
+  if (mode == 3 && bn <= 128 && eff(4) >= 0.8) mt = 4;           // tests: force the 64 x 8 tiles on small problems
   if (eff(mt) < 0.8) return -1;               // e.g. 24x24 images (75%): the per-tap gather kernel wastes nothing there
   HaloArgs h;
   h.g = g;
@@ -1884,13 +1898,15 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
     }
   }
   h.nitems = ni;
-#define FGC_H(BN_, NACC2_) return mt == 2 ? launch_halo<BN_, 2, NACC2_>(h, s) : launch_halo<BN_, 1, 2>(h, s)
+#define FGC_H(BN_, NACC2_, NACC4_)                                   \
+  return mt == 4 ? launch_halo<BN_, 4, NACC4_>(h, s)                 \
+                 : (mt == 2 ? launch_halo<BN_, 2, NACC2_>(h, s) : launch_halo<BN_, 1, 2>(h, s))
   switch (bn) {
-    case 16: FGC_H(16, 2);
-    case 32: FGC_H(32, 2);
-    case 64: FGC_H(64, 2);
-    case 256: FGC_H(256, 1);
-    default: FGC_H(128, 2);
+    case 16: FGC_H(16, 2, 2);
+    case 32: FGC_H(32, 2, 2);
+    case 64: FGC_H(64, 2, 2);
+    case 256: return mt == 2 ? launch_halo<256, 2, 1>(h, s) : launch_halo<256, 1, 2>(h, s);
+    default: FGC_H(128, 2, 1);
   }
 #undef FGC_H
 }

@@ -438,3 +438,30 @@ def test_conv_with_patch_sources(env, case):
     cub.conv_wgrad(xb, gy.bfloat16().contiguous(), dw, db)
     torch.cuda.synchronize()
     close(dw, dw_ref, 3e-2, "conv_wgrad with patch sources")
+
+
+@pytest.mark.parametrize("case", [(2, 64, 24, [(128, False)], 3, 128, ACT_LRELU), (3, 64, 16, [(64, False), (3, False)], 3, 64, ACT_NONE),
+                                  (2, 128, 8, [(64, False)], 7, 3, ACT_TANH)], ids=str)
+def test_conv_halo_tall_tiles(env, case):
+    """64 x 8 pixel tiles (four 128-pixel sub-tiles per CTA, single or double buffered accumulators), forced on small inputs."""
+    cub, ref, dev = env["cub"], env["ref"], env["dev"]
+    N, H, W, srcs, k, cout, act = case
+    xs, w, b = _conv_inputs((N, H, W, srcs, k, 1, cout, act), dev, seed=60)
+    want = ref.conv_fwd(xs, w, b, act=act)
+    xb = [(x.bfloat16().contiguous(), u, cub.small_patch(x.bfloat16().contiguous(), k) if x.shape[-1] < 64 else None) for x, u in xs]
+    cub.lib.fgc_set_conv_flags(3, 1)
+    try:
+        c0 = conv_counts(cub)
+        got = cub.conv_fwd(xb, w.float().contiguous(), b.float().contiguous(), act=act)
+        torch.cuda.synchronize()
+        assert conv_counts(cub)[0] == c0[0] + 1
+        close(got, want, 3e-2, "conv_fwd, 64x8 tiles")
+        gy = rnd((N, H, W, cout), 61, dev)
+        wd = rnd((k, k, sum(c for c, _ in srcs), cout), 62, dev, 1.0 / math.sqrt(k * k * cout))
+        want_d = ref.conv_dgrad(gy, wd, 0, srcs[0][0])
+        if cout >= 64:
+            got_d = cub.conv_dgrad(gy.bfloat16().contiguous(), wd.float().contiguous(), 0, srcs[0][0])
+            torch.cuda.synchronize()
+            close(got_d, want_d, 3e-2, "conv_dgrad, 64x8 tiles")
+    finally:
+        cub.lib.fgc_set_conv_flags(1, 1)
