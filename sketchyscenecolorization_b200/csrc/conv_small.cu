@@ -64,6 +64,8 @@ __device__ __forceinline__ void load_x_tile(const ConvGeom& g, int n, int ih0, i
   }
 }
 
+constexpr int kTW = 64;        // forward tile: 16 rows x 64 columns, 4 pixels (16 columns apart) per thread
+
 template <typename T>
 __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const __grid_constant__ SmallArgs a) {
   extern __shared__ __align__(16) float sm_small[];
@@ -84,60 +86,72 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const __grid_consta
   // input row of output row oh under filter row kh:  oh*stride + sign*(kh - pad_t)
   const int org_h = g.sign > 0 ? -g.pad_t : g.pad_t - (k - 1);
   const int org_w = g.sign > 0 ? -g.pad_l : g.pad_l - (k - 1);
-  load_x_tile<T>(g, n, ty * kTS * g.stride + org_h, tx * kTS * g.stride + org_w, a.tile_h, a.tile_w, xt);
+  load_x_tile<T>(g, n, ty * kTS * g.stride + org_h, tx * kTW * g.stride + org_w, a.tile_h, a.tile_w, xt);
   __syncthreads();
+  // each weight vector read from shared memory feeds 4 pixels: the kernel is bound by shared-memory return bandwidth,
+  // not by the FMA pipe, so the register blocking is what sets its speed
   const int ly = tid >> 4, lx = tid & 15;
   const int plane = a.tile_h * a.tile_w;
-  float acc[8];
+  float acc[4][8];
 #pragma unroll
-  for (int q = 0; q < 8; q++) acc[q] = 0.f;
+  for (int p = 0; p < 4; p++)
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[p][q] = 0.f;
   for (int kh = 0; kh < k; kh++) {
     const int khl = g.sign > 0 ? kh : k - 1 - kh;
     for (int kw = 0; kw < k; kw++) {
       const int kwl = g.sign > 0 ? kw : k - 1 - kw;
       const float* xp = xt + (ly * g.stride + khl) * a.tile_w + lx * g.stride + kwl;
       const float4* wp = reinterpret_cast<const float4*>(wsm + (size_t)(kh * k + kw) * ctot * 8);
-#pragma unroll 4
+#pragma unroll 2
       for (int c = 0; c < ctot; c++) {
-        const float x = xp[c * plane];
         const float4 w0 = wp[2 * c], w1 = wp[2 * c + 1];
-        acc[0] += x * w0.x; acc[1] += x * w0.y; acc[2] += x * w0.z; acc[3] += x * w0.w;
-        acc[4] += x * w1.x; acc[5] += x * w1.y; acc[6] += x * w1.z; acc[7] += x * w1.w;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+          const float x = xp[c * plane + p * 16 * g.stride];
+          acc[p][0] += x * w0.x; acc[p][1] += x * w0.y; acc[p][2] += x * w0.z; acc[p][3] += x * w0.w;
+          acc[p][4] += x * w1.x; acc[p][5] += x * w1.y; acc[p][6] += x * w1.z; acc[p][7] += x * w1.w;
+        }
       }
     }
   }
-  const int oh = ty * kTS + ly, ow = tx * kTS + lx;
-  if (oh >= g.OH || ow >= g.OW) return;
-  const long long m = ((long long)n * g.OH + oh) * g.OW + ow;
+  const int oh = ty * kTS + ly;
+  if (oh >= g.OH) return;
+  float bias[8];
 #pragma unroll
-  for (int q = 0; q < 8; q++) {
-    float v = acc[q];
-    if (a.bias && q < a.nout) v += __ldg(a.bias + q);
-    acc[q] = small_act(v, a.act);
-  }
-  if (a.y_dtype == FGC_F32) {
-    float* yp = reinterpret_cast<float*>(a.y) + m * a.nout;
+  for (int q = 0; q < 8; q++) bias[q] = (a.bias && q < a.nout) ? __ldg(a.bias + q) : 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; q++)
-      if (q < a.nout) yp[q] = a.accumulate ? yp[q] + acc[q] : acc[q];
-  } else {
-    __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.nout;
-    if (a.nout == 8 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
-      if (a.accumulate) {
-        uint4 p = *reinterpret_cast<const uint4*>(yp);
-        const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&p);
+  for (int p = 0; p < 4; p++) {
+    const int ow = tx * kTW + lx + 16 * p;
+    if (ow >= g.OW) continue;
+    const long long m = ((long long)n * g.OH + oh) * g.OW + ow;
+    float v[8];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          float2 f = __bfloat1622float2(pp[e]);
-          acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
-        }
-      }
-      *reinterpret_cast<uint4*>(yp) = make_uint4(bf16x2_bits(acc[0], acc[1]), bf16x2_bits(acc[2], acc[3]),
-                                                 bf16x2_bits(acc[4], acc[5]), bf16x2_bits(acc[6], acc[7]));
-    } else {
+    for (int q = 0; q < 8; q++) v[q] = small_act(acc[p][q] + bias[q], a.act);
+    if (a.y_dtype == FGC_F32) {
+      float* yp = reinterpret_cast<float*>(a.y) + m * a.nout;
 #pragma unroll
       for (int q = 0; q < 8; q++)
-        if (q < a.nout) yp[q] = __float2bfloat16_rn(a.accumulate ? __bfloat162float(yp[q]) + acc[q] : acc[q]);
+        if (q < a.nout) yp[q] = a.accumulate ? yp[q] + v[q] : v[q];
+    } else {
+      __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.nout;
+      if (a.nout == 8 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
+        if (a.accumulate) {
+          uint4 pv = *reinterpret_cast<const uint4*>(yp);
+          const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&pv);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            float2 f = __bfloat1622float2(pp[e]);
+            v[2 * e] += f.x; v[2 * e + 1] += f.y;
+          }
+        }
+        *reinterpret_cast<uint4*>(yp) = make_uint4(bf16x2_bits(v[0], v[1]), bf16x2_bits(v[2], v[3]), bf16x2_bits(v[4], v[5]),
+                                                   bf16x2_bits(v[6], v[7]));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          if (q < a.nout) yp[q] = __float2bfloat16_rn(a.accumulate ? __bfloat162float(yp[q]) + v[q] : v[q]);
+      }
     }
   }
 }
@@ -153,7 +167,8 @@ struct SmallWgradArgs {
   int KKP, S;                // threads per pixel slice (multiple of 32), pixel slices per CTA
 };
 
-template <typename T>
+// NKK rows of dW per thread (kk = lane-group index + j*KKP): every gy vector read from shared memory feeds NKK rows
+template <typename T, int NKK>
 __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const __grid_constant__ SmallWgradArgs a) {
   extern __shared__ __align__(16) float sm_small[];
   const ConvGeom& g = a.g;
@@ -162,17 +177,23 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const __grid_cons
   float* xt = sm_small;                          // [ctot][tile_h][tile_w]
   float* gyt = sm_small + ((ctot * plane + 3) & ~3);   // [256][8], 16-byte aligned rows
   const int tid = threadIdx.x;
-  const int kk = tid % a.KKP, slice = tid / a.KKP;
-  const bool active = kk < KK;
-  int xoff = 0;
-  if (active) {
-    const int tap = kk / ctot, c = kk - tap * ctot;
-    const int kh = tap / k, kw = tap - kh * k;
-    xoff = c * plane + kh * a.tile_w + kw;
-  }
-  float acc[8];
+  const int kt = tid % a.KKP, slice = tid / a.KKP;
+  int xoff[NKK];
+  bool act_[NKK];
 #pragma unroll
-  for (int q = 0; q < 8; q++) acc[q] = 0.f;
+  for (int j = 0; j < NKK; j++) {
+    const int kk = kt + j * a.KKP;
+    act_[j] = kk < KK;
+    const int kc = act_[j] ? kk : 0;
+    const int tap = kc / ctot, c = kc - tap * ctot;
+    const int kh = tap / k, kw = tap - kh * k;
+    xoff[j] = c * plane + kh * a.tile_w + kw;
+  }
+  float acc[NKK][8];
+#pragma unroll
+  for (int j = 0; j < NKK; j++)
+#pragma unroll
+    for (int q = 0; q < 8; q++) acc[j][q] = 0.f;
   const T* gy = reinterpret_cast<const T*>(a.gy);
   for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
     int bt = t;
@@ -189,20 +210,25 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const __grid_cons
       gyt[i] = v;
     }
     __syncthreads();
-    if (active) {
-#pragma unroll 4
-      for (int p = slice; p < 256; p += a.S) {
-        const float x = xt[xoff + ((p >> 4) * a.tile_w + (p & 15)) * g.stride];
-        const float4 g0 = *reinterpret_cast<const float4*>(gyt + p * 8), g1 = *reinterpret_cast<const float4*>(gyt + p * 8 + 4);
-        acc[0] += x * g0.x; acc[1] += x * g0.y; acc[2] += x * g0.z; acc[3] += x * g0.w;
-        acc[4] += x * g1.x; acc[5] += x * g1.y; acc[6] += x * g1.z; acc[7] += x * g1.w;
+#pragma unroll 2
+    for (int p = slice; p < 256; p += a.S) {
+      const int po = ((p >> 4) * a.tile_w + (p & 15)) * g.stride;
+      const float4 g0 = *reinterpret_cast<const float4*>(gyt + p * 8), g1 = *reinterpret_cast<const float4*>(gyt + p * 8 + 4);
+#pragma unroll
+      for (int j = 0; j < NKK; j++) {
+        const float x = xt[xoff[j] + po];
+        acc[j][0] += x * g0.x; acc[j][1] += x * g0.y; acc[j][2] += x * g0.z; acc[j][3] += x * g0.w;
+        acc[j][4] += x * g1.x; acc[j][5] += x * g1.y; acc[j][6] += x * g1.z; acc[j][7] += x * g1.w;
       }
     }
   }
-  if (active) {
+#pragma unroll
+  for (int j = 0; j < NKK; j++) {
+    if (!act_[j]) continue;
+    const int kk = kt + j * a.KKP;
 #pragma unroll
     for (int q = 0; q < 8; q++)
-      if (q < a.Cout) atomicAdd(a.dw + (long long)kk * a.Cout + q, acc[q]);
+      if (q < a.Cout) atomicAdd(a.dw + (long long)kk * a.Cout + q, acc[j][q]);
   }
 }
 
@@ -402,8 +428,9 @@ int conv_small_fwd_try(const ConvGeom& g, int src_dtype, const float* w, long lo
   a.w = w; a.tap_stride = tap_stride; a.k_stride = k_stride; a.n_stride = n_stride; a.base = base;
   a.nout = nout; a.bias = bias; a.act = act; a.accumulate = accumulate; a.y = y; a.y_dtype = y_dtype;
   a.ctot = g.cbase[g.nsrc - 1] + g.C[g.nsrc - 1];
-  a.tile_h = a.tile_w = (kTS - 1) * g.stride + g.k;
-  a.tiles_x = (g.OW + kTS - 1) / kTS;
+  a.tile_h = (kTS - 1) * g.stride + g.k;
+  a.tile_w = (kTW - 1) * g.stride + g.k;
+  a.tiles_x = (g.OW + kTW - 1) / kTW;
   a.tiles_y = (g.OH + kTS - 1) / kTS;
   size_t smem = sizeof(float) * ((size_t)g.k * g.k * a.ctot * 8 + (size_t)a.ctot * a.tile_h * a.tile_w);
   if (smem > 96 * 1024) return -1;
@@ -436,24 +463,35 @@ int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int C
   long long ntiles = (long long)g.N * a.tiles_x * a.tiles_y;
   if (ntiles > 0x7FFFFFFFLL) return -1;
   a.ntiles = (int)ntiles;
-  a.KKP = ((KK + 31) / 32) * 32;
+  int nkk = (KK + 31) / 32;                      // rows of dW per thread
+  if (nkk > 5) nkk = 5;
+  a.KKP = ((((KK + nkk - 1) / nkk) + 31) / 32) * 32;   // threads per pixel slice
   a.S = 512 / a.KKP;
   if (a.S < 1) a.S = 1;
   if (a.S > 16) a.S = 16;
+  if (a.KKP * nkk < KK || a.KKP > 512) return -1;
   const int threads = a.KKP * a.S;
   size_t smem = sizeof(float) * ((((size_t)Cin_total * a.tile_h * a.tile_w + 3) & ~(size_t)3) + 256 * 8);
   if (smem > 96 * 1024) return -1;
   int grid = num_sms() * 2;
   if (grid > a.ntiles) grid = a.ntiles;
-  if (src_dtype == FGC_F32) {
-    static bool set = false;
-    if (!set) { cudaFuncSetAttribute(conv_small_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
-    conv_small_wgrad_kernel<float><<<grid, threads, smem, s>>>(a);
-  } else {
-    static bool set = false;
-    if (!set) { cudaFuncSetAttribute(conv_small_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; }
-    conv_small_wgrad_kernel<__nv_bfloat16><<<grid, threads, smem, s>>>(a);
+#define FGC_SW(T_, N_)                                                                                              \
+  do {                                                                                                              \
+    static bool set = false;                                                                                        \
+    if (!set) { cudaFuncSetAttribute(conv_small_wgrad_kernel<T_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; } \
+    conv_small_wgrad_kernel<T_, N_><<<grid, threads, smem, s>>>(a);                                                 \
+  } while (0)
+#define FGC_SWN(T_)                                    \
+  switch (nkk) {                                       \
+    case 1: FGC_SW(T_, 1); break;                      \
+    case 2: FGC_SW(T_, 2); break;                      \
+    case 3: FGC_SW(T_, 3); break;                      \
+    case 4: FGC_SW(T_, 4); break;                      \
+    default: FGC_SW(T_, 5); break;                     \
   }
+  if (src_dtype == FGC_F32) { FGC_SWN(float) } else { FGC_SWN(__nv_bfloat16) }
+#undef FGC_SWN
+#undef FGC_SW
   g_conv_counts[3]++;
   count_launch();
   return check_launch("conv_small_wgrad");

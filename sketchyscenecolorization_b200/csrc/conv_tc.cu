@@ -1853,11 +1853,13 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
   int mt = 2;
   long long tiles2 = (long long)g.N * ((g.OH + 31) / 32) * ((g.OW + 7) / 8) * (ia.Npad / bn);
   if (eff(1) > eff(2) + 1e-9 || tiles2 < (long long)num_sms()) mt = 1;
-  // 64 x 8 pixel tiles halve the weight bytes per pixel again (the weights are re-read per tile and are 59% of the
-  // L2 -> SM traffic of a 128 -> 128 layer); worth it where there are many tiles and the accumulators still fit
+  // 64 x 8 pixel tiles halve the weight bytes per pixel again (the weights are re-read per tile); worth it where there
+  // are many tiles and the accumulators can still be double buffered
   static int mt4 = -1;
   if (mt4 < 0) { const char* e = getenv("FGC_HALO_MT4"); mt4 = e ? atoi(e) : 1; }
-  if (mt4 && mt == 2 && bn <= 128 && eff(4) >= eff(2) - 1e-9 && tiles2 >= 8LL * num_sms()) mt = 4;
+  // measured (profiles/r1h): 64 -> 64 @192 0.37 -> 0.28 ms, [128,3] -> 64 0.74 -> 0.55 ms; with 128 outputs the four
+  // accumulators fill TMEM, the epilogue no longer overlaps the next tile and the layer gets slower (0.75 -> 0.80 ms)
+  if (mt4 && mt == 2 && bn <= 64 && eff(4) >= eff(2) - 1e-9 && tiles2 >= 8LL * num_sms()) mt = 4;
   if (mode == 3 && bn <= 128 && eff(4) >= 0.8) mt = 4;           // tests: force the 64 x 8 tiles on small problems
   if (eff(mt) < 0.8) return -1;               // e.g. 24x24 images (75%): the per-tap gather kernel wastes nothing there
   HaloArgs h;
