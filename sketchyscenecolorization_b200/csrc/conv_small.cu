@@ -473,12 +473,16 @@ int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int C
   const int threads = a.KKP * a.S;
   size_t smem = sizeof(float) * ((((size_t)Cin_total * a.tile_h * a.tile_w + 3) & ~(size_t)3) + 256 * 8);
   if (smem > 96 * 1024) return -1;
-  int grid = num_sms() * 2;
-  if (grid > a.ntiles) grid = a.ntiles;
+  // persistent CTAs: exactly as many as are resident at once (a second wave would double the run time)
 #define FGC_SW(T_, N_)                                                                                              \
   do {                                                                                                              \
     static bool set = false;                                                                                        \
     if (!set) { cudaFuncSetAttribute(conv_small_wgrad_kernel<T_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); set = true; } \
+    int per_sm = 1;                                                                                                 \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_small_wgrad_kernel<T_, N_>, threads, smem) != cudaSuccess || per_sm < 1) \
+      per_sm = 1;                                                                                                   \
+    int grid = num_sms() * per_sm;                                                                                  \
+    if (grid > a.ntiles) grid = a.ntiles;                                                                           \
     conv_small_wgrad_kernel<T_, N_><<<grid, threads, smem, s>>>(a);                                                 \
   } while (0)
 #define FGC_SWN(T_)                                    \
