@@ -180,9 +180,12 @@ def dominant_kernel_roofline(ops, torch, pk, reps=5):
     torch.cuda.synchronize()
     ms = sorted(e0.elapsed_time(e1) for e0, e1 in evs)[len(evs) // 2]
     ach = flop / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "conv_igemm_kernel<bf16,128> 3x3 128->128 @192x192 bs64 (incl. weight pack)",
+    return {"bound": "tensor", "kernel": "conv_halo_kernel<128,2,2> 3x3 128->128 @192x192 bs64 (incl. weight pack)",
             "achieved": round(ach, 2), "peak": pk["burst"], "unit": "TFLOP/s", "frac": round(ach / pk["burst"], 4),
-            "peak_source": pk["src"] + " bf16 burst", "ms_per_launch": round(ms, 4), "flop_per_launch": flop, "traffic": None}
+            "peak_source": pk["src"] + " bf16 burst", "ms_per_launch": round(ms, 4), "flop_per_launch": flop,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, `ncu --set full` (profiles/r1g_ncu_conv_summary.txt):
+            # 604.5 MB + 553.1 MB -- the input once, the output once; L2 -> SM operand traffic of the same launch: 4.65 GB
+            "traffic": 1157.7e6, "traffic_unit": "bytes/launch (DRAM)", "l2_to_sm_bytes_per_launch": 4.65e9}
 
 
 def run_product(args):
@@ -318,9 +321,14 @@ def run_product(args):
                 "roofline": roof}
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroying the process group while CUDA graphs that captured its all-reduce
+        # are still alive hung the 2-GPU run after the result line was printed (r1j).  Everything is flushed; exit now.
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -463,8 +463,10 @@ int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int C
   long long ntiles = (long long)g.N * a.tiles_x * a.tiles_y;
   if (ntiles > 0x7FFFFFFFLL) return -1;
   a.ntiles = (int)ntiles;
-  int nkk = (KK + 31) / 32;                      // rows of dW per thread
-  if (nkk > 5) nkk = 5;
+  // rows of dW per thread.  Measured (profiles/r1i,r1j): register blocking over several rows (one gy read feeding up to 5
+  // rows) is SLOWER here than one row per thread -- 7x7 stem 0.51 -> 0.81 ms -- because the block then holds 16 pixel
+  // slices of 32 threads and every slice walks the same 256-pixel tile; one row per thread and 3 slices it stays.
+  int nkk = 1;
   a.KKP = ((((KK + nkk - 1) / nkk) + 31) / 32) * 32;   // threads per pixel slice
   a.S = 512 / a.KKP;
   if (a.S < 1) a.S = 1;
