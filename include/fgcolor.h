@@ -99,19 +99,25 @@ int fgc_conv2d_wgrad(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H,
 int fgc_chan_stats(const void* x, int dtype, long long M, int C, double* acc, float* stats, fgc_stream stream);
 int fgc_cbn_act_fwd(const void* x, int dtype, int N, int HW, int C, const float* stats, const float* scale,
                     const float* offset, const int32_t* labels, int act, void* y, fgc_stream stream);
-/* scratch: 2*N*C + 2*C floats.  dscale/doffset [n_labels,C] accumulate. */
+/* scratch: 2*N*C + 2*C floats.  dscale/doffset [n_labels,C] accumulate.
+ * dbias (NULL ok, here and in fgc_prelu_bwd / fgc_minmax_bwd): fp32 [C], += column sums of the gradient written -- the
+ * bias gradient of the convolution whose output this normalisation / activation consumed (mru.conv2d adds the bias before
+ * the normaliser, mru.py:125-140), so that no separate pass over the gradient tensor is needed for it. */
 int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int C, const float* stats,
                     const float* scale, const float* offset, const int32_t* labels, int act,
-                    float* dscale, float* doffset, void* gx, float* scratch, fgc_stream stream);
+                    float* dscale, float* doffset, void* gx, float* scratch, float* dbias, fgc_stream stream);
 int fgc_prelu_fwd(const void* x, int dtype, long long n, const float* a, void* y, fgc_stream stream);
-int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, const float* a, float* da /*NULL ok*/,
-                  void* gx, fgc_stream stream);
+/* C: channel count of the NHWC tensor (only used when dbias != NULL) */
+int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, int C, const float* a, float* da /*NULL ok*/,
+                  float* dbias /*NULL ok*/, void* gx, fgc_stream stream);
+/* out[C] += column sums of x[M,C] (bias gradients that no fused kernel produces) */
+int fgc_colsum(const void* x, int dtype, long long M, int C, float* out, fgc_stream stream);
 /* gate=(x-mn)/(mx-mn) per (n,c); mn,mx fp32 [N,C]; scratch: 2*N*C uint32. */
 int fgc_minmax_fwd(const void* x, int dtype, int N, int HW, int C, void* gate, float* mn, float* mx,
                    uint32_t* scratch, fgc_stream stream);
 /* gradient w.r.t. the pre-lrelu conv output (leak 0.2); scratch: 4*N*C floats. */
 int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, int C, const float* mn,
-                   const float* mx, void* gpre, float* scratch, fgc_stream stream);
+                   const float* mx, void* gpre, float* scratch, float* dbias /*NULL ok*/, fgc_stream stream);
 /* gradient through an activation fused in a conv epilogue, from its output y (tanh / miu_relu). */
 int fgc_act_bwd(const void* gy, const void* y, int dtype, long long n, int act, void* gx, fgc_stream stream);
 

@@ -82,11 +82,12 @@ SIGNATURES = {
     "fgc_conv2d_wgrad": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "fgc_chan_stats": [_P, _I, _LL, _I, _P, _P, _P],
     "fgc_cbn_act_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P],
-    "fgc_cbn_act_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P],
+    "fgc_cbn_act_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     "fgc_prelu_fwd": [_P, _I, _LL, _P, _P, _P],
-    "fgc_prelu_bwd": [_P, _P, _I, _LL, _P, _P, _P, _P],
+    "fgc_prelu_bwd": [_P, _P, _I, _LL, _I, _P, _P, _P, _P, _P],
+    "fgc_colsum": [_P, _I, _LL, _I, _P, _P],
     "fgc_minmax_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
-    "fgc_minmax_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "fgc_minmax_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "fgc_act_bwd": [_P, _P, _I, _LL, _I, _P, _P],
     "fgc_gate_fma_fwd": [_P, _P, _P, _I, _LL, _P, _P],
     "fgc_gate_fma_bwd": [_P, _P, _P, _I, _LL, _P, _P, _P],

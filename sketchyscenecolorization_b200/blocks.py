@@ -78,14 +78,15 @@ def norm_act_fwd(ops, store, scope, x, labels, kind):
     return ops.prelu_fwd(x, a), (x,)
 
 
-def norm_act_bwd(ops, store, scope, gy, ctx, labels, kind, need_wgrad=True):
+def norm_act_bwd(ops, store, scope, gy, ctx, labels, kind, need_wgrad=True, dbias=None):
+    """dbias: bias-gradient accumulator of the convolution whose output was normalised here (fused column sums)."""
     if kind == "cbn":
         x, mean, rstd = ctx
         return ops.cbn_act_bwd(gy, x, mean, rstd, store.p[scope + "/scale"], store.p[scope + "/offset"], labels,
-                               store.g[scope + "/scale"], store.g[scope + "/offset"], ACT_MIU)
+                               store.g[scope + "/scale"], store.g[scope + "/offset"], ACT_MIU, dbias=dbias)
     (x,) = ctx
     return ops.prelu_bwd(gy, x, store.p[scope + "/prelu/param"],
-                         store.g[scope + "/prelu/param"] if need_wgrad else None)
+                         store.g[scope + "/prelu/param"] if need_wgrad else None, dbias=dbias)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -103,7 +104,8 @@ def enc_block_fwd(ops, wv, scope, x, ht, labels, kind, save=True):
     hp = ops.gate_fma_fwd(ht, rg, im)                                            # mru.py:426
     p, c_p = norm_act_fwd(ops, st, scope + "/norm_activation_merge_1", hp, labels, kind)
     w, b = wv.get(scope + "/Conv_1")
-    h1_raw = ops.conv_fwd([(p, False)], w, b)                                    # mru.py:431-436
+    ps_ = (p, False, ops.small_patch(p, 3) if p.shape[-1] < 64 else None)     # unit 1: 8 channels at full resolution
+    h1_raw = ops.conv_fwd([ps_], w, b)                                           # mru.py:431-436
     h1, c_h1 = norm_act_fwd(ops, st, scope + "/Conv_1", h1_raw, labels, kind)
     w, b = wv.get(scope + "/Conv_2")
     h2 = ops.conv_fwd([(h1, False)], w, b)                                       # mru.py:437-442
@@ -112,7 +114,7 @@ def enc_block_fwd(ops, wv, scope, x, ht, labels, kind, save=True):
     out = ops.addpool_fwd(sk, h2)                                                # mru.py:453,457
     ctx = None
     if save:
-        ctx = dict(x=x, xs_=xs_, ht=ht, a=a, c_a=c_a, rg_raw=rg_raw, rg=rg, mn=mn, mx=mx, im=im, c_p=c_p, p=p, c_h1=c_h1, h1=h1)
+        ctx = dict(x=x, xs_=xs_, ps_=ps_, ht=ht, a=a, c_a=c_a, rg_raw=rg_raw, rg=rg, mn=mn, mx=mx, im=im, c_p=c_p, p=p, c_h1=c_h1, h1=h1)
     return out, ctx
 
 
@@ -122,23 +124,31 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
     x, ht = ctx["x"], ctx["ht"]
     cin = ht.shape[-1]
     g_full = ops.unpool_bwd(g_out)                    # d/d(sk) = d/d(h2)
+    # bias gradients: column sums of the gradient at a conv output.  They come out of the kernel that produces that
+    # gradient (dbias= of the norm / activation / min-max backward); for Conv_2 / Conv_3 the gradient is the un-pooled
+    # g_out / 4 replicated 2x2, whose column sums equal those of the (4x smaller) g_out itself.
     # Conv_3 (1x1 skip on the raw hidden state)
     w3, _ = wv.get(scope + "/Conv_3")
     if nw:
-        ops.conv_wgrad([(ht, False)], g_full, *wv.grads(scope + "/Conv_3"))
+        dw3, db3 = wv.grads(scope + "/Conv_3")
+        ops.colsum_(g_out, db3)
+        ops.conv_wgrad([(ht, False)], g_full, dw3, None)
     g_ht = ops.conv_dgrad(g_full, w3, 0, cin) if need_ht_grad else None
     # Conv_2
     w2, _ = wv.get(scope + "/Conv_2")
     if nw:
-        ops.conv_wgrad([(ctx["h1"], False)], g_full, *wv.grads(scope + "/Conv_2"))
+        dw2, db2 = wv.grads(scope + "/Conv_2")
+        ops.colsum_(g_out, db2)
+        ops.conv_wgrad([(ctx["h1"], False)], g_full, dw2, None)
     g_h1 = ops.conv_dgrad(g_full, w2, 0, w2.shape[2])
     del g_full
-    g_h1raw = norm_act_bwd(ops, st, scope + "/Conv_1", g_h1, ctx["c_h1"], labels, kind, nw)
+    dw1, db1 = wv.grads(scope + "/Conv_1") if nw else (None, None)
+    g_h1raw = norm_act_bwd(ops, st, scope + "/Conv_1", g_h1, ctx["c_h1"], labels, kind, nw, dbias=db1)
     del g_h1
     # Conv_1
     w1, _ = wv.get(scope + "/Conv_1")
     if nw:
-        ops.conv_wgrad([(ctx["p"], False)], g_h1raw, *wv.grads(scope + "/Conv_1"))
+        ops.conv_wgrad([ctx["ps_"]], g_h1raw, dw1, None)
     g_p = ops.conv_dgrad(g_h1raw, w1, 0, cin)
     del g_h1raw
     g_hp = norm_act_bwd(ops, st, scope + "/norm_activation_merge_1", g_p, ctx["c_p"], labels, kind, nw)
@@ -154,11 +164,12 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
     g_x = ops.conv_dgrad(g_im, wc, 0, x.shape[-1]) if need_x_grad else None
     del g_im
     # update gate
-    g_rgraw = ops.minmax_bwd(g_rg, ctx["rg_raw"], ctx["mn"], ctx["mx"])
+    dwu, dbu = wv.grads(scope + "/update_gate") if nw else (None, None)
+    g_rgraw = ops.minmax_bwd(g_rg, ctx["rg_raw"], ctx["mn"], ctx["mx"], dbias=dbu)
     del g_rg
     wu, _ = wv.get(scope + "/update_gate")
     if nw:
-        ops.conv_wgrad([(ctx["a"], False), ctx["xs_"]], g_rgraw, *wv.grads(scope + "/update_gate"))
+        ops.conv_wgrad([(ctx["a"], False), ctx["xs_"]], g_rgraw, dwu, None)
     if need_x_grad:
         ops.conv_dgrad(g_rgraw, wu, cin, x.shape[-1], out=g_x, acc=True)
     if need_ht_grad:
@@ -221,25 +232,28 @@ def dec_block_bwd(ops, wv, scope, g_out, ctx, labels, xs_need_grad):
     g_sk, g_h2, g_zg = ops.blend_bwd(g_out, ctx["sk"], ctx["h2"], ctx["zg"])
     # skip path
     if chid != cout:
-        g_skraw = norm_act_bwd(ops, st, scope + "/Conv_4", g_sk, ctx["c_sk"], labels, "cbn")
+        dw4, db4 = wv.grads(scope + "/Conv_4")
+        g_skraw = norm_act_bwd(ops, st, scope + "/Conv_4", g_sk, ctx["c_sk"], labels, "cbn", dbias=db4)
         w4, _ = wv.get(scope + "/Conv_4")
-        ops.conv_wgrad([(ht_low, False)], g_skraw, *wv.grads(scope + "/Conv_4"))
+        ops.conv_wgrad([(ht_low, False)], g_skraw, dw4, None)
         g_ht = ops.conv_dgrad(g_skraw, w4, 0, chid)
         del g_skraw
     else:
         g_ht = g_sk
     # Conv_3
-    g_h2raw = norm_act_bwd(ops, st, scope + "/Conv_3", g_h2, ctx["c_h2"], labels, "cbn")
+    dw3, db3 = wv.grads(scope + "/Conv_3")
+    g_h2raw = norm_act_bwd(ops, st, scope + "/Conv_3", g_h2, ctx["c_h2"], labels, "cbn", dbias=db3)
     del g_h2
     w3, _ = wv.get(scope + "/Conv_3")
-    ops.conv_wgrad([(ctx["h1"], False)], g_h2raw, *wv.grads(scope + "/Conv_3"))
+    ops.conv_wgrad([(ctx["h1"], False)], g_h2raw, dw3, None)
     g_h1 = ops.conv_dgrad(g_h2raw, w3, 0, cout)
     del g_h2raw
     # Conv_2
-    g_h1raw = norm_act_bwd(ops, st, scope + "/Conv_2", g_h1, ctx["c_h1"], labels, "cbn")
+    dw2, db2 = wv.grads(scope + "/Conv_2")
+    g_h1raw = norm_act_bwd(ops, st, scope + "/Conv_2", g_h1, ctx["c_h1"], labels, "cbn", dbias=db2)
     del g_h1
     w2, _ = wv.get(scope + "/Conv_2")
-    ops.conv_wgrad([(ctx["gh"], False)] + ctx["xsrc"], g_h1raw, *wv.grads(scope + "/Conv_2"))
+    ops.conv_wgrad([(ctx["gh"], False)] + ctx["xsrc"], g_h1raw, dw2, None)
     g_gh = ops.conv_dgrad(g_h1raw, w2, 0, chid)
     g_xs = [ops.conv_dgrad(g_h1raw, w2, offs[i], xs[i].shape[-1]) if xs_need_grad[i] else None
             for i in range(len(xs))]
@@ -252,9 +266,10 @@ def dec_block_bwd(ops, wv, scope, g_out, ctx, labels, xs_need_grad):
     f_w = [(ctx["h_up"], False)] + ctx["xsrc"]
     for (gg, raw, mn, mx, sc) in ((g_rg, ctx["rg_raw"], ctx["mn0"], ctx["mx0"], scope + "/Conv"),
                                   (g_zg, ctx["zg_raw"], ctx["mn1"], ctx["mx1"], scope + "/Conv_1")):
-        g_raw = ops.minmax_bwd(gg, raw, mn, mx)
+        dwg, dbg = wv.grads(sc)
+        g_raw = ops.minmax_bwd(gg, raw, mn, mx, dbias=dbg)
         w, _ = wv.get(sc)
-        ops.conv_wgrad(f_w, g_raw, *wv.grads(sc))
+        ops.conv_wgrad(f_w, g_raw, dwg, None)
         ops.conv_dgrad(g_raw, w, 0, chid, ups=True, out=g_ht, acc=True)
         for i in range(len(xs)):
             if xs_need_grad[i]:

@@ -136,6 +136,14 @@ int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const fl
   return fgc_sum2x2(scratch, FGC_F32, N, H / 2, W / 2, c_len, gx, gx_dtype, accumulate, stream);
 }
 
+int fgc_colsum(const void* x, int dtype, long long M, int C, float* out, fgc_stream stream) {
+  FGC_REQUIRE(M > 0 && C > 0 && out, "colsum: bad arguments");
+  int e = colsum_launch(x, dtype, M, C, out, as_stream(stream));
+  if (e) return e;
+  FGC_LAUNCH_CHECK("colsum");
+  return FGC_OK;
+}
+
 int fgc_conv2d_wgrad(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W,
                      const void* gy, int gy_dtype, int k, int Cin_total, int Cout,
                      int stride, int pad_t, int pad_l, int OH, int OW,

@@ -233,22 +233,28 @@ template <typename T, int V>
 __global__ void cbn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                      const float* __restrict__ stats, const float* __restrict__ scale,
                                      const float* __restrict__ offset, const int32_t* __restrict__ labels, int act,
-                                     const float* __restrict__ m12, T* __restrict__ gx) {
+                                     const float* __restrict__ m12, T* __restrict__ gx, float* dbias) {
+  extern __shared__ float sh_db[];               // [C] block-level column sums of gx (only when dbias != NULL)
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
-  if (rl >= lanes) return;
+  if (dbias) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sh_db[i] = 0.f;
+    __syncthreads();
+  }
+  const bool on = rl < lanes;
   const int n = blockIdx.y;
   const int l = labels[n];
-  float mean[V], rstd[V], ga[V], be[V], m1[V], m2[V];
+  float mean[V], rstd[V], ga[V], be[V], m1[V], m2[V], bs[V];
 #pragma unroll
   for (int k = 0; k < V; k++) {
     int c = v * V + k;
     mean[k] = stats[c]; rstd[k] = stats[C + c];
     ga[k] = scale[l * C + c]; be[k] = offset[l * C + c];
     m1[k] = m12[c]; m2[k] = m12[C + c];
+    bs[k] = 0.f;
   }
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  const int r0 = blockIdx.x * rows_per_block, r1 = on ? min(r0 + rows_per_block, HW) : 0;
   const long long base = (long long)n * HW * C + v * V;
 #pragma unroll 2
   for (int r = r0 + rl; r < r1; r += lanes) {
@@ -261,8 +267,17 @@ __global__ void cbn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restri
       float gg = g[k];
       if (act == FGC_ACT_MIU) gg *= miu_relu_grad(xh * ga[k] + be[k]);
       o[k] = rstd[k] * (gg * ga[k] - m1[k] - xh * m2[k]);
+      bs[k] += o[k];
     }
     stv<T, V>(gx + base + (long long)r * C, o);
+  }
+  if (dbias) {                                   // bias gradient of the convolution in front: column sums of gx
+    if (on) {
+#pragma unroll
+      for (int k = 0; k < V; k++) atomicAdd(&sh_db[v * V + k], bs[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sh_db[i]);
   }
 }
 
@@ -302,6 +317,50 @@ __global__ void prelu_bwd_kernel(const T* __restrict__ gy, const T* __restrict__
     float t = block_sum(acc, red);
     if (threadIdx.x == 0) atomicAdd(da, t);
   }
+}
+
+// row-walking variant that also accumulates the column sums of gx (bias gradient of the convolution in front)
+template <typename T, int V>
+__global__ void prelu_bwd_rows_kernel(const T* __restrict__ gy, const T* __restrict__ x, long long M, int C, int rows_per_block,
+                                      const float* __restrict__ ap, float* da, T* __restrict__ gx, float* dbias) {
+  extern __shared__ float sh_db[];               // [C]
+  __shared__ float red[32];
+  const int CV = C / V;
+  const int lanes = blockDim.x / CV;
+  const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sh_db[i] = 0.f;
+  __syncthreads();
+  const bool on = rl < lanes;
+  const float a = *ap;
+  float acc = 0.f, bs[V];
+#pragma unroll
+  for (int k = 0; k < V; k++) bs[k] = 0.f;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = on ? (r0 + rows_per_block < M ? r0 + rows_per_block : M) : 0;
+#pragma unroll 2
+  for (long long r = r0 + rl; r < r1; r += lanes) {
+    float xv[kMaxV], g[kMaxV], o[kMaxV];
+    ldv<T, V>(x + r * C + v * V, xv);
+    ldv<T, V>(gy + r * C + v * V, g);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      bool m = a * xv[k] >= xv[k];
+      o[k] = m ? a * g[k] : g[k];
+      if (m) acc += g[k] * xv[k];
+      bs[k] += o[k];
+    }
+    stv<T, V>(gx + r * C + v * V, o);
+  }
+  if (on) {
+#pragma unroll
+    for (int k = 0; k < V; k++) atomicAdd(&sh_db[v * V + k], bs[k]);
+  }
+  if (da) {
+    float t = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(da, t);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sh_db[i]);
 }
 
 // ======================================================================================================
@@ -434,14 +493,19 @@ __global__ void minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __re
 template <typename T, int V>
 __global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                         const float* __restrict__ mn, const float* __restrict__ mx, int N,
-                                        const float* __restrict__ sums, T* __restrict__ gpre) {
+                                        const float* __restrict__ sums, T* __restrict__ gpre, float* dbias) {
+  extern __shared__ float sh_db[];               // [C] block-level column sums of gpre (only when dbias != NULL)
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
-  if (rl >= lanes) return;
+  if (dbias) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sh_db[i] = 0.f;
+    __syncthreads();
+  }
+  const bool on = rl < lanes;
   const int n = blockIdx.y;
   const long long NC = (long long)N * C;
-  float lo[V], hi[V], d[V], a_mx[V], a_mn[V];   // per-(n,c): min, max, range, gradient shares of the arg-max / arg-min pixels
+  float lo[V], hi[V], d[V], a_mx[V], a_mn[V], bs[V];   // per-(n,c): min, max, range, shares of the arg-max / arg-min pixels
 #pragma unroll
   for (int k = 0; k < V; k++) {
     long long q = (long long)n * C + v * V + k;
@@ -449,8 +513,9 @@ __global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __res
     float A = sums[q], S = sums[NC + q];
     a_mx[k] = (-A / (d[k] * d[k])) / sums[2 * NC + q];
     a_mn[k] = ((A - d[k] * S) / (d[k] * d[k])) / sums[3 * NC + q];
+    bs[k] = 0.f;
   }
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+  const int r0 = blockIdx.x * rows_per_block, r1 = on ? min(r0 + rows_per_block, HW) : 0;
   const long long base = (long long)n * HW * C + v * V;
 #pragma unroll 2
   for (int r = r0 + rl; r < r1; r += lanes) {
@@ -463,8 +528,17 @@ __global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __res
       if (a[k] == hi[k]) rr += a_mx[k];
       if (a[k] == lo[k]) rr += a_mn[k];
       o[k] = rr * (a[k] > 0.f ? 1.f : 0.2f);
+      bs[k] += o[k];
     }
     stv<T, V>(gpre + base + (long long)r * C, o);
+  }
+  if (dbias) {
+    if (on) {
+#pragma unroll
+      for (int k = 0; k < V; k++) atomicAdd(&sh_db[v * V + k], bs[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sh_db[i]);
   }
 }
 
@@ -783,7 +857,7 @@ int fgc_cbn_act_fwd(const void* x, int dtype, int N, int HW, int C, const float*
 
 int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int C, const float* stats,
                     const float* scale, const float* offset, const int32_t* labels, int act,
-                    float* dscale, float* doffset, void* gx, float* scratch, fgc_stream stream) {
+                    float* dscale, float* doffset, void* gx, float* scratch, float* dbias, fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
   int vec = vmin(vmin(vec_width(x, C, dtype), vec_width(gy, C, dtype)), vec_width(gx, C, dtype));
   float* sums = scratch;                       // [2,N,C]
@@ -801,8 +875,8 @@ int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int
   (void)n;
   RowRed pa = rowred_plan(C, vec, HW, N);
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    cbn_bwd_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, 0, s>>>((const T*)gy, (const T*)x, HW, C, pa.rows_per_block, stats,
-                                                                      scale, offset, labels, act, m12, (T*)gx);
+    cbn_bwd_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, dbias ? C * sizeof(float) : 0, s>>>(
+        (const T*)gy, (const T*)x, HW, C, pa.rows_per_block, stats, scale, offset, labels, act, m12, (T*)gx, dbias);
   });
   count_launch(3);
   FGC_LAUNCH_CHECK("cbn_act_bwd");
@@ -820,9 +894,22 @@ int fgc_prelu_fwd(const void* x, int dtype, long long n, const float* a, void* y
   FGC_LAUNCH_CHECK("prelu_fwd");
   return FGC_OK;
 }
-int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, const float* a, float* da, void* gx,
-                  fgc_stream stream) {
+int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, int C, const float* a, float* da, float* dbias,
+                  void* gx, fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
+  if (dbias) {
+    FGC_REQUIRE(C > 0 && n % C == 0 && C <= 1024, "prelu_bwd: bad channel count %d for the bias-gradient variant", C);
+    int vec = vmin(vmin(vec_width(x, C, dtype), vec_width(gy, C, dtype)), vec_width(gx, C, dtype));
+    const long long M = n / C;
+    RowRed p = rowred_plan(C, vec, M, 1);
+    FGC_DISPATCH_TV(dtype, vec, T, V, {
+      prelu_bwd_rows_kernel<T, V><<<p.nblk, p.threads, C * sizeof(float), s>>>((const T*)gy, (const T*)x, M, C, p.rows_per_block, a, da,
+                                                                             (T*)gx, dbias);
+    });
+    count_launch();
+    FGC_LAUNCH_CHECK("prelu_bwd");
+    return FGC_OK;
+  }
   int vec = vmin(vmin(vec_width(x, n, dtype), vec_width(gy, n, dtype)), vec_width(gx, n, dtype));
   FGC_DISPATCH_TV(dtype, vec, T, V, {
     long long nvec = n / V;
@@ -859,7 +946,7 @@ int fgc_minmax_fwd(const void* x, int dtype, int N, int HW, int C, void* gate, f
   return FGC_OK;
 }
 int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, int C, const float* mn,
-                   const float* mx, void* gpre, float* scratch, fgc_stream stream) {
+                   const float* mx, void* gpre, float* scratch, float* dbias, fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
   int vec = vmin(vmin(vec_width(x, C, dtype), vec_width(ggate, C, dtype)), vec_width(gpre, C, dtype));
   cudaMemsetAsync(scratch, 0, sizeof(float) * 4 * N * C, s);
@@ -873,8 +960,8 @@ int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, i
   (void)n;
   RowRed pa = rowred_plan(C, vec, HW, N);
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    minmax_bwd_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, 0, s>>>((const T*)ggate, (const T*)x, HW, C, pa.rows_per_block, mn,
-                                                                         mx, N, scratch, (T*)gpre);
+    minmax_bwd_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, dbias ? C * sizeof(float) : 0, s>>>(
+        (const T*)ggate, (const T*)x, HW, C, pa.rows_per_block, mn, mx, N, scratch, (T*)gpre, dbias);
   });
   count_launch(2);
   FGC_LAUNCH_CHECK("minmax_bwd");

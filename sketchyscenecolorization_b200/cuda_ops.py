@@ -168,7 +168,7 @@ class CudaOps(OpsBase):
                                        self._f32(offset), self._p(labels), act, self._p(y), self._s()), "cbn_act_fwd")
         return y
 
-    def cbn_act_bwd(self, gy, x, mean, rstd, scale, offset, labels, dscale, doffset, act=ACT_MIU):
+    def cbn_act_bwd(self, gy, x, mean, rstd, scale, offset, labels, dscale, doffset, act=ACT_MIU, dbias=None):
         N, H, W, Cc = x.shape
         assert gy.dtype == x.dtype
         gx = self._empty(x.shape, x.dtype)
@@ -176,7 +176,8 @@ class CudaOps(OpsBase):
         keep = []
         check(self.lib.fgc_cbn_act_bwd(self._p(gy), self._p(x), self._dt(x), N, H * W, Cc, self._stats_ptr(mean, rstd, keep),
                                        self._f32(scale), self._f32(offset), self._p(labels), act, self._f32(dscale),
-                                       self._f32(doffset), self._p(gx), self._p(scratch), self._s()), "cbn_act_bwd")
+                                       self._f32(doffset), self._p(gx), self._p(scratch),
+                                       None if dbias is None else self._f32(dbias.reshape(-1)), self._s()), "cbn_act_bwd")
         return gx
 
     def prelu_fwd(self, x, a):
@@ -184,12 +185,19 @@ class CudaOps(OpsBase):
         check(self.lib.fgc_prelu_fwd(self._p(x), self._dt(x), x.numel(), self._f32(a), self._p(y), self._s()), "prelu_fwd")
         return y
 
-    def prelu_bwd(self, gy, x, a, da):
+    def prelu_bwd(self, gy, x, a, da, dbias=None):
         assert gy.dtype == x.dtype
         gx = self._empty(x.shape, x.dtype)
-        check(self.lib.fgc_prelu_bwd(self._p(gy), self._p(x), self._dt(x), x.numel(), self._f32(a),
-                                     None if da is None else self._f32(da), self._p(gx), self._s()), "prelu_bwd")
+        check(self.lib.fgc_prelu_bwd(self._p(gy), self._p(x), self._dt(x), x.numel(), x.shape[-1], self._f32(a),
+                                     None if da is None else self._f32(da),
+                                     None if dbias is None else self._f32(dbias.reshape(-1)), self._p(gx), self._s()), "prelu_bwd")
         return gx
+
+    def colsum_(self, x, out):
+        """out[C] += sum over all leading dims of x[..., C]"""
+        Cc = x.shape[-1]
+        check(self.lib.fgc_colsum(self._p(x), self._dt(x), x.numel() // Cc, Cc, self._f32(out.reshape(-1)), self._s()), "colsum")
+        return out
 
     def minmax_fwd(self, x):
         N, H, W, Cc = x.shape
@@ -201,13 +209,14 @@ class CudaOps(OpsBase):
                                       self._p(scratch), self._s()), "minmax_fwd")
         return gate, mn, mx
 
-    def minmax_bwd(self, ggate, x, mn, mx):
+    def minmax_bwd(self, ggate, x, mn, mx, dbias=None):
         N, H, W, Cc = x.shape
         assert ggate.dtype == x.dtype
         gpre = self._empty(x.shape, x.dtype)
         scratch = self._empty((4 * N * Cc,), torch.float32)
         check(self.lib.fgc_minmax_bwd(self._p(ggate), self._p(x), self._dt(x), N, H * W, Cc, self._f32(mn), self._f32(mx),
-                                      self._p(gpre), self._p(scratch), self._s()), "minmax_bwd")
+                                      self._p(gpre), self._p(scratch), None if dbias is None else self._f32(dbias.reshape(-1)),
+                                      self._s()), "minmax_bwd")
         return gpre
 
     def act_bwd(self, gy, y, act):

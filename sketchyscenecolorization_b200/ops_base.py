@@ -47,15 +47,20 @@ class OpsBase:
         """act(scale[l_n,c] * (x-mean)*rstd + offset[l_n,c]); act in {ACT_NONE, ACT_MIU}."""
         raise NotImplementedError
 
-    def cbn_act_bwd(self, gy, x, mean, rstd, scale, offset, labels, dscale, doffset, act=ACT_MIU):
-        """returns gx; accumulates into dscale/doffset [25,C]."""
+    def cbn_act_bwd(self, gy, x, mean, rstd, scale, offset, labels, dscale, doffset, act=ACT_MIU, dbias=None):
+        """returns gx; accumulates into dscale/doffset [25,C].  dbias (here, in prelu_bwd and in minmax_bwd): optional fp32
+        [C] that receives += the column sums of the returned gradient = the bias gradient of the convolution in front."""
+        raise NotImplementedError
+
+    def colsum_(self, x, out):
+        """out[C] += column sums of x[..., C]"""
         raise NotImplementedError
 
     def prelu_fwd(self, x, a):
         """max(a*x, x), a = fp32 scalar tensor (models_collection.prelu, :56-60)."""
         raise NotImplementedError
 
-    def prelu_bwd(self, gy, x, a, da):
+    def prelu_bwd(self, gy, x, a, da, dbias=None):
         """returns gx; accumulates da (None => skip)."""
         raise NotImplementedError
 
@@ -63,7 +68,7 @@ class OpsBase:
         """(gate, mn[N,C], mx[N,C]) with gate = (x-mn)/(mx-mn) per (n,c) over H,W, no epsilon (mru.py:415-416)."""
         raise NotImplementedError
 
-    def minmax_bwd(self, ggate, x, mn, mx):
+    def minmax_bwd(self, ggate, x, mn, mx, dbias=None):
         """gradient w.r.t. the PRE-lrelu conv output: min-max backward (arg-min/arg-max routing, ties split
         evenly) times lrelu'(x) with leak 0.2; x is the post-lrelu tensor given to minmax_fwd."""
         raise NotImplementedError

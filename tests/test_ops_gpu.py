@@ -208,6 +208,13 @@ def test_cbn(env, shape):
         close(gx, gx_r, 2e-4, "cbn bwd gx")
         close(ds, ds_r, 1e-4, "cbn dscale")
         close(do, do_r, 1e-4, "cbn doffset")
+        # fused bias gradient (column sums of gx), accumulating
+        db = torch.full((Cc,), 0.5, device=dev)
+        ds2, do2 = torch.zeros_like(ds), torch.zeros_like(do)
+        gx2 = cu.cbn_act_bwd(gy.float().contiguous(), xf, mean, rstd, scale.float(), offset.float(), labels, ds2, do2, act, dbias=db)
+        close(gx2, gx_r, 2e-4, "cbn bwd gx (dbias variant)")
+        want_db = gx_r.reshape(-1, Cc).sum(0) + 0.5
+        assert (db.double() - want_db).abs().max().item() <= 1e-4 * max(1.0, gx_r.abs().sum(dim=(0, 1, 2)).max().item()), "cbn dbias"
     # bf16 storage
     xb = x.bfloat16().contiguous()
     mb, rb = env["cub"].chan_stats(xb)
@@ -226,6 +233,15 @@ def test_prelu_minmax_actbwd(env, shape):
     da_r, da = torch.zeros((), device=dev, dtype=torch.float64), torch.zeros((), device=dev)
     close(cu.prelu_bwd(gf, xf, af, da), ref.prelu_bwd(gy, x, a, da_r), 1e-6, "prelu bwd")
     close(da, da_r, 1e-4, "prelu da")
+    Cc = shape[-1]
+    da2, db = torch.zeros((), device=dev), torch.full((Cc,), -0.25, device=dev)
+    gx_r = ref.prelu_bwd(gy, x, a, None)
+    close(cu.prelu_bwd(gf, xf, af, da2, dbias=db), gx_r, 1e-6, "prelu bwd (dbias variant)")
+    close(da2, da_r, 1e-4, "prelu da (dbias variant)")
+    close(db, gx_r.reshape(-1, Cc).sum(0) - 0.25, 1e-5, "prelu dbias")
+    cs = torch.full((Cc,), 1.5, device=dev)
+    cu.colsum_(gf, cs)
+    close(cs, gy.reshape(-1, Cc).sum(0) + 1.5, 1e-5, "colsum")
     # min-max (with an exact tie for the maximum in one map)
     xl = torch.where(x > 0, x, 0.2 * x)
     xl[0, 0, 0, 0] = xl[0, 1, 1, 0] = xl[0, :, :, 0].max() + 0.5
@@ -235,7 +251,11 @@ def test_prelu_minmax_actbwd(env, shape):
     close(g, g_r, 1e-5, "minmax fwd")
     close(mn, mn_r, 1e-7, "mn")
     close(mx, mx_r, 1e-7, "mx")
-    close(cu.minmax_bwd(gf, xlf, mn, mx), ref.minmax_bwd(gy, xlf.double(), mn_r, mx_r), 2e-4, "minmax bwd")
+    gmm_r = ref.minmax_bwd(gy, xlf.double(), mn_r, mx_r)
+    close(cu.minmax_bwd(gf, xlf, mn, mx), gmm_r, 2e-4, "minmax bwd")
+    dbm = torch.zeros((Cc,), device=dev)
+    close(cu.minmax_bwd(gf, xlf, mn, mx, dbias=dbm), gmm_r, 2e-4, "minmax bwd (dbias variant)")
+    assert (dbm.double() - gmm_r.reshape(-1, Cc).sum(0)).abs().max().item() <= 2e-4 * gmm_r.abs().sum(dim=(0, 1, 2)).max().item(), "minmax dbias"
     # activation backward from the output
     y_t, y_m = torch.tanh(x), (x + torch.sqrt(0.09 + x * x)) / 2
     close(cu.act_bwd(gf, y_t.float().contiguous(), ACT_TANH), ref.act_bwd(gy, y_t, ACT_TANH), 1e-5, "tanh bwd")

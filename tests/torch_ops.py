@@ -111,7 +111,7 @@ class TorchOps(OpsBase):
         y = xh * self._c(scale)[lab][:, None, None, :] + self._c(offset)[lab][:, None, None, :]
         return _act(y, act).to(self.act_dtype)
 
-    def cbn_act_bwd(self, gy, x, mean, rstd, scale, offset, labels, dscale, doffset, act=ACT_MIU):
+    def cbn_act_bwd(self, gy, x, mean, rstd, scale, offset, labels, dscale, doffset, act=ACT_MIU, dbias=None):
         lab = labels.long()
         xh = (self._c(x) - mean) * rstd
         gam = self._c(scale)[lab][:, None, None, :]
@@ -127,18 +127,28 @@ class TorchOps(OpsBase):
         M = x.shape[0] * x.shape[1] * x.shape[2]
         m1 = gxh.sum(dim=(0, 1, 2)) / M
         m2 = (gxh * xh).sum(dim=(0, 1, 2)) / M
-        return (rstd * (gxh - m1 - xh * m2)).to(self.act_dtype)
+        gx = rstd * (gxh - m1 - xh * m2)
+        if dbias is not None:
+            dbias += gx.reshape(-1, gx.shape[-1]).sum(0).to(dbias.dtype).reshape(dbias.shape)
+        return gx.to(self.act_dtype)
 
     def prelu_fwd(self, x, a):
         xc = self._c(x)
         return torch.where(a * xc >= xc, a * xc, xc).to(self.act_dtype)
 
-    def prelu_bwd(self, gy, x, a, da):
+    def prelu_bwd(self, gy, x, a, da, dbias=None):
         xc, g = self._c(x), self._c(gy)
         m = a * xc >= xc
         if da is not None:
             da += (g * xc * m).sum().to(da.dtype)
-        return torch.where(m, a * g, g).to(self.act_dtype)
+        gx = torch.where(m, a * g, g)
+        if dbias is not None:
+            dbias += gx.reshape(-1, gx.shape[-1]).sum(0).to(dbias.dtype).reshape(dbias.shape)
+        return gx.to(self.act_dtype)
+
+    def colsum_(self, x, out):
+        out += self._c(x).reshape(-1, x.shape[-1]).sum(0).to(out.dtype).reshape(out.shape)
+        return out
 
     def minmax_fwd(self, x):
         xc = self._c(x)
@@ -147,7 +157,7 @@ class TorchOps(OpsBase):
         gate = (xc - mn[:, None, None, :]) / (mx - mn)[:, None, None, :]
         return gate.to(self.act_dtype), mn, mx
 
-    def minmax_bwd(self, ggate, x, mn, mx):
+    def minmax_bwd(self, ggate, x, mn, mx, dbias=None):
         xc, g = self._c(x), self._c(ggate)
         mnb, mxb = mn[:, None, None, :], mx[:, None, None, :]
         d = mxb - mnb
@@ -157,7 +167,10 @@ class TorchOps(OpsBase):
         is_mx = (xc == mxb).to(xc.dtype)
         is_mn = (xc == mnb).to(xc.dtype)
         gx = gx + is_mx * g_mx / is_mx.sum(dim=(1, 2), keepdim=True) + is_mn * g_mn / is_mn.sum(dim=(1, 2), keepdim=True)
-        return (gx * torch.where(xc > 0, torch.ones_like(xc), torch.full_like(xc, 0.2))).to(self.act_dtype)
+        gx = gx * torch.where(xc > 0, torch.ones_like(xc), torch.full_like(xc, 0.2))
+        if dbias is not None:
+            dbias += gx.reshape(-1, gx.shape[-1]).sum(0).to(dbias.dtype).reshape(dbias.shape)
+        return gx.to(self.act_dtype)
 
     def act_bwd(self, gy, y, act):
         yc, g = self._c(y), self._c(gy)
