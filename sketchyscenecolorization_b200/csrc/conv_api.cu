@@ -14,7 +14,7 @@ int conv_wgrad_simple(const ConvGeom& g, int src_dtype, const void* gy, int Cin_
 int colsum_launch(const void* x, int dtype, long long M, int C, float* out, cudaStream_t s);
 int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride, long long n_stride,
                    long long base, int nout, const float* bias, int act, int accumulate, void* y, int y_dtype, void* ws,
-                   cudaStream_t s);
+                   cudaStream_t s, int pool2 = 0);
 int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s);
 size_t conv_ws_bytes(const ConvGeom& g, int nout, int x3);
 extern int g_halo_mode, g_small_mode;
@@ -129,6 +129,11 @@ int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const fl
   if (!ups)
     return conv_igemm_run(g, gy_dtype, w, (long long)Cin_total * Cout, 1, Cout, (long long)c_off * Cout, c_len, nullptr,
                           FGC_ACT_NONE, accumulate, gx, gx_dtype, ws, s);
+  // gradient of an x2-upsampled source = 2x2 sums of the full-resolution gradient: folded into the epilogue of the
+  // halo-reuse kernel (warp shuffles) where that kernel takes the layer, else via a full-resolution fp32 scratch
+  e = conv_igemm_run(g, gy_dtype, w, (long long)Cin_total * Cout, 1, Cout, (long long)c_off * Cout, c_len, nullptr, FGC_ACT_NONE,
+                     accumulate, gx, gx_dtype, ws, s, 1);
+  if (e != 1) return e;
   FGC_REQUIRE(scratch != nullptr, "conv_dgrad: ups needs a full-resolution fp32 scratch");
   e = conv_igemm_run(g, gy_dtype, w, (long long)Cin_total * Cout, 1, Cout, (long long)c_off * Cout, c_len, nullptr, FGC_ACT_NONE, 0,
                      scratch, FGC_F32, ws, s);

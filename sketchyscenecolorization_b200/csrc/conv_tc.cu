@@ -446,6 +446,7 @@ struct IgemmArgs {
   int fast;                  // stride-1 SAME geometry: output pixel index == input pixel index
   int tiles_m;               // ceil(M / (128*MT))
   int any_small;             // some source goes through the flattened (small) path
+  int pool2;                 // halo kernel only: y is [N, OH/2, OW/2, Nout] and receives the 2x2-summed result
 };
 
 // event trace: (role, event, tile, clock64) rows appended by one lane of CTA 0
@@ -776,6 +777,7 @@ struct HaloArgs {
   int act, accumulate;
   void* y;
   int y_dtype, vec_ok;
+  int pool2;                 // y is [N, OH/2, OW/2, Nout]: 2x2 sums of the result (gradient w.r.t. an x2-upsampled source)
   const int4* tbl;           // slab table written by pack_weights_kernel (small slabs: source and first flattened index)
   int any_small;
   int box_rows;              // 16*MT + k - 1
@@ -998,8 +1000,11 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
 #pragma unroll 1
       for (int tile = grp; tile < MT; tile += EW / 4) {
         const int oh = ty * TH + 16 * tile + (l >> 3), ow = tx * 8 + (l & 7);
-        const bool mvalid = oh < g.OH && ow < g.OW;
-        const long long m = ((long long)n * g.OH + oh) * g.OW + ow;
+        // pool2: a warp holds 4 rows x 8 columns of the tile, so the 2x2 partners of a pixel are lanes l^1 and l^8;
+        // the lane of the even row / even column stores the sum at the low-resolution pixel
+        const bool mvalid = oh < g.OH && ow < g.OW && (!a.pool2 || ((l & 1) == 0 && (l & 8) == 0));
+        const long long m = a.pool2 ? ((long long)n * (g.OH >> 1) + (oh >> 1)) * (g.OW >> 1) + (ow >> 1)
+                                    : ((long long)n * g.OH + oh) * g.OW + ow;
         const bool last_tile = tile + EW / 4 >= MT;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -1029,6 +1034,13 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
               for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
               break;
             default: break;
+          }
+          if (a.pool2) {
+#pragma unroll
+            for (int q = 0; q < 32; q++) {
+              v[q] += __shfl_xor_sync(0xffffffffu, v[q], 1);
+              v[q] += __shfl_xor_sync(0xffffffffu, v[q], 8);
+            }
           }
           if (!mvalid) continue;
           if (nb >= a.Nout) continue;
@@ -1684,6 +1696,8 @@ int g_trace_cap = 0;
 int g_halo_mode = -1;      // fgc_set_conv_flags / env FGC_HALO
 
 static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s);
+static bool conv_halo_eligible(const IgemmArgs& ia, int bn);
+constexpr int kNotTaken = 1;      // conv_igemm_run(pool2 = 1): layer not eligible, nothing launched
 int conv_small_fwd_try(const ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride,
                        long long n_stride, long long base, int nout, const float* bias, int act, int accumulate, void* y,
                        int y_dtype, cudaStream_t s);
@@ -1692,12 +1706,23 @@ int conv_rows_try(const ConvGeom& g, int src_dtype, const float* w, long long ta
 int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s);
 
 // run y[M, nout] (=|+=) act(implicit_gemm(g) + bias) with weights w addressed as described in pack_weights_kernel
+// pool2 = 1: y is the 2x2-summed low-resolution result (input gradient of an x2-upsampled source).  Only the halo-reuse
+// kernel implements it; returns kNotTaken (nothing launched) when the layer does not qualify, and the caller falls back
+// to a full-resolution scratch + fgc_sum2x2.
 int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride, long long n_stride,
                    long long base, int nout, const float* bias, int act, int accumulate, void* y, int y_dtype, void* ws,
-                   cudaStream_t s) {
+                   cudaStream_t s, int pool2) {
   FGC_REQUIRE(geom_fits(g), "conv: tensor too large for pixel packing");
+  if (pool2) {
+    IgemmArgs probe;
+    probe.g = g;
+    probe.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
+    const int bn0 = pick_bn(nout, src_dtype == FGC_F32);
+    probe.Npad = ((nout + bn0 - 1) / bn0) * bn0;
+    if (src_dtype == FGC_F32 || (g.OH & 1) || (g.OW & 1) || !conv_halo_eligible(probe, bn0)) return kNotTaken;
+  }
   FGC_REQUIRE(g.M < (1LL << 31), "conv: more than 2^31 output pixels");
-  {
+  if (!pool2) {
     int r = conv_rows_try(g, src_dtype, w, tap_stride, k_stride, n_stride, base, nout, bias, act, accumulate, y, y_dtype, s);
     if (r >= 0) return r;                 // skinny product (<= 64 rows): CUDA-core kernel (conv_small.cu)
     r = conv_small_fwd_try(g, src_dtype, w, tap_stride, k_stride, n_stride, base, nout, bias, act, accumulate, y, y_dtype, s);
@@ -1740,10 +1765,12 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
   a.any_small = 0;
   for (int i = 0; i < g.nsrc; i++) a.any_small |= !g.big[i];
   a.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
+  a.pool2 = pool2;
   if (x3) return launch_igemm_f32(a, bn, s);
   {
     int r = conv_halo_try(a, bn, s);      // stride-1 SAME layers with wide sources: halo-reuse kernel (tensor-map TMA)
     if (r >= 0) return r;
+    FGC_REQUIRE(!pool2, "conv: pooled output requested but the halo-reuse kernel did not take the layer");
   }
   // two A tiles per CTA (each weight tile feeds 256 pixels) once there is enough work to fill the machine twice over
   long long ctas2 = ((g.M + 255) / 256) * (npad / bn);
@@ -1825,31 +1852,47 @@ static int launch_halo(HaloArgs& h, cudaStream_t s) {
   return check_launch("conv_halo");
 }
 
-// returns -1 when the layer is not eligible (the caller falls back to conv_igemm_kernel), else the launch status
-static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
+static double halo_eff(const ConvGeom& g, int mt) {       // tile efficiency: (16*mt) x 8 rectangles against the image size
+  int th = 16 * mt;
+  double cover = (double)(((g.OH + th - 1) / th) * th) * (((g.OW + 7) / 8) * 8);
+  return (double)g.OH * g.OW / cover;
+}
+
+// does the halo-reuse kernel take this layer?  (needs ia.g, ia.fast, ia.Npad)
+static bool conv_halo_eligible(const IgemmArgs& ia, int bn) {
   if (g_halo_mode < 0) { const char* e = getenv("FGC_HALO"); g_halo_mode = e ? atoi(e) : 1; }
   const int mode = g_halo_mode;      // 0 = off, 1 = on (default), 2 = also 1x1 layers, 3 = on + 64 x 8 tiles wherever they fit
-  if (!mode) return -1;
+  if (!mode) return false;
   const ConvGeom& g = ia.g;
-  if (!ia.fast || (g.k & 1) == 0 || g.k > 15 || g.pad_t != (g.k - 1) / 2 || g.pad_l != g.pad_t) return -1;
-  if (g.k == 1 && mode < 2) return -1;
-  bool any_big = false, any_gather = false;
+  if (!ia.fast || (g.k & 1) == 0 || g.k > 15 || g.pad_t != (g.k - 1) / 2 || g.pad_l != g.pad_t) return false;
+  if (g.k == 1 && mode < 2) return false;
+  bool any_big = false;
+  int nitems = 0;
   for (int i = 0; i < g.nsrc; i++) {
     if (!g.big[i]) {
       if (g.patch[i] && (reinterpret_cast<uintptr_t>(g.patch[i]) & 15) == 0) any_big = true;
-      else any_gather = true;
+      nitems += g.slab_begin[i + 1] - g.slab_begin[i];
       continue;
     }
-    if (g.ups[i]) return -1;                       // tensor TMA cannot replicate pixels
+    if (g.ups[i]) return false;                    // tensor TMA cannot replicate pixels
+    if ((g.C[i] + 63) / 64 > 255) return false;
+    nitems += ((g.C[i] + 63) / 64) * g.k;
     any_big = true;
   }
-  if (!any_big) return -1;
-  // tile efficiency: th x 8 rectangles against the image size
-  auto eff = [&](int mt) {
-    int th = 16 * mt;
-    double cover = (double)(((g.OH + th - 1) / th) * th) * (((g.OW + 7) / 8) * 8);
-    return (double)g.OH * g.OW / cover;
-  };
+  if (!any_big || nitems > kMaxItems || g.nslabs >= 0x4000) return false;
+  (void)bn;
+  return halo_eff(g, 1) >= 0.8 || halo_eff(g, 2) >= 0.8;
+}
+
+// returns -1 when the layer is not eligible (the caller falls back to conv_igemm_kernel), else the launch status
+static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
+  if (!conv_halo_eligible(ia, bn)) return -1;
+  const int mode = g_halo_mode;
+  const ConvGeom& g = ia.g;
+  bool any_gather = false;
+  for (int i = 0; i < g.nsrc; i++)
+    if (!g.big[i] && !(g.patch[i] && (reinterpret_cast<uintptr_t>(g.patch[i]) & 15) == 0)) any_gather = true;
+  auto eff = [&](int mt) { return halo_eff(g, mt); };
   int mt = 2;
   long long tiles2 = (long long)g.N * ((g.OH + 31) / 32) * ((g.OW + 7) / 8) * (ia.Npad / bn);
   if (eff(1) > eff(2) + 1e-9 || tiles2 < (long long)num_sms()) mt = 1;
@@ -1873,6 +1916,7 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
   h.y = ia.y;
   h.y_dtype = ia.y_dtype;
   h.vec_ok = ia.vec_ok;
+  h.pool2 = ia.pool2;
   h.tbl = ia.tbl;
   h.any_small = any_gather ? 1 : 0;
   int ni = 0;

@@ -123,6 +123,7 @@ DGRAD_CASES = [
     (2, 20, 20, 11, 8, 3, 3, 8, False, True),           # direct narrow kernel: 8-channel gy -> image slice, accumulating
     (2, 20, 20, 3, 0, 3, 7, 8, False, False),           # direct narrow kernel: stem 7x7, mirrored taps
     (2, 20, 20, 11, 0, 8, 3, 8, False, False),          # direct narrow kernel: 8 -> 8
+    (8, 64, 80, 139, 0, 128, 3, 128, True, True),       # upsampled source, 2x2 sums folded into the halo epilogue, accumulating
     (48, 1, 1, 1024, 512, 512, 1, 2048, False, False),  # skinny-product kernel (<= 64 rows): LSTM kernel slice, float4 weights
     (33, 1, 1, 200, 7, 90, 1, 130, False, True),        # skinny-product kernel: ragged K / N, unaligned slice, accumulating
 ]
