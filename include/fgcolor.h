@@ -50,7 +50,10 @@ typedef struct {
 } fgc_src;
 /* out[n,h,w,q] = x[n, h+kh-pad, w+kw-pad, c] for q = (kh*k+kw)*C + c < k*k*C, else 0 (stride 1, SAME); out is bf16 with
  * 8*ceil(k*k*C/8) channels (the TMA boxes of the consumers are 64 channels wide; the rest is out-of-bounds zero fill).  ups = 1 reads x through the x2 nearest-neighbour upsample. */
-int fgc_im2col_small(const void* x, int dtype, int N, int H, int W, int C, int ups, int k, void* out, fgc_stream stream);
+int fgc_im2col_small(const void* x, int dtype, int N, int H, int W, int C, int ups, int k, int mirror, void* out,
+                     fgc_stream stream);
+/* mirror = 1 flattens the mirrored taps, out[.., q] = x[n, h-(kh-pad), w-(kw-pad), c]: the patch tensor of a NARROW gradient
+ * tensor for fgc_conv2d_dgrad (gy_patch), whose taps run mirrored; fgc_conv2d_wgrad's gy_patch takes mirror = 0. */
 
 /* Bytes of device workspace `ws` a forward (n_out = Cout, sources = the conv inputs) or input-gradient
  * (n_out = c_len, one source of Cout channels) call needs for its packed bf16 weight tiles. */
@@ -83,13 +86,16 @@ int fgc_conv2d_fwd(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, i
  * ups=1: gx is the 2x2-summed low-res gradient [N,H/2,W/2,c_len]; `scratch` must then hold N*H*W*c_len floats. */
 int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const float* w, int k, int Cin_total,
                      int Cout, int c_off, int c_len, int ups, int accumulate, void* gx, int gx_dtype,
-                     void* scratch, void* ws, fgc_stream stream);
+                     void* scratch, void* ws, const void* gy_patch /*NULL ok: mirrored patch tensor of a narrow gy*/,
+                     fgc_stream stream);
 
 /* dw[k,k,Cin_total,Cout] += sum_m x[m+tap,ci]*gy[m,co];  db[Cout] += sum_m gy (db may be NULL). */
 int fgc_conv2d_wgrad(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W,
                      const void* gy, int gy_dtype, int k, int Cin_total, int Cout,
                      int stride, int pad_t, int pad_l, int OH, int OW,
-                     float* dw, float* db, fgc_stream stream);
+                     float* dw, float* db, const void* gy_patch /*NULL ok: patch tensor of a narrow gy under a large filter
+                     (the 7x7, 64 -> 3 head): the kernel then reduces over gy's taps instead of gathering x 49 times*/,
+                     fgc_stream stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Conditional batch-norm with batch statistics (models_collection.batchnorm, :22-34) fused with miu_relu

@@ -75,11 +75,11 @@ SIGNATURES = {
     "fgc_set_conv_impl": [_I],
     "fgc_set_conv_flags": [_I, _I],
     "fgc_debug_conv_counts": [_P],
-    "fgc_im2col_small": [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "fgc_im2col_small": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "fgc_debug_set_trace": [_P, _I],
     "fgc_conv2d_fwd": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
-    "fgc_conv2d_dgrad": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P],
-    "fgc_conv2d_wgrad": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "fgc_conv2d_dgrad": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
+    "fgc_conv2d_wgrad": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "fgc_chan_stats": [_P, _I, _LL, _I, _P, _P, _P],
     "fgc_cbn_act_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P],
     "fgc_cbn_act_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],

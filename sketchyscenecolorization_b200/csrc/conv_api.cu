@@ -15,7 +15,8 @@ int colsum_launch(const void* x, int dtype, long long M, int C, float* out, cuda
 int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_stride, long long k_stride, long long n_stride,
                    long long base, int nout, const float* bias, int act, int accumulate, void* y, int y_dtype, void* ws,
                    cudaStream_t s, int pool2 = 0);
-int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s);
+int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s,
+                   const void* gy_patch = nullptr);
 size_t conv_ws_bytes(const ConvGeom& g, int nout, int x3);
 extern int g_halo_mode, g_small_mode;
 extern long long g_conv_counts[6];
@@ -109,7 +110,7 @@ int fgc_conv2d_fwd(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, i
 
 int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const float* w, int k, int Cin_total,
                      int Cout, int c_off, int c_len, int ups, int accumulate, void* gx, int gx_dtype,
-                     void* scratch, void* ws, fgc_stream stream) {
+                     void* scratch, void* ws, const void* gy_patch, fgc_stream stream) {
   FGC_REQUIRE(k % 2 == 1, "conv_dgrad: odd kernel sizes only (got %d)", k);
   FGC_REQUIRE(c_off >= 0 && c_len > 0 && c_off + c_len <= Cin_total, "conv_dgrad: bad channel slice");
   cudaStream_t s = as_stream(stream);
@@ -120,7 +121,7 @@ int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const fl
     return FGC_OK;
   }
   // a stride-1 SAME conv over gy with the taps mirrored and the weight matrix transposed
-  fgc_src src{gy, Cout, 0, nullptr};
+  fgc_src src{gy, Cout, 0, gy_patch};
   ConvGeom g;
   int pad = (k - 1) / 2;
   int e = build_geom(g, &src, 1, N, H, W, k, 1, pad, pad, H, W, -1);
@@ -152,7 +153,7 @@ int fgc_colsum(const void* x, int dtype, long long M, int C, float* out, fgc_str
 int fgc_conv2d_wgrad(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W,
                      const void* gy, int gy_dtype, int k, int Cin_total, int Cout,
                      int stride, int pad_t, int pad_l, int OH, int OW,
-                     float* dw, float* db, fgc_stream stream) {
+                     float* dw, float* db, const void* gy_patch, fgc_stream stream) {
   FGC_REQUIRE(src_dtype == gy_dtype, "conv_wgrad: sources and gy must share a dtype");
   ConvGeom g;
   int e = build_geom(g, srcs, nsrc, N, H, W, k, stride, pad_t, pad_l, OH, OW, 1);
@@ -170,7 +171,7 @@ int fgc_conv2d_wgrad(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H,
     FGC_LAUNCH_CHECK("conv_wgrad_simple");
     return FGC_OK;
   }
-  return conv_wgrad_run(g, src_dtype, gy, Cin_total, Cout, dw, s);
+  return conv_wgrad_run(g, src_dtype, gy, Cin_total, Cout, dw, s, gy_patch);
 }
 
 }  // extern "C"

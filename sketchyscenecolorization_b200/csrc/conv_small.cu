@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const __grid_cons
 // outside the image (stride 1, SAME).  One thread writes one 16-byte chunk (8 consecutive q).
 template <typename T>
 __global__ void im2col_small_kernel(const T* __restrict__ x, long long nchunks, int H, int W, int C, int ups, int k, int CP,
-                                    __nv_bfloat16* __restrict__ out) {
+                                    int sign, __nv_bfloat16* __restrict__ out) {
   const int pad = (k - 1) / 2, KK = k * k * C, CPV = CP / 8;
   const int Hs = ups ? (H >> 1) : H, Ws = ups ? (W >> 1) : W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nchunks; i += (long long)gridDim.x * blockDim.x) {
@@ -254,7 +254,7 @@ __global__ void im2col_small_kernel(const T* __restrict__ x, long long nchunks, 
     for (int e = 0; e < 8; e++) {
       float val = 0.f;
       if (q < KK) {
-        int ih = h + kh - pad, iw = w + kw - pad;
+        int ih = h + sign * (kh - pad), iw = w + sign * (kw - pad);
         if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
           if (ups) { ih >>= 1; iw >>= 1; }
           val = ld1<T>(x + ((n * Hs + ih) * Ws + iw) * C + c);
@@ -505,7 +505,9 @@ int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int C
 
 }  // namespace fgc
 
-extern "C" int fgc_im2col_small(const void* x, int dtype, int N, int H, int W, int C, int ups, int k, void* out, fgc_stream stream) {
+extern "C" int fgc_im2col_small(const void* x, int dtype, int N, int H, int W, int C, int ups, int k, int mirror, void* out,
+                                fgc_stream stream) {
+  const int sign = mirror ? -1 : 1;
   using namespace fgc;
   FGC_REQUIRE(k % 2 == 1 && C > 0 && N > 0, "im2col_small: bad arguments");
   FGC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "im2col_small: out must be 16-byte aligned");
@@ -514,10 +516,10 @@ extern "C" int fgc_im2col_small(const void* x, int dtype, int N, int H, int W, i
   const long long nchunks = (long long)N * H * W * (CP / 8);
   cudaStream_t s = as_stream(stream);
   if (dtype == FGC_F32)
-    im2col_small_kernel<float><<<ew_grid(nchunks, 256), 256, 0, s>>>((const float*)x, nchunks, H, W, C, ups, k, CP, (__nv_bfloat16*)out);
+    im2col_small_kernel<float><<<ew_grid(nchunks, 256), 256, 0, s>>>((const float*)x, nchunks, H, W, C, ups, k, CP, sign, (__nv_bfloat16*)out);
   else if (dtype == FGC_BF16)
     im2col_small_kernel<__nv_bfloat16><<<ew_grid(nchunks, 256), 256, 0, s>>>((const __nv_bfloat16*)x, nchunks, H, W, C, ups, k, CP,
-                                                                            (__nv_bfloat16*)out);
+                                                                            sign, (__nv_bfloat16*)out);
   else { set_error("im2col_small: bad dtype %d", dtype); return FGC_EINVAL; }
   count_launch();
   return check_launch("im2col_small");

@@ -1463,7 +1463,8 @@ struct WgradHaloArgs {
   ConvGeom g;
   int Cout;
   float* dw;                 // HWIO fp32, accumulated with red.add
-  long long dw_tap, dw_c;    // dW(tap, c, n) at dw + tap*dw_tap + c*dw_c + n
+  long long dw_tap, dw_c, dw_n;   // dW(tap, c, n) at dw + tap_eff*dw_tap + c*dw_c + n*dw_n
+  int tap_flip;              // tap_eff = k*k-1-tap (operand-swapped evaluation of small-Cout layers, see conv_wgrad_run)
   int nvs;                   // slabs of the layer
   int kslabs, kslabs_per_cta;
   int tiles_w, tiles_per_img;
@@ -1608,6 +1609,7 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_halo_kernel(const __grid_co
       const int q = 2 * b + (row >> 6), kk = row & 63;
       int tap = 0, cg = 0;
       const bool rvalid = have[q] && slab_elem(g, si[q], kk, &tap, &cg);
+      if (a.tap_flip) tap = g.k * g.k - 1 - tap;
       float* dwrow = a.dw + tap * a.dw_tap + cg * a.dw_c;
       if (!have[2 * b]) continue;
 #pragma unroll 1
@@ -1618,7 +1620,7 @@ __global__ void __launch_bounds__(128, 1) conv_wgrad_halo_kernel(const __grid_co
 #pragma unroll
         for (int e = 0; e < 32; e++) {
           const int n = n0 + c0 + e;
-          if (n < a.Cout) atomicAdd(dwrow + n, __uint_as_float(r[e]));
+          if (n < a.Cout) atomicAdd(dwrow + n * a.dw_n, __uint_as_float(r[e]));
         }
       }
     }
@@ -2091,16 +2093,18 @@ static int conv_wgrad_halo_try(const WgradArgs& a, int bn, cudaStream_t s) {
   if (g_halo_mode < 0) { const char* e = getenv("FGC_HALO"); g_halo_mode = e ? atoi(e) : 1; }
   if (!g_wgrad_halo_mode || !g_halo_mode) return -1;
   const ConvGeom& g = a.g;
-  if (!a.fast || a.tap_flip || (g.k & 1) == 0 || g.k < 3 || g.k > 9 || g.pad_t != (g.k - 1) / 2 || g.pad_l != g.pad_t) return -1;
+  if (!a.fast || (g.k & 1) == 0 || g.k < 3 || g.k > 9 || g.pad_t != (g.k - 1) / 2 || g.pad_l != g.pad_t) return -1;
   if ((g.H & 7) || (g.W & 7)) return -1;
   if ((a.Cout & 7) || a.Cout < 8 || (reinterpret_cast<uintptr_t>(a.gy) & 15)) return -1;
-  if (a.dw_n != 1 || g.nslabs > kMaxVS) return -1;
+  if (g.nslabs > kMaxVS) return -1;
   WgradHaloArgs h;
   h.g = g;
   h.Cout = a.Cout;
   h.dw = a.dw;
   h.dw_tap = a.dw_tap;
   h.dw_c = a.dw_c;
+  h.dw_n = a.dw_n;
+  h.tap_flip = a.tap_flip;
   int nv = 0;
   for (int i = 0; i < g.nsrc; i++) {
     if (g.big[i]) {
@@ -2136,7 +2140,8 @@ static int pick_bn_wgrad(int nout, int x3) {
   return 128;
 }
 
-int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s) {
+int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s,
+                   const void* gy_patch) {
   FGC_REQUIRE(geom_fits(g), "wgrad: tensor too large for pixel packing");
   {
     int r = conv_small_wgrad_try(g, src_dtype, gy, Cin_total, Cout, dw, s);
@@ -2160,7 +2165,7 @@ int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, in
       g.C[0] % 8 == 0 && g.pad_t == (g.k - 1) / 2 && g.pad_l == (g.k - 1) / 2) {
     ConvGeom gs = g;
     gs.src[0] = gy;
-    gs.patch[0] = nullptr;
+    gs.patch[0] = gy_patch;              // the narrow gradient is the gathered operand here: its patch tensor feeds TMA
     gs.C[0] = Cout;
     finish_geom(gs);
     a.g = gs;

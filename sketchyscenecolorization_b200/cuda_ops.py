@@ -98,7 +98,7 @@ class CudaOps(OpsBase):
                                       self._p(y), self._dt(y), self._p(ws), self._s()), "conv2d_fwd")
         return y
 
-    def small_patch(self, x, k, ups=False):
+    def small_patch(self, x, k, ups=False, mirror=False):
         """bf16 training mode only: flattened (tap, channel) copy of a narrow source for the TMA-fed conv kernels."""
         N, h, w, Cc = x.shape
         H, W = (2 * h, 2 * w) if ups else (h, w)
@@ -106,11 +106,12 @@ class CudaOps(OpsBase):
             return None
         cp = 8 * ((k * k * Cc + 7) // 8)
         out = self._empty((N, H, W, cp), torch.bfloat16)
-        check(self.lib.fgc_im2col_small(self._p(x), self._dt(x), N, H, W, Cc, 1 if ups else 0, k, self._p(out), self._s()),
+        check(self.lib.fgc_im2col_small(self._p(x), self._dt(x), N, H, W, Cc, 1 if ups else 0, k, 1 if mirror else 0, self._p(out),
+                                        self._s()),
               "im2col_small")
         return out
 
-    def conv_dgrad(self, gy, w, c_off, c_len, *, ups=False, out=None, acc=False, out_dtype=None):
+    def conv_dgrad(self, gy, w, c_off, c_len, *, ups=False, out=None, acc=False, out_dtype=None, gy_patch=None):
         N, H, W, cout = gy.shape
         k, cin = w.shape[0], w.shape[2]
         assert w.shape[3] == cout
@@ -123,17 +124,18 @@ class CudaOps(OpsBase):
         ws = self._ws([cout], k, c_len, self._dt(gy))
         check(self.lib.fgc_conv2d_dgrad(self._p(gy), self._dt(gy), N, H, W, self._f32(w), k, cin, cout, c_off, c_len,
                                         1 if ups else 0, 1 if acc else 0, self._p(out), self._dt(out),
-                                        self._p(scratch), self._p(ws), self._s()), "conv2d_dgrad")
+                                        self._p(scratch), self._p(ws), self._p(gy_patch), self._s()), "conv2d_dgrad")
         return out
 
-    def conv_wgrad(self, srcs, gy, dw, db, *, stride=1):
+    def conv_wgrad(self, srcs, gy, dw, db, *, stride=1, gy_patch=None):
         arr, N, H, W, dt = self._srcs(srcs)
         k, cin, cout = dw.shape[0], dw.shape[2], dw.shape[3]
         OH, pt = _same_pad(H, k, stride)
         OW, pl = _same_pad(W, k, stride)
         assert tuple(gy.shape) == (N, OH, OW, cout)
         check(self.lib.fgc_conv2d_wgrad(arr, len(srcs), dt, N, H, W, self._p(gy), self._dt(gy), k, cin, cout, stride, pt, pl,
-                                        OH, OW, self._f32(dw), None if db is None else self._f32(db.reshape(-1)), self._s()),
+                                        OH, OW, self._f32(dw), None if db is None else self._f32(db.reshape(-1)), self._p(gy_patch),
+                                        self._s()),
               "conv2d_wgrad")
 
     # ---------------- normalisation / activations ----------------

@@ -79,8 +79,10 @@ class Generator:
         # head
         g = ops.act_bwd(g_out, ctx["out"], ACT_TANH)
         w, _ = wv.get(p + "/Conv_1")
-        ops.conv_wgrad([(ctx["ht_last"], False)], g, *wv.grads(p + "/Conv_1"))
-        g_ht = ops.conv_dgrad(g, w, 0, w.shape[2])
+        # 3-channel gradient under a 7x7 filter: its flattened (tap, channel) patch tensors let both products run on the
+        # TMA-fed kernels (K = 147 instead of gathering the 3 channels 49 times)
+        ops.conv_wgrad([(ctx["ht_last"], False)], g, *wv.grads(p + "/Conv_1"), gy_patch=ops.small_patch(g, w.shape[0]))
+        g_ht = ops.conv_dgrad(g, w, 0, w.shape[2], gy_patch=ops.small_patch(g, w.shape[0], mirror=True))
         del g
         g_enc = {}          # gradients flowing into encoder outputs through the skip connections
         g_nz = None

@@ -29,12 +29,12 @@ class OpsBase:
         """y = act(conv2d_SAME(concat(srcs), w) + b);  w HWIO fp32, b fp32 [Cout] or None."""
         raise NotImplementedError
 
-    def conv_dgrad(self, gy, w, c_off, c_len, *, ups=False, out=None, acc=False, out_dtype=None):
+    def conv_dgrad(self, gy, w, c_off, c_len, *, ups=False, out=None, acc=False, out_dtype=None, gy_patch=None):
         """Gradient of a stride-1 conv w.r.t. input channels [c_off, c_off+c_len) of the concatenated input.
         ups=True: the source was read through the x2 upsample, the result is the 2x2-summed low-res gradient."""
         raise NotImplementedError
 
-    def conv_wgrad(self, srcs, gy, dw, db, *, stride=1):
+    def conv_wgrad(self, srcs, gy, dw, db, *, stride=1, gy_patch=None):
         """dw += d/dw, db += sum_{n,h,w} gy  (always accumulating; dw HWIO fp32 view, db fp32 [Cout] or None)."""
         raise NotImplementedError
 
@@ -114,10 +114,12 @@ class OpsBase:
     def meanpool_fwd(self, x):
         raise NotImplementedError
 
-    def small_patch(self, x, k, ups=False):
+    def small_patch(self, x, k, ups=False, mirror=False):
         """Optional accelerator for a NARROW conv source (C < 64): a pre-flattened (tap, channel) copy of x for kernel size k
         that TMA-fed kernels fetch instead of gathering element-wise; pass it as the third element of the source tuple.
-        Returns None where it would not help (implementations are free to ignore it: the value of the conv is unchanged)."""
+        Returns None where it would not help (implementations are free to ignore it: the value of the conv is unchanged).
+        The same works for a NARROW gradient tensor under a large filter (the 7x7, 64 -> 3 head): conv_dgrad(gy_patch=) takes
+        the mirror=True patch of gy, conv_wgrad(gy_patch=) the plain one."""
         return None
 
     def upsample_fwd(self, x):

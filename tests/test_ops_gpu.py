@@ -486,3 +486,30 @@ def test_conv_halo_tall_tiles(env, case):
             close(got_d, want_d, 3e-2, "conv_dgrad, 64x8 tiles")
     finally:
         cub.lib.fgc_set_conv_flags(1, 1)
+
+
+def test_conv_head_backward_with_gy_patches(env):
+    """7x7, 64 -> 3 head: input gradient from the mirrored patch tensor of the 3-channel gy (halo-reuse kernel) and weight
+    gradient from its plain patch tensor (operand-swapped halo-reuse wgrad) equal the reference."""
+    cub, ref, dev = env["cub"], env["ref"], env["dev"]
+    N, H, W, cin, cout, k = 3, 32, 40, 64, 3, 7
+    x = rnd((N, H, W, cin), 70, dev)
+    gy = rnd((N, H, W, cout), 71, dev)
+    w = rnd((k, k, cin, cout), 72, dev, 1.0 / math.sqrt(k * k * cout))
+    xb, gb = x.bfloat16().contiguous(), gy.bfloat16().contiguous()
+    want = ref.conv_dgrad(gy, w, 0, cin)
+    c0 = conv_counts(cub)
+    got = cub.conv_dgrad(gb, w.float().contiguous(), 0, cin, gy_patch=cub.small_patch(gb, k, mirror=True))
+    torch.cuda.synchronize()
+    assert conv_counts(cub)[0] == c0[0] + 1
+    close(got, want, 3e-2, "head dgrad via gy patch")
+    dw0, db0 = rnd(w.shape, 73, dev), rnd((cout,), 74, dev)
+    dw_ref, db_ref = dw0.clone(), db0.clone()
+    ref.conv_wgrad([(x, False)], gy, dw_ref, db_ref)
+    dw, db = dw0.float().contiguous(), db0.float().contiguous()
+    c0 = conv_counts(cub)
+    cub.conv_wgrad([(xb, False)], gb, dw, db, gy_patch=cub.small_patch(gb, k))
+    torch.cuda.synchronize()
+    assert conv_counts(cub)[5] == c0[5] + 1
+    close(dw, dw_ref, 3e-2, "head wgrad via gy patch")
+    close(db, db_ref, 1e-2, "head db")

@@ -70,7 +70,7 @@ class TorchOps(OpsBase):
             y = y + self._c(b).view(1, -1, 1, 1)
         return _act(y, act).permute(0, 2, 3, 1).contiguous().to(self._od(out_dtype))
 
-    def conv_dgrad(self, gy, w, c_off, c_len, *, ups=False, out=None, acc=False, out_dtype=None):
+    def conv_dgrad(self, gy, w, c_off, c_len, *, ups=False, out=None, acc=False, out_dtype=None, gy_patch=None):
         k = w.shape[0]
         ws = self._c(w)[:, :, c_off:c_off + c_len, :]
         g = F.conv_transpose2d(self._c(gy).permute(0, 3, 1, 2), ws.permute(3, 2, 0, 1), padding=k // 2)
@@ -85,7 +85,7 @@ class TorchOps(OpsBase):
             return out
         return g.contiguous().to(self._od(out_dtype))
 
-    def conv_wgrad(self, srcs, gy, dw, db, *, stride=1):
+    def conv_wgrad(self, srcs, gy, dw, db, *, stride=1, gy_patch=None):
         x = self._cat(srcs).permute(0, 3, 1, 2)
         k = dw.shape[0]
         pt, pb = _same_pad(x.shape[2], k, stride)
