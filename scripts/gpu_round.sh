@@ -36,7 +36,7 @@ if [ "$(wc -l < gpurun_out/launches_$T.csv)" -lt 200 ]; then
   wc -l gpurun_out/launches_$T.csv
 fi
 echo "=== ncu full"
-ONLY_FIRST=1 REPS=1 timeout -k 10 600 ncu --set full --clock-control none --import-source on -k "regex:conv_halo|conv_igemm|conv_wgrad_kernel" -c 6 -f -o gpurun_out/prof_conv_$T \
+ONLY_FIRST=1 REPS=1 timeout -k 10 600 ncu --set full --clock-control none --import-source on -k "regex:conv_halo_kernel|conv_wgrad_halo_kernel|conv_igemm|conv_wgrad_kernel" -c 6 -f -o gpurun_out/prof_conv_$T \
     python scripts/prof_conv.py > gpurun_out/ncu_full_$T.log 2>&1
 echo "=== ncu full (elementwise)"
 ONLY=cbn_act_fwd,cbn_act_bwd,minmax_fwd,gate_fma_fwd,blend_fwd REPS=1 timeout -k 10 600 ncu --set full --clock-control none --import-source on \
