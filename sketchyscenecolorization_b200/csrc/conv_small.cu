@@ -237,8 +237,19 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const __grid_cons
 template <typename T>
 __global__ void im2col_small_kernel(const T* __restrict__ x, long long nchunks, int H, int W, int C, int ups, int k, int CP,
                                     int sign, __nv_bfloat16* __restrict__ out) {
+  // per flattened index q: row / column shift and the element offset inside the source relative to the pixel's own
+  // element 0 -- the same for every pixel, so it is tabulated once per block instead of divided out per element
+  extern __shared__ int sh_tab[];                // [CP] offsets, [CP] packed (dh + 64) | (dw + 64) << 8 | valid << 16
   const int pad = (k - 1) / 2, KK = k * k * C, CPV = CP / 8;
   const int Hs = ups ? (H >> 1) : H, Ws = ups ? (W >> 1) : W;
+  for (int q = threadIdx.x; q < CP; q += blockDim.x) {
+    int tap = q / C, c = q - tap * C;
+    int kh = tap / k, kw = tap - kh * k;
+    int dh = sign * (kh - pad), dw = sign * (kw - pad);
+    sh_tab[q] = (dh * Ws + dw) * C + c;          // used on the interior fast path of non-upsampled sources
+    sh_tab[CP + q] = (dh + 64) | ((dw + 64) << 8) | ((q < KK ? 1 : 0) << 16) | (c << 20);
+  }
+  __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nchunks; i += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(i % CPV);
     long long p = i / CPV;
@@ -246,26 +257,45 @@ __global__ void im2col_small_kernel(const T* __restrict__ x, long long nchunks, 
     p /= W;
     const int h = (int)(p % H);
     const long long n = p / H;
-    float v[8];
-    int q = ch * 8;
-    int tap = q / C, c = q - tap * C;
-    int kh = tap / k, kw = tap - kh * k;
-#pragma unroll
-    for (int e = 0; e < 8; e++) {
-      float val = 0.f;
-      if (q < KK) {
-        int ih = h + sign * (kh - pad), iw = w + sign * (kw - pad);
-        if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
-          if (ups) { ih >>= 1; iw >>= 1; }
-          val = ld1<T>(x + ((n * Hs + ih) * Ws + iw) * C + c);
+    const int q0 = ch * 8;
+    uint4 o;
+    if (!ups && C == 8 && q0 < KK) {
+      // one chunk = the 8 channels of one tap: a single 16-byte load (the source rows are 16-byte aligned for C = 8)
+      const int t = sh_tab[CP + q0];
+      const int ih = h + (t & 0xFF) - 64, iw = w + ((t >> 8) & 0xFF) - 64;
+      o = make_uint4(0, 0, 0, 0);
+      if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
+        if (sizeof(T) == 2) {
+          o = __ldg(reinterpret_cast<const uint4*>(x + ((n * H + ih) * W + iw) * 8));
+        } else {
+          const float* f = reinterpret_cast<const float*>(x) + ((n * H + ih) * W + iw) * 8;
+          o = make_uint4(bf16x2_bits(f[0], f[1]), bf16x2_bits(f[2], f[3]), bf16x2_bits(f[4], f[5]), bf16x2_bits(f[6], f[7]));
         }
       }
-      v[e] = val;
-      q++; c++;
-      if (c == C) { c = 0; kw++; if (kw == k) { kw = 0; kh++; } }
+    } else {
+      float v[8];
+      const bool interior = !ups && h >= pad && h < H - pad && w >= pad && w < W - pad;
+      const T* px = x + ((n * Hs + (ups ? 0 : h)) * Ws + (ups ? 0 : w)) * C;
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int t = sh_tab[CP + q0 + e];
+        float val = 0.f;
+        if ((t >> 16) & 1) {
+          if (interior) {
+            val = ld1<T>(px + sh_tab[q0 + e]);
+          } else {
+            int ih = h + (t & 0xFF) - 64, iw = w + ((t >> 8) & 0xFF) - 64;
+            if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
+              if (ups) { ih >>= 1; iw >>= 1; }
+              val = ld1<T>(x + ((n * Hs + ih) * Ws + iw) * C + (t >> 20));
+            }
+          }
+        }
+        v[e] = val;
+      }
+      o = make_uint4(bf16x2_bits(v[0], v[1]), bf16x2_bits(v[2], v[3]), bf16x2_bits(v[4], v[5]), bf16x2_bits(v[6], v[7]));
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(bf16x2_bits(v[0], v[1]), bf16x2_bits(v[2], v[3]), bf16x2_bits(v[4], v[5]),
-                                                       bf16x2_bits(v[6], v[7]));
+    *reinterpret_cast<uint4*>(out + i * 8) = o;
   }
 }
 
@@ -516,9 +546,9 @@ extern "C" int fgc_im2col_small(const void* x, int dtype, int N, int H, int W, i
   const long long nchunks = (long long)N * H * W * (CP / 8);
   cudaStream_t s = as_stream(stream);
   if (dtype == FGC_F32)
-    im2col_small_kernel<float><<<ew_grid(nchunks, 256), 256, 0, s>>>((const float*)x, nchunks, H, W, C, ups, k, CP, sign, (__nv_bfloat16*)out);
+    im2col_small_kernel<float><<<ew_grid(nchunks, 256), 256, 2 * CP * sizeof(int), s>>>((const float*)x, nchunks, H, W, C, ups, k, CP, sign, (__nv_bfloat16*)out);
   else if (dtype == FGC_BF16)
-    im2col_small_kernel<__nv_bfloat16><<<ew_grid(nchunks, 256), 256, 0, s>>>((const __nv_bfloat16*)x, nchunks, H, W, C, ups, k, CP,
+    im2col_small_kernel<__nv_bfloat16><<<ew_grid(nchunks, 256), 256, 2 * CP * sizeof(int), s>>>((const __nv_bfloat16*)x, nchunks, H, W, C, ups, k, CP,
                                                                             sign, (__nv_bfloat16*)out);
   else { set_error("im2col_small: bad dtype %d", dtype); return FGC_EINVAL; }
   count_launch();
