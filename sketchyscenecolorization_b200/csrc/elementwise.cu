@@ -80,7 +80,7 @@ __global__ void chan_stats_kernel(const T* __restrict__ x, long long M, int C, i
       float ps[V], pss[V];
 #pragma unroll
       for (int i = 0; i < V; i++) ps[i] = pss[i] = 0.f;
-#pragma unroll 8
+#pragma unroll 4
       for (int j = 0; j < 16; j++) {
         long long r = rb + (long long)j * lanes;
         if (r < r1) {
@@ -152,7 +152,7 @@ __global__ void cbn_act_fwd_kernel(const T* __restrict__ x, int HW, int C, int r
 
 // per-(n,c) sums of g and g*xhat where g = gy*act'(y)    -> sums[0][n][c], sums[1][n][c]
 template <typename T, int V>
-__global__ void __launch_bounds__(256, 2) cbn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restrict__ x, int HW, int C, int rows_per_block,
+__global__ void cbn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                       const float* __restrict__ stats, const float* __restrict__ scale,
                                       const float* __restrict__ offset, const int32_t* __restrict__ labels, int act,
                                       int N, float* sums) {
@@ -173,10 +173,12 @@ __global__ void __launch_bounds__(256, 2) cbn_bwd_reduce_kernel(const T* __restr
     ga[k] = scale[l * C + c]; be[k] = offset[l * C + c];
     s1[k] = s2[k] = 0.f;
   }
-  for (int rb = r0 + rl; rb < r1; rb += 4 * lanes) {       // four independent row loads per tensor in flight per thread
-    float a[4][kMaxV], g[4][kMaxV];
+  // two independent row loads per tensor in flight per thread; four (profiles/r1q) cost registers / resident CTAs and ran
+  // 15-20% slower on the 604 MB tensor
+  for (int rb = r0 + rl; rb < r1; rb += 2 * lanes) {
+    float a[2][kMaxV], g[2][kMaxV];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < 2; u++) {
       int r = rb + u * lanes;
       if (r < r1) {
         long long off = ((long long)n * HW + r) * C + v * V;
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(256, 2) cbn_bwd_reduce_kernel(const T* __restr
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < 2; u++) {
       if (rb + u * lanes >= r1) continue;
 #pragma unroll
       for (int k = 0; k < V; k++) {
@@ -435,7 +437,7 @@ __global__ void minmax_apply_kernel(const T* __restrict__ x, int HW, int C, int 
 }
 // sums[0] = sum g*(x-mn), sums[1] = sum g, sums[2] = #(x==mx), sums[3] = #(x==mn)   each [N,C]
 template <typename T, int V>
-__global__ void __launch_bounds__(256, 2) minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
+__global__ void minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                          const float* __restrict__ mn, const float* __restrict__ mx, int N, float* sums) {
   extern __shared__ float sh_red[];              // [4][C] block-level partial sums
   const int CV = C / V;
@@ -451,10 +453,10 @@ __global__ void __launch_bounds__(256, 2) minmax_bwd_reduce_kernel(const T* __re
     lo[k] = mn[(long long)n * C + v * V + k]; hi[k] = mx[(long long)n * C + v * V + k];
     s0[k] = s1[k] = c0[k] = c1[k] = 0.f;
   }
-  for (int rb = r0 + rl; rb < r1; rb += 4 * lanes) {       // four independent row loads per tensor in flight per thread
-    float a[4][kMaxV], g[4][kMaxV];
+  for (int rb = r0 + rl; rb < r1; rb += 2 * lanes) {       // two independent row loads in flight per thread
+    float a[2][kMaxV], g[2][kMaxV];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < 2; u++) {
       int r = rb + u * lanes;
       if (r < r1) {
         long long off = ((long long)n * HW + r) * C + v * V;
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(256, 2) minmax_bwd_reduce_kernel(const T* __re
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < 2; u++) {
       if (rb + u * lanes >= r1) continue;
 #pragma unroll
       for (int k = 0; k < V; k++) {
@@ -865,7 +867,6 @@ int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N * C, s);
   const int rvec = vec;
   RowRed p = rowred_plan(C, rvec, HW, N);
-  FGC_REQUIRE(p.threads <= 256, "cbn_act_bwd: %d channels need 4-element alignment (or <= 256 channels)", C);
   long long n = (long long)N * HW * C;
   FGC_DISPATCH_TV(dtype, rvec, T, V, {
     cbn_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 2 * C * sizeof(float), s>>>((const T*)gy, (const T*)x, HW, C,
@@ -953,7 +954,6 @@ int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, i
   cudaMemsetAsync(scratch, 0, sizeof(float) * 4 * N * C, s);
   const int rvec = vec;
   RowRed p = rowred_plan(C, rvec, HW, N);
-  FGC_REQUIRE(p.threads <= 256, "minmax_bwd: %d channels need 4-element alignment (or <= 256 channels)", C);
   long long n = (long long)N * HW * C;
   FGC_DISPATCH_TV(dtype, rvec, T, V, {
     minmax_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 4 * C * sizeof(float), s>>>((const T*)ggate, (const T*)x, HW, C,
