@@ -33,6 +33,9 @@ const char* fgc_last_error(void);
 int fgc_version(void);
 /* number of kernel launches issued through this library by the calling process (bench.py `gpu_launches`) */
 long long fgc_launch_count(void);
+/* host-side CRC-32C (Castagnoli) of data[0:n) continuing from crc (0 = fresh), unmasked: the checksum TensorFlow's
+ * tensor-bundle snapshot files carry (tf.train.Saver V2; main_procedure.py:141,235-237) */
+unsigned int fgc_crc32c(const void* data, size_t n, unsigned int crc);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Convolution family.  Replaces tf.nn.conv2d(NCHW, SAME)+bias(+activation) in mru.conv2d (mru.py:95-140),

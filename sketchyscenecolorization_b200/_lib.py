@@ -71,6 +71,7 @@ SIGNATURES = {
     "fgc_last_error": [],
     "fgc_version": [],
     "fgc_launch_count": [],
+    "fgc_crc32c": [_P, _SZ, C.c_uint],
     "fgc_conv2d_ws_bytes": [C.POINTER(C.c_int), _I, _I, _I, _I],
     "fgc_set_conv_impl": [_I],
     "fgc_set_conv_flags": [_I, _I],

@@ -1,21 +1,35 @@
-"""Snapshots in the reference's directory / file-name layout (main_procedure.py:141,235-237,550,559;
+"""Snapshots in the reference's directory / file-name layout AND byte format (main_procedure.py:141,235-237,550,559;
 obj_colorization_main.py:58-62):
 
-    <ckpt_dir>/model_<i>.ckpt-<i>.index                  JSON: variable name -> dtype, shape, byte offset
-    <ckpt_dir>/model_<i>.ckpt-<i>.data-00000-of-00001    raw little-endian tensors, concatenated
-    <ckpt_dir>/checkpoint                                'model_checkpoint_path: "model_<i>.ckpt-<i>"' (+ history)
+    <ckpt_dir>/model_<i>.ckpt-<i>.index                  TensorFlow V2 tensor-bundle index (SSTable of BundleEntryProto)
+    <ckpt_dir>/model_<i>.ckpt-<i>.data-00000-of-00001    the tensors' bytes, little endian, in key order
+    <ckpt_dir>/checkpoint                                text CheckpointState: model_checkpoint_path + history
 
-All global variables are saved under the reference's TF variable names: weights, Adam second moments
-(`<name>/Adam_1`), SN `u` vectors, optimiser step counts and `counter`.  The byte format of .index/.data is
-this package's own (TF's SSTable/protobuf tensor bundle is listed under "next" in DESIGN.md)."""
+written / read by tf_bundle.py (no TensorFlow needed).  Everything `tf.train.Saver()` of the reference graph saves is
+present under the reference's variable names, so that a TF-1 reader of the reference finds every key it asks for:
+
+    <var>                       weights (fp32, the reference's HWIO / [25,C] layouts)
+    <var>/Adam, <var>/Adam_1    AdamOptimizer slots m and v.  beta1 = 0 (graph_single.py:588), so m is just the last
+                                gradient and never influences a later step: it is written as zeros.
+    beta1_power, beta2_power    non-slot Adam accumulators of the generator's optimiser (created first, graph_single.py:208),
+    beta1_power_1, beta2_power_1   and of the discriminator's: beta^(t+1) after t steps
+    discriminator/<scope>/discriminator/<scope>/u   spectral-norm vectors (sn.py:17-18; doubled path, provisional -- SURVEY 8a)
+    Variable                    the int32 iteration `counter` (main_procedure.py:105, an unnamed tf.Variable)
+
+`restore` also still reads the JSON-indexed snapshots written by earlier versions of this package."""
 from __future__ import annotations
 
 import json
+import math
 import os
 import re
 
 import numpy as np
 import torch
+
+from . import tf_bundle
+
+_BETA2 = 0.9
 
 
 def latest_checkpoint(ckpt_dir):
@@ -31,33 +45,28 @@ def latest_checkpoint(ckpt_dir):
 
 
 def _collect(model, counter):
+    """name -> numpy array of everything the reference's Saver would save."""
     out = {}
-    for store, tag in ((model.gstore, "generator"), (model.dstore, "discriminator")):
+    for store, suffix in ((model.gstore, ""), (model.dstore, "_1")):
         if store is None:
             continue
         for k, v in store.p.items():
-            out[k] = v
+            out[k] = v.detach().float().cpu().numpy()
             o = store.offsets[k]
-            out[k + "/Adam_1"] = store.adam_v[o:o + v.numel()].view(v.shape)
+            out[k + "/Adam"] = np.zeros(tuple(v.shape), dtype=np.float32)
+            out[k + "/Adam_1"] = store.adam_v[o:o + v.numel()].view(v.shape).detach().float().cpu().numpy()
         for k, v in store.state.items():
-            out[k] = v
-        out["beta2_power/" + tag] = torch.tensor(float(store.adam_t))
-    out["counter"] = torch.tensor(float(counter))
+            out[k] = v.detach().float().cpu().numpy()
+        out["beta1_power" + suffix] = np.float32(0.0)
+        out["beta2_power" + suffix] = np.float32(_BETA2 ** (store.adam_t + 1))
+    out["Variable"] = np.int32(counter)
     return out
 
 
 def save(model, ckpt_dir, step, counter, max_to_keep=100):
     os.makedirs(ckpt_dir, exist_ok=True)
     name = "model_%d.ckpt-%d" % (step, step)
-    index, off = {}, 0
-    with open(os.path.join(ckpt_dir, name + ".data-00000-of-00001"), "wb") as f:
-        for k, v in _collect(model, counter).items():
-            a = v.detach().float().cpu().numpy().astype("<f4")
-            index[k] = {"dtype": "float32", "shape": list(a.shape), "offset": off, "nbytes": a.nbytes}
-            f.write(a.tobytes())
-            off += a.nbytes
-    with open(os.path.join(ckpt_dir, name + ".index"), "w") as f:
-        json.dump(index, f)
+    tf_bundle.write_bundle(os.path.join(ckpt_dir, name), _collect(model, counter))
     state = os.path.join(ckpt_dir, "checkpoint")
     hist = []
     if os.path.exists(state):
@@ -70,27 +79,39 @@ def save(model, ckpt_dir, step, counter, max_to_keep=100):
     return os.path.join(ckpt_dir, name)
 
 
-def restore(model, prefix, strict=True):
-    """Loads a snapshot written by `save`; returns the saved `counter`."""
+def _load_legacy(prefix):
     index = json.load(open(prefix + ".index"))
     blob = np.fromfile(prefix + ".data-00000-of-00001", dtype=np.uint8)
+    out = {}
+    for k, e in index.items():
+        out[k] = blob[e["offset"]:e["offset"] + e["nbytes"]].view("<f4").reshape(e["shape"]).copy()
+    return out
 
-    def get(k):
-        e = index[k]
-        return torch.from_numpy(blob[e["offset"]:e["offset"] + e["nbytes"]].view("<f4").reshape(e["shape"]).copy())
 
-    for store, tag in ((model.gstore, "generator"), (model.dstore, "discriminator")):
+def restore(model, prefix, strict=True):
+    """Loads a snapshot (TensorFlow V2 bundle, e.g. one written by `save` or by the reference's tf.train.Saver; or the JSON
+    format of earlier versions of this package).  Returns the saved iteration counter."""
+    with open(prefix + ".index", "rb") as f:
+        legacy = f.read(1) == b"{"
+    t = _load_legacy(prefix) if legacy else tf_bundle.read_bundle(prefix)
+
+    for store, suffix, tag in ((model.gstore, "", "generator"), (model.dstore, "_1", "discriminator")):
         if store is None:
             continue
         for k, v in list(store.p.items()) + list(store.state.items()):
-            if k in index:
-                v.copy_(get(k).to(v.dtype))
+            if k in t:
+                v.copy_(torch.from_numpy(np.asarray(t[k], dtype=np.float32)).reshape(v.shape).to(v.dtype))
             elif strict:
                 raise KeyError("snapshot %s has no variable %s" % (prefix, k))
         for k, v in store.p.items():
-            if k + "/Adam_1" in index:
+            if k + "/Adam_1" in t:
                 o = store.offsets[k]
-                store.adam_v[o:o + v.numel()].copy_(get(k + "/Adam_1").reshape(-1))
-        if "beta2_power/" + tag in index:
-            store.adam_t = int(get("beta2_power/" + tag).item())
-    return int(get("counter").item()) if "counter" in index else 0
+                store.adam_v[o:o + v.numel()].copy_(torch.from_numpy(np.asarray(t[k + "/Adam_1"], dtype=np.float32)).reshape(-1))
+        if "beta2_power" + suffix in t:
+            b2 = float(t["beta2_power" + suffix])
+            store.adam_t = max(0, int(round(math.log(max(b2, 1e-300)) / math.log(_BETA2))) - 1)
+        elif "beta2_power/" + tag in t:                      # legacy: the step count itself
+            store.adam_t = int(t["beta2_power/" + tag])
+    if "Variable" in t:
+        return int(t["Variable"])
+    return int(t["counter"]) if "counter" in t else 0

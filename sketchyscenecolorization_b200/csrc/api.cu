@@ -26,7 +26,36 @@ int check_launch(const char* what) {
 }
 }  // namespace fgc
 
+// CRC-32C (Castagnoli), slicing-by-8, host only: the checksum of TensorFlow's tensor-bundle snapshots (tf_bundle.py)
+static uint32_t g_crc_tab[8][256];
+static bool g_crc_ready = false;
+static void crc_init() {
+  for (uint32_t i = 0; i < 256; i++) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+    g_crc_tab[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; i++)
+    for (int t = 1; t < 8; t++) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xFF];
+  g_crc_ready = true;
+}
+
 extern "C" {
+/* crc32c of data[0:n) continuing from `crc` (0 for a fresh checksum); unmasked */
+unsigned int fgc_crc32c(const void* data, size_t n, unsigned int crc) {
+  if (!g_crc_ready) crc_init();
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = ~crc;
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7)) { c = g_crc_tab[0][(c ^ *p++) & 0xFF] ^ (c >> 8); n--; }
+  while (n >= 8) {
+    uint64_t v = *reinterpret_cast<const uint64_t*>(p) ^ c;
+    c = g_crc_tab[7][v & 0xFF] ^ g_crc_tab[6][(v >> 8) & 0xFF] ^ g_crc_tab[5][(v >> 16) & 0xFF] ^ g_crc_tab[4][(v >> 24) & 0xFF] ^
+        g_crc_tab[3][(v >> 32) & 0xFF] ^ g_crc_tab[2][(v >> 40) & 0xFF] ^ g_crc_tab[1][(v >> 48) & 0xFF] ^ g_crc_tab[0][v >> 56];
+    p += 8; n -= 8;
+  }
+  while (n--) c = g_crc_tab[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  return ~c;
+}
 const char* fgc_last_error(void) { return fgc::g_err; }
 int fgc_version(void) { return 100; }
 long long fgc_launch_count(void) { return fgc::g_launches.load(); }
