@@ -30,6 +30,8 @@ GF_GFLOP = 57.989          # generator conv forward, GFLOP / image   
 DF_GFLOP = 64.633          # discriminator conv forward
 STEP_GFLOP = 4 * GF_GFLOP + 8 * DF_GFLOP      # 749.02 GFLOP / image / iteration
 METRIC = "fg-colorization train images/sec @192x192 bs64 per GPU"
+WORKLOAD = ("fg-colorization MRU G+D training iteration (D step + G step), 192x192, bs 64/GPU, 15-token captions "
+            "(BASELINE.json configs[1])")
 
 
 def peaks():
@@ -150,7 +152,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": spi * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "fg-colorization MRU G+D training iteration (D step + G step), 192x192, 15-token captions",
+            "config": {"workload": WORKLOAD,
+                       "sample": sample,
                        "note": "CPU restatement of the reference TF1 graph (oracle/fgcolor_oracle.py, torch-CPU autograd); "
                                "TensorFlow 1.x is not installable in this image"},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
@@ -303,8 +306,7 @@ def run_product(args):
         line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "fg-colorization MRU G+D training iteration (D step + G step), 192x192, bs 64/GPU, "
-                                       "15-token captions (BASELINE.json configs[1])",
+                "config": {"workload": WORKLOAD,
                            "global_batch": BS * world, "parallelism": "dp%d" % world,
                            "precision": "bf16 activations + single-pass bf16 tcgen05 convs, fp32 accumulate/master/BN/LSTM/Adam",
                            "l2_policy": "per-step working set (tens of GB of activations) far exceeds the 126 MB L2",
