@@ -83,8 +83,17 @@ def train(**kwargs):
     tr.counter = iter_from                                          # sess.run(counter.assign(iter_from)), :176
     print_parameter_count(model)
     rank = int(os.environ.get("RANK", "0"))
-    q1 = kwargs.get('input_iter') or SyntheticInput(batch_size, *SIZE[small], vocab_size=Config.vocab_size, seed=1234 + rank)
-    q2 = kwargs.get('input_iter_d') or SyntheticInput(batch_size, *SIZE[small], vocab_size=Config.vocab_size, seed=4321 + rank)
+    q1, q2 = kwargs.get('input_iter'), kwargs.get('input_iter_d')
+    rec_dir = os.path.join(kwargs.get('data_base_dir', 'data'), 'tfrecord', 'train')
+    if (q1 is None or q2 is None) and os.path.isdir(rec_dir) and os.listdir(rec_dir):
+        # the reference's two independent TFRecord shuffle queues (main_procedure.py:109-122)
+        from .tfrecord_input import PairedTrainInput
+        mk = lambda seed: PairedTrainInput(batch_size, kwargs.get('data_base_dir', 'data'), small=small,      # noqa: E731
+                                           distance_map=Config.distance_map != 0, seed=seed)
+        q1, q2 = q1 or mk(1234 + rank), q2 or mk(4321 + rank)
+    else:                                 # the dataset is not part of the reference repository: seeded synthetic batches
+        q1 = q1 or SyntheticInput(batch_size, *SIZE[small], vocab_size=Config.vocab_size, seed=1234 + rank)
+        q2 = q2 or SyntheticInput(batch_size, *SIZE[small], vocab_size=Config.vocab_size, seed=4321 + rank)
     dev = model.device
     summ = open(os.path.join(log_dir, 'summaries.jsonl'), 'a') if rank == 0 else None
 
@@ -194,5 +203,44 @@ def test(model=None):
 
 
 def validation(**kwargs):
-    raise NotImplementedError("validation reads the TFRecord validation queue (main_procedure.py:245-358); the TFRecord reader "
-                              "is listed under 'next' in DESIGN.md")
+    """One ordered pass over data/tfrecord/<Config.dataset_type> (main_procedure.py:245-358): for every sample writes
+    <category>_<name>_{output,target,input}.png into <results_dir>/with_text (or without_text).  Batches of
+    Config.batch_size, as in the reference (conditional BN sees the batch).  kwargs: optional `model`, `data_base_dir`."""
+    import cv2
+    from .tfrecord_input import PairedEvalInput
+    small, lstm_hybrid = Config.small_img != 0, Config.LSTM_hybrid != 0
+    batch_size = Config.batch_size
+    output_folder = os.path.join(Config.results_dir, 'with_text' if lstm_hybrid else 'without_text')
+    print(output_folder)
+    os.makedirs(output_folder, exist_ok=True)
+    model = kwargs.get('model')
+    if model is None:
+        model = _build_model(Config.infer_precision, SIZE[small], Config.vocab_size, lstm_hybrid, with_discriminator=False)
+        prefix = checkpoint.latest_checkpoint(Config.ckpt_dir)
+        print('Restore trained model:', prefix)
+        if prefix is None:
+            raise RuntimeError("no snapshot in %s" % Config.ckpt_dir)
+        checkpoint.restore(model, prefix, strict=True)
+    queue = PairedEvalInput(Config.dataset_type, batch_size, data_base_dir=kwargs.get('data_base_dir', 'data'), small=small,
+                            distance_map=Config.distance_map != 0)
+    counter, prev_time = 0, float("-inf")
+    for b in queue:
+        ret = graph_single.build_single_graph(b['images'], b['sketch'], None, b['cls'], None, b['text'], batch_size=batch_size,
+                                              training=False, LSTM_hybrid=lstm_hybrid, vocab_size=Config.vocab_size,
+                                              data_format=Config.data_format, distance_map=Config.distance_map != 0,
+                                              block_type=Config.block_type, model=model, noise=kwargs.get('noise'))
+        if counter % 100 == 0:
+            curr_time = time()
+            print("Now at iteration %d. Elapsed time: %.5fs." % (counter, curr_time - prev_time))
+            prev_time = curr_time
+        to_img = lambda t: ((np.transpose(t.detach().float().cpu().numpy(), (0, 2, 3, 1)) + 1) / 2.) * 255   # noqa: E731
+        generated, target, sketch = to_img(ret[0])[:, :, :, ::-1].astype(np.uint8), to_img(ret[1])[:, :, :, ::-1].astype(np.uint8), \
+            to_img(ret[2]).astype(np.uint8)
+        for i in range(batch_size):
+            stem = '%s_%s' % (b['categories'][i], b['image_names'][i][:-4])
+            cv2.imwrite(os.path.join(output_folder, stem + '_output.png'), generated[i])
+            cv2.imwrite(os.path.join(output_folder, stem + '_target.png'), target[i])
+            cv2.imwrite(os.path.join(output_folder, stem + '_input.png'), sketch[i])
+            print('Saved file %s' % b['categories'][i])
+        counter += 1
+    return counter

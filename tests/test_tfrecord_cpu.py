@@ -1,0 +1,190 @@
+"""TFRecord / tf.train.Example input pipeline without TensorFlow (tfrecord_input.py): the record framing is checked against
+tensorboard's independent RecordWriter, the Example encoding against the protobuf runtime (schema of feature.proto /
+example.proto built with descriptor_pb2), the pre-processing against the TF-1 resize / normalisation rules of
+input_pipeline.get_paired_input, and `--mode val` end to end on a small CPU model."""
+import io
+import os
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from sketchyscenecolorization_b200 import tfrecord_input as TI
+
+
+def _example(i, rng):
+    img = rng.integers(0, 256, (384, 384, 3), dtype=np.uint8)
+    sk = np.full((384, 384, 3), 255, np.uint8)
+    sk[40 + i:44 + i, 20:300] = 0
+    sk[100:300, 150 + 2 * i:153 + 2 * i] = 0
+    text = np.array([0] * 9 + [24, 3, 6, 22, 5, 25], dtype=np.uint8)
+    return dict(ImageName=("img%03d.png" % i).encode(), cartoon_data=img.tobytes(), sketch_data=sk.tobytes(), Category=b"bus",
+                Category_id=2, Color_text=b"the bus is orange with gray windows", Text_vocab_indices=text.tobytes()), img, sk, text
+
+
+def test_record_framing_matches_tensorboard(tmp_path):
+    rw = pytest.importorskip("tensorboard.summary.writer.record_writer")
+    payloads = [b"", b"x", os.urandom(1000), bytes(range(256)) * 3]
+    path = str(tmp_path / "a.tfrecord")
+    w = rw.RecordWriter(open(path, "wb"))
+    for p in payloads:
+        w.write(p)
+    w.close()
+    assert list(TI.read_tfrecord(path)) == payloads
+    mine = str(tmp_path / "b.tfrecord")
+    TI.write_tfrecord(mine, payloads)
+    assert open(mine, "rb").read() == open(path, "rb").read()
+    bad = bytearray(open(mine, "rb").read())
+    bad[14] ^= 1                                            # first data byte of the second record
+    open(mine, "wb").write(bad)
+    with pytest.raises(ValueError):
+        list(TI.read_tfrecord(mine))
+
+
+def _feature_messages():
+    """Example / Features / Feature / *List message classes from the protobuf runtime (schema of feature.proto)."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name="fgc_feature_test.proto", package="fgctest", syntax="proto3")
+
+    def msg(name, fields, nested=None):
+        m = fd.message_type.add(name=name)
+        for fname, num, typ, label, tname in fields:
+            f = m.field.add(name=fname, number=num, type=typ, label=label)
+            if tname:
+                f.type_name = tname
+        return m
+
+    msg("BytesList", [("value", 1, F.TYPE_BYTES, F.LABEL_REPEATED, None)])
+    msg("FloatList", [("value", 1, F.TYPE_FLOAT, F.LABEL_REPEATED, None)])
+    msg("Int64List", [("value", 1, F.TYPE_INT64, F.LABEL_REPEATED, None)])
+    feat = msg("Feature", [("bytes_list", 1, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, ".fgctest.BytesList"),
+                           ("float_list", 2, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, ".fgctest.FloatList"),
+                           ("int64_list", 3, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, ".fgctest.Int64List")])
+    feat.oneof_decl.add(name="kind")
+    for f in feat.field:
+        f.oneof_index = 0
+    feats = msg("Features", [("feature", 1, F.TYPE_MESSAGE, F.LABEL_REPEATED, ".fgctest.Features.FeatureEntry")])
+    entry = feats.nested_type.add(name="FeatureEntry")
+    entry.field.add(name="key", number=1, type=F.TYPE_STRING, label=F.LABEL_OPTIONAL)
+    entry.field.add(name="value", number=2, type=F.TYPE_MESSAGE, label=F.LABEL_OPTIONAL, type_name=".fgctest.Feature")
+    entry.options.map_entry = True
+    msg("Example", [("features", 1, F.TYPE_MESSAGE, F.LABEL_OPTIONAL, ".fgctest.Features")])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    return message_factory.GetMessageClass(pool.FindMessageTypeByName("fgctest.Example"))
+
+
+def test_example_encoding_matches_protobuf_runtime():
+    Example = _feature_messages()
+    feats = dict(ImageName=b"a.png", Category_id=7, Text_vocab_indices=bytes(range(15)), floats=[0.5, -2.0, 3.25],
+                 ints=[1, -1, 1 << 40], blob=os.urandom(300))
+    ex = Example()
+    for k, v in feats.items():
+        f = ex.features.feature[k]
+        if isinstance(v, bytes):
+            f.bytes_list.value.append(v)
+        elif isinstance(v, list) and isinstance(v[0], float):
+            f.float_list.value.extend(v)
+        else:
+            f.int64_list.value.extend(v if isinstance(v, list) else [v])
+    # what the runtime wrote parses here ...
+    got = TI.parse_example(ex.SerializeToString())
+    assert got["ImageName"] == b"a.png" and got["Category_id"] == [7] and got["ints"] == [1, -1, 1 << 40]
+    assert got["floats"] == [0.5, -2.0, 3.25] and got["blob"] == feats["blob"] and got["Text_vocab_indices"] == bytes(range(15))
+    # ... and what is written here parses in the runtime to the same message
+    back = Example()
+    back.ParseFromString(TI.encode_example(feats))
+    assert back == ex
+
+
+def test_decode_follows_tf1_preprocessing():
+    rng = np.random.default_rng(0)
+    feats, img, sk, text = _example(3, rng)
+    ex = TI.parse_example(TI.encode_example(feats))
+    d = TI.decode_paired_example(ex, (192, 192), dequantize=False)
+    assert d["images"].shape == (3, 192, 192) and d["sketch"].shape == (3, 192, 192) and d["images"].dtype == np.float32
+    assert d["cls"] == 2 and d["category"] == "bus" and d["name"] == "img003.png" and list(d["text"]) == list(text)
+    # BILINEAR 384 -> 192 in TF 1 (no half-pixel centres): the top-left pixel of every 2x2 block
+    sub = img[::2, ::2].astype(np.float32)
+    want = (sub - sub.min()) / (sub.max() - sub.min() + 1) * 2 - 1
+    assert np.allclose(d["images"], want.transpose(2, 0, 1), atol=1e-6)
+    # AREA: 2x2 block mean; /255*2-1
+    area = sk.astype(np.float32).reshape(192, 2, 192, 2, 3).mean(axis=(1, 3))
+    assert np.allclose(d["sketch"], (area / 255 * 2 - 1).transpose(2, 0, 1), atol=1e-6)
+    assert d["sketch"].min() >= -1 and d["sketch"].max() <= 1
+    # dequantisation noise: U(0, 1/256) before the [-1,1] map -> at most 2/256 above the noiseless value, never below
+    dn = TI.decode_paired_example(ex, (192, 192), rng=np.random.default_rng(1))
+    delta = dn["images"] - d["images"]
+    assert delta.min() >= -1e-6 and delta.max() <= 2.0 / 256 + 1e-6 and delta.std() > 1e-4
+    # generic bilinear rule at a non-integer factor against a direct evaluation
+    small = TI._resize_bilinear_tf1(img.astype(np.float32), (100, 100))
+    y, x = 37, 81
+    sy, sx = y * 3.84, x * 3.84
+    y0, x0 = int(sy), int(sx)
+    fy, fx = sy - y0, sx - x0
+    ref = (img[y0, x0] * (1 - fx) + img[y0, x0 + 1] * fx) * (1 - fy) + (img[y0 + 1, x0] * (1 - fx) + img[y0 + 1, x0 + 1] * fx) * fy
+    assert np.allclose(small[y, x], ref, atol=1e-3)
+    # distance map branch: normalised EDT of the binarised sketch
+    dm = TI.decode_paired_example(ex, (192, 192), distance_map=True, dequantize=False)
+    assert 0.95 < dm["sketch"].max() <= 1.0 and dm["sketch"].min() == pytest.approx(-1.0, abs=1e-5)   # block means of EDT / max
+
+
+def _write_split(base, mode, n_per_file, files=("bus", "car")):
+    d = os.path.join(base, "tfrecord", mode)
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(7)
+    k = 0
+    for name in files:
+        recs = []
+        for _ in range(n_per_file):
+            recs.append(TI.encode_example(_example(k, rng)[0]))
+            k += 1
+        TI.write_tfrecord(os.path.join(d, name + ".tfrecord"), recs)
+    return k
+
+
+def test_train_and_eval_queues(tmp_path):
+    base = str(tmp_path)
+    total = _write_split(base, "train", 5)
+    q = TI.PairedTrainInput(4, base, small=True, min_after_dequeue=6, seed=3, num_threads=2, prefetch=2)
+    seen = set()
+    for _ in range(12):
+        b = next(q)
+        assert b["sketch"].shape == (4, 3, 64, 64) and b["images"].shape == (4, 3, 64, 64) and b["text"].shape == (4, 15)
+        assert b["cls"].dtype == torch.int32 and b["images_d"] is b["images"] and b["cls_d"] is b["cls"]
+        assert float(b["images"].min()) >= -1.0 and float(b["images"].max()) <= 1.0
+        seen.update(b["image_names"])
+    assert len(seen) == total                               # the shuffle buffer lets every sample through
+    a, b = next(TI.PairedTrainInput(4, base, small=True, min_after_dequeue=6, seed=9)), next(TI.PairedTrainInput(4, base, small=True, min_after_dequeue=6, seed=9))
+    assert a["image_names"] == b["image_names"] and torch.equal(a["images"], b["images"])     # seeded: reproducible
+    _write_split(base, "val", 3)
+    batches = list(TI.PairedEvalInput("val", 4, base, small=True))
+    assert len(batches) == 1 and batches[0]["image_names"] == ["img000.png", "img001.png", "img002.png", "img003.png"]   # 6 // 4
+
+
+def test_validation_mode_end_to_end(tmp_path, monkeypatch):
+    """`--mode val`: ordered pass over data/tfrecord/val with a resident model -> <category>_<name>_{output,target,input}.png."""
+    from sketchyscenecolorization_b200 import main_procedure
+    from sketchyscenecolorization_b200.config import Config
+    from sketchyscenecolorization_b200.trainer import FgColorModel
+    from torch_ops import TorchOps
+    base = str(tmp_path)
+    _write_split(base, "val", 2, files=("bus",))
+    Config.set_from_dict(dict(dataset_type="val", batch_size=2, ckpt_dir=os.path.join(base, "snapshot"),
+                              results_dir=os.path.join(base, "validation_results"), data_format="NCHW", distance_map=0, small_img=1,
+                              LSTM_hybrid=1, block_type="MRU", vocab_size=58))
+    model = FgColorModel(TorchOps(torch.float64), "cpu", size=16, H=64, W=64, param_dtype=torch.float64, with_discriminator=False)
+    model.initialize(seed=1, perturb_tables=0.1)
+    n = main_procedure.validation(model=model, data_base_dir=base, noise=torch.zeros(2, 256))
+    assert n == 1
+    out = os.path.join(base, "validation_results", "with_text")
+    import cv2
+    for i in range(2):
+        for kind in ("output", "target", "input"):
+            p = os.path.join(out, "bus_img%03d_%s.png" % (i, kind))
+            assert os.path.exists(p) and cv2.imread(p).shape == (64, 64, 3)
+    # the input picture is the AREA-resized sketch: white background, dark strokes
+    inp = cv2.imread(os.path.join(out, "bus_img000_input.png"))
+    assert inp.max() >= 254 and inp.min() < 140
