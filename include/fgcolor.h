@@ -206,6 +206,20 @@ int fgc_reg_loss(const float* flat, const long long* start, const int32_t* len, 
 int fgc_adam_step(float* flat, float* grad, float* v, const long long* start, const int32_t* len, const float* reg,
                   int nchunks, float lr_t, const float* lr_t_dev, float beta2, float eps, int add_reg, fgc_stream s);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Real-data input path (input_pipeline.get_paired_input, :72-126; the queues of :131-181 batch its outputs):
+ * raw record payloads -> the tensors the graph is fed.  cartoon: uint8 [N,R,R,3] (`cartoon_data`, R = 384);
+ * sketch: uint8 (sketch_dtype 0, `sketch_data`) or fp32 (sketch_dtype 1: the 0..255 distance map the reference computes
+ * on the host with scipy through tf.py_func, :90-100) [N,R,R,3].  Per sample: image = BILINEAR resize (TF-1 legacy
+ * kernel; at the integer factors R/OH, R/OW a pixel pick), (image - min) / (max - min + 1) over the whole resized picture,
+ * + U[0, 1/256) dequantisation noise when `dequantize` (counter based: value i of splitmix64(seed), i = NCHW output
+ * index, top 24 bits * 2^-32), * 2 - 1; sketch = AREA resize (block mean) / 255 * 2 - 1.  Outputs fp32 NCHW
+ * [N,3,OH,OW].  scratch: 2*N uint32.  FGC_EUNSUPPORTED when R is not a multiple of OH and OW.
+ * -------------------------------------------------------------------------------------------------------*/
+int fgc_paired_input(const uint8_t* cartoon, const void* sketch, int sketch_dtype, int N, int R, int OH, int OW,
+                     unsigned long long seed, int dequantize, float* images, float* sketches, uint32_t* scratch,
+                     fgc_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

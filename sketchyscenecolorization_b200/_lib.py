@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libfgcolor.so")
-SOURCES = ["api.cu", "elementwise.cu", "text.cu", "sn.cu", "loss.cu", "conv_simple.cu", "conv_small.cu", "conv_tc.cu", "conv_api.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "text.cu", "sn.cu", "loss.cu", "conv_simple.cu", "conv_small.cu", "conv_tc.cu", "conv_api.cu", "input.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -106,6 +106,7 @@ SIGNATURES = {
     "fgc_nchw_to_nhwc": [_P, _I, _I, _I, _I, _P, _I, _P],
     "fgc_nhwc_to_nchw": [_P, _I, _I, _I, _I, _P, _I, _P],
     "fgc_cast": [_P, _I, _P, _I, _LL, _P],
+    "fgc_paired_input": [_P, _P, _I, _I, _I, _I, _I, C.c_ulonglong, _I, _P, _P, _P, _P],
     "fgc_l2norm_rows_fwd": [_P, _I, _I, _P, _P, _P],
     "fgc_l2norm_rows_bwd": [_P, _P, _P, _I, _I, _P, _P],
     "fgc_embedding_fwd": [_P, _P, _I, _I, _I, _I, _P, _P],

@@ -333,6 +333,18 @@ class CudaOps(OpsBase):
         check(self.lib.fgc_cast(self._p(x), self._dt(x), self._p(y), self._dt(y), x.numel(), self._s()), "cast")
         return y
 
+    # ---------------- real-data input ----------------
+    def paired_input(self, cartoon, sketch, out_hw, seed=0, dequantize=True):
+        N, R = cartoon.shape[0], cartoon.shape[1]
+        assert cartoon.dtype == torch.uint8 and cartoon.shape == (N, R, R, 3) and sketch.shape == cartoon.shape
+        assert sketch.dtype in (torch.uint8, torch.float32)
+        images, sketches = self._empty((N, 3) + tuple(out_hw), torch.float32), self._empty((N, 3) + tuple(out_hw), torch.float32)
+        scratch = self._empty((2 * N,), torch.int32)
+        check(self.lib.fgc_paired_input(self._p(cartoon), self._p(sketch), 0 if sketch.dtype == torch.uint8 else 1, N, R,
+                                        out_hw[0], out_hw[1], int(seed) & 0xFFFFFFFFFFFFFFFF, 1 if dequantize else 0,
+                                        self._p(images), self._p(sketches), self._p(scratch), self._s()), "paired_input")
+        return images, sketches
+
     # ---------------- text fusion ----------------
     def _dst(self, out, shape, dtype=torch.float32):
         if out is None:

@@ -88,7 +88,7 @@ def train(**kwargs):
     if (q1 is None or q2 is None) and os.path.isdir(rec_dir) and os.listdir(rec_dir):
         # the reference's two independent TFRecord shuffle queues (main_procedure.py:109-122)
         from .tfrecord_input import PairedTrainInput
-        mk = lambda seed: PairedTrainInput(batch_size, kwargs.get('data_base_dir', 'data'), small=small,      # noqa: E731
+        mk = lambda seed: PairedTrainInput(batch_size, model.ops, kwargs.get('data_base_dir', 'data'), small=small,      # noqa: E731
                                            distance_map=Config.distance_map != 0, seed=seed)
         q1, q2 = q1 or mk(1234 + rank), q2 or mk(4321 + rank)
     else:                                 # the dataset is not part of the reference repository: seeded synthetic batches
@@ -221,7 +221,7 @@ def validation(**kwargs):
         if prefix is None:
             raise RuntimeError("no snapshot in %s" % Config.ckpt_dir)
         checkpoint.restore(model, prefix, strict=True)
-    queue = PairedEvalInput(Config.dataset_type, batch_size, data_base_dir=kwargs.get('data_base_dir', 'data'), small=small,
+    queue = PairedEvalInput(Config.dataset_type, batch_size, model.ops, data_base_dir=kwargs.get('data_base_dir', 'data'), small=small,
                             distance_map=Config.distance_map != 0)
     counter, prev_time = 0, float("-inf")
     for b in queue:

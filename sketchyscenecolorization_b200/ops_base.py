@@ -151,6 +151,13 @@ class OpsBase:
     def cast(self, x, dtype):
         raise NotImplementedError
 
+    # ---------------- real-data input (input_pipeline.get_paired_input, :72-126) ----------------
+    def paired_input(self, cartoon, sketch, out_hw, seed=0, dequantize=True):
+        """cartoon uint8 [N,R,R,3], sketch uint8 | fp32 (0..255 distance map) [N,R,R,3] on the op device ->
+        (images, sketches) fp32 NCHW [N,3,H,W] in [-1,1]: image picked at the integer resize factor (TF-1 BILINEAR),
+        min-max normalised per picture, + U[0,1/256) noise, sketch block mean (AREA)."""
+        raise NotImplementedError
+
     # ---------------- text fusion (models_collection.encode_feat_with_text, :150-248) ----------------
     def l2norm_rows_fwd(self, x, out=None):
         """rows [R,D] fp32: (x * rsqrt(max(sum x^2,1e-12)), inv[R]).  `out`: optional destination of the normalised rows

@@ -14,6 +14,12 @@ File format (tensorflow/core/lib/io/record_writer.cc, example.proto, feature.pro
     Example = { Features features = 1 { map<string, Feature> feature = 1 } }
     Feature = oneof { BytesList bytes_list = 1; FloatList float_list = 2 (packed floats); Int64List int64_list = 3 (packed varints) }
 
+Split of the work: the record framing, the proto parsing, the shuffle queue and (only with --distance_map 1) scipy's
+distance transform -- which the reference also runs on the host, through tf.py_func -- stay on host threads; everything
+per pixel (resize, min-max normalisation, dequantisation noise, [-1,1] map, NCHW transpose) is one device call per batch,
+`fgc_paired_input` (csrc/input.cu) behind `ops.paired_input`.  There is no host implementation of that step in this
+package (the tests check the kernel against a numpy restatement kept outside it).
+
 TF-1 resize semantics that matter at 384 -> 192 (legacy kernels, align_corners = False, no half-pixel centres): the source
 coordinate of output pixel y is 2*y exactly, so BILINEAR picks the top-left pixel of each 2x2 block, while AREA averages
 the block.  The framing and the proto encoding are pinned against tensorboard's independent TFRecord writer and its
@@ -131,55 +137,28 @@ def parse_example(buf):
 
 
 # ----------------------------------------------------------------------------------------------------------
-# get_paired_input
+# get_paired_input: the record fields on the host, the per-pixel work in one device pass per batch
 # ----------------------------------------------------------------------------------------------------------
-def _resize_bilinear_tf1(img, out_hw):
-    """tf.image.resize_images(BILINEAR), TF-1 legacy kernel: src = dst * (in / out), no half-pixel offset."""
-    H, W = img.shape[:2]
-    oh, ow = out_hw
-    ys, xs = np.arange(oh) * (H / oh), np.arange(ow) * (W / ow)
-    y0, x0 = np.floor(ys).astype(int), np.floor(xs).astype(int)
-    y1, x1 = np.minimum(y0 + 1, H - 1), np.minimum(x0 + 1, W - 1)
-    fy, fx = (ys - y0)[:, None, None], (xs - x0)[None, :, None]
-    top = img[y0][:, x0] * (1 - fx) + img[y0][:, x1] * fx
-    bot = img[y1][:, x0] * (1 - fx) + img[y1][:, x1] * fx
-    return (top * (1 - fy) + bot * fy).astype(np.float32)
+def distance_map_255(sketch_u8):
+    """:90-100 (Config.pre_calculated_dist_map is False): binarise at 250, Euclidean distance transform, scale so the
+    maximum is 255.  The reference runs exactly this on the host too (scipy inside tf.py_func); float32 [R,R,3]."""
+    from scipy import ndimage
+    binar = np.where(sketch_u8 < 250, 0.0, 255.0).astype(np.float32)
+    dist = ndimage.distance_transform_edt(binar).astype(np.float32)
+    return dist / dist.max() * np.float32(255.)
 
 
-def _resize_area(img, out_hw):
-    """tf.image.resize_images(AREA) at an integer factor: block mean."""
-    H, W, C = img.shape
-    oh, ow = out_hw
-    if H % oh or W % ow:
-        raise NotImplementedError("AREA resize at a non-integer factor (%dx%d -> %dx%d)" % (H, W, oh, ow))
-    return img.reshape(oh, H // oh, ow, W // ow, C).mean(axis=(1, 3)).astype(np.float32)
-
-
-def decode_paired_example(ex, img_dim=(192, 192), distance_map=False, rng=None, dequantize=True):
-    """One parsed Example -> dict(images, sketch [3,H,W] float32 in [-1,1], cls int, category, name, color_text (str),
-    text int32 [15]) -- get_paired_input (:45-126), NCHW."""
-    image = np.frombuffer(ex['cartoon_data'], dtype=np.uint8).astype(np.float32).reshape(RAW, RAW, 3)
-    sketch = np.frombuffer(ex['sketch_data'], dtype=np.uint8).astype(np.float32).reshape(RAW, RAW, 3)
-    if distance_map:                                        # :90-100 (Config.pre_calculated_dist_map is False)
-        from scipy import ndimage
-        sketch = np.where(sketch < 250, 0.0, 255.0).astype(np.float32)
-        sketch = ndimage.distance_transform_edt(sketch).astype(np.float32)
-        sketch = sketch / sketch.max() * 255.
-    if RAW != img_dim[0] and RAW != img_dim[1]:             # :103-105
-        image = _resize_bilinear_tf1(image, img_dim)
-        sketch = _resize_area(sketch, img_dim)
-    image = (image - image.min()) / (image.max() - image.min() + 1)
-    if dequantize:                                          # tf.random_uniform(0, 1/256), :116
-        rng = rng or np.random.default_rng()
-        image = image + rng.random(image.shape, dtype=np.float32) * (1. / 256)
-    sketch = sketch / 255.
-    image, sketch = image * 2. - 1, sketch * 2. - 1
+def raw_paired_example(ex, distance_map=False):
+    """One parsed Example -> the raw sample: cartoon uint8 [384,384,3], sketch uint8 [384,384,3] (float32 0..255 distance
+    map when `distance_map`), cls, category, name, color_text, text int32 [15] (:72-88, :117-124)."""
+    cartoon = np.frombuffer(ex['cartoon_data'], dtype=np.uint8).reshape(RAW, RAW, 3)
+    sketch = np.frombuffer(ex['sketch_data'], dtype=np.uint8).reshape(RAW, RAW, 3)
+    if distance_map:
+        sketch = distance_map_255(sketch)
     text = np.frombuffer(ex['Text_vocab_indices'], dtype=np.uint8).astype(np.int32).reshape(TEXT_LEN)
     cid = ex['Category_id']
-    return dict(images=np.ascontiguousarray(image.transpose(2, 0, 1), dtype=np.float32),
-                sketch=np.ascontiguousarray(sketch.transpose(2, 0, 1), dtype=np.float32),
-                cls=int(cid[0] if isinstance(cid, list) else cid), category=ex['Category'].decode(), name=ex['ImageName'].decode(),
-                color_text=ex['Color_text'].decode(), text=text)
+    return dict(cartoon=cartoon, sketch=sketch, cls=int(cid[0] if isinstance(cid, list) else cid), category=ex['Category'].decode(),
+                name=ex['ImageName'].decode(), color_text=ex['Color_text'].decode(), text=text)
 
 
 def _record_files(data_base_dir, mode):
@@ -189,10 +168,17 @@ def _record_files(data_base_dir, mode):
     return files
 
 
-def _stack(samples, want_d=False):
-    out = dict(sketch=torch.from_numpy(np.stack([s['sketch'] for s in samples])),
-               images=torch.from_numpy(np.stack([s['images'] for s in samples])),
-               cls=torch.tensor([s['cls'] for s in samples], dtype=torch.int32),
+def _device_batch(samples, ops, dim, seed, dequantize=True, want_d=False):
+    """Raw samples -> the batch dict of the queues.  The uint8 payloads are stacked into (pinned) host memory, copied to the
+    device of `ops` and resized / normalised / dequantised / transposed there by ONE call (ops.paired_input ->
+    fgc_paired_input): 0.88 MB per sample cross the bus instead of the 0.88 MB of fp32 results plus the host arithmetic."""
+    dev = torch.device(getattr(ops, 'device', 'cpu'))
+    cartoon = torch.from_numpy(np.stack([s['cartoon'] for s in samples]))
+    sketch = torch.from_numpy(np.stack([s['sketch'] for s in samples]))
+    if dev.type == 'cuda':
+        cartoon, sketch = cartoon.pin_memory().to(dev, non_blocking=True), sketch.pin_memory().to(dev, non_blocking=True)
+    images, sketches = ops.paired_input(cartoon, sketch, dim, seed=seed, dequantize=dequantize)
+    out = dict(sketch=sketches, images=images, cls=torch.tensor([s['cls'] for s in samples], dtype=torch.int32),
                text=torch.from_numpy(np.stack([s['text'] for s in samples])),
                categories=[s['category'] for s in samples], image_names=[s['name'] for s in samples],
                color_texts=[s['color_text'] for s in samples])
@@ -204,14 +190,15 @@ def _stack(samples, want_d=False):
 class PairedTrainInput:
     """build_input_queue_paired('train') (:131-157): an endless shuffled stream of batches.  Files are visited in a
     shuffled order every epoch (string_input_producer(shuffle=True)); samples pass through a shuffle buffer that holds
-    at least `min_after_dequeue` decoded samples before one is drawn at random (tf.train.shuffle_batch).  Decoding runs
-    in `num_threads` host threads (numpy releases the GIL), `prefetch` batches ahead of the consumer.  Under data
+    at least `min_after_dequeue` records before one is drawn at random (tf.train.shuffle_batch).  Record parsing (and the
+    distance transform, when asked for) runs in `num_threads` host threads, `prefetch` batches ahead of the consumer; the
+    pixel work of a batch is one device call on the consumer's stream (`ops`: the model's operator set).  Under data
     parallelism give every rank its own `seed`.  main_procedure.train uses two of these (the second feeds images_d)."""
 
-    def __init__(self, batch_size, data_base_dir='data', small=False, distance_map=False, min_after_dequeue=512, seed=0,
+    def __init__(self, batch_size, ops, data_base_dir='data', small=False, distance_map=False, min_after_dequeue=512, seed=0,
                  num_threads=4, prefetch=4, mode='train'):
         from concurrent.futures import ThreadPoolExecutor
-        self.n, self.dim, self.dm = batch_size, ((64, 64) if small else (192, 192)), distance_map
+        self.n, self.ops, self.dim, self.dm = batch_size, ops, ((64, 64) if small else (192, 192)), distance_map
         self.files = _record_files(data_base_dir, mode)
         if not self.files:
             raise FileNotFoundError("no TFRecord files under %s" % os.path.join(data_base_dir, 'tfrecord', mode))
@@ -239,9 +226,8 @@ class PairedTrainInput:
 
     def _submit(self):
         raws = [self._draw_raw() for _ in range(self.n)]
-        seeds = self.rng.integers(1 << 62, size=self.n)
-        return [self.pool.submit(lambda r, s: decode_paired_example(parse_example(r), self.dim, self.dm, np.random.default_rng(s)),
-                                 r, s) for r, s in zip(raws, seeds)]
+        seed = int(self.rng.integers(1 << 62))              # the batch's dequantisation-noise stream
+        return seed, [self.pool.submit(lambda r: raw_paired_example(parse_example(r), self.dm), r) for r in raws]
 
     def __iter__(self):
         return self
@@ -249,25 +235,24 @@ class PairedTrainInput:
     def __next__(self):
         while len(self.pending) < self.prefetch:
             self.pending.append(self._submit())
-        futs = self.pending.pop(0)
-        return _stack([f.result() for f in futs], want_d=True)
+        seed, futs = self.pending.pop(0)
+        return _device_batch([f.result() for f in futs], self.ops, self.dim, seed, want_d=True)
 
 
 class PairedEvalInput:
     """build_input_queue_paired_test('val' | 'test') (:160-181): one ordered epoch; the last partial batch is dropped as
     tf.train.batch does."""
 
-    def __init__(self, mode, batch_size, data_base_dir='data', small=False, distance_map=False):
+    def __init__(self, mode, batch_size, ops, data_base_dir='data', small=False, distance_map=False):
         assert mode in ('test', 'val')
-        self.n, self.dim, self.dm = batch_size, ((64, 64) if small else (192, 192)), distance_map
+        self.n, self.ops, self.dim, self.dm = batch_size, ops, ((64, 64) if small else (192, 192)), distance_map
         self.files = _record_files(data_base_dir, mode)
 
     def __iter__(self):
-        batch = []
+        batch, k = [], 0
         for f in self.files:
             for rec in read_tfrecord(f):
-                batch.append(decode_paired_example(parse_example(rec), self.dim, self.dm, dequantize=True,
-                                                   rng=np.random.default_rng(len(batch))))
+                batch.append(raw_paired_example(parse_example(rec), self.dm))
                 if len(batch) == self.n:
-                    yield _stack(batch)
-                    batch = []
+                    yield _device_batch(batch, self.ops, self.dim, seed=k)
+                    batch, k = [], k + 1

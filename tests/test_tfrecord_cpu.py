@@ -100,35 +100,54 @@ def test_example_encoding_matches_protobuf_runtime():
 
 
 def test_decode_follows_tf1_preprocessing():
+    """The raw-sample view of a record, and the oracle restatement of get_paired_input's pixel work (the checker of
+    fgc_paired_input; the product has no host implementation of it)."""
+    from oracle import input_oracle as IO
     rng = np.random.default_rng(0)
     feats, img, sk, text = _example(3, rng)
     ex = TI.parse_example(TI.encode_example(feats))
-    d = TI.decode_paired_example(ex, (192, 192), dequantize=False)
-    assert d["images"].shape == (3, 192, 192) and d["sketch"].shape == (3, 192, 192) and d["images"].dtype == np.float32
-    assert d["cls"] == 2 and d["category"] == "bus" and d["name"] == "img003.png" and list(d["text"]) == list(text)
+    raw = TI.raw_paired_example(ex)
+    assert raw["cartoon"].dtype == np.uint8 and np.array_equal(raw["cartoon"], img) and np.array_equal(raw["sketch"], sk)
+    assert raw["cls"] == 2 and raw["category"] == "bus" and raw["name"] == "img003.png" and list(raw["text"]) == list(text)
+    images, sketch = IO.paired_preprocess(raw["cartoon"], raw["sketch"], (192, 192))
+    assert images.shape == (3, 192, 192) and sketch.shape == (3, 192, 192) and images.dtype == np.float32
     # BILINEAR 384 -> 192 in TF 1 (no half-pixel centres): the top-left pixel of every 2x2 block
     sub = img[::2, ::2].astype(np.float32)
     want = (sub - sub.min()) / (sub.max() - sub.min() + 1) * 2 - 1
-    assert np.allclose(d["images"], want.transpose(2, 0, 1), atol=1e-6)
+    assert np.allclose(images, want.transpose(2, 0, 1), atol=1e-6)
     # AREA: 2x2 block mean; /255*2-1
     area = sk.astype(np.float32).reshape(192, 2, 192, 2, 3).mean(axis=(1, 3))
-    assert np.allclose(d["sketch"], (area / 255 * 2 - 1).transpose(2, 0, 1), atol=1e-6)
-    assert d["sketch"].min() >= -1 and d["sketch"].max() <= 1
-    # dequantisation noise: U(0, 1/256) before the [-1,1] map -> at most 2/256 above the noiseless value, never below
-    dn = TI.decode_paired_example(ex, (192, 192), rng=np.random.default_rng(1))
-    delta = dn["images"] - d["images"]
+    assert np.allclose(sketch, (area / 255 * 2 - 1).transpose(2, 0, 1), atol=1e-6)
+    assert sketch.min() >= -1 and sketch.max() <= 1
+    # dequantisation noise: U[0, 1/256) before the [-1,1] map -> at most 2/256 above the noiseless value, never below
+    noise = IO.splitmix_noise(1, 3 * 192 * 192)
+    assert noise.min() >= 0 and noise.max() < 1 / 256 and abs(noise.mean() - 0.5 / 256) < 2e-5 and len(np.unique(noise)) > 100000
+    assert np.array_equal(IO.splitmix_noise(1, 10, offset=5), noise[5:15])
+    dn, _ = IO.paired_preprocess(raw["cartoon"], raw["sketch"], (192, 192), noise.reshape(3, 192, 192))
+    delta = dn - images
     assert delta.min() >= -1e-6 and delta.max() <= 2.0 / 256 + 1e-6 and delta.std() > 1e-4
+    # splitmix64 known answers (seed 1234567: the published reference outputs of the generator)
+    with np.errstate(over="ignore"):
+        i = np.arange(2, dtype=np.uint64)
+        z = np.uint64(1234567) + (i + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    assert [int(v) for v in z] == [6457827717110365317, 3203168211198807973]
+    assert np.array_equal(IO.splitmix_noise(1234567, 2), (z >> np.uint64(40)).astype(np.float32) * np.float32(2.0 ** -32))
     # generic bilinear rule at a non-integer factor against a direct evaluation
-    small = TI._resize_bilinear_tf1(img.astype(np.float32), (100, 100))
+    small = IO.resize_bilinear_tf1(img.astype(np.float32), (100, 100))
     y, x = 37, 81
     sy, sx = y * 3.84, x * 3.84
     y0, x0 = int(sy), int(sx)
     fy, fx = sy - y0, sx - x0
     ref = (img[y0, x0] * (1 - fx) + img[y0, x0 + 1] * fx) * (1 - fy) + (img[y0 + 1, x0] * (1 - fx) + img[y0 + 1, x0 + 1] * fx) * fy
     assert np.allclose(small[y, x], ref, atol=1e-3)
-    # distance map branch: normalised EDT of the binarised sketch
-    dm = TI.decode_paired_example(ex, (192, 192), distance_map=True, dequantize=False)
-    assert 0.95 < dm["sketch"].max() <= 1.0 and dm["sketch"].min() == pytest.approx(-1.0, abs=1e-5)   # block means of EDT / max
+    # distance map branch: normalised EDT of the binarised sketch (host work in the reference as well), then the same pass
+    dm = TI.raw_paired_example(ex, distance_map=True)["sketch"]
+    assert dm.dtype == np.float32 and dm.max() == pytest.approx(255.0) and dm.min() == 0.0
+    _, dms = IO.paired_preprocess(raw["cartoon"], dm, (192, 192))
+    assert 0.95 < dms.max() <= 1.0 and dms.min() == pytest.approx(-1.0, abs=1e-5)   # block means of EDT / max
 
 
 def _write_split(base, mode, n_per_file, files=("bus", "car")):
@@ -148,7 +167,9 @@ def _write_split(base, mode, n_per_file, files=("bus", "car")):
 def test_train_and_eval_queues(tmp_path):
     base = str(tmp_path)
     total = _write_split(base, "train", 5)
-    q = TI.PairedTrainInput(4, base, small=True, min_after_dequeue=6, seed=3, num_threads=2, prefetch=2)
+    from torch_ops import TorchOps
+    ops = TorchOps(torch.float32)
+    q = TI.PairedTrainInput(4, ops, base, small=True, min_after_dequeue=6, seed=3, num_threads=2, prefetch=2)
     seen = set()
     for _ in range(12):
         b = next(q)
@@ -157,10 +178,10 @@ def test_train_and_eval_queues(tmp_path):
         assert float(b["images"].min()) >= -1.0 and float(b["images"].max()) <= 1.0
         seen.update(b["image_names"])
     assert len(seen) == total                               # the shuffle buffer lets every sample through
-    a, b = next(TI.PairedTrainInput(4, base, small=True, min_after_dequeue=6, seed=9)), next(TI.PairedTrainInput(4, base, small=True, min_after_dequeue=6, seed=9))
+    a, b = next(TI.PairedTrainInput(4, ops, base, small=True, min_after_dequeue=6, seed=9)), next(TI.PairedTrainInput(4, ops, base, small=True, min_after_dequeue=6, seed=9))
     assert a["image_names"] == b["image_names"] and torch.equal(a["images"], b["images"])     # seeded: reproducible
     _write_split(base, "val", 3)
-    batches = list(TI.PairedEvalInput("val", 4, base, small=True))
+    batches = list(TI.PairedEvalInput("val", 4, ops, base, small=True))
     assert len(batches) == 1 and batches[0]["image_names"] == ["img000.png", "img001.png", "img002.png", "img003.png"]   # 6 // 4
 
 

@@ -243,6 +243,12 @@ class TorchOps(OpsBase):
             dtype = self.cdt
         return x.to(dtype)
 
+    # ---- real-data input: the CPU oracle's restatement of get_paired_input
+    def paired_input(self, cartoon, sketch, out_hw, seed=0, dequantize=True):
+        from oracle import input_oracle
+        im, sk = input_oracle.paired_input(cartoon.cpu().numpy(), sketch.cpu().numpy(), tuple(out_hw), seed, dequantize)
+        return torch.from_numpy(im), torch.from_numpy(sk)
+
     # ---- text fusion
     @staticmethod
     def _into(out, val):
