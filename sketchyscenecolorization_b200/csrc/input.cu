@@ -98,17 +98,65 @@ __global__ void __launch_bounds__(256) paired_apply_kernel(const uint8_t* __rest
   }
 }
 
-// the production shape, 384 -> 192 with uint8 sketches: one thread per FOUR output pixels -- 24 contiguous source bytes
-// per row as three 8-byte loads (one cartoon row, two sketch rows), one 16-byte store per channel plane and tensor
+// ---- the production shape, 384 -> 192 with uint8 sketches: factor 2, rows 8-byte aligned -----------------------------------
+// One thread per FOUR output pixels: 24 contiguous source bytes per row as three 8-byte loads (one cartoon row, two sketch
+// rows), one 16-byte store per channel plane and tensor.  Every value a pixel can take is tabulated once per CTA in shared
+// memory -- the normalised picture value of each of the 256 byte values, the final sketch value of each of the 1021 possible
+// 2x2 sums -- with exactly the roundings of the generic kernel, so the per-element IEEE divisions (which kept the first
+// version issue-bound, ncu r1s: 78% issue slots, 3.8 TB/s) become table reads.
+__global__ void __launch_bounds__(256) paired_minmax2_kernel(const uint8_t* __restrict__ cartoon, int R, int OH, int OW,
+                                                             uint32_t* __restrict__ scratch) {
+  const int n = blockIdx.y;
+  const uint8_t* img = cartoon + (size_t)n * R * R * 3;
+  const int QW = OW / 4;
+  unsigned mn = 255u, mx = 0u;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < OH * QW; t += gridDim.x * blockDim.x) {
+    const int oy = t / QW, ox = (t % QW) * 4;
+    union { uint2 v[3]; uint8_t b[24]; } a;
+    const uint2* pa = reinterpret_cast<const uint2*>(img + ((size_t)(2 * oy) * R + 2 * ox) * 3);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) a.v[i] = __ldg(pa + i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        unsigned v = a.b[6 * j + c];
+        mn = min(mn, v);
+        mx = max(mx, v);
+      }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ unsigned smn[8], smx[8];
+  if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { mn = min(mn, smn[w]); mx = max(mx, smx[w]); }
+    if (mn <= mx) {
+      atomicMax(scratch + 2 * n, enc_min((float)mn));
+      atomicMax(scratch + 2 * n + 1, __float_as_uint((float)mx));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) paired_apply2_kernel(const uint8_t* __restrict__ cartoon, const uint8_t* __restrict__ sketch,
                                                             int R, int OH, int OW, const uint32_t* __restrict__ scratch,
                                                             unsigned long long seed, int dequantize, float* __restrict__ images,
                                                             float* __restrict__ sketches) {
+  __shared__ float t_img[256];      // (v - min) / (max - min + 1), before the noise
+  __shared__ float t_sk[1024];      // sum of a 2x2 block (0..1020) -> mean / 255 * 2 - 1
   const int n = blockIdx.y;
   const uint8_t* img = cartoon + (size_t)n * R * R * 3;
   const uint8_t* sk = sketch + (size_t)n * R * R * 3;
   const float mn = dec_min(__ldg(scratch + 2 * n)), mx = __uint_as_float(__ldg(scratch + 2 * n + 1));
   const float den = __fadd_rn(__fsub_rn(mx, mn), 1.f);
+  for (int v = threadIdx.x; v < 256; v += blockDim.x) t_img[v] = __fdiv_rn(__fsub_rn((float)v, mn), den);
+  for (int v = threadIdx.x; v < 1024; v += blockDim.x)
+    t_sk[v] = __fmaf_rn(__fdiv_rn(__fmul_rn((float)v, 0.25f), 255.f), 2.f, -1.f);
+  __syncthreads();
   const size_t plane = (size_t)OH * OW;
   const int QW = OW / 4;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < OH * QW; t += gridDim.x * blockDim.x) {
@@ -125,12 +173,10 @@ __global__ void __launch_bounds__(256) paired_apply2_kernel(const uint8_t* __res
       float im[4], sq[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float q = __fdiv_rn(__fsub_rn((float)a.b[6 * j + c], mn), den);
+        float q = t_img[a.b[6 * j + c]];
         if (dequantize) q = __fadd_rn(q, (float)noise24(seed, o + j) * (1.f / 4294967296.f));
         im[j] = __fmaf_rn(q, 2.f, -1.f);
-        float acc = __fadd_rn(__fadd_rn((float)s0.b[6 * j + c], (float)s0.b[6 * j + 3 + c]),
-                              __fadd_rn((float)s1.b[6 * j + c], (float)s1.b[6 * j + 3 + c]));
-        sq[j] = __fmaf_rn(__fdiv_rn(__fmul_rn(acc, 0.25f), 255.f), 2.f, -1.f);
+        sq[j] = t_sk[(unsigned)s0.b[6 * j + c] + s0.b[6 * j + 3 + c] + s1.b[6 * j + c] + s1.b[6 * j + 3 + c]];
       }
       *reinterpret_cast<float4*>(images + o) = make_float4(im[0], im[1], im[2], im[3]);
       *reinterpret_cast<float4*>(sketches + o) = make_float4(sq[0], sq[1], sq[2], sq[3]);
@@ -155,15 +201,20 @@ extern "C" int fgc_paired_input(const uint8_t* cartoon, const void* sketch, int 
   if (cudaMemsetAsync(scratch, 0, sizeof(uint32_t) * 2 * (size_t)N, s) != cudaSuccess) return check_launch("paired_input memset");
   const int fy = R / OH, fx = R / OW;
   const int px = OH * OW;
-  dim3 grid1(max(1, min(cdiv(px, 256 * 4), 64)), N);
-  paired_minmax_kernel<<<grid1, 256, 0, s>>>(cartoon, R, OH, OW, fy, fx, scratch);
-  count_launch();
-  FGC_LAUNCH_CHECK("paired_minmax");
   const bool fast = sketch_dtype == 0 && fy == 2 && fx == 2 && OW % 4 == 0 && R % 8 == 0 && (reinterpret_cast<uintptr_t>(cartoon) & 7) == 0 &&
                     (reinterpret_cast<uintptr_t>(sketch) & 7) == 0 && (reinterpret_cast<uintptr_t>(images) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(sketches) & 15) == 0;
+  if (fast) {        // ~3 loop trips per thread amortise the tables; 12 x N CTAs cover the 148 SMs from N = 13 up
+    dim3 grid(max(1, min(cdiv(px / 4, 256), N >= 32 ? 12 : 36)), N);
+    paired_minmax2_kernel<<<grid, 256, 0, s>>>(cartoon, R, OH, OW, scratch);
+  } else {
+    dim3 grid1(max(1, min(cdiv(px, 256 * 4), 64)), N);
+    paired_minmax_kernel<<<grid1, 256, 0, s>>>(cartoon, R, OH, OW, fy, fx, scratch);
+  }
+  count_launch();
+  FGC_LAUNCH_CHECK("paired_minmax");
   if (fast) {
-    dim3 grid(max(1, cdiv(px / 4, 256)), N);
+    dim3 grid(max(1, min(cdiv(px / 4, 256), N >= 32 ? 12 : 36)), N);
     paired_apply2_kernel<<<grid, 256, 0, s>>>(cartoon, (const uint8_t*)sketch, R, OH, OW, scratch, seed, dequantize, images, sketches);
   } else {
     dim3 grid(max(1, cdiv(px, 256)), N);
