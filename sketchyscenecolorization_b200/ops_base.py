@@ -151,6 +151,30 @@ class OpsBase:
     def cast(self, x, dtype):
         raise NotImplementedError
 
+    # ---------------- 4x4 convolutions of the Pix2Pix / Residual variants in phase form (models_collection.py:380-405) ------
+    def space_to_depth(self, x):
+        """[N,2h,2w,C] -> [N,h,w,4C], channel (py*2+px)*C + c = pixel (2y+py, 2x+px) (tf.space_to_depth order)."""
+        raise NotImplementedError
+
+    def depth_to_space(self, x):
+        """Inverse of space_to_depth: [N,h,w,4C] -> [N,2h,2w,C]."""
+        raise NotImplementedError
+
+    def phase_weights(self, f, mode):
+        """4x4 filter -> the odd-size filter of the equivalent stride-1 SAME convolution (fp32, zero where no tap lands):
+        mode 'conv'   f [4,4,C,Co] (stride 2, pad 1)              -> [3,3,4C,Co] over space_to_depth(x);
+        mode 'deconv' f [4,4,Co,C] (conv2d_transpose, stride 2)   -> [3,3,C,4Co], output through depth_to_space;
+        mode 'k5'     f [4,4,C,Co] (stride 1, pad 1: H -> H-1)    -> [5,5,C,Co], output cropped by one row / column."""
+        raise NotImplementedError
+
+    def phase_wgrad(self, dw, df, mode):
+        """df += the entries of dw (gradient of the expanded filter) at the positions phase_weights writes."""
+        raise NotImplementedError
+
+    def copy_rect(self, x, H, W):
+        """[N,h,w,C] -> [N,H,W,C]: the overlapping top-left rectangle is copied, the rest is zero (crop or zero-pad)."""
+        raise NotImplementedError
+
     # ---------------- real-data input (input_pipeline.get_paired_input, :72-126) ----------------
     def paired_input(self, cartoon, sketch, out_hw, seed=0, dequantize=True):
         """cartoon uint8 [N,R,R,3], sketch uint8 | fp32 (0..255 distance map) [N,R,R,3] on the op device ->

@@ -133,6 +133,65 @@ def discriminator_vars(size=64):
     return v
 
 
+# ------------------------------------------------------------------------------------------------
+# --block_type Pix2Pix (models_collection.py:380-538, 789-841): 4x4 filters without bias or regulariser, plain batch norm
+# (`offset` zeros, `scale` N(1, 0.02), created directly in the layer scope), the text LSTM / noise FC / SN class head of
+# the MRU variant under the same names
+# ------------------------------------------------------------------------------------------------
+def pix2pix_enc_channels(size):
+    return [size, size * 2, size * 4, size * 8, size * 8]
+
+
+def pix2pix_dec_channels(size):
+    return [size * 8, size * 4, size * 2, size]
+
+
+def _bn(scope, c):
+    return [VarSpec(scope + "/offset", (c,), ("const", 0.0)), VarSpec(scope + "/scale", (c,), ("normal1", 0.02))]
+
+
+def pix2pix_generator_vars(size=64, vocab_size=58, H=192, W=192):
+    assert H % 32 == 0 and W % 32 == 0, "image size must be a multiple of 32"
+    p = "generator"
+    ch = pix2pix_enc_channels(size)
+    v = [VarSpec(p + "/encoder_1/conv/filter", (4, 4, 3, ch[0]), ("normal", 0.02))]
+    for k in range(2, 6):
+        v.append(VarSpec(p + "/encoder_%d/conv/filter" % k, (4, 4, ch[k - 2], ch[k - 1]), ("normal", 0.02)))
+        v += _bn(p + "/encoder_%d" % k, ch[k - 1])
+    d = ch[4]
+    v.append(VarSpec(p + "/TextLSTM/embedding", (vocab_size, d), ("uniform", 0.08)))
+    for cell, kin in (("WLSTM", 2 * d), ("ALSTM", 4 * d)):
+        b = p + "/TextLSTM/RNN/%s/multi_rnn_cell/cell_0/basic_lstm_cell" % cell
+        v.append(VarSpec(b + "/kernel", (kin, 4 * d), ("glorot_uniform", None)))
+        v.append(VarSpec(b + "/bias", (4 * d,), ("const", 0.0)))
+    nfc = (d // 8) * (H // 32) * (W // 32)
+    v.append(VarSpec(p + "/fully_connected/weights", (NOISE_DIM, nfc), ("xavier", None), reg=1e-6))
+    v.append(VarSpec(p + "/fully_connected/biases", (nfc,), ("const", 0.0)))
+    cin = d + d // 8
+    for i, co in enumerate(pix2pix_dec_channels(size)):
+        k = 5 - i
+        v.append(VarSpec(p + "/decoder_%d/deconv/filter" % k, (4, 4, co, cin), ("normal", 0.02)))
+        v += _bn(p + "/decoder_%d" % k, co)
+        cin = co + ch[k - 2]
+    v.append(VarSpec(p + "/decoder_1/deconv/filter", (4, 4, 3, cin), ("normal", 0.02)))
+    return v
+
+
+def pix2pix_discriminator_vars(size=64):
+    p = "discriminator"
+    chans = [6, size, size * 2, size * 4, size * 8, 1]
+    v = []
+    for k in range(1, 6):
+        v.append(VarSpec(p + "/layer_%d/conv/filter" % k, (4, 4, chans[k - 1], chans[k]), ("normal", 0.02)))
+        if 2 <= k <= 4:
+            v += _bn(p + "/layer_%d" % k, chans[k])
+    fc = p + "/fully_connected"
+    v.append(VarSpec(fc + "/weights", (chans[4], NUM_CLASSES), ("xavier", None), reg=1e-6, sn=True))
+    v.append(VarSpec(fc + "/" + fc + "/u", (1, NUM_CLASSES), ("trunc_normal", 1.0), trainable=False))
+    v.append(VarSpec(fc + "/biases", (NUM_CLASSES,), ("const", 0.0)))
+    return v
+
+
 class ParamStore:
     """Flat fp32 parameter / gradient / Adam-v buffers of one network plus named views."""
 
@@ -204,6 +263,8 @@ class ParamStore:
             shape = s.shape
             if kind == "normal":
                 t = torch.randn(shape, generator=g, dtype=f64) * arg
+            elif kind == "normal1":
+                t = 1.0 + torch.randn(shape, generator=g, dtype=f64) * arg
             elif kind == "trunc_normal":
                 t = torch.randn(shape, generator=g, dtype=f64)
                 for _ in range(8):

@@ -18,7 +18,8 @@ import torch
 
 from .discriminator import Discriminator
 from .generator import Generator
-from .params import ParamStore, discriminator_vars, generator_vars
+from .params import (ParamStore, discriminator_vars, generator_vars, pix2pix_discriminator_vars, pix2pix_generator_vars)
+from .pix2pix import Pix2PixDiscriminator, Pix2PixGenerator
 
 
 def lr_decay(counter, max_iter):
@@ -30,15 +31,18 @@ class FgColorModel:
     """Generator + discriminator + parameter stores on one device."""
 
     def __init__(self, ops, device, *, size=64, H=192, W=192, vocab_size=58, lstm_hybrid=True,
-                 param_dtype=torch.float32, with_discriminator=True):
-        self.ops, self.device, self.size, self.H, self.W = ops, device, size, H, W
-        self.gstore = ParamStore(generator_vars(size, vocab_size, H, W), device, param_dtype)
-        self.G = Generator(ops, self.gstore, size, lstm_hybrid)
+                 param_dtype=torch.float32, with_discriminator=True, block_type='MRU'):
+        if block_type not in ('MRU', 'Pix2Pix'):
+            raise NotImplementedError("block_type %r is not built (MRU, Pix2Pix)" % block_type)
+        self.ops, self.device, self.size, self.H, self.W, self.block_type = ops, device, size, H, W, block_type
+        pix = block_type == 'Pix2Pix'
+        self.gstore = ParamStore((pix2pix_generator_vars if pix else generator_vars)(size, vocab_size, H, W), device, param_dtype)
+        self.G = (Pix2PixGenerator if pix else Generator)(ops, self.gstore, size, lstm_hybrid)
         self.dstore = None
         self.D = None
         if with_discriminator:
-            self.dstore = ParamStore(discriminator_vars(size), device, param_dtype)
-            self.D = Discriminator(ops, self.dstore, size)
+            self.dstore = ParamStore((pix2pix_discriminator_vars if pix else discriminator_vars)(size), device, param_dtype)
+            self.D = (Pix2PixDiscriminator if pix else Discriminator)(ops, self.dstore, size)
 
     def initialize(self, seed=0, perturb_tables=0.0):
         self.gstore.initialize(seed, perturb_tables)
@@ -55,6 +59,8 @@ class FgColorModel:
         """batch: dict(sketch, images, images_d [N,3,H,W] fp32; cls, cls_d int32 [N]; text host [N,15]; noise [N,256]).
         Leaves dL_d/dtheta_D in dstore.grad; returns dict of fp32 0-d loss tensors (total under 'loss')."""
         ops = self.ops
+        if self.block_type == 'Pix2Pix':
+            return self._d_step_grads_pairs(batch)
         self.dstore.grad.zero_()
         fake, _ = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=False)
         wv = self.D.new_weight_view(need_wgrad=True)
@@ -82,13 +88,36 @@ class FgColorModel:
         reg = ops.reg_loss(self.dstore)                                  # :571
         return dict(loss=l_real + l_fake + l_ac + reg, gan=l_real + l_fake, ac=l_ac, reg=reg)
 
+    def _d_step_grads_pairs(self, batch):
+        """Pix2Pix discriminator: it looks at (sketch, image) pairs and batch-normalises, so the real and the fake pass stay
+        two instantiations with their own batch statistics (graph_single.py:269-272)."""
+        ops = self.ops
+        self.dstore.grad.zero_()
+        fake, _ = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=False)
+        wv = self.D.new_weight_view(need_wgrad=True)
+        sk = ops.nchw_to_nhwc(batch["sketch"])
+        d, lg, dctx = self.D.forward(sk, ops.nchw_to_nhwc(batch["images_d"]), wv)
+        l_real, g_rd = ops.softplus_mean(d, -1.0)
+        l_ac, g_rl = ops.ce_loss(lg, batch["cls_d"], True, 1.0)
+        self.D.backward(g_rd, g_rl, dctx, need_x_grad=False)
+        d, lg, dctx = self.D.forward(sk, fake, wv)
+        l_fake, g_fd = ops.softplus_mean(d, 1.0)
+        self.D.backward(g_fd, None, dctx, need_x_grad=False)
+        del dctx
+        wv.finish_backward()
+        reg = ops.reg_loss(self.dstore)
+        return dict(loss=l_real + l_fake + l_ac + reg, gan=l_real + l_fake, ac=l_ac, reg=reg)
+
     # ---- loss_g and dL/dtheta_G (+ SN u update)
     def g_step_grads(self, batch):
         ops = self.ops
         self.gstore.grad.zero_()
         fake, gctx = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=True)
         wv = self.D.new_weight_view(need_wgrad=False)
-        fd, fl, fctx = self.D.forward(fake, wv)
+        if self.block_type == 'Pix2Pix':
+            fd, fl, fctx = self.D.forward(ops.nchw_to_nhwc(batch["sketch"]), fake, wv)
+        else:
+            fd, fl, fctx = self.D.forward(fake, wv)
         l_gan, g_fd = ops.softplus_mean(fd, -1.0)                        # graph_single.py:401
         l_ac, g_fl = ops.ce_loss(fl, batch["cls"], False, 0.5)          # :350-352 (ld2 = 0.5)
         g_fake = self.D.backward(g_fd, g_fl, fctx, need_x_grad=True)

@@ -243,6 +243,72 @@ class TorchOps(OpsBase):
             dtype = self.cdt
         return x.to(dtype)
 
+    # ---- phase form of the 4x4 convolutions
+    def space_to_depth(self, x):
+        N, H, W, C = x.shape
+        return x.reshape(N, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, H // 2, W // 2, 4 * C).contiguous()
+
+    def depth_to_space(self, x):
+        N, h, w, C4 = x.shape
+        C = C4 // 4
+        return x.reshape(N, h, w, 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, 2 * h, 2 * w, C).contiguous()
+
+    @staticmethod
+    def _phase_index(mode):
+        """ky (0..3) -> (row of the expanded filter, phase) per axis."""
+        if mode == "conv":        # input row 2y + ky - 1 = 2 (y + dy) + py
+            return [((ky - 1) // 2 + 1, (ky - 1) % 2) for ky in range(4)]
+        if mode == "deconv":      # output row 2y + py takes input row y + dy through tap ky = py + 1 - 2 dy
+            return [((((ky + 1) % 2) + 1 - ky) // 2 + 1, (ky + 1) % 2) for ky in range(4)]
+        return [(ky + 1, 0) for ky in range(4)]
+
+    def phase_weights(self, f, mode):
+        idx = self._phase_index(mode)
+        A, B = f.shape[2], f.shape[3]
+        if mode == "conv":
+            w = f.new_zeros(3, 3, 4, A, B)
+        elif mode == "deconv":
+            w = f.new_zeros(3, 3, B, 4, A)
+        else:
+            w = f.new_zeros(5, 5, A, B)
+        for ky in range(4):
+            for kx in range(4):
+                (ry, py), (rx, px) = idx[ky], idx[kx]
+                if mode == "conv":
+                    w[ry, rx, py * 2 + px] = f[ky, kx]
+                elif mode == "deconv":
+                    w[ry, rx, :, py * 2 + px] = f[ky, kx].t()
+                else:
+                    w[ry, rx] = f[ky, kx]
+        if mode == "conv":
+            return w.reshape(3, 3, 4 * A, B)
+        if mode == "deconv":
+            return w.reshape(3, 3, B, 4 * A)
+        return w
+
+    def phase_wgrad(self, dw, df, mode):
+        idx = self._phase_index(mode)
+        A, B = df.shape[2], df.shape[3]
+        if mode == "conv":
+            dw = dw.reshape(3, 3, 4, A, B)
+        elif mode == "deconv":
+            dw = dw.reshape(3, 3, B, 4, A)
+        for ky in range(4):
+            for kx in range(4):
+                (ry, py), (rx, px) = idx[ky], idx[kx]
+                if mode == "conv":
+                    df[ky, kx] += dw[ry, rx, py * 2 + px].to(df.dtype)
+                elif mode == "deconv":
+                    df[ky, kx] += dw[ry, rx, :, py * 2 + px].t().to(df.dtype)
+                else:
+                    df[ky, kx] += dw[ry, rx].to(df.dtype)
+
+    def copy_rect(self, x, H, W):
+        N, h, w, C = x.shape
+        out = x.new_zeros(N, H, W, C)
+        out[:, :min(h, H), :min(w, W)] = x[:, :min(h, H), :min(w, W)]
+        return out
+
     # ---- real-data input: the CPU oracle's restatement of get_paired_input
     def paired_input(self, cartoon, sketch, out_hw, seed=0, dequantize=True):
         from oracle import input_oracle
