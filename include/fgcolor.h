@@ -207,6 +207,24 @@ int fgc_adam_step(float* flat, float* grad, float* v, const long long* start, co
                   int nchunks, float lr_t, const float* lr_t_dev, float beta2, float eps, int add_reg, fgc_stream s);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Layout passes that put the 4x4 layers of the Pix2Pix / Residual variants (models_collection.nchw_conv, :380-391;
+ * nchw_deconv = tf.nn.conv2d_transpose, :394-405) on the stride-1 SAME convolutions above ("phase form"):
+ *   4x4 stride 2 pad 1        = 3x3 SAME over space_to_depth(x);
+ *   conv2d_transpose 4x4 s2   = depth_to_space of a 3x3 SAME convolution to 4*Co channels;
+ *   4x4 stride 1 pad 1        = 5x5 SAME (first filter row / column zero), cropped by one row and column.
+ * Depth channel order is tf.space_to_depth's: (py*2+px)*C + c  <->  pixel (2y+py, 2x+px).
+ * -------------------------------------------------------------------------------------------------------*/
+int fgc_space_to_depth(const void* x /*[N,2h,2w,C]*/, int dtype, int N, int h, int w, int C, void* out /*[N,h,w,4C]*/, fgc_stream s);
+int fgc_depth_to_space(const void* x /*[N,h,w,4C]*/, int dtype, int N, int h, int w, int C, void* out /*[N,2h,2w,C]*/, fgc_stream s);
+/* out[N,H,W,C] = the top-left min(h,H) x min(w,W) rectangle of x[N,h,w,C], zero elsewhere (crop, or zero-pad a gradient) */
+int fgc_copy_rect(const void* x, int dtype, int N, int h, int w, int C, void* out, int H, int W, fgc_stream s);
+/* f[4,4,A,B] fp32 -> w: mode 0 (conv, A = Cin, B = Cout) [3,3,4A,B]; mode 1 (transposed conv, TF filter layout
+ * [kh,kw,out,in]: A = Cout, B = Cin) [3,3,B,4A]; mode 2 (stride-1 conv) [5,5,A,B].  Taps that do not land are zero. */
+int fgc_phase_weights(const float* f, int A, int B, int mode, float* w, fgc_stream s);
+/* df[4,4,A,B] += the entries of dw at the positions fgc_phase_weights writes (adjoint of the scatter) */
+int fgc_phase_wgrad(const float* dw, int A, int B, int mode, float* df, fgc_stream s);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Real-data input path (input_pipeline.get_paired_input, :72-126; the queues of :131-181 batch its outputs):
  * raw record payloads -> the tensors the graph is fed.  cartoon: uint8 [N,R,R,3] (`cartoon_data`, R = 384);
  * sketch: uint8 (sketch_dtype 0, `sketch_data`) or fp32 (sketch_dtype 1: the 0..255 distance map the reference computes

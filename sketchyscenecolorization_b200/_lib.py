@@ -106,6 +106,11 @@ SIGNATURES = {
     "fgc_nchw_to_nhwc": [_P, _I, _I, _I, _I, _P, _I, _P],
     "fgc_nhwc_to_nchw": [_P, _I, _I, _I, _I, _P, _I, _P],
     "fgc_cast": [_P, _I, _P, _I, _LL, _P],
+    "fgc_space_to_depth": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "fgc_depth_to_space": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "fgc_copy_rect": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P],
+    "fgc_phase_weights": [_P, _I, _I, _I, _P, _P],
+    "fgc_phase_wgrad": [_P, _I, _I, _I, _P, _P],
     "fgc_paired_input": [_P, _P, _I, _I, _I, _I, _I, C.c_ulonglong, _I, _P, _P, _P, _P],
     "fgc_l2norm_rows_fwd": [_P, _I, _I, _P, _P, _P],
     "fgc_l2norm_rows_bwd": [_P, _P, _P, _I, _I, _P, _P],

@@ -799,6 +799,78 @@ __global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long l
     st1<TO>(y + i, ld1<TI>(x + i));
 }
 
+// ======================================================================================================
+// layout passes of the phase-form 4x4 convolutions (Pix2Pix / Residual variants, models_collection.py:380-405)
+// ======================================================================================================
+// TO_DEPTH: dst[n,y,x,(py*2+px)*C + c] = src[n,2y+py,2x+px,c] (tf.space_to_depth order); else the inverse copy
+template <typename T, int V, bool TO_DEPTH>
+__device__ __forceinline__ void depth_space_body(const T* __restrict__ src, long long nlow, int h, int w, int C, T* __restrict__ dst) {
+  const int CV = C / V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nlow; i += (long long)gridDim.x * blockDim.x) {
+    UpIdx u = up_index<V>(i, h, w, C);                      // hi[py*2+px]: the four full-resolution pixels of low-res pixel i / CV
+    const long long d = (i / CV) * 4LL * C + (i % CV) * V;  // this channel vector inside phase 0 of the depth tensor
+    float a[kMaxV];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (TO_DEPTH) {
+        ldv<T, V>(src + u.hi[j], a);
+        stv<T, V>(dst + d + (long long)j * C, a);
+      } else {
+        ldv<T, V>(src + d + (long long)j * C, a);
+        stv<T, V>(dst + u.hi[j], a);
+      }
+    }
+  }
+}
+template <typename T, int V>
+__global__ void space_to_depth_kernel(const T* __restrict__ src, long long nlow, int h, int w, int C, T* __restrict__ dst) {
+  depth_space_body<T, V, true>(src, nlow, h, w, C, dst);
+}
+template <typename T, int V>
+__global__ void depth_to_space_kernel(const T* __restrict__ src, long long nlow, int h, int w, int C, T* __restrict__ dst) {
+  depth_space_body<T, V, false>(src, nlow, h, w, C, dst);
+}
+// dst[N,H,W,C]: top-left min(h,H) x min(w,W) rectangle of src[N,h,w,C], zero elsewhere
+template <typename T, int V>
+__global__ void copy_rect_kernel(const T* __restrict__ src, int h, int w, int C, T* __restrict__ dst, long long nvec, int H, int W) {
+  const int CV = C / V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long long p = i / CV;
+    int x = (int)(p % W);
+    long long q = p / W;
+    int y = (int)(q % H);
+    long long n = q / H;
+    float a[kMaxV];
+#pragma unroll
+    for (int k = 0; k < V; k++) a[k] = 0.f;
+    if (y < h && x < w) ldv<T, V>(src + ((n * h + y) * (long long)w + x) * C + (long long)cv * V, a);
+    stv<T, V>(dst + i * V, a);
+  }
+}
+// position of 4x4 filter element (ky, kx, a, b) of f[4,4,A,B] inside the expanded odd-size filter (see fgc_phase_weights)
+__device__ __forceinline__ long long phase_dest(int e, int A, int B, int mode) {
+  int b = e % B;
+  int t = e / B;
+  int a = t % A;
+  t /= A;
+  int kx = t & 3, ky = t >> 2;
+  if (mode == 2) return (((long long)(ky + 1) * 5 + (kx + 1)) * A + a) * B + b;
+  const int py = (ky & 1) ^ 1, px = (kx & 1) ^ 1;                          // ky: 0 1 2 3 -> phase 1 0 1 0 (both modes)
+  if (mode == 0) {                                                         // rows 0 1 1 2: input row 2y+ky-1 = 2(y+dy)+py
+    const int ry = (ky + 1) >> 1, rx = (kx + 1) >> 1;
+    return (((long long)(ry * 3 + rx)) * (4 * A) + (py * 2 + px) * A + a) * B + b;
+  }
+  const int ry = 2 - ((ky + 1) >> 1), rx = 2 - ((kx + 1) >> 1);            // rows 2 1 1 0: tap ky = py + 1 - 2 dy
+  return (((long long)(ry * 3 + rx)) * B + b) * (4 * A) + (py * 2 + px) * A + a;
+}
+__global__ void phase_weights_kernel(const float* __restrict__ f, int n, int A, int B, int mode, float* __restrict__ w) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) w[phase_dest(e, A, B, mode)] = __ldg(f + e);
+}
+__global__ void phase_wgrad_kernel(const float* __restrict__ dw, int n, int A, int B, int mode, float* __restrict__ df) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) df[e] += __ldg(dw + phase_dest(e, A, B, mode));
+}
+
 // choose block / rows-per-block for the per-(n,c) row reductions
 struct RowRed { int threads, V, lanes, rows_per_block, nblk; };
 static RowRed rowred_plan(int C, int vec, long long rows, long long other_blocks) {
@@ -1143,6 +1215,51 @@ int fgc_cast(const void* x, int x_dtype, void* y, int y_dtype, long long n, fgc_
   FGC_DISPATCH_2(x_dtype, y_dtype, TI, TO, (cast_kernel<TI, TO><<<ew_grid(n, 256), 256, 0, s>>>((const TI*)x, (TO*)y, n)));
   count_launch();
   FGC_LAUNCH_CHECK("cast");
+  return FGC_OK;
+}
+
+/* ---- phase-form layout passes ---- */
+int fgc_space_to_depth(const void* x, int dtype, int N, int h, int w, int C, void* out, fgc_stream stream) {
+  FGC_REQUIRE(N > 0 && h > 0 && w > 0 && C > 0 && x && out, "space_to_depth: bad arguments");
+  int vec = vmin(vec_width(x, C, dtype), vec_width(out, C, dtype));
+  FGC_UP_LAUNCH("space_to_depth", space_to_depth_kernel, (const T*)x, nv, h, w, C, (T*)out);
+}
+int fgc_depth_to_space(const void* x, int dtype, int N, int h, int w, int C, void* out, fgc_stream stream) {
+  FGC_REQUIRE(N > 0 && h > 0 && w > 0 && C > 0 && x && out, "depth_to_space: bad arguments");
+  int vec = vmin(vec_width(x, C, dtype), vec_width(out, C, dtype));
+  FGC_UP_LAUNCH("depth_to_space", depth_to_space_kernel, (const T*)x, nv, h, w, C, (T*)out);
+}
+int fgc_copy_rect(const void* x, int dtype, int N, int h, int w, int C, void* out, int H, int W, fgc_stream stream) {
+  FGC_REQUIRE(N > 0 && h > 0 && w > 0 && H > 0 && W > 0 && C > 0 && x && out, "copy_rect: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  int vec = vmin(vec_width(x, C, dtype), vec_width(out, C, dtype));
+  long long n = (long long)N * H * W * C;
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    long long nv = n / V;
+    copy_rect_kernel<T, V><<<ew_grid(nv, 256), 256, 0, s>>>((const T*)x, h, w, C, (T*)out, nv, H, W);
+  });
+  count_launch();
+  FGC_LAUNCH_CHECK("copy_rect");
+  return FGC_OK;
+}
+static long long phase_numel(int A, int B, int mode) { return (mode == 2 ? 25LL : 36LL) * A * B; }
+int fgc_phase_weights(const float* f, int A, int B, int mode, float* w, fgc_stream stream) {
+  FGC_REQUIRE(A > 0 && B > 0 && mode >= 0 && mode <= 2 && f && w && 16LL * A * B < (1LL << 31), "phase_weights: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  if (cudaMemsetAsync(w, 0, sizeof(float) * phase_numel(A, B, mode), s) != cudaSuccess) return check_launch("phase_weights memset");
+  int n = 16 * A * B;
+  phase_weights_kernel<<<ew_grid(n, 256), 256, 0, s>>>(f, n, A, B, mode, w);
+  count_launch();
+  FGC_LAUNCH_CHECK("phase_weights");
+  return FGC_OK;
+}
+int fgc_phase_wgrad(const float* dw, int A, int B, int mode, float* df, fgc_stream stream) {
+  FGC_REQUIRE(A > 0 && B > 0 && mode >= 0 && mode <= 2 && dw && df && 16LL * A * B < (1LL << 31), "phase_wgrad: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  int n = 16 * A * B;
+  phase_wgrad_kernel<<<ew_grid(n, 256), 256, 0, s>>>(dw, n, A, B, mode, df);
+  count_launch();
+  FGC_LAUNCH_CHECK("phase_wgrad");
   return FGC_OK;
 }
 

@@ -333,6 +333,46 @@ class CudaOps(OpsBase):
         check(self.lib.fgc_cast(self._p(x), self._dt(x), self._p(y), self._dt(y), x.numel(), self._s()), "cast")
         return y
 
+    # ---------------- phase form of the 4x4 convolutions ----------------
+    _PHASE_MODE = {"conv": 0, "deconv": 1, "k5": 2}
+
+    def space_to_depth(self, x):
+        N, H, W, Cc = x.shape
+        assert H % 2 == 0 and W % 2 == 0
+        y = self._empty((N, H // 2, W // 2, 4 * Cc), x.dtype)
+        check(self.lib.fgc_space_to_depth(self._p(x), self._dt(x), N, H // 2, W // 2, Cc, self._p(y), self._s()), "space_to_depth")
+        return y
+
+    def depth_to_space(self, x):
+        N, h, w, C4 = x.shape
+        assert C4 % 4 == 0
+        y = self._empty((N, 2 * h, 2 * w, C4 // 4), x.dtype)
+        check(self.lib.fgc_depth_to_space(self._p(x), self._dt(x), N, h, w, C4 // 4, self._p(y), self._s()), "depth_to_space")
+        return y
+
+    def copy_rect(self, x, H, W):
+        N, h, w, Cc = x.shape
+        y = self._empty((N, H, W, Cc), x.dtype)
+        check(self.lib.fgc_copy_rect(self._p(x), self._dt(x), N, h, w, Cc, self._p(y), H, W, self._s()), "copy_rect")
+        return y
+
+    @staticmethod
+    def _phase_shape(f, mode):
+        A, B = f.shape[2], f.shape[3]
+        return {"conv": (3, 3, 4 * A, B), "deconv": (3, 3, B, 4 * A), "k5": (5, 5, A, B)}[mode]
+
+    def phase_weights(self, f, mode):
+        assert f.dtype == torch.float32 and tuple(f.shape[:2]) == (4, 4)
+        w = self._empty(self._phase_shape(f, mode), torch.float32)
+        check(self.lib.fgc_phase_weights(self._f32(f), f.shape[2], f.shape[3], self._PHASE_MODE[mode], self._p(w), self._s()),
+              "phase_weights")
+        return w
+
+    def phase_wgrad(self, dw, df, mode):
+        assert tuple(dw.shape) == self._phase_shape(df, mode)
+        check(self.lib.fgc_phase_wgrad(self._f32(dw), df.shape[2], df.shape[3], self._PHASE_MODE[mode], self._f32(df), self._s()),
+              "phase_wgrad")
+
     # ---------------- real-data input ----------------
     def paired_input(self, cartoon, sketch, out_hw, seed=0, dequantize=True):
         N, R = cartoon.shape[0], cartoon.shape[1]

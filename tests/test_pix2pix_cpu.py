@@ -133,3 +133,29 @@ def test_generator_without_text_and_training_steps(setup):
     before = m.gstore.flat.clone()
     od, og = tr.d_step(bb), tr.g_step(bb)
     assert torch.isfinite(od["loss"]) and torch.isfinite(og["loss"]) and not torch.equal(before, m.gstore.flat)
+
+
+def test_snapshot_roundtrip_and_graph_builder(setup, tmp_path):
+    """Snapshots of a Pix2Pix model carry the reference's variable names (TF V2 bundle) and restore bit for bit; the graph
+    builder refuses a block type the bound model was not built with."""
+    from sketchyscenecolorization_b200 import checkpoint, graph_single, tf_bundle
+    m, ops, b, bb = setup["m"], setup["ops"], setup["b"], setup["bb"]
+    checkpoint.save(m, str(tmp_path), 7, 8)
+    prefix = checkpoint.latest_checkpoint(str(tmp_path))
+    keys = set(tf_bundle.read_bundle(prefix))
+    for k in ("generator/encoder_1/conv/filter", "generator/decoder_5/deconv/filter/Adam_1", "generator/encoder_3/scale",
+              "discriminator/layer_4/offset", "discriminator/fully_connected/discriminator/fully_connected/u", "Variable"):
+        assert k in keys, k
+    m2 = FgColorModel(ops, "cpu", size=SIZE, H=H, W=W, param_dtype=torch.float64, block_type="Pix2Pix")
+    m2.initialize(seed=99)
+    assert checkpoint.restore(m2, prefix) == 8
+    assert torch.equal(m2.gstore.flat.float(), m.gstore.flat.float()) and torch.equal(m2.dstore.flat.float(), m.dstore.flat.float())
+    ret = graph_single.build_single_graph(b["images"], b["sketch"], None, bb["cls"], None, bb["text"], batch_size=N, training=False,
+                                          LSTM_hybrid=True, vocab_size=58, block_type="Pix2Pix", model=m, noise=b["noise"])
+    ref = P.generator_forward(setup["gp"], b["sketch"], b["text"], b["cls"], b["noise"], SIZE)
+    assert (ret[0].double() - ref).abs().max().item() < 1e-5          # the builder feeds fp32 tensors
+    with pytest.raises(ValueError):
+        graph_single.build_single_graph(b["images"], b["sketch"], None, bb["cls"], None, bb["text"], batch_size=N, training=False,
+                                        LSTM_hybrid=True, vocab_size=58, block_type="MRU", model=m, noise=b["noise"])
+    with pytest.raises(NotImplementedError):
+        FgColorModel(ops, "cpu", size=SIZE, H=H, W=W, block_type="Residual")
