@@ -127,6 +127,8 @@ int fgc_minmax_fwd(const void* x, int dtype, int N, int HW, int C, void* gate, f
 /* gradient w.r.t. the pre-lrelu conv output (leak 0.2); scratch: 4*N*C floats. */
 int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, int C, const float* mn,
                    const float* mx, void* gpre, float* scratch, float* dbias /*NULL ok*/, fgc_stream stream);
+/* y = tanh(x) as a pass of its own (after a batch norm: generate_residual, models_collection.py:665); gradient: fgc_act_bwd */
+int fgc_tanh_fwd(const void* x, int dtype, long long n, void* y, fgc_stream stream);
 /* gradient through an activation fused in a conv epilogue, from its output y (tanh / miu_relu). */
 int fgc_act_bwd(const void* gy, const void* y, int dtype, long long n, int act, void* gx, fgc_stream stream);
 

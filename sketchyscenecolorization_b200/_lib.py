@@ -106,6 +106,7 @@ SIGNATURES = {
     "fgc_nchw_to_nhwc": [_P, _I, _I, _I, _I, _P, _I, _P],
     "fgc_nhwc_to_nchw": [_P, _I, _I, _I, _I, _P, _I, _P],
     "fgc_cast": [_P, _I, _P, _I, _LL, _P],
+    "fgc_tanh_fwd": [_P, _I, _LL, _P, _P],
     "fgc_space_to_depth": [_P, _I, _I, _I, _I, _I, _P, _P],
     "fgc_depth_to_space": [_P, _I, _I, _I, _I, _I, _P, _P],
     "fgc_copy_rect": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P],

@@ -297,6 +297,17 @@ __global__ void prelu_fwd_kernel(const T* __restrict__ x, long long nvec, const 
     stv<T, V>(y + i * V, o);
   }
 }
+// tanh as a pass of its own (after a batch norm: generate_residual, models_collection.py:665)
+template <typename T, int V>
+__global__ void tanh_fwd_kernel(const T* __restrict__ x, long long nvec, T* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float v[kMaxV], o[kMaxV];
+    ldv<T, V>(x + i * V, v);
+#pragma unroll
+    for (int k = 0; k < V; k++) o[k] = tanhf(v[k]);
+    stv<T, V>(y + i * V, o);
+  }
+}
 template <typename T, int V>
 __global__ void prelu_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, long long nvec,
                                  const float* __restrict__ ap, float* da, T* __restrict__ gx) {
@@ -966,6 +977,18 @@ int fgc_prelu_fwd(const void* x, int dtype, long long n, const float* a, void* y
   });
   count_launch();
   FGC_LAUNCH_CHECK("prelu_fwd");
+  return FGC_OK;
+}
+int fgc_tanh_fwd(const void* x, int dtype, long long n, void* y, fgc_stream stream) {
+  FGC_REQUIRE(n > 0 && x && y, "tanh_fwd: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  int vec = vmin(vec_width(x, n, dtype), vec_width(y, n, dtype));
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    long long nvec = n / V;
+    tanh_fwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)x, nvec, (T*)y);
+  });
+  count_launch();
+  FGC_LAUNCH_CHECK("tanh_fwd");
   return FGC_OK;
 }
 int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, int C, const float* a, float* da, float* dbias,

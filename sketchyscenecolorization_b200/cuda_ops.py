@@ -350,6 +350,11 @@ class CudaOps(OpsBase):
         check(self.lib.fgc_depth_to_space(self._p(x), self._dt(x), N, h, w, C4 // 4, self._p(y), self._s()), "depth_to_space")
         return y
 
+    def tanh_fwd(self, x):
+        y = self._empty(x.shape, x.dtype)
+        check(self.lib.fgc_tanh_fwd(self._p(x), self._dt(x), x.numel(), self._p(y), self._s()), "tanh_fwd")
+        return y
+
     def copy_rect(self, x, H, W):
         N, h, w, Cc = x.shape
         y = self._empty((N, H, W, Cc), x.dtype)

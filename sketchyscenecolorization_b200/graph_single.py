@@ -27,9 +27,8 @@ def build_single_graph(images, sketches, images_d, image_data_class_id, image_da
     m = model or _default_model
     if m is None:
         raise RuntimeError("build_single_graph: no model bound (call graph_single.bind_model(FgColorModel(...)) first)")
-    if block_type not in ('MRU', 'Pix2Pix'):
-        raise NotImplementedError("block_type %r: the MRU and Pix2Pix networks are built (Residual is listed as 'next' in "
-                                  "DESIGN.md)" % block_type)
+    if block_type not in ('MRU', 'Pix2Pix', 'Residual'):
+        raise ValueError("block_type %r (MRU, Pix2Pix, Residual)" % (block_type,))
     if block_type != getattr(m, 'block_type', 'MRU'):
         raise ValueError("build_single_graph(block_type=%r) on a model built as %r" % (block_type, m.block_type))
     if data_format != 'NCHW':

@@ -28,8 +28,8 @@ def _dtype(name):
 
 def _build_model(precision, img_dim, vocab_size, lstm_hybrid, device=None, with_discriminator=True):
     block_type = getattr(Config, 'block_type', 'MRU') or 'MRU'
-    if block_type not in ('MRU', 'Pix2Pix'):
-        raise NotImplementedError("block_type %r is not built (MRU, Pix2Pix)" % block_type)
+    if block_type not in ('MRU', 'Pix2Pix', 'Residual'):
+        raise ValueError("block_type %r (MRU, Pix2Pix, Residual)" % (block_type,))
     from .cuda_ops import CudaOps
     from .trainer import FgColorModel
     dev = device or "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
@@ -67,8 +67,8 @@ def train(**kwargs):
     batch_size, max_iter_step, diters = Config.batch_size, Config.max_iter_step, Config.disc_iterations
     log_dir, ckpt_dir = Config.log_dir, Config.ckpt_dir
     small, lstm_hybrid = Config.small_img != 0, Config.LSTM_hybrid != 0
-    if Config.block_type not in ('MRU', 'Pix2Pix'):
-        raise NotImplementedError("block_type %r is not built (MRU, Pix2Pix)" % Config.block_type)
+    if Config.block_type not in ('MRU', 'Pix2Pix', 'Residual'):
+        raise ValueError("block_type %r (MRU, Pix2Pix, Residual)" % (Config.block_type,))
     if Config.optimizer != 'Adam':
         raise NotImplementedError("optimizer %r: the path is built for the default Adam(beta1=0, beta2=0.9)" % Config.optimizer)
     iter_from = kwargs['iter_from']

@@ -171,6 +171,11 @@ class OpsBase:
         """df += the entries of dw (gradient of the expanded filter) at the positions phase_weights writes."""
         raise NotImplementedError
 
+    def tanh_fwd(self, x):
+        """tanh as a pass of its own (after a batch norm: generate_residual, models_collection.py:665); its gradient is
+        act_bwd(g, y, ACT_TANH)."""
+        raise NotImplementedError
+
     def copy_rect(self, x, H, W):
         """[N,h,w,C] -> [N,H,W,C]: the overlapping top-left rectangle is copied, the rest is zero (crop or zero-pad)."""
         raise NotImplementedError

@@ -192,6 +192,75 @@ def pix2pix_discriminator_vars(size=64):
     return v
 
 
+# ------------------------------------------------------------------------------------------------
+# --block_type Residual (residual_util.py:16-175; models_collection.py:541-672, 844-893).  residual_util.batchnorm keeps its
+# tables in a `batchnorm` sub-scope (:57); the generator's first and last layer use models_collection.batchnorm (no sub-scope)
+# ------------------------------------------------------------------------------------------------
+RESIDUAL_UNITS = [3, 4, 6, 3]          # models_collection.py:609
+
+
+def _res_filter(scope, kind, k, cin, cout):
+    shape = (4, 4, cout, cin) if kind == "deconv" else (k, k, cin, cout)
+    return [VarSpec("%s/%s/filter" % (scope, kind), shape, ("normal", 0.02))]
+
+
+def _res_block(scope, kind, cin, cout):
+    q = int(round(cout / 4))
+    first = {"en": "conv", "de": "deconv", "pu": "conv_ex"}[kind]
+    v = _res_filter(scope + "/block_1", first, 4, cin, q) + _bn(scope + "/block_1/batchnorm", q)
+    v += _res_filter(scope + "/block_2", "conv_ex", 3, q, q) + _bn(scope + "/block_2/batchnorm", q)
+    v += _res_filter(scope + "/block_3", "conv_ex", 1, q, cout) + _bn(scope + "/block_3/batchnorm", cout)
+    if kind != "pu":
+        v += _res_filter(scope + "/block_add", first, 4, cin, cout) + _bn(scope + "/block_add/batchnorm", cout)
+    return v
+
+
+def residual_generator_vars(size=64, vocab_size=58, H=192, W=192):
+    assert H % 32 == 0 and W % 32 == 0, "image size must be a multiple of 32"
+    p = "generator"
+    ench = [size * 2, size * 4, size * 8, size * 8]
+    v = _res_filter(p + "/encoder_1", "conv_ex", 7, 3, size) + _bn(p + "/encoder_1", size)
+    cin = size
+    for lvl, co in enumerate(ench):
+        v += _res_block("%s/encoder_%d_0" % (p, lvl + 2), "en", cin, co)
+        for u in range(1, RESIDUAL_UNITS[lvl]):
+            v += _res_block("%s/encoder_%d_%d" % (p, lvl + 2, u), "pu", co, co)
+        cin = co
+    d = cin
+    v.append(VarSpec(p + "/TextLSTM/embedding", (vocab_size, d), ("uniform", 0.08)))
+    for cell, kin in (("WLSTM", 2 * d), ("ALSTM", 4 * d)):
+        b = p + "/TextLSTM/RNN/%s/multi_rnn_cell/cell_0/basic_lstm_cell" % cell
+        v.append(VarSpec(b + "/kernel", (kin, 4 * d), ("glorot_uniform", None)))
+        v.append(VarSpec(b + "/bias", (4 * d,), ("const", 0.0)))
+    nfc = (d // 8) * (H // 32) * (W // 32)
+    v.append(VarSpec(p + "/fully_connected/weights", (NOISE_DIM, nfc), ("xavier", None), reg=1e-6))
+    v.append(VarSpec(p + "/fully_connected/biases", (nfc,), ("const", 0.0)))
+    skip_ch = [size] + ench
+    cin = d + d // 8
+    for i, co in enumerate([size * 8, size * 4, size * 2, size]):
+        skip = 4 - i
+        v += _res_block("%s/decoder_%d_0" % (p, skip + 1), "de", cin, co)
+        for u in range(1, RESIDUAL_UNITS[skip - 1]):
+            v += _res_block("%s/decoder_%d_%d" % (p, skip + 1, u), "pu", co, co)
+        cin = co + skip_ch[skip - 1]
+    v += _res_filter(p + "/decoder_1", "deconv", 4, cin, 3) + _bn(p + "/decoder_1", 3)
+    return v
+
+
+def residual_discriminator_vars(size=64):
+    p = "discriminator"
+    chans = [6, size, size * 2, size * 4, size * 8, 512]
+    v = []
+    for k in range(1, 6):
+        v += _res_block("%s/layer_%d" % (p, k), "en", chans[k - 1], chans[k])
+    v += _res_filter(p + "/layer_5", "conv_ex", 4, 512, 1)
+    fc = p + "/fully_connected"
+    v.append(VarSpec(fc + "/weights", (chans[4], NUM_CLASSES), ("xavier", None), reg=1e-6, sn=True))
+    v.append(VarSpec(fc + "/" + fc + "/u", (1, NUM_CLASSES), ("trunc_normal", 1.0), trainable=False))
+    v.append(VarSpec(fc + "/biases", (NUM_CLASSES,), ("const", 0.0)))
+    return v
+
+
 class ParamStore:
     """Flat fp32 parameter / gradient / Adam-v buffers of one network plus named views."""
 

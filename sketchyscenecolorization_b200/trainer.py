@@ -18,8 +18,14 @@ import torch
 
 from .discriminator import Discriminator
 from .generator import Generator
-from .params import (ParamStore, discriminator_vars, generator_vars, pix2pix_discriminator_vars, pix2pix_generator_vars)
+from .params import (ParamStore, discriminator_vars, generator_vars, pix2pix_discriminator_vars, pix2pix_generator_vars,
+                     residual_discriminator_vars, residual_generator_vars)
 from .pix2pix import Pix2PixDiscriminator, Pix2PixGenerator
+from .residual import ResidualDiscriminator, ResidualGenerator
+
+_NETS = {'MRU': (generator_vars, Generator, discriminator_vars, Discriminator),
+         'Pix2Pix': (pix2pix_generator_vars, Pix2PixGenerator, pix2pix_discriminator_vars, Pix2PixDiscriminator),
+         'Residual': (residual_generator_vars, ResidualGenerator, residual_discriminator_vars, ResidualDiscriminator)}
 
 
 def lr_decay(counter, max_iter):
@@ -32,17 +38,17 @@ class FgColorModel:
 
     def __init__(self, ops, device, *, size=64, H=192, W=192, vocab_size=58, lstm_hybrid=True,
                  param_dtype=torch.float32, with_discriminator=True, block_type='MRU'):
-        if block_type not in ('MRU', 'Pix2Pix'):
-            raise NotImplementedError("block_type %r is not built (MRU, Pix2Pix)" % block_type)
+        if block_type not in _NETS:
+            raise NotImplementedError("block_type %r (the reference has MRU, Pix2Pix, Residual)" % (block_type,))
         self.ops, self.device, self.size, self.H, self.W, self.block_type = ops, device, size, H, W, block_type
-        pix = block_type == 'Pix2Pix'
-        self.gstore = ParamStore((pix2pix_generator_vars if pix else generator_vars)(size, vocab_size, H, W), device, param_dtype)
-        self.G = (Pix2PixGenerator if pix else Generator)(ops, self.gstore, size, lstm_hybrid)
+        gvars, gcls, dvars, dcls = _NETS[block_type]
+        self.gstore = ParamStore(gvars(size, vocab_size, H, W), device, param_dtype)
+        self.G = gcls(ops, self.gstore, size, lstm_hybrid)
         self.dstore = None
         self.D = None
         if with_discriminator:
-            self.dstore = ParamStore((pix2pix_discriminator_vars if pix else discriminator_vars)(size), device, param_dtype)
-            self.D = (Pix2PixDiscriminator if pix else Discriminator)(ops, self.dstore, size)
+            self.dstore = ParamStore(dvars(size), device, param_dtype)
+            self.D = dcls(ops, self.dstore, size)
 
     def initialize(self, seed=0, perturb_tables=0.0):
         self.gstore.initialize(seed, perturb_tables)
@@ -59,7 +65,7 @@ class FgColorModel:
         """batch: dict(sketch, images, images_d [N,3,H,W] fp32; cls, cls_d int32 [N]; text host [N,15]; noise [N,256]).
         Leaves dL_d/dtheta_D in dstore.grad; returns dict of fp32 0-d loss tensors (total under 'loss')."""
         ops = self.ops
-        if self.block_type == 'Pix2Pix':
+        if self.block_type != 'MRU':
             return self._d_step_grads_pairs(batch)
         self.dstore.grad.zero_()
         fake, _ = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=False)
@@ -89,8 +95,8 @@ class FgColorModel:
         return dict(loss=l_real + l_fake + l_ac + reg, gan=l_real + l_fake, ac=l_ac, reg=reg)
 
     def _d_step_grads_pairs(self, batch):
-        """Pix2Pix discriminator: it looks at (sketch, image) pairs and batch-normalises, so the real and the fake pass stay
-        two instantiations with their own batch statistics (graph_single.py:269-272)."""
+        """Pix2Pix / Residual discriminators: they look at (sketch, image) pairs and batch-normalise, so the real and the fake
+        pass stay two instantiations with their own batch statistics (graph_single.py:269-272)."""
         ops = self.ops
         self.dstore.grad.zero_()
         fake, _ = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=False)
@@ -114,7 +120,7 @@ class FgColorModel:
         self.gstore.grad.zero_()
         fake, gctx = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=True)
         wv = self.D.new_weight_view(need_wgrad=False)
-        if self.block_type == 'Pix2Pix':
+        if self.block_type != 'MRU':
             fd, fl, fctx = self.D.forward(ops.nchw_to_nhwc(batch["sketch"]), fake, wv)
         else:
             fd, fl, fctx = self.D.forward(fake, wv)

@@ -158,4 +158,4 @@ def test_snapshot_roundtrip_and_graph_builder(setup, tmp_path):
         graph_single.build_single_graph(b["images"], b["sketch"], None, bb["cls"], None, bb["text"], batch_size=N, training=False,
                                         LSTM_hybrid=True, vocab_size=58, block_type="MRU", model=m, noise=b["noise"])
     with pytest.raises(NotImplementedError):
-        FgColorModel(ops, "cpu", size=SIZE, H=H, W=W, block_type="Residual")
+        FgColorModel(ops, "cpu", size=SIZE, H=H, W=W, block_type="Unet")

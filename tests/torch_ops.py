@@ -303,6 +303,9 @@ class TorchOps(OpsBase):
                 else:
                     df[ky, kx] += dw[ry, rx].to(df.dtype)
 
+    def tanh_fwd(self, x):
+        return torch.tanh(self._c(x)).to(self.act_dtype)
+
     def copy_rect(self, x, H, W):
         N, h, w, C = x.shape
         out = x.new_zeros(N, H, W, C)
