@@ -34,6 +34,20 @@ WORKLOAD = ("fg-colorization MRU G+D training iteration (D step + G step), 192x1
             "(BASELINE.json configs[1])")
 
 
+def block_type_flops(block_type):
+    """(generator, discriminator) conv forward GFLOP / image at 192x192 -- algorithmic (true 4x4 taps, not the zero-padded
+    phase form the Pix2Pix layers run in).  None where not tabulated."""
+    if block_type == "MRU":
+        return GF_GFLOP, DF_GFLOP
+    if block_type == "Pix2Pix":       # models_collection.py:408-538, 789-841 (size 64)
+        enc = [(96, 3, 64), (48, 64, 128), (24, 128, 256), (12, 256, 512), (6, 512, 512)]            # (output side, Cin, Cout)
+        dec = [(6, 576, 512), (12, 1024, 256), (24, 512, 128), (48, 256, 64), (96, 128, 3)]          # (INPUT side, Cin, Cout)
+        dis = [(96, 6, 64), (48, 64, 128), (24, 128, 256), (23, 256, 512), (22, 512, 1)]
+        mac = lambda rows: sum(s * s * 16 * ci * co for s, ci, co in rows)                           # noqa: E731
+        return 2 * (mac(enc) + mac(dec)) / 1e9, 2 * mac(dis) / 1e9
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -208,8 +222,13 @@ def run_product(args):
         dist.init_process_group("nccl", device_id=torch.device(dev))
         pg = dist.group.WORLD
     ops = CudaOps(dev, torch.bfloat16)          # training mode: bf16 NHWC activations, fp32 master weights / stats / Adam
-    model = FgColorModel(ops, dev, size=SIZE, H=H, W=W)
+    model = FgColorModel(ops, dev, size=SIZE, H=H, W=W, block_type=args.block_type)
     model.initialize(seed=0)                    # identical on every rank (reference initialisers)
+    fl = block_type_flops(args.block_type)
+    # D step = Gf + 6 Df for MRU; the pair discriminators run real and fake separately, same conv work
+    step_gflop = (4 * fl[0] + 8 * fl[1]) if fl else None
+    workload = WORKLOAD if args.block_type == "MRU" else WORKLOAD.replace("MRU G+D", args.block_type + " G+D").replace(
+        " (BASELINE.json configs[1])", " (--block_type %s; BASELINE.json configs[1] is the MRU default)" % args.block_type)
     graphs = not args.no_graphs
     tr = FgColorTrainer(model, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=pg, world_size=world,
                         use_cuda_graphs=graphs)
@@ -296,23 +315,23 @@ def run_product(args):
         ips = BS * world * args.steps / (ms * 1e-3)
         ips_e2e = BS * world * args.steps / (ms_e2e * 1e-3)
         roof = dominant_kernel_roofline(ops, torch, pk)
-        step_tflops = STEP_GFLOP * 1e9 * ips / world / 1e12
+        step_tflops = (step_gflop * 1e9 * ips / world / 1e12) if step_gflop else None
         cores = os.cpu_count() or 1
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.block_type == "MRU":     # the CPU arm restates the MRU graph
             c_ips, c_spi, cores, c_bs = cpu_reference_images_per_sec(1, 1)
             cpu = {"value": c_ips, "unit": "images/s", "cores": cores, "kind": "port",
                    "sample": "oracle (torch-CPU restatement of the TF1 graph), bs %d, 1 timed training iteration after 1 warm-up" % c_bs}
         line = {"metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": WORKLOAD,
+                "config": {"workload": workload,
                            "global_batch": BS * world, "parallelism": "dp%d" % world,
                            "precision": "bf16 activations + single-pass bf16 tcgen05 convs, fp32 accumulate/master/BN/LSTM/Adam",
                            "l2_policy": "per-step working set (tens of GB of activations) far exceeds the 126 MB L2",
-                           "conv_flop_per_image": STEP_GFLOP * 1e9,
-                           "step_conv_tflops_per_gpu": round(step_tflops, 2),
-                           "step_conv_frac_of_sustained_peak": round(step_tflops / pk["sustained"], 4),
+                           "conv_flop_per_image": step_gflop * 1e9 if step_gflop else None,
+                           "step_conv_tflops_per_gpu": round(step_tflops, 2) if step_tflops else None,
+                           "step_conv_frac_of_sustained_peak": round(step_tflops / pk["sustained"], 4) if step_tflops else None,
                            "host_enqueue_ms_per_step": round(host_ms, 2),
                            "cuda_graphs": graphs,
                            "loss_d": ld_v, "loss_g": lg_v},
@@ -340,6 +359,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--block-type", dest="block_type", default="MRU", choices=["MRU", "Pix2Pix", "Residual"],
+                    help="network family (obj_colorization_main.py --block_type); the BASELINE metric is the MRU default")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
