@@ -261,6 +261,46 @@ def residual_discriminator_vars(size=64):
     return v
 
 
+# ------------------------------------------------------------------------------------------------
+# background-colorization generator (Background_Colorization/bg_colorization_main.py:302-420, scope `generator`, :585):
+# the residual generator with a 1024-channel fifth level, the caption cells under generator/mLSTM_G, no noise input, a
+# region-segmentation branch, and EVERY batch norm in its `batchnorm` sub-scope (:86-98)
+# ------------------------------------------------------------------------------------------------
+BG_TEXT_SCOPE = "generator/mLSTM_G"
+
+
+def bg_generator_vars(ngf=64, vocab_size=18, seg_classes=3):
+    p = "generator"
+    ench = [ngf * 2, ngf * 4, ngf * 8, ngf * 16]
+    v = _res_filter(p + "/encoder_1", "conv_ex", 7, 3, ngf) + _bn(p + "/encoder_1/batchnorm", ngf)
+    cin = ngf
+    for lvl, co in enumerate(ench):
+        v += _res_block("%s/encoder_%d_0" % (p, lvl + 2), "en", cin, co)
+        for u in range(1, RESIDUAL_UNITS[lvl]):
+            v += _res_block("%s/encoder_%d_%d" % (p, lvl + 2, u), "pu", co, co)
+        cin = co
+    d = cin
+    v.append(VarSpec(BG_TEXT_SCOPE + "/embedding", (vocab_size, d), ("uniform", 0.08)))
+    for cell, kin in (("WLSTM", 2 * d), ("ALSTM", 4 * d)):
+        b = BG_TEXT_SCOPE + "/RNN/%s/multi_rnn_cell/cell_0/basic_lstm_cell" % cell
+        v.append(VarSpec(b + "/kernel", (kin, 4 * d), ("glorot_uniform", None)))
+        v.append(VarSpec(b + "/bias", (4 * d,), ("const", 0.0)))
+    v += _res_filter(p + "/region_br_projection", "conv_ex", 1, d, seg_classes) + _bn(p + "/region_br_projection/batchnorm", seg_classes)
+    skip_ch = [ngf] + ench
+    for i, co in enumerate([ngf * 8, ngf * 4, ngf * 2, ngf]):
+        skip = 4 - i
+        v += _res_block("%s/decoder_%d_0" % (p, skip + 1), "de", cin, co)
+        for u in range(1, RESIDUAL_UNITS[skip - 1]):
+            v += _res_block("%s/decoder_%d_%d" % (p, skip + 1, u), "pu", co, co)
+        s = "%s/region_br_%d" % (p, skip + 1)
+        v += _res_filter(s, "deconv", 4, seg_classes, seg_classes) + _bn(s + "/batchnorm", seg_classes)
+        cin = co + skip_ch[skip - 1]
+    v += _res_filter(p + "/decoder_1", "deconv", 4, cin, 3) + _bn(p + "/decoder_1/batchnorm", 3)
+    s = p + "/region_br_1"
+    v += _res_filter(s, "deconv", 4, seg_classes, seg_classes) + _bn(s + "/batchnorm", seg_classes)
+    return v
+
+
 class ParamStore:
     """Flat fp32 parameter / gradient / Adam-v buffers of one network plus named views."""
 

@@ -21,12 +21,14 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-_PRE = "generator/TextLSTM"
-_KW = _PRE + "/RNN/WLSTM/multi_rnn_cell/cell_0/basic_lstm_cell/kernel"
-_BW = _PRE + "/RNN/WLSTM/multi_rnn_cell/cell_0/basic_lstm_cell/bias"
-_KA = _PRE + "/RNN/ALSTM/multi_rnn_cell/cell_0/basic_lstm_cell/kernel"
-_BA = _PRE + "/RNN/ALSTM/multi_rnn_cell/cell_0/basic_lstm_cell/bias"
-_EMB = _PRE + "/embedding"
+_PRE = "generator/TextLSTM"           # the fg networks; the background generator keeps the same cells under generator/mLSTM_G
+
+
+def _names(prefix):
+    """(embedding, WLSTM kernel, WLSTM bias, ALSTM kernel, ALSTM bias) variable names under `prefix`."""
+    cell = prefix + "/RNN/%s/multi_rnn_cell/cell_0/basic_lstm_cell/%s"
+    return (prefix + "/embedding", cell % ("WLSTM", "kernel"), cell % ("WLSTM", "bias"), cell % ("ALSTM", "kernel"),
+            cell % ("ALSTM", "bias"))
 
 
 def _mat(w2d):
@@ -46,7 +48,7 @@ def _op(ops, t):
     return _rows(t if ops.act_dtype != torch.bfloat16 else ops.cast(t, torch.bfloat16))
 
 
-def text_fusion_fwd(ops, store, e4, ids_host, save=True):
+def text_fusion_fwd(ops, store, e4, ids_host, save=True, prefix=_PRE):
     """e4: [N,h,w,D] activation; ids_host: int array [N,T] on the HOST (numpy / CPU tensor), or an int32 DEVICE tensor.
     With host ids, time steps at which every caption is <pad> are skipped outright (the reference's tf.cond, :235);
     with device ids nothing on the host depends on the data (CUDA-graph capture): every step runs and <pad> samples
@@ -58,7 +60,7 @@ def text_fusion_fwd(ops, store, e4, ids_host, save=True):
     R = N * P
     T = ids_host.shape[1]
     dev = e4.device
-    emb, kw, bw, ka, ba = store.p[_EMB], store.p[_KW], store.p[_BW], store.p[_KA], store.p[_BA]
+    emb, kw, bw, ka, ba = (store.p[n] for n in _names(prefix))
     # [N,T] int32 on the device; pad mask = (id == 0)
     ids_dev = ids_host.to(torch.int32).contiguous() if on_device else torch.as_tensor(ids_np, device=dev).contiguous()
     f32 = torch.float32
@@ -102,14 +104,15 @@ def text_fusion_fwd(ops, store, e4, ids_host, save=True):
     return out, ctx
 
 
-def text_fusion_bwd(ops, store, g_out, ctx):
+def text_fusion_bwd(ops, store, g_out, ctx, prefix=_PRE):
     """Returns g_e4 [N,h,w,D]; accumulates gradients of embedding / both LSTM kernels / biases."""
     N, hh, ww, D = ctx["shape"]
     P = hh * ww
     R = N * P
     f32 = torch.float32
-    kw, ka = store.p[_KW], store.p[_KA]
-    dkw, dbw, dka, dba, demb = store.g[_KW], store.g[_BW], store.g[_KA], store.g[_BA], store.g[_EMB]
+    n_emb, n_kw, n_bw, n_ka, n_ba = _names(prefix)
+    kw, ka = store.p[n_kw], store.p[n_ka]
+    dkw, dbw, dka, dba, demb = store.g[n_kw], store.g[n_bw], store.g[n_ka], store.g[n_ba], store.g[n_emb]
     steps = ctx["steps"]
     S = len(steps)
     if S == 0:                # all-pad batch: output is relu(0) = 0, no gradient reaches e4

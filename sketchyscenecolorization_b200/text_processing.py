@@ -21,11 +21,18 @@ DEFAULT_VOCAB = (
     "wing with white bus windows butterfly edge car cat chair chicken tail head cloud cow dog duck horse house roof moon "
     "person hair in shirt pants skirt pig rabbit road sheep star sun tree truck carriage grass").split()
 
+# the background model's 18-entry vocabulary (Background_Colorization/data/bg_vocab.txt)
+BG_VOCAB = "<pad> <unk> sky is blue and grass green ground gray purple black yellow brown cyan pink orange red".split()
+
 _TOKEN_BREAK = re.compile(r"(\W+)")
 
 
 def default_vocab_dict():
     return {w: i for i, w in enumerate(DEFAULT_VOCAB)}
+
+
+def bg_vocab_dict():
+    return {w: i for i, w in enumerate(BG_VOCAB)}
 
 
 def load_vocab_dict_from_file(dict_file):
