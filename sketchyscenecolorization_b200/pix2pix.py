@@ -18,7 +18,6 @@ import torch
 
 from . import blocks, text_fusion
 from .ops_base import ACT_MIU, ACT_NONE, ACT_TANH
-from .params import pix2pix_dec_channels, pix2pix_enc_channels
 
 
 # ------------------------------------------------------------------------------------------------

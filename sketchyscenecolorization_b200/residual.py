@@ -19,14 +19,6 @@ from .pix2pix import _Filters, _slopes, bn_bwd, bn_fwd
 UNITS = [3, 4, 6, 3]                       # models_collection.py:609
 
 
-def residual_enc_channels(size):
-    return [size * 2, size * 4, size * 8, size * 8]
-
-
-def residual_dec_channels(size):
-    return [size * 8, size * 4, size * 2, size]
-
-
 class Layers:
     """conv -> batch norm -> activation units over one parameter store, with their backward passes."""
 

@@ -33,7 +33,7 @@ import struct
 import numpy as np
 import torch
 
-from .tf_bundle import _field_bytes, _field_varint, _parse, _read_varint, _varint, crc32c, mask_crc
+from .tf_bundle import _field_bytes, _parse, _read_varint, _varint, crc32c, mask_crc
 
 RAW = 384            # "cannot change" (input_pipeline.py:82,87)
 TEXT_LEN = 15
