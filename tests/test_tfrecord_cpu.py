@@ -209,3 +209,48 @@ def test_validation_mode_end_to_end(tmp_path, monkeypatch):
     # the input picture is the AREA-resized sketch: white background, dark strokes
     inp = cv2.imread(os.path.join(out, "bus_img000_input.png"))
     assert inp.max() >= 254 and inp.min() < 140
+
+
+def test_test_mode_end_to_end(tmp_path):
+    """`--mode test` (main_procedure.py:361-492): data/captions/<category>/test.json x data/images/<category>/sketch/<key> ->
+    <category>_<stem>_{output,input}.png; class id = index of the category folder, strokes thickened for house / road."""
+    import cv2
+    import json
+    from oracle import fgcolor_oracle as O
+    from sketchyscenecolorization_b200 import main_procedure
+    from sketchyscenecolorization_b200.config import Config
+    from sketchyscenecolorization_b200.pipeline_fg import thicken_drawings
+    from sketchyscenecolorization_b200.text_processing import default_vocab_dict, preprocess_sentence
+    from sketchyscenecolorization_b200.trainer import FgColorModel
+    from torch_ops import TorchOps
+    base = tmp_path / "data"
+    sketches = {}
+    for cate, key, text in (("bus", "228_1.png", "A yellow bus with blue window"), ("road", "7_3.png", "the road is gray")):
+        os.makedirs(base / "captions" / cate)
+        os.makedirs(base / "images" / cate / "sketch")
+        sk = np.full((64, 64, 3), 255, np.uint8)
+        sk[20:22, 8:56] = 0
+        sk[40:42, 8:56] = 0
+        cv2.imwrite(str(base / "images" / cate / "sketch" / key), sk)
+        json.dump([dict(key=key, color_text=text)], open(base / "captions" / cate / "test.json", "w"))
+        sketches[cate] = (sk, key, text)
+    res = str(tmp_path / "test_results")
+    Config.set_from_dict(dict(dataset_type="test", batch_size=1, ckpt_dir=str(tmp_path / "snapshot"), results_dir=res,
+                              data_format="NCHW", distance_map=0, small_img=1, LSTM_hybrid=1, block_type="MRU", vocab_size=58))
+    model = FgColorModel(TorchOps(torch.float64), "cpu", size=16, H=64, W=64, param_dtype=torch.float64, with_discriminator=False)
+    model.initialize(seed=1, perturb_tables=0.1)
+    noise = torch.zeros(1, 256)
+    assert main_procedure.test(model=model, noise=noise, data_base_dir=str(base)) == 2
+    gp = {k: v.double() for k, v in model.gstore.state_dict().items()}
+    for ci, cate in enumerate(("bus", "road")):                       # sorted folder order: bus -> 0, road -> 1
+        sk, key, text = sketches[cate]
+        out = cv2.imread(os.path.join(res, "%s_%s_output.png" % (cate, key[:-4])))
+        inp = cv2.imread(os.path.join(res, "%s_%s_input.png" % (cate, key[:-4])))
+        assert out.shape == (64, 64, 3) and inp.shape == (64, 64, 3)
+        want_in = thicken_drawings(sk.astype(np.float32)) if cate == "road" else sk
+        assert np.array_equal(inp, want_in)                           # the road's strokes are one pixel thicker
+        x = torch.from_numpy(want_in.astype(np.float64) / 255 * 2 - 1).permute(2, 0, 1)[None]
+        ids = torch.tensor([preprocess_sentence(text, default_vocab_dict(), 15)])
+        ref = O.generator_forward(gp, x, ids, torch.tensor([ci]), noise.double(), 16)
+        want = (((ref[0].permute(1, 2, 0).numpy() + 1) / 2) * 255)[:, :, ::-1].astype(np.uint8)
+        assert np.abs(out.astype(int) - want.astype(int)).max() <= 1
