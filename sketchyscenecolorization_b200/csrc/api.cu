@@ -4,6 +4,7 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fgc {
 static thread_local char g_err[512] = "";
@@ -40,12 +41,43 @@ static void crc_init() {
   g_crc_ready = true;
 }
 
+#if defined(__x86_64__)
+// SSE4.2 crc32 instructions (Castagnoli polynomial in hardware): ~8 GB/s on one dependency chain against ~1 GB/s for the
+// table walk -- the TFRecord reader checks 0.9 MB of payload per sample (tfrecord_input.py)
+static inline uint64_t crc32c_hw_u64(uint64_t c, uint64_t v) { __asm__("crc32q %1, %0" : "+r"(c) : "rm"(v)); return c; }
+static inline uint32_t crc32c_hw_u8(uint32_t c, uint8_t v) { __asm__("crc32b %1, %0" : "+r"(c) : "rm"(v)); return c; }
+static bool cpu_has_sse42() {
+  unsigned a = 1, b = 0, c = 0, d = 0;
+  __asm__ volatile("cpuid" : "+a"(a), "=b"(b), "+c"(c), "=d"(d));
+  return (c >> 20) & 1u;
+}
+static uint32_t crc32c_hw(const uint8_t* p, size_t n, uint32_t c) {
+  while (n && (reinterpret_cast<uintptr_t>(p) & 7)) { c = crc32c_hw_u8(c, *p++); n--; }
+  uint64_t c64 = c;
+  while (n >= 32) {
+    c64 = crc32c_hw_u64(c64, *reinterpret_cast<const uint64_t*>(p));
+    c64 = crc32c_hw_u64(c64, *reinterpret_cast<const uint64_t*>(p + 8));
+    c64 = crc32c_hw_u64(c64, *reinterpret_cast<const uint64_t*>(p + 16));
+    c64 = crc32c_hw_u64(c64, *reinterpret_cast<const uint64_t*>(p + 24));
+    p += 32; n -= 32;
+  }
+  while (n >= 8) { c64 = crc32c_hw_u64(c64, *reinterpret_cast<const uint64_t*>(p)); p += 8; n -= 8; }
+  c = (uint32_t)c64;
+  while (n--) c = crc32c_hw_u8(c, *p++);
+  return c;
+}
+#endif
+
 extern "C" {
 /* crc32c of data[0:n) continuing from `crc` (0 for a fresh checksum); unmasked */
 unsigned int fgc_crc32c(const void* data, size_t n, unsigned int crc) {
-  if (!g_crc_ready) crc_init();
   const uint8_t* p = static_cast<const uint8_t*>(data);
   uint32_t c = ~crc;
+#if defined(__x86_64__)
+  static const bool hw = cpu_has_sse42() && !getenv("FGC_CRC_TABLE");
+  if (hw) return ~crc32c_hw(p, n, c);
+#endif
+  if (!g_crc_ready) crc_init();
   while (n && (reinterpret_cast<uintptr_t>(p) & 7)) { c = g_crc_tab[0][(c ^ *p++) & 0xFF] ^ (c >> 8); n--; }
   while (n >= 8) {
     uint64_t v = *reinterpret_cast<const uint64_t*>(p) ^ c;

@@ -33,7 +33,7 @@ import struct
 import numpy as np
 import torch
 
-from .tf_bundle import _field_bytes, _parse, _read_varint, _varint, crc32c, mask_crc
+from .tf_bundle import _field_bytes, _read_varint, _varint, crc32c, mask_crc
 
 RAW = 384            # "cannot change" (input_pipeline.py:82,87)
 TEXT_LEN = 15
@@ -61,6 +61,39 @@ def read_tfrecord(path, verify=True):
             if verify and mask_crc(crc32c(data)) != struct.unpack("<I", tail)[0]:
                 raise ValueError("%s: corrupt record data" % path)
             yield data
+
+
+def _crc_view(view):
+    """CRC-32C of a buffer without copying it (tf_bundle.crc32c takes the pointer of a numpy view)."""
+    return crc32c(np.frombuffer(view, dtype=np.uint8))
+
+
+def read_tfrecord_views(path, verify=True):
+    """Like read_tfrecord, but the file is memory mapped and every payload is a memoryview into the mapping: the queues hold
+    hundreds of 0.9 MB records in their shuffle buffer, and a view costs neither the allocation nor the copy (nor the
+    memory) of a bytes object.  The mapping lives as long as any view of it."""
+    import mmap
+    size = os.path.getsize(path)
+    if size == 0:
+        return
+    with open(path, "rb") as f:
+        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+    mv = memoryview(mm)
+    pos = 0
+    while pos < size:
+        if pos + 12 > size:
+            raise ValueError("%s: truncated record header" % path)
+        length, lcrc = struct.unpack_from("<QI", mv, pos)
+        if verify and mask_crc(_crc_view(mv[pos:pos + 8])) != lcrc:
+            raise ValueError("%s: corrupt record length" % path)
+        start, end = pos + 12, pos + 12 + length
+        if end + 4 > size:
+            raise ValueError("%s: truncated record" % path)
+        data = mv[start:end]
+        if verify and mask_crc(_crc_view(data)) != struct.unpack_from("<I", mv, end)[0]:
+            raise ValueError("%s: corrupt record data" % path)
+        yield data
+        pos = end + 4
 
 
 def write_tfrecord(path, records):
@@ -93,30 +126,58 @@ def encode_example(features):
     return _field_bytes(1, out)                                                                 # Example.features
 
 
+def _fields(mv):
+    """(field number, wire type, value) of one message held in a memoryview; length-delimited values are VIEWS, not copies
+    (a record carries two 442 KB payloads five messages deep: copying them at every level dominated the reader)."""
+    pos, n = 0, len(mv)
+    while pos < n:
+        key, pos = _read_varint(mv, pos)
+        num, wt = key >> 3, key & 7
+        if wt == 0:
+            v, pos = _read_varint(mv, pos)
+        elif wt == 2:
+            ln, pos = _read_varint(mv, pos)
+            v = mv[pos:pos + ln]
+            pos += ln
+        elif wt == 5:
+            v = struct.unpack_from("<I", mv, pos)[0]
+            pos += 4
+        elif wt == 1:
+            v = struct.unpack_from("<Q", mv, pos)[0]
+            pos += 8
+        else:
+            raise ValueError("unsupported protobuf wire type %d" % wt)
+        yield num, wt, v
+
+
+_SMALL = 4096       # byte values up to this size are returned as `bytes`, larger ones as memoryviews into the record
+
+
 def parse_example(buf):
-    """-> dict name -> bytes (single bytes value) | list of bytes | list of ints | list of floats."""
+    """-> dict name -> bytes | memoryview (single bytes value; memoryview above 4 KB) | list of them | list of ints |
+    list of floats."""
     out = {}
-    for num, _, feats in _parse(buf):
+    for num, _, feats in _fields(memoryview(buf)):
         if num != 1:
             continue
-        for n2, _, entry in _parse(feats):
+        for n2, _, entry in _fields(feats):
             if n2 != 1:
                 continue
             key, val = None, None
-            for n3, _, v in _parse(entry):
+            for n3, _, v in _fields(entry):
                 if n3 == 1:
-                    key = v.decode()
+                    key = bytes(v).decode()
                 elif n3 == 2:
                     val = v
             if key is None or val is None:
                 continue
-            for kind, _, lst in _parse(val):
+            for kind, _, lst in _fields(val):
                 if kind == 1:                                        # BytesList
-                    items = [v for n5, _, v in _parse(lst) if n5 == 1]
+                    items = [(v if len(v) > _SMALL else bytes(v)) for n5, _, v in _fields(lst) if n5 == 1]
                     out[key] = items[0] if len(items) == 1 else items
                 elif kind == 2:                                      # FloatList: packed or repeated fixed32
                     vals = []
-                    for n5, wt, v in _parse(lst):
+                    for n5, wt, v in _fields(lst):
                         if n5 == 1 and wt == 2:
                             vals += list(struct.unpack("<%df" % (len(v) // 4), v))
                         elif n5 == 1:
@@ -124,7 +185,7 @@ def parse_example(buf):
                     out[key] = vals
                 elif kind == 3:                                      # Int64List: packed or repeated varints
                     vals = []
-                    for n5, wt, v in _parse(lst):
+                    for n5, wt, v in _fields(lst):
                         if n5 == 1 and wt == 2:
                             pos = 0
                             while pos < len(v):
@@ -157,8 +218,9 @@ def raw_paired_example(ex, distance_map=False):
         sketch = distance_map_255(sketch)
     text = np.frombuffer(ex['Text_vocab_indices'], dtype=np.uint8).astype(np.int32).reshape(TEXT_LEN)
     cid = ex['Category_id']
-    return dict(cartoon=cartoon, sketch=sketch, cls=int(cid[0] if isinstance(cid, list) else cid), category=ex['Category'].decode(),
-                name=ex['ImageName'].decode(), color_text=ex['Color_text'].decode(), text=text)
+    return dict(cartoon=cartoon, sketch=sketch, cls=int(cid[0] if isinstance(cid, list) else cid),
+                category=bytes(ex['Category']).decode(), name=bytes(ex['ImageName']).decode(),
+                color_text=bytes(ex['Color_text']).decode(), text=text)
 
 
 def _record_files(data_base_dir, mode):
@@ -168,20 +230,36 @@ def _record_files(data_base_dir, mode):
     return files
 
 
-def _device_batch(samples, ops, dim, seed, dequantize=True, want_d=False):
-    """Raw samples -> the batch dict of the queues.  The uint8 payloads are stacked into (pinned) host memory, copied to the
-    device of `ops` and resized / normalised / dequantised / transposed there by ONE call (ops.paired_input ->
-    fgc_paired_input): 0.88 MB per sample cross the bus instead of the 0.88 MB of fp32 results plus the host arithmetic."""
+def _host_buffers(n, sketch_dtype, pinned):
+    shape = (n, RAW, RAW, 3)
+    mk = lambda dt: torch.empty(shape, dtype=dt, pin_memory=pinned)          # noqa: E731
+    return mk(torch.uint8), mk(torch.float32 if sketch_dtype == np.float32 else torch.uint8)
+
+
+def _fill_slot(rec, distance_map, cartoon_np, sketch_np, i):
+    """Worker-thread half of a batch: parse one record (zero copy) and copy its two payloads into slot i of the batch's host
+    buffers (numpy's copy releases the GIL).  Returns the sample's metadata."""
+    s = raw_paired_example(parse_example(rec), distance_map)
+    np.copyto(cartoon_np[i], s.pop('cartoon'))
+    np.copyto(sketch_np[i], s.pop('sketch'))
+    return s
+
+
+def _finish_batch(meta, cartoon, sketch, ops, dim, seed, dequantize=True, want_d=False, slot=None):
+    """Consumer half: ONE copy of the raw uint8 batch to the device of `ops` (0.88 MB per sample instead of the fp32 results)
+    and ONE device call for everything per pixel (ops.paired_input -> fgc_paired_input).  `slot`: the reusable host-buffer
+    record of the batch; the event recorded after the copies tells the producer when the buffers may be overwritten."""
     dev = torch.device(getattr(ops, 'device', 'cpu'))
-    cartoon = torch.from_numpy(np.stack([s['cartoon'] for s in samples]))
-    sketch = torch.from_numpy(np.stack([s['sketch'] for s in samples]))
     if dev.type == 'cuda':
-        cartoon, sketch = cartoon.pin_memory().to(dev, non_blocking=True), sketch.pin_memory().to(dev, non_blocking=True)
+        cartoon, sketch = cartoon.to(dev, non_blocking=True), sketch.to(dev, non_blocking=True)
+        if slot is not None:
+            slot['event'] = torch.cuda.Event()
+            slot['event'].record()
     images, sketches = ops.paired_input(cartoon, sketch, dim, seed=seed, dequantize=dequantize)
-    out = dict(sketch=sketches, images=images, cls=torch.tensor([s['cls'] for s in samples], dtype=torch.int32),
-               text=torch.from_numpy(np.stack([s['text'] for s in samples])),
-               categories=[s['category'] for s in samples], image_names=[s['name'] for s in samples],
-               color_texts=[s['color_text'] for s in samples])
+    out = dict(sketch=sketches, images=images, cls=torch.tensor([s['cls'] for s in meta], dtype=torch.int32),
+               text=torch.from_numpy(np.stack([s['text'] for s in meta])),
+               categories=[s['category'] for s in meta], image_names=[s['name'] for s in meta],
+               color_texts=[s['color_text'] for s in meta])
     if want_d:                                              # the discriminator's own queue: same record fields under *_d names
         out['images_d'], out['cls_d'] = out['images'], out['cls']
     return out
@@ -189,14 +267,18 @@ def _device_batch(samples, ops, dim, seed, dequantize=True, want_d=False):
 
 class PairedTrainInput:
     """build_input_queue_paired('train') (:131-157): an endless shuffled stream of batches.  Files are visited in a
-    shuffled order every epoch (string_input_producer(shuffle=True)); samples pass through a shuffle buffer that holds
-    at least `min_after_dequeue` records before one is drawn at random (tf.train.shuffle_batch).  Record parsing (and the
-    distance transform, when asked for) runs in `num_threads` host threads, `prefetch` batches ahead of the consumer; the
-    pixel work of a batch is one device call on the consumer's stream (`ops`: the model's operator set).  Under data
-    parallelism give every rank its own `seed`.  main_procedure.train uses two of these (the second feeds images_d)."""
+    shuffled order every epoch (string_input_producer(shuffle=True)); records pass through a shuffle buffer that holds
+    at least `min_after_dequeue` of them before one is drawn at random (tf.train.shuffle_batch).  A reader thread streams
+    the files (hardware CRC-32C of every frame) into the buffer; `num_threads` workers parse the drawn records without
+    copying and write their payloads straight into the batch's pinned host buffers (plus the distance transform, when asked
+    for); `prefetch` batches are in flight ahead of the consumer, whose share is one host-to-device copy and one device call
+    per batch on its own stream (`ops`: the model's operator set).  Under data parallelism give every rank its own `seed`.
+    main_procedure.train uses two of these (the second feeds images_d)."""
 
     def __init__(self, batch_size, ops, data_base_dir='data', small=False, distance_map=False, min_after_dequeue=512, seed=0,
                  num_threads=4, prefetch=4, mode='train'):
+        import queue
+        import threading
         from concurrent.futures import ThreadPoolExecutor
         self.n, self.ops, self.dim, self.dm = batch_size, ops, ((64, 64) if small else (192, 192)), distance_map
         self.files = _record_files(data_base_dir, mode)
@@ -205,21 +287,45 @@ class PairedTrainInput:
         self.rng = np.random.default_rng(seed)
         self.min_after = min_after_dequeue
         self.pool = ThreadPoolExecutor(max_workers=num_threads)
+        self.pinned = torch.device(getattr(ops, 'device', 'cpu')).type == 'cuda'
         self.buf = []
-        self.raw = self._raw_stream()
         self.prefetch = prefetch
         self.pending = []
+        self._slots = []                                    # reusable (pinned) host buffers: allocated once, prefetch + 1 of them
+        # the file order is drawn here (seeded) and handed to the reader, so that a seed fixes the whole stream
+        self._orders = queue.Queue(maxsize=2)
+        self._records = queue.Queue(maxsize=max(2 * batch_size, 64))
+        self._closed = False
+        self._orders.put(self.rng.permutation(len(self.files)))
+        self._reader = threading.Thread(target=self._read_loop, daemon=True)
+        self._reader.start()
 
-    def _raw_stream(self):
+    def _read_loop(self):
+        try:
+            while not self._closed:
+                order = self._orders.get()
+                for i in order:
+                    for rec in read_tfrecord_views(self.files[i]):
+                        self._records.put(rec)
+                        if self._closed:
+                            return
+                self._records.put(None)                 # end of an epoch: the consumer draws the next file order
+        except Exception as e:                          # noqa: BLE001 -- surfaced in the consumer thread
+            self._records.put(e)
+
+    def _next_record(self):
         while True:
-            order = self.rng.permutation(len(self.files))
-            for i in order:
-                for rec in read_tfrecord(self.files[i]):
-                    yield rec
+            rec = self._records.get()
+            if rec is None:
+                self._orders.put(self.rng.permutation(len(self.files)))
+                continue
+            if isinstance(rec, Exception):
+                raise rec
+            return rec
 
     def _draw_raw(self):
         while len(self.buf) < self.min_after + 1:
-            self.buf.append(next(self.raw))
+            self.buf.append(self._next_record())
         j = int(self.rng.integers(len(self.buf)))
         self.buf[j], self.buf[-1] = self.buf[-1], self.buf[j]
         return self.buf.pop()
@@ -227,7 +333,23 @@ class PairedTrainInput:
     def _submit(self):
         raws = [self._draw_raw() for _ in range(self.n)]
         seed = int(self.rng.integers(1 << 62))              # the batch's dequantisation-noise stream
-        return seed, [self.pool.submit(lambda r: raw_paired_example(parse_example(r), self.dm), r) for r in raws]
+        slot = self._free_slot()
+        cn, sn = slot['cartoon'].numpy(), slot['sketch'].numpy()
+        futs = [self.pool.submit(_fill_slot, r, self.dm, cn, sn, i) for i, r in enumerate(raws)]
+        return seed, futs, slot
+
+    def _free_slot(self):
+        """A host-buffer pair no batch in flight is using (page-locked memory is expensive to allocate: cudaHostAlloc)."""
+        busy = {id(p[2]) for p in self.pending}
+        for sl in self._slots:
+            if id(sl) not in busy:
+                if sl.get('event') is not None:            # its last host-to-device copy must have left the buffers
+                    sl['event'].synchronize()
+                    sl['event'] = None
+                return sl
+        cartoon, sketch = _host_buffers(self.n, np.float32 if self.dm else np.uint8, self.pinned)
+        self._slots.append(dict(cartoon=cartoon, sketch=sketch, event=None))
+        return self._slots[-1]
 
     def __iter__(self):
         return self
@@ -235,8 +357,12 @@ class PairedTrainInput:
     def __next__(self):
         while len(self.pending) < self.prefetch:
             self.pending.append(self._submit())
-        seed, futs = self.pending.pop(0)
-        return _device_batch([f.result() for f in futs], self.ops, self.dim, seed, want_d=True)
+        seed, futs, slot = self.pending.pop(0)
+        meta = [f.result() for f in futs]
+        return _finish_batch(meta, slot['cartoon'], slot['sketch'], self.ops, self.dim, seed, want_d=True, slot=slot)
+
+    def close(self):
+        self._closed = True
 
 
 class PairedEvalInput:
@@ -249,10 +375,14 @@ class PairedEvalInput:
         self.files = _record_files(data_base_dir, mode)
 
     def __iter__(self):
-        batch, k = [], 0
+        pinned = torch.device(getattr(self.ops, 'device', 'cpu')).type == 'cuda'
+        recs, k = [], 0
         for f in self.files:
-            for rec in read_tfrecord(f):
-                batch.append(raw_paired_example(parse_example(rec), self.dm))
-                if len(batch) == self.n:
-                    yield _device_batch(batch, self.ops, self.dim, seed=k)
-                    batch, k = [], k + 1
+            for rec in read_tfrecord_views(f):
+                recs.append(rec)
+                if len(recs) == self.n:
+                    cartoon, sketch = _host_buffers(self.n, np.float32 if self.dm else np.uint8, pinned)
+                    cn, sn = cartoon.numpy(), sketch.numpy()
+                    meta = [_fill_slot(r, self.dm, cn, sn, i) for i, r in enumerate(recs)]
+                    yield _finish_batch(meta, cartoon, sketch, self.ops, self.dim, seed=k)
+                    recs, k = [], k + 1

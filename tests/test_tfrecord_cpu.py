@@ -254,3 +254,37 @@ def test_test_mode_end_to_end(tmp_path):
         ref = O.generator_forward(gp, x, ids, torch.tensor([ci]), noise.double(), 16)
         want = (((ref[0].permute(1, 2, 0).numpy() + 1) / 2) * 255)[:, :, ::-1].astype(np.uint8)
         assert np.abs(out.astype(int) - want.astype(int)).max() <= 1
+
+
+def test_mapped_reader_and_hardware_crc(tmp_path):
+    """read_tfrecord_views (memory-mapped, zero-copy payloads) yields what read_tfrecord yields and rejects the same corruption;
+    the SSE4.2 CRC-32C path of fgc_crc32c equals the table walk (FGC_CRC_TABLE=1 forces the latter) on ragged lengths, unaligned
+    starts and continued checksums."""
+    import subprocess
+    import sys
+    payloads = [b"", b"x", os.urandom(100003), bytes(range(256)) * 5]
+    path = str(tmp_path / "a.tfrecord")
+    TI.write_tfrecord(path, payloads)
+    assert [bytes(v) for v in TI.read_tfrecord_views(path)] == payloads
+    empty = str(tmp_path / "empty.tfrecord")
+    open(empty, "wb").close()
+    assert list(TI.read_tfrecord_views(empty)) == []
+    bad = bytearray(open(path, "rb").read())
+    bad[12 + 4 + 13 + 40] ^= 0x10                                         # inside the third record's payload
+    open(path, "wb").write(bad)
+    with pytest.raises(ValueError):
+        list(TI.read_tfrecord_views(path))
+    open(path, "wb").write(bytes(bad[:-3]))
+    with pytest.raises(ValueError):
+        list(TI.read_tfrecord_views(path))
+    code = ("import sys, random; sys.path.insert(0, %r)\n"
+            "from sketchyscenecolorization_b200.tf_bundle import crc32c\n"
+            "random.seed(1); buf = bytes(random.getrandbits(8) for _ in range(70001))\n"
+            "print([crc32c(buf[a:b], c) for a, b, c in ((0, 70001, 0), (3, 77, 0), (1, 65536, 12345), (5, 5, 7), (7, 8, 0), (2, 41, 0xFFFFFFFF))])"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for env in ({}, {"FGC_CRC_TABLE": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **env), timeout=300)
+        assert r.returncode == 0, r.stderr[-1000:]
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] and outs[0].startswith("[")
