@@ -115,6 +115,32 @@ def synth_batch(n, seed):
                 text=torch.randint(2, 58, (n, 15), generator=g).int(), noise=torch.randn(n, 256, generator=g))
 
 
+def write_synthetic_tfrecords(base, n_records=256, files=4, seed=7):
+    """A synthetic dataset in the reference's own on-disk format (data_preparation.py:21-32: raw 384x384x3 uint8 picture and
+    sketch, class id, 15 caption ids) for `--input tfrecord`: the e2e leg then starts from RECORD FILES -- framing, CRC-32C,
+    proto parsing, shuffle queue, raw uint8 host-to-device copy, fgc_paired_input -- instead of from ready fp32 tensors."""
+    import numpy as np
+    from sketchyscenecolorization_b200 import tfrecord_input as TI
+    d = os.path.join(base, "tfrecord", "train")
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    per = n_records // files
+    for f in range(files):
+        recs = []
+        for i in range(per):
+            sk = np.full((384, 384, 3), 255, np.uint8)
+            for _ in range(6):
+                r, c = rng.integers(8, 370, 2)
+                sk[r:r + 2, c // 2:c // 2 + 180] = 0
+                sk[r // 2:r // 2 + 180, c:c + 2] = 0
+            recs.append(TI.encode_example(dict(
+                ImageName=("img%d_%d.png" % (f, i)).encode(), cartoon_data=rng.integers(0, 256, (384, 384, 3), dtype=np.uint8).tobytes(),
+                sketch_data=sk.tobytes(), Category=b"bus", Category_id=int(rng.integers(0, 25)), Color_text=b"synthetic",
+                Text_vocab_indices=rng.integers(2, 58, 15, dtype=np.uint8).tobytes())))
+        TI.write_tfrecord(os.path.join(d, "part%d.tfrecord" % f), recs)
+    return base
+
+
 # ----------------------------------------------------------------------------------------------------------
 # reference arm: the CPU restatement of the reference graph (TensorFlow 1.x cannot be installed here)
 # ----------------------------------------------------------------------------------------------------------
@@ -290,11 +316,32 @@ def run_product(args):
     # ---- end to end: pinned host buffers -> device every step, losses read back every step
     d_keys = ("sketch", "images_d", "cls", "cls_d", "noise", "text")
     g_keys = ("sketch", "images", "cls", "noise", "text")
+    queues = None
+    if args.input == "tfrecord":        # start from record files in the reference's dataset format (rank 0 writes them)
+        import tempfile
+        from sketchyscenecolorization_b200.tfrecord_input import PairedTrainInput
+        base = os.path.join(tempfile.gettempdir(), "fgc_bench_records_%d" % os.getuid())
+        if local == 0 and not os.path.isdir(os.path.join(base, "tfrecord", "train")):
+            write_synthetic_tfrecords(base)
+        barrier()
+        queues = [PairedTrainInput(BS, ops, base, min_after_dequeue=128, seed=s0 + rank, num_threads=6) for s0 in (1234, 4321)]
+
+        def from_queue(q, keys):
+            b = next(q)
+            b["noise"] = torch.randn(BS, 256, device=dev)
+            b["text"] = b["text"].to(dev, non_blocking=True) if graphs else b["text"].numpy()
+            for k in ("cls", "cls_d"):
+                b[k] = b[k].to(dev, non_blocking=True)
+            return {k: b[k] for k in keys}
+        for _ in range(2):              # fill the shuffle buffers and the prefetch pipeline outside the timed region
+            from_queue(queues[0], d_keys), from_queue(queues[1], g_keys)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        if graphs:      # pinned host tensors are copied straight into the graphs' static input buffers
+        if queues is not None:
+            bA, bB = from_queue(queues[0], d_keys), from_queue(queues[1], g_keys)
+        elif graphs:      # pinned host tensors are copied straight into the graphs' static input buffers
             bA, bB = {k: hostA[k] for k in d_keys}, {k: hostB[k] for k in g_keys}
         else:
             bA = {k: (hostA[k].to(dev, non_blocking=True) if k != "text" else hostA[k].numpy()) for k in d_keys}
@@ -337,7 +384,12 @@ def run_product(args):
                            "loss_d": ld_v, "loss_g": lg_v},
                 "clocks": clocks,
                 "e2e": {"value": ips_e2e, "unit": "images/s",
-                        "h2d_bytes_per_step": h2d_bytes(hostA, d_keys) + h2d_bytes(hostB, g_keys), "d2h_bytes_per_step": 8},
+                        "h2d_bytes_per_step": (h2d_bytes(hostA, d_keys) + h2d_bytes(hostB, g_keys)) if queues is None
+                        else 2 * BS * (2 * 384 * 384 * 3 + 15 * 4 + 4),
+                        "d2h_bytes_per_step": 8,
+                        "input": "pinned fp32 tensors" if queues is None else
+                        "TFRecord files -> mapped reader + CRC-32C + proto parse + shuffle queue (host threads) -> raw uint8 H2D -> "
+                        "fgc_paired_input"},
                 "gpu_launches": launches,
                 "roofline": roof}
         if cpu:
@@ -361,6 +413,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-type", dest="block_type", default="MRU", choices=["MRU", "Pix2Pix", "Residual"],
                     help="network family (obj_colorization_main.py --block_type); the BASELINE metric is the MRU default")
+    ap.add_argument("--input", default="tensors", choices=["tensors", "tfrecord"],
+                    help="source of the e2e leg: ready pinned fp32 tensors (default) or synthetic TFRecord files through the "
+                         "real input pipeline")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -18,4 +18,7 @@ for bt in Pix2Pix Residual; do
   timeout -k 10 600 python bench.py --steps 5 --warmup 3 --block-type $bt > gpurun_out/bench_${bt}_$T.json 2> gpurun_out/bench_${bt}_$T.err
   tail -c 2500 gpurun_out/bench_${bt}_$T.json; tail -n 5 gpurun_out/bench_${bt}_$T.err
 done
+echo "=== bench, e2e leg from TFRecord files (MRU)"
+timeout -k 10 600 python bench.py --steps 5 --warmup 3 --input tfrecord --no-cpu-baseline > gpurun_out/bench_tfrecord_$T.json 2> gpurun_out/bench_tfrecord_$T.err
+tail -c 2500 gpurun_out/bench_tfrecord_$T.json; tail -n 5 gpurun_out/bench_tfrecord_$T.err
 echo "=== bg 768 timing"; timeout -k 10 300 python scripts/prof_bg.py > gpurun_out/prof_bg_$T.log 2>&1; cat gpurun_out/prof_bg_$T.log
