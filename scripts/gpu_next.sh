@@ -21,4 +21,7 @@ done
 echo "=== bench, e2e leg from TFRecord files (MRU)"
 timeout -k 10 600 python bench.py --steps 5 --warmup 3 --input tfrecord --no-cpu-baseline > gpurun_out/bench_tfrecord_$T.json 2> gpurun_out/bench_tfrecord_$T.err
 tail -c 2500 gpurun_out/bench_tfrecord_$T.json; tail -n 5 gpurun_out/bench_tfrecord_$T.err
+echo "=== the same with the raw-batch copies on a side stream"
+FGC_INPUT_SIDE_STREAM=1 timeout -k 10 600 python bench.py --steps 5 --warmup 3 --input tfrecord --no-cpu-baseline > gpurun_out/bench_tfrecord_side_$T.json 2> gpurun_out/bench_tfrecord_side_$T.err
+tail -c 1200 gpurun_out/bench_tfrecord_side_$T.json; tail -n 5 gpurun_out/bench_tfrecord_side_$T.err
 echo "=== bg 768 timing"; timeout -k 10 300 python scripts/prof_bg.py > gpurun_out/prof_bg_$T.log 2>&1; cat gpurun_out/prof_bg_$T.log

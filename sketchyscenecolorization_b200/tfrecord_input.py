@@ -245,12 +245,25 @@ def _fill_slot(rec, distance_map, cartoon_np, sketch_np, i):
     return s
 
 
-def _finish_batch(meta, cartoon, sketch, ops, dim, seed, dequantize=True, want_d=False, slot=None):
+def _finish_batch(meta, cartoon, sketch, ops, dim, seed, dequantize=True, want_d=False, slot=None, copy_stream=None):
     """Consumer half: ONE copy of the raw uint8 batch to the device of `ops` (0.88 MB per sample instead of the fp32 results)
     and ONE device call for everything per pixel (ops.paired_input -> fgc_paired_input).  `slot`: the reusable host-buffer
     record of the batch; the event recorded after the copies tells the producer when the buffers may be overwritten."""
     dev = torch.device(getattr(ops, 'device', 'cpu'))
-    if dev.type == 'cuda':
+    if dev.type == 'cuda' and copy_stream is not None:
+        # the copies go out on their own stream: the host runs ahead of the device, so they overlap the kernels of the
+        # previous training step still executing on the compute stream, which then only waits for the event
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(copy_stream):
+            cartoon, sketch = cartoon.to(dev, non_blocking=True), sketch.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        cur.wait_event(ev)
+        cartoon.record_stream(cur)
+        sketch.record_stream(cur)
+        if slot is not None:
+            slot['event'] = ev
+    elif dev.type == 'cuda':
         cartoon, sketch = cartoon.to(dev, non_blocking=True), sketch.to(dev, non_blocking=True)
         if slot is not None:
             slot['event'] = torch.cuda.Event()
@@ -276,7 +289,7 @@ class PairedTrainInput:
     main_procedure.train uses two of these (the second feeds images_d)."""
 
     def __init__(self, batch_size, ops, data_base_dir='data', small=False, distance_map=False, min_after_dequeue=512, seed=0,
-                 num_threads=4, prefetch=4, mode='train'):
+                 num_threads=4, prefetch=4, mode='train', side_stream=None):
         import queue
         import threading
         from concurrent.futures import ThreadPoolExecutor
@@ -288,6 +301,9 @@ class PairedTrainInput:
         self.min_after = min_after_dequeue
         self.pool = ThreadPoolExecutor(max_workers=num_threads)
         self.pinned = torch.device(getattr(ops, 'device', 'cpu')).type == 'cuda'
+        if side_stream is None:                             # opt-in until it has been measured (FGC_INPUT_SIDE_STREAM=1)
+            side_stream = os.environ.get("FGC_INPUT_SIDE_STREAM") == "1"
+        self.copy_stream = torch.cuda.Stream(device=getattr(ops, 'device')) if (side_stream and self.pinned) else None
         self.buf = []
         self.prefetch = prefetch
         self.pending = []
@@ -359,7 +375,8 @@ class PairedTrainInput:
             self.pending.append(self._submit())
         seed, futs, slot = self.pending.pop(0)
         meta = [f.result() for f in futs]
-        return _finish_batch(meta, slot['cartoon'], slot['sketch'], self.ops, self.dim, seed, want_d=True, slot=slot)
+        return _finish_batch(meta, slot['cartoon'], slot['sketch'], self.ops, self.dim, seed, want_d=True, slot=slot,
+                             copy_stream=self.copy_stream)
 
     def close(self):
         self._closed = True
