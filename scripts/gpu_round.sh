@@ -17,7 +17,7 @@ if ! tail -n 1 gpurun_out/conv_fwd.log | grep -q passed || grep -q failed gpurun
   export FGC_HALO=${FALLBACK_HALO:-0} FGC_SMALL=${FALLBACK_SMALL:-0}
   echo "continuing with FGC_HALO=$FGC_HALO FGC_SMALL=$FGC_SMALL"
 fi
-bash scripts/gpu_tests.sh ops_base model
+bash scripts/gpu_tests.sh ops_base model input variants
 echo "=== smoke"; timeout -k 10 300 python __graft_entry__.py --smoke > gpurun_out/smoke_$T.log 2>&1; tail -n 3 gpurun_out/smoke_$T.log
 fi
 echo "=== prof_conv"; timeout -k 10 300 python scripts/prof_conv.py > gpurun_out/prof_conv_$T.log 2>&1; cat gpurun_out/prof_conv_$T.log
