@@ -288,3 +288,53 @@ def test_mapped_reader_and_hardware_crc(tmp_path):
         assert r.returncode == 0, r.stderr[-1000:]
         outs.append(r.stdout.strip())
     assert outs[0] == outs[1] and outs[0].startswith("[")
+
+
+def test_data_preparation_writes_what_the_queues_read(tmp_path):
+    """data_preparation.py (images + captions -> per-category TFRecords) followed by the ordered queue: every field comes back,
+    the class id is the index of the category folder, the caption ids are the reference's."""
+    import cv2
+    import importlib.util
+    import json
+    from oracle import input_oracle as IO
+    from sketchyscenecolorization_b200.text_processing import default_vocab_dict, preprocess_sentence
+    from torch_ops import TorchOps
+    spec = importlib.util.spec_from_file_location("data_preparation", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "data_preparation", "data_preparation.py"))
+    DP = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(DP)
+    base = tmp_path / "data"
+    rng = np.random.default_rng(3)
+    pics = {}
+    for cate, n in (("bus", 2), ("cat", 1)):
+        for sub in ("cartoon", "edgemap"):
+            os.makedirs(base / "images" / cate / sub)
+        os.makedirs(base / "captions" / cate)
+        entries = []
+        for i in range(n):
+            key = "%s_%d.png" % (cate, i)
+            img = rng.integers(0, 256, (384, 384, 3), dtype=np.uint8)
+            edge = np.full((384, 384, 3), 255, np.uint8)
+            edge[100 + i:104 + i, 30:350] = 0
+            cv2.imwrite(str(base / "images" / cate / "cartoon" / key), img[:, :, ::-1])
+            cv2.imwrite(str(base / "images" / cate / "edgemap" / key), edge)
+            entries.append(dict(key=key, color_text="the %s is yellow with blue windows" % cate))
+            pics[key] = (img, edge)
+        for split in ("train", "val"):
+            json.dump(entries, open(base / "captions" / cate / (split + ".json"), "w"))
+    written = DP.data_preparation(dataset="both", data_base_dir=str(base), text_len=15)
+    assert written == {("train", "bus"): 2, ("train", "cat"): 1, ("val", "bus"): 2, ("val", "cat"): 1}
+    assert sorted(os.listdir(base / "tfrecord" / "val")) == ["bus.tfrecord", "cat.tfrecord"]
+    batches = list(TI.PairedEvalInput("val", 3, TorchOps(torch.float32), str(base)))
+    assert len(batches) == 1
+    b = batches[0]
+    assert b["image_names"] == ["bus_0.png", "bus_1.png", "cat_0.png"] and b["categories"] == ["bus", "bus", "cat"]
+    assert b["cls"].tolist() == [0, 0, 1]
+    assert b["text"][2].tolist() == preprocess_sentence("the cat is yellow with blue windows", default_vocab_dict(), 15)
+    for i, key in enumerate(b["image_names"]):
+        img, edge = pics[key]
+        _, want_s = IO.paired_preprocess(img, edge, (192, 192))
+        assert np.array_equal(b["sketch"][i].numpy(), want_s)
+        want_i, _ = IO.paired_preprocess(img, edge, (192, 192))
+        d = b["images"][i].numpy() - want_i
+        assert d.min() >= 0 and d.max() <= 2.0 / 256 + 1e-6
