@@ -208,6 +208,13 @@ int fgc_reg_loss(const float* flat, const long long* start, const int32_t* len, 
 int fgc_adam_step(float* flat, float* grad, float* v, const long long* start, const int32_t* len, const float* reg,
                   int nchunks, float lr_t, const float* lr_t_dev, float beta2, float eps, int add_reg, fgc_stream s);
 
+/* The reference's other optimisers (graph_single.get_optimizer, :584-593) over the same chunk table: kind 1 =
+ * RMSPropOptimizer(decay 0.9, momentum 0, epsilon 1e-10), s1 = rms (the caller initialises it to 1 as TF does); kind 2 =
+ * AdadeltaOptimizer (rho 0.95, epsilon 1e-8), s1 = accum, s2 = accum_update; kind 3 = AdagradOptimizer, s1 = accumulator
+ * (initial value 0.1).  g += reg*w first (if add_reg); lr_dev (device scalar, may be NULL) overrides lr. */
+int fgc_opt_step(float* flat, float* grad, float* s1, float* s2 /*kind 2 only*/, const long long* start, const int32_t* len,
+                 const float* reg, int nchunks, int kind, float lr, const float* lr_dev, int add_reg, fgc_stream s);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Layout passes that put the 4x4 layers of the Pix2Pix / Residual variants (models_collection.nchw_conv, :380-391;
  * nchw_deconv = tf.nn.conv2d_transpose, :394-405) on the stride-1 SAME convolutions above ("phase form"):

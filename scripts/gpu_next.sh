@@ -13,6 +13,7 @@ run() {  # name, timeout, args...
 run pix2pix_model 300 tests/test_pix2pix_gpu.py -k "inference or training or bf16"
 run residual 400 tests/test_residual_gpu.py
 run bg 600 tests/test_bg_gpu.py
+run optimizers 120 tests/test_optimizers_gpu.py
 for bt in Pix2Pix Residual; do
   echo "=== bench --block-type $bt"
   timeout -k 10 600 python bench.py --steps 5 --warmup 3 --block-type $bt > gpurun_out/bench_${bt}_$T.json 2> gpurun_out/bench_${bt}_$T.err

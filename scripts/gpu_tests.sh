@@ -19,6 +19,6 @@ for t in $tiers; do
     conv_wgrad) run conv_wgrad 150 tests/test_ops_gpu.py -k "tcgen05 and conv_wgrad" ;;
     model)      run model 900 tests/test_model_gpu.py ;;
     input)      run input 300 tests/test_tfrecord_gpu.py ;;
-    variants)   run variants 900 tests/test_pix2pix_gpu.py tests/test_residual_gpu.py tests/test_bg_gpu.py ;;
+    variants)   run variants 900 tests/test_pix2pix_gpu.py tests/test_residual_gpu.py tests/test_bg_gpu.py tests/test_optimizers_gpu.py ;;
   esac
 done

@@ -129,6 +129,7 @@ SIGNATURES = {
     "fgc_smooth_l1": [_P, _P, _I, _LL, _F, _P, _I, _P, _P],
     "fgc_reg_loss": [_P, _P, _P, _P, _I, _P, _I, _P],
     "fgc_adam_step": [_P, _P, _P, _P, _P, _P, _I, _F, _P, _F, _F, _I, _P],
+    "fgc_opt_step": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P, _I, _P],
 }
 _RESTYPE = {"fgc_last_error": C.c_char_p, "fgc_launch_count": C.c_longlong, "fgc_conv2d_ws_bytes": C.c_size_t}
 

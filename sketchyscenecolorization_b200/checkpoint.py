@@ -50,15 +50,26 @@ def _collect(model, counter):
     for store, suffix in ((model.gstore, ""), (model.dstore, "_1")):
         if store is None:
             continue
+        opt = getattr(store, "optimizer", "adam")
+        slot = lambda t, k, v: t[store.offsets[k]:store.offsets[k] + v.numel()].view(v.shape).detach().float().cpu().numpy()  # noqa: E731
         for k, v in store.p.items():
             out[k] = v.detach().float().cpu().numpy()
-            o = store.offsets[k]
-            out[k + "/Adam"] = np.zeros(tuple(v.shape), dtype=np.float32)
-            out[k + "/Adam_1"] = store.adam_v[o:o + v.numel()].view(v.shape).detach().float().cpu().numpy()
+            if opt == "adam":
+                out[k + "/Adam"] = np.zeros(tuple(v.shape), dtype=np.float32)
+                out[k + "/Adam_1"] = slot(store.adam_v, k, v)
+            elif opt == "rmsprop":                          # slots `rms` and `momentum` (zero: momentum = 0.0)
+                out[k + "/RMSProp"] = slot(store.adam_v, k, v)
+                out[k + "/RMSProp_1"] = np.zeros(tuple(v.shape), dtype=np.float32)
+            elif opt == "adadelta":                         # slots `accum` and `accum_update`
+                out[k + "/Adadelta"] = slot(store.adam_v, k, v)
+                out[k + "/Adadelta_1"] = slot(store.opt_s2, k, v)
+            else:
+                out[k + "/Adagrad"] = slot(store.adam_v, k, v)
         for k, v in store.state.items():
             out[k] = v.detach().float().cpu().numpy()
-        out["beta1_power" + suffix] = np.float32(0.0)
-        out["beta2_power" + suffix] = np.float32(_BETA2 ** (store.adam_t + 1))
+        if opt == "adam":
+            out["beta1_power" + suffix] = np.float32(0.0)
+            out["beta2_power" + suffix] = np.float32(_BETA2 ** (store.adam_t + 1))
     out["Variable"] = np.int32(counter)
     return out
 
@@ -103,10 +114,14 @@ def restore(model, prefix, strict=True):
                 v.copy_(torch.from_numpy(np.asarray(t[k], dtype=np.float32)).reshape(v.shape).to(v.dtype))
             elif strict:
                 raise KeyError("snapshot %s has no variable %s" % (prefix, k))
+        s1_name = {"adam": "/Adam_1", "rmsprop": "/RMSProp", "adadelta": "/Adadelta", "adagrad": "/Adagrad"}[
+            getattr(store, "optimizer", "adam")]
         for k, v in store.p.items():
-            if k + "/Adam_1" in t:
-                o = store.offsets[k]
-                store.adam_v[o:o + v.numel()].copy_(torch.from_numpy(np.asarray(t[k + "/Adam_1"], dtype=np.float32)).reshape(-1))
+            o = store.offsets[k]
+            if k + s1_name in t:
+                store.adam_v[o:o + v.numel()].copy_(torch.from_numpy(np.asarray(t[k + s1_name], dtype=np.float32)).reshape(-1))
+            if getattr(store, "opt_s2", None) is not None and k + "/Adadelta_1" in t:
+                store.opt_s2[o:o + v.numel()].copy_(torch.from_numpy(np.asarray(t[k + "/Adadelta_1"], dtype=np.float32)).reshape(-1))
         if "beta2_power" + suffix in t:
             b2 = float(t["beta2_power" + suffix])
             store.adam_t = max(0, int(round(math.log(max(b2, 1e-300)) / math.log(_BETA2))) - 1)

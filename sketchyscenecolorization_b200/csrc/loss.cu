@@ -102,6 +102,38 @@ __global__ void adam_step_kernel(float* __restrict__ flat, float* __restrict__ g
     flat[s0 + i] = w - lr_t * g / (sqrtf(vv) + eps);
   }
 }
+// the reference's other optimisers (graph_single.get_optimizer, :584-593), same chunk table as Adam.
+// kind 1 RMSProp (decay 0.9, momentum 0, eps 1e-10), 2 Adadelta (rho 0.95, eps 1e-8), 3 Adagrad
+__global__ void opt_step_kernel(float* __restrict__ flat, float* __restrict__ grad, float* __restrict__ s1, float* __restrict__ s2,
+                                const long long* __restrict__ start, const int32_t* __restrict__ len,
+                                const float* __restrict__ reg, int kind, float lr, const float* __restrict__ lr_dev, int add_reg) {
+  if (lr_dev) lr = *lr_dev;
+  int ch = blockIdx.x;
+  long long s0 = start[ch];
+  int L = len[ch];
+  float r = add_reg ? reg[ch] : 0.f;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    float w = flat[s0 + i];
+    float g = grad[s0 + i] + r * w;
+    grad[s0 + i] = g;
+    if (kind == 1) {
+      float ms = 0.9f * s1[s0 + i] + 0.1f * g * g;
+      s1[s0 + i] = ms;
+      flat[s0 + i] = w - lr * g / sqrtf(ms + 1e-10f);
+    } else if (kind == 2) {
+      float acc = 0.95f * s1[s0 + i] + 0.05f * g * g;
+      float au = s2[s0 + i];
+      float upd = sqrtf(au + 1e-8f) * rsqrtf(acc + 1e-8f) * g;
+      s1[s0 + i] = acc;
+      s2[s0 + i] = 0.95f * au + 0.05f * upd * upd;
+      flat[s0 + i] = w - lr * upd;
+    } else {
+      float acc = s1[s0 + i] + g * g;
+      s1[s0 + i] = acc;
+      flat[s0 + i] = w - lr * g / sqrtf(acc);
+    }
+  }
+}
 }  // namespace fgc
 
 using namespace fgc;
@@ -149,6 +181,14 @@ int fgc_adam_step(float* flat, float* grad, float* v, const long long* start, co
   adam_step_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(flat, grad, v, start, len, reg, lr_t, lr_t_dev, beta2, eps, add_reg);
   count_launch();
   FGC_LAUNCH_CHECK("adam_step");
+  return FGC_OK;
+}
+int fgc_opt_step(float* flat, float* grad, float* s1, float* s2, const long long* start, const int32_t* len, const float* reg,
+                 int nchunks, int kind, float lr, const float* lr_dev, int add_reg, fgc_stream stream) {
+  FGC_REQUIRE(kind >= 1 && kind <= 3 && (kind != 2 || s2 != nullptr), "opt_step: kind %d (1 RMSProp, 2 Adadelta with two slots, 3 Adagrad)", kind);
+  opt_step_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(flat, grad, s1, s2, start, len, reg, kind, lr, lr_dev, add_reg);
+  count_launch();
+  FGC_LAUNCH_CHECK("opt_step");
   return FGC_OK;
 }
 

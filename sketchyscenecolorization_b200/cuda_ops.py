@@ -521,6 +521,15 @@ class CudaOps(OpsBase):
                                      store.chunk_start.numel(), float(lr_t), None if lr_dev is None else self._f32(lr_dev),
                                      0.9, 1e-8, 1 if add_reg_grad else 0, self._s()), "adam_step")
 
+    _OPT_KIND = {'rmsprop': 1, 'adadelta': 2, 'adagrad': 3}
+
+    def optimizer_step(self, store, kind, lr, add_reg_grad=True, lr_dev=None):
+        s2 = store.opt_s2 if kind == 'adadelta' else None
+        check(self.lib.fgc_opt_step(self._f32(store.flat), self._f32(store.grad), self._f32(store.adam_v),
+                                    None if s2 is None else self._f32(s2), self._p(store.chunk_start), self._p(store.chunk_len),
+                                    self._p(store.chunk_reg), store.chunk_start.numel(), self._OPT_KIND[kind], float(lr),
+                                    None if lr_dev is None else self._f32(lr_dev), 1 if add_reg_grad else 0, self._s()), "opt_step")
+
 
 def enable_op_timing(ops):
     """Debug aid: wrap every operator of a CudaOps instance with CUDA events (synchronising after each call) and

@@ -69,8 +69,8 @@ def train(**kwargs):
     small, lstm_hybrid = Config.small_img != 0, Config.LSTM_hybrid != 0
     if Config.block_type not in ('MRU', 'Pix2Pix', 'Residual'):
         raise ValueError("block_type %r (MRU, Pix2Pix, Residual)" % (Config.block_type,))
-    if Config.optimizer != 'Adam':
-        raise NotImplementedError("optimizer %r: the path is built for the default Adam(beta1=0, beta2=0.9)" % Config.optimizer)
+    if Config.optimizer.lower() not in ('adam', 'rmsprop', 'adadelta', 'adagrad'):
+        raise ValueError("optimizer %r (RMSprop, Adam, AdaDelta, AdaGrad)" % (Config.optimizer,))
     iter_from = kwargs['iter_from']
     world = int(kwargs.get('world_size', 1))
     print('Iteration starts from: %d' % iter_from)
@@ -78,7 +78,7 @@ def train(**kwargs):
     model = _build_model(Config.train_precision, SIZE[small], Config.vocab_size, lstm_hybrid)
     model.initialize(seed=int(kwargs.get('seed', 0)))
     tr = FgColorTrainer(model, lr_g=Config.lr_G, lr_d=Config.lr_D, max_iter=max_iter_step,
-                        process_group=kwargs.get('process_group'), world_size=world)
+                        process_group=kwargs.get('process_group'), world_size=world, optimizer=Config.optimizer)
     if iter_from > 0:
         prefix = checkpoint.latest_checkpoint(ckpt_dir)
         print('Restore:', prefix)

@@ -256,3 +256,10 @@ class OpsBase:
     def adam_step(self, store, lr, add_reg_grad=True, lr_dev=None):
         """g += reg*w; v = .9v+.1g^2; w -= lr*sqrt(1-.9^t)*g/(sqrt(v)+1e-8); increments store.adam_t first."""
         raise NotImplementedError
+
+    def optimizer_step(self, store, kind, lr, add_reg_grad=True, lr_dev=None):
+        """The reference's other optimisers (graph_single.get_optimizer, :584-593) as one fused pass over the flat buffers;
+        kind 'rmsprop' (decay 0.9, momentum 0, eps 1e-10; store.adam_v is the rms slot, initialised to 1), 'adadelta'
+        (rho 0.95, eps 1e-8; slots store.adam_v and store.opt_s2, zeros), 'adagrad' (store.adam_v = accumulator, initialised
+        to 0.1).  lr_dev: optional device scalar overriding lr (CUDA-graph replay)."""
+        raise NotImplementedError

@@ -317,7 +317,9 @@ class ParamStore:
         self.n_flat = off
         self.flat = torch.zeros(off, dtype=dtype, device=self.device)
         self.grad = torch.zeros(off, dtype=dtype, device=self.device)
-        self.adam_v = torch.zeros(off, dtype=dtype, device=self.device)
+        self.adam_v = torch.zeros(off, dtype=dtype, device=self.device)     # Adam v / RMSProp rms / Adadelta accum / Adagrad accum
+        self.opt_s2 = None                                                  # Adadelta accum_update (allocated on demand)
+        self.optimizer = 'adam'
         self.adam_t = 0
         self.p, self.g = OrderedDict(), OrderedDict()
         self.state = OrderedDict()      # non-trainable (SN `u`)
@@ -340,6 +342,18 @@ class ParamStore:
         self.chunk_start = torch.tensor([r[0] for r in rows], dtype=torch.int64, device=self.device)
         self.chunk_len = torch.tensor([r[1] for r in rows], dtype=torch.int32, device=self.device)
         self.chunk_reg = torch.tensor([r[2] for r in rows], dtype=torch.float32, device=self.device)
+
+    OPT_SLOT_INIT = {'adam': 0.0, 'rmsprop': 1.0, 'adadelta': 0.0, 'adagrad': 0.1}   # TF-1 slot initialisers
+
+    def set_optimizer(self, kind):
+        """Choose the optimiser whose slots this store carries (graph_single.get_optimizer, :584-593) and reset them."""
+        kind = kind.lower()
+        if kind not in self.OPT_SLOT_INIT:
+            raise ValueError("optimizer %r (Adam, RMSprop, AdaDelta, AdaGrad)" % kind)
+        self.optimizer = kind
+        self.adam_v.fill_(self.OPT_SLOT_INIT[kind])
+        self.opt_s2 = torch.zeros_like(self.adam_v) if kind == 'adadelta' else None
+        self.adam_t = 0
 
     # --- counts (reference: main_procedure.print_parameter_count, :28-59) ---
     def num_trainable_tensors(self):
@@ -394,5 +408,7 @@ class ParamStore:
                 t = (torch.rand(shape, generator=g, dtype=f64) * 2 - 1) * lim
             dst = self.p[s.name] if s.trainable else self.state[s.name]
             dst.copy_(t.to(self.dtype))
-        self.adam_v.zero_()
+        self.adam_v.fill_(self.OPT_SLOT_INIT[self.optimizer])
+        if self.opt_s2 is not None:
+            self.opt_s2.zero_()
         self.adam_t = 0

@@ -150,8 +150,12 @@ class FgColorTrainer:
     G_KEYS = ("sketch", "images", "cls", "text", "noise")
 
     def __init__(self, model, *, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=None, world_size=1,
-                 use_cuda_graphs=False):
+                 use_cuda_graphs=False, optimizer='Adam'):
         self.m, self.lr_g, self.lr_d, self.max_iter = model, lr_g, lr_d, max_iter
+        self.optimizer = optimizer.lower()                    # graph_single.get_optimizer (:584-593)
+        for store in (model.gstore, model.dstore):
+            if store is not None and store.optimizer != self.optimizer:
+                store.set_optimizer(self.optimizer)
         self.pg, self.world = process_group, world_size
         self.counter = 0
         self.use_graphs = use_cuda_graphs
@@ -166,16 +170,22 @@ class FgColorTrainer:
             store.grad.mul_(1.0 / self.world)
 
     # ---- eager steps
+    def _apply(self, store, lr, lr_dev):
+        if self.optimizer == 'adam':
+            self.m.ops.adam_step(store, lr, lr_dev=lr_dev)
+        else:
+            self.m.ops.optimizer_step(store, self.optimizer, lr, lr_dev=lr_dev)
+
     def _d_eager(self, batch, lr_dev=None):
         out = self.m.d_step_grads(batch)
         self._allreduce(self.m.dstore)
-        self.m.ops.adam_step(self.m.dstore, self.lr_d * lr_decay(self.counter, self.max_iter), lr_dev=lr_dev)
+        self._apply(self.m.dstore, self.lr_d * lr_decay(self.counter, self.max_iter), lr_dev)
         return out
 
     def _g_eager(self, batch, lr_dev=None):
         out = self.m.g_step_grads(batch)
         self._allreduce(self.m.gstore)
-        self.m.ops.adam_step(self.m.gstore, self.lr_g * lr_decay(self.counter, self.max_iter), lr_dev=lr_dev)
+        self._apply(self.m.gstore, self.lr_g * lr_decay(self.counter, self.max_iter), lr_dev)
         return out
 
     # ---- CUDA-graph steps
@@ -210,7 +220,8 @@ class FgColorTrainer:
             v = torch.as_tensor(v) if not torch.is_tensor(v) else v
             st["inputs"][k].copy_(v, non_blocking=True)
         store.adam_t += 1
-        st["lr"].fill_(base_lr * lr_decay(self.counter, self.max_iter) * math.sqrt(1.0 - 0.9 ** store.adam_t))
+        bias = math.sqrt(1.0 - 0.9 ** store.adam_t) if self.optimizer == 'adam' else 1.0      # Adam's step-size correction
+        st["lr"].fill_(base_lr * lr_decay(self.counter, self.max_iter) * bias)
         st["graph"].replay()
         return st["outputs"]
 

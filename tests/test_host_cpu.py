@@ -98,3 +98,44 @@ def test_adam_matches_oracle_update(setup):
     m.dstore.flat.copy_(before)
     m.dstore.adam_v.zero_()
     m.dstore.adam_t = 0
+
+
+@pytest.mark.parametrize("name", ["RMSprop", "AdaDelta", "AdaGrad"])
+def test_other_optimizers_match_oracle_updates(setup, name, tmp_path):
+    """--optimizer RMSprop | AdaDelta | AdaGrad (graph_single.get_optimizer, :584-593): two D steps against the oracle's
+    restatement of the TF-1 update rules (slot initialisers included), and the slots survive a snapshot under TF's slot names."""
+    from sketchyscenecolorization_b200 import checkpoint, tf_bundle
+    s = setup
+    ops = s["ops"]
+    m = FgColorModel(ops, "cpu", size=SIZE, H=H, W=W, param_dtype=torch.float64)
+    m.initialize(seed=3, perturb_tables=0.1)
+    tr = FgColorTrainer(m, lr_g=2e-4, lr_d=1e-4, max_iter=1000, optimizer=name)
+    kind = name.lower()
+    p = m.dstore.flat.clone()
+    s1 = torch.full_like(p, {"rmsprop": 1.0, "adadelta": 0.0, "adagrad": 0.1}[kind])
+    s2 = torch.zeros_like(p)
+    assert torch.equal(m.dstore.adam_v, s1)
+    for step in range(2):
+        tr.d_step(s["bb"])
+        g = m.dstore.grad.clone()                   # includes the decay term after the step
+        lr = 1e-4 * lr_decay(tr.counter, 1000)
+        if kind == "rmsprop":
+            p, s1 = O.rmsprop_update(p, g, s1, lr)
+        elif kind == "adadelta":
+            p, s1, s2 = O.adadelta_update(p, g, s1, s2, lr)
+        else:
+            p, s1 = O.adagrad_update(p, g, s1, lr)
+        assert (m.dstore.flat - p).abs().max().item() < 1e-12, (name, step)
+        m.dstore.flat.copy_(p)                      # keep the two trajectories on the same point
+    prefix = checkpoint.save(m, str(tmp_path), 1, 2)
+    keys = set(tf_bundle.read_bundle(prefix))
+    slot = {"rmsprop": "RMSProp", "adadelta": "Adadelta", "adagrad": "Adagrad"}[kind]
+    assert "discriminator/Conv/weights/" + slot in keys and "discriminator/Conv/weights/Adam" not in keys
+    m2 = FgColorModel(ops, "cpu", size=SIZE, H=H, W=W, param_dtype=torch.float64)
+    FgColorTrainer(m2, optimizer=name)
+    checkpoint.restore(m2, prefix)
+    for k, v in m.dstore.p.items():
+        o = m.dstore.offsets[k]
+        assert torch.equal(m2.dstore.adam_v[o:o + v.numel()].float(), m.dstore.adam_v[o:o + v.numel()].float()), k
+        if kind == "adadelta":
+            assert torch.equal(m2.dstore.opt_s2[o:o + v.numel()].float(), m.dstore.opt_s2[o:o + v.numel()].float()), k

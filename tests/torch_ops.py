@@ -452,3 +452,23 @@ class TorchOps(OpsBase):
         store.adam_v.mul_(0.9).add_(0.1 * g * g)
         lr_t = lr * math.sqrt(1 - 0.9 ** store.adam_t)
         store.flat -= lr_t * g / (store.adam_v.sqrt() + 1e-8)
+
+    def optimizer_step(self, store, kind, lr, add_reg_grad=True, lr_dev=None):
+        if add_reg_grad:
+            self.add_reg_grad(store)
+        if lr_dev is not None:
+            lr = float(lr_dev)
+        g = store.grad
+        if kind == 'rmsprop':
+            store.adam_v.mul_(0.9).add_(0.1 * g * g)
+            store.flat -= lr * g / (store.adam_v + 1e-10).sqrt()
+        elif kind == 'adadelta':
+            store.adam_v.mul_(0.95).add_(0.05 * g * g)
+            upd = (store.opt_s2 + 1e-8).sqrt() * (store.adam_v + 1e-8).rsqrt() * g
+            store.opt_s2.mul_(0.95).add_(0.05 * upd * upd)
+            store.flat -= lr * upd
+        elif kind == 'adagrad':
+            store.adam_v.add_(g * g)
+            store.flat -= lr * g / store.adam_v.sqrt()
+        else:
+            raise ValueError(kind)
