@@ -22,10 +22,27 @@ def _valid(appendix):
     return bool(appendix) and len(appendix.split('-')) == 6
 
 
+def _process_group():
+    """(process group, world size) under torchrun, else (None, 1)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return None, 1
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        backend = os.environ.get("FGC_DIST_BACKEND", "nccl")
+        if backend == "nccl":
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group(backend)
+    return dist.group.WORLD, world
+
+
 def launch_training(**kwargs):
     appendix = kwargs["resume_from"]
+    pg, world = _process_group()
     if appendix is None or appendix == '':
-        cur_time = strftime("%Y-%m-%d-%H-%M-%S", gmtime())
+        # one time stamp for all ranks: each would otherwise read its own clock and may land in a different second / directory
+        cur_time = main_procedure.shared_string(strftime("%Y-%m-%d-%H-%M-%S", gmtime()), pg, world)
         log_dir, ckpt_dir = os.path.join(OUTPUTS, cur_time, 'log'), os.path.join(OUTPUTS, cur_time, 'snapshot')
         os.makedirs(log_dir, exist_ok=True)
         os.makedirs(ckpt_dir, exist_ok=True)
@@ -48,15 +65,7 @@ def launch_training(**kwargs):
             json.dump(kwargs, fp, indent=4)
         print("Launching training from checkpoint: %s" % appendix)
     Config.set_from_dict(kwargs)
-    extra = {}
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        if not dist.is_initialized():
-            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-            dist.init_process_group("nccl")
-        extra = dict(process_group=dist.group.WORLD, world_size=world)
+    extra = dict(process_group=pg, world_size=world) if world > 1 else {}
     status = main_procedure.train(**kwargs, **extra)
     return status, appendix
 
@@ -105,7 +114,8 @@ def build_parser():
     p.add_argument('--vocab_size', '-vs', type=int, default=58)
     p.add_argument('--disc_iterations', '-di', type=int, default=1)
     p.add_argument('--ld', '-ld', type=int, default=10)
-    p.add_argument('--num_gpu', '-gpu', type=int, default=1, help="informational: one process per GPU under torchrun")
+    p.add_argument('--num_gpu', '-gpu', type=int, default=1,
+                   help="GPUs to train on; N > 1 re-launches this command under torch.distributed.run, one process per GPU")
     p.add_argument('--extra_info', '-ei', type=str, default='')
     p.add_argument('--summary_write_freq', '-swf', type=int, default=100)
     p.add_argument('--save_model_freq', '-smf', type=int, default=10000)
@@ -116,8 +126,27 @@ def build_parser():
     return p
 
 
+def _relaunch_data_parallel(n, argv):
+    """`--num_gpu N` in the reference builds N in-graph towers (graph_single.py:107-218); here it means N processes, one per
+    GPU: replace this process by `python -m torch.distributed.run --nproc-per-node N <this command>`."""
+    import socket
+    import sys
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.abspath(__file__)] + list(argv)
+    print("Launching %d data-parallel processes: %s" % (n, " ".join(cmd)))
+    os.execv(sys.executable, cmd)
+
+
 def main(argv=None):
+    import sys
+    argv = list(sys.argv[1:] if argv is None else argv)
     args = build_parser().parse_args(argv)
+    if args.mode == 'train' and args.num_gpu > 1 and "WORLD_SIZE" not in os.environ:
+        _relaunch_data_parallel(args.num_gpu, argv)
     if args.mode == 'inference':
         assert args.infer_name != '' and args.instruction != ''
     d_params = {

@@ -59,6 +59,27 @@ def print_parameter_count(model, verbose=False):
     return g, d
 
 
+def any_rank_true(flag, process_group=None, world_size=1, device="cpu"):
+    """Data-parallel agreement on a per-rank condition (a NaN loss): every rank must leave the session loop in the same
+    iteration, or the others would wait for it in the next all-reduce.  One tiny MAX all-reduce; a no-op for one process."""
+    if world_size <= 1:
+        return bool(flag)
+    import torch.distributed as dist
+    t = torch.tensor([1.0 if flag else 0.0], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=process_group)
+    return bool(t.item() > 0)
+
+
+def shared_string(value, process_group=None, world_size=1, src=0):
+    """Rank `src`'s string on every rank (the run directory's time stamp must not differ between ranks)."""
+    if world_size <= 1:
+        return value
+    import torch.distributed as dist
+    box = [value]
+    dist.broadcast_object_list(box, src=src, group=process_group)
+    return box[0]
+
+
 def train(**kwargs):
     """Alternating D / G optimisation (main_procedure.py:62-242).  kwargs: iter_from, and optionally `input_iter`
     (two-queue stand-in yielding batch dicts) and `process_group`/`world_size` for data parallelism."""
@@ -120,12 +141,12 @@ def train(**kwargs):
         for j in range(diters):                                       # each sess.run dequeues a fresh batch
             od = tr.d_step(fetch())
             loss_d_out = float(od['loss'])
-            if math.isnan(loss_d_out):
+            if any_rank_true(math.isnan(loss_d_out), kwargs.get('process_group'), world, dev):
                 print("NaN occurred during training D")
                 return -1
         og = tr.g_step(fetch())
         loss_g_out = float(og['loss'])
-        if math.isnan(loss_g_out):
+        if any_rank_true(math.isnan(loss_g_out), kwargs.get('process_group'), world, dev):
             print("NaN occurred during training G")
             return -1
         if want_summary and summ is not None:                         # scalar names of graph_single.py:71-98

@@ -47,7 +47,12 @@ def _worker(rank, world, port, out_dir):
     tr = FgColorTrainer(m, max_iter=100, process_group=dist.group.WORLD, world_size=world)
     tr.d_step(_batch(10 + rank))
     tr.g_step(_batch(20 + rank))
-    torch.save(dict(d=m.dstore.flat.clone(), g=m.gstore.flat.clone(), dg=m.dstore.grad.clone(), gg=m.gstore.grad.clone()),
+    # session-loop agreement helpers (main_procedure.train under data parallelism)
+    from sketchyscenecolorization_b200 import main_procedure as MP
+    agree = [MP.any_rank_true(rank == 1, dist.group.WORLD, world), MP.any_rank_true(False, dist.group.WORLD, world)]
+    stamp = MP.shared_string("stamp-from-rank-%d" % rank, dist.group.WORLD, world)
+    torch.save(dict(d=m.dstore.flat.clone(), g=m.gstore.flat.clone(), dg=m.dstore.grad.clone(), gg=m.gstore.grad.clone(),
+                    agree=agree, stamp=stamp),
                os.path.join(out_dir, "rank%d.pt" % rank))
     dist.destroy_process_group()
 
@@ -59,6 +64,9 @@ def test_two_rank_gloo_allreduce_matches_mean_of_shard_gradients(tmp_path):
     # replicas stay bit-identical: same averaged gradient, same Adam update
     for k in ("d", "g", "dg", "gg"):
         assert torch.equal(r0[k], r1[k]), k
+    # a NaN seen by ONE rank ends the loop on every rank; the run directory's time stamp is rank 0's everywhere
+    assert r0["agree"] == [True, False] and r1["agree"] == [True, False]
+    assert r0["stamp"] == r1["stamp"] == "stamp-from-rank-0"
     # and the averaged D gradient is the mean of the two shard gradients computed independently
     from torch_ops import TorchOps
     ops = TorchOps(torch.float64)
@@ -100,3 +108,25 @@ def test_snapshot_round_trip_reference_layout(tmp_path):
     checkpoint.save(m, ck, 199, counter=200)
     assert checkpoint.latest_checkpoint(ck).endswith("model_199.ckpt-199")
     assert open(os.path.join(ck, "checkpoint")).read().count("all_model_checkpoint_paths") == 2
+
+
+def test_num_gpu_relaunches_under_torch_distributed_run(monkeypatch):
+    """`--num_gpu N` (N in-graph towers in the reference) re-launches the same command with one process per GPU."""
+    import sys
+    import obj_colorization_main as M
+    seen = {}
+
+    def fake_execv(exe, cmd):
+        seen["cmd"] = cmd
+        raise SystemExit(0)
+    monkeypatch.setattr(os, "execv", fake_execv)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    try:
+        M.main(["--mode", "train", "--num_gpu", "4", "--batch_size", "64"])
+    except SystemExit:
+        pass
+    cmd = seen["cmd"]
+    assert cmd[0] == sys.executable and cmd[1:3] == ["-m", "torch.distributed.run"]
+    assert cmd[cmd.index("--nproc-per-node") + 1] == "4" and cmd[cmd.index("--master-addr") + 1] == "127.0.0.1"
+    assert cmd[-6:] == ["--mode", "train", "--num_gpu", "4", "--batch_size", "64"] and cmd[-7].endswith("obj_colorization_main.py")
+    assert M.main_procedure.any_rank_true(True) is True and M.main_procedure.shared_string("x") == "x"
