@@ -136,6 +136,12 @@ def train(**kwargs):
             elapsed = curr_time - prev_time
             print("Now at iteration %d. Elapsed time: %.5fs. Average time: %.5fs/iter"
                   % (i, elapsed, elapsed / float(Config.count_left_time_freq)))
+            if elapsed != float("inf"):                               # main_procedure.py:182-188
+                left_sec = (max_iter_step - i) * (elapsed / float(Config.count_left_time_freq))
+                left_day = int(left_sec / 24 / 60 / 60)
+                left_hour = int((left_sec - (24 * 60 * 60) * left_day) / 60 / 60)
+                left_min = int((left_sec - (24 * 60 * 60) * left_day - (60 * 60) * left_hour) / 60)
+                print("Left time:%dd %dh %dm" % (left_day, left_hour, left_min))
             prev_time = curr_time
         want_summary = i % Config.summary_write_freq == 0
         for j in range(diters):                                       # each sess.run dequeues a fresh batch
