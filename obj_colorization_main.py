@@ -38,6 +38,8 @@ def _process_group():
 
 
 def launch_training(**kwargs):
+    # objects a caller may hand through (a resident model, input iterators): not parameters, not written to param_<iter>.json
+    runtime = {k: kwargs.pop(k) for k in ('model', 'input_iter', 'input_iter_d') if k in kwargs}
     appendix = kwargs["resume_from"]
     pg, world = _process_group()
     if appendix is None or appendix == '':
@@ -66,7 +68,7 @@ def launch_training(**kwargs):
         print("Launching training from checkpoint: %s" % appendix)
     Config.set_from_dict(kwargs)
     extra = dict(process_group=pg, world_size=world) if world > 1 else {}
-    status = main_procedure.train(**kwargs, **extra)
+    status = main_procedure.train(**kwargs, **extra, **runtime)
     return status, appendix
 
 

@@ -96,8 +96,10 @@ def train(**kwargs):
     world = int(kwargs.get('world_size', 1))
     print('Iteration starts from: %d' % iter_from)
 
-    model = _build_model(Config.train_precision, SIZE[small], Config.vocab_size, lstm_hybrid)
-    model.initialize(seed=int(kwargs.get('seed', 0)))
+    model = kwargs.get('model')                                     # a resident model (tests); else built on the CUDA operator set
+    if model is None:
+        model = _build_model(Config.train_precision, SIZE[small], Config.vocab_size, lstm_hybrid)
+        model.initialize(seed=int(kwargs.get('seed', 0)))
     tr = FgColorTrainer(model, lr_g=Config.lr_G, lr_d=Config.lr_D, max_iter=max_iter_step,
                         process_group=kwargs.get('process_group'), world_size=world, optimizer=Config.optimizer)
     if iter_from > 0:

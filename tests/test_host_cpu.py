@@ -139,3 +139,70 @@ def test_other_optimizers_match_oracle_updates(setup, name, tmp_path):
         assert torch.equal(m2.dstore.adam_v[o:o + v.numel()].float(), m.dstore.adam_v[o:o + v.numel()].float()), k
         if kind == "adadelta":
             assert torch.equal(m2.dstore.opt_s2[o:o + v.numel()].float(), m.dstore.opt_s2[o:o + v.numel()].float()), k
+
+
+def test_session_loop_snapshots_resume_and_nan_status(tmp_path, monkeypatch):
+    """main_procedure.train (main_procedure.py:62-242) on a resident CPU model: alternating D / G steps on fresh batches,
+    summaries every `summary_write_freq`, snapshots at i % save_model_freq == save_model_freq - 1 in the reference's layout,
+    resume from the latest one (iter_from = its step + 1, obj_colorization_main.py:58-62), status -1 on a NaN loss."""
+    import json
+    import os
+    import obj_colorization_main as M
+    from sketchyscenecolorization_b200 import checkpoint, main_procedure
+    from sketchyscenecolorization_b200.config import Config
+    monkeypatch.chdir(tmp_path)
+    ops = TorchOps(torch.float32)
+    m = FgColorModel(ops, "cpu", size=16, H=64, W=64)
+    m.initialize(seed=1)
+    params = dict(dataset_type="train", resume_from="", batch_size=2, max_iter_step=3, disc_iterations=1, optimizer="Adam", lr_G=2e-4,
+                  lr_D=1e-4, num_gpu=1, small_img=1, distance_map=0, LSTM_hybrid=1, block_type="MRU", vocab_size=58, ld=10,
+                  extra_info="", summary_write_freq=1, save_model_freq=2, count_left_time_freq=1, count_inception_score_freq=-1,
+                  infer_name="", instruction="")
+    before = m.gstore.flat.clone()
+    status, stamp = M.launch_training(model=m, **params)
+    assert status == 0 and len(stamp.split("-")) == 6
+    run = tmp_path / "outputs" / stamp
+    assert json.load(open(run / "log" / "param_0.json"))["batch_size"] == 2
+    assert checkpoint.latest_checkpoint(str(run / "snapshot")).endswith("model_1.ckpt-1")            # saved at i = 1 only
+    recs = [json.loads(ln) for ln in open(run / "log" / "summaries.jsonl")]
+    assert [r["step"] for r in recs] == [0, 1, 2] and all(k in recs[0] for k in ("GAN_loss/G", "ACGAN_loss/D", "l1_perceptual_loss"))
+    assert not torch.equal(before, m.gstore.flat)
+    # resume: a fresh model picks up weights, optimiser slots and the counter from the snapshot and continues at iteration 2
+    m2 = FgColorModel(ops, "cpu", size=16, H=64, W=64)
+    m2.initialize(seed=99)
+    params2 = dict(params, resume_from=stamp, max_iter_step=4)
+    status, stamp2 = M.launch_training(model=m2, **params2)
+    assert status == 0 and stamp2 == stamp and os.path.exists(run / "log" / "param_2.json")
+    assert checkpoint.latest_checkpoint(str(run / "snapshot")).endswith("model_3.ckpt-3")
+    assert m2.dstore.adam_t == 4                                                                    # 2 restored + 2 new steps
+    # NaN: the loop returns -1 (the caller restarts from the latest snapshot)
+    from sketchyscenecolorization_b200.input_pipeline import SyntheticInput
+
+    class Poisoned(SyntheticInput):
+        def __next__(self):
+            b = super().__next__()
+            b["images_d"][0, 0, 0, 0] = float("nan")
+            return b
+    Config.set_from_dict(dict(params2, log_dir=str(run / "log"), ckpt_dir=str(run / "snapshot"), max_iter_step=6))
+    assert main_procedure.train(iter_from=4, model=m2, input_iter_d=Poisoned(2, 64, 64, seed=5)) == -1
+
+
+def test_width_preserving_encoder_block(setup):
+    """size 8: generator unit 1 maps 8 -> 8 channels, so the block has no 1x1 skip convolution (mru.py:446-452 is guarded by
+    cin != cout) and the hidden state joins the sum as it is -- forward and both gradient sets against the oracle."""
+    ops = setup["ops"]
+    m = FgColorModel(ops, "cpu", size=8, H=64, W=64, param_dtype=torch.float64)
+    m.initialize(seed=3, perturb_tables=0.1)
+    assert "generator/mru_conv_unit_t_1_layer_0/Conv_3/weights" not in m.gstore.p
+    gp = {k: v.clone().requires_grad_(True) for k, v in m.gstore.state_dict().items()}
+    dp = {k: v.clone().requires_grad_(True) for k, v in m.dstore.state_dict().items()}
+    gspecs, dspecs = O.generator_specs(8, 58, 64, 64), O.discriminator_specs(8)
+    b, bb = setup["b"], setup["bb"]
+    r = m.d_step_grads(bb)
+    ld, _, _ = O.d_step_loss(gp, dp, gspecs, dspecs, b, 8)
+    assert abs(r["loss"].item() - ld.item()) < 1e-10
+    assert _worst(m.dstore, O.grads_of(ld, dp, dspecs), ops) < 1e-7
+    r = m.g_step_grads(bb)
+    lg, _, _, _ = O.g_step_loss(gp, dp, gspecs, dspecs, b, 8)
+    assert abs(r["loss"].item() - lg.item()) < 1e-10
+    assert _worst(m.gstore, O.grads_of(lg, gp, gspecs), ops) < 1e-7
