@@ -3,7 +3,8 @@
 NOT YET RUN ON HARDWARE (written after the round's GPU budget was spent): skipped unless FGC_UNVERIFIED=1.  The operators the
 network is made of have run on a B200 (tests/test_ops_gpu.py, tests/test_pix2pix_gpu.py), the host code is checked against the
 oracle on the CPU (tests/test_bg_cpu.py).  The published size -- 768 x 768, ngf 64, batch 1 -- is compared against the
-oracle on the host in fp64, with the fp32 run beside it as the yardstick (a few minutes of CPU work)."""
+oracle on the host in fp64, with the fp32 run beside it as the yardstick (seconds of CPU work; at this size the two differ
+by 1.25e-3)."""
 import os
 
 import pytest
