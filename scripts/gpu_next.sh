@@ -7,8 +7,8 @@ T=${TAG:-r2a}
 run() {  # name, timeout, args...
   local name=$1 to=$2; shift 2
   echo "=== $name"
-  FGC_UNVERIFIED=1 timeout -k 10 "$to" python -m pytest -v -m gpu -p no:cacheprovider "$@" > "gpurun_out/${name}_$T.log" 2>&1
-  echo "exit $? : $(tail -n 3 gpurun_out/${name}_$T.log | tr '\n' ' ')"; grep -E "^(FAILED|ERROR)|rel err|max-abs err|Error" "gpurun_out/${name}_$T.log" | head -20
+  FGC_UNVERIFIED=1 timeout -k 10 "$to" python -m pytest -v -rP -m gpu -p no:cacheprovider "$@" > "gpurun_out/${name}_$T.log" 2>&1
+  echo "exit $? : $(tail -n 3 gpurun_out/${name}_$T.log | tr '\n' ' ')"; grep -E "^(FAILED|ERROR)|rel err|max-abs err|Error|yardstick" "gpurun_out/${name}_$T.log" | head -20
 }
 run input_queue 200 tests/test_tfrecord_gpu.py
 run pix2pix_model 300 tests/test_pix2pix_gpu.py -k "inference or training or bf16"
