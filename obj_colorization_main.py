@@ -100,31 +100,39 @@ def launch_inference(**kwargs):
         main_procedure.inference(kwargs["infer_name"], kwargs["instruction"])
 
 
+# (flag, short flag, type, default, choices) -- obj_colorization_main.py:160-206 of the reference
+_FLAGS = [
+    ('mode', 'md', str, 'train', ['train', 'val', 'test', 'inference']),
+    ('resume_from', 'rf', str, '', None),
+    ('batch_size', 'bs', int, 2, None),                      # per GPU
+    ('max_iter', 'mi', int, 100000, None),
+    ('optimizer', 'opt', str, 'Adam', ["RMSprop", "Adam", "AdaDelta", "AdaGrad"]),
+    ('lr_G', 'lrg', float, 2e-4, None),
+    ('lr_D', 'lrd', float, 1e-4, None),
+    ('small_img', 'si', int, 0, [0, 1]),
+    ('lstm_hybrid', 'lh', int, 1, [0, 1]),
+    ('distance_map', 'dm', int, 0, [0, 1]),
+    ('block_type', 'bt', str, 'MRU', ['MRU', 'Pix2Pix', 'Residual']),
+    ('vocab_size', 'vs', int, 58, None),
+    ('disc_iterations', 'di', int, 1, None),
+    ('ld', 'ld', int, 10, None),
+    ('num_gpu', 'gpu', int, 1, None),                        # N > 1: re-launched under torch.distributed.run, one process per GPU
+    ('extra_info', 'ei', str, '', None),
+    ('summary_write_freq', 'swf', int, 100, None),
+    ('save_model_freq', 'smf', int, 10000, None),
+    ('count_left_time_freq', 'clt', int, 100, None),
+    ('count_inception_score_freq', 'cis', int, -1, None),
+    ('infer_name', 'in', str, '', None),
+    ('instruction', 'ins', str, '', None),
+]
+# Config key <- flag, where the two names differ (:208-232)
+_RENAMED = {'dataset_type': 'mode', 'max_iter_step': 'max_iter', 'LSTM_hybrid': 'lstm_hybrid'}
+
+
 def build_parser():
     p = argparse.ArgumentParser()
-    p.add_argument('--mode', '-md', type=str, choices=['train', 'val', 'test', 'inference'], default='train')
-    p.add_argument('--resume_from', '-rf', type=str, default='')
-    p.add_argument('--batch_size', '-bs', type=int, default=2, help="Batch size per gpu")
-    p.add_argument('--max_iter', '-mi', type=int, default=100000)
-    p.add_argument('--optimizer', '-opt', type=str, choices=["RMSprop", "Adam", "AdaDelta", "AdaGrad"], default='Adam')
-    p.add_argument('--lr_G', '-lrg', type=float, default=2e-4)
-    p.add_argument('--lr_D', '-lrd', type=float, default=1e-4)
-    p.add_argument('--small_img', '-si', type=int, choices=[0, 1], default=0)
-    p.add_argument('--lstm_hybrid', '-lh', type=int, choices=[0, 1], default=1)
-    p.add_argument('--distance_map', '-dm', type=int, choices=[0, 1], default=0)
-    p.add_argument('--block_type', '-bt', type=str, choices=['MRU', 'Pix2Pix', 'Residual'], default='MRU')
-    p.add_argument('--vocab_size', '-vs', type=int, default=58)
-    p.add_argument('--disc_iterations', '-di', type=int, default=1)
-    p.add_argument('--ld', '-ld', type=int, default=10)
-    p.add_argument('--num_gpu', '-gpu', type=int, default=1,
-                   help="GPUs to train on; N > 1 re-launches this command under torch.distributed.run, one process per GPU")
-    p.add_argument('--extra_info', '-ei', type=str, default='')
-    p.add_argument('--summary_write_freq', '-swf', type=int, default=100)
-    p.add_argument('--save_model_freq', '-smf', type=int, default=10000)
-    p.add_argument('--count_left_time_freq', '-clt', type=int, default=100)
-    p.add_argument('--count_inception_score_freq', '-cis', type=int, default=-1)
-    p.add_argument('--infer_name', '-in', type=str, default='')
-    p.add_argument('--instruction', '-ins', type=str, default='')
+    for name, short, typ, default, choices in _FLAGS:
+        p.add_argument('--' + name, '-' + short, type=typ, default=default, choices=choices)
     return p
 
 
@@ -151,16 +159,8 @@ def main(argv=None):
         _relaunch_data_parallel(args.num_gpu, argv)
     if args.mode == 'inference':
         assert args.infer_name != '' and args.instruction != ''
-    d_params = {
-        "dataset_type": args.mode, "resume_from": args.resume_from, "batch_size": args.batch_size,
-        "max_iter_step": args.max_iter, "disc_iterations": args.disc_iterations, "optimizer": args.optimizer,
-        "lr_G": args.lr_G, "lr_D": args.lr_D, "num_gpu": args.num_gpu, "small_img": args.small_img,
-        "distance_map": args.distance_map, "LSTM_hybrid": args.lstm_hybrid, "block_type": args.block_type,
-        "vocab_size": args.vocab_size, "ld": args.ld, "extra_info": args.extra_info,
-        "summary_write_freq": args.summary_write_freq, "save_model_freq": args.save_model_freq,
-        "count_left_time_freq": args.count_left_time_freq, "count_inception_score_freq": args.count_inception_score_freq,
-        "infer_name": args.infer_name, "instruction": args.instruction,
-    }
+    d_params = {name: getattr(args, name) for name, *_ in _FLAGS if name not in _RENAMED.values()}
+    d_params.update({key: getattr(args, flag) for key, flag in _RENAMED.items()})
     if args.mode == 'train':
         status, appendix = launch_training(**d_params)
         while status == -1:                     # NaN during training: restart from the latest snapshot
