@@ -206,3 +206,26 @@ def test_width_preserving_encoder_block(setup):
     lg, _, _, _ = O.g_step_loss(gp, dp, gspecs, dspecs, b, 8)
     assert abs(r["loss"].item() - lg.item()) < 1e-10
     assert _worst(m.gstore, O.grads_of(lg, gp, gspecs), ops) < 1e-7
+
+
+def test_generator_without_caption(setup):
+    """--lstm_hybrid 0 (models_collection.py:298-302): the bottleneck feeds the decoder as it is; forward and generator
+    gradients against the oracle (the caption-encoder variables receive no gradient)."""
+    ops, b, bb = setup["ops"], setup["b"], setup["bb"]
+    m = FgColorModel(ops, "cpu", size=SIZE, H=H, W=W, param_dtype=torch.float64, lstm_hybrid=False)
+    m.initialize(seed=3, perturb_tables=0.1)
+    gp = {k: v.clone().requires_grad_(True) for k, v in m.gstore.state_dict().items()}
+    dp = {k: v.clone().requires_grad_(True) for k, v in m.dstore.state_dict().items()}
+    out = m.generate(b["sketch"], bb["text"], bb["cls"], b["noise"])
+    ref = O.generator_forward(gp, b["sketch"], b["text"], b["cls"], b["noise"], SIZE, lstm_hybrid=False)
+    assert (out - ref).abs().max().item() < 1e-10
+    r = m.g_step_grads(bb)
+    rd, rl = O.discriminator_forward(dp, b["images_d"], SIZE)
+    fd, fl = O.discriminator_forward(dp, ref, SIZE)
+    lg, _, _ = O.losses(rd, rl, fd, fl, b["cls_d"], b["cls"], b["images"], ref, O.reg_loss(gp, setup["gspecs"]),
+                        O.reg_loss(dp, setup["dspecs"]))
+    assert abs(r["loss"].item() - lg.item()) < 1e-10
+    grads = O.grads_of(lg, gp, setup["gspecs"])
+    assert all(float(g.abs().max()) == 0.0 for k, g in grads.items() if "TextLSTM" in k)
+    assert _worst(m.gstore, {k: g for k, g in grads.items() if "TextLSTM" not in k}, ops) < 1e-7
+    assert float(m.gstore.g["generator/TextLSTM/embedding"].abs().max()) == 0.0
