@@ -22,7 +22,7 @@ def test_generator_inference_parity(cfg):
     """~110 batch-normalised layers amplify rounding by three to four orders of magnitude at random initialisation: the oracle
     run in fp32 instead of fp64 on the CPU already moves the picture by about 1e-3 (measured at several sizes).  The 1e-3 bar of
     the MRU path is therefore at the noise floor of an fp32 reference here; bounds are stated against that yardstick -- fp32
-    CUDA-core convolutions within 30 yardsticks, bf16x3 tensor-core convolutions within 1000 (tests/test_residual_gpu.py)."""
+    CUDA-core convolutions within 30 yardsticks, bf16x3 tensor-core convolutions within 100 (tests/test_residual_gpu.py)."""
     from oracle import bg_oracle as B
     from sketchyscenecolorization_b200.bg import BgColorModel
     from sketchyscenecolorization_b200.cuda_ops import CudaOps
@@ -41,7 +41,7 @@ def test_generator_inference_parity(cfg):
     x = img.float().permute(0, 2, 3, 1).contiguous()
     try:
         for impl, bound, tag in ((1, max(INFER_TOL, 30 * yard), "fp32 CUDA-core convolutions"),
-                                 (0, max(INFER_TOL, 1000 * yard), "bf16x3 tensor-core convolutions")):
+                                 (0, max(INFER_TOL, 100 * yard), "bf16x3 tensor-core convolutions")):
             m.ops.lib.fgc_set_conv_impl(impl)
             out, reg = m.generate(x, ids.numpy())
             torch.cuda.synchronize()

@@ -50,9 +50,10 @@ def _yardstick_and_bounds(ref64, ref32):
     (measured at several sizes; 3e-6 for the MRU generator, 4e-7 for Pix2Pix).  So the 1e-3 bar of the MRU path is at the
     noise floor of an fp32 reference here, and the bounds are stated against that yardstick: the fp32 CUDA-core convolutions
     (every other kernel as in the product) within 30 yardsticks, the bf16x3 tensor-core convolutions (unit round-off 2^-16
-    per product against 2^-24) within 1000."""
+    per product against 2^-24) within 100 (emulating the
+    operand split in the oracle predicts 4e-3 here, 1.3e-2 for the background generator)."""
     yard = (ref32.double() - ref64).abs().max().item()
-    return yard, max(INFER_TOL, 30 * yard), max(INFER_TOL, 1000 * yard)
+    return yard, max(INFER_TOL, 30 * yard), max(INFER_TOL, 100 * yard)
 
 
 @pytest.mark.parametrize("cfg", [(8, 64, 64, 2), (64, 192, 192, 1)], ids=["size8_64px_n2", "size64_192px_n1"])
