@@ -98,7 +98,8 @@ def train(**kwargs):
 
     model = kwargs.get('model')                                     # a resident model (tests); else built on the CUDA operator set
     if model is None:
-        model = _build_model(Config.train_precision, SIZE[small], Config.vocab_size, lstm_hybrid)
+        precision = Config.train_precision_residual if Config.block_type == 'Residual' else Config.train_precision
+        model = _build_model(precision, SIZE[small], Config.vocab_size, lstm_hybrid)
         model.initialize(seed=int(kwargs.get('seed', 0)))
     tr = FgColorTrainer(model, lr_g=Config.lr_G, lr_d=Config.lr_D, max_iter=max_iter_step,
                         process_group=kwargs.get('process_group'), world_size=world, optimizer=Config.optimizer)
