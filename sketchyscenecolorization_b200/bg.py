@@ -6,7 +6,10 @@ pre- / post-processing (:752-765, 838-882).  It is the fg `Residual` generator (
 the caption fused at 24 x 24 (576 mLSTM positions instead of 36), no noise input and a second output: three region logits per
 pixel from a 1x1 projection of the bottleneck upsampled by five transposed convolutions.  Built from residual.Layers, i.e. the
 stride-1 SAME tensor-core convolutions (4x4 layers in phase form), plain batch norm with batch statistics -- at batch 1, as the
-reference runs it, also at test time -- and the fused LSTM kernels.  Forward only: training this network (its own
+reference runs it, also at test time -- and the fused LSTM kernels.  Precision: with the bf16x3 tensor-core convolutions the
+picture is within ~1e-2 of exact arithmetic (about two grey levels; an fp32 run of the reference is itself 1e-3 away: this
+network amplifies rounding ~1000x); FGC_CONV_IMPL=simple runs the fp32 CUDA-core convolutions instead.
+Forward only: training this network (its own
 discriminator, the segmentation loss, Adam with beta1 = 0.5) is outside SURVEY 8.
 """
 from __future__ import annotations
