@@ -289,7 +289,7 @@ class PairedTrainInput:
     main_procedure.train uses two of these (the second feeds images_d)."""
 
     def __init__(self, batch_size, ops, data_base_dir='data', small=False, distance_map=False, min_after_dequeue=512, seed=0,
-                 num_threads=4, prefetch=4, mode='train', side_stream=None):
+                 num_threads=None, prefetch=4, mode='train', side_stream=None):
         import queue
         import threading
         from concurrent.futures import ThreadPoolExecutor
@@ -299,6 +299,9 @@ class PairedTrainInput:
             raise FileNotFoundError("no TFRecord files under %s" % os.path.join(data_base_dir, 'tfrecord', mode))
         self.rng = np.random.default_rng(seed)
         self.min_after = min_after_dequeue
+        if num_threads is None:     # the reference uses 4; take more where the host has them (two queues per rank, N ranks per box)
+            ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            num_threads = max(4, min(8, (os.cpu_count() or 8) // (2 * ranks)))
         self.pool = ThreadPoolExecutor(max_workers=num_threads)
         self.pinned = torch.device(getattr(ops, 'device', 'cpu')).type == 'cuda'
         if side_stream is None:                             # opt-in until it has been measured (FGC_INPUT_SIDE_STREAM=1)
