@@ -1,6 +1,6 @@
 """GPU parity of the background-colorization generator (BASELINE.json configs[3]) against oracle/bg_oracle.py.
 
-NOT YET RUN ON HARDWARE (written after the round's GPU budget was spent): skipped unless FGC_UNVERIFIED=1.  The operators the
+Green on a B200 since round 2 (profiles/r2a_bg_gpu_tests.log).  The operators the
 network is made of have run on a B200 (tests/test_ops_gpu.py, tests/test_pix2pix_gpu.py), the host code is checked against the
 oracle on the CPU (tests/test_bg_cpu.py).  The published size -- 768 x 768, ngf 64, batch 1 -- is compared against the
 oracle on the host in fp64, with the fp32 run beside it as the yardstick (seconds of CPU work; at this size the two differ
@@ -10,9 +10,7 @@ import os
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FGC_UNVERIFIED") != "1",
-                                 reason="background generator GPU path not yet run on hardware (set FGC_UNVERIFIED=1 to run)")]
+pytestmark = [pytest.mark.gpu]
 
 INFER_TOL = 1e-3
 

@@ -3,19 +3,15 @@ fgc_phase_weights / fgc_phase_wgrad) against the plain-torch operators, the 4x4 
 convolutions, and the generator / training graphs against oracle/pix2pix_oracle.py.
 
 Run on a B200 (profiles/r1u_pix2pix_ops_gpu_tests.log, 22 passed): the layout kernels, the filter scatter / gather and the three
-phase-form layers (forward, input gradient, filter gradient).  NOT YET RUN ON HARDWARE: the three model-level tests at the bottom
--- the round's GPU budget ended with the call above.  The host code they exercise is checked against autograd on the CPU
-(tests/test_pix2pix_cpu.py) and every operator they call has its own GPU test, but an unmeasured claim must not turn the suite
-red or green by accident: they are skipped unless FGC_UNVERIFIED=1, and the first GPU call of the next round runs
-`FGC_UNVERIFIED=1 python -m pytest tests/test_pix2pix_gpu.py -m gpu`."""
+phase-form layers (forward, input gradient, filter gradient); since round 2 also the three model-level tests at the bottom
+(profiles/r2a_pix2pix_model_gpu_tests.log).  The host code they exercise is checked against autograd on the CPU
+(tests/test_pix2pix_cpu.py)."""
 import os
 
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
-unverified = pytest.mark.skipif(os.environ.get("FGC_UNVERIFIED") != "1",
-                                reason="Pix2Pix model-level GPU tests not yet run on hardware (set FGC_UNVERIFIED=1 to run)")
 
 INFER_TOL = 1e-3
 GRAD_TOL = 5e-3
@@ -124,7 +120,6 @@ def _dev_batch(b):
     return out
 
 
-@unverified
 @pytest.mark.parametrize("cfg", [(16, 64, 64, 3), (64, 192, 192, 2)], ids=["size16_64px_n3", "size64_192px_n2"])
 def test_generator_inference_parity(cfg):
     from oracle import fgcolor_oracle as O
@@ -144,7 +139,6 @@ def test_generator_inference_parity(cfg):
     assert err <= INFER_TOL, "pix2pix generator max-abs err %.3e" % err
 
 
-@unverified
 def test_training_graph_gradients():
     from oracle import fgcolor_oracle as O
     from oracle import pix2pix_oracle as P
@@ -177,7 +171,6 @@ def test_training_graph_gradients():
     check(m.gstore, O.grads_of(lg, gp, gspecs), "G")
 
 
-@unverified
 def test_bf16_training_steps_run():
     """Training mode (bf16 activations, CUDA-graph replay): two iterations stay finite and move the weights."""
     from oracle import fgcolor_oracle as O

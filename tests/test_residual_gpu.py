@@ -1,18 +1,12 @@
 """GPU parity of `--block_type Residual` against oracle/residual_oracle.py.
 
-NOT YET RUN ON HARDWARE (written after the round's GPU budget was spent): skipped unless FGC_UNVERIFIED=1.  What the model is
-made of HAS run on a B200 -- the direct 7x7 / 3x3 / 1x1 convolutions, batch norm without activation, the PReLU kernels, the
-text fusion, the phase-form 4x4 layers and their layout kernels (tests/test_ops_gpu.py, tests/test_pix2pix_gpu.py) -- except
-fgc_tanh_fwd, tested here; the host code is checked against autograd on the CPU (tests/test_residual_cpu.py).  The first GPU
-call of the next round runs `FGC_UNVERIFIED=1 python -m pytest tests/test_residual_gpu.py -m gpu`."""
-import os
-
+Green on a B200 since round 2 (profiles/r2a_residual_gpu_tests.log).  The operators the model is made of have their own GPU
+tests (tests/test_ops_gpu.py, tests/test_pix2pix_gpu.py); the host code is checked against autograd on the CPU
+(tests/test_residual_cpu.py)."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FGC_UNVERIFIED") != "1",
-                                 reason="Residual GPU path not yet run on hardware (set FGC_UNVERIFIED=1 to run)")]
+pytestmark = [pytest.mark.gpu]
 
 INFER_TOL = 1e-3
 GRAD_TOL = 5e-3

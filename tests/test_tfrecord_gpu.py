@@ -89,9 +89,6 @@ def test_paired_input_full_batch_properties(cu):
     assert torch.equal(noisy_i, again_i) and not torch.equal(noisy_i, other_i)              # counter based: seed -> stream
 
 
-@pytest.mark.skipif(os.environ.get("FGC_UNVERIFIED") != "1",
-                    reason="the queue's host side was rewritten (mapped reader, pinned slot reuse, copy events) after its last GPU "
-                           "run; its CUDA branch has not run on hardware yet (set FGC_UNVERIFIED=1 to run)")
 def test_train_queue_on_device(cu, tmp_path):
     """TFRecord files -> PairedTrainInput with the CUDA operator set: batches arrive on the device and equal the oracle's
     treatment of the same raw samples.  (Green on a B200 with the first version of the queue, profiles/r1t; the rewritten host
