@@ -235,7 +235,8 @@ def run_product(args):
     import torch
     import torch.distributed as dist
     from sketchyscenecolorization_b200.cuda_ops import CudaOps
-    from sketchyscenecolorization_b200.trainer import FgColorModel, FgColorTrainer
+    from sketchyscenecolorization_b200.main_procedure import TrainSession
+    from sketchyscenecolorization_b200.trainer import FgColorModel
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -256,12 +257,39 @@ def run_product(args):
     workload = WORKLOAD if args.block_type == "MRU" else WORKLOAD.replace("MRU G+D", args.block_type + " G+D").replace(
         " (BASELINE.json configs[1])", " (--block_type %s; BASELINE.json configs[1] is the MRU default)" % args.block_type)
     graphs = not args.no_graphs
-    tr = FgColorTrainer(model, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=pg, world_size=world,
-                        use_cuda_graphs=graphs)
 
     hostA, hostB = synth_batch(BS, 1234 + rank), synth_batch(BS, 4321 + rank)
     pin = lambda b: {k: v.pin_memory() for k, v in b.items()}  # noqa: E731
     hostA, hostB = pin(hostA), pin(hostB)
+
+    class Cycle:            # the two queues of main_procedure.train: here pinned host batches, handed out again and again
+        def __init__(self, *batches):
+            self.b, self.i = batches, 0
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            self.i += 1
+            return self.b[(self.i - 1) % len(self.b)]
+
+    # The session object of the reference-facing entry point (main_procedure.train is a loop over TrainSession.iteration):
+    # the e2e leg below times exactly what `obj_colorization_main.py --mode train` runs per iteration.
+    queues = None
+    if args.input == "tfrecord":        # start from record files in the reference's dataset format (rank 0 writes them)
+        import tempfile
+        from sketchyscenecolorization_b200.tfrecord_input import PairedTrainInput
+        base = os.path.join(tempfile.gettempdir(), "fgc_bench_records_%d" % os.getuid())
+        if local == 0 and not os.path.isdir(os.path.join(base, "tfrecord", "train")):
+            write_synthetic_tfrecords(base)
+        if world > 1:
+            dist.barrier()
+        queues = [PairedTrainInput(BS, ops, base, min_after_dequeue=128, seed=s0 + rank, num_threads=6) for s0 in (1234, 4321)]
+    sess = TrainSession(model, batch_size=BS, max_iter=100000, lr_g=2e-4, lr_d=1e-4, process_group=pg, world_size=world,
+                        use_cuda_graphs=graphs,
+                        input_iter=queues[0] if queues else Cycle(hostA, hostB),
+                        input_iter_d=queues[1] if queues else Cycle(hostA))
+    tr = sess.tr
 
     def to_dev(hb):
         d = {k: v.to(dev, non_blocking=True) for k, v in hb.items() if k != "text"}
@@ -313,42 +341,17 @@ def run_product(args):
     clocks = sampler.stop() if rank == 0 else None
     ld_v, lg_v = float(ld), float(lg)
 
-    # ---- end to end: pinned host buffers -> device every step, losses read back every step
-    d_keys = ("sketch", "images_d", "cls", "cls_d", "noise", "text")
-    g_keys = ("sketch", "images", "cls", "noise", "text")
-    queues = None
-    if args.input == "tfrecord":        # start from record files in the reference's dataset format (rank 0 writes them)
-        import tempfile
-        from sketchyscenecolorization_b200.tfrecord_input import PairedTrainInput
-        base = os.path.join(tempfile.gettempdir(), "fgc_bench_records_%d" % os.getuid())
-        if local == 0 and not os.path.isdir(os.path.join(base, "tfrecord", "train")):
-            write_synthetic_tfrecords(base)
-        barrier()
-        queues = [PairedTrainInput(BS, ops, base, min_after_dequeue=128, seed=s0 + rank, num_threads=6) for s0 in (1234, 4321)]
-
-        def from_queue(q, keys):
-            b = next(q)
-            b["noise"] = torch.randn(BS, 256, device=dev)
-            b["text"] = b["text"].to(dev, non_blocking=True) if graphs else b["text"].numpy()
-            for k in ("cls", "cls_d"):
-                b[k] = b[k].to(dev, non_blocking=True)
-            return {k: b[k] for k in keys}
-        for _ in range(2):              # fill the shuffle buffers and the prefetch pipeline outside the timed region
-            from_queue(queues[0], d_keys), from_queue(queues[1], g_keys)
+    # ---- end to end, through the session loop's own iteration: pinned host buffers (or record files) -> device every step,
+    # the loss scalars and the NaN verdict read back every step
+    d_keys = ("sketch", "images_d", "cls", "cls_d", "text")
+    g_keys = ("sketch", "images", "cls", "text")
+    for _ in range(2):                  # fill the shuffle buffers / prefetch pipeline outside the timed region
+        sess.iteration()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for _ in range(args.steps):
-        if queues is not None:
-            bA, bB = from_queue(queues[0], d_keys), from_queue(queues[1], g_keys)
-        elif graphs:      # pinned host tensors are copied straight into the graphs' static input buffers
-            bA, bB = {k: hostA[k] for k in d_keys}, {k: hostB[k] for k in g_keys}
-        else:
-            bA = {k: (hostA[k].to(dev, non_blocking=True) if k != "text" else hostA[k].numpy()) for k in d_keys}
-            bB = {k: (hostB[k].to(dev, non_blocking=True) if k != "text" else hostB[k].numpy()) for k in g_keys}
-        od = tr.d_step(bA)
-        og = tr.g_step(bB)
-        _ = (float(od["loss"]), float(og["loss"]))        # D2H read of both loss scalars
+        e2e_ld, e2e_lg, nan_d, nan_g = sess.iteration()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -386,7 +389,8 @@ def run_product(args):
                 "e2e": {"value": ips_e2e, "unit": "images/s",
                         "h2d_bytes_per_step": (h2d_bytes(hostA, d_keys) + h2d_bytes(hostB, g_keys)) if queues is None
                         else 2 * BS * (2 * 384 * 384 * 3 + 15 * 4 + 4),
-                        "d2h_bytes_per_step": 8,
+                        "d2h_bytes_per_step": 16,
+                        "api": "main_procedure.TrainSession.iteration (the body of main_procedure.train's loop)",
                         "input": "pinned fp32 tensors" if queues is None else
                         "TFRecord files -> mapped reader + CRC-32C + proto parse + shuffle queue (host threads) -> raw uint8 H2D -> "
                         "fgc_paired_input"},

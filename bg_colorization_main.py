@@ -110,4 +110,7 @@ if __name__ == "__main__":
     parser.add_argument("--progress_freq", type=int, default=50)
     parser.add_argument("--save_freq", type=int, default=20000)
     a = parser.parse_args()
+    if a.mode != "test":        # the reference's default is 'train'; say what is there instead of a traceback
+        parser.error("--mode train is not built here: training the background model is outside the scope of this package "
+                     "(DESIGN.md section 7).  Use --mode test --resume_from <run> for the 768x768 inference path.")
     bg_colorization(**vars(a))

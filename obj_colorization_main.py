@@ -39,7 +39,8 @@ def _process_group():
 
 def launch_training(**kwargs):
     # objects a caller may hand through (a resident model, input iterators): not parameters, not written to param_<iter>.json
-    runtime = {k: kwargs.pop(k) for k in ('model', 'input_iter', 'input_iter_d') if k in kwargs}
+    runtime = {k: kwargs.pop(k) for k in ('model', 'input_iter', 'input_iter_d', 'synthetic_input', 'use_cuda_graphs', 'data_base_dir')
+               if k in kwargs}
     appendix = kwargs["resume_from"]
     pg, world = _process_group()
     if appendix is None or appendix == '':
@@ -124,6 +125,9 @@ _FLAGS = [
     ('count_inception_score_freq', 'cis', int, -1, None),
     ('infer_name', 'in', str, '', None),
     ('instruction', 'ins', str, '', None),
+    # B200 additions (not in the reference)
+    ('cuda_graphs', 'cg', int, 1, [0, 1]),                   # training steps replay CUDA graphs (0: every kernel launched from Python)
+    ('synthetic_input', 'syn', int, 0, [0, 1]),              # train on seeded synthetic batches when data/tfrecord/train is absent
 ]
 # Config key <- flag, where the two names differ (:208-232)
 _RENAMED = {'dataset_type': 'mode', 'max_iter_step': 'max_iter', 'LSTM_hybrid': 'lstm_hybrid'}

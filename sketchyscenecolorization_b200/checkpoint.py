@@ -99,12 +99,50 @@ def _load_legacy(prefix):
     return out
 
 
-def restore(model, prefix, strict=True):
+def default_aliases(key):
+    """Other names a TensorFlow-written snapshot may hold `key` under.  Two names of this package's inventory are provisional
+    (checking them needs one of the published checkpoints, which cannot be fetched here): the spectral-norm vector --
+    sn.py:17-18 opens a nested variable_scope named after the weight's own scope, which yields either the doubled path
+    `discriminator/<s>/discriminator/<s>/u` or, when TF re-enters the existing scope, `discriminator/<s>/u` -- and the LSTM
+    variables, `kernel` / `bias` since TF 1.2, `weights` / `biases` before."""
+    out = []
+    m = re.match(r"^(.*)/\1/u$", key)
+    if m:
+        out.append(m.group(1) + "/u")
+    if key.endswith("/basic_lstm_cell/kernel"):
+        out.append(key[:-len("kernel")] + "weights")
+    if key.endswith("/basic_lstm_cell/bias"):
+        out.append(key[:-len("bias")] + "biases")
+    return out
+
+
+def restore(model, prefix, strict=True, key_map=None):
     """Loads a snapshot (TensorFlow V2 bundle, e.g. one written by `save` or by the reference's tf.train.Saver; or the JSON
-    format of earlier versions of this package).  Returns the saved iteration counter."""
+    format of earlier versions of this package).  Returns the saved iteration counter.
+
+    key_map: optional dict {this package's variable name: name in the snapshot} or callable name -> name | [names], tried
+    before the name itself; `default_aliases` is tried after it."""
     with open(prefix + ".index", "rb") as f:
         legacy = f.read(1) == b"{"
     t = _load_legacy(prefix) if legacy else tf_bundle.read_bundle(prefix)
+    if key_map is not None or any(a in t and k not in t for store in (model.gstore, model.dstore) if store is not None
+                                  for k in list(store.p) + list(store.state) for a in default_aliases(k)):
+        t = dict(t)
+        for store in (model.gstore, model.dstore):
+            if store is None:
+                continue
+            for k in list(store.p) + list(store.state):
+                cands = []
+                if key_map is not None:
+                    c = key_map(k) if callable(key_map) else key_map.get(k)
+                    cands += [c] if isinstance(c, str) else list(c or [])
+                cands += [k] + default_aliases(k)
+                src = next((c for c in cands if c in t), None)
+                if src is not None and src != k:
+                    t[k] = t[src]
+                    for slot in ("/Adam", "/Adam_1", "/RMSProp", "/RMSProp_1", "/Adadelta", "/Adadelta_1", "/Adagrad"):
+                        if src + slot in t:
+                            t[k + slot] = t[src + slot]
 
     for store, suffix, tag in ((model.gstore, "", "generator"), (model.dstore, "_1", "discriminator")):
         if store is None:

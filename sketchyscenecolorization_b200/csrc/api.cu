@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 
 #include "common.cuh"
 #include <stdlib.h>
@@ -29,7 +30,7 @@ int check_launch(const char* what) {
 
 // CRC-32C (Castagnoli), slicing-by-8, host only: the checksum of TensorFlow's tensor-bundle snapshots (tf_bundle.py)
 static uint32_t g_crc_tab[8][256];
-static bool g_crc_ready = false;
+static std::once_flag g_crc_once;     // the table walk is live on non-x86 hosts, called from several reader threads
 static void crc_init() {
   for (uint32_t i = 0; i < 256; i++) {
     uint32_t c = i;
@@ -38,7 +39,6 @@ static void crc_init() {
   }
   for (uint32_t i = 0; i < 256; i++)
     for (int t = 1; t < 8; t++) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xFF];
-  g_crc_ready = true;
 }
 
 #if defined(__x86_64__)
@@ -77,7 +77,7 @@ unsigned int fgc_crc32c(const void* data, size_t n, unsigned int crc) {
   static const bool hw = cpu_has_sse42() && !getenv("FGC_CRC_TABLE");
   if (hw) return ~crc32c_hw(p, n, c);
 #endif
-  if (!g_crc_ready) crc_init();
+  std::call_once(g_crc_once, crc_init);
   while (n && (reinterpret_cast<uintptr_t>(p) & 7)) { c = g_crc_tab[0][(c ^ *p++) & 0xFF] ^ (c >> 8); n--; }
   while (n >= 8) {
     uint64_t v = *reinterpret_cast<const uint64_t*>(p) ^ c;

@@ -26,6 +26,8 @@ def _same_pad(size, k, stride):
 
 
 class CudaOps(OpsBase):
+    supports_cuda_graphs = True     # nothing allocates or synchronises inside the library; TrainSession replays graphs on it
+
     def __init__(self, device="cuda:0", act_dtype=torch.float32):
         if not torch.cuda.is_available():
             raise RuntimeError("CudaOps needs a CUDA device (sm_100a); there is no CPU path in this package")

@@ -80,10 +80,106 @@ def shared_string(value, process_group=None, world_size=1, src=0):
     return box[0]
 
 
+class TrainSession:
+    """One process' share of the training session (main_procedure.py:124-237): the trainer, the two input queues and
+    `iteration(i)` = `disc_iterations` D steps + one G step, each on a freshly dequeued batch, the loss scalars read back
+    and the NaN verdict agreed across ranks.  `train` below is a loop over it; `bench.py` times the same object.
+
+    On the CUDA operator set the two steps replay CUDA graphs (`use_cuda_graphs`, default on; `--cuda_graphs 0` /
+    kwargs `use_cuda_graphs=False` launches every kernel from Python): caption ids then stay on the device.  Host traffic
+    per iteration: the batches' host-to-device copies and ONE device-to-host read of the loss scalars -- with more than one
+    rank the NaN flags are MAX-reduced on the device first, so the verdict rides in the same read."""
+
+    D_KEYS = ('sketch', 'images_d', 'cls', 'cls_d', 'text', 'noise')
+    G_KEYS = ('sketch', 'images', 'cls', 'text', 'noise')
+
+    def __init__(self, model, *, batch_size, max_iter, lr_g, lr_d, optimizer='Adam', disc_iterations=1, iter_from=0,
+                 input_iter=None, input_iter_d=None, process_group=None, world_size=1, use_cuda_graphs=None,
+                 small=False, vocab_size=58, distance_map=False, data_base_dir='data', synthetic_input=None):
+        from .trainer import FgColorTrainer
+        self.model, self.n, self.diters = model, batch_size, disc_iterations
+        self.pg, self.world = process_group, int(world_size)
+        self.dev = model.device
+        on_cuda = bool(getattr(model.ops, 'supports_cuda_graphs', False))
+        if use_cuda_graphs is None:
+            use_cuda_graphs = os.environ.get("FGC_CUDA_GRAPHS", "1") != "0"
+        self.graphs = bool(use_cuda_graphs) and on_cuda
+        self.tr = FgColorTrainer(model, lr_g=lr_g, lr_d=lr_d, max_iter=max_iter, process_group=process_group,
+                                 world_size=self.world, optimizer=optimizer, use_cuda_graphs=self.graphs)
+        self.tr.counter = iter_from                                  # sess.run(counter.assign(iter_from)), :176
+        rank = int(os.environ.get("RANK", "0"))
+        self._own = []                                               # queues created here (closed by close())
+        q1, q2 = input_iter, input_iter_d
+        if q1 is None or q2 is None:
+            rec_dir = os.path.join(data_base_dir, 'tfrecord', 'train')
+            synthetic_input = bool(synthetic_input) or os.environ.get("FGC_SYNTHETIC_INPUT") == "1"
+            if os.path.isdir(rec_dir) and os.listdir(rec_dir):
+                # the reference's two independent TFRecord shuffle queues (main_procedure.py:109-122)
+                from .tfrecord_input import PairedTrainInput
+                for seed, have in ((1234 + rank, q1), (4321 + rank, q2)):
+                    if have is None:
+                        self._own.append(PairedTrainInput(batch_size, model.ops, data_base_dir, small=small,
+                                                          distance_map=distance_map, seed=seed))
+                it = iter(self._own)
+                q1, q2 = q1 or next(it), q2 or next(it)
+            elif synthetic_input:      # asked for (bench, tests): seeded synthetic batches of the SURVEY 8(d) shape
+                q1 = q1 or SyntheticInput(batch_size, *SIZE[small], vocab_size=vocab_size, seed=1234 + rank)
+                q2 = q2 or SyntheticInput(batch_size, *SIZE[small], vocab_size=vocab_size, seed=4321 + rank)
+            else:                      # the reference fails in os.listdir of build_input_queue_paired (input_pipeline.py:133)
+                raise FileNotFoundError(
+                    "%s holds no TFRecord files (the FOREGROUND dataset is not part of the repository).  Pass "
+                    "synthetic_input=True / set FGC_SYNTHETIC_INPUT=1 to train on seeded synthetic batches." % rec_dir)
+        self.q1, self.q2 = q1, q2
+        self.last_d = self.last_g = None
+
+    # ---- batches: opt_d dequeues both queues, opt_g only the first (graph_single.py:257-289; main_procedure.py:202-227)
+    def _text(self, t):
+        if self.graphs:
+            return torch.as_tensor(t).to(self.dev, non_blocking=True)
+        return t.numpy() if torch.is_tensor(t) else np.asarray(t)
+
+    def _noise(self):
+        return torch.randn(self.n, 256, device=self.dev)
+
+    def fetch_d(self):
+        a, b = next(self.q1), next(self.q2)
+        out = {k: a[k] if self.graphs else a[k].to(self.dev, non_blocking=True) for k in ('sketch', 'cls')}
+        for k in ('images_d', 'cls_d'):
+            out[k] = b[k] if self.graphs else b[k].to(self.dev, non_blocking=True)
+        out['text'], out['noise'] = self._text(a['text']), self._noise()
+        return out
+
+    def fetch_g(self):
+        a = next(self.q1)
+        out = {k: a[k] if self.graphs else a[k].to(self.dev, non_blocking=True) for k in ('sketch', 'images', 'cls')}
+        out['text'], out['noise'] = self._text(a['text']), self._noise()
+        return out
+
+    # ---- one iteration of the session loop
+    def iteration(self):
+        """Returns (loss_d, loss_g, nan_d, nan_g) as Python values: one device-to-host read."""
+        for _ in range(self.diters):
+            od = self.tr.d_step(self.fetch_d())
+        og = self.tr.g_step(self.fetch_g())
+        self.last_d, self.last_g = od, og
+        lo = torch.stack([od['loss'].float().reshape(()), og['loss'].float().reshape(())])
+        bad = torch.isnan(lo).float()
+        if self.world > 1:            # every rank must leave the loop in the same iteration
+            import torch.distributed as dist
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=self.pg)
+        v = torch.cat([lo, bad]).tolist()
+        return v[0], v[1], v[2] > 0, v[3] > 0
+
+    def close(self):
+        for q in self._own:
+            q.close()
+        self._own = []
+
+
 def train(**kwargs):
-    """Alternating D / G optimisation (main_procedure.py:62-242).  kwargs: iter_from, and optionally `input_iter`
-    (two-queue stand-in yielding batch dicts) and `process_group`/`world_size` for data parallelism."""
-    from .trainer import FgColorTrainer
+    """Alternating D / G optimisation (main_procedure.py:62-242).  kwargs: iter_from, and optionally `input_iter` /
+    `input_iter_d` (two-queue stand-ins yielding batch dicts), `process_group` / `world_size` for data parallelism,
+    `use_cuda_graphs`, `synthetic_input`, a resident `model`."""
     status = 0
     batch_size, max_iter_step, diters = Config.batch_size, Config.max_iter_step, Config.disc_iterations
     log_dir, ckpt_dir = Config.log_dir, Config.ckpt_dir
@@ -101,72 +197,66 @@ def train(**kwargs):
         precision = Config.train_precision_residual if Config.block_type == 'Residual' else Config.train_precision
         model = _build_model(precision, SIZE[small], Config.vocab_size, lstm_hybrid)
         model.initialize(seed=int(kwargs.get('seed', 0)))
-    tr = FgColorTrainer(model, lr_g=Config.lr_G, lr_d=Config.lr_D, max_iter=max_iter_step,
-                        process_group=kwargs.get('process_group'), world_size=world, optimizer=Config.optimizer)
     if iter_from > 0:
         prefix = checkpoint.latest_checkpoint(ckpt_dir)
         print('Restore:', prefix)
         checkpoint.restore(model, prefix)
-    tr.counter = iter_from                                          # sess.run(counter.assign(iter_from)), :176
+    graphs = kwargs.get('use_cuda_graphs')
+    if graphs is None and getattr(Config, 'cuda_graphs', None) is not None:
+        graphs = bool(Config.cuda_graphs)
+    sess = TrainSession(model, batch_size=batch_size, max_iter=max_iter_step, lr_g=Config.lr_G, lr_d=Config.lr_D,
+                        optimizer=Config.optimizer, disc_iterations=diters, iter_from=iter_from,
+                        input_iter=kwargs.get('input_iter'), input_iter_d=kwargs.get('input_iter_d'),
+                        process_group=kwargs.get('process_group'), world_size=world, use_cuda_graphs=graphs, small=small,
+                        vocab_size=Config.vocab_size, distance_map=Config.distance_map != 0,
+                        data_base_dir=kwargs.get('data_base_dir', 'data'),
+                        synthetic_input=kwargs.get('synthetic_input') or getattr(Config, 'synthetic_input', 0))
+    tr = sess.tr
     print_parameter_count(model)
     rank = int(os.environ.get("RANK", "0"))
-    q1, q2 = kwargs.get('input_iter'), kwargs.get('input_iter_d')
-    rec_dir = os.path.join(kwargs.get('data_base_dir', 'data'), 'tfrecord', 'train')
-    if (q1 is None or q2 is None) and os.path.isdir(rec_dir) and os.listdir(rec_dir):
-        # the reference's two independent TFRecord shuffle queues (main_procedure.py:109-122)
-        from .tfrecord_input import PairedTrainInput
-        mk = lambda seed: PairedTrainInput(batch_size, model.ops, kwargs.get('data_base_dir', 'data'), small=small,      # noqa: E731
-                                           distance_map=Config.distance_map != 0, seed=seed)
-        q1, q2 = q1 or mk(1234 + rank), q2 or mk(4321 + rank)
-    else:                                 # the dataset is not part of the reference repository: seeded synthetic batches
-        q1 = q1 or SyntheticInput(batch_size, *SIZE[small], vocab_size=Config.vocab_size, seed=1234 + rank)
-        q2 = q2 or SyntheticInput(batch_size, *SIZE[small], vocab_size=Config.vocab_size, seed=4321 + rank)
-    dev = model.device
     summ = open(os.path.join(log_dir, 'summaries.jsonl'), 'a') if rank == 0 else None
-
-    def fetch():
-        a, b = next(q1), next(q2)      # (images, sketches, ids, text) and an independent images_d queue, :109-122
-        out = {k: a[k].to(dev, non_blocking=True) for k in ('sketch', 'images', 'cls')}
-        out['images_d'], out['cls_d'] = b['images_d'].to(dev, non_blocking=True), b['cls_d'].to(dev, non_blocking=True)
-        out['text'] = a['text'].numpy()
-        out['noise'] = torch.randn(batch_size, 256, device=dev)
-        return out
-
-    prev_time = float("-inf")
-    for i in range(iter_from, max_iter_step):
-        if i % Config.count_left_time_freq == 0:
-            curr_time = time()
-            elapsed = curr_time - prev_time
-            print("Now at iteration %d. Elapsed time: %.5fs. Average time: %.5fs/iter"
-                  % (i, elapsed, elapsed / float(Config.count_left_time_freq)))
-            if elapsed != float("inf"):                               # main_procedure.py:182-188
-                left_sec = (max_iter_step - i) * (elapsed / float(Config.count_left_time_freq))
-                left_day = int(left_sec / 24 / 60 / 60)
-                left_hour = int((left_sec - (24 * 60 * 60) * left_day) / 60 / 60)
-                left_min = int((left_sec - (24 * 60 * 60) * left_day - (60 * 60) * left_hour) / 60)
-                print("Left time:%dd %dh %dm" % (left_day, left_hour, left_min))
-            prev_time = curr_time
-        want_summary = i % Config.summary_write_freq == 0
-        for j in range(diters):                                       # each sess.run dequeues a fresh batch
-            od = tr.d_step(fetch())
-            loss_d_out = float(od['loss'])
-            if any_rank_true(math.isnan(loss_d_out), kwargs.get('process_group'), world, dev):
+    nvtx = torch.cuda.nvtx if torch.cuda.is_available() else None
+    try:
+        prev_time = float("-inf")
+        for i in range(iter_from, max_iter_step):
+            if i % Config.count_left_time_freq == 0:
+                curr_time = time()
+                elapsed = curr_time - prev_time
+                print("Now at iteration %d. Elapsed time: %.5fs. Average time: %.5fs/iter"
+                      % (i, elapsed, elapsed / float(Config.count_left_time_freq)))
+                if elapsed != float("inf"):                               # main_procedure.py:182-188
+                    left_sec = (max_iter_step - i) * (elapsed / float(Config.count_left_time_freq))
+                    left_day = int(left_sec / 24 / 60 / 60)
+                    left_hour = int((left_sec - (24 * 60 * 60) * left_day) / 60 / 60)
+                    left_min = int((left_sec - (24 * 60 * 60) * left_day - (60 * 60) * left_hour) / 60)
+                    print("Left time:%dd %dh %dm" % (left_day, left_hour, left_min))
+                prev_time = curr_time
+            want_summary = i % Config.summary_write_freq == 0
+            if nvtx is not None:
+                nvtx.range_push("train_iteration_%d" % i)
+            loss_d_out, loss_g_out, nan_d, nan_g = sess.iteration()
+            if nvtx is not None:
+                nvtx.range_pop()
+            if nan_d:                                                     # main_procedure.py:213-216
                 print("NaN occurred during training D")
                 return -1
-        og = tr.g_step(fetch())
-        loss_g_out = float(og['loss'])
-        if any_rank_true(math.isnan(loss_g_out), kwargs.get('process_group'), world, dev):
-            print("NaN occurred during training G")
-            return -1
-        if want_summary and summ is not None:                         # scalar names of graph_single.py:71-98
-            rec = {"step": i, "GAN_loss/G": float(og['gan']), "GAN_loss/D": float(od['gan']), "ACGAN_loss/G": float(og['ac']),
-                   "ACGAN_loss/D": float(od['ac']), "l1_perceptual_loss": float(og['l1']), "total_loss/g": loss_g_out,
-                   "total_loss/d": loss_d_out, "learning_rate_g": Config.lr_G * max(0.2, 1 - 0.9 * i / max_iter_step)}
-            summ.write(json.dumps(rec) + "\n")
-            summ.flush()
-        if i % Config.save_model_freq == Config.save_model_freq - 1 and rank == 0:
-            checkpoint.save(model, ckpt_dir, i, tr.counter)
-            print('Save model_{}.ckpt'.format(i))
+            if nan_g:                                                     # :229-232
+                print("NaN occurred during training G")
+                return -1
+            if want_summary and summ is not None:                         # scalar names of graph_single.py:71-98
+                od, og = sess.last_d, sess.last_g
+                rec = {"step": i, "GAN_loss/G": float(og['gan']), "GAN_loss/D": float(od['gan']), "ACGAN_loss/G": float(og['ac']),
+                       "ACGAN_loss/D": float(od['ac']), "l1_perceptual_loss": float(og['l1']), "total_loss/g": loss_g_out,
+                       "total_loss/d": loss_d_out, "learning_rate_g": Config.lr_G * max(0.2, 1 - 0.9 * i / max_iter_step)}
+                summ.write(json.dumps(rec) + "\n")
+                summ.flush()
+            if i % Config.save_model_freq == Config.save_model_freq - 1 and rank == 0:
+                checkpoint.save(model, ckpt_dir, i, tr.counter)
+                print('Save model_{}.ckpt'.format(i))
+    finally:
+        sess.close()
+        if summ is not None:
+            summ.close()
     return status
 
 

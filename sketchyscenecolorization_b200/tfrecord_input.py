@@ -382,7 +382,24 @@ class PairedTrainInput:
                              copy_stream=self.copy_stream)
 
     def close(self):
+        """Stop the reader thread, the parser pool and drop the page-locked batch buffers (the NaN-restart loop of
+        obj_colorization_main builds a fresh pair of queues every time)."""
+        import queue
         self._closed = True
+        try:                                    # the reader may be blocked in put() on a full queue, or in get() on the orders
+            while True:
+                self._records.get_nowait()
+        except queue.Empty:
+            pass
+        try:
+            self._orders.put_nowait(np.zeros(0, dtype=np.int64))
+        except queue.Full:
+            pass
+        for _, futs, _ in self.pending:
+            for f in futs:
+                f.cancel()
+        self.pool.shutdown(wait=False)
+        self.pending, self.buf, self._slots = [], [], []
 
 
 class PairedEvalInput:

@@ -166,8 +166,11 @@ class FgColorTrainer:
         """average_gradients (graph_single.py:33-68): one all-reduce of the flat fp32 gradient bucket."""
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(store.grad, op=dist.ReduceOp.SUM, group=self.pg)
-            store.grad.mul_(1.0 / self.world)
+            if dist.get_backend(self.pg) == "nccl":       # ncclAvg: the division rides in the collective
+                dist.all_reduce(store.grad, op=dist.ReduceOp.AVG, group=self.pg)
+            else:                                         # gloo (CPU tests) has no AVG
+                dist.all_reduce(store.grad, op=dist.ReduceOp.SUM, group=self.pg)
+                store.grad.mul_(1.0 / self.world)
 
     # ---- eager steps
     def _apply(self, store, lr, lr_dev):
@@ -196,9 +199,13 @@ class FgColorTrainer:
         base_lr = self.lr_d if kind == "d" else self.lr_g
         st = self._g.setdefault(kind, dict(calls=0))
         st["calls"] += 1
-        if st["calls"] == 1:                    # lazy one-time initialisation inside the library happens here
-            return eager(batch)
         dev = self.m.device
+        if st["calls"] == 1:                    # lazy one-time initialisation inside the library happens here
+            onto = {}
+            for k in keys:
+                v = batch[k] if torch.is_tensor(batch[k]) else torch.as_tensor(batch[k])
+                onto[k] = v.to(dev, dtype=torch.float32 if v.is_floating_point() else torch.int32, non_blocking=True)
+            return eager(onto)
         if "graph" not in st:
             st["inputs"] = {}
             for k in keys:

@@ -159,7 +159,7 @@ def test_session_loop_snapshots_resume_and_nan_status(tmp_path, monkeypatch):
                   extra_info="", summary_write_freq=1, save_model_freq=2, count_left_time_freq=1, count_inception_score_freq=-1,
                   infer_name="", instruction="")
     before = m.gstore.flat.clone()
-    status, stamp = M.launch_training(model=m, **params)
+    status, stamp = M.launch_training(model=m, synthetic_input=True, **params)
     assert status == 0 and len(stamp.split("-")) == 6
     run = tmp_path / "outputs" / stamp
     assert json.load(open(run / "log" / "param_0.json"))["batch_size"] == 2
@@ -171,7 +171,7 @@ def test_session_loop_snapshots_resume_and_nan_status(tmp_path, monkeypatch):
     m2 = FgColorModel(ops, "cpu", size=16, H=64, W=64)
     m2.initialize(seed=99)
     params2 = dict(params, resume_from=stamp, max_iter_step=4)
-    status, stamp2 = M.launch_training(model=m2, **params2)
+    status, stamp2 = M.launch_training(model=m2, synthetic_input=True, **params2)
     assert status == 0 and stamp2 == stamp and os.path.exists(run / "log" / "param_2.json")
     assert checkpoint.latest_checkpoint(str(run / "snapshot")).endswith("model_3.ckpt-3")
     assert m2.dstore.adam_t == 4                                                                    # 2 restored + 2 new steps
@@ -184,7 +184,10 @@ def test_session_loop_snapshots_resume_and_nan_status(tmp_path, monkeypatch):
             b["images_d"][0, 0, 0, 0] = float("nan")
             return b
     Config.set_from_dict(dict(params2, log_dir=str(run / "log"), ckpt_dir=str(run / "snapshot"), max_iter_step=6))
-    assert main_procedure.train(iter_from=4, model=m2, input_iter_d=Poisoned(2, 64, 64, seed=5)) == -1
+    assert main_procedure.train(iter_from=4, model=m2, synthetic_input=True, input_iter_d=Poisoned(2, 64, 64, seed=5)) == -1
+    # no dataset and no explicit request for synthetic batches: fail like the reference's os.listdir (input_pipeline.py:133)
+    with pytest.raises(FileNotFoundError):
+        main_procedure.train(iter_from=4, model=m2)
 
 
 def test_width_preserving_encoder_block(setup):

@@ -188,3 +188,117 @@ def test_cuda_graph_replay_matches_eager():
         # BOTH trainers: bound the difference by the total step budget and compare the bulk in relative L2.
         assert (a - b_).abs().max().item() <= 2 * 4 * 2e-4 * 3.2, (a - b_).abs().max().item()
         assert ((a - b_).norm() / a.norm()).item() <= 5e-3, ((a - b_).norm() / a.norm()).item()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the benchmarked network -- size 64, 192 x 192 -- against the fp64 oracle, in both numeric modes
+# ------------------------------------------------------------------------------------------------------------------
+# Bounds of the single-pass bf16 TRAINING mode against the fp64 oracle at the full-size network (N = 2, random initialisation,
+# cBN tables perturbed).  bf16 operands carry 2^-9 relative rounding per product; the 46-convolution generator with batch
+# statistics and eps-free min-max gates amplifies it (2e-2 max-abs on the generator output), so the
+# gradients are held to a direction bound (cosine) and a per-tensor relative-L2 bound instead of an entry-wise one.
+BF16_LOSS_REL = 0.03
+BF16_COS_D, BF16_COS_G = 0.98, 0.95
+BF16_L2_D, BF16_L2_G = 0.35, 0.60
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_full_size_training_graph_gradients(mode):
+    """D-step and G-step of the size-64, 192 x 192 network (every production kernel instantiation: 16 x 8 / 32 x 8 / 64 x 8
+    pixel tiles, 64..768-wide N tiles, patch-tensor sources) against torch autograd on the fp64 oracle."""
+    from oracle import fgcolor_oracle as O
+    size, H, W, N = 64, 192, 192, 2
+    m = _model(size, H, W, torch.float32 if mode == "fp32" else torch.bfloat16)
+    gp, dp = _oracle_params(m, torch.float64)
+    gspecs, dspecs = O.generator_specs(size, 58, H, W), O.discriminator_specs(size)
+    b = O.make_batch(N, H, W, 21, torch.float64, n_pad=2)
+    b["text"][0, :9] = 0
+    db = _dev_batch(b)
+
+    def check(store, ref, tag, cos_min, l2_max):
+        for s in store.specs:
+            if s.trainable and s.reg > 0:
+                store.g[s.name] += s.reg * store.p[s.name]
+        worst, k, l2, cos = _cmp_grads(store, ref)
+        print("%s %s grads vs fp64 oracle: worst entry err (rel. to tensor max) %.3e at %s, worst tensor rel-L2 %.3e, cosine %.6f"
+              % (mode, tag, worst, k, l2, cos))
+        assert l2 <= l2_max, "%s grads: worst relative L2 error %.3e" % (tag, l2)
+        assert cos >= cos_min, "%s grads: cosine %.6f" % (tag, cos)
+
+    loss_rel = 1e-3 if mode == "fp32" else BF16_LOSS_REL
+    r = m.d_step_grads(db)
+    ld, _, _ = O.d_step_loss(gp, dp, gspecs, dspecs, b, size)
+    gd = O.grads_of(ld, dp, dspecs)
+    torch.cuda.synchronize()
+    print("%s loss_d %.6f (oracle %.6f)" % (mode, r["loss"].item(), ld.item()))
+    assert abs(r["loss"].item() - ld.item()) <= loss_rel * abs(ld.item())
+    check(m.dstore, gd, "D", 0.9995 if mode == "fp32" else BF16_COS_D, 5e-2 if mode == "fp32" else BF16_L2_D)
+    r = m.g_step_grads(db)
+    lg, _, _, _ = O.g_step_loss(gp, dp, gspecs, dspecs, b, size)
+    gg = O.grads_of(lg, gp, gspecs)
+    torch.cuda.synchronize()
+    print("%s loss_g %.6f (oracle %.6f)" % (mode, r["loss"].item(), lg.item()))
+    assert abs(r["loss"].item() - lg.item()) <= loss_rel * abs(lg.item())
+    check(m.gstore, gg, "G", 0.9995 if mode == "fp32" else BF16_COS_G, 5e-2 if mode == "fp32" else BF16_L2_G)
+
+
+def test_bf16_inference_error_is_stated():
+    """The training-mode forward (single-pass bf16) against the fp64 oracle at the full-size network: NOT the parity mode
+    (inference / val / test run bf16x3 and meet 1e-3, above) -- this pins how far the benchmarked arithmetic is from the
+    reference's, so the number in DESIGN.md section 7 is a tested one."""
+    from oracle import fgcolor_oracle as O
+    size, H, W, N = 64, 192, 192, 1
+    m = _model(size, H, W, torch.bfloat16)
+    gp, _ = _oracle_params(m, torch.float64)
+    b = O.make_batch(N, H, W, 11, torch.float64, n_pad=12)
+    with torch.no_grad():
+        ref = O.generator_forward(gp, b["sketch"], b["text"], b["cls"], b["noise"], size)
+    db = _dev_batch(b)
+    out = m.generate(db["sketch"], db["text"], db["cls"], db["noise"])
+    torch.cuda.synchronize()
+    d = (out.cpu().double() - ref).abs()
+    print("single-pass bf16 generator vs fp64 oracle: max-abs %.3e, mean-abs %.3e" % (d.max().item(), d.mean().item()))
+    assert d.max().item() <= 0.15 and d.mean().item() <= 1.5e-2
+
+
+def test_bf16_trains_like_fp32():
+    """200 iterations of the session loop at size 16 / 64 x 64 on eight cycling batches, once in the split-precision mode
+    (bf16x3 convolutions, fp32 activations) and once in the benchmarked mode (single-pass bf16): same data, same noise,
+    same initial weights.  GAN training is chaotic, so the curves are compared as curves: the reconstruction loss must fall
+    in both, and the bf16 run's window means must stay within a band of the fp32 run's."""
+    from sketchyscenecolorization_b200.input_pipeline import SyntheticInput
+    from sketchyscenecolorization_b200.main_procedure import TrainSession
+
+    class Cycle:
+        def __init__(self, seed, n=8):
+            src = SyntheticInput(8, 64, 64, seed=seed)
+            self.b, self.i = [next(src) for _ in range(n)], 0
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            self.i += 1
+            return self.b[(self.i - 1) % len(self.b)]
+
+    curves = {}
+    for mode, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        torch.manual_seed(3)
+        torch.cuda.manual_seed(3)
+        m = _model(16, 64, 64, dt, seed=4)
+        s = TrainSession(m, batch_size=8, max_iter=200, lr_g=2e-4, lr_d=1e-4, small=True, input_iter=Cycle(1), input_iter_d=Cycle(2))
+        rows = []
+        for _ in range(200):
+            ld, lg, nd, ng = s.iteration()
+            assert not nd and not ng
+            rows.append((ld, lg, float(s.last_g["l1"])))
+        curves[mode] = torch.tensor(rows)
+    first = {k: v[:20].mean(0) for k, v in curves.items()}
+    last = {k: v[-40:].mean(0) for k, v in curves.items()}
+    print("first-20 / last-40 means (loss_d, loss_g, l1): fp32 %s -> %s; bf16 %s -> %s"
+          % (first["fp32"].tolist(), last["fp32"].tolist(), first["bf16"].tolist(), last["bf16"].tolist()))
+    for mode in ("fp32", "bf16"):
+        assert last[mode][2] < 0.8 * first[mode][2], "%s: the reconstruction loss did not fall" % mode
+    assert abs(last["bf16"][2] - last["fp32"][2]) <= 0.25 * last["fp32"][2]
+    assert abs(last["bf16"][1] - last["fp32"][1]) <= 0.25 * last["fp32"][1]
+    assert abs(last["bf16"][0] - last["fp32"][0]) <= 0.5 * max(last["fp32"][0], 0.5)

@@ -137,3 +137,40 @@ def test_bundle_roundtrip(tmp_path):
         f.write(bytes([b[0] ^ 1]))
     with pytest.raises(ValueError):
         tb.read_bundle(prefix)
+
+
+def test_restore_accepts_the_other_spellings_of_the_provisional_keys(tmp_path):
+    """The SN `u` vectors and the LSTM variables may sit under other names in a TensorFlow-written snapshot:
+    `restore` finds the single-path `u`, the pre-1.2 `weights` / `biases` LSTM names, and whatever `key_map` says."""
+    import torch
+    from sketchyscenecolorization_b200 import checkpoint, tf_bundle
+    from sketchyscenecolorization_b200.trainer import FgColorModel
+    from torch_ops import TorchOps
+    m = FgColorModel(TorchOps(torch.float32), "cpu", size=8, H=64, W=64)
+    m.initialize(seed=3)
+    prefix = checkpoint.save(m, str(tmp_path), 0, 1)
+    t = tf_bundle.read_bundle(prefix)
+    renamed = {}
+    for k, v in t.items():
+        k2 = k
+        mm = __import__("re").match(r"^(.*)/\1/u$", k)
+        if mm:
+            k2 = mm.group(1) + "/u"
+        k2 = k2.replace("basic_lstm_cell/kernel", "basic_lstm_cell/weights").replace("basic_lstm_cell/bias", "basic_lstm_cell/biases")
+        if k2.startswith("generator/TextLSTM/embedding"):
+            k2 = k2.replace("generator/TextLSTM/embedding", "generator/TextLSTM/my_embedding")
+        renamed[k2] = v
+    assert set(renamed) != set(t)
+    other = os.path.join(str(tmp_path), "other", "model_0.ckpt-0")
+    os.makedirs(os.path.dirname(other))
+    tf_bundle.write_bundle(other, renamed)
+    m2 = FgColorModel(TorchOps(torch.float32), "cpu", size=8, H=64, W=64)
+    m2.initialize(seed=9)
+    with pytest.raises(KeyError):
+        checkpoint.restore(m2, other)                       # the embedding is under a name no built-in alias covers
+    checkpoint.restore(m2, other, key_map={"generator/TextLSTM/embedding": "generator/TextLSTM/my_embedding"})
+    assert torch.equal(m2.gstore.flat, m.gstore.flat) and torch.equal(m2.dstore.flat, m.dstore.flat)
+    for k, v in m.dstore.state.items():
+        assert torch.equal(m2.dstore.state[k], v)
+    o = m.gstore.offsets["generator/TextLSTM/embedding"]
+    assert torch.equal(m2.gstore.adam_v[o:o + 10], m.gstore.adam_v[o:o + 10])
