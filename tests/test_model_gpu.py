@@ -262,17 +262,25 @@ def test_bf16_inference_error_is_stated():
 
 
 def test_bf16_trains_like_fp32():
-    """200 iterations of the session loop at size 16 / 64 x 64 on eight cycling batches, once in the split-precision mode
-    (bf16x3 convolutions, fp32 activations) and once in the benchmarked mode (single-pass bf16): same data, same noise,
-    same initial weights.  GAN training is chaotic, so the curves are compared as curves: the reconstruction loss must fall
-    in both, and the bf16 run's window means must stay within a band of the fp32 run's."""
+    """200 iterations of the session loop at size 16 / 64 x 64 on eight cycling batches whose target pictures are a function of
+    the sketch and the class (0.6 * sketch + 0.4 * class colour: learnable, unlike uniform noise), once in the split-precision
+    mode (bf16x3 convolutions, fp32 activations) and once in the benchmarked mode (single-pass bf16): same data, same noise,
+    same initial weights, learning rates 5x the defaults so that 200 iterations show the whole descent.  GAN training is
+    chaotic, so the curves are compared as curves: the reconstruction loss must fall by 10x in both, and the bf16 run's window
+    means must stay within a band of the fp32 run's."""
     from sketchyscenecolorization_b200.input_pipeline import SyntheticInput
     from sketchyscenecolorization_b200.main_procedure import TrainSession
 
     class Cycle:
         def __init__(self, seed, n=8):
             src = SyntheticInput(8, 64, 64, seed=seed)
-            self.b, self.i = [next(src) for _ in range(n)], 0
+            color = torch.rand(25, 3, generator=torch.Generator().manual_seed(99)) * 2 - 1
+            self.b, self.i = [], 0
+            for _ in range(n):
+                b = next(src)
+                for key, ck in (("images", "cls"), ("images_d", "cls_d")):
+                    b[key] = (0.6 * b["sketch"] + 0.4 * color[b[ck].long()][:, :, None, None]).contiguous()
+                self.b.append(b)
 
         def __iter__(self):
             return self
@@ -286,19 +294,22 @@ def test_bf16_trains_like_fp32():
         torch.manual_seed(3)
         torch.cuda.manual_seed(3)
         m = _model(16, 64, 64, dt, seed=4)
-        s = TrainSession(m, batch_size=8, max_iter=200, lr_g=2e-4, lr_d=1e-4, small=True, input_iter=Cycle(1), input_iter_d=Cycle(2))
+        s = TrainSession(m, batch_size=8, max_iter=200, lr_g=1e-3, lr_d=5e-4, small=True, input_iter=Cycle(1), input_iter_d=Cycle(2))
         rows = []
         for _ in range(200):
             ld, lg, nd, ng = s.iteration()
             assert not nd and not ng
             rows.append((ld, lg, float(s.last_g["l1"])))
         curves[mode] = torch.tensor(rows)
-    first = {k: v[:20].mean(0) for k, v in curves.items()}
+    first = {k: v[:5].mean(0) for k, v in curves.items()}
+    mid = {k: v[40:80].mean(0) for k, v in curves.items()}
     last = {k: v[-40:].mean(0) for k, v in curves.items()}
-    print("first-20 / last-40 means (loss_d, loss_g, l1): fp32 %s -> %s; bf16 %s -> %s"
-          % (first["fp32"].tolist(), last["fp32"].tolist(), first["bf16"].tolist(), last["bf16"].tolist()))
+    print("means over iterations 0-4 / 40-79 / 160-199 of (loss_d, loss_g, l1): fp32 %s / %s / %s; bf16 %s / %s / %s"
+          % tuple([[round(x, 3) for x in d[k].tolist()] for k in ("fp32", "bf16") for d in (first, mid, last)]))
     for mode in ("fp32", "bf16"):
-        assert last[mode][2] < 0.8 * first[mode][2], "%s: the reconstruction loss did not fall" % mode
-    assert abs(last["bf16"][2] - last["fp32"][2]) <= 0.25 * last["fp32"][2]
-    assert abs(last["bf16"][1] - last["fp32"][1]) <= 0.25 * last["fp32"][1]
-    assert abs(last["bf16"][0] - last["fp32"][0]) <= 0.5 * max(last["fp32"][0], 0.5)
+        assert last[mode][2] < 0.1 * first[mode][2], "%s: the reconstruction loss did not fall" % mode
+    assert abs(first["bf16"][2] - first["fp32"][2]) <= 0.02 * first["fp32"][2]          # same start
+    for w in (mid, last):                                                               # same descent, within a band
+        assert abs(w["bf16"][2] - w["fp32"][2]) <= 0.5 * w["fp32"][2]
+        assert abs(w["bf16"][1] - w["fp32"][1]) <= 0.5 * w["fp32"][1]
+        assert abs(w["bf16"][0] - w["fp32"][0]) <= 0.5 * max(w["fp32"][0], 0.5)
