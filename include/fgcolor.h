@@ -171,6 +171,19 @@ int fgc_l2norm_rows_fwd(const float* x, int R, int D, float* y, float* inv, fgc_
 int fgc_l2norm_rows_bwd(const float* gy, const float* y, const float* inv, int R, int D, float* gx, fgc_stream s);
 int fgc_embedding_fwd(const float* table, const int32_t* ids, int N, int T, int t, int D, float* out, fgc_stream s);
 int fgc_embedding_bwd(const float* g, const int32_t* ids, int N, int T, int t, int D, float* dtable, fgc_stream s);
+/* models_collection.py:182,211 for every time step at once: out[t, n, :] = table[ids[n, t], :]  ([T, N, D]) and its scatter-add */
+int fgc_embedding_all_fwd(const float* table, const int32_t* ids, int N, int T, int D, float* out, fgc_stream stream);
+int fgc_embedding_all_bwd(const float* g, const int32_t* ids, int N, int T, int D, float* dtable, fgc_stream stream);
+/* models_collection.py:173-213, the word LSTM (BasicLSTMCell :184, dynamic over T tokens, <pad> steps skipped :235) as ONE
+ * persistent launch.  gx [T, N, 4D]: the input half of the gate pre-activations, x_t @ kernel[0:Din] + bias, for every step;
+ * kh [D, 4D]: the recurrent rows kernel[Din:Din+D] (row-major, gate order i, j, f, o); ids [N, T] (0 = <pad>: state kept).
+ * Writes h_all / c_all [T+1, N, D] (slot 0 = the zero initial state, slot t+1 = state after step t) and pre_all [T, N, 4D].
+ * barrier: 4 bytes of device scratch.  D: multiple of 4, 16..512; N <= 256.  The backward call runs BPTT over the same
+ * sequence: g_hext [T, N, D] = gradient arriving at h(t) from outside the recurrence -> g_pre_all [T, N, 4D]. */
+int fgc_lstm_seq_fwd(const float* gx, const float* kh, const int32_t* ids, int T, int N, int D, float* h_all, float* c_all,
+                     float* pre_all, unsigned int* barrier, fgc_stream stream);
+int fgc_lstm_seq_bwd(const float* g_hext, const float* pre_all, const float* c_all, const float* kh, const int32_t* ids, int T,
+                     int N, int D, float* g_pre_all, unsigned int* barrier, fgc_stream stream);
 /* pre = gates (+gates2) (+grow[r/P]); R = N*P rows of 4*D; gates2/grow may be NULL */
 int fgc_lstm_cell_fwd(const float* gates, const float* gates2, const float* grow, const float* c_prev,
                       const float* h_prev, const int32_t* ids, int T, int t, int N, int P, int D,

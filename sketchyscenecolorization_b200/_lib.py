@@ -117,6 +117,10 @@ SIGNATURES = {
     "fgc_l2norm_rows_bwd": [_P, _P, _P, _I, _I, _P, _P],
     "fgc_embedding_fwd": [_P, _P, _I, _I, _I, _I, _P, _P],
     "fgc_embedding_bwd": [_P, _P, _I, _I, _I, _I, _P, _P],
+    "fgc_embedding_all_fwd": [_P, _P, _I, _I, _I, _P, _P],
+    "fgc_embedding_all_bwd": [_P, _P, _I, _I, _I, _P, _P],
+    "fgc_lstm_seq_fwd": [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "fgc_lstm_seq_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P],
     "fgc_lstm_cell_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "fgc_lstm_cell_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "fgc_rows_group_sum": [_P, _I, _I, _I, _P, _P],

@@ -425,6 +425,41 @@ class CudaOps(OpsBase):
         D = dtable.shape[1]
         check(self.lib.fgc_embedding_bwd(self._f32(g), self._p(ids), N, T, t, D, self._f32(dtable), self._s()), "embedding_bwd")
 
+    def embedding_all_fwd(self, table, ids):
+        N, T = ids.shape
+        D = table.shape[1]
+        out = self._empty((T, N, D), torch.float32)
+        check(self.lib.fgc_embedding_all_fwd(self._f32(table), self._p(ids), N, T, D, self._p(out), self._s()), "embedding_all_fwd")
+        return out
+
+    def embedding_all_bwd(self, g, ids, dtable):
+        N, T = ids.shape
+        D = dtable.shape[1]
+        assert tuple(g.shape) == (T, N, D)
+        check(self.lib.fgc_embedding_all_bwd(self._f32(g), self._p(ids), N, T, D, self._f32(dtable), self._s()), "embedding_all_bwd")
+
+    def lstm_seq_supported(self, N, D):
+        return D % 4 == 0 and 16 <= D <= 512 and N <= 256
+
+    def lstm_seq_fwd(self, gx, kh, ids):
+        T, N, D4 = gx.shape
+        D = D4 // 4
+        assert tuple(kh.shape) == (D, D4) and tuple(ids.shape) == (N, T)
+        h_all, c_all = self._empty((T + 1, N, D), torch.float32), self._empty((T + 1, N, D), torch.float32)
+        pre_all = self._empty((T, N, D4), torch.float32)
+        bar = self._empty((16,), torch.int32)
+        check(self.lib.fgc_lstm_seq_fwd(self._f32(gx), self._f32(kh), self._p(ids), T, N, D, self._p(h_all), self._p(c_all),
+                                        self._p(pre_all), self._p(bar), self._s()), "lstm_seq_fwd")
+        return h_all, c_all, pre_all
+
+    def lstm_seq_bwd(self, g_hext, pre_all, c_all, kh, ids):
+        T, N, D = g_hext.shape
+        g_pre_all = self._empty((T, N, 4 * D), torch.float32)
+        bar = self._empty((16,), torch.int32)
+        check(self.lib.fgc_lstm_seq_bwd(self._f32(g_hext), self._f32(pre_all), self._f32(c_all), self._f32(kh), self._p(ids), T, N, D,
+                                        self._p(g_pre_all), self._p(bar), self._s()), "lstm_seq_bwd")
+        return g_pre_all
+
     def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None):
         R, D = c_prev.shape
         N, T = ids.shape

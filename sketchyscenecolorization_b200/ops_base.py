@@ -204,6 +204,30 @@ class OpsBase:
         """dtable[ids[n,t]] += g[n]"""
         raise NotImplementedError
 
+    def embedding_all_fwd(self, table, ids):
+        """table[ids[n, t]] for every step: [T, N, D]"""
+        raise NotImplementedError
+
+    def embedding_all_bwd(self, g, ids, dtable):
+        """dtable[ids[n, t]] += g[t, n] over all steps"""
+        raise NotImplementedError
+
+    def lstm_seq_supported(self, N, D):
+        """Whether lstm_seq_fwd / lstm_seq_bwd take this batch / hidden size (else the caller steps the cell itself)."""
+        return False
+
+    def lstm_seq_fwd(self, gx, kh, ids):
+        """A whole BasicLSTMCell recurrence from the zero state (the word LSTM, models_collection.py:173-213): gx [T,N,4D] is the
+        input half of the gate pre-activations (x_t @ kernel[0:Din] + bias) of every step, kh [D,4D] the recurrent rows of the
+        kernel; <pad> steps (ids[n,t] == 0) keep the state.  Returns (h_all [T+1,N,D], c_all [T+1,N,D], pre_all [T,N,4D]);
+        slot 0 of the state stacks is the zero initial state, slot t+1 the state after step t."""
+        raise NotImplementedError
+
+    def lstm_seq_bwd(self, g_hext, pre_all, c_all, kh, ids):
+        """BPTT through lstm_seq_fwd: g_hext [T,N,D] is the gradient reaching h(t) from outside the recurrence; returns the
+        gate gradients of every step [T,N,4D] (the operand of the weight / input gradients)."""
+        raise NotImplementedError
+
     def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None):
         """BasicLSTMCell pointwise part.  pre = gates [+ gates2] [+ grow[r // P]]  ([R,4D], order i,j,f,o);
         c = c_prev*sig(f+1) + sig(i)*tanh(j); h = tanh(c)*sig(o); rows whose sample token ids[r//P, t] == 0 (<pad>) keep

@@ -232,3 +232,28 @@ def test_generator_without_caption(setup):
     assert all(float(g.abs().max()) == 0.0 for k, g in grads.items() if "TextLSTM" in k)
     assert _worst(m.gstore, {k: g for k, g in grads.items() if "TextLSTM" not in k}, ops) < 1e-7
     assert float(m.gstore.g["generator/TextLSTM/embedding"].abs().max()) == 0.0
+
+
+def test_word_lstm_fallback_path_equals_sequence_operator(setup):
+    """text_fusion steps the word LSTM a cell at a time where the operator set declines the size (lstm_seq_supported False:
+    hidden sizes beyond 512, the background generator): same forward and same gradients as the one-launch operator."""
+    from sketchyscenecolorization_b200 import text_fusion as TF
+
+    class NoSeq(TorchOps):
+        def lstm_seq_supported(self, N, D):
+            return False
+
+    outs = []
+    for cls in (TorchOps, NoSeq):
+        ops = cls(torch.float64)
+        m = FgColorModel(ops, "cpu", size=8, H=64, W=64, param_dtype=torch.float64)
+        m.initialize(seed=3, perturb_tables=0.1)
+        g = torch.Generator().manual_seed(0)
+        e4 = torch.randn(3, 2, 2, 64, generator=g, dtype=torch.float64)
+        ids = torch.tensor([[0, 0, 5, 7, 9], [0, 0, 0, 0, 0], [2, 4, 6, 8, 10]], dtype=torch.int32)
+        out, ctx = TF.text_fusion_fwd(ops, m.gstore, e4, ids.numpy())
+        m.gstore.grad.zero_()
+        g_e4 = TF.text_fusion_bwd(ops, m.gstore, torch.randn(out.shape, generator=g, dtype=torch.float64), ctx)
+        outs.append((out, g_e4, m.gstore.grad.clone()))
+    for a, b in zip(*outs):
+        assert (a - b).abs().max().item() <= 1e-12 * max(1.0, b.abs().max().item())

@@ -341,6 +341,57 @@ def test_text_ops(env):
     close(cu.atanh_relu_bwd(gy.float(), h.float()), ref.atanh_relu_bwd(gy, h), 1e-4, "atanh_relu bwd")
 
 
+@pytest.mark.parametrize("shape", [(15, 64, 512), (5, 3, 128), (4, 70, 64), (2, 1, 16), (15, 130, 512)], ids=str)
+def test_word_lstm_sequence_kernels(env, shape):
+    """fgc_lstm_seq_fwd / _bwd (the word LSTM's recurrence and its BPTT, one persistent launch each, grid barrier per step)
+    and the all-steps embedding gather / scatter against the plain-torch operators: the production size (T 15, N 64,
+    D 512: 128 co-resident CTAs), ragged batches, more than one 64-sample chunk, captions with leading <pad>s."""
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    T, N, D = shape
+    g = torch.Generator().manual_seed(T * 1000 + N)
+    ids = torch.randint(1, 58, (N, T), generator=g)
+    for n in range(N):                                      # pads are a prefix (text_processing.py:50-52); one all-pad row
+        ids[n, :int(torch.randint(0, T, (1,), generator=g))] = 0
+    if N > 2:
+        ids[1, :] = 0
+    ids = ids.to(dev, torch.int32).contiguous()
+    table = rnd((58, D), 1, dev)
+    e_r, e = ref.embedding_all_fwd(table, ids), cu.embedding_all_fwd(table.float(), ids)
+    assert e.shape == (T, N, D)
+    close(e, e_r, 1e-7, "embedding_all")
+    gx, kh = rnd((T, N, 4 * D), 2, dev), rnd((D, 4 * D), 3, dev, 1.0 / math.sqrt(D))
+    want = ref.lstm_seq_fwd(gx, kh, ids)
+    got = cu.lstm_seq_fwd(gx.float().contiguous(), kh.float().contiguous(), ids)
+    torch.cuda.synchronize()
+    for a, b, what in zip(got, want, ("h_all", "c_all", "pre_all")):
+        assert a.shape == b.shape
+        close(a, b, 2e-5, "lstm_seq_fwd " + what)
+    assert float(got[0][0].abs().max()) == 0.0 and float(got[1][0].abs().max()) == 0.0      # slot 0: the zero initial state
+    g_hext = rnd((T, N, D), 4, dev)
+    want_b = ref.lstm_seq_bwd(g_hext, want[2], want[1], kh, ids)
+    got_b = cu.lstm_seq_bwd(g_hext.float().contiguous(), got[2], got[1], kh.float().contiguous(), ids)
+    torch.cuda.synchronize()
+    close(got_b, want_b, 5e-5, "lstm_seq_bwd")
+    # against autograd through the plain recurrence (pins the hand-written BPTT of both implementations)
+    gxa, kha = gx.clone().requires_grad_(True), kh.clone().requires_grad_(True)
+    h, c = torch.zeros(N, D, dtype=torch.float64, device=dev), torch.zeros(N, D, dtype=torch.float64, device=dev)
+    loss = 0.0
+    for t in range(T):
+        pre = gxa[t] + h @ kha
+        i, j, f, o = pre.chunk(4, dim=1)
+        c2 = c * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j)
+        h2 = torch.tanh(c2) * torch.sigmoid(o)
+        m = (ids[:, t] != 0)[:, None]
+        c, h = torch.where(m, c2, c), torch.where(m, h2, h)
+        loss = loss + (h * g_hext[t]).sum()
+    loss.backward()
+    close(got_b, gxa.grad, 5e-5, "lstm_seq_bwd vs autograd")
+    dt_r, dt_ = torch.zeros_like(table), torch.zeros_like(table).float()
+    ref.embedding_all_bwd(g_hext, ids, dt_r)
+    cu.embedding_all_bwd(g_hext.float().contiguous(), ids, dt_)
+    close(dt_, dt_r, 1e-5, "embedding_all bwd")
+
+
 @pytest.mark.parametrize("kc", [(27 * 8, 8), (1152, 128), (768, 1), (768, 25), (6912, 768)], ids=str)
 def test_spectral_norm(env, kc):
     cu, ref, dev = env["cu"], env["ref"], env["dev"]

@@ -340,6 +340,39 @@ class TorchOps(OpsBase):
     def embedding_bwd(self, g, ids, t, dtable):
         dtable.index_add_(0, ids[:, t].long(), g.to(dtable.dtype))
 
+    def embedding_all_fwd(self, table, ids):
+        return table[ids.long().t()].to(self.cdt).contiguous()
+
+    def embedding_all_bwd(self, g, ids, dtable):
+        dtable.index_add_(0, ids.long().t().reshape(-1), g.reshape(-1, g.shape[-1]).to(dtable.dtype))
+
+    def lstm_seq_supported(self, N, D):
+        return True
+
+    def lstm_seq_fwd(self, gx, kh, ids):
+        T, N, D4 = gx.shape
+        D = D4 // 4
+        h_all, c_all = gx.new_zeros((T + 1, N, D)), gx.new_zeros((T + 1, N, D))
+        pre_all = gx.new_zeros((T, N, D4))
+        for t in range(T):
+            pre = gx[t] + h_all[t] @ kh
+            i, j, f, o = pre.chunk(4, dim=1)
+            c = c_all[t] * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j)
+            h = torch.tanh(c) * torch.sigmoid(o)
+            m = (ids[:, t] != 0)[:, None]
+            pre_all[t], c_all[t + 1], h_all[t + 1] = pre, torch.where(m, c, c_all[t]), torch.where(m, h, h_all[t])
+        return h_all, c_all, pre_all
+
+    def lstm_seq_bwd(self, g_hext, pre_all, c_all, kh, ids):
+        T, N, D = g_hext.shape
+        g_pre_all = torch.zeros_like(pre_all)
+        g_h, g_c = torch.zeros_like(g_hext[0]), torch.zeros_like(g_hext[0])
+        for t in range(T - 1, -1, -1):
+            g_pre, g_c, g_pass = self.lstm_cell_bwd(g_c, g_hext[t] + g_h, pre_all[t], c_all[t], c_all[t + 1], ids, t, 1)
+            g_pre_all[t] = g_pre
+            g_h = g_pre @ kh.t() + g_pass
+        return g_pre_all
+
     def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None):
         pre = gates.clone()
         if gates2 is not None:
