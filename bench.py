@@ -408,6 +408,103 @@ def run_product(args):
         os._exit(0)
 
 
+# ----------------------------------------------------------------------------------------------------------
+# the other configurations of BASELINE.json, one line each (not the driver's headline): --mode infer | bg
+# ----------------------------------------------------------------------------------------------------------
+def _time_calls(torch, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in ev:
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    ms = sorted(e0.elapsed_time(e1) for e0, e1 in ev)
+    return ms[len(ms) // 2], ms[0]
+
+
+def run_infer(args):
+    """BASELINE.json configs[0]: one 192x192 sketch + 'the bus is orange' through the generator (main_procedure.py:593-597), in
+    the parity mode inference runs in (fp32 storage, bf16x3 tensor-core convolutions), checked against the fp64 oracle in the
+    same run.  value = latency of one picture resident on the device; e2e = host sketch in, host picture out."""
+    import torch
+    from oracle import fgcolor_oracle as O
+    from sketchyscenecolorization_b200.cuda_ops import CudaOps
+    from sketchyscenecolorization_b200.trainer import FgColorModel
+    dev = "cuda:0"
+    ops = CudaOps(dev, torch.float32)
+    m = FgColorModel(ops, dev, size=SIZE, H=H, W=W, with_discriminator=False)
+    m.initialize(seed=0, perturb_tables=0.1)
+    b = O.make_batch(1, H, W, 11, torch.float64, n_pad=12)
+    b["text"][0, 12:] = torch.tensor([24, 3, 6])            # 'the bus is orange' (tests/golden/text_ids.json), class 2 = bus
+    b["cls"][0] = 2
+    sk, noise = b["sketch"].float().to(dev), b["noise"].float().to(dev)
+    ids_host, ids_dev, cls = b["text"].numpy(), b["text"].int().to(dev), b["cls"].int().to(dev)
+    eager_ms, _ = _time_calls(torch, lambda: m.generate(sk, ids_host, cls, noise), args.steps, args.warmup)
+    n0 = ops.launch_count()
+    out = m.generate(sk, ids_host, cls, noise)
+    launches = ops.launch_count() - n0
+    replay_ms, replay_best = _time_calls(torch, lambda: m.generate_replay(sk, ids_dev, cls, noise), args.steps, args.warmup + 2)
+    sk_host, noise_host = b["sketch"].float().pin_memory(), b["noise"].float().pin_memory()
+
+    def e2e():
+        return m.generate_replay(sk_host, ids_dev, cls, noise_host).cpu()
+    e2e_ms, _ = _time_calls(torch, e2e, args.steps, args.warmup)
+    gp = {k: v.detach().cpu().double() for k, v in m.gstore.state_dict().items()}
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        ref = O.generator_forward(gp, b["sketch"], b["text"], b["cls"], b["noise"], SIZE)
+        cpu_s = time.perf_counter() - t0
+    err = (m.generate_replay(sk, ids_dev, cls, noise).cpu().double() - ref).abs().max().item()
+    err_eager = (out.cpu().double() - ref).abs().max().item()
+    infer_gflop = GF_GFLOP + 3 * 0.151 * 2
+    print(json.dumps({
+        "metric": "fg-colorization inference latency @192x192 bs1", "value": replay_ms, "unit": "ms/image", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": replay_ms, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (bf16x3 split tensor-core products)", "data": "synthetic",
+        "config": {"workload": "single 192x192 sketch + 'the bus is orange' fg-colorization inference (BASELINE.json configs[0])",
+                   "max_abs_err_vs_fp64_oracle": err, "max_abs_err_eager_vs_fp64_oracle": err_eager, "tolerance": 1e-3,
+                   "cuda_graph_replay_ms": replay_ms, "cuda_graph_replay_best_ms": replay_best, "eager_ms": eager_ms,
+                   "gflop_per_image": round(infer_gflop, 2), "tflops": round(infer_gflop / replay_ms, 2)},
+        "e2e": {"value": e2e_ms, "unit": "ms/image", "h2d_bytes_per_step": sk_host.numel() * 4 + noise_host.numel() * 4,
+                "d2h_bytes_per_step": 3 * H * W * 4, "api": "FgColorModel.generate_replay (host sketch in, host picture out)"},
+        "gpu_launches": launches * args.steps,
+        "cpu_baseline": {"value": cpu_s * 1e3, "unit": "ms/image", "cores": os.cpu_count() or 1, "kind": "port",
+                         "sample": "oracle generator_forward, fp64, one picture"}}), flush=True)
+
+
+def run_bg(args):
+    """BASELINE.json configs[3]: the background generator, 768x768, batch 1, 8-token caption."""
+    import numpy as np
+    import torch
+    from sketchyscenecolorization_b200.bg import BgColorModel
+    from sketchyscenecolorization_b200.cuda_ops import CudaOps
+    ids = np.array([[0, 2, 3, 4, 5, 8, 3, 7]], dtype=np.int32)
+    res = {}
+    for name, dt in (("parity", torch.float32), ("bf16", torch.bfloat16)):
+        ops = CudaOps("cuda:0", dt)
+        m = BgColorModel(ops, "cuda:0", ngf=64, vocab_size=18)
+        m.initialize(seed=0)
+        img = torch.rand(1, 768, 768, 3, device="cuda") * 2 - 1
+        n0 = ops.launch_count()
+        m.generate(img, ids)
+        launches = ops.launch_count() - n0
+        med, best = _time_calls(torch, lambda: m.generate(img, ids), args.steps, args.warmup)
+        res[name] = dict(ms=med, best_ms=best, launches=launches)
+        del m, ops
+        torch.cuda.empty_cache()
+    print(json.dumps({
+        "metric": "background-colorization generator inference latency @768x768 bs1", "value": res["parity"]["ms"], "unit": "ms/image",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["parity"]["ms"], "higher_is_better": False,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (bf16x3 split tensor-core products)", "data": "synthetic",
+        "config": {"workload": "background-colorization generator 768x768 inference, bs 1 (BASELINE.json configs[3])",
+                   "parity_mode": res["parity"], "single_pass_bf16": res["bf16"],
+                   "parity": "tests/test_bg_gpu.py: max-abs vs the fp64 oracle against the fp32-oracle yardstick (DESIGN.md section 7)"},
+        "gpu_launches": res["parity"]["launches"] * args.steps}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -421,9 +518,15 @@ def main():
                     help="source of the e2e leg: ready pinned fp32 tensors (default) or synthetic TFRecord files through the "
                          "real input pipeline")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
+    ap.add_argument("--mode", default="train", choices=["train", "infer", "bg"],
+                    help="train: the headline (BASELINE.json configs[1]); infer: configs[0] latency + parity; bg: configs[3] latency")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "infer":
+        run_infer(args)
+    elif args.mode == "bg":
+        run_bg(args)
     else:
         run_product(args)
 

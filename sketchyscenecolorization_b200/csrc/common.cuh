@@ -95,6 +95,12 @@ template <> __device__ __forceinline__ void stv<__nv_bfloat16, 8>(__nv_bfloat16*
 __device__ __forceinline__ float miu_relu(float x) { return 0.5f * (x + sqrtf(0.09f + x * x)); }
 __device__ __forceinline__ float miu_relu_grad(float x) { return 0.5f * (1.f + x * rsqrtf(0.09f + x * x)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// single-MUFU forms for the streaming passes (relative error 2^-23 / 2^-22.9: far inside every tolerance of the path; the
+// IEEE sqrtf / division sequences cost 8-12 issue slots per element, and those passes are issue-bound next to HBM)
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float miu_relu_fast(float x) { return 0.5f * (x + sqrt_approx(fmaf(x, x, 0.09f))); }
+__device__ __forceinline__ float miu_relu_grad_fast(float x) { return fmaf(0.5f * x, rsqrt_approx(fmaf(x, x, 0.09f)), 0.5f); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

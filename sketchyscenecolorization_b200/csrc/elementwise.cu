@@ -62,7 +62,7 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
 // channel statistics (tf.nn.moments over N,H,W; biased variance)
 // ======================================================================================================
 template <typename T, int V>
-__global__ void chan_stats_kernel(const T* __restrict__ x, long long M, int C, int rows_per_block, double* acc) {
+__global__ void __launch_bounds__(256, 4) chan_stats_kernel(const T* __restrict__ x, long long M, int C, int rows_per_block, double* acc) {
   extern __shared__ double sh_stats[];          // [2*C] block-level partial sums
   const int CV = C / V;
   const int lanes = blockDim.x / CV;          // row lanes per block
@@ -73,30 +73,29 @@ __global__ void chan_stats_kernel(const T* __restrict__ x, long long M, int C, i
   long long r1 = r0 + rows_per_block;
   if (r1 > M) r1 = M;
   if (rl < lanes) {
-    double s[V], ss[V];
+    // fp32 partials per thread (a thread sees rows_per_block / lanes ~ 100 rows), fp64 from the block level on
+    float s[V], ss[V];
 #pragma unroll
-    for (int i = 0; i < V; i++) s[i] = ss[i] = 0.0;
-    for (long long rb = r0 + rl; rb < r1; rb += (long long)lanes * 16) {
-      float ps[V], pss[V];
+    for (int i = 0; i < V; i++) s[i] = ss[i] = 0.f;
+    const T* px = x + v * V;
+    for (long long rb = r0 + rl; rb < r1; rb += (long long)lanes * 4) {      // four independent row loads in flight
+      float a[4][kMaxV];
 #pragma unroll
-      for (int i = 0; i < V; i++) ps[i] = pss[i] = 0.f;
-#pragma unroll 4
-      for (int j = 0; j < 16; j++) {
+      for (int j = 0; j < 4; j++) {
         long long r = rb + (long long)j * lanes;
-        if (r < r1) {
-          float a[kMaxV];
-          ldv<T, V>(x + r * C + v * V, a);
-#pragma unroll
-          for (int i = 0; i < V; i++) { ps[i] += a[i]; pss[i] += a[i] * a[i]; }
-        }
+        if (r < r1) ldv<T, V>(px + r * C, a[j]);
       }
 #pragma unroll
-      for (int i = 0; i < V; i++) { s[i] += ps[i]; ss[i] += pss[i]; }
+      for (int j = 0; j < 4; j++) {
+        if (rb + (long long)j * lanes >= r1) continue;
+#pragma unroll
+        for (int i = 0; i < V; i++) { s[i] += a[j][i]; ss[i] = fmaf(a[j][i], a[j][i], ss[i]); }
+      }
     }
 #pragma unroll
     for (int i = 0; i < V; i++) {
-      atomicAdd(&sh_stats[v * V + i], s[i]);
-      atomicAdd(&sh_stats[C + v * V + i], ss[i]);
+      atomicAdd(&sh_stats[v * V + i], (double)s[i]);
+      atomicAdd(&sh_stats[C + v * V + i], (double)ss[i]);
     }
   }
   __syncthreads();
@@ -119,7 +118,7 @@ __global__ void chan_stats_finalize(const double* acc, long long M, int C, float
 // walks rows (pixels), so the per-(n,c) parameters (statistics, class-table rows, min/max) are loaded ONCE per thread
 // instead of once per element -- the first versions were bound by L1/TEX parameter traffic (ncu: 87-96% L1, < 2 TB/s).
 template <typename T, int V>
-__global__ void cbn_act_fwd_kernel(const T* __restrict__ x, int HW, int C, int rows_per_block, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256, 4) cbn_act_fwd_kernel(const T* __restrict__ x, int HW, int C, int rows_per_block, const float* __restrict__ stats,
                                    const float* __restrict__ scale, const float* __restrict__ offset,
                                    const int32_t* __restrict__ labels, int act, T* __restrict__ y) {
   const int CV = C / V;
@@ -128,23 +127,24 @@ __global__ void cbn_act_fwd_kernel(const T* __restrict__ x, int HW, int C, int r
   if (rl >= lanes) return;
   const int n = blockIdx.y;
   const int l = labels[n];
-  float mean[V], rstd[V], ga[V], be[V];
+  float A[V], B[V];              // (x - mean) * rstd * scale + offset = x * A + B
 #pragma unroll
   for (int k = 0; k < V; k++) {
     int c = v * V + k;
-    mean[k] = stats[c]; rstd[k] = stats[C + c];
-    ga[k] = scale[l * C + c]; be[k] = offset[l * C + c];
+    A[k] = stats[C + c] * scale[l * C + c];
+    B[k] = fmaf(-stats[c], A[k], offset[l * C + c]);
   }
   const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
   const long long base = (long long)n * HW * C + v * V;
+  const bool miu = act == FGC_ACT_MIU;
 #pragma unroll 4
   for (int r = r0 + rl; r < r1; r += lanes) {
     float a[kMaxV], o[kMaxV];
     ldv<T, V>(x + base + (long long)r * C, a);
 #pragma unroll
     for (int k = 0; k < V; k++) {
-      float t = (a[k] - mean[k]) * rstd[k] * ga[k] + be[k];
-      o[k] = act == FGC_ACT_MIU ? miu_relu(t) : t;
+      float t = fmaf(a[k], A[k], B[k]);
+      o[k] = miu ? miu_relu_fast(t) : t;
     }
     stv<T, V>(y + base + (long long)r * C, o);
   }
@@ -152,7 +152,7 @@ __global__ void cbn_act_fwd_kernel(const T* __restrict__ x, int HW, int C, int r
 
 // per-(n,c) sums of g and g*xhat where g = gy*act'(y)    -> sums[0][n][c], sums[1][n][c]
 template <typename T, int V>
-__global__ void cbn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restrict__ x, int HW, int C, int rows_per_block,
+__global__ void __launch_bounds__(256, 3) cbn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                       const float* __restrict__ stats, const float* __restrict__ scale,
                                       const float* __restrict__ offset, const int32_t* __restrict__ labels, int act,
                                       int N, float* sums) {
@@ -165,14 +165,15 @@ __global__ void cbn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restr
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh_red[i] = 0.f;
   __syncthreads();
   int r0 = blockIdx.x * rows_per_block, r1 = rl < lanes ? min(r0 + rows_per_block, HW) : 0;
-  float mean[V], rstd[V], ga[V], be[V], s1[V], s2[V];
+  float rs[V], nm[V], A[V], B[V], s1[V], s2[V];      // xhat = x * rs + nm;  scale * xhat + offset = x * A + B
 #pragma unroll
   for (int k = 0; k < V; k++) {
     int c = v * V + k;
-    mean[k] = stats[c]; rstd[k] = stats[C + c];
-    ga[k] = scale[l * C + c]; be[k] = offset[l * C + c];
+    rs[k] = stats[C + c]; nm[k] = -stats[c] * rs[k];
+    A[k] = rs[k] * scale[l * C + c]; B[k] = fmaf(-stats[c], A[k], offset[l * C + c]);
     s1[k] = s2[k] = 0.f;
   }
+  const bool miu = act == FGC_ACT_MIU;
   // two independent row loads per tensor in flight per thread; four (profiles/r1q) cost registers / resident CTAs and ran
   // 15-20% slower on the 604 MB tensor
   for (int rb = r0 + rl; rb < r1; rb += 2 * lanes) {
@@ -191,10 +192,9 @@ __global__ void cbn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restr
       if (rb + u * lanes >= r1) continue;
 #pragma unroll
       for (int k = 0; k < V; k++) {
-        float xh = (a[u][k] - mean[k]) * rstd[k];
         float gg = g[u][k];
-        if (act == FGC_ACT_MIU) gg *= miu_relu_grad(xh * ga[k] + be[k]);
-        s1[k] += gg; s2[k] += gg * xh;
+        if (miu) gg *= miu_relu_grad_fast(fmaf(a[u][k], A[k], B[k]));
+        s1[k] += gg; s2[k] = fmaf(gg, fmaf(a[u][k], rs[k], nm[k]), s2[k]);
       }
     }
   }
@@ -216,11 +216,12 @@ __global__ void cbn_bwd_reduce_kernel(const T* __restrict__ gy, const T* __restr
 // sample and spent 48 us per call on L2 latency alone.
 __global__ void cbn_bwd_finalize_kernel(const float* __restrict__ sums, int N, int C, long long M, const float* __restrict__ scale,
                                         const int32_t* __restrict__ labels, float* dscale, float* doffset, float* m12) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // a warp per channel: its lanes take the samples (the one-thread-per-channel form walked the 64 samples in sequence and
+  // was pure latency: 33 us per call); class-table updates are fire-and-forget red.add
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double m1 = 0, m2 = 0;
-#pragma unroll 8
-  for (int n = 0; n < N; n++) {
+  for (int n = lane; n < N; n += 32) {
     const int l = __ldg(labels + n);
     const float s1 = __ldg(sums + (long long)n * C + c), s2 = __ldg(sums + ((long long)N + n) * C + c);
     const float g = __ldg(scale + l * C + c);
@@ -228,11 +229,15 @@ __global__ void cbn_bwd_finalize_kernel(const float* __restrict__ sums, int N, i
     atomicAdd(dscale + l * C + c, s2);
     m1 += (double)g * s1; m2 += (double)g * s2;
   }
-  m12[c] = (float)(m1 / (double)M);
-  m12[C + c] = (float)(m2 / (double)M);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o); }
+  if (lane == 0) {
+    m12[c] = (float)(m1 / (double)M);
+    m12[C + c] = (float)(m2 / (double)M);
+  }
 }
 template <typename T, int V>
-__global__ void cbn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, int HW, int C, int rows_per_block,
+__global__ void __launch_bounds__(256, 3) cbn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                      const float* __restrict__ stats, const float* __restrict__ scale,
                                      const float* __restrict__ offset, const int32_t* __restrict__ labels, int act,
                                      const float* __restrict__ m12, T* __restrict__ gx, float* dbias) {
@@ -247,15 +252,20 @@ __global__ void cbn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restri
   const bool on = rl < lanes;
   const int n = blockIdx.y;
   const int l = labels[n];
-  float mean[V], rstd[V], ga[V], be[V], m1[V], m2[V], bs[V];
+  // gx = rstd * (g * scale - m1 - xhat * m2) = g * G + x * X + K  with  G = rstd * scale, X = -rstd^2 * m2,
+  // K = rstd * (mean * rstd * m2 - m1);   act'(scale * xhat + offset) is evaluated at x * A + B
+  float A[V], B[V], G[V], X[V], K[V], bs[V];
 #pragma unroll
   for (int k = 0; k < V; k++) {
     int c = v * V + k;
-    mean[k] = stats[c]; rstd[k] = stats[C + c];
-    ga[k] = scale[l * C + c]; be[k] = offset[l * C + c];
-    m1[k] = m12[c]; m2[k] = m12[C + c];
+    const float mean = stats[c], rstd = stats[C + c], ga = scale[l * C + c];
+    G[k] = rstd * ga;
+    A[k] = G[k]; B[k] = fmaf(-mean, G[k], offset[l * C + c]);      // (A aliases G: one register)
+    X[k] = -rstd * rstd * m12[C + c];
+    K[k] = rstd * (mean * rstd * m12[C + c] - m12[c]);
     bs[k] = 0.f;
   }
+  const bool miu = act == FGC_ACT_MIU;
   const int r0 = blockIdx.x * rows_per_block, r1 = on ? min(r0 + rows_per_block, HW) : 0;
   const long long base = (long long)n * HW * C + v * V;
 #pragma unroll 2
@@ -265,10 +275,9 @@ __global__ void cbn_bwd_apply_kernel(const T* __restrict__ gy, const T* __restri
     ldv<T, V>(gy + base + (long long)r * C, g);
 #pragma unroll
     for (int k = 0; k < V; k++) {
-      float xh = (a[k] - mean[k]) * rstd[k];
       float gg = g[k];
-      if (act == FGC_ACT_MIU) gg *= miu_relu_grad(xh * ga[k] + be[k]);
-      o[k] = rstd[k] * (gg * ga[k] - m1[k] - xh * m2[k]);
+      if (miu) gg *= miu_relu_grad_fast(fmaf(a[k], A[k], B[k]));
+      o[k] = fmaf(gg, G[k], fmaf(a[k], X[k], K[k]));
       bs[k] += o[k];
     }
     stv<T, V>(gx + base + (long long)r * C, o);
@@ -380,7 +389,7 @@ __global__ void prelu_bwd_rows_kernel(const T* __restrict__ gy, const T* __restr
 // min-max gate normalisation
 // ======================================================================================================
 template <typename T, int V>
-__global__ void minmax_reduce_kernel(const T* __restrict__ x, int HW, int C, int rows_per_block, uint32_t* mn_ord,
+__global__ void __launch_bounds__(256, 4) minmax_reduce_kernel(const T* __restrict__ x, int HW, int C, int rows_per_block, uint32_t* mn_ord,
                                      uint32_t* mx_ord) {
   extern __shared__ uint32_t sh_mm[];            // [2][C] block-level min / max (order-preserving encoding)
   const int CV = C / V;
@@ -421,19 +430,21 @@ __global__ void minmax_reduce_kernel(const T* __restrict__ x, int HW, int C, int
   }
 }
 template <typename T, int V>
-__global__ void minmax_apply_kernel(const T* __restrict__ x, int HW, int C, int rows_per_block, const uint32_t* __restrict__ mn_ord,
+__global__ void __launch_bounds__(256, 4) minmax_apply_kernel(const T* __restrict__ x, int HW, int C, int rows_per_block, const uint32_t* __restrict__ mn_ord,
                                     const uint32_t* __restrict__ mx_ord, T* __restrict__ gate, float* mn, float* mx) {
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
   if (rl >= lanes) return;
   const int n = blockIdx.y;
-  float lo[V], hi[V];
+  float lo[V], inv[V];           // (x - mn) / (mx - mn) as (x - mn) * inv: one IEEE division per (n, c) instead of one per element
 #pragma unroll
   for (int k = 0; k < V; k++) {
     long long q = (long long)n * C + v * V + k;
-    lo[k] = ord2f(mn_ord[q]); hi[k] = ord2f(mx_ord[q]);
-    if (blockIdx.x == 0 && rl == 0) { mn[q] = lo[k]; mx[q] = hi[k]; }
+    lo[k] = ord2f(mn_ord[q]);
+    const float hi = ord2f(mx_ord[q]);
+    inv[k] = 1.0f / (hi - lo[k]);
+    if (blockIdx.x == 0 && rl == 0) { mn[q] = lo[k]; mx[q] = hi; }
   }
   const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
   const long long base = (long long)n * HW * C + v * V;
@@ -442,13 +453,13 @@ __global__ void minmax_apply_kernel(const T* __restrict__ x, int HW, int C, int 
     float a[kMaxV], o[kMaxV];
     ldv<T, V>(x + base + (long long)r * C, a);
 #pragma unroll
-    for (int k = 0; k < V; k++) o[k] = (a[k] - lo[k]) / (hi[k] - lo[k]);
+    for (int k = 0; k < V; k++) o[k] = (a[k] - lo[k]) * inv[k];
     stv<T, V>(gate + base + (long long)r * C, o);
   }
 }
 // sums[0] = sum g*(x-mn), sums[1] = sum g, sums[2] = #(x==mx), sums[3] = #(x==mn)   each [N,C]
 template <typename T, int V>
-__global__ void minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
+__global__ void __launch_bounds__(256, 3) minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                          const float* __restrict__ mn, const float* __restrict__ mx, int N, float* sums) {
   extern __shared__ float sh_red[];              // [4][C] block-level partial sums
   const int CV = C / V;
@@ -504,7 +515,7 @@ __global__ void minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __re
   }
 }
 template <typename T, int V>
-__global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
+__global__ void __launch_bounds__(256, 3) minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                         const float* __restrict__ mn, const float* __restrict__ mx, int N,
                                         const float* __restrict__ sums, T* __restrict__ gpre, float* dbias) {
   extern __shared__ float sh_db[];               // [C] block-level column sums of gpre (only when dbias != NULL)
@@ -518,14 +529,16 @@ __global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __res
   const bool on = rl < lanes;
   const int n = blockIdx.y;
   const long long NC = (long long)N * C;
-  float lo[V], hi[V], d[V], a_mx[V], a_mn[V], bs[V];   // per-(n,c): min, max, range, shares of the arg-max / arg-min pixels
+  float lo[V], hi[V], invd[V], a_mx[V], a_mn[V], bs[V];   // per-(n,c): min, max, 1/range, shares of the arg-max / arg-min pixels
 #pragma unroll
   for (int k = 0; k < V; k++) {
     long long q = (long long)n * C + v * V + k;
-    lo[k] = mn[q]; hi[k] = mx[q]; d[k] = hi[k] - lo[k];
+    lo[k] = mn[q]; hi[k] = mx[q];
+    const float d = hi[k] - lo[k];
+    invd[k] = 1.0f / d;
     float A = sums[q], S = sums[NC + q];
-    a_mx[k] = (-A / (d[k] * d[k])) / sums[2 * NC + q];
-    a_mn[k] = ((A - d[k] * S) / (d[k] * d[k])) / sums[3 * NC + q];
+    a_mx[k] = (-A / (d * d)) / sums[2 * NC + q];
+    a_mn[k] = ((A - d * S) / (d * d)) / sums[3 * NC + q];
     bs[k] = 0.f;
   }
   const int r0 = blockIdx.x * rows_per_block, r1 = on ? min(r0 + rows_per_block, HW) : 0;
@@ -537,7 +550,7 @@ __global__ void minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __res
     ldv<T, V>(gg + base + (long long)r * C, g);
 #pragma unroll
     for (int k = 0; k < V; k++) {
-      float rr = g[k] / d[k];
+      float rr = g[k] * invd[k];
       if (a[k] == hi[k]) rr += a_mx[k];
       if (a[k] == lo[k]) rr += a_mn[k];
       o[k] = rr * (a[k] > 0.f ? 1.f : 0.2f);
@@ -956,7 +969,7 @@ int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int
                                                                                           p.rows_per_block, stats, scale, offset,
                                                                                           labels, act, N, sums);
   });
-  cbn_bwd_finalize_kernel<<<cdiv(C, 32), 32, 0, s>>>(sums, N, C, (long long)N * HW, scale, labels, dscale, doffset, m12);
+  cbn_bwd_finalize_kernel<<<cdiv(C, 8), 256, 0, s>>>(sums, N, C, (long long)N * HW, scale, labels, dscale, doffset, m12);
   (void)n;
   RowRed pa = rowred_plan(C, vec, HW, N);
   FGC_DISPATCH_TV(dtype, vec, T, V, {

@@ -28,6 +28,23 @@ _NETS = {'MRU': (generator_vars, Generator, discriminator_vars, Discriminator),
          'Residual': (residual_generator_vars, ResidualGenerator, residual_discriminator_vars, ResidualDiscriminator)}
 
 
+class _Range:
+    """NVTX range (tracing) around a phase of the step; a no-op without CUDA."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.on = torch.cuda.is_available()
+        if self.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def lr_decay(counter, max_iter):
     """graph_single.py:139 -- max(0.2, 1 - 0.9*counter/max_iter)."""
     return max(0.2, 1.0 - (float(counter) / max_iter * 0.9))
@@ -59,6 +76,33 @@ class FgColorModel:
     def generate(self, sketch_nchw, text_ids_host, labels, noise):
         out, _ = self.G.forward(sketch_nchw, text_ids_host, labels, noise, save=False)
         return self.ops.nhwc_to_nchw(out, out_dtype=torch.float32)
+
+    def generate_replay(self, sketch_nchw, text_ids, labels, noise):
+        """`generate` as a CUDA-graph replay (CUDA operator set): batch-1 inference is ~830 launches of microsecond kernels,
+        i.e. bound by the host's launch rate; the first call at a batch shape runs eagerly, the second is captured, later ones
+        copy the four inputs into the graph's buffers and replay it.  Caption ids go to the device (the <pad> steps are masked
+        inside the cells instead of skipped).  The returned tensor is the graph's output buffer: consume it before the next call."""
+        if not getattr(self.ops, 'supports_cuda_graphs', False):
+            return self.generate(sketch_nchw, text_ids, labels, noise)
+        dev = self.device
+        key = tuple(sketch_nchw.shape)
+        st = self.__dict__.setdefault('_gen_graphs', {}).setdefault(key, dict(calls=0))
+        st['calls'] += 1
+        ins = dict(sketch=torch.as_tensor(sketch_nchw).to(dev, torch.float32), text=torch.as_tensor(text_ids).to(dev, torch.int32),
+                   cls=torch.as_tensor(labels).to(dev, torch.int32), noise=torch.as_tensor(noise).to(dev, torch.float32))
+        if st['calls'] == 1:
+            return self.generate(ins['sketch'], ins['text'], ins['cls'], ins['noise'])
+        if 'graph' not in st:
+            st['in'] = {k: torch.empty_like(v) for k, v in ins.items()}
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                st['out'] = self.generate(st['in']['sketch'], st['in']['text'], st['in']['cls'], st['in']['noise'])
+            st['graph'] = graph
+        for k, v in ins.items():
+            st['in'][k].copy_(v, non_blocking=True)
+        st['graph'].replay()
+        return st['out']
 
     # ---- loss_d and dL/dtheta_D
     def d_step_grads(self, batch):
@@ -180,15 +224,21 @@ class FgColorTrainer:
             self.m.ops.optimizer_step(store, self.optimizer, lr, lr_dev=lr_dev)
 
     def _d_eager(self, batch, lr_dev=None):
-        out = self.m.d_step_grads(batch)
-        self._allreduce(self.m.dstore)
-        self._apply(self.m.dstore, self.lr_d * lr_decay(self.counter, self.max_iter), lr_dev)
+        with _Range("fgc.d_step.forward_backward"):
+            out = self.m.d_step_grads(batch)
+        with _Range("fgc.d_step.allreduce"):
+            self._allreduce(self.m.dstore)
+        with _Range("fgc.d_step.optimizer"):
+            self._apply(self.m.dstore, self.lr_d * lr_decay(self.counter, self.max_iter), lr_dev)
         return out
 
     def _g_eager(self, batch, lr_dev=None):
-        out = self.m.g_step_grads(batch)
-        self._allreduce(self.m.gstore)
-        self._apply(self.m.gstore, self.lr_g * lr_decay(self.counter, self.max_iter), lr_dev)
+        with _Range("fgc.g_step.forward_backward"):
+            out = self.m.g_step_grads(batch)
+        with _Range("fgc.g_step.allreduce"):
+            self._allreduce(self.m.gstore)
+        with _Range("fgc.g_step.optimizer"):
+            self._apply(self.m.gstore, self.lr_g * lr_decay(self.counter, self.max_iter), lr_dev)
         return out
 
     # ---- CUDA-graph steps
@@ -229,7 +279,8 @@ class FgColorTrainer:
         store.adam_t += 1
         bias = math.sqrt(1.0 - 0.9 ** store.adam_t) if self.optimizer == 'adam' else 1.0      # Adam's step-size correction
         st["lr"].fill_(base_lr * lr_decay(self.counter, self.max_iter) * bias)
-        st["graph"].replay()
+        with _Range("fgc.%s_step.graph_replay" % kind):
+            st["graph"].replay()
         return st["outputs"]
 
     def d_step(self, batch):
