@@ -84,6 +84,15 @@ int fgc_conv2d_fwd(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, i
                    const float* w, int k, int Cin_total, int Cout, const float* bias,
                    int stride, int pad_t, int pad_l, int OH, int OW, int act,
                    void* y, int y_dtype, void* ws, fgc_stream stream);
+/* The same, adding into y (y += act(conv + bias)) when `accumulate` != 0: the extra passes of the six-product mode. */
+int fgc_conv2d_fwd_acc(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W,
+                       const float* w, int k, int Cin_total, int Cout, const float* bias,
+                       int stride, int pad_t, int pad_l, int OH, int OW, int act, int accumulate,
+                       void* y, int y_dtype, void* ws, fgc_stream stream);
+/* Term `level` (0, 1, 2) of the three-way bf16 split of an fp32 tensor: r = x minus its first `level` bf16 terms;
+ * out_bf16 (optional) = bf16(r), out_f32 (optional) = r.  With bf16x3 (fp32 sources, the parity mode of mru.conv2d) these
+ * give the six-product mode: x1w1 + x1w2 + x2w1 (one bf16x3 pass) + x2w2 + x1w3 + x3w1 (three accumulating bf16 passes). */
+int fgc_split_term(const float* x, long long n, int level, void* out_bf16, float* out_f32, fgc_stream stream);
 
 /* gx[N,H,W,c_len] (=|+=) d/d(input channels [c_off,c_off+c_len)) of a stride-1 SAME conv given gy[N,H,W,Cout].
  * ups=1: gx is the 2x2-summed low-res gradient [N,H/2,W/2,c_len]; `scratch` must then hold N*H*W*c_len floats. */

@@ -32,8 +32,8 @@ cases = [  # name, fn, algorithmic bytes (bf16 storage: 2 B per element read or 
     ("minmax_bwd", lambda: ops.minmax_bwd(y, x, mn, mx), 10 * E),
     ("gate_fma_fwd", lambda: ops.gate_fma_fwd(x, z, y), 8 * E),
     ("gate_fma_bwd", lambda: ops.gate_fma_bwd(x, z, y), 10 * E),
-    ("blend_fwd", lambda: ops.blend_fwd(low, y, z), 8 * E + E // 2),
-    ("blend_bwd", lambda: ops.blend_bwd(x, low, y, z), 12 * E + E),
+    ("blend_fwd", lambda: ops.blend_fwd(low, y, z), 6 * E + E // 2),          # reads h2, zg, sk/4; writes out
+    ("blend_bwd", lambda: ops.blend_bwd(x, low, y, z), 11 * E),               # reads g, h2, zg, sk/4; writes g_h2, g_zg, g_sk/4
     ("mul_up_fwd", lambda: ops.mul_up_fwd(z, low), 4 * E + E // 2),
     ("addpool_fwd", lambda: ops.addpool_fwd(x, y), 4 * E + E // 2),
     ("prelu_fwd", lambda: ops.prelu_fwd(x, a), 4 * E),

@@ -79,6 +79,8 @@ SIGNATURES = {
     "fgc_im2col_small": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "fgc_debug_set_trace": [_P, _I],
     "fgc_conv2d_fwd": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "fgc_conv2d_fwd_acc": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "fgc_split_term": [_P, _LL, _I, _P, _P, _P],
     "fgc_conv2d_dgrad": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
     "fgc_conv2d_wgrad": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "fgc_chan_stats": [_P, _I, _LL, _I, _P, _P, _P],

@@ -14,6 +14,7 @@ class Config(object):
     # single-pass bf16 forward is O(1) away from the fp32 one there, so it trains in the split mode until bf16 has been measured
     train_precision_residual = 'fp32'
     infer_precision = 'fp32'     # inference / val / test always meet the 1e-3 parity bar
+    conv_terms = 2               # 2: bf16x3 split products; 3: six products (CudaOps(conv_terms=3)), see DESIGN.md section 7
 
     @staticmethod
     def set_from_dict(d):

@@ -93,6 +93,14 @@ int fgc_conv2d_fwd(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, i
                    const float* w, int k, int Cin_total, int Cout, const float* bias,
                    int stride, int pad_t, int pad_l, int OH, int OW, int act,
                    void* y, int y_dtype, void* ws, fgc_stream stream) {
+  return fgc_conv2d_fwd_acc(srcs, nsrc, src_dtype, N, H, W, w, k, Cin_total, Cout, bias, stride, pad_t, pad_l, OH, OW, act, 0, y,
+                            y_dtype, ws, stream);
+}
+
+int fgc_conv2d_fwd_acc(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W,
+                       const float* w, int k, int Cin_total, int Cout, const float* bias,
+                       int stride, int pad_t, int pad_l, int OH, int OW, int act, int accumulate,
+                       void* y, int y_dtype, void* ws, fgc_stream stream) {
   ConvGeom g;
   int e = build_geom(g, srcs, nsrc, N, H, W, k, stride, pad_t, pad_l, OH, OW, 1);
   if (e) return e;
@@ -100,12 +108,13 @@ int fgc_conv2d_fwd(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, i
   FGC_REQUIRE(cin == Cin_total, "conv_fwd: sources have %d channels, weights expect %d", cin, Cin_total);
   cudaStream_t s = as_stream(stream);
   if (conv_impl() == 1) {
+    FGC_REQUIRE(!accumulate, "conv_fwd: the CUDA-core checker does not accumulate");
     e = conv_fwd_simple(g, src_dtype, w, Cin_total, Cout, bias, act, y, y_dtype, s);
     if (e) return e;
     FGC_LAUNCH_CHECK("conv_fwd_simple");
     return FGC_OK;
   }
-  return conv_igemm_run(g, src_dtype, w, (long long)Cin_total * Cout, Cout, 1, 0, Cout, bias, act, 0, y, y_dtype, ws, s);
+  return conv_igemm_run(g, src_dtype, w, (long long)Cin_total * Cout, Cout, 1, 0, Cout, bias, act, accumulate, y, y_dtype, ws, s);
 }
 
 int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const float* w, int k, int Cin_total,

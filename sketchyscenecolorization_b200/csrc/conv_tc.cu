@@ -795,22 +795,14 @@ struct HaloArgs {
 // epilogue warps: one group of 4 per sub-tile, at most 2 groups (MT = 4: each group drains two sub-tiles in turn)
 __host__ __device__ constexpr int halo_epi_warps(int mt) { return mt > 2 ? 8 : 4 * mt; }
 
-// SWAP (BN = 128, MT = 2): the operand roles are exchanged -- the 128 output channels of the weight slab are the M side of
-// the MMA and the tile's 256 pixels its N side (one M128 x N256 x K16 instruction where the plain form issues two
-// M128 x N128 ones).  Same boxes, same weight slabs, same flops, but per K step the tensor core reads 4 KB of weights +
-// 8 KB of pixels from shared memory instead of 2 x (4 + 4) KB: the plain form sits exactly on the 128 B/clk shared-memory
-// read limit at N = 128 (ncu r1o: tensor pipe 45%), the exchanged one at 96 B/clk -- the ratio of the 256-wide layers,
-// which run at 1.24 PFLOP/s.  The accumulator then holds one output CHANNEL per TMEM lane and one pixel per column, so an
-// epilogue thread owns a channel: the bias is one register, and per-channel reductions need no shuffles.
-template <int BN, int MT, int NACC, bool SWAP = false>
+template <int BN, int MT, int NACC>
 __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
   static_assert(NACC * MT * BN <= 512, "accumulators exceed TMEM");
-  static_assert(!SWAP || (BN == 128 && MT == 2), "operand exchange: 128 channels x 256 pixels");
   constexpr int EW = halo_epi_warps(MT);
   constexpr int B_BYTES = BN * 128;
   constexpr int ACC_COLS = MT * BN;
   constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : (NACC * ACC_COLS <= 64 ? 64 : (NACC * ACC_COLS <= 128 ? 128 : (NACC * ACC_COLS <= 256 ? 256 : 512)));
-  constexpr uint32_t IDESC = SWAP ? make_idesc(BN, 128 * MT, 0, 0) : make_idesc(128, BN, 0, 0);
+  constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
   constexpr int MMA_WARP = 4, ALOAD_WARP = 5, BLOAD_WARP = 6, EPI_WARP0 = 8;
   constexpr int TH = 16 * MT;
 
@@ -914,26 +906,15 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
             const uint64_t db = desc_kmajor(smem_u32(sB + (size_t)bslot * B_BYTES), 1024);
             // box row of output row r under filter row kh = j:  r + j (forward) or r + k-1-j (mirrored taps of dgrad)
             const int jrow = big ? (sign > 0 ? j : k - 1 - j) : 0;
-            if constexpr (SWAP) {
-              // the pixel rows of both sub-tiles are contiguous atoms in either kind of A slot: one N = 256 operand
-              const uint64_t da = desc_kmajor(sa + (boxed ? (uint32_t)jrow * 1024u : 0u), 1024);
-              const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
+#pragma unroll
+            for (int tt = 0; tt < MT; tt++) {
+              const uint32_t aoff = boxed ? (uint32_t)(16 * tt + jrow) * 1024u : (uint32_t)tt * 16384u;
+              const uint64_t da = desc_kmajor(sa + aoff, 1024);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS + tt * BN);
 #pragma unroll
               for (int kk = 0; kk < 4; kk++) {
                 const uint32_t acc = (it > 0 || j > 0 || kk > 0) ? 1u : 0u;
-                umma_bf16(d_tmem, db + 2 * kk, da + 2 * kk, IDESC, acc);
-              }
-            } else {
-#pragma unroll
-              for (int tt = 0; tt < MT; tt++) {
-                const uint32_t aoff = boxed ? (uint32_t)(16 * tt + jrow) * 1024u : (uint32_t)tt * 16384u;
-                const uint64_t da = desc_kmajor(sa + aoff, 1024);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS + tt * BN);
-#pragma unroll
-                for (int kk = 0; kk < 4; kk++) {
-                  const uint32_t acc = (it > 0 || j > 0 || kk > 0) ? 1u : 0u;
-                  umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, acc);
-                }
+                umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, acc);
               }
             }
             umma_commit(smem_u32(&b_empty[bslot]));
@@ -1016,76 +997,6 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
       const int ty = rr / a.tiles_w, tx = rr - ty * a.tiles_w;
       mbar_wait(smem_u32(&acc_full[buf]), (ti / NACC) & 1);
       tc_fence_after();
-      if constexpr (SWAP) {
-        // TMEM lane l = output channel n0 + l, column p = pixel (p >> 3, p & 7) of the 32 x 8 tile; group `grp` drains the
-        // columns of sub-tile `grp`.  Per pixel a warp writes 32 consecutive channels (64 bytes of the NHWC row).
-        const int ch = n0 + l;
-        const bool cvalid = ch < a.Nout;
-        const float bias_c = (a.bias && cvalid) ? __ldg(a.bias + ch) : 0.f;
-        const int ow0 = tx * 8;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + grp * 128 + c0), r);
-          if (c0 + 32 >= 128) {                          // last read of this accumulator set by this warp
-            tc_fence_before();
-            mbar_arrive(smem_u32(&acc_empty[buf]));
-          }
-          float v[32];
-#pragma unroll
-          for (int q = 0; q < 32; q++) v[q] = __uint_as_float(r[q]) + bias_c;
-          switch (a.act) {
-            case FGC_ACT_LRELU:
-#pragma unroll
-              for (int q = 0; q < 32; q++) v[q] = v[q] > 0.f ? v[q] : 0.2f * v[q];
-              break;
-            case FGC_ACT_TANH:
-#pragma unroll
-              for (int q = 0; q < 32; q++) v[q] = tanhf(v[q]);
-              break;
-            case FGC_ACT_MIU:
-#pragma unroll
-              for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
-              break;
-            default: break;
-          }
-          if (!cvalid) continue;
-          const int oh0 = ty * TH + grp * 16 + (c0 >> 3);          // four tile rows per chunk
-          if (a.pool2) {
-            // the 2x2 partners of a pixel are columns p^1 and p^8: registers of this thread
-#pragma unroll
-            for (int q = 0; q < 32; q++) {
-              if ((q & 1) || (q & 8)) continue;
-              const int oh = oh0 + (q >> 3), ow = ow0 + (q & 7);
-              if (oh >= g.OH || ow >= g.OW) continue;
-              float sum = (v[q] + v[q + 1]) + (v[q + 8] + v[q + 9]);
-              const long long m = ((long long)n * (g.OH >> 1) + (oh >> 1)) * (g.OW >> 1) + (ow >> 1);
-              if (a.y_dtype == FGC_F32) {
-                float* yp = reinterpret_cast<float*>(a.y) + m * a.Nout + ch;
-                *yp = a.accumulate ? *yp + sum : sum;
-              } else {
-                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.Nout + ch;
-                *yp = __float2bfloat16_rn(a.accumulate ? __bfloat162float(*yp) + sum : sum);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 32; q++) {
-              const int oh = oh0 + (q >> 3), ow = ow0 + (q & 7);
-              if (oh >= g.OH || ow >= g.OW) continue;
-              const long long m = ((long long)n * g.OH + oh) * g.OW + ow;
-              if (a.y_dtype == FGC_F32) {
-                float* yp = reinterpret_cast<float*>(a.y) + m * a.Nout + ch;
-                *yp = a.accumulate ? *yp + v[q] : v[q];
-              } else {
-                __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.Nout + ch;
-                *yp = __float2bfloat16_rn(a.accumulate ? __bfloat162float(*yp) + v[q] : v[q]);
-              }
-            }
-          }
-        }
-        continue;
-      }
 #pragma unroll 1
       for (int tile = grp; tile < MT; tile += EW / 4) {
         const int oh = ty * TH + 16 * tile + (l >> 3), ow = tx * 8 + (l & 7);
@@ -1901,7 +1812,7 @@ static bool make_tmap_nhwc(CUtensorMap* out, const void* ptr, int C, int W, int 
 }
 
 // ---- halo-reuse forward / dgrad launcher ----
-template <int BN, int MT, int NACC, bool SWAP = false>
+template <int BN, int MT, int NACC>
 static int launch_halo(HaloArgs& h, cudaStream_t s) {
   constexpr int B_BYTES = BN * 128;
   const int budget = 216 * 1024;
@@ -1932,12 +1843,12 @@ static int launch_halo(HaloArgs& h, cudaStream_t s) {
   size_t smem = (size_t)a_slots * h.a_slot_bytes + (size_t)b_slots * B_BYTES + (2 * a_slots + 2 * b_slots + 2 * NACC) * 8 + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_halo_kernel<BN, MT, NACC, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_halo_kernel<BN, MT, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   long long ntiles = (long long)h.tiles_m * (h.Npad / BN);
   int grid = ntiles < num_sms() ? (int)ntiles : num_sms();
-  conv_halo_kernel<BN, MT, NACC, SWAP><<<grid, 32 * (8 + halo_epi_warps(MT)), smem, s>>>(h);
+  conv_halo_kernel<BN, MT, NACC><<<grid, 32 * (8 + halo_epi_warps(MT)), smem, s>>>(h);
   g_conv_counts[0]++;
   count_launch();
   return check_launch("conv_halo");
@@ -2043,13 +1954,7 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
     case 32: FGC_H(32, 2, 2);
     case 64: FGC_H(64, 2, 2);
     case 256: return mt == 2 ? launch_halo<256, 2, 1>(h, s) : launch_halo<256, 1, 2>(h, s);
-    default: {
-      // 128 output channels, 32 x 8 pixel tiles: exchanged operand roles (FGC_HALO_SWAP=0 keeps the plain form)
-      static int swap = -1;
-      if (swap < 0) { const char* e = getenv("FGC_HALO_SWAP"); swap = e ? atoi(e) : 1; }
-      if (mt == 2 && swap) return launch_halo<128, 2, 2, true>(h, s);
-      FGC_H(128, 2, 1);
-    }
+    default: FGC_H(128, 2, 1);
   }
 #undef FGC_H
 }

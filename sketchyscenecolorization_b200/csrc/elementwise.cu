@@ -63,17 +63,16 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
 // ======================================================================================================
 template <typename T, int V>
 __global__ void __launch_bounds__(256, 4) chan_stats_kernel(const T* __restrict__ x, long long M, int C, int rows_per_block, double* acc) {
-  extern __shared__ double sh_stats[];          // [2*C] block-level partial sums
+  extern __shared__ float sh_part[];          // [lanes][2*C] per-thread partial sums (no shared-memory atomics: the fp64
+                                              // CAS loops of the first version, 16 row lanes deep per address, were its tail)
   const int CV = C / V;
   const int lanes = blockDim.x / CV;          // row lanes per block
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh_stats[i] = 0.0;
-  __syncthreads();
   long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > M) r1 = M;
   if (rl < lanes) {
-    // fp32 partials per thread (a thread sees rows_per_block / lanes ~ 100 rows), fp64 from the block level on
+    // fp32 partials per thread (a thread sees rows_per_block / lanes rows: a few hundred), fp64 from the block level on
     float s[V], ss[V];
 #pragma unroll
     for (int i = 0; i < V; i++) s[i] = ss[i] = 0.f;
@@ -92,14 +91,16 @@ __global__ void __launch_bounds__(256, 4) chan_stats_kernel(const T* __restrict_
         for (int i = 0; i < V; i++) { s[i] += a[j][i]; ss[i] = fmaf(a[j][i], a[j][i], ss[i]); }
       }
     }
+    float* mine = sh_part + (size_t)rl * 2 * C + v * V;
 #pragma unroll
-    for (int i = 0; i < V; i++) {
-      atomicAdd(&sh_stats[v * V + i], (double)s[i]);
-      atomicAdd(&sh_stats[C + v * V + i], (double)ss[i]);
-    }
+    for (int i = 0; i < V; i++) { mine[i] = s[i]; mine[C + i] = ss[i]; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&acc[i], sh_stats[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    double t = 0.0;
+    for (int l = 0; l < lanes; l++) t += (double)sh_part[(size_t)l * 2 * C + i];
+    atomicAdd(&acc[i], t);
+  }
 }
 __global__ void chan_stats_finalize(const double* acc, long long M, int C, float* stats) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,14 +157,13 @@ __global__ void __launch_bounds__(256, 3) cbn_bwd_reduce_kernel(const T* __restr
                                       const float* __restrict__ stats, const float* __restrict__ scale,
                                       const float* __restrict__ offset, const int32_t* __restrict__ labels, int act,
                                       int N, float* sums) {
-  extern __shared__ float sh_red[];              // [2][C] block-level partial sums
+  extern __shared__ float sh_red[];              // [lanes][2][C] per-thread partial sums (deposited, then added per column:
+                                                 // fp32 atomicAdd on shared memory is a CAS loop, `lanes` deep per address)
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
   const int n = blockIdx.y;
   const int l = labels[n];
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh_red[i] = 0.f;
-  __syncthreads();
   int r0 = blockIdx.x * rows_per_block, r1 = rl < lanes ? min(r0 + rows_per_block, HW) : 0;
   float rs[V], nm[V], A[V], B[V], s1[V], s2[V];      // xhat = x * rs + nm;  scale * xhat + offset = x * A + B
 #pragma unroll
@@ -199,16 +199,16 @@ __global__ void __launch_bounds__(256, 3) cbn_bwd_reduce_kernel(const T* __restr
     }
   }
   if (rl < lanes) {
+    float* mine = sh_red + (size_t)rl * 2 * C + v * V;
 #pragma unroll
-    for (int k = 0; k < V; k++) {
-      atomicAdd(&sh_red[v * V + k], s1[k]);
-      atomicAdd(&sh_red[C + v * V + k], s2[k]);
-    }
+    for (int k = 0; k < V; k++) { mine[k] = s1[k]; mine[C + k] = s2[k]; }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {       // one global atomic per table entry and block
+    float t = 0.f;
+    for (int q2 = 0; q2 < lanes; q2++) t += sh_red[(size_t)q2 * 2 * C + i];
     int q = i / C, c = i - q * C;
-    atomicAdd(&sums[((long long)q * N + n) * C + c], sh_red[i]);
+    atomicAdd(&sums[((long long)q * N + n) * C + c], t);
   }
 }
 // one thread per channel: table gradients and batch means.  The per-sample loads are independent (unrolled, all in flight
@@ -241,14 +241,10 @@ __global__ void __launch_bounds__(256, 3) cbn_bwd_apply_kernel(const T* __restri
                                      const float* __restrict__ stats, const float* __restrict__ scale,
                                      const float* __restrict__ offset, const int32_t* __restrict__ labels, int act,
                                      const float* __restrict__ m12, T* __restrict__ gx, float* dbias) {
-  extern __shared__ float sh_db[];               // [C] block-level column sums of gx (only when dbias != NULL)
+  extern __shared__ float sh_db[];               // [lanes][C] per-thread column sums of gx (only when dbias != NULL)
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
-  if (dbias) {
-    for (int i = threadIdx.x; i < C; i += blockDim.x) sh_db[i] = 0.f;
-    __syncthreads();
-  }
   const bool on = rl < lanes;
   const int n = blockIdx.y;
   const int l = labels[n];
@@ -282,13 +278,18 @@ __global__ void __launch_bounds__(256, 3) cbn_bwd_apply_kernel(const T* __restri
     }
     stv<T, V>(gx + base + (long long)r * C, o);
   }
-  if (dbias) {                                   // bias gradient of the convolution in front: column sums of gx
+  if (dbias) {                                   // bias gradient of the convolution in front: column sums of the result
     if (on) {
+      float* mine = sh_db + (size_t)rl * C + v * V;
 #pragma unroll
-      for (int k = 0; k < V; k++) atomicAdd(&sh_db[v * V + k], bs[k]);
+      for (int k = 0; k < V; k++) mine[k] = bs[k];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sh_db[i]);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      float t = 0.f;
+      for (int q2 = 0; q2 < lanes; q2++) t += sh_db[(size_t)q2 * C + i];
+      atomicAdd(dbias + i, t);
+    }
   }
 }
 
@@ -345,13 +346,11 @@ __global__ void prelu_bwd_kernel(const T* __restrict__ gy, const T* __restrict__
 template <typename T, int V>
 __global__ void prelu_bwd_rows_kernel(const T* __restrict__ gy, const T* __restrict__ x, long long M, int C, int rows_per_block,
                                       const float* __restrict__ ap, float* da, T* __restrict__ gx, float* dbias) {
-  extern __shared__ float sh_db[];               // [C]
+  extern __shared__ float sh_db[];               // [lanes][C] per-thread column sums
   __shared__ float red[32];
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) sh_db[i] = 0.f;
-  __syncthreads();
   const bool on = rl < lanes;
   const float a = *ap;
   float acc = 0.f, bs[V];
@@ -374,15 +373,20 @@ __global__ void prelu_bwd_rows_kernel(const T* __restrict__ gy, const T* __restr
     stv<T, V>(gx + r * C + v * V, o);
   }
   if (on) {
+    float* mine = sh_db + (size_t)rl * C + v * V;
 #pragma unroll
-    for (int k = 0; k < V; k++) atomicAdd(&sh_db[v * V + k], bs[k]);
+    for (int k = 0; k < V; k++) mine[k] = bs[k];
   }
   if (da) {
     float t = block_sum(acc, red);
     if (threadIdx.x == 0) atomicAdd(da, t);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sh_db[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    float t = 0.f;
+    for (int q2 = 0; q2 < lanes; q2++) t += sh_db[(size_t)q2 * C + i];
+    atomicAdd(dbias + i, t);
+  }
 }
 
 // ======================================================================================================
@@ -461,13 +465,11 @@ __global__ void __launch_bounds__(256, 4) minmax_apply_kernel(const T* __restric
 template <typename T, int V>
 __global__ void __launch_bounds__(256, 3) minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                          const float* __restrict__ mn, const float* __restrict__ mx, int N, float* sums) {
-  extern __shared__ float sh_red[];              // [4][C] block-level partial sums
+  extern __shared__ float sh_red[];              // [lanes][4][C] per-thread partial sums, added per column below
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) sh_red[i] = 0.f;
-  __syncthreads();
   int r0 = blockIdx.x * rows_per_block, r1 = rl < lanes ? min(r0 + rows_per_block, HW) : 0;
   float lo[V], hi[V], s0[V], s1[V], c0[V], c1[V];
 #pragma unroll
@@ -498,19 +500,16 @@ __global__ void __launch_bounds__(256, 3) minmax_bwd_reduce_kernel(const T* __re
     }
   }
   if (rl < lanes) {
+    float* mine = sh_red + (size_t)rl * 4 * C + v * V;
 #pragma unroll
-    for (int k = 0; k < V; k++) {
-      int c = v * V + k;
-      atomicAdd(&sh_red[c], s0[k]); atomicAdd(&sh_red[C + c], s1[k]);
-      if (c0[k] != 0.f) atomicAdd(&sh_red[2 * C + c], c0[k]);
-      if (c1[k] != 0.f) atomicAdd(&sh_red[3 * C + c], c1[k]);
-    }
+    for (int k = 0; k < V; k++) { mine[k] = s0[k]; mine[C + k] = s1[k]; mine[2 * C + k] = c0[k]; mine[3 * C + k] = c1[k]; }
   }
   __syncthreads();
   long long NC = (long long)N * C;
   for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+    float val = 0.f;
+    for (int q2 = 0; q2 < lanes; q2++) val += sh_red[(size_t)q2 * 4 * C + i];
     int q = i / C, c = i - q * C;
-    float val = sh_red[i];
     if (val != 0.f) atomicAdd(&sums[q * NC + (long long)n * C + c], val);
   }
 }
@@ -518,14 +517,10 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256, 3) minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                         const float* __restrict__ mn, const float* __restrict__ mx, int N,
                                         const float* __restrict__ sums, T* __restrict__ gpre, float* dbias) {
-  extern __shared__ float sh_db[];               // [C] block-level column sums of gpre (only when dbias != NULL)
+  extern __shared__ float sh_db[];               // [lanes][C] per-thread column sums of gpre (only when dbias != NULL)
   const int CV = C / V;
   const int lanes = blockDim.x / CV;
   const int v = threadIdx.x % CV, rl = threadIdx.x / CV;
-  if (dbias) {
-    for (int i = threadIdx.x; i < C; i += blockDim.x) sh_db[i] = 0.f;
-    __syncthreads();
-  }
   const bool on = rl < lanes;
   const int n = blockIdx.y;
   const long long NC = (long long)N * C;
@@ -558,13 +553,18 @@ __global__ void __launch_bounds__(256, 3) minmax_bwd_apply_kernel(const T* __res
     }
     stv<T, V>(gpre + base + (long long)r * C, o);
   }
-  if (dbias) {
+  if (dbias) {                                   // bias gradient of the convolution in front: column sums of the result
     if (on) {
+      float* mine = sh_db + (size_t)rl * C + v * V;
 #pragma unroll
-      for (int k = 0; k < V; k++) atomicAdd(&sh_db[v * V + k], bs[k]);
+      for (int k = 0; k < V; k++) mine[k] = bs[k];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dbias + i, sh_db[i]);
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      float t = 0.f;
+      for (int q2 = 0; q2 < lanes; q2++) t += sh_db[(size_t)q2 * C + i];
+      atomicAdd(dbias + i, t);
+    }
   }
 }
 
@@ -916,6 +916,18 @@ static RowRed rowred_plan(int C, int vec, long long rows, long long other_blocks
   return p;
 }
 
+
+// ---- terms of the three-way bf16 split of an fp32 tensor (the six-product mode of the convolutions):
+// x = x1 + x2 + x3 + O(2^-24 x) with x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2)
+__global__ void split_term_kernel(const float* __restrict__ x, long long n, int level, __nv_bfloat16* __restrict__ out_bf16,
+                                  float* __restrict__ out_f32) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float r = x[i];
+    for (int l = 0; l < level; l++) r -= __bfloat162float(__float2bfloat16_rn(r));      // residual after `level` terms
+    if (out_bf16) out_bf16[i] = __float2bfloat16_rn(r);
+    if (out_f32) out_f32[i] = r;
+  }
+}
 }  // namespace fgc
 
 using namespace fgc;
@@ -927,9 +939,9 @@ int fgc_chan_stats(const void* x, int dtype, long long M, int C, double* acc, fl
   cudaStream_t s = as_stream(stream);
   cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, s);
   int vec = vec_width(x, C, dtype);
-  RowRed p = rowred_plan(C, vec, M, 3);      // a third of the usual block count: every block ends in 2*C fp64 atomics
+  RowRed p = rowred_plan(C, vec, M, 6);      // one wave of 4 blocks per SM: every block ends in 2*C fp64 atomics
   FGC_DISPATCH_TV(dtype, vec, T, V,
-                  (chan_stats_kernel<T, V><<<p.nblk, p.threads, 2 * C * sizeof(double), s>>>((const T*)x, M, C, p.rows_per_block, acc)));
+                  (chan_stats_kernel<T, V><<<p.nblk, p.threads, (size_t)p.lanes * 2 * C * sizeof(float), s>>>((const T*)x, M, C, p.rows_per_block, acc)));
   chan_stats_finalize<<<cdiv(C, 128), 128, 0, s>>>(acc, M, C, stats);
   count_launch(2);
   FGC_LAUNCH_CHECK("chan_stats");
@@ -965,7 +977,7 @@ int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int
   RowRed p = rowred_plan(C, rvec, HW, N);
   long long n = (long long)N * HW * C;
   FGC_DISPATCH_TV(dtype, rvec, T, V, {
-    cbn_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 2 * C * sizeof(float), s>>>((const T*)gy, (const T*)x, HW, C,
+    cbn_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, (size_t)p.lanes * 2 * C * sizeof(float), s>>>((const T*)gy, (const T*)x, HW, C,
                                                                                           p.rows_per_block, stats, scale, offset,
                                                                                           labels, act, N, sums);
   });
@@ -973,7 +985,7 @@ int fgc_cbn_act_bwd(const void* gy, const void* x, int dtype, int N, int HW, int
   (void)n;
   RowRed pa = rowred_plan(C, vec, HW, N);
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    cbn_bwd_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, dbias ? C * sizeof(float) : 0, s>>>(
+    cbn_bwd_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, dbias ? (size_t)pa.lanes * C * sizeof(float) : 0, s>>>(
         (const T*)gy, (const T*)x, HW, C, pa.rows_per_block, stats, scale, offset, labels, act, m12, (T*)gx, dbias);
   });
   count_launch(3);
@@ -1013,7 +1025,7 @@ int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, int C, 
     const long long M = n / C;
     RowRed p = rowred_plan(C, vec, M, 1);
     FGC_DISPATCH_TV(dtype, vec, T, V, {
-      prelu_bwd_rows_kernel<T, V><<<p.nblk, p.threads, C * sizeof(float), s>>>((const T*)gy, (const T*)x, M, C, p.rows_per_block, a, da,
+      prelu_bwd_rows_kernel<T, V><<<p.nblk, p.threads, (size_t)p.lanes * C * sizeof(float), s>>>((const T*)gy, (const T*)x, M, C, p.rows_per_block, a, da,
                                                                              (T*)gx, dbias);
     });
     count_launch();
@@ -1064,13 +1076,13 @@ int fgc_minmax_bwd(const void* ggate, const void* x, int dtype, int N, int HW, i
   RowRed p = rowred_plan(C, rvec, HW, N);
   long long n = (long long)N * HW * C;
   FGC_DISPATCH_TV(dtype, rvec, T, V, {
-    minmax_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, 4 * C * sizeof(float), s>>>((const T*)ggate, (const T*)x, HW, C,
+    minmax_bwd_reduce_kernel<T, V><<<dim3(p.nblk, N), p.threads, (size_t)p.lanes * 4 * C * sizeof(float), s>>>((const T*)ggate, (const T*)x, HW, C,
                                                                                              p.rows_per_block, mn, mx, N, scratch);
   });
   (void)n;
   RowRed pa = rowred_plan(C, vec, HW, N);
   FGC_DISPATCH_TV(dtype, vec, T, V, {
-    minmax_bwd_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, dbias ? C * sizeof(float) : 0, s>>>(
+    minmax_bwd_apply_kernel<T, V><<<dim3(pa.nblk, N), pa.threads, dbias ? (size_t)pa.lanes * C * sizeof(float) : 0, s>>>(
         (const T*)ggate, (const T*)x, HW, C, pa.rows_per_block, mn, mx, N, scratch, (T*)gpre, dbias);
   });
   count_launch(2);
@@ -1251,6 +1263,14 @@ int fgc_cast(const void* x, int x_dtype, void* y, int y_dtype, long long n, fgc_
   FGC_DISPATCH_2(x_dtype, y_dtype, TI, TO, (cast_kernel<TI, TO><<<ew_grid(n, 256), 256, 0, s>>>((const TI*)x, (TO*)y, n)));
   count_launch();
   FGC_LAUNCH_CHECK("cast");
+  return FGC_OK;
+}
+
+int fgc_split_term(const float* x, long long n, int level, void* out_bf16, float* out_f32, fgc_stream stream) {
+  FGC_REQUIRE(x && n > 0 && level >= 0 && level <= 2 && (out_bf16 || out_f32), "split_term: bad arguments");
+  split_term_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, n, level, (__nv_bfloat16*)out_bf16, out_f32);
+  count_launch();
+  FGC_LAUNCH_CHECK("split_term");
   return FGC_OK;
 }
 

@@ -28,7 +28,16 @@ def _same_pad(size, k, stride):
 class CudaOps(OpsBase):
     supports_cuda_graphs = True     # nothing allocates or synchronises inside the library; TrainSession replays graphs on it
 
-    def __init__(self, device="cuda:0", act_dtype=torch.float32):
+    def __init__(self, device="cuda:0", act_dtype=torch.float32, conv_terms=2):
+        """act_dtype float32: fp32 storage, tensor-core products in the split mode -- conv_terms = 2: bf16x3 (x = x1 + x2,
+        three products per K step: the parity mode of the MRU / Pix2Pix networks), conv_terms = 3: six products
+        (x = x1 + x2 + x3; forward convolutions without an epilogue activation -- every convolution of the Residual and
+        background generators -- get the three missing products x2 w2 + x1 w3 + x3 w1 as accumulating bf16 passes: ~110
+        batch-normalised layers amplify the bf16x3 residue 2^-16 to 4e-3 .. 1e-2 on the picture).
+        act_dtype bfloat16: bf16 storage, single-pass bf16 products (training throughput mode)."""
+        if conv_terms not in (2, 3):
+            raise ValueError("conv_terms must be 2 (bf16x3) or 3 (six products)")
+        self.conv_terms = conv_terms
         if not torch.cuda.is_available():
             raise RuntimeError("CudaOps needs a CUDA device (sm_100a); there is no CPU path in this package")
         if act_dtype not in _DT:
@@ -98,7 +107,29 @@ class CudaOps(OpsBase):
         check(self.lib.fgc_conv2d_fwd(arr, len(srcs), dt, N, H, W, self._f32(w), k, cin, cout,
                                       None if b is None else self._f32(b.reshape(-1)), stride, pt, pl, OH, OW, act,
                                       self._p(y), self._dt(y), self._p(ws), self._s()), "conv2d_fwd")
+        if self.conv_terms == 3 and srcs[0][0].dtype == torch.float32 and act == ACT_NONE and y.dtype == torch.float32:
+            self._six_product_passes(srcs, w, k, cin, cout, stride, pt, pl, OH, OW, y)
         return y
+
+    def _split(self, x, level, bf16):
+        out = self._empty(x.shape, torch.bfloat16 if bf16 else torch.float32)
+        check(self.lib.fgc_split_term(self._f32(x), x.numel(), level, self._p(out) if bf16 else None, None if bf16 else self._p(out),
+                                      self._s()), "split_term")
+        return out
+
+    def _six_product_passes(self, srcs, w, k, cin, cout, stride, pt, pl, OH, OW, y):
+        """y (= x1 w1 + x1 w2 + x2 w1 from the bf16x3 pass) += x2 w2 + x1 w3 + x3 w1: three single-pass bf16 convolutions
+        that accumulate into the fp32 result.  A single-pass convolution rounds its fp32 filter argument to bf16, so handing
+        it the filter's residual after one / two terms multiplies by w2 / w3."""
+        xs = [e[0] for e in srcs]
+        ups = [e[1] for e in srcs]
+        for lx, lw in ((1, 1), (0, 2), (2, 0)):
+            terms = [(self._split(x, lx, True), u) for x, u in zip(xs, ups)]
+            wt = w if lw == 0 else self._split(w, lw, False)
+            arr, N, H, W, dt = self._srcs(terms)
+            ws = self._ws([t[0].shape[3] for t in terms], k, cout, dt)
+            check(self.lib.fgc_conv2d_fwd_acc(arr, len(terms), dt, N, H, W, self._f32(wt), k, cin, cout, None, stride, pt, pl, OH, OW,
+                                              ACT_NONE, 1, self._p(y), self._dt(y), self._p(ws), self._s()), "conv2d_fwd_acc")
 
     def small_patch(self, x, k, ups=False, mirror=False):
         """bf16 training mode only: flattened (tap, channel) copy of a narrow source for the TMA-fed conv kernels."""

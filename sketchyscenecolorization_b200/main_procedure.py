@@ -33,7 +33,7 @@ def _build_model(precision, img_dim, vocab_size, lstm_hybrid, device=None, with_
     from .cuda_ops import CudaOps
     from .trainer import FgColorModel
     dev = device or "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
-    ops = CudaOps(dev, _dtype(precision))
+    ops = CudaOps(dev, _dtype(precision), conv_terms=int(getattr(Config, 'conv_terms', 2)))
     return FgColorModel(ops, dev, H=img_dim[0], W=img_dim[1], vocab_size=vocab_size, lstm_hybrid=lstm_hybrid,
                         with_discriminator=with_discriminator, block_type=block_type)
 

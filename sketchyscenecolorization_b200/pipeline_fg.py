@@ -248,8 +248,11 @@ def build_instance_colorization(data_base_dir, image_id, input_text, inst_indice
         y1, x1, y2, x2 = bbox
         labels = torch.tensor([SKE_TO_FG_CLASS[class_id46]], dtype=torch.int32, device=dev)
         noise = torch.randn(1, 256, generator=gen).to(dev)
-        sk = torch.from_numpy(sketch).to(dev)
-        out = model.generate(sk.to(noise.dtype), ids, labels, noise)            # [1,3,192,192], batch 1 (see module docstring)
+        sk = torch.from_numpy(np.ascontiguousarray(sketch)).to(dev)      # the prepared sketch is a transposed view
+        # batch 1 per instance (see module docstring); on the CUDA operator set every instance after the second replays one
+        # captured graph instead of ~830 launches from Python
+        gen_fn = getattr(model, 'generate_replay', None) if getattr(model.ops, 'supports_cuda_graphs', False) else None
+        out = (gen_fn or model.generate)(sk.to(noise.dtype).contiguous(), ids, labels, noise)        # [1,3,192,192]
         color = instance_result_postprocessing(out.detach().float().cpu().numpy(), bbox, 'NCHW', class_id46)
         box = new_result_image[y1: y2, x1: x2]
         sel = inner_mask[y1: y2, x1: x2] == inst_idx + 1

@@ -341,6 +341,37 @@ def test_text_ops(env):
     close(cu.atanh_relu_bwd(gy.float(), h.float()), ref.atanh_relu_bwd(gy, h), 1e-4, "atanh_relu bwd")
 
 
+@pytest.mark.parametrize("case", [(2, 24, 24, 128, 3, 128), (2, 16, 16, 512, 3, 64), (64, 1, 1, 1024, 1, 512)], ids=str)
+def test_six_product_convolution(env, case):
+    """CudaOps(conv_terms=3): x = x1 + x2 + x3, w = w1 + w2 + w3 in bf16 terms, the six products of order <= 2^-16 kept
+    (one bf16x3 pass + three accumulating bf16 passes, fgc_conv2d_fwd_acc / fgc_split_term) -- against fp64, next to bf16x3
+    and the fp32 CUDA-core convolution.  What it shows (printed): the operand residue of bf16x3 (~2^-17 of the largest
+    entry) disappears; what remains is the accumulation in fp32 -- the floor any fp32 implementation has."""
+    from sketchyscenecolorization_b200.cuda_ops import CudaOps
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    N, H, W, cin, k, cout = case
+    x, w = rnd((N, H, W, cin), 1, dev), rnd((k, k, cin, cout), 2, dev, 1.0 / math.sqrt(k * k * cin))
+    b = rnd((cout,), 3, dev, 0.3)
+    want = ref.conv_fwd([(x, False)], w, b)
+    xf, wf, bf = x.float().contiguous(), w.float().contiguous(), b.float().contiguous()
+    want32 = ref.conv_fwd([(xf.double(), False)], wf.double(), bf.double())        # fp64 arithmetic on the fp32-rounded operands
+    cu6 = CudaOps(dev, torch.float32, conv_terms=3)
+    errs = {}
+    _set_impl(cu, 1)
+    try:
+        errs["fp32 CUDA cores"] = cu.conv_fwd([(xf, False)], wf, bf)
+    finally:
+        _set_impl(cu, 0)
+    errs["bf16x3"] = cu.conv_fwd([(xf, False)], wf, bf)
+    errs["six products"] = cu6.conv_fwd([(xf, False)], wf, bf)
+    torch.cuda.synchronize()
+    scale = want32.abs().max().item()
+    e = {kk: (v.double() - want32).abs().max().item() / scale for kk, v in errs.items()}
+    print("conv %s, max-abs error / largest entry vs fp64 on the same fp32 operands: %s" % (case, {kk: "%.2e" % v for kk, v in e.items()}))
+    assert e["six products"] <= 1e-5 and e["six products"] <= 1.05 * e["bf16x3"] and e["bf16x3"] <= 1e-4
+    close(errs["six products"], want, 1e-5, "six-product conv vs fp64 of the fp64 operands")
+
+
 @pytest.mark.parametrize("shape", [(15, 64, 512), (5, 3, 128), (4, 70, 64), (2, 1, 16), (15, 130, 512)], ids=str)
 def test_word_lstm_sequence_kernels(env, shape):
     """fgc_lstm_seq_fwd / _bwd (the word LSTM's recurrence and its BPTT, one persistent launch each, grid barrier per step)
