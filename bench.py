@@ -205,6 +205,16 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------
 # product arm
 # ----------------------------------------------------------------------------------------------------------
+def _profile_json(name):
+    """A committed ncu-derived summary under profiles/ (written by scripts/ncu_traffic.py / scripts/tensor_pipe_summary.py from
+    captures of THIS kernel set); None when absent -- nothing is pasted into this file."""
+    p = os.path.join(ROOT, "profiles", name)
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def dominant_kernel_roofline(ops, torch, pk, reps=5):
     """The dominant kernel of the step: the 128->128 3x3 conv at 192x192 (D unit-1 Conv_2 / G decoder unit 8), bs 64,
     single-pass bf16.  Algorithmic FLOPs per launch = 2 * 64 * 192^2 * 9 * 128 * 128."""
@@ -223,12 +233,14 @@ def dominant_kernel_roofline(ops, torch, pk, reps=5):
     torch.cuda.synchronize()
     ms = sorted(e0.elapsed_time(e1) for e0, e1 in evs)[len(evs) // 2]
     ach = flop / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "conv_halo_kernel<128,2,2> 3x3 128->128 @192x192 bs64 (incl. weight pack)",
+    tr = _profile_json("dominant_kernel_traffic.json") or {}
+    return {"bound": "tensor", "kernel": tr.get("kernel", "conv_halo_kernel<128,2,2,swap> 3x3 128->128 @192x192 bs64") + " (incl. weight pack)",
             "achieved": round(ach, 2), "peak": pk["burst"], "unit": "TFLOP/s", "frac": round(ach / pk["burst"], 4),
             "peak_source": pk["src"] + " bf16 burst", "ms_per_launch": round(ms, 4), "flop_per_launch": flop,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, `ncu --set full` (profiles/r1g_ncu_conv_summary.txt):
-            # 604.5 MB + 553.1 MB -- the input once, the output once; L2 -> SM operand traffic of the same launch: 4.65 GB
-            "traffic": 1157.7e6, "traffic_unit": "bytes/launch (DRAM)", "l2_to_sm_bytes_per_launch": 4.65e9}
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+            "traffic": tr.get("dram_bytes_per_launch"), "traffic_unit": "bytes/launch (DRAM)",
+            "traffic_source": tr.get("source"), "l2_to_sm_bytes_per_launch": tr.get("l2_to_sm_bytes_per_launch"),
+            "tensor_pipe_pct": tr.get("tensor_pipe_pct")}
 
 
 def run_product(args):
@@ -384,6 +396,8 @@ def run_product(args):
                            "step_conv_frac_of_sustained_peak": round(step_tflops / pk["sustained"], 4) if step_tflops else None,
                            "host_enqueue_ms_per_step": round(host_ms, 2),
                            "cuda_graphs": graphs,
+                           "g_conv_tensor_pipe_pct": (_profile_json("g_conv_tensor_pipe.json") or {}).get("g_conv_tensor_pipe_pct"),
+                           "g_conv_tensor_pipe_source": (_profile_json("g_conv_tensor_pipe.json") or {}).get("source"),
                            "loss_d": ld_v, "loss_g": lg_v},
                 "clocks": clocks,
                 "e2e": {"value": ips_e2e, "unit": "images/s",

@@ -804,14 +804,27 @@ struct HaloArgs {
 // epilogue warps: one group of 4 per sub-tile, at most 2 groups (MT = 4: each group drains two sub-tiles in turn)
 __host__ __device__ constexpr int halo_epi_warps(int mt) { return mt > 2 ? 8 : 4 * mt; }
 
-template <int BN, int MT, int NACC>
+// SWAP (BN = 128, MT = 2): the operand roles are exchanged -- the 128 output channels of the weight slab are the M side of
+// the MMA and the tile's 256 pixels its N side: ONE M128 x N256 x K16 instruction where the plain form issues two
+// M128 x N128 ones.  Same boxes, same weight slabs, same flops, but per K step the tensor core fetches 4 KB of weights +
+// 8 KB of pixels from shared memory instead of 2 x (4 + 4) KB -- the operand traffic per flop of the 256-wide layers, which
+// run at 1.24 PFLOP/s where the 128-wide ones reach 0.92 (measured across all kernels of this file: an MMA costs about its
+// operand fetch plus its math time, so fewer operand bytes per flop is what raises the tensor pipe's share).  The
+// accumulator then holds one output CHANNEL per TMEM lane and one pixel per column; a thread owns a channel, which is the
+// wrong way round for NHWC stores (2 bytes per lane: measured 0.86 ms against 0.75 ms).  So the epilogue transposes through
+// a per-warp shared-memory staging tile: 32 pixels x 32 channels of bf16 written channel-major by column, read back
+// pixel-major, and stored as 16 bytes per lane exactly like the plain epilogue.
+constexpr int kSwapStageRow = 80;                      // bytes per staged pixel row (64 + 16: conflict-free 16-byte reads)
+constexpr int kSwapStageBytes = 32 * kSwapStageRow;    // per epilogue warp
+template <int BN, int MT, int NACC, bool SWAP = false>
 __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_kernel(const __grid_constant__ HaloArgs a) {
   static_assert(NACC * MT * BN <= 512, "accumulators exceed TMEM");
+  static_assert(!SWAP || (BN == 128 && MT == 2), "operand exchange: 128 channels x 256 pixels");
   constexpr int EW = halo_epi_warps(MT);
   constexpr int B_BYTES = BN * 128;
   constexpr int ACC_COLS = MT * BN;
   constexpr int TMEM_COLS = NACC * ACC_COLS <= 32 ? 32 : (NACC * ACC_COLS <= 64 ? 64 : (NACC * ACC_COLS <= 128 ? 128 : (NACC * ACC_COLS <= 256 ? 256 : 512)));
-  constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
+  constexpr uint32_t IDESC = SWAP ? make_idesc(BN, 128 * MT, 0, 0) : make_idesc(128, BN, 0, 0);
   constexpr int MMA_WARP = 4, ALOAD_WARP = 5, BLOAD_WARP = 6, EPI_WARP0 = 8;
   constexpr int TH = 16 * MT;
 
@@ -820,7 +833,8 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
   const int a_slots = a.a_slots, b_slots = a.b_slots;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)a_slots * a.a_slot_bytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + (size_t)b_slots * B_BYTES);
+  uint8_t* sStage = sB + (size_t)b_slots * B_BYTES;                 // SWAP: one staging tile per epilogue warp
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sStage + (SWAP ? EW * kSwapStageBytes : 0));
   uint64_t* a_empty = a_full + a_slots;
   uint64_t* b_full = a_empty + a_slots;
   uint64_t* b_empty = b_full + b_slots;
@@ -915,15 +929,26 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
             const uint64_t db = desc_kmajor(smem_u32(sB + (size_t)bslot * B_BYTES), 1024);
             // box row of output row r under filter row kh = j:  r + j (forward) or r + k-1-j (mirrored taps of dgrad)
             const int jrow = big ? (sign > 0 ? j : k - 1 - j) : 0;
-#pragma unroll
-            for (int tt = 0; tt < MT; tt++) {
-              const uint32_t aoff = boxed ? (uint32_t)(16 * tt + jrow) * 1024u : (uint32_t)tt * 16384u;
-              const uint64_t da = desc_kmajor(sa + aoff, 1024);
-              const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS + tt * BN);
+            if constexpr (SWAP) {
+              // the pixel rows of both sub-tiles are contiguous atoms in either kind of A slot: one N = 256 operand
+              const uint64_t da = desc_kmajor(sa + (boxed ? (uint32_t)jrow * 1024u : 0u), 1024);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
 #pragma unroll
               for (int kk = 0; kk < 4; kk++) {
                 const uint32_t acc = (it > 0 || j > 0 || kk > 0) ? 1u : 0u;
-                umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, acc);
+                umma_bf16(d_tmem, db + 2 * kk, da + 2 * kk, IDESC, acc);
+              }
+            } else {
+#pragma unroll
+              for (int tt = 0; tt < MT; tt++) {
+                const uint32_t aoff = boxed ? (uint32_t)(16 * tt + jrow) * 1024u : (uint32_t)tt * 16384u;
+                const uint64_t da = desc_kmajor(sa + aoff, 1024);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS + tt * BN);
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                  const uint32_t acc = (it > 0 || j > 0 || kk > 0) ? 1u : 0u;
+                  umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, acc);
+                }
               }
             }
             umma_commit(smem_u32(&b_empty[bslot]));
@@ -1018,6 +1043,84 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
       const int ty = rr / a.tiles_w, tx = rr - ty * a.tiles_w;
       mbar_wait(smem_u32(&acc_full[buf]), (ti / NACC) & 1);
       tc_fence_after();
+      if constexpr (SWAP) {
+        // TMEM lane l = output channel n0 + l, column p = pixel (p >> 3, p & 7) of the 32 x 8 tile; warp group `grp` drains
+        // the columns of sub-tile `grp`, 32 pixels (4 tile rows) at a time: bias + activation per channel, bf16 into the
+        // warp's staging tile [pixel][channel], then lane = pixel reads its 32 channels back and stores 4 x 16 bytes.
+        const int ch = n0 + l;
+        const float bias_c = (a.bias && ch < a.Nout) ? __ldg(a.bias + ch) : 0.f;
+        uint8_t* stage = sStage + (size_t)ei * kSwapStageBytes;
+        const int nb = n0 + quarter * 32;                  // first channel of this warp's 32
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * ACC_COLS + grp * 128 + c0), r);
+          if (c0 + 32 >= 128) {                          // last read of this accumulator set by this warp
+            tc_fence_before();
+            mbar_arrive(smem_u32(&acc_empty[buf]));
+          }
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < 32; q++) v[q] = __uint_as_float(r[q]) + bias_c;
+          switch (a.act) {
+            case FGC_ACT_LRELU:
+#pragma unroll
+              for (int q = 0; q < 32; q++) v[q] = v[q] > 0.f ? v[q] : 0.2f * v[q];
+              break;
+            case FGC_ACT_TANH:
+#pragma unroll
+              for (int q = 0; q < 32; q++) v[q] = tanhf(v[q]);
+              break;
+            case FGC_ACT_MIU:
+#pragma unroll
+              for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
+              break;
+            default: break;
+          }
+          if (a.pool2) {
+            // the 2x2 partners of a pixel are columns q^1 and q^8: registers of this thread
+#pragma unroll
+            for (int q = 0; q < 32; q++)
+              if (!(q & 1) && !(q & 8)) v[q] = (v[q] + v[q + 1]) + (v[q + 8] + v[q + 9]);
+          }
+          __syncwarp();                                  // the previous chunk's reads of the staging tile are done
+#pragma unroll
+          for (int q = 0; q < 32; q++)
+            *reinterpret_cast<__nv_bfloat16*>(stage + q * kSwapStageRow + lane * 2) = __float2bfloat16_rn(v[q]);
+          __syncwarp();
+          // lane = pixel of the chunk
+          const int oh = ty * TH + grp * 16 + (c0 >> 3) + (lane >> 3), ow = tx * 8 + (lane & 7);
+          const bool mvalid = oh < g.OH && ow < g.OW && (!a.pool2 || ((lane & 1) == 0 && (lane & 8) == 0));
+          if (!mvalid || nb >= a.Nout) continue;
+          const long long m = a.pool2 ? ((long long)n * (g.OH >> 1) + (oh >> 1)) * (g.OW >> 1) + (ow >> 1)
+                                      : ((long long)n * g.OH + oh) * g.OW + ow;
+          const int nrem = a.Nout - nb;
+          __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.Nout + nb;
+          const uint4* sp = reinterpret_cast<const uint4*>(stage + lane * kSwapStageRow);
+          if (a.vec_ok && nrem >= 32 && (a.Nout & 7) == 0) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; q4++) {
+              uint4 o = sp[q4];
+              if (a.accumulate) {
+                const uint4 p = *reinterpret_cast<const uint4*>(yp + q4 * 8);
+                const __nv_bfloat162* pp = reinterpret_cast<const __nv_bfloat162*>(&p);
+                __nv_bfloat162* oo = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int e2 = 0; e2 < 4; e2++) {
+                  const float2 f = __bfloat1622float2(pp[e2]), w2 = __bfloat1622float2(oo[e2]);
+                  oo[e2] = __floats2bfloat162_rn(f.x + w2.x, f.y + w2.y);
+                }
+              }
+              *reinterpret_cast<uint4*>(yp + q4 * 8) = o;
+            }
+          } else {
+            const __nv_bfloat16* sv = reinterpret_cast<const __nv_bfloat16*>(sp);
+            for (int q = 0; q < 32 && q < nrem; q++)
+              yp[q] = a.accumulate ? __float2bfloat16_rn(__bfloat162float(yp[q]) + __bfloat162float(sv[q])) : sv[q];
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int tile = grp; tile < MT; tile += EW / 4) {
         const int oh = ty * TH + 16 * tile + (l >> 3), ow = tx * 8 + (l & 7);
@@ -2209,10 +2312,11 @@ static bool make_tmap_rows64(CUtensorMap* out, const void* ptr, long long rows, 
 }
 
 // ---- halo-reuse forward / dgrad launcher ----
-template <int BN, int MT, int NACC>
+template <int BN, int MT, int NACC, bool SWAP = false>
 static int launch_halo(HaloArgs& h, cudaStream_t s) {
   constexpr int B_BYTES = BN * 128;
-  const int budget = 216 * 1024;
+  constexpr int STAGE = SWAP ? halo_epi_warps(MT) * kSwapStageBytes : 0;
+  const int budget = 216 * 1024 - STAGE;
   h.box_rows = 16 * MT + h.g.k - 1;
   h.a_slot_bytes = h.box_rows * 1024;
   int a_slots = 3;
@@ -2239,15 +2343,15 @@ static int launch_halo(HaloArgs& h, cudaStream_t s) {
   }
   { static int pf = -1; if (pf < 0) { const char* e = getenv("FGC_HALO_PF"); pf = e ? atoi(e) : 1; } h.l2_prefetch = pf; }
   h.dbg = 0;
-  size_t smem = (size_t)a_slots * h.a_slot_bytes + (size_t)b_slots * B_BYTES + (2 * a_slots + 2 * b_slots + 2 * NACC) * 8 + 16 + 1024;
+  size_t smem = (size_t)a_slots * h.a_slot_bytes + (size_t)b_slots * B_BYTES + STAGE + (2 * a_slots + 2 * b_slots + 2 * NACC) * 8 + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(conv_halo_kernel<BN, MT, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_halo_kernel<BN, MT, NACC, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   long long ntiles = (long long)h.tiles_m * (h.Npad / BN);
   int grid = ntiles < num_sms() ? (int)ntiles : num_sms();
-  conv_halo_kernel<BN, MT, NACC><<<grid, 32 * (8 + halo_epi_warps(MT)), smem, s>>>(h);
+  conv_halo_kernel<BN, MT, NACC, SWAP><<<grid, 32 * (8 + halo_epi_warps(MT)), smem, s>>>(h);
   g_conv_counts[0]++;
   count_launch();
   return check_launch("conv_halo");
@@ -2400,12 +2504,15 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
     case 256: return mt == 2 ? launch_halo<256, 2, 1>(h, s) : launch_halo<256, 1, 2>(h, s);
     default: {
       // 128 output channels, 32 x 8 pixel tiles: the CTA-pair kernel (FGC_HALO2=0 keeps the single-CTA form)
-      static int halo2 = -1;
-      if (halo2 < 0) { const char* e = getenv("FGC_HALO2"); halo2 = e ? atoi(e) : 1; }
+      static int halo2 = -1, swap = -1;
+      if (halo2 < 0) { const char* e = getenv("FGC_HALO2"); halo2 = e ? atoi(e) : 0; }
+      if (swap < 0) { const char* e = getenv("FGC_HALO_SWAP"); swap = e ? atoi(e) : 1; }
       if (mt == 2 && halo2 && !any_gather) {
         int r = launch_halo2<2>(h, s);
         if (r >= 0) return r;
       }
+      // bf16 output: exchanged operand roles (one N = 256 MMA per K step) with the transposing epilogue
+      if (mt == 2 && swap && h.y_dtype == FGC_BF16) return launch_halo<128, 2, 2, true>(h, s);
       FGC_H(128, 2, 1);
     }
   }

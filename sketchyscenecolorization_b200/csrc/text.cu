@@ -136,12 +136,18 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gc, const float* 
 // so it stays in a register and one barrier per step suffices).
 // ------------------------------------------------------------------------------------------------------
 constexpr int LS_UNITS = 4, LS_THREADS = 256, LS_ROWS = 64, LS_MAXCH = 4;
+constexpr int LS_GC = 512;              // backward: columns of the gate gradients staged per pass
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// 16-byte global -> shared copies that bypass registers (LDGSTS, L2 only): a thread keeps all its copies of a stage in flight
+__device__ __forceinline__ void ls_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ls_cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -172,11 +178,11 @@ lstm_seq_fwd_kernel(const float* __restrict__ gx, const float* __restrict__ kh, 
     for (int n0 = 0; n0 < N; n0 += LS_ROWS) {
       const int nn = min(LS_ROWS, N - n0);
       __syncthreads();
-      for (int i = tid; i < nn * D4; i += LS_THREADS) {
+      for (int i = tid; i < nn * D4; i += LS_THREADS) {      // all of a thread's copies in flight at once (one L2 round trip)
         const int r = i / D4, c4 = i - r * D4;
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(hprev + (size_t)(n0 + r) * D) + c4);
-        *reinterpret_cast<float4*>(Hs + (size_t)r * HS + c4 * 4) = v;
+        ls_cp_async16(Hs + (size_t)r * HS + c4 * 4, hprev + (size_t)(n0 + r) * D + c4 * 4);
       }
+      ls_cp_async_wait_all();
       __syncthreads();
       if (nl < nn) {
         const int n = n0 + nl;
@@ -223,6 +229,7 @@ lstm_seq_bwd_kernel(const float* __restrict__ g_hext, const float* __restrict__ 
                     unsigned int* bar) {
   extern __shared__ __align__(16) float ls_smem[];
   float* WT = ls_smem;                 // [unit][4D + 4]: rows d0..d0+3 of the recurrent weights (row pitch skewed by 4 banks)
+  float* GS = ls_smem + (size_t)LS_UNITS * (4 * D + 4);      // [LS_ROWS][LS_GC + 4]: stage of the gate gradients
   const int tid = threadIdx.x, u = tid & 3, nl = tid >> 2;
   const int d0 = blockIdx.x * LS_UNITS, d = d0 + u;
   const int C4 = 4 * D, WTS = C4 + 4;
@@ -263,20 +270,35 @@ lstm_seq_bwd_kernel(const float* __restrict__ g_hext, const float* __restrict__ 
     epoch++;
     grid_barrier(bar, epoch * gridDim.x);
     const float4* wt = reinterpret_cast<const float4*>(WT + (size_t)u * WTS);
+    // g_h(t-1)[n, k] = sum_col g_pre[n, col] * K[D + k, col]: the 4D gate gradients of the chunk's rows stream through a
+    // shared-memory stage in column blocks of LS_GC (coalesced cp.async, all in flight), four k per row from the stage
 #pragma unroll
     for (int ci = 0; ci < LS_MAXCH; ci++) {
-      const int n = ci * LS_ROWS + nl;
-      if (ci < nch && n < N) {
-        const float4* gp = reinterpret_cast<const float4*>(g_pre_all + ((size_t)t * N + n) * C4);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < D; c++) {           // 4D columns, four per iteration
-          const float4 gv = __ldcg(gp + c);
-          const float4 wv = wt[c];
-          s0 = fmaf(gv.x, wv.x, s0); s1 = fmaf(gv.y, wv.y, s1); s2 = fmaf(gv.z, wv.z, s2); s3 = fmaf(gv.w, wv.w, s3);
+      if (ci >= nch) continue;
+      const int n0 = ci * LS_ROWS, nn = min(LS_ROWS, N - n0);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int cb = 0; cb < C4; cb += LS_GC) {
+        const int gc4 = min(LS_GC, C4 - cb) >> 2;           // float4 columns of this pass (4D is a multiple of 16)
+        __syncthreads();
+        const float* gsrc = g_pre_all + ((size_t)t * N + n0) * C4 + cb;
+        for (int i = tid; i < nn * gc4; i += LS_THREADS) {
+          const int r = i / gc4, c4 = i - r * gc4;
+          ls_cp_async16(GS + (size_t)r * (LS_GC + 4) + c4 * 4, gsrc + (size_t)r * C4 + c4 * 4);
         }
-        g_hrec[ci] = (s0 + s1) + (s2 + s3) + g_pass[ci];
+        ls_cp_async_wait_all();
+        __syncthreads();
+        if (nl < nn) {
+          const float4* gp = reinterpret_cast<const float4*>(GS + (size_t)nl * (LS_GC + 4));
+          const float4* wv4 = wt + (cb >> 2);
+#pragma unroll 8
+          for (int c = 0; c < gc4; c++) {
+            const float4 gv = gp[c];
+            const float4 wv = wv4[c];
+            s0 = fmaf(gv.x, wv.x, s0); s1 = fmaf(gv.y, wv.y, s1); s2 = fmaf(gv.z, wv.z, s2); s3 = fmaf(gv.w, wv.w, s3);
+          }
+        }
       }
+      if (nl < nn) g_hrec[ci] = (s0 + s1) + (s2 + s3) + g_pass[ci];
     }
   }
 }
@@ -395,7 +417,9 @@ int fgc_lstm_seq_bwd(const float* g_hext, const float* pre_all, const float* c_a
                      int D, float* g_pre_all, unsigned int* barrier, fgc_stream stream) {
   int e = lstm_seq_check(T, N, D);
   if (e) return e;
-  const size_t smem = (size_t)LS_UNITS * (4 * D + 4) * sizeof(float);
+  const size_t smem = ((size_t)LS_UNITS * (4 * D + 4) + (size_t)LS_ROWS * (LS_GC + 4)) * sizeof(float);
+  static bool attr_b = false;
+  if (!attr_b) { cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_b = true; }
   cudaMemsetAsync(barrier, 0, sizeof(unsigned int), as_stream(stream));
   lstm_seq_bwd_kernel<<<D / LS_UNITS, LS_THREADS, smem, as_stream(stream)>>>(g_hext, pre_all, c_all, kh, ids, T, N, D, g_pre_all, barrier);
   count_launch();
