@@ -84,11 +84,19 @@ int fgc_conv2d_fwd(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, i
                    const float* w, int k, int Cin_total, int Cout, const float* bias,
                    int stride, int pad_t, int pad_l, int OH, int OW, int act,
                    void* y, int y_dtype, void* ws, fgc_stream stream);
-/* The same, adding into y (y += act(conv + bias)) when `accumulate` != 0: the extra passes of the six-product mode. */
+/* The same with flags in `accumulate`: bit 0 = add into y (y += act(conv + bias): the extra passes of the six-product mode);
+ * bit 1 = only the centre filter column of w is non-zero (see fgc_tapsum_w). */
 int fgc_conv2d_fwd_acc(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W,
                        const float* w, int k, int Cin_total, int Cout, const float* bias,
                        int stride, int pad_t, int pad_l, int OH, int OW, int act, int accumulate,
                        void* y, int y_dtype, void* ws, fgc_stream stream);
+/* Second half of a column-folded k x k convolution with few outputs (models_collection.py:372-374, the 7x7 64 -> 3 head):
+ * z [N,H,W,Cz] fp32 holds, in channel kw*Cout + co, the k x 1 VERTICAL convolution with filter column kw (computed by
+ * fgc_conv2d_fwd_acc with flag 2 on a filter whose other columns are zero); y[n,h,w,co] = act(bias[co] +
+ * sum_kw z[n,h,w + kw - (k-1)/2, kw*Cout + co]) with zero padding in w.  On the tensor path a 3-output 7x7 layer is 49
+ * N = 16 instructions per K step; folded it is 7 N = 32 ones. */
+int fgc_tapsum_w(const float* z, int N, int H, int W, int k, int Cout, int Cz, const float* bias, int act, void* y, int y_dtype,
+                 fgc_stream stream);
 /* Term `level` (0, 1, 2) of the three-way bf16 split of an fp32 tensor: r = x minus its first `level` bf16 terms;
  * out_bf16 (optional) = bf16(r), out_f32 (optional) = r.  With bf16x3 (fp32 sources, the parity mode of mru.conv2d) these
  * give the six-product mode: x1w1 + x1w2 + x2w1 (one bf16x3 pass) + x2w2 + x1w3 + x3w1 (three accumulating bf16 passes). */

@@ -81,6 +81,7 @@ SIGNATURES = {
     "fgc_conv2d_fwd": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "fgc_conv2d_fwd_acc": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "fgc_split_term": [_P, _LL, _I, _P, _P, _P],
+    "fgc_tapsum_w": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P],
     "fgc_conv2d_dgrad": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
     "fgc_conv2d_wgrad": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P],
     "fgc_chan_stats": [_P, _I, _LL, _I, _P, _P, _P],

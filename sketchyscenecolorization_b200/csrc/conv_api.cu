@@ -20,6 +20,7 @@ int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, in
 size_t conv_ws_bytes(const ConvGeom& g, int nout, int x3);
 extern int g_halo_mode, g_small_mode;
 extern long long g_conv_counts[6];
+extern int g_center_col;
 extern long long* g_trace;
 extern int g_trace_cap;
 
@@ -108,13 +109,18 @@ int fgc_conv2d_fwd_acc(const fgc_src* srcs, int nsrc, int src_dtype, int N, int 
   FGC_REQUIRE(cin == Cin_total, "conv_fwd: sources have %d channels, weights expect %d", cin, Cin_total);
   cudaStream_t s = as_stream(stream);
   if (conv_impl() == 1) {
-    FGC_REQUIRE(!accumulate, "conv_fwd: the CUDA-core checker does not accumulate");
+    FGC_REQUIRE(!(accumulate & 1), "conv_fwd: the CUDA-core checker does not accumulate");
     e = conv_fwd_simple(g, src_dtype, w, Cin_total, Cout, bias, act, y, y_dtype, s);
     if (e) return e;
     FGC_LAUNCH_CHECK("conv_fwd_simple");
     return FGC_OK;
   }
-  return conv_igemm_run(g, src_dtype, w, (long long)Cin_total * Cout, Cout, 1, 0, Cout, bias, act, accumulate, y, y_dtype, ws, s);
+  // accumulate: bit 0 = add into y; bit 1 = only the centre filter COLUMN of w is non-zero (the column-folded 7x7 head,
+  // fgc_tapsum_w): kernels that walk the filter by columns skip the others, the rest multiply the zeros
+  g_center_col = (accumulate & 2) ? 1 : 0;
+  e = conv_igemm_run(g, src_dtype, w, (long long)Cin_total * Cout, Cout, 1, 0, Cout, bias, act, accumulate & 1, y, y_dtype, ws, s);
+  g_center_col = 0;
+  return e;
 }
 
 int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const float* w, int k, int Cin_total,

@@ -2182,6 +2182,7 @@ static int launch_igemm_bf16(IgemmArgs& a, int bn, int mt, cudaStream_t s) {
 long long* g_trace = nullptr;
 int g_trace_cap = 0;
 int g_halo_mode = -1;      // fgc_set_conv_flags / env FGC_HALO
+int g_center_col = 0;      // set around one forward call (fgc_conv2d_fwd_acc flag 2): only the centre filter column carries weights
 
 static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s);
 static bool conv_halo_eligible(const IgemmArgs& ia, int bn);
@@ -2476,6 +2477,7 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
       if (ncb > 255) return -1;
       for (int cg = 0; cg < ncb; cg++)
         for (int kw = 0; kw < g.k; kw++) {
+          if (g_center_col && kw != g.pad_l) continue;       // the other filter columns are zero by contract: skip their boxes
           if (ni >= kMaxItems) return -1;
           h.items[ni++] = (uint16_t)(0x8000u | (i << 12) | (kw << 8) | cg);
         }

@@ -928,6 +928,29 @@ __global__ void split_term_kernel(const float* __restrict__ x, long long n, int 
     if (out_f32) out_f32[i] = r;
   }
 }
+
+// ---- second half of a column-folded k x k convolution with few outputs (the 7x7, 64 -> 3 head): z[n,h,w, kw*Cout + co] holds
+// the k x 1 (vertical) convolution with filter column kw; y[n,h,w,co] = act(bias[co] + sum_kw z[n,h,w + kw - pad, kw*Cout + co])
+template <typename TO>
+__global__ void tapsum_w_kernel(const float* __restrict__ z, long long npix, int W, int k, int Cout, int Cz, const float* __restrict__ bias,
+                                int act, TO* __restrict__ y) {
+  const int pad = (k - 1) / 2;
+  const long long total = npix * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const long long p = i / Cout;
+    const int w = (int)(p % W);
+    float acc = bias ? bias[co] : 0.f;
+    for (int kw = 0; kw < k; kw++) {
+      const int ww = w + kw - pad;
+      if (ww >= 0 && ww < W) acc += __ldg(z + (p + kw - pad) * Cz + kw * Cout + co);
+    }
+    if (act == FGC_ACT_TANH) acc = tanhf(acc);
+    else if (act == FGC_ACT_LRELU) acc = acc > 0.f ? acc : 0.2f * acc;
+    else if (act == FGC_ACT_MIU) acc = miu_relu(acc);
+    st1<TO>(y + i, acc);
+  }
+}
 }  // namespace fgc
 
 using namespace fgc;
@@ -1271,6 +1294,18 @@ int fgc_split_term(const float* x, long long n, int level, void* out_bf16, float
   split_term_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, n, level, (__nv_bfloat16*)out_bf16, out_f32);
   count_launch();
   FGC_LAUNCH_CHECK("split_term");
+  return FGC_OK;
+}
+
+int fgc_tapsum_w(const float* z, int N, int H, int W, int k, int Cout, int Cz, const float* bias, int act, void* y, int y_dtype,
+                 fgc_stream stream) {
+  FGC_REQUIRE(z && y && k % 2 == 1 && Cz >= k * Cout, "tapsum_w: bad arguments");
+  const long long npix = (long long)N * H * W;
+  cudaStream_t s = as_stream(stream);
+  if (y_dtype == FGC_F32) tapsum_w_kernel<float><<<ew_grid(npix * Cout, 256), 256, 0, s>>>(z, npix, W, k, Cout, Cz, bias, act, (float*)y);
+  else tapsum_w_kernel<__nv_bfloat16><<<ew_grid(npix * Cout, 256), 256, 0, s>>>(z, npix, W, k, Cout, Cz, bias, act, (__nv_bfloat16*)y);
+  count_launch();
+  FGC_LAUNCH_CHECK("tapsum_w");
   return FGC_OK;
 }
 

@@ -97,7 +97,34 @@ class CudaOps(OpsBase):
         n = self.lib.fgc_conv2d_ws_bytes(arr, len(cs), k, nout, dt)
         return self._empty((n,), torch.uint8)
 
+    def _conv_fwd_column_folded(self, src, w, b, act, out_dtype):
+        """A k x k, stride-1 layer with very few outputs over one wide bf16 source (the generator's 7x7, 64 -> 3 head,
+        models_collection.py:372-374).  On the tensor path its natural form is k*k narrow (N = 16) instructions per K step,
+        each paying a full 128-pixel operand fetch: 1.22 ms for 44 GFLOP.  Folded: z = the k x 1 vertical convolution with
+        k*Cout outputs (filter column kw in channels kw*Cout..: one N = 32 instruction per filter row; the filter is handed
+        over as a k x k one whose only non-zero column is the centre, flag 2 lets the halo kernel skip the rest), then
+        y[.., w, co] = act(b + sum_kw z[.., w + kw - pad, kw*Cout + co]) -- a small streaming pass."""
+        x = src[0]
+        N, H, W, cin = x.shape
+        k, cout = w.shape[0], w.shape[3]
+        w2 = torch.zeros((k, k, cin, k * cout), dtype=torch.float32, device=self.device)
+        # pure re-indexing: w2[kh, centre, c, kw*Cout + co] = w[kh, kw, c, co]
+        w2[:, (k - 1) // 2].copy_(w.permute(0, 2, 1, 3).reshape(k, cin, k * cout))
+        arr, N, H, W, dt = self._srcs([src])
+        pad = (k - 1) // 2
+        z = self._empty((N, H, W, k * cout), torch.float32)
+        ws = self._ws([cin], k, k * cout, dt)
+        check(self.lib.fgc_conv2d_fwd_acc(arr, 1, dt, N, H, W, self._f32(w2), k, cin, k * cout, None, 1, pad, pad, H, W, ACT_NONE, 2,
+                                          self._p(z), self._dt(z), self._p(ws), self._s()), "conv2d_fwd (column folded)")
+        y = self._empty((N, H, W, cout), out_dtype or self.act_dtype)
+        check(self.lib.fgc_tapsum_w(self._f32(z), N, H, W, k, cout, k * cout, None if b is None else self._f32(b.reshape(-1)), act,
+                                    self._p(y), self._dt(y), self._s()), "tapsum_w")
+        return y
+
     def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None):
+        if (len(srcs) == 1 and stride == 1 and w.shape[0] >= 5 and w.shape[0] * w.shape[3] <= 32 and srcs[0][0].dtype == torch.bfloat16
+                and srcs[0][0].shape[3] >= 64 and not srcs[0][1] and srcs[0][0].shape[2] % 8 == 0):
+            return self._conv_fwd_column_folded(srcs[0], w, b, act, out_dtype)
         arr, N, H, W, dt = self._srcs(srcs)
         k, cin, cout = w.shape[0], w.shape[2], w.shape[3]
         OH, pt = _same_pad(H, k, stride)
