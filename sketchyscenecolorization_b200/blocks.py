@@ -109,15 +109,21 @@ def enc_block_fwd(ops, wv, scope, x, ht, labels, kind, save=True):
     h1, c_h1 = norm_act_fwd(ops, st, scope + "/Conv_1", h1_raw, labels, kind)
     w, b = wv.get(scope + "/Conv_2")
     h2 = ops.conv_fwd([(h1, False)], w, b)                                       # mru.py:437-442
+    ht_p = None
     if scope + "/Conv_3/weights" in st.p:
+        # mru.py:446-453,457: mean_pool(conv1x1(ht) + h2).  A 1x1 convolution (+ bias) commutes with the 2x2 mean, so the
+        # skip runs on the POOLED hidden state -- a quarter of the products, and the full-resolution skip tensor (1.2 GB
+        # per pass in the discriminator's first unit) is never written; it accumulates into mean_pool(h2).
         w, b = wv.get(scope + "/Conv_3")
-        sk = ops.conv_fwd([(ht, False)], w, b)                                   # mru.py:446-452 (1x1, only when cin != cout)
+        ht_p = ops.meanpool_fwd(ht)
+        out = ops.meanpool_fwd(h2)
+        ops.conv_fwd([(ht_p, False)], w, b, out=out, acc=True)
     else:
-        sk = ht                                                                  # same width: the hidden state passes as it is
-    out = ops.addpool_fwd(sk, h2)                                                # mru.py:453,457
+        out = ops.addpool_fwd(ht, h2)                                            # same width: the hidden state passes as it is
     ctx = None
     if save:
-        ctx = dict(x=x, xs_=xs_, ps_=ps_, ht=ht, a=a, c_a=c_a, rg_raw=rg_raw, rg=rg, mn=mn, mx=mx, im=im, c_p=c_p, p=p, c_h1=c_h1, h1=h1)
+        ctx = dict(x=x, xs_=xs_, ps_=ps_, ht=ht, ht_p=ht_p, a=a, c_a=c_a, rg_raw=rg_raw, rg=rg, mn=mn, mx=mx, im=im, c_p=c_p, p=p,
+                   c_h1=c_h1, h1=h1)
     return out, ctx
 
 
@@ -130,14 +136,14 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
     # bias gradients: column sums of the gradient at a conv output.  They come out of the kernel that produces that
     # gradient (dbias= of the norm / activation / min-max backward); for Conv_2 / Conv_3 the gradient is the un-pooled
     # g_out / 4 replicated 2x2, whose column sums equal those of the (4x smaller) g_out itself.
-    # Conv_3 (1x1 skip on the raw hidden state; identity when the block keeps its width)
+    # Conv_3 (1x1 skip, evaluated on the pooled hidden state -- see the forward pass; identity when the block keeps its width)
     if scope + "/Conv_3/weights" in st.p:
         w3, _ = wv.get(scope + "/Conv_3")
         if nw:
             dw3, db3 = wv.grads(scope + "/Conv_3")
             ops.colsum_(g_out, db3)
-            ops.conv_wgrad([(ht, False)], g_full, dw3, None)
-        g_ht = ops.conv_dgrad(g_full, w3, 0, cin) if need_ht_grad else None
+            ops.conv_wgrad([(ctx["ht_p"], False)], g_out, dw3, None)
+        g_ht = ops.unpool_bwd(ops.conv_dgrad(g_out, w3, 0, cin)) if need_ht_grad else None
     else:
         g_ht = ops.unpool_bwd(g_out) if need_ht_grad else None     # its own buffer: the branches below accumulate into it
     # Conv_2

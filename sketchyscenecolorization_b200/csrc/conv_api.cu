@@ -6,7 +6,7 @@
 #include "conv_geom.cuh"
 
 namespace fgc {
-int conv_fwd_simple(const ConvGeom& g, int src_dtype, const float* w, int Cin_total, int Cout, const float* bias, int act,
+int conv_fwd_simple(const ConvGeom& g, int src_dtype, const float* w, int Cin_total, int Cout, const float* bias, int act, int accumulate,
                     void* y, int y_dtype, cudaStream_t s);
 int conv_dgrad_simple(const void* gy, int gy_dtype, int N, int H, int W, const float* w, int k, int Cin_total, int Cout,
                       int c_off, int c_len, int ups, int accumulate, void* gx, int gx_dtype, cudaStream_t s);
@@ -109,8 +109,7 @@ int fgc_conv2d_fwd_acc(const fgc_src* srcs, int nsrc, int src_dtype, int N, int 
   FGC_REQUIRE(cin == Cin_total, "conv_fwd: sources have %d channels, weights expect %d", cin, Cin_total);
   cudaStream_t s = as_stream(stream);
   if (conv_impl() == 1) {
-    FGC_REQUIRE(!(accumulate & 1), "conv_fwd: the CUDA-core checker does not accumulate");
-    e = conv_fwd_simple(g, src_dtype, w, Cin_total, Cout, bias, act, y, y_dtype, s);
+    e = conv_fwd_simple(g, src_dtype, w, Cin_total, Cout, bias, act, accumulate & 1, y, y_dtype, s);
     if (e) return e;
     FGC_LAUNCH_CHECK("conv_fwd_simple");
     return FGC_OK;

@@ -20,7 +20,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 template <typename TS, typename TO>
 __global__ void conv_fwd_simple_kernel(ConvGeom g, const float* __restrict__ w, int Cin_total, int Cout,
-                                       const float* __restrict__ bias, int act, TO* __restrict__ y) {
+                                       const float* __restrict__ bias, int act, int accumulate, TO* __restrict__ y) {
   long long total = g.M * Cout;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     int co = (int)(idx % Cout);
@@ -45,7 +45,9 @@ __global__ void conv_fwd_simple_kernel(ConvGeom g, const float* __restrict__ w, 
         }
       }
     }
-    st1<TO>(y + idx, apply_act(acc, act));
+    float v = apply_act(acc, act);
+    if (accumulate) v += (float)y[idx];        // plain load: y is written by this kernel
+    st1<TO>(y + idx, v);
   }
 }
 
@@ -198,10 +200,10 @@ int colsum_launch(const void* x, int dtype, long long M, int C, float* out, cuda
 }
 
 int conv_fwd_simple(const ConvGeom& g, int src_dtype, const float* w, int Cin_total, int Cout, const float* bias, int act,
-                    void* y, int y_dtype, cudaStream_t s) {
+                    int accumulate, void* y, int y_dtype, cudaStream_t s) {
   long long total = g.M * Cout;
   int grid = ew_grid(total, 128);
-#define FGC_L(TS, TO) conv_fwd_simple_kernel<TS, TO><<<grid, 128, 0, s>>>(g, w, Cin_total, Cout, bias, act, (TO*)y)
+#define FGC_L(TS, TO) conv_fwd_simple_kernel<TS, TO><<<grid, 128, 0, s>>>(g, w, Cin_total, Cout, bias, act, accumulate, (TO*)y)
   if (src_dtype == FGC_F32 && y_dtype == FGC_F32) FGC_L(float, float);
   else if (src_dtype == FGC_F32 && y_dtype == FGC_BF16) FGC_L(float, __nv_bfloat16);
   else if (src_dtype == FGC_BF16 && y_dtype == FGC_F32) FGC_L(__nv_bfloat16, float);

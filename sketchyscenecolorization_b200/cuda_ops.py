@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -38,6 +39,7 @@ class CudaOps(OpsBase):
         if conv_terms not in (2, 3):
             raise ValueError("conv_terms must be 2 (bf16x3) or 3 (six products)")
         self.conv_terms = conv_terms
+        self.fold_narrow_dgrad = os.environ.get("FGC_FOLD_DGRAD", "1") != "0"
         if not torch.cuda.is_available():
             raise RuntimeError("CudaOps needs a CUDA device (sm_100a); there is no CPU path in this package")
         if act_dtype not in _DT:
@@ -121,7 +123,9 @@ class CudaOps(OpsBase):
                                     self._p(y), self._dt(y), self._s()), "tapsum_w")
         return y
 
-    def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None):
+    def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None, out=None, acc=False):
+        if out is not None:
+            return self._conv_fwd_into(srcs, w, b, stride, act, out, acc)
         if (len(srcs) == 1 and stride == 1 and w.shape[0] >= 5 and w.shape[0] * w.shape[3] <= 32 and srcs[0][0].dtype == torch.bfloat16
                 and srcs[0][0].shape[3] >= 64 and not srcs[0][1] and srcs[0][0].shape[2] % 8 == 0):
             return self._conv_fwd_column_folded(srcs[0], w, b, act, out_dtype)
@@ -137,6 +141,21 @@ class CudaOps(OpsBase):
         if self.conv_terms == 3 and srcs[0][0].dtype == torch.float32 and act == ACT_NONE and y.dtype == torch.float32:
             self._six_product_passes(srcs, w, k, cin, cout, stride, pt, pl, OH, OW, y)
         return y
+
+    def _conv_fwd_into(self, srcs, w, b, stride, act, out, acc):
+        """out (+)= act(conv + b): fgc_conv2d_fwd_acc, flag bit 0."""
+        arr, N, H, W, dt = self._srcs(srcs)
+        k, cin, cout = w.shape[0], w.shape[2], w.shape[3]
+        OH, pt = _same_pad(H, k, stride)
+        OW, pl = _same_pad(W, k, stride)
+        assert tuple(out.shape) == (N, OH, OW, cout) and out.is_contiguous()
+        ws = self._ws([e[0].shape[3] for e in srcs], k, cout, dt)
+        check(self.lib.fgc_conv2d_fwd_acc(arr, len(srcs), dt, N, H, W, self._f32(w), k, cin, cout,
+                                          None if b is None else self._f32(b.reshape(-1)), stride, pt, pl, OH, OW, act,
+                                          1 if acc else 0, self._p(out), self._dt(out), self._p(ws), self._s()), "conv2d_fwd_acc")
+        if self.conv_terms == 3 and srcs[0][0].dtype == torch.float32 and act == ACT_NONE and out.dtype == torch.float32:
+            self._six_product_passes(srcs, w, k, cin, cout, stride, pt, pl, OH, OW, out)
+        return out
 
     def _split(self, x, level, bf16):
         out = self._empty(x.shape, torch.bfloat16 if bf16 else torch.float32)
@@ -175,6 +194,16 @@ class CudaOps(OpsBase):
         N, H, W, cout = gy.shape
         k, cin = w.shape[0], w.shape[2]
         assert w.shape[3] == cout
+        if (k == 3 and k * c_len <= 32 and not ups and gy_patch is None and gy.dtype == torch.bfloat16 and cout >= 64 and W % 8 == 0
+                and self.fold_narrow_dgrad):
+            # gradient towards a NARROW source (the 8-channel stem features under a 128-wide layer) = a stride-1 convolution of
+            # gy with the flipped, transposed filter to c_len outputs: k*k N = 16 instructions per K step on the tensor path,
+            # k N = 32 ones in the column-folded form of the 7x7 head
+            wt = w[:, :, c_off:c_off + c_len, :].flip(0, 1).permute(0, 1, 3, 2).contiguous()
+            g = self._conv_fwd_column_folded((gy, False), wt, None, ACT_NONE, out_dtype if out is None else out.dtype)
+            if out is None:
+                return g
+            return self.add_(out, g) if acc else out.copy_(g)
         oshape = (N, H // 2, W // 2, c_len) if ups else (N, H, W, c_len)
         if out is None:
             out = self._empty(oshape, out_dtype or self.act_dtype)

@@ -25,8 +25,9 @@ class OpsBase:
     act_dtype = None
 
     # ---------------- convolution family (mru.conv2d, mru.py:95-140) ----------------
-    def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None):
-        """y = act(conv2d_SAME(concat(srcs), w) + b);  w HWIO fp32, b fp32 [Cout] or None."""
+    def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None, out=None, acc=False):
+        """y = act(conv2d_SAME(concat(srcs), w) + b);  w HWIO fp32, b fp32 [Cout] or None.  out= writes into the given tensor,
+        with acc=True adds to it."""
         raise NotImplementedError
 
     def conv_dgrad(self, gy, w, c_off, c_len, *, ups=False, out=None, acc=False, out_dtype=None, gy_patch=None):

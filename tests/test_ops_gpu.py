@@ -108,6 +108,29 @@ def test_conv_fwd(env, case, impl):
         _set_impl(cu, 0)
 
 
+@pytest.mark.parametrize("acc", [False, True], ids=["write", "acc"])
+@pytest.mark.parametrize("case", [CONV_CASES[i] for i in (6, 12)] + [(4, 12, 12, [(8, False)], 1, 1, 128, ACT_NONE)],
+                         ids=["1x1", "halo", "skip-low-res"])
+def test_conv_fwd_into(env, case, acc):
+    """conv_fwd(out=, acc=): the pooled 1x1 skip of the encoder cell accumulates into mean_pool(h2) (blocks.enc_block_fwd)."""
+    cu, ref, dev = env["cu"], env["ref"], env["dev"]
+    N, H, W, srcs, k, stride, cout, act = case
+    xs, w, b = _conv_inputs(case, dev)
+    init = rnd((N, -(-H // stride), -(-W // stride), cout), 40, dev)
+    want = ref.conv_fwd(xs, w, b, stride=stride, act=act, out=init.clone(), acc=acc)
+    out = init.float().contiguous()
+    got = cu.conv_fwd([(x.float().contiguous(), u) for x, u in xs], w.float().contiguous(), b.float().contiguous(),
+                      stride=stride, act=act, out=out, acc=acc)
+    torch.cuda.synchronize()
+    assert got is out
+    close(got, want, 1e-4, "conv_fwd(out=) fp32")
+    outb = init.bfloat16().contiguous()
+    env["cub"].conv_fwd([(x.bfloat16().contiguous(), u) for x, u in xs], w.float().contiguous(), b.float().contiguous(),
+                        stride=stride, act=act, out=outb, acc=acc)
+    torch.cuda.synchronize()
+    close(outb, want, 3e-2, "conv_fwd(out=) bf16")
+
+
 DGRAD_CASES = [
     # (N, H, W, Cin_total, c_off, c_len, k, Cout, ups, acc)
     (2, 16, 16, 64, 0, 64, 3, 64, False, False),
@@ -126,6 +149,8 @@ DGRAD_CASES = [
     (8, 64, 80, 139, 0, 128, 3, 128, True, True),       # upsampled source, 2x2 sums folded into the halo epilogue, accumulating
     (48, 1, 1, 1024, 512, 512, 1, 2048, False, False),  # skinny-product kernel (<= 64 rows): LSTM kernel slice, float4 weights
     (33, 1, 1, 200, 7, 90, 1, 130, False, True),        # skinny-product kernel: ragged K / N, unaligned slice, accumulating
+    (2, 16, 24, 139, 131, 8, 3, 128, False, True),      # column-folded narrow gradient (bf16), slice at the end, accumulating
+    (2, 24, 16, 8, 0, 8, 3, 128, False, False),         # column-folded narrow gradient: the discriminator's unit-1 Conv_1
 ]
 
 

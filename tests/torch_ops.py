@@ -60,7 +60,10 @@ class TorchOps(OpsBase):
     def _cat(self, srcs):
         return torch.cat([_up(self._c(e[0])) if e[1] else self._c(e[0]) for e in srcs], dim=-1)
 
-    def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None):
+    def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None, out=None, acc=False):
+        if out is not None:
+            y = self.conv_fwd(srcs, w, b, stride=stride, act=act, out_dtype=out.dtype)
+            return out.add_(y) if acc else out.copy_(y)
         x = self._cat(srcs).permute(0, 3, 1, 2)
         k = w.shape[0]
         pt, pb = _same_pad(x.shape[2], k, stride)
