@@ -519,6 +519,59 @@ def run_bg(args):
         "gpu_launches": res["parity"]["launches"] * args.steps}), flush=True)
 
 
+def run_rmi(args):
+    """BASELINE.json configs[4]: the instance-matching model (ResNet-101 trunk at output stride 8 + word LSTM + multimodal LSTM
+    over 96 x 96 positions), 768x768, bs 32, 15-token captions of mixed length.  value = pictures per second with the batch
+    resident on the device, in the throughput mode (bf16 storage, single-pass tensor-core products); the parity mode (fp32
+    storage, bf16x3 products; tests/test_rmi_gpu.py) is timed beside it at the batch that fits its fp32 intermediates."""
+    import numpy as np
+    import torch
+    from sketchyscenecolorization_b200.cuda_ops import CudaOps
+    from sketchyscenecolorization_b200.rmi import RMIModel
+    rs = np.random.RandomState(0)
+    res = {}
+    for name, dt, N in (("bf16", torch.bfloat16, args.rmi_batch), ("parity", torch.float32, max(1, args.rmi_batch // 4))):
+        ops = CudaOps("cuda:0", dt)
+        m = RMIModel(ops, "cuda:0")
+        m.initialize(seed=0)
+        im = (torch.rand(N, 768, 768, 3, device="cuda") * 255.0 - 115.0).contiguous()
+        im_dev = im if dt == torch.float32 else ops.cast(im, dt)
+        words = rs.randint(2, 59, size=(N, 15))
+        lengths = rs.randint(4, 16, size=(N,))
+        n0 = ops.launch_count()
+        up, sg = m.forward(im_dev, words, lengths)
+        launches = ops.launch_count() - n0
+        assert torch.isfinite(up).all().item() and up.shape == (N, 768, 768, 1)
+        med, best = _time_calls(torch, lambda: m.forward(im_dev, words, lengths), args.steps, args.warmup)
+        t_med, _ = _time_calls(torch, lambda: m.trunk(im_dev), args.steps, 1)
+        res[name] = dict(batch=N, ms=med, best_ms=best, trunk_ms=t_med, launches=launches, images_per_s=N / med * 1e3)
+        if name == "bf16":
+            im_host = im.cpu().pin_memory()
+
+            def e2e():
+                u, s_ = m.forward(ops.cast(im_host.to("cuda", non_blocking=True), dt), words, lengths)
+                return (u >= 1e-9).to(torch.uint8).cpu()
+            e_med, _ = _time_calls(torch, e2e, max(2, args.steps // 2), 1)
+            res["e2e"] = dict(ms=e_med, images_per_s=N / e_med * 1e3, h2d=im_host.numel() * 4, d2h=N * 768 * 768)
+        del m, ops, im, im_dev, up, sg
+        torch.cuda.empty_cache()
+    trunk_gflop, fusion_gflop = 2 * 398.1, 2 * (18.9 + 18.4 + 9.2 * 9.5)     # per picture; mean caption length 9.5 steps
+    b = res["bf16"]
+    print(json.dumps({
+        "metric": "instance-matching (RMI) inference images/sec @768x768 bs%d" % b["batch"], "value": b["images_per_s"], "unit": "images/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": b["ms"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Instance_Matching RMI_model (DeepLab ResNet-101 trunk + LSTM) referring-segmentation inference, "
+                               "768x768, bs %d (BASELINE.json configs[4])" % b["batch"],
+                   "single_pass_bf16": b, "parity_mode": res["parity"],
+                   "gflop_per_image": round(trunk_gflop + fusion_gflop, 1),
+                   "tflops": round((trunk_gflop + fusion_gflop) * b["images_per_s"] / 1e3, 1),
+                   "parity": "tests/test_rmi_gpu.py: max-abs of the 768x768 score map vs the fp64 oracle"},
+        "e2e": {"value": res["e2e"]["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": res["e2e"]["h2d"],
+                "d2h_bytes_per_step": res["e2e"]["d2h"], "api": "RMIModel.forward (pinned host pictures in, host masks out)"},
+        "gpu_launches": b["launches"] * args.steps}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -532,8 +585,10 @@ def main():
                     help="source of the e2e leg: ready pinned fp32 tensors (default) or synthetic TFRecord files through the "
                          "real input pipeline")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from Python instead of replaying CUDA graphs")
-    ap.add_argument("--mode", default="train", choices=["train", "infer", "bg"],
-                    help="train: the headline (BASELINE.json configs[1]); infer: configs[0] latency + parity; bg: configs[3] latency")
+    ap.add_argument("--mode", default="train", choices=["train", "infer", "bg", "rmi"],
+                    help="train: the headline (BASELINE.json configs[1]); infer: configs[0] latency + parity; bg: configs[3] latency; "
+                         "rmi: configs[4] throughput")
+    ap.add_argument("--rmi-batch", dest="rmi_batch", type=int, default=32)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -541,6 +596,8 @@ def main():
         run_infer(args)
     elif args.mode == "bg":
         run_bg(args)
+    elif args.mode == "rmi":
+        run_rmi(args)
     else:
         run_product(args)
 

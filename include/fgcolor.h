@@ -201,7 +201,7 @@ int fgc_lstm_seq_fwd(const float* gx, const float* kh, const int32_t* ids, int T
                      float* pre_all, unsigned int* barrier, fgc_stream stream);
 int fgc_lstm_seq_bwd(const float* g_hext, const float* pre_all, const float* c_all, const float* kh, const int32_t* ids, int T,
                      int N, int D, float* g_pre_all, unsigned int* barrier, fgc_stream stream);
-/* pre = gates (+gates2) (+grow[r/P]); R = N*P rows of 4*D; gates2/grow may be NULL */
+/* pre = gates (+gates2) (+grow[r/P]); R = N*P rows of 4*D; gates2/grow may be NULL; pre may be NULL (inference: not kept) */
 int fgc_lstm_cell_fwd(const float* gates, const float* gates2, const float* grow, const float* c_prev,
                       const float* h_prev, const int32_t* ids, int T, int t, int N, int P, int D,
                       float* c, float* h, float* pre, fgc_stream s);
@@ -276,6 +276,28 @@ int fgc_phase_wgrad(const float* dw, int A, int B, int mode, float* df, fgc_stre
 int fgc_paired_input(const uint8_t* cartoon, const void* sketch, int sketch_dtype, int N, int R, int OH, int OW,
                      unsigned long long seed, int dequantize, float* images, float* sketches, uint32_t* scratch,
                      fgc_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Streaming operators of the instance-matching model (BASELINE.json configs[4]; reference Instance_Matching/): the ResNet-101
+ * trunk of deeplab_model.py and the output head of RMI_model.py.  Its contractions are the convolutions above (1x1 / 3x3 /
+ * 7x7, stride 1 / 2); tf.nn.atrous_conv2d (:289-291) runs -- as inside TensorFlow -- as a plain SAME convolution between
+ * space_to_batch and batch_to_space, and because every other operator of a residual group is per pixel the whole dilated
+ * group stays in the batch form.
+ * -------------------------------------------------------------------------------------------------------*/
+/* y = act(x*scale[c] + shift[c] + r), r = 0 (res NULL) | res (rscale NULL) | res*rscale[c] + rshift[c]; relu: 0 / 1.
+ * deeplab_model._batch_norm with stored moments (:213-233) folded to scale = gamma*rsqrt(variance/factor + 0.001),
+ * shift = beta - mean/factor*scale; _relu (:299-301); the residual sum of _bottleneck_residual (:256-262).  x: [M, C]. */
+int fgc_affine_act(const void* x, int dtype, long long M, int C, const float* scale, const float* shift, const void* res,
+                   const float* rscale, const float* rshift, int relu, void* y, fgc_stream s);
+/* tf.nn.max_pool(x, [1,3,3,1], [1,2,2,1], 'SAME') (deeplab_model.py:72): y [N, ceil(H/2), ceil(W/2), C] */
+int fgc_maxpool3x3s2(const void* x, int dtype, int N, int H, int W, int C, void* y, fgc_stream s);
+/* y[(py*r + px)*N + n, h, w, :] = x[n, h*r + py, w*r + px, :]: [N,H,W,C] -> [r*r*N, H/r, W/r, C], and its inverse (h, w =
+ * the batch-form size, N = the ORIGINAL batch) */
+int fgc_space_to_batch(const void* x, int dtype, int N, int H, int W, int C, int r, void* y, fgc_stream s);
+int fgc_batch_to_space(const void* x, int dtype, int N, int h, int w, int C, int r, void* y, fgc_stream s);
+/* tf.image.resize_bilinear(x, [H, W]) (align_corners False, TF-1: source = destination * h/H) of fp32 x [N,h,w,C] into up
+ * [N,H,W,C]; sigm (optional) = sigmoid(up) (RMI_model.py:150-151) */
+int fgc_resize_bilinear(const float* x, int N, int h, int w, int C, int H, int W, float* up, float* sigm, fgc_stream s);
 
 #ifdef __cplusplus
 }

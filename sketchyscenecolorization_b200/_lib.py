@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libfgcolor.so")
-SOURCES = ["api.cu", "elementwise.cu", "text.cu", "sn.cu", "loss.cu", "conv_simple.cu", "conv_small.cu", "conv_tc.cu", "conv_api.cu", "input.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "text.cu", "sn.cu", "loss.cu", "conv_simple.cu", "conv_small.cu", "conv_tc.cu", "conv_api.cu", "input.cu", "trunk.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -137,6 +137,11 @@ SIGNATURES = {
     "fgc_reg_loss": [_P, _P, _P, _P, _I, _P, _I, _P],
     "fgc_adam_step": [_P, _P, _P, _P, _P, _P, _I, _F, _P, _F, _F, _I, _P],
     "fgc_opt_step": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P, _I, _P],
+    "fgc_affine_act": [_P, _I, _LL, _I, _P, _P, _P, _P, _P, _I, _P, _P],
+    "fgc_maxpool3x3s2": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "fgc_space_to_batch": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "fgc_batch_to_space": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "fgc_resize_bilinear": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
 }
 _RESTYPE = {"fgc_last_error": C.c_char_p, "fgc_launch_count": C.c_longlong, "fgc_conv2d_ws_bytes": C.c_size_t}
 

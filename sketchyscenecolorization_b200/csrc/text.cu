@@ -74,13 +74,51 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, const floa
       if (gates2) v += gates2[o];
       if (grow) v += grow[(long long)n * 4 * D + (long long)q * D + d];
       p[q] = v;
-      pre[o] = v;
+      if (pre) pre[o] = v;
     }
     float cp = c_prev[idx], hp = h_prev[idx];
     if (ids[n * T + t] != 0) {
       float cn = cp * sigmoid_acc(p[2] + 1.0f) + sigmoid_acc(p[0]) * tanhf(p[1]);
       c[idx] = cn;
       h[idx] = tanhf(cn) * sigmoid_acc(p[3]);
+    } else {
+      c[idx] = cp;
+      h[idx] = hp;
+    }
+  }
+}
+// the same, four hidden units per thread (D % 4 == 0, 16-byte aligned buffers): the multimodal LSTM of the instance-matching
+// model walks N*96*96 rows x 2000 gate columns per step -- 128-bit accesses, one row / sample decode per four units
+__global__ void lstm_cell_fwd_vec4_kernel(const float4* __restrict__ gates, const float4* __restrict__ gates2,
+                                          const float4* __restrict__ grow, const float4* __restrict__ c_prev,
+                                          const float4* __restrict__ h_prev, const int32_t* __restrict__ ids, int T, int t, int N,
+                                          int P, int D4, float4* __restrict__ c, float4* __restrict__ h, float4* __restrict__ pre) {
+  const long long total = (long long)N * P * D4;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / D4;
+    const int d = (int)(idx - r * D4);
+    const int n = (int)(r / P);
+    float p[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const long long o = r * 4 * D4 + (long long)q * D4 + d;
+      float4 v = __ldcs(gates + o);
+      if (gates2) { float4 u = __ldg(gates2 + o); v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+      if (grow) { float4 u = __ldg(grow + (long long)n * 4 * D4 + (long long)q * D4 + d); v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w; }
+      p[q][0] = v.x; p[q][1] = v.y; p[q][2] = v.z; p[q][3] = v.w;
+      if (pre) pre[o] = v;
+    }
+    const float4 cp = c_prev[idx], hp = h_prev[idx];
+    if (ids[n * T + t] != 0) {
+      const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+      float cn[4], hn[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        cn[k] = cpv[k] * sigmoid_acc(p[2][k] + 1.0f) + sigmoid_acc(p[0][k]) * tanhf(p[1][k]);
+        hn[k] = tanhf(cn[k]) * sigmoid_acc(p[3][k]);
+      }
+      c[idx] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      h[idx] = make_float4(hn[0], hn[1], hn[2], hn[3]);
     } else {
       c[idx] = cp;
       h[idx] = hp;
@@ -429,8 +467,15 @@ int fgc_lstm_seq_bwd(const float* g_hext, const float* pre_all, const float* c_a
 int fgc_lstm_cell_fwd(const float* gates, const float* gates2, const float* grow, const float* c_prev,
                       const float* h_prev, const int32_t* ids, int T, int t, int N, int P, int D,
                       float* c, float* h, float* pre, fgc_stream stream) {
-  lstm_cell_fwd_kernel<<<ew_grid((long long)N * P * D, 256), 256, 0, as_stream(stream)>>>(gates, gates2, grow, c_prev, h_prev, ids,
-                                                                                         T, t, N, P, D, c, h, pre);
+  const uintptr_t al = (uintptr_t)gates | (uintptr_t)gates2 | (uintptr_t)grow | (uintptr_t)c_prev | (uintptr_t)h_prev | (uintptr_t)c |
+                       (uintptr_t)h | (uintptr_t)pre;
+  if (D % 4 == 0 && (al & 15) == 0)
+    lstm_cell_fwd_vec4_kernel<<<ew_grid((long long)N * P * (D / 4), 256), 256, 0, as_stream(stream)>>>(
+        (const float4*)gates, (const float4*)gates2, (const float4*)grow, (const float4*)c_prev, (const float4*)h_prev, ids, T, t, N, P,
+        D / 4, (float4*)c, (float4*)h, (float4*)pre);
+  else
+    lstm_cell_fwd_kernel<<<ew_grid((long long)N * P * D, 256), 256, 0, as_stream(stream)>>>(gates, gates2, grow, c_prev, h_prev, ids,
+                                                                                           T, t, N, P, D, c, h, pre);
   count_launch();
   FGC_LAUNCH_CHECK("lstm_cell_fwd");
   return FGC_OK;

@@ -479,6 +479,41 @@ class CudaOps(OpsBase):
                                         self._p(images), self._p(sketches), self._p(scratch), self._s()), "paired_input")
         return images, sketches
 
+    # ---------------- instance-matching model ----------------
+    def affine_act(self, x, scale, shift, res=None, rscale=None, rshift=None, relu=False):
+        Cc = x.shape[-1]
+        y = torch.empty_like(x)
+        check(self.lib.fgc_affine_act(self._p(x), self._dt(x), x.numel() // Cc, Cc, self._f32(scale), self._f32(shift),
+                                      self._p(res), None if rscale is None else self._f32(rscale),
+                                      None if rshift is None else self._f32(rshift), 1 if relu else 0, self._p(y), self._s()),
+              "affine_act")
+        return y
+
+    def maxpool3x3s2(self, x):
+        N, H, W, Cc = x.shape
+        y = self._empty((N, (H + 1) // 2, (W + 1) // 2, Cc), x.dtype)
+        check(self.lib.fgc_maxpool3x3s2(self._p(x), self._dt(x), N, H, W, Cc, self._p(y), self._s()), "maxpool3x3s2")
+        return y
+
+    def space_to_batch(self, x, r):
+        N, H, W, Cc = x.shape
+        y = self._empty((N * r * r, H // r, W // r, Cc), x.dtype)
+        check(self.lib.fgc_space_to_batch(self._p(x), self._dt(x), N, H, W, Cc, r, self._p(y), self._s()), "space_to_batch")
+        return y
+
+    def batch_to_space(self, x, r):
+        NB, h, w, Cc = x.shape
+        N = NB // (r * r)
+        y = self._empty((N, h * r, w * r, Cc), x.dtype)
+        check(self.lib.fgc_batch_to_space(self._p(x), self._dt(x), N, h, w, Cc, r, self._p(y), self._s()), "batch_to_space")
+        return y
+
+    def resize_bilinear_sigmoid(self, x, H, W):
+        N, h, w, Cc = x.shape
+        up, sg = self._empty((N, H, W, Cc), torch.float32), self._empty((N, H, W, Cc), torch.float32)
+        check(self.lib.fgc_resize_bilinear(self._f32(x), N, h, w, Cc, H, W, self._p(up), self._p(sg), self._s()), "resize_bilinear")
+        return up, sg
+
     # ---------------- text fusion ----------------
     def _dst(self, out, shape, dtype=torch.float32):
         if out is None:
@@ -547,13 +582,13 @@ class CudaOps(OpsBase):
                                         self._p(g_pre_all), self._p(bar), self._s()), "lstm_seq_bwd")
         return g_pre_all
 
-    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None):
+    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None, save_pre=True):
         R, D = c_prev.shape
         N, T = ids.shape
         assert R == N * P
         c = self._empty((R, D), torch.float32)
         h = self._dst(out_h, (R, D))
-        pre = self._empty((R, 4 * D), torch.float32)
+        pre = self._empty((R, 4 * D), torch.float32) if save_pre else None
         check(self.lib.fgc_lstm_cell_fwd(self._f32(gates), None if gates2 is None else self._f32(gates2),
                                          None if grow is None else self._f32(grow), self._f32(c_prev), self._f32(h_prev),
                                          self._p(ids), T, t, N, P, D, self._p(c), self._p(h), self._p(pre), self._s()),

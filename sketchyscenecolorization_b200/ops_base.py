@@ -181,6 +181,28 @@ class OpsBase:
         """[N,h,w,C] -> [N,H,W,C]: the overlapping top-left rectangle is copied, the rest is zero (crop or zero-pad)."""
         raise NotImplementedError
 
+    # ---------------- instance-matching model (Instance_Matching/deeplab_model.py, RMI_model.py) ----------------
+    def affine_act(self, x, scale, shift, res=None, rscale=None, rshift=None, relu=False):
+        """act(x*scale[c] + shift[c] + r) with r = 0 | res | res*rscale[c] + rshift[c]: stored-moment batch norm
+        (deeplab_model._batch_norm, :213-233), the residual sum and relu of _bottleneck_residual (:237-264)."""
+        raise NotImplementedError
+
+    def maxpool3x3s2(self, x):
+        """tf.nn.max_pool 3x3, stride 2, SAME (deeplab_model.py:72)."""
+        raise NotImplementedError
+
+    def space_to_batch(self, x, r):
+        """[N,H,W,C] -> [r*r*N, H/r, W/r, C], batch (py*r + px)*N + n = pixel phase (py, px) of sample n: a SAME convolution
+        of the result is tf.nn.atrous_conv2d(x, rate=r) in the same form (deeplab_model.py:289-291)."""
+        raise NotImplementedError
+
+    def batch_to_space(self, x, r):
+        raise NotImplementedError
+
+    def resize_bilinear_sigmoid(self, x, H, W):
+        """(tf.image.resize_bilinear(x, [H, W]), its sigmoid) of fp32 NHWC x (RMI_model.py:150-151)."""
+        raise NotImplementedError
+
     # ---------------- real-data input (input_pipeline.get_paired_input, :72-126) ----------------
     def paired_input(self, cartoon, sketch, out_hw, seed=0, dequantize=True):
         """cartoon uint8 [N,R,R,3], sketch uint8 | fp32 (0..255 distance map) [N,R,R,3] on the op device ->
@@ -229,10 +251,10 @@ class OpsBase:
         gate gradients of every step [T,N,4D] (the operand of the weight / input gradients)."""
         raise NotImplementedError
 
-    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None):
+    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None, save_pre=True):
         """BasicLSTMCell pointwise part.  pre = gates [+ gates2] [+ grow[r // P]]  ([R,4D], order i,j,f,o);
         c = c_prev*sig(f+1) + sig(i)*tanh(j); h = tanh(c)*sig(o); rows whose sample token ids[r//P, t] == 0 (<pad>) keep
-        (c_prev, h_prev).  Returns (c, h, pre); `out_h`: optional destination of h."""
+        (c_prev, h_prev).  Returns (c, h, pre); `out_h`: optional destination of h; save_pre=False (inference) returns pre = None."""
         raise NotImplementedError
 
     def lstm_cell_bwd(self, gc, gh, pre, c_prev, c, ids, t, P, out_gpre=None):

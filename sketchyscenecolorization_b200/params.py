@@ -412,3 +412,53 @@ class ParamStore:
         if self.opt_s2 is not None:
             self.opt_s2.zero_()
         self.adam_t = 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Instance-matching model (BASELINE.json configs[4]): Instance_Matching/deeplab_model.py (scope `ResNet`, :51-52) and
+# RMI_model.py (scope `text_sketchyscene`, :113-151).  Inference only; the stored batch-norm moments are kept in the store
+# like every other variable so that a state dict keyed by the reference names loads as it is.
+# ------------------------------------------------------------------------------------------------------------------
+RMI_UNITS = (3, 4, 23, 3)                      # deeplab_model.py:13
+RMI_FILTERS = (64, 256, 512, 1024, 2048)       # :20
+
+
+def _rmi_bn(scope, c):
+    return [VarSpec(scope + "/beta", (c,), ("const", 0.0)), VarSpec(scope + "/gamma", (c,), ("const", 1.0)),
+            VarSpec(scope + "/factor", (1,), ("const", 1.0)), VarSpec(scope + "/mean", (c,), ("const", 0.0)),
+            VarSpec(scope + "/variance", (c,), ("const", 1.0))]
+
+
+def _rmi_dw(scope, k, cin, cout):
+    return [VarSpec(scope + "/DW", (k, k, cin, cout), ("normal", math.sqrt(2.0 / (k * k * cout))))]      # deeplab_model.py:281-284
+
+
+def rmi_unit_plan(units=RMI_UNITS, filters=RMI_FILTERS):
+    """[(scope, cin, cout, stride, rate)] of the bottleneck units in graph order (deeplab_model.py:77-103)."""
+    plan = []
+    for g, (stride, rate) in enumerate(((1, 1), (2, 1), (1, 2), (1, 4))):
+        for i in range(units[g]):
+            plan.append(("ResNet/group_%d_%d" % (g + 2, i), filters[g] if i == 0 else filters[g + 1], filters[g + 1],
+                         stride if i == 0 else 1, rate))
+    return plan
+
+
+def rmi_vars(units=RMI_UNITS, filters=RMI_FILTERS, vocab_size=59, w_emb=1000, v_emb=1000, m_rnn=500, w_rnn=1000):
+    v = _rmi_dw("ResNet/group_1/conv1", 7, 3, filters[0]) + _rmi_bn("ResNet/group_1/bn_conv1", filters[0])
+    for scope, cin, cout, _, _ in rmi_unit_plan(units, filters):
+        for blk, k, a, b in (("block_1", 1, cin, cout // 4), ("block_2", 3, cout // 4, cout // 4), ("block_3", 1, cout // 4, cout)):
+            v += _rmi_dw("%s/%s/conv" % (scope, blk), k, a, b) + _rmi_bn("%s/%s/bn" % (scope, blk), b)
+        if cin != cout:
+            v += _rmi_dw(scope + "/block_add/conv", 1, cin, cout) + _rmi_bn(scope + "/block_add/bn", cout)
+    p = "text_sketchyscene"
+    xav = lambda cin, cout: ("uniform", math.sqrt(6.0 / (cin + cout)))            # xavier_initializer_conv2d, 1x1 (RMI_model.py:290-291)
+    v += [VarSpec(p + "/visual_feat_projection/DW", (1, 1, filters[4], v_emb), xav(filters[4], v_emb)),
+          VarSpec(p + "/visual_feat_projection/biases", (v_emb,), ("const", 0.0)),
+          VarSpec(p + "/embedding", (vocab_size, w_emb), ("uniform", 0.08)),                             # :128-129
+          VarSpec(p + "/wLSTM/lstm_cell/kernel", (w_emb + w_rnn, 4 * w_rnn), ("glorot_uniform", None)),
+          VarSpec(p + "/wLSTM/lstm_cell/bias", (4 * w_rnn,), ("const", 0.0)),
+          VarSpec(p + "/mLSTM/lstm_cell/kernel", (v_emb + w_emb + w_rnn + 8 + m_rnn, 4 * m_rnn), ("glorot_uniform", None)),
+          VarSpec(p + "/mLSTM/lstm_cell/bias", (4 * m_rnn,), ("const", 0.0)),
+          VarSpec(p + "/m_lstm_output_projection/DW", (1, 1, m_rnn, 1), xav(m_rnn, 1)),
+          VarSpec(p + "/m_lstm_output_projection/biases", (1,), ("const", 0.0))]
+    return v

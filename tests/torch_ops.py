@@ -315,6 +315,43 @@ class TorchOps(OpsBase):
         out[:, :min(h, H), :min(w, W)] = x[:, :min(h, H), :min(w, W)]
         return out
 
+    # ---- instance-matching model
+    def affine_act(self, x, scale, shift, res=None, rscale=None, rshift=None, relu=False):
+        y = self._c(x) * self._c(scale) + self._c(shift)
+        if res is not None:
+            y = y + (self._c(res) if rscale is None else self._c(res) * self._c(rscale) + self._c(rshift))
+        return (torch.relu(y) if relu else y).to(x.dtype)
+
+    def maxpool3x3s2(self, x):
+        xn = self._c(x).permute(0, 3, 1, 2)
+        pt, pb = _same_pad(xn.shape[2], 3, 2)
+        pl, pr = _same_pad(xn.shape[3], 3, 2)
+        y = F.max_pool2d(F.pad(xn, (pl, pr, pt, pb), value=float("-inf")), 3, 2)
+        return y.permute(0, 2, 3, 1).contiguous().to(x.dtype)
+
+    def space_to_batch(self, x, r):
+        N, H, W, C = x.shape
+        return x.view(N, H // r, r, W // r, r, C).permute(2, 4, 0, 1, 3, 5).reshape(r * r * N, H // r, W // r, C).contiguous()
+
+    def batch_to_space(self, x, r):
+        NB, h, w, C = x.shape
+        N = NB // (r * r)
+        return x.view(r, r, N, h, w, C).permute(2, 3, 0, 4, 1, 5).reshape(N, h * r, w * r, C).contiguous()
+
+    def resize_bilinear_sigmoid(self, x, H, W):
+        """TF-1 resize_bilinear, align_corners False: source = destination * (h / H), no half-pixel shift."""
+        N, h, w, C = x.shape
+        xc = self._c(x)
+        fy = torch.arange(H, dtype=self.cdt, device=x.device) * (h / H)
+        fx = torch.arange(W, dtype=self.cdt, device=x.device) * (w / W)
+        y0, x0 = fy.floor().long(), fx.floor().long()
+        y1, x1 = (y0 + 1).clamp(max=h - 1), (x0 + 1).clamp(max=w - 1)
+        ly, lx = (fy - y0).view(1, H, 1, 1), (fx - x0).view(1, 1, W, 1)
+        top = xc[:, y0][:, :, x0] + (xc[:, y0][:, :, x1] - xc[:, y0][:, :, x0]) * lx
+        bot = xc[:, y1][:, :, x0] + (xc[:, y1][:, :, x1] - xc[:, y1][:, :, x0]) * lx
+        up = top + (bot - top) * ly
+        return up, torch.sigmoid(up)
+
     # ---- real-data input: the CPU oracle's restatement of get_paired_input
     def paired_input(self, cartoon, sketch, out_hw, seed=0, dequantize=True):
         from oracle import input_oracle
@@ -376,7 +413,7 @@ class TorchOps(OpsBase):
             g_h = g_pre @ kh.t() + g_pass
         return g_pre_all
 
-    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None):
+    def lstm_cell_fwd(self, gates, gates2, grow, c_prev, h_prev, ids, t, P, out_h=None, save_pre=True):
         pre = gates.clone()
         if gates2 is not None:
             pre = pre + gates2
@@ -386,7 +423,7 @@ class TorchOps(OpsBase):
         c = c_prev * torch.sigmoid(f + 1.0) + torch.sigmoid(i) * torch.tanh(j)
         h = torch.tanh(c) * torch.sigmoid(o)
         m = (ids[:, t] != 0).repeat_interleave(P)[:, None]
-        return torch.where(m, c, c_prev), self._into(out_h, torch.where(m, h, h_prev)), pre
+        return torch.where(m, c, c_prev), self._into(out_h, torch.where(m, h, h_prev)), (pre if save_pre else None)
 
     def lstm_cell_bwd(self, gc, gh, pre, c_prev, c, ids, t, P, out_gpre=None):
         m = (ids[:, t] != 0).repeat_interleave(P)[:, None]
