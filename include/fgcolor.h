@@ -27,7 +27,7 @@ typedef void* fgc_stream;     /* cudaStream_t */
 
 enum { FGC_OK = 0, FGC_EINVAL = -1, FGC_ECUDA = -2, FGC_EUNSUPPORTED = -3 };
 enum { FGC_F32 = 0, FGC_BF16 = 1 };
-enum { FGC_ACT_NONE = 0, FGC_ACT_LRELU = 1, FGC_ACT_TANH = 2, FGC_ACT_MIU = 3 };
+enum { FGC_ACT_NONE = 0, FGC_ACT_LRELU = 1, FGC_ACT_TANH = 2, FGC_ACT_MIU = 3, FGC_ACT_RELU = 4 /* convolution epilogues only */ };
 
 const char* fgc_last_error(void);
 int fgc_version(void);
@@ -295,6 +295,9 @@ int fgc_maxpool3x3s2(const void* x, int dtype, int N, int H, int W, int C, void*
  * the batch-form size, N = the ORIGINAL batch) */
 int fgc_space_to_batch(const void* x, int dtype, int N, int H, int W, int C, int r, void* y, fgc_stream s);
 int fgc_batch_to_space(const void* x, int dtype, int N, int h, int w, int C, int r, void* y, fgc_stream s);
+/* y[r, c] = c < C ? x[r, c] : 0 for c < Cp, converted to y_dtype: a row operand whose width is not a multiple of 8 bf16
+ * elements (the 500-wide state of the multimodal LSTM) padded to one the 16-byte operand fetches of the tensor path take */
+int fgc_pad_cast_rows(const void* x, int x_dtype, long long R, int C, int Cp, void* y, int y_dtype, fgc_stream s);
 /* tf.image.resize_bilinear(x, [H, W]) (align_corners False, TF-1: source = destination * h/H) of fp32 x [N,h,w,C] into up
  * [N,H,W,C]; sigm (optional) = sigmoid(up) (RMI_model.py:150-151) */
 int fgc_resize_bilinear(const float* x, int N, int h, int w, int C, int H, int W, float* up, float* sigm, fgc_stream s);

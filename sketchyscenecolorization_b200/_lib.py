@@ -138,6 +138,7 @@ SIGNATURES = {
     "fgc_adam_step": [_P, _P, _P, _P, _P, _P, _I, _F, _P, _F, _F, _I, _P],
     "fgc_opt_step": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _P, _I, _P],
     "fgc_affine_act": [_P, _I, _LL, _I, _P, _P, _P, _P, _P, _I, _P, _P],
+    "fgc_pad_cast_rows": [_P, _I, _LL, _I, _I, _P, _I, _P],
     "fgc_maxpool3x3s2": [_P, _I, _I, _I, _I, _I, _P, _P],
     "fgc_space_to_batch": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "fgc_batch_to_space": [_P, _I, _I, _I, _I, _I, _I, _P, _P],

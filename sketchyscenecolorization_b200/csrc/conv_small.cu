@@ -37,6 +37,7 @@ __device__ __forceinline__ float small_act(float v, int act) {
     case FGC_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
     case FGC_ACT_TANH: return tanhf(v);
     case FGC_ACT_MIU: return miu_relu(v);
+    case FGC_ACT_RELU: return fmaxf(v, 0.f);
     default: return v;
   }
 }

@@ -471,6 +471,7 @@ __device__ __forceinline__ float epi_act(float v, int act) {
     case FGC_ACT_LRELU: return v > 0.f ? v : 0.2f * v;
     case FGC_ACT_TANH: return tanhf(v);
     case FGC_ACT_MIU: return miu_relu(v);
+    case FGC_ACT_RELU: return fmaxf(v, 0.f);
     default: return v;
   }
 }
@@ -698,6 +699,10 @@ __global__ void __launch_bounds__(32 * (8 * MT + 2), 1) conv_igemm_kernel(const 
           case FGC_ACT_MIU:
 #pragma unroll
             for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
+            break;
+          case FGC_ACT_RELU:
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = fmaxf(v[q], 0.f);
             break;
           default: break;
         }
@@ -1075,6 +1080,10 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
 #pragma unroll
               for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
               break;
+            case FGC_ACT_RELU:
+#pragma unroll
+              for (int q = 0; q < 32; q++) v[q] = fmaxf(v[q], 0.f);
+              break;
             default: break;
           }
           if (a.pool2) {
@@ -1156,6 +1165,10 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
             case FGC_ACT_MIU:
 #pragma unroll
               for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
+              break;
+            case FGC_ACT_RELU:
+#pragma unroll
+              for (int q = 0; q < 32; q++) v[q] = fmaxf(v[q], 0.f);
               break;
             default: break;
           }
@@ -1518,6 +1531,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * 12, 1) conv_hal
           case FGC_ACT_MIU:
 #pragma unroll
             for (int q = 0; q < 32; q++) v[q] = miu_relu(v[q]);
+            break;
+          case FGC_ACT_RELU:
+#pragma unroll
+            for (int q = 0; q < 32; q++) v[q] = fmaxf(v[q], 0.f);
             break;
           default: break;
         }

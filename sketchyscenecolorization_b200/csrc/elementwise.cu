@@ -948,6 +948,7 @@ __global__ void tapsum_w_kernel(const float* __restrict__ z, long long npix, int
     if (act == FGC_ACT_TANH) acc = tanhf(acc);
     else if (act == FGC_ACT_LRELU) acc = acc > 0.f ? acc : 0.2f * acc;
     else if (act == FGC_ACT_MIU) acc = miu_relu(acc);
+    else if (act == FGC_ACT_RELU) acc = fmaxf(acc, 0.f);
     st1<TO>(y + i, acc);
   }
 }

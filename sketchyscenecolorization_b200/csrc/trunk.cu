@@ -107,6 +107,15 @@ __global__ void space_batch_kernel(const T* __restrict__ src, int N, int h, int 
   }
 }
 
+template <typename TI, typename TO>
+__global__ void pad_cast_rows_kernel(const TI* __restrict__ x, long long total, int C, int Cp, TO* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Cp;
+    const int c = (int)(i - r * Cp);
+    st1<TO>(y + i, c < C ? ld1<TI>(x + r * C + c) : 0.f);
+  }
+}
+
 // tf.image.resize_bilinear, align_corners=False (TF-1 legacy: in = out * h/H, no half-pixel shift), fp32, and its sigmoid
 __global__ void resize_bilinear_kernel(const float* __restrict__ x, int h, int w, int C, int H, int W, long long total,
                                        float* __restrict__ up, float* __restrict__ sigm) {
@@ -190,6 +199,21 @@ int fgc_batch_to_space(const void* x, int dtype, int N, int h, int w, int C, int
   int e = space_batch(x, dtype, N, h, w, C, r, y, false, as_stream(stream));
   if (e) return e;
   FGC_LAUNCH_CHECK("batch_to_space");
+  return FGC_OK;
+}
+
+int fgc_pad_cast_rows(const void* x, int x_dtype, long long R, int C, int Cp, void* y, int y_dtype, fgc_stream stream) {
+  FGC_REQUIRE(x && y && R > 0 && C > 0 && Cp >= C, "pad_cast_rows: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  const long long total = R * Cp;
+  const int grid = ew_grid(total, 256);
+  if (x_dtype == FGC_F32 && y_dtype == FGC_F32) pad_cast_rows_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, total, C, Cp, (float*)y);
+  else if (x_dtype == FGC_F32 && y_dtype == FGC_BF16) pad_cast_rows_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((const float*)x, total, C, Cp, (__nv_bfloat16*)y);
+  else if (x_dtype == FGC_BF16 && y_dtype == FGC_F32) pad_cast_rows_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, total, C, Cp, (float*)y);
+  else if (x_dtype == FGC_BF16 && y_dtype == FGC_BF16) pad_cast_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, total, C, Cp, (__nv_bfloat16*)y);
+  else { set_error("pad_cast_rows: bad dtypes"); return FGC_EINVAL; }
+  count_launch();
+  FGC_LAUNCH_CHECK("pad_cast_rows");
   return FGC_OK;
 }
 

@@ -489,6 +489,12 @@ class CudaOps(OpsBase):
               "affine_act")
         return y
 
+    def pad_cast_rows(self, x, cp, dtype):
+        R, Cc = x.shape
+        y = self._empty((R, cp), dtype)
+        check(self.lib.fgc_pad_cast_rows(self._p(x), self._dt(x), R, Cc, cp, self._p(y), self._dt(y), self._s()), "pad_cast_rows")
+        return y
+
     def maxpool3x3s2(self, x):
         N, H, W, Cc = x.shape
         y = self._empty((N, (H + 1) // 2, (W + 1) // 2, Cc), x.dtype)

@@ -18,7 +18,7 @@ Conventions
 """
 from __future__ import annotations
 
-ACT_NONE, ACT_LRELU, ACT_TANH, ACT_MIU = 0, 1, 2, 3
+ACT_NONE, ACT_LRELU, ACT_TANH, ACT_MIU, ACT_RELU = 0, 1, 2, 3, 4     # ACT_RELU: convolution epilogues only
 
 
 class OpsBase:
@@ -185,6 +185,10 @@ class OpsBase:
     def affine_act(self, x, scale, shift, res=None, rscale=None, rshift=None, relu=False):
         """act(x*scale[c] + shift[c] + r) with r = 0 | res | res*rscale[c] + rshift[c]: stored-moment batch norm
         (deeplab_model._batch_norm, :213-233), the residual sum and relu of _bottleneck_residual (:237-264)."""
+        raise NotImplementedError
+
+    def pad_cast_rows(self, x, cp, dtype):
+        """[R, C] -> [R, cp] (cp >= C, zero columns appended) in `dtype`."""
         raise NotImplementedError
 
     def maxpool3x3s2(self, x):

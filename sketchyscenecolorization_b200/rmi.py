@@ -9,8 +9,10 @@ How it sits on the kernels of the colorization path:
   * every contraction is `ops.conv_fwd` (1x1 / 3x3 / 7x7, stride 1 / 2; the LSTM and projection matrices as k = 1 rows);
   * tf.nn.atrous_conv2d(rate r) is a plain SAME convolution in the space-to-batch form -- as inside TensorFlow -- and since
     everything else in a residual unit is per pixel, groups 4 and 5 run WHOLLY in that form: one permutation in, one out;
-  * the stored-moment batch norm is an affine map per channel; it, the relu and the residual sum are one pass
-    (`ops.affine_act`), with the shortcut's own batch norm folded into the same pass;
+  * the stored-moment batch norm is an affine map per channel.  Where a relu follows directly (stem, block_1, block_2) its
+    scale is folded into the filter once per set of weights and shift + relu ride in the convolution's epilogue; at the end
+    of a unit the last batch norm, the shortcut's own batch norm, the residual sum and the relu are one pass
+    (`ops.affine_act`);
   * the multimodal LSTM runs over N*96*96 rows x up to 15 steps.  As in text_fusion.py its input product is split by blocks of
     the kernel: [visual, spatial] rows once, [word embedding, l2n(word-LSTM output)] once per (sample, step), and only the
     [rows, 500] x [500, 2000] recurrent product per step -- 9.2 instead of 64.7 GMAC per picture and step.  Steps past a
@@ -21,6 +23,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .ops_base import ACT_RELU
 from .params import RMI_FILTERS, RMI_UNITS, ParamStore, rmi_unit_plan, rmi_vars
 from .text_fusion import _mat, _op, _word_lstm_fwd
 
@@ -81,21 +84,35 @@ class RMIModel:
                 scale = P[s + "/gamma"].double() / torch.sqrt(P[s + "/variance"].double() * inv + BN_EPS)
                 shift = P[s + "/beta"].double() - P[s + "/mean"].double() * inv * scale
                 bn[s] = (scale.to(self.store.dtype).contiguous(), shift.to(self.store.dtype).contiguous())
+        # convolution -> batch norm -> relu: the scale goes into the filter (HWIO: per output channel), the shift is the bias
+        wf = {}
+        for s in bn:
+            conv = (s[:-len("/bn")] + "/conv") if s.endswith("/bn") else s.replace("/bn_conv1", "/conv1")
+            if s.endswith("/block_1/bn") or s.endswith("/block_2/bn") or s.endswith("/bn_conv1"):
+                wf[conv] = (P[conv + "/DW"].double() * bn[s][0].double()).to(self.store.dtype).contiguous()
         d = self.dims
         km = P["text_sketchyscene/mLSTM/lstm_cell/kernel"]
         o = d["v_emb"] + d["w_emb"] + d["w_rnn"]
         k_pos = torch.cat([km[0:d["v_emb"]], km[o:o + 8]], 0).contiguous()
-        self._folded = dict(bn=bn, k_pos=k_pos, spatial={})
+        # recurrent rows of the mLSTM kernel, zero rows appended up to a multiple of 8: a bf16 operand row of 500 elements is
+        # not 16-byte aligned, and the tensor path's operand fetches fall back to 2-byte loads on it (14.6 ms instead of
+        # 1.4 ms per step at 32 x 96 x 96 rows, profiles/r2p_prof_rmi.log)
+        Dm = d["m_rnn"]
+        Dp = (Dm + 7) // 8 * 8
+        kh = km[o + 8:]
+        kh_p = torch.cat([kh, kh.new_zeros(Dp - Dm, kh.shape[1])], 0).contiguous() if Dp != Dm else kh
+        wo = P["text_sketchyscene/m_lstm_output_projection/DW"]
+        wo_p = torch.cat([wo, wo.new_zeros(1, 1, Dp - Dm, wo.shape[3])], 2).contiguous() if Dp != Dm else wo
+        self._folded = dict(bn=bn, wf=wf, k_pos=k_pos, kh_p=kh_p, wo_p=wo_p, Dp=Dp, spatial={})
         return self._folded
 
     # ---- trunk: DeepLab._build_model (:65-107)
     def _unit(self, x, scope, cin, cout, stride, bn):
         """_bottleneck_residual (:237-264); x is already in the batch form of the group's dilation."""
         ops, P = self.ops, self.store.p
-        h = ops.conv_fwd([(x, False)], P[scope + "/block_1/conv/DW"], None, stride=stride)
-        h = ops.affine_act(h, *bn[scope + "/block_1/bn"], relu=True)
-        h = ops.conv_fwd([(h, False)], P[scope + "/block_2/conv/DW"], None)
-        h = ops.affine_act(h, *bn[scope + "/block_2/bn"], relu=True)
+        wf = self._folded["wf"]
+        h = ops.conv_fwd([(x, False)], wf[scope + "/block_1/conv"], bn[scope + "/block_1/bn"][1], stride=stride, act=ACT_RELU)
+        h = ops.conv_fwd([(h, False)], wf[scope + "/block_2/conv"], bn[scope + "/block_2/bn"][1], act=ACT_RELU)
         h = ops.conv_fwd([(h, False)], P[scope + "/block_3/conv/DW"], None)
         if cin != cout:
             sc = ops.conv_fwd([(x, False)], P[scope + "/block_add/conv/DW"], None, stride=stride)
@@ -106,9 +123,9 @@ class RMIModel:
     def trunk(self, im_nhwc):
         """[N,H,W,3] (activation dtype) -> `intermediate_feat` [N,H/8,W/8,filters[4]]."""
         ops, P = self.ops, self.store.p
-        bn = self._prepare()["bn"]
-        x = ops.conv_fwd([(im_nhwc, False)], P["ResNet/group_1/conv1/DW"], None, stride=2)
-        x = ops.affine_act(x, *bn["ResNet/group_1/bn_conv1"], relu=True)
+        pre = self._prepare()
+        bn = pre["bn"]
+        x = ops.conv_fwd([(im_nhwc, False)], pre["wf"]["ResNet/group_1/conv1"], bn["ResNet/group_1/bn_conv1"][1], stride=2, act=ACT_RELU)
         x = ops.maxpool3x3s2(x)
         cur = 1                                               # dilation whose batch form x is in
         for scope, cin, cout, stride, rate in rmi_unit_plan(self.units, self.filters):
@@ -159,13 +176,16 @@ class RMIModel:
         lang, _ = ops.l2norm_rows_fwd(hw_all[1:].view(T * N, Dw))                                 # :173 (rows past the length are never read)
         g_row = ops.conv_fwd([(e_rows, False), (_op(ops, lang), False)], _mat(km[V:V + E + L]), None, out_dtype=f32).view(T, N, 4 * Dm)
         # mLSTM recurrence (:188-200): the only per-step product is h @ kernel[-Dm:]
-        kh = km[V + E + L + 8:]
+        Dp, odt = pre["Dp"], ops.act_dtype
+
+        def rows_op(x):          # [R, Dm] fp32 -> matrix-product operand, padded to an aligned width
+            return ops.pad_cast_rows(x, Dp, odt).view(R, 1, 1, Dp) if Dp != Dm else _op(ops, x)
         c, h = ops.zeros_f32((R, Dm)), ops.zeros_f32((R, Dm))
         for t in range(steps):
-            ga = ops.conv_fwd([(_op(ops, h), False)], _mat(kh), None, out_dtype=f32).view(R, 4 * Dm)
+            ga = ops.conv_fwd([(rows_op(h), False)], _mat(pre["kh_p"]), None, out_dtype=f32).view(R, 4 * Dm)
             c, h, _ = ops.lstm_cell_fwd(ga, g_pos, g_row[t], c, h, live, t, Pn, save_pre=False)
         m = ops.atanh_relu_fwd(h)                                                                 # :277-279
-        pred = ops.conv_fwd([(_op(ops, m).view(N, fh, fw, Dm), False)], P[p + "/m_lstm_output_projection/DW"],
+        pred = ops.conv_fwd([(rows_op(m).view(N, fh, fw, Dp), False)], pre["wo_p"],
                             P[p + "/m_lstm_output_projection/biases"], out_dtype=f32)             # :284-285
         up, sigm = ops.resize_bilinear_sigmoid(pred, H, W)                                        # :150-151
         return pred, up, sigm

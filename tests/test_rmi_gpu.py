@@ -89,13 +89,50 @@ def test_resize_bilinear_sigmoid(env, case):
 def test_trunk_convolutions(env, case):
     cu, cub, ref, dev = env["cu"], env["cub"], env["ref"], env["dev"]
     N, H, W, cin, k, stride, cout = case
+    from sketchyscenecolorization_b200.ops_base import ACT_NONE, ACT_RELU
     x = rnd((N, H, W, cin), 10, dev)
     w = rnd((k, k, cin, cout), 11, dev, 1.0 / np.sqrt(k * k * cin))
-    want = ref.conv_fwd([(x, False)], w, None, stride=stride)
-    got = cu.conv_fwd([(x.float().contiguous(), False)], w.float().contiguous(), None, stride=stride)
-    assert got.shape == want.shape and relerr(got, want) <= 1e-4
-    gotb = cub.conv_fwd([(x.bfloat16().contiguous(), False)], w.float().contiguous(), None, stride=stride)
-    assert relerr(gotb, want) <= 3e-2
+    b = rnd((cout,), 12, dev, 0.3)
+    for bias, act in ((None, ACT_NONE), (b, ACT_RELU)):          # plain, and batch-norm shift + relu in the epilogue
+        want = ref.conv_fwd([(x, False)], w, bias, stride=stride, act=act)
+        fb = None if bias is None else bias.float().contiguous()
+        for impl in (0, 1, 2):                                    # product routing, CUDA-core checker, gather-only tensor path
+            cu.lib.fgc_set_conv_impl(1 if impl == 1 else 0)
+            cu.lib.fgc_set_conv_flags(0 if impl == 2 else 1, 0 if impl == 2 else 1)
+            try:
+                got = cu.conv_fwd([(x.float().contiguous(), False)], w.float().contiguous(), fb, stride=stride, act=act)
+                gotb = cub.conv_fwd([(x.bfloat16().contiguous(), False)], w.float().contiguous(), fb, stride=stride, act=act)
+                torch.cuda.synchronize()
+            finally:
+                cu.lib.fgc_set_conv_impl(0)
+                cu.lib.fgc_set_conv_flags(1, 1)
+            assert got.shape == want.shape and relerr(got, want) <= 1e-4
+            if act == ACT_RELU:
+                assert got.min().item() >= 0.0
+            assert relerr(gotb, want) <= 3e-2
+
+
+@pytest.mark.parametrize("case", [(300, 500, 504), (17, 10, 16), (5, 8, 8)], ids=lambda c: "x".join(map(str, c)))
+def test_pad_cast_rows(env, case):
+    cu, dev = env["cu"], env["dev"]
+    R, C, Cp = case
+    x = rnd((R, C), 13, dev).float().contiguous()
+    for dt in (torch.float32, torch.bfloat16):
+        y = cu.pad_cast_rows(x, Cp, dt)
+        assert y.shape == (R, Cp) and y.dtype == dt
+        assert torch.equal(y[:, :C], x.to(dt)) and (y[:, C:] == 0).all()
+
+
+def test_recurrent_product_padded_operand(env):
+    """The mLSTM's per-step product with the 500-wide state padded to 504 columns (zero rows appended to the kernel)."""
+    cub, ref, dev = env["cub"], env["ref"], env["dev"]
+    h = rnd((1000, 500), 14, dev, 0.5)
+    k = rnd((500, 2000), 15, dev, 0.05)
+    want = h @ k
+    hp = cub.pad_cast_rows(h.float().contiguous(), 504, torch.bfloat16).view(1000, 1, 1, 504)
+    kp = torch.cat([k, k.new_zeros(4, 2000)], 0).float().contiguous().view(1, 1, 504, 2000)
+    got = cub.conv_fwd([(hp, False)], kp, None, out_dtype=torch.float32).view(1000, 2000)
+    assert relerr(got, want) <= 2e-2
 
 
 def _randomise_moments(P, seed):

@@ -14,7 +14,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-from sketchyscenecolorization_b200.ops_base import ACT_LRELU, ACT_MIU, ACT_NONE, ACT_TANH, OpsBase
+from sketchyscenecolorization_b200.ops_base import ACT_LRELU, ACT_MIU, ACT_NONE, ACT_RELU, ACT_TANH, OpsBase
 
 
 def _same_pad(size, k, stride):
@@ -38,6 +38,8 @@ def _act(y, act):
         return torch.tanh(y)
     if act == ACT_MIU:
         return (y + torch.sqrt(0.09 + y * y)) / 2
+    if act == ACT_RELU:
+        return torch.relu(y)
     return y
 
 
@@ -321,6 +323,11 @@ class TorchOps(OpsBase):
         if res is not None:
             y = y + (self._c(res) if rscale is None else self._c(res) * self._c(rscale) + self._c(rshift))
         return (torch.relu(y) if relu else y).to(x.dtype)
+
+    def pad_cast_rows(self, x, cp, dtype):
+        y = torch.zeros(x.shape[0], cp, dtype=self._od(dtype), device=x.device)
+        y[:, :x.shape[1]] = x
+        return y
 
     def maxpool3x3s2(self, x):
         xn = self._c(x).permute(0, 3, 1, 2)
