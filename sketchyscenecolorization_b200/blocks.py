@@ -50,14 +50,18 @@ class WeightView:
             self.gwbar[scope] = self.ops.zeros_f32(w.shape)
         return self.gwbar[scope], db
 
-    def finish_backward(self):
-        """Push dL/dW_bar through the spectral normalisation (sn.py) into the raw weight gradients."""
-        for scope, gwb in self.gwbar.items():
+    def finish_backward(self, prefixes=None):
+        """Push dL/dW_bar through the spectral normalisation (sn.py) into the raw weight gradients -- of every weight, or
+        (prefixes given) of the scopes under them only: a unit whose backward pass is over can be finished at once, which
+        is what lets its slice of the flat gradient buffer go to the all-reduce while the earlier units still run."""
+        for scope in list(self.gwbar):
+            if prefixes is not None and not any(scope == q or scope.startswith(q + "/") for q in prefixes):
+                continue
+            gwb = self.gwbar.pop(scope)
             w = self.store.p[scope + "/weights"]
             dw = self.store.g[scope + "/weights"]
             self.ops.sn_bwd(gwb.reshape(-1, w.shape[-1]), w.reshape(-1, w.shape[-1]), self.sn_ctx[scope],
                             dw.reshape(-1, w.shape[-1]))
-        self.gwbar = {}
 
     def commit_u(self):
         """u <- u' (the SPECTRAL_NORM_UPDATE_OPS run as a control dependency of the G step,

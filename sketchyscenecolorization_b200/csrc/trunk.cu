@@ -30,6 +30,19 @@ int ew_grid(long long work, int threads);
     }                                                                                 \
   } while (0)
 
+// V per-channel parameters starting at a multiple of V (16-byte loads: the per-element scalar loads made this pass L1-bound)
+template <int V> __device__ __forceinline__ void ldp(const float* __restrict__ p, float (&v)[kMaxV]) {
+  if constexpr (V == 8) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else if constexpr (V == 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  } else {
+    v[0] = __ldg(p);
+  }
+}
+
 // y = act(x*scale[c] + shift[c] + (res ? res*rscale[c] + rshift[c] : 0)); rscale == NULL: the residual is added as it is
 template <typename T, int V>
 __global__ void affine_act_kernel(const T* __restrict__ x, long long nvec, int C, const float* __restrict__ scale,
@@ -38,13 +51,16 @@ __global__ void affine_act_kernel(const T* __restrict__ x, long long nvec, int C
   const int CV = C / V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     const int c0 = (int)(i % CV) * V;
-    float a[kMaxV], r[kMaxV];
+    float a[kMaxV], r[kMaxV], sc[kMaxV], sh[kMaxV], rs[kMaxV], rt[kMaxV];
     ldv<T, V>(x + i * V, a);
+    ldp<V>(scale + c0, sc);
+    ldp<V>(shift + c0, sh);
     if (res) ldv<T, V>(res + i * V, r);
+    if (rscale) { ldp<V>(rscale + c0, rs); ldp<V>(rshift + c0, rt); }
 #pragma unroll
     for (int k = 0; k < V; k++) {
-      float v = fmaf(a[k], __ldg(scale + c0 + k), __ldg(shift + c0 + k));
-      if (res) v += rscale ? fmaf(r[k], __ldg(rscale + c0 + k), __ldg(rshift + c0 + k)) : r[k];
+      float v = fmaf(a[k], sc[k], sh[k]);
+      if (res) v += rscale ? fmaf(r[k], rs[k], rt[k]) : r[k];
       a[k] = relu ? fmaxf(v, 0.f) : v;
     }
     stv<T, V>(y + i * V, a);
@@ -115,6 +131,19 @@ __global__ void pad_cast_rows_kernel(const TI* __restrict__ x, long long total, 
     st1<TO>(y + i, c < C ? ld1<TI>(x + r * C + c) : 0.f);
   }
 }
+// fp32 -> bf16, C and Cp multiples of 4: four columns per thread (16-byte load, 8-byte store)
+__global__ void pad_cast_rows_f32_bf16_vec4_kernel(const float* __restrict__ x, long long total4, int C4, int Cp4, uint2* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Cp4;
+    const int c = (int)(i - r * Cp4);
+    uint2 o = make_uint2(0u, 0u);
+    if (c < C4) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + r * C4 + c);
+      o = make_uint2(bf16x2_bits(v.x, v.y), bf16x2_bits(v.z, v.w));
+    }
+    y[i] = o;
+  }
+}
 
 // tf.image.resize_bilinear, align_corners=False (TF-1 legacy: in = out * h/H, no half-pixel shift), fp32, and its sigmoid
 __global__ void resize_bilinear_kernel(const float* __restrict__ x, int h, int w, int C, int H, int W, long long total,
@@ -152,6 +181,7 @@ int fgc_affine_act(const void* x, int dtype, long long M, int C, const float* sc
   cudaStream_t s = as_stream(stream);
   int vec = vmin(vec_width(x, C, dtype), vec_width(y, C, dtype));
   if (res) vec = vmin(vec, vec_width(res, C, dtype));
+  if (!aligned16(scale) || !aligned16(shift) || (rscale && (!aligned16(rscale) || !aligned16(rshift)))) vec = 1;
   FGC_DISPATCH_TV(dtype, vec, T, V, {
     long long nv = M * C / V;
     affine_act_kernel<T, V><<<ew_grid(nv, 256), 256, 0, s>>>((const T*)x, nv, C, scale, shift, (const T*)res, rscale, rshift, relu, (T*)y);
@@ -207,7 +237,10 @@ int fgc_pad_cast_rows(const void* x, int x_dtype, long long R, int C, int Cp, vo
   cudaStream_t s = as_stream(stream);
   const long long total = R * Cp;
   const int grid = ew_grid(total, 256);
-  if (x_dtype == FGC_F32 && y_dtype == FGC_F32) pad_cast_rows_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, total, C, Cp, (float*)y);
+  if (x_dtype == FGC_F32 && y_dtype == FGC_BF16 && C % 4 == 0 && Cp % 4 == 0 && aligned16(x) && aligned8(y)) {
+    const long long total4 = total / 4;
+    pad_cast_rows_f32_bf16_vec4_kernel<<<ew_grid(total4, 256), 256, 0, s>>>((const float*)x, total4, C / 4, Cp / 4, (uint2*)y);
+  } else if (x_dtype == FGC_F32 && y_dtype == FGC_F32) pad_cast_rows_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, total, C, Cp, (float*)y);
   else if (x_dtype == FGC_F32 && y_dtype == FGC_BF16) pad_cast_rows_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((const float*)x, total, C, Cp, (__nv_bfloat16*)y);
   else if (x_dtype == FGC_BF16 && y_dtype == FGC_F32) pad_cast_rows_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, total, C, Cp, (float*)y);
   else if (x_dtype == FGC_BF16 && y_dtype == FGC_BF16) pad_cast_rows_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, total, C, Cp, (__nv_bfloat16*)y);

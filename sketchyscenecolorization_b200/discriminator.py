@@ -55,8 +55,11 @@ class Discriminator:
         wv.cache[p] = (wbar.view(1, 1, *w.shape), self.store.p[p + "/biases"])
         return wv.cache[p]
 
-    def backward(self, g_disc, g_logits, ctx, need_x_grad):
-        """Returns dL/d(img) (NHWC) if need_x_grad else None; accumulates weight grads when wv.need_wgrad."""
+    def backward(self, g_disc, g_logits, ctx, need_x_grad, grads_ready=None):
+        """Returns dL/d(img) (NHWC) if need_x_grad else None; accumulates weight grads when wv.need_wgrad.
+        grads_ready(lo, hi): optional; called as soon as the flat-gradient range [lo, hi) is final (the heads and unit 4 after
+        unit 4's backward pass, then unit 3, unit 2), so that a data-parallel trainer can start its all-reduce under the
+        remaining units -- the early ones at 192 x 192 / 96 x 96 are most of the pass and hold almost no parameters."""
         ops, st, p = self.ops, self.store, "discriminator"
         wv = ctx["wv"]
         nw = wv.need_wgrad
@@ -84,8 +87,14 @@ class Discriminator:
         X = ctx["X"]
         g_X = [None] * 4
         for u in (4, 3, 2, 1):
-            g, g_X[u - 1] = blocks.enc_block_bwd(ops, wv, "%s/mru_conv_unit_t_%d_layer_0" % (p, u), g, ctx["ectx"][u - 1],
+            scope = "%s/mru_conv_unit_t_%d_layer_0" % (p, u)
+            g, g_X[u - 1] = blocks.enc_block_bwd(ops, wv, scope, g, ctx["ectx"][u - 1],
                                                  None, "prelu", need_x_grad=need_x_grad, need_ht_grad=True)
+            if grads_ready is not None and nw and u >= 2:
+                wv.finish_backward([scope] + ([p + "/Conv_1", p + "/fully_connected"] if u == 4 else []))
+                lo = st.offsets[scope + "/norm_activation_in/prelu/param"]            # first variable of the unit
+                hi = st.n_flat if u == 4 else st.offsets["%s/mru_conv_unit_t_%d_layer_0/norm_activation_in/prelu/param" % (p, u + 1)]
+                grads_ready(lo, hi)
         g = blocks.norm_act_bwd(ops, st, p + "/Conv", g, ctx["c0"], None, "prelu", nw)
         w, _ = wv.get(p + "/Conv")
         if nw:

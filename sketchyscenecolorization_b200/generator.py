@@ -71,8 +71,10 @@ class Generator:
         return out, ctx
 
     # ------------------------------------------------------------------
-    def backward(self, g_out, ctx):
-        """g_out: dL/d(image) NHWC.  Accumulates all generator weight gradients into store.grad."""
+    def backward(self, g_out, ctx, grads_ready=None):
+        """g_out: dL/d(image) NHWC.  Accumulates all generator weight gradients into store.grad.
+        grads_ready(lo, hi): optional; called when the flat-gradient range [lo, hi) is final -- noise FC + decoder + head
+        (70 % of the parameters) after the decoder, the caption encoder after its BPTT, encoder unit 4 after its backward pass."""
         ops, st, p = self.ops, self.store, "generator"
         wv, labels = ctx["wv"], ctx["labels"]
         plan = decoder_plan(self.size)
@@ -104,8 +106,13 @@ class Generator:
         ops.conv_wgrad([(ctx["nz"], False)], g_fc, st.g[p + "/fully_connected/weights"].view(1, 1, *wfc.shape),
                        st.g[p + "/fully_connected/biases"])
         del g_fc
+        off = st.offsets
+        if grads_ready is not None:
+            grads_ready(off[p + "/fully_connected/weights"], st.n_flat)
         # text fusion
         g_e4 = text_fusion.text_fusion_bwd(ops, st, g_ht, ctx["tctx"]) if self.lstm_hybrid else g_ht
+        if grads_ready is not None and p + "/TextLSTM/embedding" in off:
+            grads_ready(off[p + "/TextLSTM/embedding"], off[p + "/fully_connected/weights"])
         # encoder
         g_cur = blocks.norm_act_bwd(ops, st, p + "/mru_conv_unit_last_norm", g_e4, ctx["c_last"], labels, "cbn")
         for u in (4, 3, 2, 1):
@@ -113,5 +120,8 @@ class Generator:
                 ops.add_(g_cur, g_enc[u])
             g_cur, _ = blocks.enc_block_bwd(ops, wv, "%s/mru_conv_unit_t_%d_layer_0" % (p, u), g_cur, ctx["ectx"][u - 1],
                                             labels, "cbn", need_x_grad=False, need_ht_grad=True)
+            if grads_ready is not None and u == 4:
+                first = "%s/mru_conv_unit_t_4_layer_0/norm_activation_in/offset" % p
+                grads_ready(off[first], off.get(p + "/TextLSTM/embedding", off[p + "/fully_connected/weights"]))
         ops.add_(g_cur, g_enc[0])
         ops.conv_wgrad([(ctx["s0"], False)], g_cur, *wv.grads(p + "/Conv"), stride=2)

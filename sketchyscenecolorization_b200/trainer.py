@@ -13,6 +13,7 @@ followed by `average_gradients` (NCCL all-reduce when world_size > 1, graph_sing
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -105,9 +106,10 @@ class FgColorModel:
         return st['out']
 
     # ---- loss_d and dL/dtheta_D
-    def d_step_grads(self, batch):
+    def d_step_grads(self, batch, grads_ready=None):
         """batch: dict(sketch, images, images_d [N,3,H,W] fp32; cls, cls_d int32 [N]; text host [N,15]; noise [N,256]).
-        Leaves dL_d/dtheta_D in dstore.grad; returns dict of fp32 0-d loss tensors (total under 'loss')."""
+        Leaves dL_d/dtheta_D in dstore.grad; returns dict of fp32 0-d loss tensors (total under 'loss').
+        grads_ready(lo, hi): see Discriminator.backward (MRU networks; the others finish their gradients at the end)."""
         ops = self.ops
         if self.block_type != 'MRU':
             return self._d_step_grads_pairs(batch)
@@ -132,7 +134,7 @@ class FgColorModel:
         g_d[N:].copy_(g_fd)
         g_l = torch.zeros_like(lg)
         g_l[:N].copy_(g_rl)
-        self.D.backward(g_d, g_l, dctx, need_x_grad=False)
+        self.D.backward(g_d, g_l, dctx, need_x_grad=False, grads_ready=grads_ready)
         del dctx
         wv.finish_backward()
         reg = ops.reg_loss(self.dstore)                                  # :571
@@ -159,7 +161,7 @@ class FgColorModel:
         return dict(loss=l_real + l_fake + l_ac + reg, gan=l_real + l_fake, ac=l_ac, reg=reg)
 
     # ---- loss_g and dL/dtheta_G (+ SN u update)
-    def g_step_grads(self, batch):
+    def g_step_grads(self, batch, grads_ready=None):
         ops = self.ops
         self.gstore.grad.zero_()
         fake, gctx = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=True)
@@ -175,7 +177,10 @@ class FgColorModel:
         target = ops.nchw_to_nhwc(batch["images"])
         l_l1, g_l1 = ops.smooth_l1(target, fake, 100.0)                  # :552-555,575
         ops.add_(g_fake, g_l1)
-        self.G.backward(g_fake, gctx)
+        if grads_ready is not None and self.block_type == 'MRU':
+            self.G.backward(g_fake, gctx, grads_ready=grads_ready)
+        else:
+            self.G.backward(g_fake, gctx)
         wv.commit_u()                                                    # :178-180,208-210
         reg = ops.reg_loss(self.gstore)
         return dict(loss=l_gan + l_ac + l_l1 + reg, gan=l_gan, ac=l_ac, l1=l_l1, reg=reg)
@@ -194,8 +199,10 @@ class FgColorTrainer:
     G_KEYS = ("sketch", "images", "cls", "text", "noise")
 
     def __init__(self, model, *, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=None, world_size=1,
-                 use_cuda_graphs=False, optimizer='Adam'):
+                 use_cuda_graphs=False, optimizer='Adam', overlap_allreduce=None):
         self.m, self.lr_g, self.lr_d, self.max_iter = model, lr_g, lr_d, max_iter
+        # gradient averaging started bucket by bucket under the backward pass (FGC_OVERLAP_ALLREDUCE=0: one all-reduce at its end)
+        self.overlap = (os.environ.get("FGC_OVERLAP_ALLREDUCE", "1") != "0") if overlap_allreduce is None else bool(overlap_allreduce)
         self.optimizer = optimizer.lower()                    # graph_single.get_optimizer (:584-593)
         for store in (model.gstore, model.dstore):
             if store is not None and store.optimizer != self.optimizer:
@@ -216,6 +223,38 @@ class FgColorTrainer:
                 dist.all_reduce(store.grad, op=dist.ReduceOp.SUM, group=self.pg)
                 store.grad.mul_(1.0 / self.world)
 
+    class _Buckets:
+        """The same average, started piecewise: ready(lo, hi) launches the all-reduce of grad[lo:hi] asynchronously (NCCL: on
+        its own stream, ordered after everything enqueued so far -- inside a captured step a parallel branch of the graph) as
+        soon as the backward pass has finished that range (deep layers first: they hold most parameters and finish first);
+        finish() sends whatever was not announced and joins.  Every rank issues the same collectives in the same order."""
+
+        def __init__(self, trainer, store):
+            import torch.distributed as dist
+            self.dist, self.tr, self.store = dist, trainer, store
+            self.avg = dist.get_backend(trainer.pg) == "nccl"
+            self.works, self.done = [], []
+
+        def ready(self, lo, hi):
+            if hi <= lo:
+                return
+            t = self.store.grad[lo:hi]
+            op = self.dist.ReduceOp.AVG if self.avg else self.dist.ReduceOp.SUM
+            self.works.append((self.dist.all_reduce(t, op=op, group=self.tr.pg, async_op=True), t))
+            self.done.append((lo, hi))
+
+        def finish(self):
+            pos = 0
+            for lo, hi in sorted(self.done):
+                assert lo >= pos, "overlapping gradient buckets"
+                self.ready(pos, lo)
+                pos = hi
+            self.ready(pos, self.store.n_flat)
+            for w, t in self.works:
+                w.wait()
+                if not self.avg:
+                    t.mul_(1.0 / self.tr.world)
+
     # ---- eager steps
     def _apply(self, store, lr, lr_dev):
         if self.optimizer == 'adam':
@@ -224,19 +263,21 @@ class FgColorTrainer:
             self.m.ops.optimizer_step(store, self.optimizer, lr, lr_dev=lr_dev)
 
     def _d_eager(self, batch, lr_dev=None):
+        bk = self._Buckets(self, self.m.dstore) if self.world > 1 and self.overlap else None
         with _Range("fgc.d_step.forward_backward"):
-            out = self.m.d_step_grads(batch)
+            out = self.m.d_step_grads(batch, grads_ready=bk.ready) if bk else self.m.d_step_grads(batch)
         with _Range("fgc.d_step.allreduce"):
-            self._allreduce(self.m.dstore)
+            bk.finish() if bk else self._allreduce(self.m.dstore)
         with _Range("fgc.d_step.optimizer"):
             self._apply(self.m.dstore, self.lr_d * lr_decay(self.counter, self.max_iter), lr_dev)
         return out
 
     def _g_eager(self, batch, lr_dev=None):
+        bk = self._Buckets(self, self.m.gstore) if self.world > 1 and self.overlap else None
         with _Range("fgc.g_step.forward_backward"):
-            out = self.m.g_step_grads(batch)
+            out = self.m.g_step_grads(batch, grads_ready=bk.ready) if bk else self.m.g_step_grads(batch)
         with _Range("fgc.g_step.allreduce"):
-            self._allreduce(self.m.gstore)
+            bk.finish() if bk else self._allreduce(self.m.gstore)
         with _Range("fgc.g_step.optimizer"):
             self._apply(self.m.gstore, self.lr_g * lr_decay(self.counter, self.max_iter), lr_dev)
         return out

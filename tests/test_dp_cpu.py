@@ -82,51 +82,45 @@ def test_two_rank_gloo_allreduce_matches_mean_of_shard_gradients(tmp_path):
     assert (m.dstore.grad - r0["dg"]).abs().max().item() < 1e-12
 
 
-def test_snapshot_round_trip_reference_layout(tmp_path):
-    from sketchyscenecolorization_b200 import checkpoint
-    m = _make_model(torch.float32)        # snapshots hold fp32 (the product's master-weight type)
-    m.dstore.adam_v.uniform_(0, 1)
-    m.gstore.adam_t, m.dstore.adam_t = 7, 9
-    ck = str(tmp_path / "snapshot")
-    prefix = checkpoint.save(m, ck, 99, counter=100)
-    assert os.path.basename(prefix) == "model_99.ckpt-99"
-    for suffix in (".index", ".data-00000-of-00001"):
-        assert os.path.exists(prefix + suffix)
-    assert 'model_checkpoint_path: "model_99.ckpt-99"' in open(os.path.join(ck, "checkpoint")).read()
-    assert checkpoint.latest_checkpoint(ck) == prefix
-    assert int(os.path.split(prefix)[1].split('-')[1]) + 1 == 100        # iter_from rule, obj_colorization_main.py:62
-    m2 = _make_model(torch.float32)
-    m2.initialize(seed=11)
-    assert checkpoint.restore(m2, prefix) == 100
-    assert torch.equal(m2.gstore.flat, m.gstore.flat) and torch.equal(m2.dstore.flat, m.dstore.flat)
-    for k, v in m.dstore.p.items():       # (alignment padding between variables is not part of a snapshot)
-        o = m.dstore.offsets[k]
-        assert torch.equal(m2.dstore.adam_v[o:o + v.numel()], m.dstore.adam_v[o:o + v.numel()]), k
-    assert (m2.gstore.adam_t, m2.dstore.adam_t) == (7, 9)
-    for k in m.dstore.state:
-        assert torch.equal(m2.dstore.state[k], m.dstore.state[k])
-    checkpoint.save(m, ck, 199, counter=200)
-    assert checkpoint.latest_checkpoint(ck).endswith("model_199.ckpt-199")
-    assert open(os.path.join(ck, "checkpoint")).read().count("all_model_checkpoint_paths") == 2
+def _worker_modes(rank, world, port, out_dir):
+    """The bucketed all-reduce (started under the backward pass) against the single one at its end."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sketchyscenecolorization_b200.trainer import FgColorTrainer
+    res = {}
+    for overlap in (True, False):
+        m = _make_model()
+        tr = FgColorTrainer(m, max_iter=100, process_group=dist.group.WORLD, world_size=world, overlap_allreduce=overlap)
+        seen = []
+        if overlap:
+            orig = tr._Buckets.ready
+
+            def spy(self, lo, hi, _o=orig):
+                seen.append((self.store.n_flat, lo, hi))
+                return _o(self, lo, hi)
+            tr._Buckets.ready = spy
+        tr.d_step(_batch(10 + rank))
+        tr.g_step(_batch(20 + rank))
+        if overlap:
+            tr._Buckets.ready = orig
+        res[overlap] = dict(dg=m.dstore.grad.clone(), gg=m.gstore.grad.clone(), d=m.dstore.flat.clone(), g=m.gstore.flat.clone(),
+                            seen=seen, nd=m.dstore.n_flat, ng=m.gstore.n_flat)
+    torch.save(res, os.path.join(out_dir, "modes%d.pt" % rank))
+    dist.destroy_process_group()
 
 
-def test_num_gpu_relaunches_under_torch_distributed_run(monkeypatch):
-    """`--num_gpu N` (N in-graph towers in the reference) re-launches the same command with one process per GPU."""
-    import sys
-    import obj_colorization_main as M
-    seen = {}
-
-    def fake_execv(exe, cmd):
-        seen["cmd"] = cmd
-        raise SystemExit(0)
-    monkeypatch.setattr(os, "execv", fake_execv)
-    monkeypatch.delenv("WORLD_SIZE", raising=False)
-    try:
-        M.main(["--mode", "train", "--num_gpu", "4", "--batch_size", "64"])
-    except SystemExit:
-        pass
-    cmd = seen["cmd"]
-    assert cmd[0] == sys.executable and cmd[1:3] == ["-m", "torch.distributed.run"]
-    assert cmd[cmd.index("--nproc-per-node") + 1] == "4" and cmd[cmd.index("--master-addr") + 1] == "127.0.0.1"
-    assert cmd[-6:] == ["--mode", "train", "--num_gpu", "4", "--batch_size", "64"] and cmd[-7].endswith("obj_colorization_main.py")
-    assert M.main_procedure.any_rank_true(True) is True and M.main_procedure.shared_string("x") == "x"
+def test_bucketed_allreduce_equals_single_allreduce(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker_modes, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        r = torch.load(tmp_path / ("modes%d.pt" % rank))
+        for k in ("dg", "gg", "d", "g"):
+            assert torch.equal(r[True][k], r[False][k]), k          # elementwise sums: the split does not change a bit
+        seen = r[True]["seen"]
+        # several buckets per network were announced before the end of the backward pass, and together they tile each buffer
+        assert r[True]["nd"] != r[True]["ng"]
+        for n in (r[True]["nd"], r[True]["ng"]):
+            edges = sorted((lo, hi) for nf, lo, hi in seen if nf == n and hi > lo)
+            assert len(edges) >= 3
+            assert edges[0][0] == 0 and edges[-1][1] == n and all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
