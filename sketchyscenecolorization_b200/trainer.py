@@ -105,6 +105,23 @@ class FgColorModel:
         st['graph'].replay()
         return st['out']
 
+    def _weight_view_ahead(self, need_wgrad):
+        """The discriminator's weight view with its spectral normalisation already evaluated -- on a side stream (CUDA
+        operator set, MRU networks), concurrently with the generator's forward pass that every step starts with; join() makes
+        the current stream wait for it.  ~90 launch-latency-bound kernels per step leave the critical path this way."""
+        wv = self.D.new_weight_view(need_wgrad=need_wgrad)
+        if (self.block_type != 'MRU' or not getattr(self.ops, 'supports_cuda_graphs', False) or not torch.cuda.is_available()
+                or os.environ.get("FGC_SN_SIDE_STREAM", "1") == "0"):
+            return wv, (lambda: None)
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        side.wait_stream(main)                      # parameters, `u`, and last step's readers of recycled buffers
+        with torch.cuda.stream(side):
+            self.D.prefetch_weights(wv)
+        return wv, (lambda: main.wait_stream(side))
+
     # ---- loss_d and dL/dtheta_D
     def d_step_grads(self, batch, grads_ready=None):
         """batch: dict(sketch, images, images_d [N,3,H,W] fp32; cls, cls_d int32 [N]; text host [N,15]; noise [N,256]).
@@ -114,8 +131,9 @@ class FgColorModel:
         if self.block_type != 'MRU':
             return self._d_step_grads_pairs(batch)
         self.dstore.grad.zero_()
+        wv, join = self._weight_view_ahead(True)
         fake, _ = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=False)
-        wv = self.D.new_weight_view(need_wgrad=True)
+        join()
         real = ops.nchw_to_nhwc(batch["images_d"])
         # D(real) and D(fake) as ONE pass over the 2N images: the discriminator has no batch statistics (PReLU, per-sample
         # min-max gates, spectral norm), so this equals the reference's two instantiations (graph_single.py:269,271) while
@@ -164,8 +182,9 @@ class FgColorModel:
     def g_step_grads(self, batch, grads_ready=None):
         ops = self.ops
         self.gstore.grad.zero_()
+        wv, join = self._weight_view_ahead(False)
         fake, gctx = self.G.forward(batch["sketch"], batch["text"], batch["cls"], batch["noise"], save=True)
-        wv = self.D.new_weight_view(need_wgrad=False)
+        join()
         if self.block_type != 'MRU':
             fd, fl, fctx = self.D.forward(ops.nchw_to_nhwc(batch["sketch"]), fake, wv)
         else:
@@ -201,8 +220,11 @@ class FgColorTrainer:
     def __init__(self, model, *, lr_g=2e-4, lr_d=1e-4, max_iter=100000, process_group=None, world_size=1,
                  use_cuda_graphs=False, optimizer='Adam', overlap_allreduce=None):
         self.m, self.lr_g, self.lr_d, self.max_iter = model, lr_g, lr_d, max_iter
-        # gradient averaging started bucket by bucket under the backward pass (FGC_OVERLAP_ALLREDUCE=0: one all-reduce at its end)
-        self.overlap = (os.environ.get("FGC_OVERLAP_ALLREDUCE", "1") != "0") if overlap_allreduce is None else bool(overlap_allreduce)
+        # gradient averaging: one all-reduce at the end of the backward pass (default), or started bucket by bucket under it
+        # (FGC_OVERLAP_ALLREDUCE=1 / overlap_allreduce=True).  Measured at 2 GPUs (profiles/r2s_*): 99.6 against 99.1 ms per
+        # iteration -- the collective's CTAs share the SMs with persistent one-CTA-per-SM convolution kernels, and at NVLink
+        # speed the exposed time they save (~0.5 ms) is less than what they cost; it is an option for slower fabrics.
+        self.overlap = (os.environ.get("FGC_OVERLAP_ALLREDUCE", "0") == "1") if overlap_allreduce is None else bool(overlap_allreduce)
         self.optimizer = optimizer.lower()                    # graph_single.get_optimizer (:584-593)
         for store in (model.gstore, model.dstore):
             if store is not None and store.optimizer != self.optimizer:
