@@ -72,6 +72,25 @@ class CudaOps(OpsBase):
         assert t.dtype == torch.float32 and t.is_contiguous()
         return t.data_ptr()
 
+    def run_aside(self, fn):
+        """On a side stream (three, round robin) forked from and later joined to the current one; inside a captured step this
+        is a parallel branch of the CUDA graph.  Buffers allocated by fn belong to the side stream's pool: they are recycled
+        only by later side work, which starts with a wait on the current stream, i.e. after every reader enqueued so far.
+        FGC_SIDE_STREAMS=0 runs everything inline."""
+        if os.environ.get("FGC_SIDE_STREAMS", "1") == "0":
+            return fn(), (lambda: None)
+        main = torch.cuda.current_stream()
+        pool = self.__dict__.setdefault("_side_streams", [])
+        if not pool:
+            pool.extend(torch.cuda.Stream(device=self.device) for _ in range(3))
+            self._side_next = 0
+        side = pool[self._side_next % len(pool)]
+        self._side_next += 1
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            r = fn()
+        return r, (lambda: main.wait_stream(side))
+
     def launch_count(self):
         return int(self.lib.fgc_launch_count())
 

@@ -27,6 +27,9 @@ class Generator:
         wv = blocks.WeightView(st, ops, sn=False)
         ch = encoder_channels(self.size)
         N = sketch_nchw.shape[0]
+        # the caption's word LSTM does not depend on the picture: aside, under the encoder convolutions
+        words, join_words = (ops.run_aside(lambda: text_fusion.text_words_fwd(ops, st, text_ids_host)) if self.lstm_hybrid
+                             else (None, None))
         s0 = ops.nchw_to_nhwc(sketch_nchw)                         # [N,H,W,3]
         # sketch pyramid: cascaded 2x2 means (encoder, :84-86) == AREA resize (decoder, :268-272) at 2^k factors
         S = [s0]
@@ -44,7 +47,8 @@ class Generator:
             ectx.append(c)
         tctx = None
         if self.lstm_hybrid:
-            feat, tctx = text_fusion.text_fusion_fwd(ops, st, enc[4], text_ids_host, save)   # :298
+            join_words()
+            feat, tctx = text_fusion.text_fusion_fwd(ops, st, enc[4], text_ids_host, save, words=words)   # :298
         else:
             feat = enc[4]
         # noise FC (:310-316): [N,256] -> miu_relu -> reshape NCHW [N,C/8,2h,2w]
@@ -109,10 +113,8 @@ class Generator:
         off = st.offsets
         if grads_ready is not None:
             grads_ready(off[p + "/fully_connected/weights"], st.n_flat)
-        # text fusion
-        g_e4 = text_fusion.text_fusion_bwd(ops, st, g_ht, ctx["tctx"]) if self.lstm_hybrid else g_ht
-        if grads_ready is not None and p + "/TextLSTM/embedding" in off:
-            grads_ready(off[p + "/TextLSTM/embedding"], off[p + "/fully_connected/weights"])
+        # text fusion: its weight gradients and the word LSTM's BPTT run aside, under the encoder's backward pass
+        g_e4, join_text = text_fusion.text_fusion_bwd(ops, st, g_ht, ctx["tctx"], aside=True) if self.lstm_hybrid else (g_ht, None)
         # encoder
         g_cur = blocks.norm_act_bwd(ops, st, p + "/mru_conv_unit_last_norm", g_e4, ctx["c_last"], labels, "cbn")
         for u in (4, 3, 2, 1):
@@ -125,3 +127,7 @@ class Generator:
                 grads_ready(off[first], off.get(p + "/TextLSTM/embedding", off[p + "/fully_connected/weights"]))
         ops.add_(g_cur, g_enc[0])
         ops.conv_wgrad([(ctx["s0"], False)], g_cur, *wv.grads(p + "/Conv"), stride=2)
+        if join_text is not None:
+            join_text()
+            if grads_ready is not None:
+                grads_ready(off[p + "/TextLSTM/embedding"], off[p + "/fully_connected/weights"])

@@ -24,6 +24,13 @@ ACT_NONE, ACT_LRELU, ACT_TANH, ACT_MIU, ACT_RELU = 0, 1, 2, 3, 4     # ACT_RELU:
 class OpsBase:
     act_dtype = None
 
+    # ---------------- scheduling ----------------
+    def run_aside(self, fn):
+        """Run fn() so that its work MAY overlap with what the caller enqueues next (work that depends on nothing the caller is
+        about to produce: spectral normalisation of the weights, the caption's word LSTM, weight gradients off the critical
+        path).  Returns (fn(), join): call join() before anything consumes the results.  Default: inline, join is a no-op."""
+        return fn(), (lambda: None)
+
     # ---------------- convolution family (mru.conv2d, mru.py:95-140) ----------------
     def conv_fwd(self, srcs, w, b, *, stride=1, act=ACT_NONE, out_dtype=None, out=None, acc=False):
         """y = act(conv2d_SAME(concat(srcs), w) + b);  w HWIO fp32, b fp32 [Cout] or None.  out= writes into the given tensor,

@@ -84,29 +84,20 @@ def _word_lstm_bwd(ops, g_hext, pre_w, cw_all, kw, ids, T, N, D):
     return gpw_all
 
 
-def text_fusion_fwd(ops, store, e4, ids_host, save=True, prefix=_PRE):
-    """e4: [N,h,w,D] activation; ids_host: int array [N,T] on the HOST (numpy / CPU tensor), or an int32 DEVICE tensor.
-    With host ids, mLSTM time steps at which every caption is <pad> are skipped outright (the reference's tf.cond, :235);
-    with device ids nothing on the host depends on the data (CUDA-graph capture): every step runs and <pad> samples
-    are masked inside the cell kernels -- same result.  Returns ([N,h,w,D], ctx)."""
+def text_words_fwd(ops, store, ids_host, prefix=_PRE):
+    """Everything of the caption encoder that does not depend on the picture (:182,211-224): embeddings, the word LSTM over all
+    steps, l2n(h_w), and the mLSTM's spatially constant input term of every step.  A caller may evaluate it aside
+    (ops.run_aside) while the encoder convolutions run, and hand the result to text_fusion_fwd(words=)."""
     on_device = torch.is_tensor(ids_host) and ids_host.is_cuda
     ids_np = None if on_device else np.asarray(ids_host, dtype=np.int32)
-    N, hh, ww, D = e4.shape
-    P = hh * ww
-    R = N * P
-    T = ids_host.shape[1]
-    dev = e4.device
     emb, kw, bw, ka, ba = (store.p[n] for n in _names(prefix))
-    # [N,T] int32 on the device; pad mask = (id == 0)
-    ids_dev = ids_host.to(torch.int32).contiguous() if on_device else torch.as_tensor(ids_np, device=dev).contiguous()
+    D = emb.shape[1]
+    N, T = ids_host.shape
     f32 = torch.float32
+    # [N,T] int32 on the device; pad mask = (id == 0)
+    ids_dev = ids_host.to(torch.int32).contiguous() if on_device else torch.as_tensor(ids_np, device=emb.device).contiguous()
     # steps at which at least one caption has a real token (all of them when the ids live on the device)
     ts = [t for t in range(T) if ids_np is None or (ids_np[:, t] != 0).any()]
-    S = len(ts)
-
-    e4r = ops.cast(e4, f32).view(R, D)
-    vis, inv_v = ops.l2norm_rows_fwd(e4r)                                           # :201-202
-    gv = ops.conv_fwd([(_op(ops, vis), False)], _mat(ka[0:D]), ba, out_dtype=f32).view(R, 4 * D)
     # ---- word LSTM (:182,211-213): embeddings and their gate products for all steps, then the recurrence in one launch
     e_all = ops.embedding_all_fwd(emb, ids_dev)                                      # [T,N,D]
     e_rows = _op(ops, e_all.view(T * N, D))
@@ -116,6 +107,29 @@ def text_fusion_fwd(ops, store, e4, ids_host, save=True, prefix=_PRE):
     lang_rows = _op(ops, lang_all)
     # the mLSTM's spatially constant input term of every step (:218-224)
     r_all = ops.conv_fwd([(e_rows, False), (lang_rows, False)], _mat(ka[D:3 * D]), None, out_dtype=f32).view(T, N, 4 * D)
+    return dict(ids=ids_dev, ts=ts, T=T, e_rows=e_rows, hw_all=hw_all, cw_all=cw_all, pre_w=pre_w, lang_all=lang_all, inv_l=inv_l,
+                lang_rows=lang_rows, r_all=r_all)
+
+
+def text_fusion_fwd(ops, store, e4, ids_host, save=True, prefix=_PRE, words=None):
+    """e4: [N,h,w,D] activation; ids_host: int array [N,T] on the HOST (numpy / CPU tensor), or an int32 DEVICE tensor.
+    With host ids, mLSTM time steps at which every caption is <pad> are skipped outright (the reference's tf.cond, :235);
+    with device ids nothing on the host depends on the data (CUDA-graph capture): every step runs and <pad> samples
+    are masked inside the cell kernels -- same result.  words: the result of text_words_fwd when the caller has evaluated it
+    already.  Returns ([N,h,w,D], ctx)."""
+    N, hh, ww, D = e4.shape
+    P = hh * ww
+    R = N * P
+    if words is None:
+        words = text_words_fwd(ops, store, ids_host, prefix)
+    T, ts, ids_dev, r_all = words["T"], words["ts"], words["ids"], words["r_all"]
+    emb, kw, bw, ka, ba = (store.p[n] for n in _names(prefix))
+    f32 = torch.float32
+    S = len(ts)
+
+    e4r = ops.cast(e4, f32).view(R, D)
+    vis, inv_v = ops.l2norm_rows_fwd(e4r)                                           # :201-202
+    gv = ops.conv_fwd([(_op(ops, vis), False)], _mat(ka[0:D]), ba, out_dtype=f32).view(R, 4 * D)
     # ---- mLSTM recurrence over the executed steps: slot j of ha_all holds the INPUT state of step ts[j] (slot 0 = zeros, :204)
     ha_all = ops.zeros_f32((S + 1, R, D))
     ca = ops.zeros_f32((R, D))
@@ -133,13 +147,16 @@ def text_fusion_fwd(ops, store, e4, ids_host, save=True, prefix=_PRE):
     ctx = None
     if save:
         ctx = dict(steps=steps, ids=ids_dev, vis=vis, inv_v=inv_v, ha=ha, shape=(N, hh, ww, D), in_dtype=e4.dtype, T=T,
-                   e_rows=e_rows, lang_all=lang_all, lang_rows=lang_rows, inv_l=inv_l, hw_all=hw_all, cw_all=cw_all, pre_w=pre_w,
-                   ha_all=ha_all)
+                   e_rows=words["e_rows"], lang_all=words["lang_all"], lang_rows=words["lang_rows"], inv_l=words["inv_l"],
+                   hw_all=words["hw_all"], cw_all=words["cw_all"], pre_w=words["pre_w"], ha_all=ha_all)
     return out, ctx
 
 
-def text_fusion_bwd(ops, store, g_out, ctx, prefix=_PRE):
-    """Returns g_e4 [N,h,w,D]; accumulates gradients of embedding / both LSTM kernels / biases."""
+def text_fusion_bwd(ops, store, g_out, ctx, prefix=_PRE, aside=False):
+    """Returns g_e4 [N,h,w,D]; accumulates gradients of embedding / both LSTM kernels / biases.
+    aside=True: returns (g_e4, join) instead -- only the chain that ends in g_e4 is on the caller's critical path; the word
+    LSTM's BPTT, the batched weight gradients and the embedding scatter are handed to ops.run_aside and join() must be called
+    before the gradients are consumed (they then overlap with the encoder's backward pass)."""
     N, hh, ww, D = ctx["shape"]
     P = hh * ww
     R = N * P
@@ -151,7 +168,8 @@ def text_fusion_bwd(ops, store, g_out, ctx, prefix=_PRE):
     steps = ctx["steps"]
     S = len(steps)
     if S == 0:                # all-pad batch: output is relu(0) = 0, no gradient reaches e4
-        return ops.cast(ops.zeros_f32((N, hh, ww, D)), ctx["in_dtype"])
+        z = ops.cast(ops.zeros_f32((N, hh, ww, D)), ctx["in_dtype"])
+        return (z, (lambda: None)) if aside else z
     ha_all, ids = ctx["ha_all"], ctx["ids"]
 
     # ---- mLSTM, backwards through the executed steps
@@ -168,23 +186,41 @@ def text_fusion_bwd(ops, store, g_out, ctx, prefix=_PRE):
         ops.add_(g_ha, g_ha_pass)
         ops.add_(g_gv, g_pre_a)
         ops.rows_group_sum(g_pre_a, P, out=gr_all[t])                                # [N,4D]
-    # ---- all steps at once: row terms -> l2n(h_w(t)) -> h_w(t); then the word LSTM's BPTT in one launch
-    gr = _op(ops, gr_all.view(T * N, 4 * D))
-    g_lang = ops.conv_dgrad(gr, _mat(ka[D:3 * D]), D, D, out_dtype=f32).view(T * N, D)
-    g_hext = ops.l2norm_rows_bwd(g_lang, ctx["lang_all"], ctx["inv_l"]).view(T, N, D)
-    gpw_all = _word_lstm_bwd(ops, g_hext, ctx["pre_w"], ctx["cw_all"], kw, ids, T, N, D)
-    # ---- weight gradients: one product per kernel block over all steps (rows = step x sample [x position])
-    gpa, gpw = _op(ops, gpa_all.view(S * R, 4 * D)), _op(ops, gpw_all.view(T * N, 4 * D))
-    e_rows, lang_rows = ctx["e_rows"], ctx["lang_rows"]
-    ops.conv_wgrad([(_op(ops, ha_all[:S].view(S * R, D)), False)], gpa, _mat(dka[3 * D:4 * D]), dba)
-    ops.conv_wgrad([(e_rows, False), (lang_rows, False)], gr, _mat(dka[D:3 * D]), None)
-    ops.conv_wgrad([(e_rows, False), (_op(ops, ctx["hw_all"][:T].view(T * N, D)), False)], gpw, _mat(dkw), dbw)
-    # ---- embedding rows: d/d(e_t) through both LSTMs, all steps at once, then one scatter-add
-    g_e = ops.conv_dgrad(gr, _mat(ka[D:3 * D]), 0, D, out_dtype=f32)
-    ops.conv_dgrad(gpw, _mat(kw), 0, D, out=g_e, acc=True)
-    ops.embedding_all_bwd(g_e.view(T, N, D), ids, demb)
     g_gv_op = _op(ops, g_gv)
-    ops.conv_wgrad([(_op(ops, ctx["vis"]), False)], g_gv_op, _mat(dka[0:D]), None)
+
+    def off_path():
+        # ---- all steps at once: row terms -> l2n(h_w(t)) -> h_w(t); then the word LSTM's BPTT in one launch
+        gr = _op(ops, gr_all.view(T * N, 4 * D))
+        g_lang = ops.conv_dgrad(gr, _mat(ka[D:3 * D]), D, D, out_dtype=f32).view(T * N, D)
+        g_hext = ops.l2norm_rows_bwd(g_lang, ctx["lang_all"], ctx["inv_l"]).view(T, N, D)
+        gpw_all = _word_lstm_bwd(ops, g_hext, ctx["pre_w"], ctx["cw_all"], kw, ids, T, N, D)
+        # ---- weight gradients: one product per kernel block over all steps (rows = step x sample [x position])
+        gpa, gpw = _op(ops, gpa_all.view(S * R, 4 * D)), _op(ops, gpw_all.view(T * N, 4 * D))
+        e_rows, lang_rows = ctx["e_rows"], ctx["lang_rows"]
+        ops.conv_wgrad([(_op(ops, ha_all[:S].view(S * R, D)), False)], gpa, _mat(dka[3 * D:4 * D]), dba)
+        ops.conv_wgrad([(e_rows, False), (lang_rows, False)], gr, _mat(dka[D:3 * D]), None)
+        ops.conv_wgrad([(e_rows, False), (_op(ops, ctx["hw_all"][:T].view(T * N, D)), False)], gpw, _mat(dkw), dbw)
+        # ---- embedding rows: d/d(e_t) through both LSTMs, all steps at once, then one scatter-add
+        g_e = ops.conv_dgrad(gr, _mat(ka[D:3 * D]), 0, D, out_dtype=f32)
+        ops.conv_dgrad(gpw, _mat(kw), 0, D, out=g_e, acc=True)
+        ops.embedding_all_bwd(g_e.view(T, N, D), ids, demb)
+        ops.conv_wgrad([(_op(ops, ctx["vis"]), False)], g_gv_op, _mat(dka[0:D]), None)
+
+    join = lambda: None
+    if aside:
+        _, join_side = ops.run_aside(off_path)
+        # the side work reads buffers allocated on the caller's stream: they must not return to its allocator (and be handed
+        # to the encoder's backward pass) before the join
+        keep = [gr_all, gpa_all, g_gv, g_gv_op]
+
+        def join():
+            join_side()
+            keep.clear()
+    # ---- the caller's critical path: gate gradients -> visual rows -> e4
     g_vis = ops.conv_dgrad(g_gv_op, _mat(ka[0:D]), 0, D, out_dtype=f32).view(R, D)
     g_e4 = ops.l2norm_rows_bwd(g_vis, ctx["vis"], ctx["inv_v"])
-    return ops.cast(g_e4.view(N, hh, ww, D), ctx["in_dtype"])
+    g_e4 = ops.cast(g_e4.view(N, hh, ww, D), ctx["in_dtype"])
+    if not aside:
+        off_path()
+        return g_e4
+    return g_e4, join

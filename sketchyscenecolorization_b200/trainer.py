@@ -106,21 +106,15 @@ class FgColorModel:
         return st['out']
 
     def _weight_view_ahead(self, need_wgrad):
-        """The discriminator's weight view with its spectral normalisation already evaluated -- on a side stream (CUDA
-        operator set, MRU networks), concurrently with the generator's forward pass that every step starts with; join() makes
-        the current stream wait for it.  ~90 launch-latency-bound kernels per step leave the critical path this way."""
+        """The discriminator's weight view with its spectral normalisation already evaluated -- aside (ops.run_aside: a side
+        stream on the CUDA operator set), concurrently with the generator's forward pass that every step starts with; join()
+        makes the current stream wait for it.  ~90 launch-latency-bound kernels per step leave the critical path this way
+        (99.55 -> 99.0 ms per iteration, profiles/r2t_*)."""
         wv = self.D.new_weight_view(need_wgrad=need_wgrad)
-        if (self.block_type != 'MRU' or not getattr(self.ops, 'supports_cuda_graphs', False) or not torch.cuda.is_available()
-                or os.environ.get("FGC_SN_SIDE_STREAM", "1") == "0"):
+        if self.block_type != 'MRU' or os.environ.get("FGC_SN_SIDE_STREAM", "1") == "0":
             return wv, (lambda: None)
-        main = torch.cuda.current_stream()
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream()
-        side = self._side
-        side.wait_stream(main)                      # parameters, `u`, and last step's readers of recycled buffers
-        with torch.cuda.stream(side):
-            self.D.prefetch_weights(wv)
-        return wv, (lambda: main.wait_stream(side))
+        _, join = self.ops.run_aside(lambda: self.D.prefetch_weights(wv))
+        return wv, join
 
     # ---- loss_d and dL/dtheta_D
     def d_step_grads(self, batch, grads_ready=None):
