@@ -141,11 +141,14 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
     # gradient (dbias= of the norm / activation / min-max backward); for Conv_2 / Conv_3 the gradient is the un-pooled
     # g_out / 4 replicated 2x2, whose column sums equal those of the (4x smaller) g_out itself.
     # Conv_3 (1x1 skip, evaluated on the pooled hidden state -- see the forward pass; identity when the block keeps its width)
+    cs = None
     if scope + "/Conv_3/weights" in st.p:
         w3, _ = wv.get(scope + "/Conv_3")
         if nw:
             dw3, db3 = wv.grads(scope + "/Conv_3")
-            ops.colsum_(g_out, db3)
+            cs = ops.zeros_f32(db3.shape)          # Conv_2 and Conv_3 see the same output gradient: one column-sum pass for both
+            ops.colsum_(g_out, cs)
+            ops.add_(db3, cs)
             ops.conv_wgrad([(ctx["ht_p"], False)], g_out, dw3, None)
         g_ht = ops.unpool_bwd(ops.conv_dgrad(g_out, w3, 0, cin)) if need_ht_grad else None
     else:
@@ -154,7 +157,10 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
     w2, _ = wv.get(scope + "/Conv_2")
     if nw:
         dw2, db2 = wv.grads(scope + "/Conv_2")
-        ops.colsum_(g_out, db2)
+        if cs is not None:
+            ops.add_(db2, cs)
+        else:
+            ops.colsum_(g_out, db2)
         ops.conv_wgrad([(ctx["h1"], False)], g_full, dw2, None)
     g_h1 = ops.conv_dgrad(g_full, w2, 0, w2.shape[2])
     del g_full

@@ -309,14 +309,29 @@ class CudaOps(OpsBase):
         check(self.lib.fgc_colsum(self._p(x), self._dt(x), x.numel() // Cc, Cc, self._f32(out.reshape(-1)), self._s()), "colsum")
         return out
 
+    # min-max gates: statistics per (sample, channel), so the two passes (reduce, apply) CAN run over a few samples at a time,
+    # the apply pass then reading what the reduce pass has just pulled through the 126 MB L2.  Measured (profiles/r2v_*): it
+    # loses -- 98.0 ms per iteration unchunked, 98.7 / 99.9 / 101.4 ms at 80 / 40 / 20 MB chunks: the short launches cost more
+    # than the L2 hits return.  Off by default (FGC_MINMAX_CHUNK_MB=0); kept as an option with its test.
+    _MM_CHUNK_BYTES = int(os.environ.get("FGC_MINMAX_CHUNK_MB", "0")) << 20
+
+    def _mm_chunks(self, x):
+        N = x.shape[0]
+        per = x[0].numel() * x.element_size()
+        if self._MM_CHUNK_BYTES <= 0 or N * per <= 2 * self._MM_CHUNK_BYTES:
+            return [(0, N)]
+        b = max(1, self._MM_CHUNK_BYTES // per)
+        return [(i, min(N, i + b)) for i in range(0, N, b)]
+
     def minmax_fwd(self, x):
         N, H, W, Cc = x.shape
         gate = self._empty(x.shape, x.dtype)
         mn = self._empty((N, Cc), torch.float32)
         mx = self._empty((N, Cc), torch.float32)
         scratch = self._empty((2 * N * Cc,), torch.int32)
-        check(self.lib.fgc_minmax_fwd(self._p(x), self._dt(x), N, H * W, Cc, self._p(gate), self._p(mn), self._p(mx),
-                                      self._p(scratch), self._s()), "minmax_fwd")
+        for a, b in self._mm_chunks(x):
+            check(self.lib.fgc_minmax_fwd(self._p(x[a:b]), self._dt(x), b - a, H * W, Cc, self._p(gate[a:b]), self._p(mn[a:b]),
+                                          self._p(mx[a:b]), self._p(scratch[2 * a * Cc:2 * b * Cc]), self._s()), "minmax_fwd")
         return gate, mn, mx
 
     def minmax_bwd(self, ggate, x, mn, mx, dbias=None):
@@ -324,9 +339,10 @@ class CudaOps(OpsBase):
         assert ggate.dtype == x.dtype
         gpre = self._empty(x.shape, x.dtype)
         scratch = self._empty((4 * N * Cc,), torch.float32)
-        check(self.lib.fgc_minmax_bwd(self._p(ggate), self._p(x), self._dt(x), N, H * W, Cc, self._f32(mn), self._f32(mx),
-                                      self._p(gpre), self._p(scratch), None if dbias is None else self._f32(dbias.reshape(-1)),
-                                      self._s()), "minmax_bwd")
+        for a, b in self._mm_chunks(x):
+            check(self.lib.fgc_minmax_bwd(self._p(ggate[a:b]), self._p(x[a:b]), self._dt(x), b - a, H * W, Cc, self._f32(mn[a:b]),
+                                          self._f32(mx[a:b]), self._p(gpre[a:b]), self._p(scratch[4 * a * Cc:4 * b * Cc]),
+                                          None if dbias is None else self._f32(dbias.reshape(-1)), self._s()), "minmax_bwd")
         return gpre
 
     def act_bwd(self, gy, y, act):

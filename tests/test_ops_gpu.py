@@ -288,6 +288,28 @@ def test_prelu_minmax_actbwd(env, shape):
     close(cu.act_bwd(gf, y_m.float().contiguous(), ACT_MIU), ref.act_bwd(gy, y_m, ACT_MIU), 1e-4, "miu bwd")
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_minmax_in_sample_chunks(env, dt):
+    """Large gate tensors run the reduce / apply pair a few samples at a time (L2 reuse, CudaOps._mm_chunks): statistics are
+    per (sample, channel), so the result -- bias-gradient column sums included -- is the unchunked one."""
+    from sketchyscenecolorization_b200.cuda_ops import CudaOps
+    dev = env["dev"]
+    x = rnd((7, 12, 10, 24), 3, dev).to(dt).contiguous()
+    gy = rnd((7, 12, 10, 24), 4, dev).to(dt).contiguous()
+    whole, parts = CudaOps(dev, dt), CudaOps(dev, dt)
+    whole._MM_CHUNK_BYTES = 0
+    parts._MM_CHUNK_BYTES = 2 * x[0].numel() * x.element_size()         # 2 samples per launch pair: 4 chunks, the last ragged
+    assert len(parts._mm_chunks(x)) == 4 and len(whole._mm_chunks(x)) == 1
+    g0, mn0, mx0 = whole.minmax_fwd(x)
+    g1, mn1, mx1 = parts.minmax_fwd(x)
+    assert torch.equal(g0, g1) and torch.equal(mn0, mn1) and torch.equal(mx0, mx1)
+    db0, db1 = torch.zeros(24, device=dev), torch.zeros(24, device=dev)
+    b0, b1 = whole.minmax_bwd(gy, x, mn0, mx0, dbias=db0), parts.minmax_bwd(gy, x, mn1, mx1, dbias=db1)
+    torch.cuda.synchronize()
+    assert torch.equal(b0, b1)
+    close(db1, db0, 1e-5, "dbias across chunks")
+
+
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 def test_gating(env, shape, dt):
