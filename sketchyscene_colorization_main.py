@@ -2,9 +2,9 @@
 and is appended to the scene's editing records.  Flags, defaults, directory contract and the signature of `colorization_main`
 are those of the reference's sketchyscene_colorization_main.py (:19-60, :63-112), so existing invocations keep working.
 
-FG instructions need the indices of the instances they refer to.  The reference gets them from its Instance_Matching model
-(RMI: DeepLab-v3+ trunk + mLSTM), which is outside the scope of this package: supply them with
---matched_inst_indices, or `matched_inst_indices=` / a `matcher=` callable when calling colorization_main.
+FG instructions need the indices of the instances they refer to.  As in the reference they come from the instance-matching model
+(`pipeline_match.build_instance_matching`: rmi.RMIModel restored from --match_snapshot_root + the occupied-share rule over the
+segmentation file); --matched_inst_indices, `matched_inst_indices=` or a `matcher=` callable override it.
 """
 import argparse
 import os
@@ -61,9 +61,10 @@ def colorization_main(image_id, input_text, data_base_dir, results_base_dir,
         if matched_inst_indices is None and matcher is not None:
             matched_inst_indices = matcher(data_base_dir, sketch_path, input_text, segm_npz, match_vocab_path, match_vocab_size,
                                            match_snapshot_root, match_max_len)
-        if matched_inst_indices is None:
-            raise NotImplementedError("FG instruction: the instance-matching model (Instance_Matching, RMI) is not part of this "
-                                      "package; give the matched instance indices (--matched_inst_indices / matcher=)")
+        if matched_inst_indices is None:          # reference: Pipeline_utils.fg_matching_utils.build_instance_matching (:33-37)
+            from sketchyscenecolorization_b200.pipeline_match import build_instance_matching
+            matched_inst_indices = build_instance_matching(data_base_dir, sketch_path, input_text, segm_npz, match_vocab_path,
+                                                           match_vocab_size, match_snapshot_root, match_max_len, ops=ops)
         assert type(matched_inst_indices) is list
         print('matched_inst_indices', matched_inst_indices)
         build_instance_colorization(data_base_dir, image_id, input_text, matched_inst_indices, sketch_path, inner_mat, segm_npz,

@@ -129,7 +129,9 @@ def test_background_instruction_end_to_end(tmp_path):
         kind, name = M.colorization_main(3, "the sky is purple", *args, bg_model=m)
         rec = json.load(open(os.path.join(res, "update_records", "3_records.json")))
         assert name == "3_2.png" and rec[1]["proc_bg_text"] == "the sky is purple and the ground is green"
-        with pytest.raises(NotImplementedError):
-            M.colorization_main(3, "the bus is red", *args, bg_model=m)
+        # an FG instruction goes to the instance-matching model; without a snapshot under match_snapshot_root that is an error
+        # that says so (its own tests: tests/test_pipeline_match_cpu.py)
+        with pytest.raises(FileNotFoundError):
+            M.colorization_main(3, "the bus is red", *args, bg_model=m, ops=m.ops)
     finally:
         M.build_background_colorization = orig
