@@ -131,6 +131,8 @@ class TrainSession:
                     "synthetic_input=True / set FGC_SYNTHETIC_INPUT=1 to train on seeded synthetic batches." % rec_dir)
         self.q1, self.q2 = q1, q2
         self.last_d = self.last_g = None
+        self.prefetch = os.environ.get("FGC_INPUT_PREFETCH", "1") != "0"
+        self._copy_stream, self._staged, self._stage_bufs, self._stage_free = None, {}, {}, {}
 
     # ---- batches: opt_d dequeues both queues, opt_g only the first (graph_single.py:257-289; main_procedure.py:202-227)
     def _text(self, t):
@@ -141,26 +143,95 @@ class TrainSession:
     def _noise(self):
         return torch.randn(self.n, 256, device=self.dev)
 
-    def fetch_d(self):
+    def _host_d(self):
         a, b = next(self.q1), next(self.q2)
-        out = {k: a[k] if self.graphs else a[k].to(self.dev, non_blocking=True) for k in ('sketch', 'cls')}
-        for k in ('images_d', 'cls_d'):
-            out[k] = b[k] if self.graphs else b[k].to(self.dev, non_blocking=True)
+        out = {k: a[k] for k in ('sketch', 'cls')}
+        out.update({k: b[k] for k in ('images_d', 'cls_d')})
+        out['text'] = torch.as_tensor(a['text'])
+        return out
+
+    def _host_g(self):
+        a = next(self.q1)
+        out = {k: a[k] for k in ('sketch', 'images', 'cls')}
+        out['text'] = torch.as_tensor(a['text'])
+        return out
+
+    def fetch_d(self):
+        a = self._host_d()
+        out = {k: (v if self.graphs else v.to(self.dev, non_blocking=True)) for k, v in a.items() if k != 'text'}
         out['text'], out['noise'] = self._text(a['text']), self._noise()
         return out
 
     def fetch_g(self):
-        a = next(self.q1)
-        out = {k: a[k] if self.graphs else a[k].to(self.dev, non_blocking=True) for k in ('sketch', 'images', 'cls')}
+        a = self._host_g()
+        out = {k: (v if self.graphs else v.to(self.dev, non_blocking=True)) for k, v in a.items() if k != 'text'}
         out['text'], out['noise'] = self._text(a['text']), self._noise()
         return out
+
+    # ---- input prefetch (graph-replay mode): the NEXT batch crosses PCIe on a copy stream while the current step computes;
+    # at its turn the step copies it device-to-device into the captured graph's input buffers.  One staging set per kind: the
+    # D batch of iteration i+1 is staged under the G step of iteration i, the G batch under the D step, and a set is rewritten
+    # only after the step that read it has finished (event).  Batches are drawn from the queues in the reference's order.
+    def _prefetch(self, kind):
+        try:
+            host = self._host_d() if kind == 'd' else self._host_g()
+        except StopIteration:
+            self._staged[kind] = None
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        side, bufs = self._copy_stream, self._stage_bufs.setdefault(kind, {})
+        free = self._stage_free.get(kind)
+        if free is not None:
+            side.wait_event(free)
+        dev = {}
+        with torch.cuda.stream(side):
+            for k, v in host.items():
+                v = torch.as_tensor(v)
+                if v.is_cuda:                       # the TFRecord queue hands over device tensors already
+                    dev[k] = v
+                    continue
+                b = bufs.get(k)
+                if b is None or b.shape != v.shape or b.dtype != v.dtype:
+                    b = bufs[k] = torch.empty(v.shape, dtype=v.dtype, device=self.dev)
+                b.copy_(v, non_blocking=True)
+                dev[k] = b
+            ready = torch.cuda.Event()
+            ready.record(side)
+        self._staged[kind] = (dev, ready, host)     # the host tensors stay referenced until the copy has been consumed
+
+    def _take(self, kind):
+        if kind not in self._staged:
+            self._prefetch(kind)
+        item = self._staged.pop(kind)
+        if item is None:
+            raise StopIteration
+        dev, ready, _ = item
+        torch.cuda.current_stream().wait_event(ready)
+        out = dict(dev)
+        out['noise'] = self._noise()
+        return out
+
+    def _step_done(self, kind):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._stage_free[kind] = ev
 
     # ---- one iteration of the session loop
     def iteration(self):
         """Returns (loss_d, loss_g, nan_d, nan_g) as Python values: one device-to-host read."""
-        for _ in range(self.diters):
-            od = self.tr.d_step(self.fetch_d())
-        og = self.tr.g_step(self.fetch_g())
+        if self.graphs and self.prefetch:
+            for j in range(self.diters):
+                od = self.tr.d_step(self._take('d'))
+                self._step_done('d')
+                self._prefetch('d' if j + 1 < self.diters else 'g')
+            og = self.tr.g_step(self._take('g'))
+            self._step_done('g')
+            self._prefetch('d')
+        else:
+            for _ in range(self.diters):
+                od = self.tr.d_step(self.fetch_d())
+            og = self.tr.g_step(self.fetch_g())
         self.last_d, self.last_g = od, og
         lo = torch.stack([od['loss'].float().reshape(()), og['loss'].float().reshape(())])
         bad = torch.isnan(lo).float()
