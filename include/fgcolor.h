@@ -156,6 +156,14 @@ int fgc_act_bwd(const void* gy, const void* y, int dtype, long long n, int act, 
  * -------------------------------------------------------------------------------------------------------*/
 int fgc_gate_fma_fwd(const void* ht, const void* rg, const void* im, int dtype, long long n, void* out, fgc_stream s);
 int fgc_gate_fma_bwd(const void* g, const void* rg, const void* im, int dtype, long long n, void* g_rg, void* g_im, fgc_stream s);
+/* the same gate followed by PReLU in one pass (the discriminator's cell: norm_activ = prelu, mru.py:426-430,
+ * models_collection.py:56-60): out = prelu(ht + rg*im, *a).  Backward from the three operands (the sum is recomputed):
+ * g_x = gp * prelu'(x); *da += sum gp*x over the leaky side (da may be NULL); g_rg = g_x*im; g_im = g_x*rg;
+ * g_ht (may be NULL) = g_x, or += g_x when acc_ht. */
+int fgc_gate_prelu_fwd(const void* ht, const void* rg, const void* im, int dtype, long long n, const float* a, void* out,
+                       fgc_stream s);
+int fgc_gate_prelu_bwd(const void* gp, const void* ht, const void* rg, const void* im, int dtype, long long n, const float* a,
+                       float* da, void* g_ht, int acc_ht, void* g_rg, void* g_im, fgc_stream s);
 /* full-res tensors are [N,2h,2w,C], low-res [N,h,w,C] */
 int fgc_mul_up_fwd(const void* rg, const void* ht_low, int dtype, int N, int h, int w, int C, void* out, fgc_stream s);
 int fgc_mul_up_bwd(const void* g, const void* rg, const void* ht_low, int dtype, int N, int h, int w, int C,

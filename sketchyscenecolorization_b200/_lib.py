@@ -95,6 +95,8 @@ SIGNATURES = {
     "fgc_act_bwd": [_P, _P, _I, _LL, _I, _P, _P],
     "fgc_gate_fma_fwd": [_P, _P, _P, _I, _LL, _P, _P],
     "fgc_gate_fma_bwd": [_P, _P, _P, _I, _LL, _P, _P, _P],
+    "fgc_gate_prelu_fwd": [_P, _P, _P, _I, _LL, _P, _P, _P],
+    "fgc_gate_prelu_bwd": [_P, _P, _P, _P, _I, _LL, _P, _P, _P, _I, _P, _P, _P],
     "fgc_mul_up_fwd": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
     "fgc_mul_up_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "fgc_blend_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P],

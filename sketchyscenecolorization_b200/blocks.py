@@ -105,8 +105,12 @@ def enc_block_fwd(ops, wv, scope, x, ht, labels, kind, save=True):
     rg, mn, mx = ops.minmax_fwd(rg_raw)                                          # mru.py:415-416
     w, b = wv.get(scope + "/Conv")
     im = ops.conv_fwd([xs_], w, b)                                               # mru.py:419-424
-    hp = ops.gate_fma_fwd(ht, rg, im)                                            # mru.py:426
-    p, c_p = norm_act_fwd(ops, st, scope + "/norm_activation_merge_1", hp, labels, kind)
+    fused = kind == "prelu" and getattr(ops, "fuse_gate_prelu", True)
+    if fused:                  # discriminator: gate + PReLU in one pass, the sum is recomputed by the backward pass
+        p, c_p = ops.gate_prelu_fwd(ht, rg, im, st.p[scope + "/norm_activation_merge_1/prelu/param"]), None
+    else:
+        hp = ops.gate_fma_fwd(ht, rg, im)                                        # mru.py:426
+        p, c_p = norm_act_fwd(ops, st, scope + "/norm_activation_merge_1", hp, labels, kind)
     w, b = wv.get(scope + "/Conv_1")
     ps_ = (p, False, ops.small_patch(p, 3) if p.shape[-1] < 64 else None)     # unit 1: 8 channels at full resolution
     h1_raw = ops.conv_fwd([ps_], w, b)                                           # mru.py:431-436
@@ -173,12 +177,18 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
         ops.conv_wgrad([ctx["ps_"]], g_h1raw, dw1, None)
     g_p = ops.conv_dgrad(g_h1raw, w1, 0, cin)
     del g_h1raw
-    g_hp = norm_act_bwd(ops, st, scope + "/norm_activation_merge_1", g_p, ctx["c_p"], labels, kind, nw)
-    del g_p
-    if need_ht_grad:
-        ops.add_(g_ht, g_hp)
-    g_rg, g_im = ops.gate_fma_bwd(g_hp, ctx["rg"], ctx["im"])
-    del g_hp
+    if kind == "prelu" and ctx["c_p"] is None:
+        sc = scope + "/norm_activation_merge_1/prelu/param"
+        g_rg, g_im = ops.gate_prelu_bwd(g_p, ht, ctx["rg"], ctx["im"], st.p[sc], st.g[sc] if nw else None,
+                                        g_ht=g_ht if need_ht_grad else None, acc=True)
+        del g_p
+    else:
+        g_hp = norm_act_bwd(ops, st, scope + "/norm_activation_merge_1", g_p, ctx["c_p"], labels, kind, nw)
+        del g_p
+        if need_ht_grad:
+            ops.add_(g_ht, g_hp)
+        g_rg, g_im = ops.gate_fma_bwd(g_hp, ctx["rg"], ctx["im"])
+        del g_hp
     # Conv (image branch)
     wc, _ = wv.get(scope + "/Conv")
     if nw:

@@ -615,6 +615,61 @@ __global__ void gate_fma_bwd_kernel(const T* __restrict__ g, const T* __restrict
   }
 }
 
+// The discriminator's cell runs PReLU directly on ht + rg*im (mru.py:426-430 with prelu as the normaliser): one pass instead
+// of two, and the sum is never stored -- the backward pass recomputes it from the three operands it keeps anyway.
+template <typename T, int V>
+__global__ void gate_prelu_fwd_kernel(const T* __restrict__ ht, const T* __restrict__ rg, const T* __restrict__ im, long long nvec,
+                                      const float* __restrict__ ap, T* __restrict__ out) {
+  const float a = *ap;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float h[kMaxV], b[kMaxV], c[kMaxV], o[kMaxV];
+    ldv<T, V>(ht + i * V, h); ldv<T, V>(rg + i * V, b); ldv<T, V>(im + i * V, c);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const float x = fmaf(b[k], c[k], h[k]);
+      o[k] = (a * x >= x) ? a * x : x;
+    }
+    stv<T, V>(out + i * V, o);
+  }
+}
+// g_x = g_p * prelu'(x), x = ht + rg*im recomputed;  da += sum g_p * x over the leaky side;  g_rg = g_x*im, g_im = g_x*rg,
+// g_ht (+)= g_x  (acc_ht: add into the gradient the skip branch has already written there; g_ht may be NULL)
+template <typename T, int V>
+__global__ void gate_prelu_bwd_kernel(const T* __restrict__ gp, const T* __restrict__ ht, const T* __restrict__ rg,
+                                      const T* __restrict__ im, long long nvec, const float* __restrict__ ap, float* da,
+                                      T* __restrict__ g_ht, int acc_ht, T* __restrict__ g_rg, T* __restrict__ g_im) {
+  __shared__ float red[32];
+  const float a = *ap;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float g[kMaxV], h[kMaxV], b[kMaxV], c[kMaxV], gx[kMaxV], o1[kMaxV], o2[kMaxV];
+    ldv<T, V>(gp + i * V, g); ldv<T, V>(ht + i * V, h); ldv<T, V>(rg + i * V, b); ldv<T, V>(im + i * V, c);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      const float x = fmaf(b[k], c[k], h[k]);
+      const bool m = a * x >= x;
+      gx[k] = m ? a * g[k] : g[k];
+      if (m) acc += g[k] * x;
+      o1[k] = gx[k] * c[k];
+      o2[k] = gx[k] * b[k];
+    }
+    stv<T, V>(g_rg + i * V, o1); stv<T, V>(g_im + i * V, o2);
+    if (g_ht) {
+      if (acc_ht) {
+        float old[kMaxV];
+        ldv<T, V>(g_ht + i * V, old);
+#pragma unroll
+        for (int k = 0; k < V; k++) gx[k] += old[k];
+      }
+      stv<T, V>(g_ht + i * V, gx);
+    }
+  }
+  if (da) {
+    float t = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(da, t);
+  }
+}
+
 // index helpers for low-res thread -> 4 full-res positions.  low-res tensor [N,h,w,C], full [N,2h,2w,C]
 struct UpIdx {
   long long lo;      // element offset in the low-res tensor
@@ -1148,6 +1203,36 @@ int fgc_gate_fma_bwd(const void* g, const void* rg, const void* im, int dtype, l
   });
   count_launch();
   FGC_LAUNCH_CHECK("gate_fma_bwd");
+  return FGC_OK;
+}
+
+int fgc_gate_prelu_fwd(const void* ht, const void* rg, const void* im, int dtype, long long n, const float* a, void* out,
+                       fgc_stream stream) {
+  FGC_REQUIRE(ht && rg && im && a && out && n > 0, "gate_prelu_fwd: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  int vec = vmin(vmin(vmin(vec_width(ht, n, dtype), vec_width(rg, n, dtype)), vec_width(im, n, dtype)), vec_width(out, n, dtype));
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    long long nvec = n / V;
+    gate_prelu_fwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)ht, (const T*)rg, (const T*)im, nvec, a, (T*)out);
+  });
+  count_launch();
+  FGC_LAUNCH_CHECK("gate_prelu_fwd");
+  return FGC_OK;
+}
+int fgc_gate_prelu_bwd(const void* gp, const void* ht, const void* rg, const void* im, int dtype, long long n, const float* a,
+                       float* da, void* g_ht, int acc_ht, void* g_rg, void* g_im, fgc_stream stream) {
+  FGC_REQUIRE(gp && ht && rg && im && a && g_rg && g_im && n > 0, "gate_prelu_bwd: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  int vec = vmin(vmin(vmin(vec_width(gp, n, dtype), vec_width(ht, n, dtype)), vec_width(rg, n, dtype)), vec_width(im, n, dtype));
+  vec = vmin(vmin(vec, vec_width(g_rg, n, dtype)), vec_width(g_im, n, dtype));
+  if (g_ht) vec = vmin(vec, vec_width(g_ht, n, dtype));
+  FGC_DISPATCH_TV(dtype, vec, T, V, {
+    long long nvec = n / V;
+    gate_prelu_bwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)gp, (const T*)ht, (const T*)rg, (const T*)im, nvec, a, da,
+                                                                 (T*)g_ht, acc_ht, (T*)g_rg, (T*)g_im);
+  });
+  count_launch();
+  FGC_LAUNCH_CHECK("gate_prelu_bwd");
   return FGC_OK;
 }
 

@@ -40,6 +40,7 @@ class CudaOps(OpsBase):
             raise ValueError("conv_terms must be 2 (bf16x3) or 3 (six products)")
         self.conv_terms = conv_terms
         self.fold_narrow_dgrad = os.environ.get("FGC_FOLD_DGRAD", "1") != "0"
+        self.fuse_gate_prelu = os.environ.get("FGC_GATE_PRELU", "1") != "0"
         if not torch.cuda.is_available():
             raise RuntimeError("CudaOps needs a CUDA device (sm_100a); there is no CPU path in this package")
         if act_dtype not in _DT:
@@ -363,6 +364,19 @@ class CudaOps(OpsBase):
         g_im = self._empty(g.shape, g.dtype)
         check(self.lib.fgc_gate_fma_bwd(self._p(g), self._p(rg), self._p(im), self._dt(g), g.numel(), self._p(g_rg), self._p(g_im),
                                         self._s()), "gate_fma_bwd")
+        return g_rg, g_im
+
+    def gate_prelu_fwd(self, ht, rg, im, a):
+        out = torch.empty_like(ht)
+        check(self.lib.fgc_gate_prelu_fwd(self._p(ht), self._p(rg), self._p(im), self._dt(ht), ht.numel(), self._f32(a), self._p(out),
+                                          self._s()), "gate_prelu_fwd")
+        return out
+
+    def gate_prelu_bwd(self, gp, ht, rg, im, a, da, g_ht=None, acc=False):
+        g_rg, g_im = torch.empty_like(rg), torch.empty_like(im)
+        check(self.lib.fgc_gate_prelu_bwd(self._p(gp), self._p(ht), self._p(rg), self._p(im), self._dt(ht), ht.numel(), self._f32(a),
+                                          None if da is None else self._f32(da), self._p(g_ht), 1 if acc else 0, self._p(g_rg),
+                                          self._p(g_im), self._s()), "gate_prelu_bwd")
         return g_rg, g_im
 
     def mul_up_fwd(self, rg, ht_low):

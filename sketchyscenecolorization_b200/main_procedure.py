@@ -242,6 +242,8 @@ class TrainSession:
         return v[0], v[1], v[2] > 0, v[3] > 0
 
     def close(self):
+        self._staged.clear()
+        self._stage_bufs.clear()
         for q in self._own:
             q.close()
         self._own = []

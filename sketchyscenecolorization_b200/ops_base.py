@@ -95,6 +95,15 @@ class OpsBase:
         """(g*im, g*rg)"""
         raise NotImplementedError
 
+    def gate_prelu_fwd(self, ht, rg, im, a):
+        """prelu(ht + rg*im, a) in one pass (the discriminator's cell); the sum is not kept."""
+        raise NotImplementedError
+
+    def gate_prelu_bwd(self, gp, ht, rg, im, a, da, g_ht=None, acc=False):
+        """Backward of gate_prelu_fwd from its operands: returns (g_rg, g_im); accumulates da (None => skip); g_ht (optional
+        tensor) receives the gradient towards ht -- written, or added when acc."""
+        raise NotImplementedError
+
     def mul_up_fwd(self, rg, ht_low):
         """rg * up2(ht_low)"""
         raise NotImplementedError

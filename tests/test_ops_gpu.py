@@ -288,6 +288,33 @@ def test_prelu_minmax_actbwd(env, shape):
     close(cu.act_bwd(gf, y_m.float().contiguous(), ACT_MIU), ref.act_bwd(gy, y_m, ACT_MIU), 1e-4, "miu bwd")
 
 
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_gate_prelu(env, shape, dt):
+    """prelu(ht + rg*im) as one pass and its backward from the operands (the discriminator's cell, blocks.enc_block_*)."""
+    cu, ref, dev = (env["cu"] if dt == torch.float32 else env["cub"]), env["ref"], env["dev"]
+    tol = 1e-5 if dt == torch.float32 else 2e-2
+    ht, rg, im, gp, g0 = (rnd(shape, s_, dev).to(dt).contiguous() for s_ in (1, 2, 3, 4, 5))
+    D = lambda t: t.double()  # noqa: E731
+    for aval in (0.2, 1.7, -0.3):
+        a = torch.tensor(aval, dtype=torch.float64, device=dev)
+        af = a.float()
+        close(cu.gate_prelu_fwd(ht, rg, im, af), ref.gate_prelu_fwd(D(ht), D(rg), D(im), a), tol, "gate_prelu fwd a=%g" % aval)
+        da_r, da = torch.zeros((), dtype=torch.float64, device=dev), torch.full((), 0.5, device=dev)
+        gh_r = D(g0).clone()
+        grg_r, gim_r = ref.gate_prelu_bwd(D(gp), D(ht), D(rg), D(im), a, da_r, g_ht=gh_r, acc=True)
+        gh = g0.clone()
+        grg, gim = cu.gate_prelu_bwd(gp, ht, rg, im, af, da, g_ht=gh, acc=True)
+        torch.cuda.synchronize()
+        close(grg, grg_r, tol, "g_rg")
+        close(gim, gim_r, tol, "g_im")
+        close(gh, gh_r, tol, "g_ht (accumulated)")
+        assert abs(da.item() - 0.5 - da_r.item()) <= (1e-4 if dt == torch.float32 else 2e-2) * max(1.0, (D(gp) * D(ht)).abs().sum().item())
+        gh2 = torch.empty_like(g0)
+        cu.gate_prelu_bwd(gp, ht, rg, im, af, None, g_ht=gh2, acc=False)
+        close(gh2, gh_r - D(g0), tol, "g_ht (written)")
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 def test_minmax_in_sample_chunks(env, dt):
     """Large gate tensors run the reduce / apply pair a few samples at a time (L2 reuse, CudaOps._mm_chunks): statistics are

@@ -195,6 +195,15 @@ class TorchOps(OpsBase):
     def gate_fma_bwd(self, g, rg, im):
         return (self._c(g) * self._c(im)).to(self.act_dtype), (self._c(g) * self._c(rg)).to(self.act_dtype)
 
+    def gate_prelu_fwd(self, ht, rg, im, a):
+        return self.prelu_fwd(self.gate_fma_fwd(ht, rg, im), a)
+
+    def gate_prelu_bwd(self, gp, ht, rg, im, a, da, g_ht=None, acc=False):
+        gx = self.prelu_bwd(gp, self.gate_fma_fwd(ht, rg, im), a, da)
+        if g_ht is not None:
+            g_ht.copy_(g_ht + gx if acc else gx)
+        return self.gate_fma_bwd(gx, rg, im)
+
     def mul_up_fwd(self, rg, ht_low):
         return (self._c(rg) * _up(self._c(ht_low))).to(self.act_dtype)
 
