@@ -136,6 +136,10 @@ int fgc_prelu_fwd(const void* x, int dtype, long long n, const float* a, void* y
 /* C: channel count of the NHWC tensor (only used when dbias != NULL) */
 int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, int C, const float* a, float* da /*NULL ok*/,
                   float* dbias /*NULL ok*/, void* gx, fgc_stream stream);
+/* the same without the bias-gradient output, ADDED into gx (the hidden-state gradient of a cell already holds its other
+ * branches: one pass less than prelu_bwd followed by an add) */
+int fgc_prelu_bwd_acc(const void* gy, const void* x, int dtype, long long n, const float* a, float* da /*NULL ok*/, void* gx,
+                      fgc_stream stream);
 /* out[C] += column sums of x[M,C] (bias gradients that no fused kernel produces) */
 int fgc_colsum(const void* x, int dtype, long long M, int C, float* out, fgc_stream stream);
 /* gate=(x-mn)/(mx-mn) per (n,c); mn,mx fp32 [N,C]; scratch: 2*N*C uint32. */

@@ -89,6 +89,7 @@ SIGNATURES = {
     "fgc_cbn_act_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
     "fgc_prelu_fwd": [_P, _I, _LL, _P, _P, _P],
     "fgc_prelu_bwd": [_P, _P, _I, _LL, _I, _P, _P, _P, _P, _P],
+    "fgc_prelu_bwd_acc": [_P, _P, _I, _LL, _P, _P, _P, _P],
     "fgc_colsum": [_P, _I, _LL, _I, _P, _P],
     "fgc_minmax_fwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "fgc_minmax_bwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],

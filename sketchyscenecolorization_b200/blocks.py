@@ -82,15 +82,22 @@ def norm_act_fwd(ops, store, scope, x, labels, kind):
     return ops.prelu_fwd(x, a), (x,)
 
 
-def norm_act_bwd(ops, store, scope, gy, ctx, labels, kind, need_wgrad=True, dbias=None):
-    """dbias: bias-gradient accumulator of the convolution whose output was normalised here (fused column sums)."""
+def norm_act_bwd(ops, store, scope, gy, ctx, labels, kind, need_wgrad=True, dbias=None, acc_into=None):
+    """dbias: bias-gradient accumulator of the convolution whose output was normalised here (fused column sums).
+    acc_into: tensor the result is added to (and returned) -- one pass less than add_ afterwards where the operator has that form."""
+    if kind != "cbn" and acc_into is not None and dbias is None:
+        (x,) = ctx
+        return ops.prelu_bwd(gy, x, store.p[scope + "/prelu/param"], store.g[scope + "/prelu/param"] if need_wgrad else None,
+                             acc_into=acc_into)
     if kind == "cbn":
         x, mean, rstd = ctx
-        return ops.cbn_act_bwd(gy, x, mean, rstd, store.p[scope + "/scale"], store.p[scope + "/offset"], labels,
-                               store.g[scope + "/scale"], store.g[scope + "/offset"], ACT_MIU, dbias=dbias)
-    (x,) = ctx
-    return ops.prelu_bwd(gy, x, store.p[scope + "/prelu/param"],
-                         store.g[scope + "/prelu/param"] if need_wgrad else None, dbias=dbias)
+        g = ops.cbn_act_bwd(gy, x, mean, rstd, store.p[scope + "/scale"], store.p[scope + "/offset"], labels,
+                            store.g[scope + "/scale"], store.g[scope + "/offset"], ACT_MIU, dbias=dbias)
+    else:
+        (x,) = ctx
+        g = ops.prelu_bwd(gy, x, store.p[scope + "/prelu/param"],
+                          store.g[scope + "/prelu/param"] if need_wgrad else None, dbias=dbias)
+    return g if acc_into is None else ops.add_(acc_into, g)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -207,8 +214,7 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
     if need_ht_grad:
         g_a = ops.conv_dgrad(g_rgraw, wu, 0, cin)
         del g_rgraw
-        g_ht_in = norm_act_bwd(ops, st, scope + "/norm_activation_in", g_a, ctx["c_a"], labels, kind, nw)
-        ops.add_(g_ht, g_ht_in)
+        norm_act_bwd(ops, st, scope + "/norm_activation_in", g_a, ctx["c_a"], labels, kind, nw, acc_into=g_ht)
     return g_ht, g_x
 
 

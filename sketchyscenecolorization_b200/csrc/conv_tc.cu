@@ -2420,6 +2420,12 @@ static int launch_halo2(HaloArgs& h, cudaStream_t s) {
   return check_launch("conv_halo2");
 }
 
+// lowest tile efficiency at which the halo-reuse kernel still takes a layer (env FGC_HALO_MIN_EFF; 24 x 24 images tile at 75 %)
+static double halo_min_eff() {
+  static double v = -1.0;
+  if (v < 0) { const char* e = getenv("FGC_HALO_MIN_EFF"); v = e ? atof(e) : 0.8; if (v <= 0.0 || v > 1.0) v = 0.8; }
+  return v;
+}
 static double halo_eff(const ConvGeom& g, int mt) {       // tile efficiency: (16*mt) x 8 rectangles against the image size
   int th = 16 * mt;
   double cover = (double)(((g.OH + th - 1) / th) * th) * (((g.OW + 7) / 8) * 8);
@@ -2449,7 +2455,7 @@ static bool conv_halo_eligible(const IgemmArgs& ia, int bn) {
   }
   if (!any_big || nitems > kMaxItems || g.nslabs >= 0x4000) return false;
   (void)bn;
-  return halo_eff(g, 1) >= 0.8 || halo_eff(g, 2) >= 0.8;
+  return halo_eff(g, 1) >= halo_min_eff() || halo_eff(g, 2) >= halo_min_eff();
 }
 
 // returns -1 when the layer is not eligible (the caller falls back to conv_igemm_kernel), else the launch status
@@ -2472,7 +2478,7 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
   // accumulators fill TMEM, the epilogue no longer overlaps the next tile and the layer gets slower (0.75 -> 0.80 ms)
   if (mt4 && mt == 2 && bn <= 64 && eff(4) >= eff(2) - 1e-9 && tiles2 >= 8LL * num_sms()) mt = 4;
   if (mode == 3 && bn <= 128 && eff(4) >= 0.8) mt = 4;           // tests: force the 64 x 8 tiles on small problems
-  if (eff(mt) < 0.8) return -1;               // e.g. 24x24 images (75%): the per-tap gather kernel wastes nothing there
+  if (eff(mt) < halo_min_eff()) return -1;    // e.g. 24x24 images (75%): the per-tap gather kernel wastes nothing there
   HaloArgs h;
   h.g = g;
   h.wp = ia.wp;

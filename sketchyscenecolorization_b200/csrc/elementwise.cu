@@ -320,7 +320,7 @@ __global__ void tanh_fwd_kernel(const T* __restrict__ x, long long nvec, T* __re
 }
 template <typename T, int V>
 __global__ void prelu_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ x, long long nvec,
-                                 const float* __restrict__ ap, float* da, T* __restrict__ gx) {
+                                 const float* __restrict__ ap, float* da, T* __restrict__ gx, int accumulate) {
   __shared__ float red[32];
   const float a = *ap;
   float acc = 0.f;
@@ -333,6 +333,12 @@ __global__ void prelu_bwd_kernel(const T* __restrict__ gy, const T* __restrict__
       bool m = a * v[k] >= v[k];
       o[k] = m ? a * g[k] : g[k];
       if (m) acc += g[k] * v[k];
+    }
+    if (accumulate) {                            // gx += : the gradient joins what other branches have left there
+      float old[kMaxV];
+      ldv<T, V>(gx + i * V, old);
+#pragma unroll
+      for (int k = 0; k < V; k++) o[k] += old[k];
     }
     stv<T, V>(gx + i * V, o);
   }
@@ -1095,8 +1101,17 @@ int fgc_tanh_fwd(const void* x, int dtype, long long n, void* y, fgc_stream stre
   FGC_LAUNCH_CHECK("tanh_fwd");
   return FGC_OK;
 }
+static int prelu_bwd_run(const void* gy, const void* x, int dtype, long long n, int C, const float* a, float* da, float* dbias,
+                         void* gx, int accumulate, fgc_stream stream);
 int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, int C, const float* a, float* da, float* dbias,
                   void* gx, fgc_stream stream) {
+  return prelu_bwd_run(gy, x, dtype, n, C, a, da, dbias, gx, 0, stream);
+}
+int fgc_prelu_bwd_acc(const void* gy, const void* x, int dtype, long long n, const float* a, float* da, void* gx, fgc_stream stream) {
+  return prelu_bwd_run(gy, x, dtype, n, 0, a, da, nullptr, gx, 1, stream);
+}
+static int prelu_bwd_run(const void* gy, const void* x, int dtype, long long n, int C, const float* a, float* da, float* dbias,
+                         void* gx, int accumulate, fgc_stream stream) {
   cudaStream_t s = as_stream(stream);
   if (dbias) {
     FGC_REQUIRE(C > 0 && n % C == 0 && C <= 1024, "prelu_bwd: bad channel count %d for the bias-gradient variant", C);
@@ -1114,7 +1129,7 @@ int fgc_prelu_bwd(const void* gy, const void* x, int dtype, long long n, int C, 
   int vec = vmin(vmin(vec_width(x, n, dtype), vec_width(gy, n, dtype)), vec_width(gx, n, dtype));
   FGC_DISPATCH_TV(dtype, vec, T, V, {
     long long nvec = n / V;
-    prelu_bwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)gy, (const T*)x, nvec, a, da, (T*)gx);
+    prelu_bwd_kernel<T, V><<<ew_grid(nvec, 256), 256, 0, s>>>((const T*)gy, (const T*)x, nvec, a, da, (T*)gx, accumulate);
   });
   count_launch();
   FGC_LAUNCH_CHECK("prelu_bwd");

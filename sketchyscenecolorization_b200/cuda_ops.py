@@ -296,8 +296,13 @@ class CudaOps(OpsBase):
         check(self.lib.fgc_prelu_fwd(self._p(x), self._dt(x), x.numel(), self._f32(a), self._p(y), self._s()), "prelu_fwd")
         return y
 
-    def prelu_bwd(self, gy, x, a, da, dbias=None):
+    def prelu_bwd(self, gy, x, a, da, dbias=None, acc_into=None):
         assert gy.dtype == x.dtype
+        if acc_into is not None:
+            assert dbias is None and acc_into.shape == x.shape and acc_into.dtype == x.dtype
+            check(self.lib.fgc_prelu_bwd_acc(self._p(gy), self._p(x), self._dt(x), x.numel(), self._f32(a),
+                                             None if da is None else self._f32(da), self._p(acc_into), self._s()), "prelu_bwd_acc")
+            return acc_into
         gx = self._empty(x.shape, x.dtype)
         check(self.lib.fgc_prelu_bwd(self._p(gy), self._p(x), self._dt(x), x.numel(), x.shape[-1], self._f32(a),
                                      None if da is None else self._f32(da),

@@ -68,8 +68,9 @@ class OpsBase:
         """max(a*x, x), a = fp32 scalar tensor (models_collection.prelu, :56-60)."""
         raise NotImplementedError
 
-    def prelu_bwd(self, gy, x, a, da, dbias=None):
-        """returns gx; accumulates da (None => skip)."""
+    def prelu_bwd(self, gy, x, a, da, dbias=None, acc_into=None):
+        """returns gx; accumulates da (None => skip).  acc_into: optional tensor the gradient is ADDED to (and returned)
+        instead of a new one (not together with dbias)."""
         raise NotImplementedError
 
     def minmax_fwd(self, x):

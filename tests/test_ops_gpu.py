@@ -265,6 +265,11 @@ def test_prelu_minmax_actbwd(env, shape):
     close(cu.prelu_bwd(gf, xf, af, da2, dbias=db), gx_r, 1e-6, "prelu bwd (dbias variant)")
     close(da2, da_r, 1e-4, "prelu da (dbias variant)")
     close(db, gx_r.reshape(-1, Cc).sum(0) - 0.25, 1e-5, "prelu dbias")
+    acc0 = rnd(shape, 9, dev)
+    da3 = torch.zeros((), device=dev)
+    got = cu.prelu_bwd(gf, xf, af, da3, acc_into=acc0.float().contiguous())
+    close(got, acc0 + gx_r, 1e-6, "prelu bwd (accumulating form)")
+    close(da3, da_r, 1e-4, "prelu da (accumulating form)")
     cs = torch.full((Cc,), 1.5, device=dev)
     cu.colsum_(gf, cs)
     close(cs, gy.reshape(-1, Cc).sum(0) + 1.5, 1e-5, "colsum")

@@ -141,7 +141,9 @@ class TorchOps(OpsBase):
         xc = self._c(x)
         return torch.where(a * xc >= xc, a * xc, xc).to(self.act_dtype)
 
-    def prelu_bwd(self, gy, x, a, da, dbias=None):
+    def prelu_bwd(self, gy, x, a, da, dbias=None, acc_into=None):
+        if acc_into is not None:
+            return acc_into.copy_(acc_into + self.prelu_bwd(gy, x, a, da))
         xc, g = self._c(x), self._c(gy)
         m = a * xc >= xc
         if da is not None:
