@@ -90,6 +90,15 @@ int fgc_conv2d_fwd_acc(const fgc_src* srcs, int nsrc, int src_dtype, int N, int 
                        const float* w, int k, int Cin_total, int Cout, const float* bias,
                        int stride, int pad_t, int pad_l, int OH, int OW, int act, int accumulate,
                        void* y, int y_dtype, void* ws, fgc_stream stream);
+/* One PHASE of a convolution whose result lives on a 2x finer grid: y [N, 2H, 2W, Cout] receives, at its pixels
+ * (2h + dy, 2w + dx), the stride-1 SAME convolution of the (bf16) sources with w (fp32 HWIO [k,k,Cin_total,Cout]); only the
+ * filter columns / rows whose bit is set in kw_mask / kh_mask carry weights (the rest of w is zero by contract and is
+ * skipped: no operand fetch, no MMA).  Use: the input gradient of a 3x3 layer whose OUTPUT gradient is the x2 nearest-
+ * neighbour upsample of a low-resolution tensor (the cell's Conv_2 under mean_pool, mru.py:437-457) is, per output phase, a
+ * 2x2-tap convolution of the low-resolution gradient with pre-summed filters -- 4 taps instead of 9 and no full-resolution
+ * gradient in memory.  Halo-reuse kernel only: FGC_EUNSUPPORTED (nothing launched) when the layer does not qualify. */
+int fgc_conv2d_fwd_phase(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W, const float* w, int k, int Cin_total,
+                         int Cout, int kw_mask, int kh_mask, int dy, int dx, void* y, int y_dtype, void* ws, fgc_stream stream);
 /* Second half of a column-folded k x k convolution with few outputs (models_collection.py:372-374, the 7x7 64 -> 3 head):
  * z [N,H,W,Cz] fp32 holds, in channel kw*Cout + co, the k x 1 VERTICAL convolution with filter column kw (computed by
  * fgc_conv2d_fwd_acc with flag 2 on a filter whose other columns are zero); y[n,h,w,co] = act(bias[co] +

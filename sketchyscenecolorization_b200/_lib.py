@@ -80,6 +80,7 @@ SIGNATURES = {
     "fgc_debug_set_trace": [_P, _I],
     "fgc_conv2d_fwd": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "fgc_conv2d_fwd_acc": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
+    "fgc_conv2d_fwd_phase": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "fgc_split_term": [_P, _LL, _I, _P, _P, _P],
     "fgc_tapsum_w": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _P],
     "fgc_conv2d_dgrad": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],

@@ -147,7 +147,11 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
     st, nw = wv.store, wv.need_wgrad
     x, ht = ctx["x"], ctx["ht"]
     cin = ht.shape[-1]
-    g_full = ops.unpool_bwd(g_out)                    # d/d(sk) = d/d(h2)
+    # d/d(h2) = up2(g_out) / 4.  With ops.phase_dgrad only Conv_2's weight gradient wants it in memory: the input gradient is
+    # then evaluated from g_out directly (ops.conv_dgrad_pooled_gy: per output phase a 2x2-tap convolution of the low-resolution
+    # gradient -- 2.25x fewer products; measured neutral on a B200, so it is an option)
+    phase = bool(getattr(ops, "phase_dgrad", False))
+    g_full = ops.unpool_bwd(g_out) if (nw or not phase) else None
     # bias gradients: column sums of the gradient at a conv output.  They come out of the kernel that produces that
     # gradient (dbias= of the norm / activation / min-max backward); for Conv_2 / Conv_3 the gradient is the un-pooled
     # g_out / 4 replicated 2x2, whose column sums equal those of the (4x smaller) g_out itself.
@@ -173,7 +177,7 @@ def enc_block_bwd(ops, wv, scope, g_out, ctx, labels, kind, *, need_x_grad=False
         else:
             ops.colsum_(g_out, db2)
         ops.conv_wgrad([(ctx["h1"], False)], g_full, dw2, None)
-    g_h1 = ops.conv_dgrad(g_full, w2, 0, w2.shape[2])
+    g_h1 = ops.conv_dgrad_pooled_gy(g_out, w2, 0, w2.shape[2]) if phase else ops.conv_dgrad(g_full, w2, 0, w2.shape[2])
     del g_full
     dw1, db1 = wv.grads(scope + "/Conv_1") if nw else (None, None)
     g_h1raw = norm_act_bwd(ops, st, scope + "/Conv_1", g_h1, ctx["c_h1"], labels, kind, nw, dbias=db1)

@@ -21,6 +21,7 @@ size_t conv_ws_bytes(const ConvGeom& g, int nout, int x3);
 extern int g_halo_mode, g_small_mode;
 extern long long g_conv_counts[6];
 extern int g_center_col;
+extern int g_phase_kw_mask, g_phase_kh_mask, g_phase_dy, g_phase_dx;
 extern long long* g_trace;
 extern int g_trace_cap;
 
@@ -120,6 +121,23 @@ int fgc_conv2d_fwd_acc(const fgc_src* srcs, int nsrc, int src_dtype, int N, int 
   e = conv_igemm_run(g, src_dtype, w, (long long)Cin_total * Cout, Cout, 1, 0, Cout, bias, act, accumulate & 1, y, y_dtype, ws, s);
   g_center_col = 0;
   return e;
+}
+
+int fgc_conv2d_fwd_phase(const fgc_src* srcs, int nsrc, int src_dtype, int N, int H, int W, const float* w, int k, int Cin_total,
+                         int Cout, int kw_mask, int kh_mask, int dy, int dx, void* y, int y_dtype, void* ws, fgc_stream stream) {
+  FGC_REQUIRE(k % 2 == 1 && k <= 15 && (dy == 0 || dy == 1) && (dx == 0 || dx == 1), "conv_fwd_phase: bad arguments");
+  FGC_REQUIRE((kw_mask & ((1 << k) - 1)) && (kh_mask & ((1 << k) - 1)), "conv_fwd_phase: empty tap mask");
+  if (conv_impl() == 1 || src_dtype != FGC_BF16) return FGC_EUNSUPPORTED;
+  ConvGeom g;
+  int e = build_geom(g, srcs, nsrc, N, H, W, k, 1, (k - 1) / 2, (k - 1) / 2, H, W, 1);
+  if (e) return e;
+  int cin = finish_geom(g);
+  FGC_REQUIRE(cin == Cin_total, "conv_fwd_phase: sources have %d channels, weights expect %d", cin, Cin_total);
+  g_phase_kw_mask = kw_mask; g_phase_kh_mask = kh_mask; g_phase_dy = dy; g_phase_dx = dx;
+  e = conv_igemm_run(g, src_dtype, w, (long long)Cin_total * Cout, Cout, 1, 0, Cout, nullptr, FGC_ACT_NONE, 0, y, y_dtype, ws,
+                     as_stream(stream), 2);
+  g_phase_kw_mask = g_phase_kh_mask = g_phase_dy = g_phase_dx = 0;
+  return e == 1 ? FGC_EUNSUPPORTED : e;          // 1 = kNotTaken: the halo-reuse kernel does not take this layer
 }
 
 int fgc_conv2d_dgrad(const void* gy, int gy_dtype, int N, int H, int W, const float* w, int k, int Cin_total,

@@ -789,6 +789,8 @@ struct HaloArgs {
   void* y;
   int y_dtype, vec_ok;
   int pool2;                 // y is [N, OH/2, OW/2, Nout]: 2x2 sums of the result (gradient w.r.t. an x2-upsampled source)
+  int kh_mask;               // filter rows that carry weights (bit kh; the others are zero by contract: no slab load, no MMA)
+  int up, up_dy, up_dx;      // up = 1: y is [N, 2*OH, 2*OW, Nout] and this launch writes its pixels (2h + up_dy, 2w + up_dx)
   const int4* tbl;           // slab table written by pack_weights_kernel (small slabs: source and first flattened index)
   int any_small;
   int box_rows;              // 16*MT + k - 1
@@ -918,15 +920,19 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
       const int buf = ti % NACC;
       mbar_wait(smem_u32(&acc_empty[buf]), ((ti / NACC) & 1) ^ 1);
       tc_fence_after();
+      bool first = true;                               // the tile's first MMA group overwrites the accumulator
       for (int it = 0; it < nitems; it++, ga++) {
         const int slot = ga % a_slots;
         const uint32_t item = a.items[it];
         const bool big = (item & 0x8000u) != 0;
         const bool boxed = (item & 0xC000u) != 0;      // A operand is a TMA box (8-pixel rows), not a gathered tile
         const int nb = big ? k : 1;
+        const int rows = big ? a.kh_mask : 1;          // filter rows of this box that carry weights
+        const int jlast = 31 - __clz(rows);
         mbar_wait(smem_u32(&a_full[slot]), (ga / a_slots) & 1);
         const uint32_t sa = smem_u32(sA + (size_t)slot * a.a_slot_bytes);
-        for (int j = 0; j < nb; j++, gb++) {
+        for (int j = 0; j < nb; j++) {
+          if (!((rows >> j) & 1)) continue;
           const int bslot = gb % b_slots;
           mbar_wait(smem_u32(&b_full[bslot]), (gb / b_slots) & 1);
           tc_fence_after();
@@ -940,7 +946,7 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
               const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS);
 #pragma unroll
               for (int kk = 0; kk < 4; kk++) {
-                const uint32_t acc = (it > 0 || j > 0 || kk > 0) ? 1u : 0u;
+                const uint32_t acc = (!first || kk > 0) ? 1u : 0u;
                 umma_bf16(d_tmem, db + 2 * kk, da + 2 * kk, IDESC, acc);
               }
             } else {
@@ -951,17 +957,19 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_COLS + tt * BN);
 #pragma unroll
                 for (int kk = 0; kk < 4; kk++) {
-                  const uint32_t acc = (it > 0 || j > 0 || kk > 0) ? 1u : 0u;
+                  const uint32_t acc = (!first || kk > 0) ? 1u : 0u;
                   umma_bf16(d_tmem, da + 2 * kk, db + 2 * kk, IDESC, acc);
                 }
               }
             }
             umma_commit(smem_u32(&b_empty[bslot]));
-            if (j == nb - 1) {
+            if (j == jlast) {
               umma_commit(smem_u32(&a_empty[slot]));
               if (it == nitems - 1) umma_commit(smem_u32(&acc_full[buf]));
             }
           }
+          first = false;
+          gb++;
           __syncwarp();
         }
       }
@@ -1022,7 +1030,9 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
           const int s2 = (item >> 12) & 3, kw = (item >> 8) & 15, cg = item & 0xFF;
           const int ncb = big ? (g.C[s2] + 63) >> 6 : 0;
           const int nb = big ? k : 1;
-          for (int j = 0; j < nb; j++, gb++) {
+          const int rows = big ? a.kh_mask : 1;
+          for (int j = 0; j < nb; j++) {
+            if (!((rows >> j) & 1)) continue;
             const int slab = big ? g.slab_begin[s2] + (j * k + kw) * ncb + cg
                                  : ((item & 0x4000u) ? g.slab_begin[s2] + cg : (int)item);
             const int bslot = gb % b_slots;
@@ -1030,6 +1040,7 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
             const uint32_t bar = smem_u32(&b_full[bslot]);
             mbar_arrive_expect_tx(bar, B_BYTES);
             bulk_g2s(smem_u32(sB + (size_t)bslot * B_BYTES), a.wp + ((long long)slab * a.Npad + n0) * 64, B_BYTES, bar);
+            gb++;
           }
         }
       }
@@ -1102,7 +1113,8 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
           const bool mvalid = oh < g.OH && ow < g.OW && (!a.pool2 || ((lane & 1) == 0 && (lane & 8) == 0));
           if (!mvalid || nb >= a.Nout) continue;
           const long long m = a.pool2 ? ((long long)n * (g.OH >> 1) + (oh >> 1)) * (g.OW >> 1) + (ow >> 1)
-                                      : ((long long)n * g.OH + oh) * g.OW + ow;
+                              : a.up ? ((long long)n * (2 * g.OH) + 2 * oh + a.up_dy) * (2 * g.OW) + 2 * ow + a.up_dx
+                                     : ((long long)n * g.OH + oh) * g.OW + ow;
           const int nrem = a.Nout - nb;
           __nv_bfloat16* yp = reinterpret_cast<__nv_bfloat16*>(a.y) + m * a.Nout + nb;
           const uint4* sp = reinterpret_cast<const uint4*>(stage + lane * kSwapStageRow);
@@ -1137,7 +1149,8 @@ __global__ void __launch_bounds__(32 * (8 + halo_epi_warps(MT)), 1) conv_halo_ke
         // the lane of the even row / even column stores the sum at the low-resolution pixel
         const bool mvalid = oh < g.OH && ow < g.OW && (!a.pool2 || ((l & 1) == 0 && (l & 8) == 0));
         const long long m = a.pool2 ? ((long long)n * (g.OH >> 1) + (oh >> 1)) * (g.OW >> 1) + (ow >> 1)
-                                    : ((long long)n * g.OH + oh) * g.OW + ow;
+                            : a.up ? ((long long)n * (2 * g.OH) + 2 * oh + a.up_dy) * (2 * g.OW) + 2 * ow + a.up_dx
+                                   : ((long long)n * g.OH + oh) * g.OW + ow;
         const bool last_tile = tile + EW / 4 >= MT;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -2200,6 +2213,9 @@ long long* g_trace = nullptr;
 int g_trace_cap = 0;
 int g_halo_mode = -1;      // fgc_set_conv_flags / env FGC_HALO
 int g_center_col = 0;      // set around one forward call (fgc_conv2d_fwd_acc flag 2): only the centre filter column carries weights
+// set around one call of fgc_conv2d_fwd_phase: the filter's columns / rows that carry weights (bit masks; 0 = not a phase call)
+// and the output phase (dy, dx) of the 2x finer grid this launch writes
+int g_phase_kw_mask = 0, g_phase_kh_mask = 0, g_phase_dy = 0, g_phase_dx = 0;
 
 static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s);
 static bool conv_halo_eligible(const IgemmArgs& ia, int bn);
@@ -2225,7 +2241,7 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
     probe.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
     const int bn0 = pick_bn(nout, src_dtype == FGC_F32);
     probe.Npad = ((nout + bn0 - 1) / bn0) * bn0;
-    if (src_dtype == FGC_F32 || (g.OH & 1) || (g.OW & 1) || !conv_halo_eligible(probe, bn0)) return kNotTaken;
+    if (src_dtype == FGC_F32 || (pool2 == 1 && ((g.OH & 1) || (g.OW & 1))) || !conv_halo_eligible(probe, bn0)) return kNotTaken;
   }
   FGC_REQUIRE(g.M < (1LL << 31), "conv: more than 2^31 output pixels");
   if (!pool2) {
@@ -2271,11 +2287,12 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
   a.any_small = 0;
   for (int i = 0; i < g.nsrc; i++) a.any_small |= !g.big[i];
   a.fast = (g.stride == 1 && g.OH == g.H && g.OW == g.W && g.H < 32768 && g.W < 32768) ? 1 : 0;
-  a.pool2 = pool2;
+  a.pool2 = pool2 == 1;      // pool2 == 2: a phase launch (g_phase_*), likewise a halo-kernel-only form
   if (x3) return launch_igemm_f32(a, bn, s);
   {
     int r = conv_halo_try(a, bn, s);      // stride-1 SAME layers with wide sources: halo-reuse kernel (tensor-map TMA)
     if (r >= 0) return r;
+    if (pool2 == 2) return kNotTaken;     // phase launch: the caller falls back to the full-resolution form
     FGC_REQUIRE(!pool2, "conv: pooled output requested but the halo-reuse kernel did not take the layer");
   }
   // two A tiles per CTA (each weight tile feeds 256 pixels) once there is enough work to fill the machine twice over
@@ -2491,6 +2508,13 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
   h.y_dtype = ia.y_dtype;
   h.vec_ok = ia.vec_ok;
   h.pool2 = ia.pool2;
+  const bool phase = g_phase_kh_mask != 0;
+  h.kh_mask = phase ? (g_phase_kh_mask & ((1 << g.k) - 1)) : ((1 << g.k) - 1);
+  h.up = phase ? 1 : 0;
+  h.up_dy = g_phase_dy;
+  h.up_dx = g_phase_dx;
+  const int kw_mask = g_center_col ? (1 << g.pad_l) : (phase ? g_phase_kw_mask : -1);
+  if (phase && (any_gather || !h.kh_mask || !(kw_mask & ((1 << g.k) - 1)))) return -1;
   h.tbl = ia.tbl;
   h.any_small = any_gather ? 1 : 0;
   int ni = 0;
@@ -2500,7 +2524,7 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
       if (ncb > 255) return -1;
       for (int cg = 0; cg < ncb; cg++)
         for (int kw = 0; kw < g.k; kw++) {
-          if (g_center_col && kw != g.pad_l) continue;       // the other filter columns are zero by contract: skip their boxes
+          if (!((kw_mask >> kw) & 1)) continue;              // the other filter columns are zero by contract: skip their boxes
           if (ni >= kMaxItems) return -1;
           h.items[ni++] = (uint16_t)(0x8000u | (i << 12) | (kw << 8) | cg);
         }
@@ -2532,7 +2556,7 @@ static int conv_halo_try(const IgemmArgs& ia, int bn, cudaStream_t s) {
       static int halo2 = -1, swap = -1;
       if (halo2 < 0) { const char* e = getenv("FGC_HALO2"); halo2 = e ? atoi(e) : 0; }
       if (swap < 0) { const char* e = getenv("FGC_HALO_SWAP"); swap = e ? atoi(e) : 1; }
-      if (mt == 2 && halo2 && !any_gather) {
+      if (mt == 2 && halo2 && !any_gather && !phase) {
         int r = launch_halo2<2>(h, s);
         if (r >= 0) return r;
       }

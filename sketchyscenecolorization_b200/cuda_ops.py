@@ -41,6 +41,7 @@ class CudaOps(OpsBase):
         self.conv_terms = conv_terms
         self.fold_narrow_dgrad = os.environ.get("FGC_FOLD_DGRAD", "1") != "0"
         self.fuse_gate_prelu = os.environ.get("FGC_GATE_PRELU", "1") != "0"
+        self.phase_dgrad = os.environ.get("FGC_PHASE_DGRAD", "0") == "1"       # measured neutral (profiles/r2ae_*): opt-in
         if not torch.cuda.is_available():
             raise RuntimeError("CudaOps needs a CUDA device (sm_100a); there is no CPU path in this package")
         if act_dtype not in _DT:
@@ -49,6 +50,8 @@ class CudaOps(OpsBase):
         self.device = torch.device(device)
         self.act_dtype = act_dtype
         torch.cuda.set_device(self.device)
+        # constants of conv_dgrad_pooled_gy, on the device before any step is captured into a CUDA graph
+        self._phase_mix = {d: torch.tensor(self._PHASE_MIX[d], dtype=torch.float32, device=self.device) for d in (0, 1)}
 
     # ---------------- helpers ----------------
     @staticmethod
@@ -234,6 +237,34 @@ class CudaOps(OpsBase):
         check(self.lib.fgc_conv2d_dgrad(self._p(gy), self._dt(gy), N, H, W, self._f32(w), k, cin, cout, c_off, c_len,
                                         1 if ups else 0, 1 if acc else 0, self._p(out), self._dt(out),
                                         self._p(scratch), self._p(ws), self._p(gy_patch), self._s()), "conv2d_dgrad")
+        return out
+
+    # per dimension: filter row tau of the phase filter collects the forward taps t with A[d][tau][t] = 1 (see conv_dgrad_pooled_gy)
+    _PHASE_MIX = {0: ((0, 0, 1), (1, 1, 0), (0, 0, 0)), 1: ((0, 0, 0), (0, 1, 1), (1, 0, 0))}
+    _PHASE_MASK = {0: 0b011, 1: 0b110}
+
+    def conv_dgrad_pooled_gy(self, g_low, w, c_off, c_len):
+        """Per output phase (dy, dx) of the full-resolution gradient, the source pixel 2q + d - (t - 1) of forward tap t lies
+        in the low-resolution cell q + o: d = 0 -> t = 0, 1 in o = 0 and t = 2 in o = -1; d = 1 -> t = 0 in o = +1 and t = 1, 2
+        in o = 0.  So each phase is a 2x2-tap convolution of g_low with filters pre-summed over the taps that share a cell
+        (x 1/4 for the mean): four fgc_conv2d_fwd_phase launches that write their phase of the result directly."""
+        N, h, wd, cout = g_low.shape
+        k = w.shape[0]
+        if not self.phase_dgrad or k != 3 or g_low.dtype != torch.bfloat16 or cout < 64 or wd % 8 != 0:
+            return super().conv_dgrad_pooled_gy(g_low, w, c_off, c_len)
+        wt = (w[:, :, c_off:c_off + c_len, :].permute(0, 1, 3, 2) * 0.25).contiguous()          # [ty, tx, co, ci]
+        out = self._empty((N, 2 * h, 2 * wd, c_len), self.act_dtype)
+        arr, _, _, _, dt = self._srcs([(g_low, False)])
+        ws = self._ws([cout], 3, c_len, dt)
+        mix = self._phase_mix
+        for dy in (0, 1):
+            for dx in (0, 1):
+                f = torch.einsum('ab,cd,bdxy->acxy', mix[dy], mix[dx], wt).contiguous()
+                rc = self.lib.fgc_conv2d_fwd_phase(arr, 1, dt, N, h, wd, self._f32(f), 3, cout, c_len, self._PHASE_MASK[dx],
+                                                   self._PHASE_MASK[dy], dy, dx, self._p(out), self._dt(out), self._p(ws), self._s())
+                if rc == -3 and dy == 0 and dx == 0:          # FGC_EUNSUPPORTED: not a halo-kernel layer
+                    return super().conv_dgrad_pooled_gy(g_low, w, c_off, c_len)
+                check(rc, "conv2d_fwd_phase")
         return out
 
     def conv_wgrad(self, srcs, gy, dw, db, *, stride=1, gy_patch=None):

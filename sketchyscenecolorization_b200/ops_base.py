@@ -42,6 +42,12 @@ class OpsBase:
         ups=True: the source was read through the x2 upsample, the result is the 2x2-summed low-res gradient."""
         raise NotImplementedError
 
+    def conv_dgrad_pooled_gy(self, g_low, w, c_off, c_len):
+        """conv_dgrad(up2(g_low) / 4, w, c_off, c_len): the input gradient of a 3x3 stride-1 layer that is followed by the 2x2
+        mean pool (mru.py:437-457), from the LOW-resolution output gradient; result [N, 2h, 2w, c_len].  Implementations may
+        evaluate it per output phase as 2x2-tap convolutions of g_low (4 taps instead of 9, nothing upsampled in memory)."""
+        return self.conv_dgrad(self.unpool_bwd(g_low), w, c_off, c_len)
+
     def conv_wgrad(self, srcs, gy, dw, db, *, stride=1, gy_patch=None):
         """dw += d/dw, db += sum_{n,h,w} gy  (always accumulating; dw HWIO fp32 view, db fp32 [Cout] or None)."""
         raise NotImplementedError

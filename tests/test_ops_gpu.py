@@ -5,6 +5,7 @@ tcgen05 tensor-core path (the product) and the CUDA-core checker, on shapes that
 path (big / small sources, concat, upsampled source, stride 2, 7x7, 1x1, FC rows, ragged M and N tiles).
 """
 import math
+import os
 
 import pytest
 import torch
@@ -106,6 +107,38 @@ def test_conv_fwd(env, case, impl):
         close(gotb, want, 3e-2, "conv_fwd bf16")
     finally:
         _set_impl(cu, 0)
+
+
+@pytest.mark.parametrize("case", [
+    (4, 16, 16, 128, 128, 0, 128),      # the discriminator's Conv_2 form: 128 -> 128, exchanged-role epilogue
+    (2, 32, 24, 64, 96, 0, 64),         # 64-wide tiles, channel slice at the start of a wider filter
+    (2, 16, 16, 256, 256, 0, 256),      # 256-wide N tile
+    (3, 16, 8, 72, 40, 8, 24),          # ragged channel group (72 = 64 + 8), ragged N, slice in the middle
+    (2, 12, 12, 64, 64, 0, 64),         # width not a multiple of 8: falls back to the full-resolution form
+], ids=["128x128", "64-slice", "256", "ragged", "fallback"])
+def test_conv_dgrad_pooled_gy(env, case):
+    """Input gradient of a 3x3 layer under the 2x2 mean pool from the LOW-resolution output gradient: four phase launches of
+    2x2-tap convolutions (fgc_conv2d_fwd_phase) against conv_dgrad of the upsampled gradient."""
+    cub, cu, ref, dev = env["cub"], env["cu"], env["ref"], env["dev"]
+    N, h, w_, cout, cin_total, c_off, c_len = case
+    g_low = rnd((N, h, w_, cout), 1, dev)
+    w = rnd((3, 3, cin_total, cout), 2, dev, 1.0 / math.sqrt(9 * cout))
+    want = ref.conv_dgrad(ref.unpool_bwd(g_low), w, c_off, c_len)
+    before = cub.launch_count()
+    cub.phase_dgrad = True
+    got = cub.conv_dgrad_pooled_gy(g_low.bfloat16().contiguous(), w.float().contiguous(), c_off, c_len)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    close(got, want, 3e-2, "conv_dgrad_pooled_gy bf16")
+    cub.phase_dgrad = False
+    try:
+        plain = cub.conv_dgrad_pooled_gy(g_low.bfloat16().contiguous(), w.float().contiguous(), c_off, c_len)
+    finally:
+        cub.phase_dgrad = os.environ.get("FGC_PHASE_DGRAD", "0") == "1"
+    close(got, plain.double(), 2e-2, "phase form against the full-resolution form")
+    got32 = cu.conv_dgrad_pooled_gy(g_low.float().contiguous(), w.float().contiguous(), c_off, c_len)      # fp32: full-resolution form
+    close(got32, want, 1e-4, "conv_dgrad_pooled_gy fp32")
+    assert cub.launch_count() > before
 
 
 @pytest.mark.parametrize("acc", [False, True], ids=["write", "acc"])
