@@ -76,6 +76,10 @@ int fgc_debug_conv_counts(long long out[6]);
 /* debug aid: per-role event trace (role, event, tile, clock64) of CTA 0 of the implicit-GEMM kernel; buf holds
  * 4 + 4*capacity int64 on the device, buf[0] is the event count.  NULL disables. */
 int fgc_debug_set_trace(long long* buf, int capacity);
+/* measurement aid: on = 1 makes the forward / input-gradient calls skip their weight-packing launch -- the caller guarantees
+ * that `ws` still holds the tiles an identical earlier call packed there.  bench.py times the dominant convolution kernel
+ * alone with it (the roofline figure is per kernel launch); the product path never sets it. */
+int fgc_debug_keep_packed(int on);
 
 /* y[N,OH,OW,Cout] = act(conv(concat_c(srcs), w) + bias); SAME padding (pad_t/pad_l = TF's top/left pad).
  * w: fp32 HWIO [k,k,Cin_total,Cout]; bias fp32 [Cout] or NULL.  fp32 sources run the bf16x3 split-accumulate

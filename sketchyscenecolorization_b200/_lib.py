@@ -78,6 +78,7 @@ SIGNATURES = {
     "fgc_debug_conv_counts": [_P],
     "fgc_im2col_small": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "fgc_debug_set_trace": [_P, _I],
+    "fgc_debug_keep_packed": [_I],
     "fgc_conv2d_fwd": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "fgc_conv2d_fwd_acc": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],
     "fgc_conv2d_fwd_phase": [C.POINTER(FgcSrc), _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P],

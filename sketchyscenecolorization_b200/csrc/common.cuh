@@ -69,6 +69,173 @@ template <> __device__ __forceinline__ void ldv<__nv_bfloat16, 8>(const __nv_bfl
   float2 f2 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.z)), f3 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.w));
   v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
 }
+// ---- raw vector loads + row walker ------------------------------------------------------------------
+// ldv widens right behind the load; in an unrolled loop ptxas then keeps "load, unpack, load, unpack" order and every thread
+// has ONE load in flight (chan_stats_kernel: LDGs 27-32 instructions apart, 3.7 TB/s where a bare read loop of the same shape
+// reaches 6.5, scripts/microbench/readbw.cu).  RawV keeps the loaded bytes as they are; walk_rows issues the U loads of a group
+// of rows back to back, then their arithmetic.  PREFETCH = true also issues the NEXT group's loads before the arithmetic of the
+// current one: measured slower everywhere (scripts/microbench/rowwalk.cu, profiles/r2ai_rowwalk_sweep.log: the second set of
+// raw registers spills under the occupancy caps these kernels need) -- kept for the record, off.  Measured best on the 604 MB
+// tensor: one tensor U = 4 at 4 blocks of 256 per SM (6.6 TB/s read-only, 6.3-6.5 read + write), two tensors U = 2 at 3 blocks
+// per SM (6.4 TB/s), in a single launch of ~24 blocks per SM.
+template <typename T, int V> struct RawV;
+template <> struct RawV<__nv_bfloat16, 8> { uint4 q; };
+template <> struct RawV<__nv_bfloat16, 4> { uint2 q; };
+template <> struct RawV<__nv_bfloat16, 1> { unsigned short q; };
+template <> struct RawV<float, 8> { float4 q, q1; };
+template <> struct RawV<float, 4> { float4 q; };
+template <> struct RawV<float, 1> { float q; };
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* p, RawV<__nv_bfloat16, 8>& r) { r.q = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* p, RawV<__nv_bfloat16, 4>& r) { r.q = __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* p, RawV<__nv_bfloat16, 1>& r) { r.q = __ldg(reinterpret_cast<const unsigned short*>(p)); }
+__device__ __forceinline__ void ldraw(const float* p, RawV<float, 8>& r) {
+  r.q = __ldg(reinterpret_cast<const float4*>(p)); r.q1 = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void ldraw(const float* p, RawV<float, 4>& r) { r.q = __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void ldraw(const float* p, RawV<float, 1>& r) { r.q = __ldg(p); }
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ void widen(const RawV<__nv_bfloat16, 8>& r, float (&v)[kMaxV]) {
+  v[0] = bf16lo(r.q.x); v[1] = bf16hi(r.q.x); v[2] = bf16lo(r.q.y); v[3] = bf16hi(r.q.y);
+  v[4] = bf16lo(r.q.z); v[5] = bf16hi(r.q.z); v[6] = bf16lo(r.q.w); v[7] = bf16hi(r.q.w);
+}
+__device__ __forceinline__ void widen(const RawV<__nv_bfloat16, 4>& r, float (&v)[kMaxV]) {
+  v[0] = bf16lo(r.q.x); v[1] = bf16hi(r.q.x); v[2] = bf16lo(r.q.y); v[3] = bf16hi(r.q.y);
+}
+__device__ __forceinline__ void widen(const RawV<__nv_bfloat16, 1>& r, float (&v)[kMaxV]) { v[0] = __uint_as_float((uint32_t)r.q << 16); }
+__device__ __forceinline__ void widen(const RawV<float, 8>& r, float (&v)[kMaxV]) {
+  v[0] = r.q.x; v[1] = r.q.y; v[2] = r.q.z; v[3] = r.q.w; v[4] = r.q1.x; v[5] = r.q1.y; v[6] = r.q1.z; v[7] = r.q1.w;
+}
+__device__ __forceinline__ void widen(const RawV<float, 4>& r, float (&v)[kMaxV]) { v[0] = r.q.x; v[1] = r.q.y; v[2] = r.q.z; v[3] = r.q.w; }
+__device__ __forceinline__ void widen(const RawV<float, 1>& r, float (&v)[kMaxV]) { v[0] = r.q; }
+
+// rows rb, rb + lanes, ... < r1 of one tensor; p points at this thread's V elements of row 0, rows are C elements apart;
+// f(row, values) per row, in row order.
+template <typename T, int V, int U, bool PREFETCH = false, typename F>
+__device__ __forceinline__ void walk_rows(const T* __restrict__ p, int C, int rb, int r1, int lanes, F&& f) {
+  const int nrows = rb < r1 ? (r1 - rb + lanes - 1) / lanes : 0;
+  const int nfull = nrows / U;
+  if (!PREFETCH) {                               // U loads, then their arithmetic (fewer live registers)
+    for (int g = 0; g < nfull; g++, rb += U * lanes) {
+      RawV<T, V> t[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) ldraw(p + (long long)(rb + u * lanes) * C, t[u]);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        float a[kMaxV];
+        widen(t[u], a);
+        f(rb + u * lanes, a);
+      }
+    }
+    for (; rb < r1; rb += lanes) {
+      RawV<T, V> t;
+      ldraw(p + (long long)rb * C, t);
+      float a[kMaxV];
+      widen(t, a);
+      f(rb, a);
+    }
+    return;
+  }
+  RawV<T, V> cur[U], nxt[U];
+  if (nfull > 0) {
+#pragma unroll
+    for (int u = 0; u < U; u++) ldraw(p + (long long)(rb + u * lanes) * C, cur[u]);
+  }
+  for (int g = 0; g < nfull; g++) {
+    const bool more = g + 1 < nfull;
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < U; u++) ldraw(p + (long long)(rb + (U + u) * lanes) * C, nxt[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      float a[kMaxV];
+      widen(cur[u], a);
+      f(rb + u * lanes, a);
+    }
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < U; u++) cur[u] = nxt[u];
+    }
+    rb += U * lanes;
+  }
+  for (; rb < r1; rb += lanes) {
+    RawV<T, V> t;
+    ldraw(p + (long long)rb * C, t);
+    float a[kMaxV];
+    widen(t, a);
+    f(rb, a);
+  }
+}
+// the same over two tensors read at the same offsets: f(row, values of p, values of q)
+template <typename T, int V, int U, bool PREFETCH = false, typename F>
+__device__ __forceinline__ void walk_rows2(const T* __restrict__ p, const T* __restrict__ q, int C, int rb, int r1, int lanes, F&& f) {
+  const int nrows = rb < r1 ? (r1 - rb + lanes - 1) / lanes : 0;
+  const int nfull = nrows / U;
+  if (!PREFETCH) {
+    for (int g = 0; g < nfull; g++, rb += U * lanes) {
+      RawV<T, V> tp[U], tq[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long long o = (long long)(rb + u * lanes) * C;
+        ldraw(p + o, tp[u]); ldraw(q + o, tq[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        float a[kMaxV], b[kMaxV];
+        widen(tp[u], a); widen(tq[u], b);
+        f(rb + u * lanes, a, b);
+      }
+    }
+    for (; rb < r1; rb += lanes) {
+      RawV<T, V> tp, tq;
+      const long long o = (long long)rb * C;
+      ldraw(p + o, tp); ldraw(q + o, tq);
+      float a[kMaxV], b[kMaxV];
+      widen(tp, a); widen(tq, b);
+      f(rb, a, b);
+    }
+    return;
+  }
+  RawV<T, V> cp[U], cq[U], np[U], nq[U];
+  if (nfull > 0) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long o = (long long)(rb + u * lanes) * C;
+      ldraw(p + o, cp[u]); ldraw(q + o, cq[u]);
+    }
+  }
+  for (int g = 0; g < nfull; g++) {
+    const bool more = g + 1 < nfull;
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long long o = (long long)(rb + (U + u) * lanes) * C;
+        ldraw(p + o, np[u]); ldraw(q + o, nq[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      float a[kMaxV], b[kMaxV];
+      widen(cp[u], a); widen(cq[u], b);
+      f(rb + u * lanes, a, b);
+    }
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < U; u++) { cp[u] = np[u]; cq[u] = nq[u]; }
+    }
+    rb += U * lanes;
+  }
+  for (; rb < r1; rb += lanes) {
+    RawV<T, V> tp, tq;
+    const long long o = (long long)rb * C;
+    ldraw(p + o, tp); ldraw(q + o, tq);
+    float a[kMaxV], b[kMaxV];
+    widen(tp, a); widen(tq, b);
+    f(rb, a, b);
+  }
+}
+
 __device__ __forceinline__ uint32_t bf16x2_bits(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -18,7 +18,7 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
 int conv_wgrad_run(ConvGeom& g, int src_dtype, const void* gy, int Cin_total, int Cout, float* dw, cudaStream_t s,
                    const void* gy_patch = nullptr);
 size_t conv_ws_bytes(const ConvGeom& g, int nout, int x3);
-extern int g_halo_mode, g_small_mode;
+extern int g_halo_mode, g_small_mode, g_keep_packed;
 extern long long g_conv_counts[6];
 extern int g_center_col;
 extern int g_phase_kw_mask, g_phase_kh_mask, g_phase_dy, g_phase_dx;
@@ -67,6 +67,11 @@ int fgc_debug_set_trace(long long* buf, int capacity) {
 int fgc_set_conv_flags(int halo, int small) {
   if (halo >= 0) g_halo_mode = halo;
   if (small >= 0) g_small_mode = small;
+  return FGC_OK;
+}
+
+int fgc_debug_keep_packed(int on) {
+  g_keep_packed = on ? 1 : 0;
   return FGC_OK;
 }
 

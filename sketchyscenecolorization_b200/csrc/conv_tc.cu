@@ -2212,6 +2212,7 @@ static int launch_igemm_bf16(IgemmArgs& a, int bn, int mt, cudaStream_t s) {
 long long* g_trace = nullptr;
 int g_trace_cap = 0;
 int g_halo_mode = -1;      // fgc_set_conv_flags / env FGC_HALO
+int g_keep_packed = 0;     // fgc_debug_keep_packed: the workspace already holds this call's packed weights (measurement aid)
 int g_center_col = 0;      // set around one forward call (fgc_conv2d_fwd_acc flag 2): only the centre filter column carries weights
 // set around one call of fgc_conv2d_fwd_phase: the filter's columns / rows that carry weights (bit masks; 0 = not a phase call)
 // and the output phase (dy, dx) of the 2x finer grid this launch writes
@@ -2258,7 +2259,7 @@ int conv_igemm_run(ConvGeom& g, int src_dtype, const float* w, long long tap_str
   const int bn = pick_bn(nout, x3);
   const int npad = ((nout + bn - 1) / bn) * bn;
   int4* tbl = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(ws) + (size_t)g.nslabs * npad * 64 * 2 * (x3 ? 2 : 1));
-  {
+  if (!g_keep_packed) {
     long long total = (long long)g.nslabs * npad * 8;
     int grid = (int)((total + 255) / 256);
     if (grid > num_sms() * 8) grid = num_sms() * 8;

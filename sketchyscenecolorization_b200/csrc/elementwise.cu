@@ -76,21 +76,11 @@ __global__ void __launch_bounds__(256, 4) chan_stats_kernel(const T* __restrict_
     float s[V], ss[V];
 #pragma unroll
     for (int i = 0; i < V; i++) s[i] = ss[i] = 0.f;
-    const T* px = x + v * V;
-    for (long long rb = r0 + rl; rb < r1; rb += (long long)lanes * 4) {      // four independent row loads in flight
-      float a[4][kMaxV];
+    // four row loads per group, the next group's loads issued before this group's sums (walk_rows, common.cuh)
+    walk_rows<T, V, 4>(x + r0 * C + v * V, C, rl, (int)(r1 - r0), lanes, [&](int, const float (&a)[kMaxV]) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        long long r = rb + (long long)j * lanes;
-        if (r < r1) ldv<T, V>(px + r * C, a[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        if (rb + (long long)j * lanes >= r1) continue;
-#pragma unroll
-        for (int i = 0; i < V; i++) { s[i] += a[j][i]; ss[i] = fmaf(a[j][i], a[j][i], ss[i]); }
-      }
-    }
+      for (int i = 0; i < V; i++) { s[i] += a[i]; ss[i] = fmaf(a[i], a[i], ss[i]); }
+    });
     float* mine = sh_part + (size_t)rl * 2 * C + v * V;
 #pragma unroll
     for (int i = 0; i < V; i++) { mine[i] = s[i]; mine[C + i] = ss[i]; }
@@ -138,17 +128,15 @@ __global__ void __launch_bounds__(256, 4) cbn_act_fwd_kernel(const T* __restrict
   const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
   const long long base = (long long)n * HW * C + v * V;
   const bool miu = act == FGC_ACT_MIU;
-#pragma unroll 4
-  for (int r = r0 + rl; r < r1; r += lanes) {
-    float a[kMaxV], o[kMaxV];
-    ldv<T, V>(x + base + (long long)r * C, a);
+  walk_rows<T, V, 4>(x + base, C, r0 + rl, r1, lanes, [&](int r, const float (&a)[kMaxV]) {
+    float o[kMaxV];
 #pragma unroll
     for (int k = 0; k < V; k++) {
       float t = fmaf(a[k], A[k], B[k]);
       o[k] = miu ? miu_relu_fast(t) : t;
     }
     stv<T, V>(y + base + (long long)r * C, o);
-  }
+  });
 }
 
 // per-(n,c) sums of g and g*xhat where g = gy*act'(y)    -> sums[0][n][c], sums[1][n][c]
@@ -176,27 +164,16 @@ __global__ void __launch_bounds__(256, 3) cbn_bwd_reduce_kernel(const T* __restr
   const bool miu = act == FGC_ACT_MIU;
   // two independent row loads per tensor in flight per thread; four (profiles/r1q) cost registers / resident CTAs and ran
   // 15-20% slower on the 604 MB tensor
-  for (int rb = r0 + rl; rb < r1; rb += 2 * lanes) {
-    float a[2][kMaxV], g[2][kMaxV];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      int r = rb + u * lanes;
-      if (r < r1) {
-        long long off = ((long long)n * HW + r) * C + v * V;
-        ldv<T, V>(x + off, a[u]);
-        ldv<T, V>(gy + off, g[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      if (rb + u * lanes >= r1) continue;
+  {
+    const long long base = (long long)n * HW * C + v * V;
+    walk_rows2<T, V, 2>(x + base, gy + base, C, r0 + rl, r1, lanes, [&](int, const float (&a)[kMaxV], const float (&g)[kMaxV]) {
 #pragma unroll
       for (int k = 0; k < V; k++) {
-        float gg = g[u][k];
-        if (miu) gg *= miu_relu_grad_fast(fmaf(a[u][k], A[k], B[k]));
-        s1[k] += gg; s2[k] = fmaf(gg, fmaf(a[u][k], rs[k], nm[k]), s2[k]);
+        float gg = g[k];
+        if (miu) gg *= miu_relu_grad_fast(fmaf(a[k], A[k], B[k]));
+        s1[k] += gg; s2[k] = fmaf(gg, fmaf(a[k], rs[k], nm[k]), s2[k]);
       }
-    }
+    });
   }
   if (rl < lanes) {
     float* mine = sh_red + (size_t)rl * 2 * C + v * V;
@@ -264,11 +241,8 @@ __global__ void __launch_bounds__(256, 3) cbn_bwd_apply_kernel(const T* __restri
   const bool miu = act == FGC_ACT_MIU;
   const int r0 = blockIdx.x * rows_per_block, r1 = on ? min(r0 + rows_per_block, HW) : 0;
   const long long base = (long long)n * HW * C + v * V;
-#pragma unroll 2
-  for (int r = r0 + rl; r < r1; r += lanes) {
-    float a[kMaxV], g[kMaxV], o[kMaxV];
-    ldv<T, V>(x + base + (long long)r * C, a);
-    ldv<T, V>(gy + base + (long long)r * C, g);
+  walk_rows2<T, V, 2>(x + base, gy + base, C, r0 + rl, r1, lanes, [&](int r, const float (&a)[kMaxV], const float (&g)[kMaxV]) {
+    float o[kMaxV];
 #pragma unroll
     for (int k = 0; k < V; k++) {
       float gg = g[k];
@@ -277,7 +251,7 @@ __global__ void __launch_bounds__(256, 3) cbn_bwd_apply_kernel(const T* __restri
       bs[k] += o[k];
     }
     stv<T, V>(gx + base + (long long)r * C, o);
-  }
+  });
   if (dbias) {                                   // bias gradient of the convolution in front: column sums of the result
     if (on) {
       float* mine = sh_db + (size_t)rl * C + v * V;
@@ -364,19 +338,19 @@ __global__ void prelu_bwd_rows_kernel(const T* __restrict__ gy, const T* __restr
   for (int k = 0; k < V; k++) bs[k] = 0.f;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = on ? (r0 + rows_per_block < M ? r0 + rows_per_block : M) : 0;
-#pragma unroll 2
-  for (long long r = r0 + rl; r < r1; r += lanes) {
-    float xv[kMaxV], g[kMaxV], o[kMaxV];
-    ldv<T, V>(x + r * C + v * V, xv);
-    ldv<T, V>(gy + r * C + v * V, g);
+  {
+    const long long base = r0 * C + v * V;
+    walk_rows2<T, V, 2>(x + base, gy + base, C, rl, (int)(r1 - r0), lanes, [&](int r, const float (&xv)[kMaxV], const float (&g)[kMaxV]) {
+      float o[kMaxV];
 #pragma unroll
-    for (int k = 0; k < V; k++) {
-      bool m = a * xv[k] >= xv[k];
-      o[k] = m ? a * g[k] : g[k];
-      if (m) acc += g[k] * xv[k];
-      bs[k] += o[k];
-    }
-    stv<T, V>(gx + r * C + v * V, o);
+      for (int k = 0; k < V; k++) {
+        bool m = a * xv[k] >= xv[k];
+        o[k] = m ? a * g[k] : g[k];
+        if (m) acc += g[k] * xv[k];
+        bs[k] += o[k];
+      }
+      stv<T, V>(gx + base + (long long)r * C, o);
+    });
   }
   if (on) {
     float* mine = sh_db + (size_t)rl * C + v * V;
@@ -412,20 +386,10 @@ __global__ void __launch_bounds__(256, 4) minmax_reduce_kernel(const T* __restri
   float lo[V], hi[V];
 #pragma unroll
   for (int k = 0; k < V; k++) { lo[k] = INFINITY; hi[k] = -INFINITY; }
-  for (int rb = r0 + rl; rb < r1; rb += 4 * lanes) {       // four independent row loads in flight per thread
-    float a[4][kMaxV];
+  walk_rows<T, V, 4>(x + (long long)n * HW * C + v * V, C, r0 + rl, r1, lanes, [&](int, const float (&a)[kMaxV]) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      int r = rb + u * lanes;
-      if (r < r1) ldv<T, V>(x + ((long long)n * HW + r) * C + v * V, a[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (rb + u * lanes >= r1) continue;
-#pragma unroll
-      for (int k = 0; k < V; k++) { lo[k] = fminf(lo[k], a[u][k]); hi[k] = fmaxf(hi[k], a[u][k]); }
-    }
-  }
+    for (int k = 0; k < V; k++) { lo[k] = fminf(lo[k], a[k]); hi[k] = fmaxf(hi[k], a[k]); }
+  });
   if (rl < lanes) {
 #pragma unroll
     for (int k = 0; k < V; k++) {
@@ -458,14 +422,12 @@ __global__ void __launch_bounds__(256, 4) minmax_apply_kernel(const T* __restric
   }
   const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
   const long long base = (long long)n * HW * C + v * V;
-#pragma unroll 4
-  for (int r = r0 + rl; r < r1; r += lanes) {
-    float a[kMaxV], o[kMaxV];
-    ldv<T, V>(x + base + (long long)r * C, a);
+  walk_rows<T, V, 4>(x + base, C, r0 + rl, r1, lanes, [&](int r, const float (&a)[kMaxV]) {
+    float o[kMaxV];
 #pragma unroll
     for (int k = 0; k < V; k++) o[k] = (a[k] - lo[k]) * inv[k];
     stv<T, V>(gate + base + (long long)r * C, o);
-  }
+  });
 }
 // sums[0] = sum g*(x-mn), sums[1] = sum g, sums[2] = #(x==mx), sums[3] = #(x==mn)   each [N,C]
 template <typename T, int V>
@@ -483,27 +445,16 @@ __global__ void __launch_bounds__(256, 3) minmax_bwd_reduce_kernel(const T* __re
     lo[k] = mn[(long long)n * C + v * V + k]; hi[k] = mx[(long long)n * C + v * V + k];
     s0[k] = s1[k] = c0[k] = c1[k] = 0.f;
   }
-  for (int rb = r0 + rl; rb < r1; rb += 2 * lanes) {       // two independent row loads in flight per thread
-    float a[2][kMaxV], g[2][kMaxV];
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      int r = rb + u * lanes;
-      if (r < r1) {
-        long long off = ((long long)n * HW + r) * C + v * V;
-        ldv<T, V>(x + off, a[u]);
-        ldv<T, V>(gg + off, g[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-      if (rb + u * lanes >= r1) continue;
+  {
+    const long long base = (long long)n * HW * C + v * V;
+    walk_rows2<T, V, 2>(x + base, gg + base, C, r0 + rl, r1, lanes, [&](int, const float (&a)[kMaxV], const float (&g)[kMaxV]) {
 #pragma unroll
       for (int k = 0; k < V; k++) {
-        s0[k] += g[u][k] * (a[u][k] - lo[k]); s1[k] += g[u][k];
-        c0[k] += (a[u][k] == hi[k]) ? 1.f : 0.f;
-        c1[k] += (a[u][k] == lo[k]) ? 1.f : 0.f;
+        s0[k] += g[k] * (a[k] - lo[k]); s1[k] += g[k];
+        c0[k] += (a[k] == hi[k]) ? 1.f : 0.f;
+        c1[k] += (a[k] == lo[k]) ? 1.f : 0.f;
       }
-    }
+    });
   }
   if (rl < lanes) {
     float* mine = sh_red + (size_t)rl * 4 * C + v * V;
@@ -544,11 +495,8 @@ __global__ void __launch_bounds__(256, 3) minmax_bwd_apply_kernel(const T* __res
   }
   const int r0 = blockIdx.x * rows_per_block, r1 = on ? min(r0 + rows_per_block, HW) : 0;
   const long long base = (long long)n * HW * C + v * V;
-#pragma unroll 2
-  for (int r = r0 + rl; r < r1; r += lanes) {
-    float a[kMaxV], g[kMaxV], o[kMaxV];
-    ldv<T, V>(x + base + (long long)r * C, a);
-    ldv<T, V>(gg + base + (long long)r * C, g);
+  walk_rows2<T, V, 2>(x + base, gg + base, C, r0 + rl, r1, lanes, [&](int r, const float (&a)[kMaxV], const float (&g)[kMaxV]) {
+    float o[kMaxV];
 #pragma unroll
     for (int k = 0; k < V; k++) {
       float rr = g[k] * invd[k];
@@ -558,7 +506,7 @@ __global__ void __launch_bounds__(256, 3) minmax_bwd_apply_kernel(const T* __res
       bs[k] += o[k];
     }
     stv<T, V>(gpre + base + (long long)r * C, o);
-  }
+  });
   if (dbias) {                                   // bias gradient of the convolution in front: column sums of the result
     if (on) {
       float* mine = sh_db + (size_t)rl * C + v * V;

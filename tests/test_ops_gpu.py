@@ -658,6 +658,93 @@ def test_conv_with_patch_sources(env, case):
     close(dw, dw_ref, 3e-2, "conv_wgrad with patch sources")
 
 
+@pytest.mark.parametrize("case", [(5000, 3, "bf16"), (77, 3, "f32"), (64, 2048, "f32"), (40, 300, "bf16"), (9000, 11, "f32"),
+                                  (300, 256, "bf16")], ids=str)
+def test_colsum_generic_forms(env, case):
+    """fgc_colsum outside the vectorised form: narrow rows (the bias gradient of a 3-channel layer: row lanes of a block combined in
+    shared memory, one atomic per channel and block) and wide rows over few samples (columns spread over grid.y)."""
+    cu, dev = env["cu"], env["dev"]
+    M, Cc, dt = case
+    x = rnd((M, Cc), 31, dev)
+    xd = (x.bfloat16() if dt == "bf16" else x.float()).contiguous()
+    out = torch.full((Cc,), 0.5, device=dev)
+    cu.colsum_(xd, out)
+    torch.cuda.synchronize()
+    close(out, xd.double().sum(0) + 0.5, 2e-5, "colsum %s" % (case,))
+
+
+def test_keep_packed_measurement_switch(env):
+    """fgc_debug_keep_packed (bench.py's kernel-only timing of the dominant layer): a repeated identical call that skips the
+    weight-packing launch returns the same bytes."""
+    cub, dev = env["cub"], env["dev"]
+    x = rnd((2, 32, 32, 128), 5, dev).bfloat16().contiguous()
+    w = (rnd((3, 3, 128, 128), 6, dev) * 0.05).float().contiguous()
+    b = rnd((128,), 7, dev).float().contiguous()
+    arr, N, H, W, dt = cub._srcs([(x, False)])
+    ws = cub._ws([128], 3, 128, dt)
+    ys = [torch.empty((2, 32, 32, 128), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+    st = torch.cuda.current_stream().cuda_stream
+    try:
+        for i, y in enumerate(ys):
+            cub.lib.fgc_debug_keep_packed(i)
+            rc = cub.lib.fgc_conv2d_fwd(arr, 1, dt, N, H, W, w.data_ptr(), 3, 128, 128, b.data_ptr(), 1, 1, 1, H, W, ACT_NONE,
+                                        y.data_ptr(), 1, ws.data_ptr(), st)
+            assert rc == 0
+    finally:
+        cub.lib.fgc_debug_keep_packed(0)
+    torch.cuda.synchronize()
+    assert torch.equal(ys[0].view(torch.int16), ys[1].view(torch.int16))
+    assert ys[0].float().abs().max().item() > 0
+
+
+def _patch_reference(x, k, ups, mirror):
+    """out[n,h,w,(kh*k+kw)*C + c] = x[n, h + s*(kh-pad), w + s*(kw-pad), c] (s = -1: mirrored taps), zeros outside the image and in
+    the tail that pads k*k*C to a multiple of 8 -- plain indexing on the device, no arithmetic."""
+    if ups:
+        x = x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    N, H, W, Cc = x.shape
+    pad = (k - 1) // 2
+    cp = 8 * ((k * k * Cc + 7) // 8)
+    xp = torch.nn.functional.pad(x, (0, 0, pad, pad, pad, pad))
+    out = torch.zeros((N, H, W, cp), dtype=x.dtype, device=x.device)
+    s = -1 if mirror else 1
+    for kh in range(k):
+        for kw in range(k):
+            dh, dw = s * (kh - pad), s * (kw - pad)
+            out[..., (kh * k + kw) * Cc:(kh * k + kw + 1) * Cc] = xp[:, pad + dh:pad + dh + H, pad + dw:pad + dw + W, :]
+    return out
+
+
+@pytest.mark.parametrize("case", [(3, 40, 24, 3, 7), (2, 37, 16, 3, 3), (2, 21, 32, 8, 3), (1, 9, 8, 11, 3), (2, 5, 24, 5, 5),
+                                  (2, 192, 192, 3, 7), (2, 192, 192, 8, 3), (1, 16, 8, 40, 3)], ids=str)
+@pytest.mark.parametrize("mirror", [False, True])
+def test_patch_tensor_bit_exact(env, case, mirror):
+    """fgc_im2col_small is byte movement: the row-tiled kernel (sources that are not upsampled; rows staged in shared memory with
+    the SAME padding as zeros) and the per-element kernel (upsampled sources) reproduce the indexed reference bit for bit, from
+    bf16 and from fp32 sources (fp32: round-to-nearest-even to bf16)."""
+    cub, dev = env["cub"], env["dev"]
+    N, H, W, Cc, k = case
+    x32 = rnd((N, H, W, Cc), 77, dev).float().contiguous()
+    xb = x32.bfloat16().contiguous()
+    want = _patch_reference(xb, k, False, mirror)
+    got = cub.small_patch(xb, k, mirror=mirror)
+    torch.cuda.synchronize()
+    assert got is not None and got.shape == want.shape
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16)), "patch tensor (bf16 source) differs"
+    # fp32 source through the C entry point (CudaOps.small_patch hands bf16 tensors over only)
+    out = torch.empty_like(want)
+    rc = cub.lib.fgc_im2col_small(x32.data_ptr(), 0, N, H, W, Cc, 0, k, 1 if mirror else 0, out.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert rc == 0 and torch.equal(out.view(torch.int16), want.view(torch.int16)), "patch tensor (fp32 source) differs"
+    if H % 2 == 0 and W % 2 == 0 and H <= 64:       # the upsampled form keeps the per-element kernel
+        lo = xb[:, :H // 2, :W // 2].contiguous()
+        want_u = _patch_reference(lo, k, True, mirror)
+        got_u = cub.small_patch(lo, k, ups=True, mirror=mirror)
+        torch.cuda.synchronize()
+        assert torch.equal(got_u.view(torch.int16), want_u.view(torch.int16)), "patch tensor (upsampled source) differs"
+
+
 @pytest.mark.parametrize("case", [(2, 64, 24, [(128, False)], 3, 128, ACT_LRELU), (3, 64, 16, [(64, False), (3, False)], 3, 64, ACT_NONE),
                                   (2, 128, 8, [(64, False)], 7, 3, ACT_TANH)], ids=str)
 def test_conv_halo_tall_tiles(env, case):
