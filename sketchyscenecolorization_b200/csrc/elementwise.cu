@@ -913,7 +913,9 @@ static RowRed rowred_plan(int C, int vec, long long rows, long long other_blocks
   p.threads = 256;
   if (CV > 256) p.threads = ((CV + 31) / 32) * 32;
   p.lanes = p.threads / CV;
-  long long target = (long long)num_sms() * 24;                     // blocks wanted overall (several waves: short tail)
+  static int waves = 0;                                             // env FGC_ROWRED_WAVES: tuning knob (blocks per SM overall)
+  if (!waves) { const char* e = getenv("FGC_ROWRED_WAVES"); waves = e ? atoi(e) : 24; if (waves < 1) waves = 24; }
+  long long target = (long long)num_sms() * waves;                  // blocks wanted overall (several waves: short tail)
   long long want = target / (other_blocks > 0 ? other_blocks : 1);
   if (want < 1) want = 1;
   long long rpb = (rows + want - 1) / want;
@@ -959,6 +961,54 @@ __global__ void tapsum_w_kernel(const float* __restrict__ z, long long npix, int
     else if (act == FGC_ACT_MIU) acc = miu_relu(acc);
     else if (act == FGC_ACT_RELU) acc = fmaxf(acc, 0.f);
     st1<TO>(y + i, acc);
+  }
+}
+// one thread per PIXEL with its CO outputs in registers (CO = 8: the folded input gradients towards the 8-channel stem features,
+// two 16-byte loads per filter column and one 16-byte store; CO = 3: the 7x7 head).  The per-element form above splits a 64-bit
+// index twice per output element (~100 instructions for 3 loads): 234 us for a 528 MB pass.
+template <typename TO, int CO>
+__global__ void __launch_bounds__(256) tapsum_w_pix_kernel(const float* __restrict__ z, unsigned npix, int W, int k, int Cz,
+                                                          const float* __restrict__ bias, int act, TO* __restrict__ y) {
+  const int pad = (k - 1) / 2;
+  float b[CO];
+#pragma unroll
+  for (int q = 0; q < CO; q++) b[q] = bias ? __ldg(bias + q) : 0.f;
+  for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+    const int w = (int)(p % (unsigned)W);
+    float acc[CO];
+#pragma unroll
+    for (int q = 0; q < CO; q++) acc[q] = b[q];
+    for (int kw = 0; kw < k; kw++) {
+      const int ww = w + kw - pad;
+      if (ww < 0 || ww >= W) continue;
+      const float* zp = z + ((long long)p + kw - pad) * Cz + kw * CO;
+      if (CO % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < CO; q += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(zp + q));
+          acc[q] += t.x; acc[q + 1] += t.y; acc[q + 2] += t.z; acc[q + 3] += t.w;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < CO; q++) acc[q] += __ldg(zp + q);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CO; q++) {
+      float v = acc[q];
+      if (act == FGC_ACT_TANH) v = tanhf(v);
+      else if (act == FGC_ACT_LRELU) v = v > 0.f ? v : 0.2f * v;
+      else if (act == FGC_ACT_MIU) v = miu_relu(v);
+      else if (act == FGC_ACT_RELU) v = fmaxf(v, 0.f);
+      acc[q] = v;
+    }
+    if (CO == 8 && sizeof(TO) == 2) {
+      *reinterpret_cast<uint4*>(y + (size_t)p * CO) = make_uint4(bf16x2_bits(acc[0], acc[1]), bf16x2_bits(acc[2], acc[3]),
+                                                                 bf16x2_bits(acc[4], acc[5]), bf16x2_bits(acc[6], acc[7]));
+    } else {
+#pragma unroll
+      for (int q = 0; q < CO; q++) st1<TO>(y + (size_t)p * CO + q, acc[q]);
+    }
   }
 }
 }  // namespace fgc
@@ -1351,7 +1401,15 @@ int fgc_tapsum_w(const float* z, int N, int H, int W, int k, int Cout, int Cz, c
   FGC_REQUIRE(z && y && k % 2 == 1 && Cz >= k * Cout, "tapsum_w: bad arguments");
   const long long npix = (long long)N * H * W;
   cudaStream_t s = as_stream(stream);
-  if (y_dtype == FGC_F32) tapsum_w_kernel<float><<<ew_grid(npix * Cout, 256), 256, 0, s>>>(z, npix, W, k, Cout, Cz, bias, act, (float*)y);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && (Cz & 3) == 0;
+  const unsigned np = (unsigned)npix;
+  if (npix < (1LL << 31) && Cout == 8 && al16) {
+    if (y_dtype == FGC_F32) tapsum_w_pix_kernel<float, 8><<<ew_grid(npix, 256), 256, 0, s>>>(z, np, W, k, Cz, bias, act, (float*)y);
+    else tapsum_w_pix_kernel<__nv_bfloat16, 8><<<ew_grid(npix, 256), 256, 0, s>>>(z, np, W, k, Cz, bias, act, (__nv_bfloat16*)y);
+  } else if (npix < (1LL << 31) && Cout == 3) {
+    if (y_dtype == FGC_F32) tapsum_w_pix_kernel<float, 3><<<ew_grid(npix, 256), 256, 0, s>>>(z, np, W, k, Cz, bias, act, (float*)y);
+    else tapsum_w_pix_kernel<__nv_bfloat16, 3><<<ew_grid(npix, 256), 256, 0, s>>>(z, np, W, k, Cz, bias, act, (__nv_bfloat16*)y);
+  } else if (y_dtype == FGC_F32) tapsum_w_kernel<float><<<ew_grid(npix * Cout, 256), 256, 0, s>>>(z, npix, W, k, Cout, Cz, bias, act, (float*)y);
   else tapsum_w_kernel<__nv_bfloat16><<<ew_grid(npix * Cout, 256), 256, 0, s>>>(z, npix, W, k, Cout, Cz, bias, act, (__nv_bfloat16*)y);
   count_launch();
   FGC_LAUNCH_CHECK("tapsum_w");
