@@ -162,8 +162,20 @@ __global__ void colsum_vec_kernel(const T* __restrict__ x, long long M, int C, i
 #pragma unroll
       for (int k = 0; k < V; k++) s[k] += a[k];
     });
+    // few channel vectors per row (CV a power of two below 32): lanes CV apart hold the same channels -- combine them with
+    // shuffles first.  C = 8 is ONE vector: all 256 threads of a block used to queue on the same 8 shared-memory words
+    // (174 us for a 75 MB tensor, 0.4 TB/s)
+    int CVp = CV;
+    if (CV < 32 && (CV & (CV - 1)) == 0 && lanes * CV == (int)blockDim.x) {
 #pragma unroll
-    for (int k = 0; k < V; k++) atomicAdd(&sh_col[v * V + k], s[k]);
+      for (int k = 0; k < V; k++)
+        for (int o = 16; o >= CV; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+      CVp = 32;                                  // one depositor per channel vector and warp
+    }
+    if (CVp == CV || (threadIdx.x & 31) < CV) {
+#pragma unroll
+      for (int k = 0; k < V; k++) atomicAdd(&sh_col[v * V + k], s[k]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&out[i], sh_col[i]);

@@ -42,6 +42,13 @@ __device__ __forceinline__ float small_act(float v, int act) {
   }
 }
 
+// non-coherent scalar load widened to fp32 (the staging loops below issue several before the first dependent shared-memory store)
+template <typename T> __device__ __forceinline__ float ldnc(const T* p);
+template <> __device__ __forceinline__ float ldnc<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ldnc<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+
 // input tile of every source -> shared memory, channel-planar fp32 [ctot][tile_h][tile_w], zero outside the image
 template <typename T>
 __device__ __forceinline__ void load_x_tile(const ConvGeom& g, int n, int ih0, int iw0, int tile_h, int tile_w, float* xt) {
@@ -52,25 +59,37 @@ __device__ __forceinline__ void load_x_tile(const ConvGeom& g, int n, int ih0, i
     const int Hs = ups ? (g.H >> 1) : g.H, Ws = ups ? (g.W >> 1) : g.W;
     float* dst = xt + g.cbase[s] * plane;
     if (!ups) {
-      // a tile row is tile_w * C consecutive source elements: threads walk it with the (column, channel) split carried along
-      // instead of divided out per element (the generic loop below costs ~120 instructions per element -- three integer
+      // the flattened (row, column, channel) index of the tile advances by blockDim.x per step: its three parts are carried
+      // along instead of divided out per element (the generic loop below costs ~120 instructions per element -- three integer
       // divisions and 64-bit indexing -- and was a quarter to a half of these kernels' time on the 3 / 8 / 11-channel layers)
-      const int rowlen = tile_w * C;
       const int dq = (int)blockDim.x / C, dr = (int)blockDim.x - dq * C;
-      const int col0 = (int)threadIdx.x / C, c0 = (int)threadIdx.x - col0 * C;
-      for (int r = 0; r < tile_h; r++) {
-        const int ih = ih0 + r;
-        const bool row_in = (unsigned)ih < (unsigned)g.H;
-        const long long roff = (((long long)n * g.H + (row_in ? ih : 0)) * g.W + iw0) * C;
-        float* drow = dst + r * tile_w;
-        int col = col0, c = c0;
-        for (int j = threadIdx.x; j < rowlen; j += blockDim.x) {
-          float v = 0.f;
-          if (row_in && (unsigned)(iw0 + col) < (unsigned)g.W) v = ld1<T>(src + (roff + j));
-          drow[c * plane + col] = v;
-          col += dq; c += dr;
-          if (c >= C) { c -= C; col++; }
+      const int pc = (int)threadIdx.x / C;
+      int c = (int)threadIdx.x - pc * C, r = pc / tile_w, col = pc - r * tile_w;
+      const long long img = (long long)n * g.H;
+      const int total = plane * C, B = (int)blockDim.x;
+      // eight elements per thread and step: the loads first, then the shared-memory stores -- one load in flight per thread made
+      // the staging of a tile pure latency (7 dependent round trips per 16 x 16 tile of an 11-channel source: the weight-gradient
+      // kernel took 700 us whatever the filter size)
+      constexpr int SU = 8;
+      for (int idx = threadIdx.x; idx < total; idx += SU * B) {
+        float v[SU];
+        int so[SU];
+#pragma unroll
+        for (int u = 0; u < SU; u++) {
+          v[u] = 0.f;
+          so[u] = -1;
+          if (idx + u * B < total) {
+            const int ih = ih0 + r, iw = iw0 + col;
+            so[u] = c * plane + r * tile_w + col;
+            if ((unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W) v[u] = ldnc<T>(src + ((img + ih) * g.W + iw) * C + c);
+            c += dr; col += dq;
+            if (c >= C) { c -= C; col++; }
+            while (col >= tile_w) { col -= tile_w; r++; }
+          }
         }
+#pragma unroll
+        for (int u = 0; u < SU; u++)
+          if (so[u] >= 0) dst[so[u]] = v[u];
       }
       continue;
     }
@@ -189,6 +208,7 @@ struct SmallWgradArgs {
   int tile_h, tile_w;
   int tiles_x, tiles_y, ntiles;
   int KKP, S;                // threads per pixel slice (multiple of 32), pixel slices per CTA
+  int dbg;                   // timing experiments (env FGC_SWG_DBG): 1 skip the final atomics, 2 skip the products, 4 / 8 skip the x / gy staging
 };
 
 // NKK rows of dW per thread (kk = lane-group index + j*KKP): every gy vector read from shared memory feeds NKK rows
@@ -225,34 +245,89 @@ __global__ void __launch_bounds__(512) conv_small_wgrad_kernel(const __grid_cons
     const int ty = bt % a.tiles_y;
     const int n = bt / a.tiles_y;
     __syncthreads();                             // previous tile fully consumed
-    load_x_tile<T>(g, n, ty * kTS * g.stride - g.pad_t, tx * kTS * g.stride - g.pad_l, a.tile_h, a.tile_w, xt);
-    for (int i = tid; i < 256 * 8; i += blockDim.x) {
-      const int p = i >> 3, co = i & 7;
-      const int oh = ty * kTS + (p >> 4), ow = tx * kTS + (p & 15);
-      float v = 0.f;
-      if (co < a.Cout && oh < g.OH && ow < g.OW) v = ld1<T>(gy + (((long long)n * g.OH + oh) * g.OW + ow) * a.Cout + co);
-      gyt[i] = v;
+    const bool gy_vec = sizeof(T) == 2 && a.Cout == 8 && (reinterpret_cast<uintptr_t>(gy) & 15) == 0 && blockDim.x >= 256;
+    uint4 raw = make_uint4(0, 0, 0, 0);          // 8 bf16 outputs per pixel = one 16-byte load per thread, issued before the x tile's
+    if (gy_vec && tid < 256 && !(a.dbg & 8)) {   // loads so that a tile costs ONE exposed memory round trip
+      const int oh = ty * kTS + (tid >> 4), ow = tx * kTS + (tid & 15);
+      if (oh < g.OH && ow < g.OW) raw = __ldg(reinterpret_cast<const uint4*>(gy + (((long long)n * g.OH + oh) * g.OW + ow) * 8));
+    }
+    if (!(a.dbg & 4)) load_x_tile<T>(g, n, ty * kTS * g.stride - g.pad_t, tx * kTS * g.stride - g.pad_l, a.tile_h, a.tile_w, xt);
+    if (a.dbg & 8) {
+    } else if (gy_vec) {
+      if (tid < 256) {
+        const int p = tid;
+        float4 lo4, hi4;
+        lo4.x = __uint_as_float(raw.x << 16); lo4.y = __uint_as_float(raw.x & 0xFFFF0000u);
+        lo4.z = __uint_as_float(raw.y << 16); lo4.w = __uint_as_float(raw.y & 0xFFFF0000u);
+        hi4.x = __uint_as_float(raw.z << 16); hi4.y = __uint_as_float(raw.z & 0xFFFF0000u);
+        hi4.z = __uint_as_float(raw.w << 16); hi4.w = __uint_as_float(raw.w & 0xFFFF0000u);
+        *reinterpret_cast<float4*>(gyt + p * 8) = lo4;
+        *reinterpret_cast<float4*>(gyt + p * 8 + 4) = hi4;
+      }
+    } else {
+#pragma unroll 4
+      for (int i = tid; i < 256 * 8; i += blockDim.x) {
+        const int p = i >> 3, co = i & 7;
+        const int oh = ty * kTS + (p >> 4), ow = tx * kTS + (p & 15);
+        float v = 0.f;
+        if (co < a.Cout && oh < g.OH && ow < g.OW) v = ldnc<T>(gy + (((long long)n * g.OH + oh) * g.OW + ow) * a.Cout + co);
+        gyt[i] = v;
+      }
     }
     __syncthreads();
-#pragma unroll 2
-    for (int p = slice; p < 256; p += a.S) {
-      const int po = ((p >> 4) * a.tile_w + (p & 15)) * g.stride;
-      const float4 g0 = *reinterpret_cast<const float4*>(gyt + p * 8), g1 = *reinterpret_cast<const float4*>(gyt + p * 8 + 4);
+    // a slice takes half rows of the tile (8 consecutive pixels: 32 units over S slices), unrolled with constant offsets --
+    // per pixel two 16-byte gy reads, one x read and the 8 FMAs, no index arithmetic (the per-pixel form spent 7 of its 40
+    // instructions per pixel on it)
+    const int st = g.stride;
+    for (int u = (a.dbg & 2) ? 32 : slice; u < 32; u += a.S) {
+      const int py = u >> 1, px0 = (u & 1) << 3;
+      const float* gp = gyt + (py * 16 + px0) * 8;
+      const int pbase = (py * a.tile_w + px0) * st;
+      if (st == 1) {
 #pragma unroll
-      for (int j = 0; j < NKK; j++) {
-        const float x = xt[xoff[j] + po];
-        acc[j][0] += x * g0.x; acc[j][1] += x * g0.y; acc[j][2] += x * g0.z; acc[j][3] += x * g0.w;
-        acc[j][4] += x * g1.x; acc[j][5] += x * g1.y; acc[j][6] += x * g1.z; acc[j][7] += x * g1.w;
+        for (int q = 0; q < 8; q++) {
+          const float4 g0 = *reinterpret_cast<const float4*>(gp + q * 8), g1 = *reinterpret_cast<const float4*>(gp + q * 8 + 4);
+#pragma unroll
+          for (int j = 0; j < NKK; j++) {
+            const float x = xt[xoff[j] + pbase + q];
+            acc[j][0] += x * g0.x; acc[j][1] += x * g0.y; acc[j][2] += x * g0.z; acc[j][3] += x * g0.w;
+            acc[j][4] += x * g1.x; acc[j][5] += x * g1.y; acc[j][6] += x * g1.z; acc[j][7] += x * g1.w;
+          }
+        }
+      } else {
+#pragma unroll 2
+        for (int q = 0; q < 8; q++) {
+          const float4 g0 = *reinterpret_cast<const float4*>(gp + q * 8), g1 = *reinterpret_cast<const float4*>(gp + q * 8 + 4);
+#pragma unroll
+          for (int j = 0; j < NKK; j++) {
+            const float x = xt[xoff[j] + pbase + q * st];
+            acc[j][0] += x * g0.x; acc[j][1] += x * g0.y; acc[j][2] += x * g0.z; acc[j][3] += x * g0.w;
+            acc[j][4] += x * g1.x; acc[j][5] += x * g1.y; acc[j][6] += x * g1.z; acc[j][7] += x * g1.w;
+          }
+        }
       }
     }
   }
+  // the S pixel slices of the CTA hold partial sums of the same rows: combined in shared memory, then ONE atomic per element of dW
+  // and CTA (a 3 x 3, 3-channel filter is 27 rows under 16 slices: 444 CTAs x 512 threads x 8 atomics on 216 addresses cost
+  // 480 of the kernel's 690 us)
+  __syncthreads();                               // the last tile's operands are dead: the buffer is reused
+  float* part = sm_small;                        // [NKK][S][KKP][8]
 #pragma unroll
   for (int j = 0; j < NKK; j++) {
-    if (!act_[j]) continue;
-    const int kk = kt + j * a.KKP;
-#pragma unroll
-    for (int q = 0; q < 8; q++)
-      if (q < a.Cout) atomicAdd(a.dw + (long long)kk * a.Cout + q, acc[j][q]);
+    float* mine = part + ((size_t)(j * a.S + slice) * a.KKP + kt) * 8;
+    *reinterpret_cast<float4*>(mine) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+    *reinterpret_cast<float4*>(mine + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+  }
+  __syncthreads();
+  if (a.dbg & 1) return;
+  for (int o = tid; o < NKK * a.KKP * 8; o += blockDim.x) {
+    const int j = o / (a.KKP * 8), rem = o - j * a.KKP * 8;
+    const int kk = (rem >> 3) + j * a.KKP, q = rem & 7;
+    if (kk >= KK || q >= a.Cout) continue;
+    float t = 0.f;
+    for (int sl = 0; sl < a.S; sl++) t += part[((size_t)(j * a.S + sl) * a.KKP) * 8 + rem];
+    atomicAdd(a.dw + (long long)kk * a.Cout + q, t);
   }
 }
 
@@ -629,6 +704,7 @@ int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int C
   SmallWgradArgs a;
   a.g = g;
   a.gy = gy; a.Cout = Cout; a.ctot = Cin_total; a.dw = dw;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FGC_SWG_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   a.tile_h = a.tile_w = (kTS - 1) * g.stride + g.k;
   a.tiles_x = (g.OW + kTS - 1) / kTS;
   a.tiles_y = (g.OH + kTS - 1) / kTS;
@@ -646,6 +722,7 @@ int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int C
   if (a.KKP * nkk < KK || a.KKP > 512) return -1;
   const int threads = a.KKP * a.S;
   size_t smem = sizeof(float) * ((((size_t)Cin_total * a.tile_h * a.tile_w + 3) & ~(size_t)3) + 256 * 8);
+  if (smem < sizeof(float) * 8 * (size_t)threads * nkk) smem = sizeof(float) * 8 * (size_t)threads * nkk;     // the final cross-slice sums
   if (smem > 96 * 1024) return -1;
   // persistent CTAs: exactly as many as are resident at once (a second wave would double the run time)
 #define FGC_SW(T_, N_)                                                                                              \

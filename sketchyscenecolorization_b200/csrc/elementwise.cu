@@ -390,7 +390,19 @@ __global__ void __launch_bounds__(256, 4) minmax_reduce_kernel(const T* __restri
 #pragma unroll
     for (int k = 0; k < V; k++) { lo[k] = fminf(lo[k], a[k]); hi[k] = fmaxf(hi[k], a[k]); }
   });
-  if (rl < lanes) {
+  // few channel vectors per row (CV a power of two below 32, e.g. the 8-channel gates of unit 1: ONE vector): lanes CV apart hold
+  // the same channels and are combined with shuffles, so a warp sends CV * V atomics instead of 32 * V to the same few words
+  bool deposit = rl < lanes;
+  if (CV < 32 && (CV & (CV - 1)) == 0) {         // then lanes * CV == blockDim.x: every thread of every warp takes part
+#pragma unroll
+    for (int k = 0; k < V; k++)
+      for (int o = 16; o >= CV; o >>= 1) {
+        lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+        hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+      }
+    deposit = (int)(threadIdx.x & 31) < CV;
+  }
+  if (deposit) {
 #pragma unroll
     for (int k = 0; k < V; k++) {
       atomicMin(&sh_mm[v * V + k], f2ord(lo[k]));
