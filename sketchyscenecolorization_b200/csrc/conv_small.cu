@@ -30,6 +30,7 @@ struct SmallArgs {
   int ctot;
   int tile_h, tile_w;        // input tile extent: (kTS-1)*stride + k
   int tiles_x, tiles_y;
+  int dbg;                   // timing experiments (env FGC_SF_DBG): 1 skip the products, 2 skip the tile staging, 4 skip the weight staging
 };
 
 __device__ __forceinline__ float small_act(float v, int act) {
@@ -58,6 +59,37 @@ __device__ __forceinline__ void load_x_tile(const ConvGeom& g, int n, int ih0, i
     const int C = g.C[s], ups = g.ups[s];
     const int Hs = ups ? (g.H >> 1) : g.H, Ws = ups ? (g.W >> 1) : g.W;
     float* dst = xt + g.cbase[s] * plane;
+    if (!ups && C == 8 && sizeof(T) == 2 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      // 8 bf16 channels = one 16-byte load per pixel of the tile (the stem features next to the 3-channel picture in the unit-1
+      // gates: 72 % of that tile's elements); two pixels per thread and step in flight
+      const long long img = (long long)n * g.H;
+      const int B = (int)blockDim.x;
+      for (int pos = threadIdx.x; pos < plane; pos += 2 * B) {
+        uint4 raw[2];
+        int po[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          raw[u] = make_uint4(0, 0, 0, 0);
+          po[u] = pos + u * B;
+          if (po[u] < plane) {
+            const int r = po[u] / tile_w, col = po[u] - r * tile_w;
+            const int ih = ih0 + r, iw = iw0 + col;
+            if ((unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W)
+              raw[u] = __ldg(reinterpret_cast<const uint4*>(src + ((img + ih) * g.W + iw) * 8));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+          if (po[u] >= plane) continue;
+          float* d = dst + po[u];
+          d[0] = __uint_as_float(raw[u].x << 16); d[plane] = __uint_as_float(raw[u].x & 0xFFFF0000u);
+          d[2 * plane] = __uint_as_float(raw[u].y << 16); d[3 * plane] = __uint_as_float(raw[u].y & 0xFFFF0000u);
+          d[4 * plane] = __uint_as_float(raw[u].z << 16); d[5 * plane] = __uint_as_float(raw[u].z & 0xFFFF0000u);
+          d[6 * plane] = __uint_as_float(raw[u].w << 16); d[7 * plane] = __uint_as_float(raw[u].w & 0xFFFF0000u);
+        }
+      }
+      continue;
+    }
     if (!ups) {
       // the flattened (row, column, channel) index of the tile advances by blockDim.x per step: its three parts are carried
       // along instead of divided out per element (the generic loop below costs ~120 instructions per element -- three integer
@@ -121,7 +153,7 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const __grid_consta
   const int tx = bt % a.tiles_x; bt /= a.tiles_x;
   const int ty = bt % a.tiles_y;
   const int n = bt / a.tiles_y;
-  for (int i = tid; i < KK * 8; i += blockDim.x) {
+  for (int i = (a.dbg & 4) ? KK * 8 : tid; i < KK * 8; i += blockDim.x) {
     const int q = i >> 3, co = i & 7;
     const int tap = q / ctot, c = q - tap * ctot;
     wsm[i] = co < a.nout ? __ldg(a.w + tap * a.tap_stride + c * a.k_stride + co * a.n_stride + a.base) : 0.f;
@@ -129,7 +161,7 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const __grid_consta
   // input row of output row oh under filter row kh:  oh*stride + sign*(kh - pad_t)
   const int org_h = g.sign > 0 ? -g.pad_t : g.pad_t - (k - 1);
   const int org_w = g.sign > 0 ? -g.pad_l : g.pad_l - (k - 1);
-  load_x_tile<T>(g, n, ty * kTS * g.stride + org_h, tx * kTW * g.stride + org_w, a.tile_h, a.tile_w, xt);
+  if (!(a.dbg & 2)) load_x_tile<T>(g, n, ty * kTS * g.stride + org_h, tx * kTW * g.stride + org_w, a.tile_h, a.tile_w, xt);
   __syncthreads();
   // each weight vector read from shared memory feeds 4 pixels: the kernel is bound by shared-memory return bandwidth,
   // not by the FMA pipe, so the register blocking is what sets its speed
@@ -140,7 +172,7 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(const __grid_consta
   for (int p = 0; p < 4; p++)
 #pragma unroll
     for (int q = 0; q < 8; q++) acc[p][q] = 0.f;
-  for (int kh = 0; kh < k; kh++) {
+  for (int kh = (a.dbg & 1) ? k : 0; kh < k; kh++) {
     const int khl = g.sign > 0 ? kh : k - 1 - kh;
     for (int kw = 0; kw < k; kw++) {
       const int kwl = g.sign > 0 ? kw : k - 1 - kw;
@@ -674,6 +706,7 @@ int conv_small_fwd_try(const ConvGeom& g, int src_dtype, const float* w, long lo
   a.g = g;
   a.w = w; a.tap_stride = tap_stride; a.k_stride = k_stride; a.n_stride = n_stride; a.base = base;
   a.nout = nout; a.bias = bias; a.act = act; a.accumulate = accumulate; a.y = y; a.y_dtype = y_dtype;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("FGC_SF_DBG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   a.ctot = g.cbase[g.nsrc - 1] + g.C[g.nsrc - 1];
   a.tile_h = (kTS - 1) * g.stride + g.k;
   a.tile_w = (kTW - 1) * g.stride + g.k;
@@ -714,7 +747,11 @@ int conv_small_wgrad_try(const ConvGeom& g, int src_dtype, const void* gy, int C
   // rows of dW per thread.  Measured (profiles/r1i,r1j): register blocking over several rows (one gy read feeding up to 5
   // rows) is SLOWER here than one row per thread -- 7x7 stem 0.51 -> 0.81 ms -- because the block then holds 16 pixel
   // slices of 32 threads and every slice walks the same 256-pixel tile; one row per thread and 3 slices it stays.
-  int nkk = 1;
+  // With the half-row unrolled products (round 2) two rows per thread win on the filters of ~100 rows and more (7x7 stem 685 ->
+  // 603 us, [8,3] -> 8 gate 728 -> 652 us; three rows lose again: profiles/r2at_small_conv_experiments.log); env FGC_SWG_NKK overrides.
+  int nkk = KK >= 96 ? 2 : 1;
+  { static int e_nkk = -1; if (e_nkk < 0) { const char* e = getenv("FGC_SWG_NKK"); e_nkk = e ? atoi(e) : 0; }
+    if (e_nkk >= 1 && e_nkk <= 5 && KK >= 96) nkk = e_nkk; }
   a.KKP = ((((KK + nkk - 1) / nkk) + 31) / 32) * 32;   // threads per pixel slice
   a.S = 512 / a.KKP;
   if (a.S < 1) a.S = 1;
