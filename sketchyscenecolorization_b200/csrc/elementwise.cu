@@ -442,8 +442,10 @@ __global__ void __launch_bounds__(256, 4) minmax_apply_kernel(const T* __restric
   });
 }
 // sums[0] = sum g*(x-mn), sums[1] = sum g, sums[2] = #(x==mx), sums[3] = #(x==mn)   each [N,C]
+// (the two min-max backward kernels carry 48 per-(n,c) registers: four rows per tensor in flight at 2 blocks per SM measured
+// 0.540 ms for the pair on the 604 MB tensor against 0.632 with two rows at 3 blocks per SM; the cBN pair prefers the latter)
 template <typename T, int V>
-__global__ void __launch_bounds__(256, 3) minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
+__global__ void __launch_bounds__(256, 2) minmax_bwd_reduce_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                          const float* __restrict__ mn, const float* __restrict__ mx, int N, float* sums) {
   extern __shared__ float sh_red[];              // [lanes][4][C] per-thread partial sums, added per column below
   const int CV = C / V;
@@ -459,7 +461,7 @@ __global__ void __launch_bounds__(256, 3) minmax_bwd_reduce_kernel(const T* __re
   }
   {
     const long long base = (long long)n * HW * C + v * V;
-    walk_rows2<T, V, 2>(x + base, gg + base, C, r0 + rl, r1, lanes, [&](int, const float (&a)[kMaxV], const float (&g)[kMaxV]) {
+    walk_rows2<T, V, 4>(x + base, gg + base, C, r0 + rl, r1, lanes, [&](int, const float (&a)[kMaxV], const float (&g)[kMaxV]) {
 #pragma unroll
       for (int k = 0; k < V; k++) {
         s0[k] += g[k] * (a[k] - lo[k]); s1[k] += g[k];
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(256, 3) minmax_bwd_reduce_kernel(const T* __re
   }
 }
 template <typename T, int V>
-__global__ void __launch_bounds__(256, 3) minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
+__global__ void __launch_bounds__(256, 2) minmax_bwd_apply_kernel(const T* __restrict__ gg, const T* __restrict__ x, int HW, int C, int rows_per_block,
                                         const float* __restrict__ mn, const float* __restrict__ mx, int N,
                                         const float* __restrict__ sums, T* __restrict__ gpre, float* dbias) {
   extern __shared__ float sh_db[];               // [lanes][C] per-thread column sums of gpre (only when dbias != NULL)
@@ -507,7 +509,7 @@ __global__ void __launch_bounds__(256, 3) minmax_bwd_apply_kernel(const T* __res
   }
   const int r0 = blockIdx.x * rows_per_block, r1 = on ? min(r0 + rows_per_block, HW) : 0;
   const long long base = (long long)n * HW * C + v * V;
-  walk_rows2<T, V, 2>(x + base, gg + base, C, r0 + rl, r1, lanes, [&](int r, const float (&a)[kMaxV], const float (&g)[kMaxV]) {
+  walk_rows2<T, V, 4>(x + base, gg + base, C, r0 + rl, r1, lanes, [&](int r, const float (&a)[kMaxV], const float (&g)[kMaxV]) {
     float o[kMaxV];
 #pragma unroll
     for (int k = 0; k < V; k++) {
